@@ -1,0 +1,180 @@
+"""Generate tests/golden/*.npz by running the LIVE reference (read-only at
+/root/reference) on seeded inputs.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the reference does not travel to the GPU box):
+    python oracle/gen_golden.py
+The fixtures are committed; tests read only the .npz files.
+
+The reference package imports `nengo` unconditionally
+(ssp_bayes_opt/__init__.py:15-16); nengo is not installed, so the module is
+stubbed in sys.modules before import.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF = os.environ.get("SSPBO_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    for name in ("nengo", "nengo.params", "nengo.utils", "nengo.utils.builder", "nengo.dists",
+                 "nengo.processes", "nengo.solvers", "nengo.neurons"):
+        sys.modules.setdefault(name, MagicMock())
+    sys.modules["nengo"].Network = type("Network", (object,), {})
+    sys.path.insert(0, REF)
+    import ssp_bayes_opt  # noqa: F401
+    from ssp_bayes_opt import sspspace, blr, agents
+    return sspspace, blr, agents
+
+
+def himmelblau(x):
+    return -((x[:, 0] ** 2 + x[:, 1] - 11) ** 2 + (x[:, 0] + x[:, 1] ** 2 - 7) ** 2
+             + x[:, 0] + x[:, 1]) / 100
+
+
+def main():
+    sspspace, blr, agents = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    quiet = contextlib.redirect_stdout(io.StringIO())
+
+    # ---- 1. phase matrices + encode, the spaces of the reference's own tests ----
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    rng = np.random.default_rng(42)
+    x2 = rng.uniform(b2[:, 0], b2[:, 1], size=(24, 2))
+    spaces = {
+        "hex51": sspspace.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=b2, length_scale=1.0, rng=0),
+        "rand51": sspspace.RandomSSPSpace(2, ssp_dim=51, domain_bounds=b2, length_scale=1.0, rng=0),
+        "hex151": sspspace.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=b2, length_scale=0.5),
+        "rand512": sspspace.RandomSSPSpace(2, ssp_dim=512, domain_bounds=b2, length_scale=1.0, rng=3),
+    }
+    enc = {}
+    for name, sp in spaces.items():
+        enc[f"{name}_A"] = sp.phase_matrix
+        enc[f"{name}_ls"] = np.asarray(sp.length_scale, dtype=np.float64).reshape(-1)
+        enc[f"{name}_phi"] = sp.encode(x2)
+    enc["x2"] = x2
+    # small length scale / wide bounds (tests/test_ssps.py:92-98): |theta| ~ 1e3 rad
+    b15 = 15 * np.array([[-1.0, 1.0], [-1.0, 1.0]])
+    sp = sspspace.HexagonalSSPSpace(2, ssp_dim=151, scale_min=2 * np.pi / np.sqrt(6) - 0.5,
+                                    scale_max=2 * np.pi / np.sqrt(6) + 0.5, domain_bounds=b15,
+                                    length_scale=0.05)
+    x15 = np.random.default_rng(7).uniform(-15, 15, size=(24, 2))
+    enc["hexsmall_A"] = sp.phase_matrix
+    enc["hexsmall_ls"] = np.asarray(sp.length_scale).reshape(-1)
+    enc["hexsmall_phi"] = sp.encode(x15)
+    enc["x15"] = x15
+    # C3 space: Random n=6 ssp_dim=1024 -> d=1023
+    b6 = np.array([[0.0, 1.0]] * 6)
+    sp6 = sspspace.RandomSSPSpace(6, ssp_dim=1024, domain_bounds=b6, length_scale=0.25, rng=0)
+    x6 = np.random.default_rng(11).uniform(0, 1, size=(8, 6))
+    enc["rand1024_A"] = sp6.phase_matrix
+    enc["rand1024_ls"] = np.asarray(sp6.length_scale).reshape(-1)
+    enc["rand1024_phi"] = sp6.encode(x6)
+    enc["x6"] = x6
+    np.savez_compressed(os.path.join(OUT, "encode.npz"), **enc)
+
+    # ---- 2. grid sample points + from-set decode ----
+    sp = spaces["hex51"]
+    ssps, pts = sp.get_sample_pts_and_ssps(20, "grid")
+    q = sp.encode(np.array([[1.3, -3.4], [0.2, 4.1], [-4.9, -4.9]]))
+    dec = sp.decode(q, method="from-set", samples=(ssps, pts))
+    b3 = np.array([[0.0, 1.0], [-1.0, 2.0], [3.0, 4.0]])
+    sp3 = sspspace.RandomSSPSpace(3, ssp_dim=31, domain_bounds=b3, length_scale=1.0, rng=1)
+    pts3 = sp3.get_sample_points(4, "grid")
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), A=sp.phase_matrix, bounds=b2, pts=pts,
+                        ssps=ssps, queries=q, decoded=dec, bounds3=b3, pts3=pts3,
+                        bind=sp.bind(q[0], q[1]), invert=sp.invert(q))
+
+    # ---- 3. BLR: batch init update, sequential updates, predict ----
+    out = {}
+    xs = np.random.default_rng(42).uniform(b2[:, 0], b2[:, 1], size=(8, 2))
+    ys = himmelblau(xs).reshape(-1, 1)
+    for name in ("hex51", "rand51"):
+        sp = spaces[name]
+        model = blr.BayesianLinearRegression(sp.ssp_dim)
+        model.update(sp.encode(xs), ys)
+        out[f"{name}_beta"] = np.float64(model.beta)
+        out[f"{name}_m0"], out[f"{name}_S0"] = model.m.copy(), model.S.copy()
+        xt = np.random.default_rng(5).uniform(b2[:, 0], b2[:, 1], size=(40, 2))
+        yt = himmelblau(xt).reshape(-1, 1)
+        for i in range(40):
+            model.update(sp.encode(xt[i:i + 1]), yt[i:i + 1])
+        out[f"{name}_m40"], out[f"{name}_S40"] = model.m.copy(), model.S.copy()
+        xc = np.random.default_rng(6).uniform(b2[:, 0], b2[:, 1], size=(64, 2))
+        mu, var = model.predict(sp.encode(xc))
+        out[f"{name}_mu"], out[f"{name}_var"] = mu, var
+        out[f"{name}_xt"], out[f"{name}_yt"], out[f"{name}_xc"] = xt, yt, xc
+    out["xs"], out["ys"] = xs, ys
+    # single-target beta rule (blr.py:57-58)
+    model = blr.BayesianLinearRegression(spaces["hex51"].ssp_dim)
+    model.update(spaces["hex51"].encode(xs[:1]), ys[:1])
+    out["single_beta"] = np.float64(np.ravel(model.beta)[0])
+    out["single_m"], out["single_S"] = model.m.copy(), model.S.copy()
+    np.savez_compressed(os.path.join(OUT, "blr.npz"), **out)
+
+    # ---- 4. posterior after 1000 sequential updates (north-star 1e-6 bar) ----
+    sp = sspspace.RandomSSPSpace(2, ssp_dim=128, domain_bounds=b2, length_scale=1.0, rng=2)  # d=127
+    xt = np.random.default_rng(8).uniform(b2[:, 0], b2[:, 1], size=(1000, 2))
+    yt = himmelblau(xt).reshape(-1, 1)
+    model = blr.BayesianLinearRegression(sp.ssp_dim)
+    model.update(sp.encode(xt[:10]), yt[:10])
+    for i in range(10, 1000):
+        model.update(sp.encode(xt[i:i + 1]), yt[i:i + 1])
+    np.savez_compressed(os.path.join(OUT, "blr1000.npz"), A=sp.phase_matrix, xt=xt, yt=yt,
+                        beta=np.float64(model.beta), m=model.m, S=model.S)
+
+    # ---- 5. SSPAgent.eval / update scalars (MI and pure UCB) ----
+    out = {}
+    for tag, gamma_c in (("mi", 1.0), ("ucb", 0.0)):
+        sp = sspspace.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=b2, length_scale=1.0, rng=0)
+        with quiet:
+            agt = agents.SSPAgent(xs, ys, sp, decoder_method="from-set", gamma_c=gamma_c,
+                                  beta_ucb=10.0, var_decay=0.25, length_scale=1.0)
+        xt = np.random.default_rng(9).uniform(b2[:, 0], b2[:, 1], size=(6, 2))
+        for i in range(6):
+            x_t = xt[i:i + 1]
+            y_t = np.atleast_2d(himmelblau(x_t))
+            _, var_t, _ = agt.eval(x_t)
+            agt.update(x_t, y_t, var_t, step_num=i)
+        xc = np.random.default_rng(10).uniform(b2[:, 0], b2[:, 1], size=(256, 2))
+        mu, var, acq = agt.eval(xc)
+        out[f"{tag}_mu"], out[f"{tag}_var"], out[f"{tag}_acq"] = mu, var, acq
+        out[f"{tag}_gamma_t"] = np.float64(np.ravel(agt.gamma_t)[0])
+        out[f"{tag}_var_weight"] = np.float64(agt.var_weight)
+        out[f"{tag}_m"], out[f"{tag}_S"] = agt.blr.m, agt.blr.S
+        out[f"{tag}_beta"] = np.float64(agt.blr.beta)
+        out[f"{tag}_init_pts"] = agt.init_samples[1]
+        out[f"{tag}_decoded"] = agt.decode(agt.encode(xc[:3]))
+        out["xt"], out["xc"] = xt, xc
+    np.savez_compressed(os.path.join(OUT, "agent.npz"), **out)
+
+    # ---- 6. trajectory agent encode / decode ----
+    bt = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    L, xd = 4, 2
+    trajs = np.random.default_rng(12).uniform(-2, 2, size=(10, L * xd))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True)
+    with quiet:
+        agt = agents.SSPTrajectoryAgent(trajs, tys, x_dim=xd, traj_len=L, ssp_dim=51, domain_bounds=bt,
+                                        length_scale=0.7, time_length_scale=1.3,
+                                        decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    xc = np.random.default_rng(13).uniform(-2, 2, size=(32, L * xd))
+    mu, var, acq = agt.eval(xc)
+    np.savez_compressed(
+        os.path.join(OUT, "traj.npz"), Ax=agt.ssp_x_space.phase_matrix, At=agt.ssp_t_space.phase_matrix,
+        ls_x=np.ravel(agt.ssp_x_space.length_scale), ls_t=np.ravel(agt.ssp_t_space.length_scale),
+        timestep_ssps=agt.timestep_ssps, trajs=trajs, tys=tys, xc=xc, phi=agt.encode(xc), mu=mu, var=var,
+        acq=acq, beta=np.float64(agt.blr.beta), m=agt.blr.m, S=agt.blr.S, init_pts=agt.init_samples[1],
+        decoded=agt.decode(agt.encode(xc[:1])), bounds=bt)
+    print("golden fixtures written to", os.path.abspath(OUT))
+    for f in sorted(os.listdir(OUT)):
+        print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+"""Pin the numpy oracle against outputs of the live reference (tests/golden/*.npz,
+written by oracle/gen_golden.py).  CPU only."""
+import numpy as np
+
+from oracle import ssp_oracle as orc
+
+B2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+
+
+def test_phase_matrices_bit_exact(golden):
+    g = golden("encode.npz")
+    assert np.array_equal(orc.random_phase_matrix(2, 51, rng=0), g["rand51_A"])
+    assert np.array_equal(orc.random_phase_matrix(2, 512, rng=3), g["rand512_A"])
+    assert np.array_equal(orc.random_phase_matrix(6, 1024, rng=0), g["rand1024_A"])
+    assert g["rand1024_A"].shape == (1023, 6)          # ssp_dim is a request (sspspace.py:821-827)
+    assert np.array_equal(orc.hex_phase_matrix(2, 51), g["hex51_A"])
+    assert g["hex51_A"].shape[0] == 25
+    assert np.array_equal(orc.hex_phase_matrix(2, 151), g["hex151_A"])
+    s = 2 * np.pi / np.sqrt(6)
+    assert np.array_equal(orc.hex_phase_matrix(2, 151, scale_min=s - 0.5, scale_max=s + 0.5), g["hexsmall_A"])
+
+
+def test_encode_matches_reference(golden):
+    g = golden("encode.npz")
+    for name, xk in (("hex51", "x2"), ("rand51", "x2"), ("hex151", "x2"), ("rand512", "x2"),
+                     ("hexsmall", "x15"), ("rand1024", "x6")):
+        phi = orc.encode(g[f"{name}_A"], g[f"{name}_ls"], g[xk])
+        assert phi.shape == g[f"{name}_phi"].shape
+        np.testing.assert_allclose(phi, g[f"{name}_phi"], rtol=0, atol=1e-15)
+        # unit norm (tests/test_ssps.py:31-37) and the closed form of SURVEY section 7
+        np.testing.assert_allclose(np.linalg.norm(phi, axis=1), 1.0, atol=1e-12)
+        np.testing.assert_allclose(orc.encode_closed_form(g[f"{name}_A"], g[f"{name}_ls"], g[xk]), phi,
+                                   atol=5e-13)
+
+
+def test_grid_points_decode_bind(golden):
+    g = golden("decode.npz")
+    pts = orc.grid_sample_points(g["bounds"], 20)
+    assert np.array_equal(pts, g["pts"])
+    assert np.array_equal(orc.grid_sample_points(g["bounds3"], 4), g["pts3"])   # n>=3 meshgrid('xy') order
+    ssps = orc.encode(g["A"], np.ones(2), pts)
+    np.testing.assert_allclose(ssps, g["ssps"], atol=1e-15)
+    assert np.array_equal(orc.decode_from_set(g["queries"], g["ssps"], g["pts"]), g["decoded"])
+    np.testing.assert_allclose(orc.bind(g["queries"][0], g["queries"][1]), g["bind"], atol=1e-15)
+    assert np.array_equal(orc.invert(g["queries"]), g["invert"])
+
+
+def test_blr_matches_reference(golden):
+    g = golden("blr.npz")
+    e = golden("encode.npz")
+    for name in ("hex51", "rand51"):
+        A, ls = e[f"{name}_A"], e[f"{name}_ls"]
+        model = orc.BLR(A.shape[0])
+        model.update(orc.encode(A, ls, g["xs"]), g["ys"])
+        assert model.beta == g[f"{name}_beta"]
+        np.testing.assert_allclose(model.m, g[f"{name}_m0"], rtol=0, atol=1e-11 * np.abs(model.m).max())
+        np.testing.assert_allclose(model.S, g[f"{name}_S0"], rtol=0, atol=1e-11 * np.abs(model.S).max())
+        for i in range(40):
+            model.update(orc.encode(A, ls, g[f"{name}_xt"][i:i + 1]), g[f"{name}_yt"][i:i + 1])
+        np.testing.assert_allclose(model.m, g[f"{name}_m40"], rtol=0, atol=1e-10 * np.abs(model.m).max())
+        np.testing.assert_allclose(model.S, g[f"{name}_S40"], rtol=0, atol=1e-10 * np.abs(model.S).max())
+        mu, var = model.predict(orc.encode(A, ls, g[f"{name}_xc"]))
+        assert mu.shape == (1, 64) and var.shape == (64,)          # tests/test_blr.py:28-39
+        np.testing.assert_allclose(mu, g[f"{name}_mu"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(var, g[f"{name}_var"], rtol=1e-9)
+    model = orc.BLR(e["hex51_A"].shape[0])
+    model.update(orc.encode(e["hex51_A"], e["hex51_ls"], g["xs"][:1]), g["ys"][:1])
+    assert np.ravel(model.beta)[0] == g["single_beta"]
+    np.testing.assert_allclose(model.S, g["single_S"], rtol=1e-12, atol=1e-13)
+
+
+def test_blr_1000_updates(golden):
+    g = golden("blr1000.npz")
+    A = g["A"]
+    model = orc.BLR(A.shape[0])
+    phis = orc.encode(A, np.ones(2), g["xt"])
+    model.update(phis[:10], g["yt"][:10])
+    for i in range(10, 1000):
+        model.update(phis[i:i + 1], g["yt"][i:i + 1])
+    assert model.beta == g["beta"]
+    np.testing.assert_allclose(model.S, g["S"], rtol=0, atol=1e-9 * np.abs(g["S"]).max())
+    np.testing.assert_allclose(model.m, g["m"], rtol=0, atol=1e-9 * np.abs(g["m"]).max())
+
+
+def test_blr_sequential_equals_batch():
+    """The reference's own invariant, tests/test_blr.py:72-92."""
+    rng = np.random.default_rng(4)
+    xs, ys = rng.normal(size=(6, 10)), rng.normal(size=(6, 1))
+    a, b = orc.BLR(10, beta=1.0), orc.BLR(10, beta=1.0)
+    a.update(xs, ys)
+    for i in range(6):
+        b.update(xs[i:i + 1], ys[i:i + 1])
+    assert np.allclose(a.m, b.m, atol=1e-6) and np.allclose(a.S, b.S, atol=1e-6)
+
+
+def test_agent_eval_matches_reference(golden):
+    g = golden("agent.npz")
+    A = golden("encode.npz")["hex51_A"]
+    for tag in ("mi", "ucb"):
+        model = orc.BLR(A.shape[0])
+        model.m, model.S, model.beta = g[f"{tag}_m"], g[f"{tag}_S"], float(g[f"{tag}_beta"])
+        phis = orc.encode(A, np.ones(2), g["xc"])
+        mu, var, acq = orc.agent_eval(phis, model, float(g[f"{tag}_var_weight"]), float(g[f"{tag}_gamma_t"]))
+        np.testing.assert_allclose(mu, g[f"{tag}_mu"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=1e-10)
+        np.testing.assert_allclose(acq, g[f"{tag}_acq"], rtol=1e-9, atol=1e-12)
+        score, idx = orc.score_and_argmax(phis, model, float(g[f"{tag}_var_weight"]), float(g[f"{tag}_gamma_t"]))
+        assert idx == int(np.argmax(g[f"{tag}_mu"].ravel() + g[f"{tag}_acq"]))
+    assert g["ucb_gamma_t"] == 0.0 and g["mi_gamma_t"] > 0.0
+    assert g["mi_var_weight"] == 10.0 + 6 * 0.25                    # var_decay is ADDED (ssp_agent.py:208-211)
+
+
+def test_agent_replay_from_scratch(golden):
+    """Replay SSPAgent construction + 6 updates with oracle primitives only."""
+    g = golden("agent.npz")
+    b = golden("blr.npz")
+    A = golden("encode.npz")["hex51_A"]
+    ls = np.ones(2)
+    for tag, gamma_c in (("mi", 1.0), ("ucb", 0.0)):
+        model = orc.BLR(A.shape[0])
+        model.update(orc.encode(A, ls, b["xs"]), b["ys"])
+        lam, gam = 10.0, 0.0
+        from tests.conftest import himmelblau
+        for i in range(6):
+            x_t = g["xt"][i:i + 1]
+            phi = orc.encode(A, ls, x_t)
+            _, var_t, _ = orc.agent_eval(phi, model, lam, gam)
+            model.update(phi, np.atleast_2d(himmelblau(x_t)))
+            lam, gam = orc.agent_update_scalars(lam, gam, 0.25, gamma_c, var_t)
+        np.testing.assert_allclose(model.m, g[f"{tag}_m"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(np.ravel(gam)[0], g[f"{tag}_gamma_t"], rtol=1e-12)
+        pts = orc.grid_sample_points(B2, 100)                       # ssp_agent.py:117-120
+        assert np.array_equal(pts, g[f"{tag}_init_pts"])
+
+
+def test_trajectory_matches_reference(golden):
+    g = golden("traj.npz")
+    L, xd = 4, 2
+    T = orc.traj_timestep_ssps(g["At"], g["ls_t"], L)
+    np.testing.assert_allclose(T, g["timestep_ssps"], atol=1e-15)
+    phi = orc.traj_encode(g["Ax"], g["ls_x"], T, g["xc"], L, xd)
+    np.testing.assert_allclose(phi, g["phi"], atol=1e-14)
+    model = orc.BLR(g["Ax"].shape[0])
+    model.m, model.S, model.beta = g["m"], g["S"], float(g["beta"])
+    mu, var, acq = orc.agent_eval(phi, model, 5.0, 0.0)
+    np.testing.assert_allclose(mu, g["mu"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(acq, g["acq"], rtol=1e-10)
+    pts = g["init_pts"]
+    ssps = orc.encode(g["Ax"], g["ls_x"], pts)
+    dec = orc.traj_decode_from_set(phi[:1], T, ssps, pts)
+    assert np.array_equal(dec, g["decoded"])
+
+
+def test_counter_uniform_is_range_consistent():
+    a = orc.counter_uniform(0, 0, 1000, 6)
+    b = orc.counter_uniform(0, 400, 100, 6)
+    assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
+    assert np.array_equal(a[400:500], b)
+    assert abs(a.mean() - 0.5) < 0.02
