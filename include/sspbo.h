@@ -1,0 +1,135 @@
+/*
+ * sspbo.h - C ABI of the B200-native SSP-BO hot path.
+ *
+ * The reference (ctn-waterloo/ssp-bayesopt) is pure Python/numpy and has no FFI of
+ * its own; its boundary for this path is the Python method surface.  Each entry
+ * point below names the reference method (file:line under ssp_bayes_opt/) whose
+ * arithmetic it replaces; `ssp_bayesopt_b200/` re-hosts those methods on top of
+ * this ABI with ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the ABI.
+ *   - every function returns 0 on success, a negative SSPBO_E* code on failure;
+ *     sspbo_last_error(ctx) gives the message.  No exception crosses the ABI.
+ *   - pointers named *_dev are caller-owned DEVICE pointers on ctx's device,
+ *     row-major; *_host are host pointers.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).  All device work is stream-ordered
+ *     and asynchronous unless the function returns a host value.
+ *   - one ctx per device; a ctx is not thread-safe; distinct ctxs are independent.
+ *   - psi-space: d = 2K+1, psi = [DC, cos(theta_1..K), sin(theta_1..K)],
+ *     phi = B psi with B the real inverse-DFT matrix.
+ */
+#ifndef SSPBO_H
+#define SSPBO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSPBO_OK            0
+#define SSPBO_EINVAL       -1   /* bad argument / shape                      */
+#define SSPBO_ECUDA        -2   /* CUDA runtime error (message has details) */
+#define SSPBO_ESTATE       -3   /* call order (space/blr not initialised)   */
+#define SSPBO_EUNSUPPORTED -4   /* shape outside what the kernels cover     */
+
+#define SSPBO_F32 0
+#define SSPBO_F64 1
+
+/* scoring engines for sspbo_score */
+#define SSPBO_ENGINE_AUTO 0     /* tcgen05 when the shape is covered, else SIMT */
+#define SSPBO_ENGINE_SIMT 1     /* fp32 CUDA-core kernel (any d)                */
+#define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel               */
+
+typedef struct sspbo_ctx sspbo_ctx;
+
+int  sspbo_abi_version(void);
+int  sspbo_ctx_create(int device, sspbo_ctx** out);
+void sspbo_ctx_destroy(sspbo_ctx* ctx);
+const char* sspbo_last_error(const sspbo_ctx* ctx);
+
+/* ---- SSP space ---------------------------------------------------------------
+ * Replaces the state of SSPSpace.__init__/update_lengthscale (sspspace.py:216-252).
+ * A_plus_host: the K positive-frequency rows phase_matrix[1:K+1] (K x n, float64);
+ * inv_ls_host: 1/length_scale per axis (n).  d = 2K+1 (conjsym, sspspace.py:821-827).
+ * Re-setting the space keeps the BLR state only if K is unchanged. */
+int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus_host, const double* inv_ls_host, int K, int n);
+
+/* Trajectory mode (SSPTrajectoryAgent.encode, agents/ssp_traj_agent.py:145-163):
+ * candidates are rows of L waypoints (L*n values); the spectrum is the sum over
+ * waypoints of exp(i(theta_k(x_j) + tau[j][k])).  tau_host: L x K float64, radians
+ * (phase of timestep j at frequency k, i.e. A_t[k]*t_j/ls_t).  L=1 with tau=NULL
+ * restores the plain space. */
+int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L);
+
+int sspbo_space_dims(const sspbo_ctx* ctx, int* d, int* K, int* n, int* L);
+
+/* ---- K1: encode ---------------------------------------------------------------
+ * SSPSpace.encode (sspspace.py:254-276): phi = Re IFFT(exp(i A (x/l)^T))^T.
+ * x_dev: N x (n*L), dtype SSPBO_F32|SSPBO_F64.  phi_out_dev: N x d float64. */
+int sspbo_encode(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, double* phi_out_dev, void* stream);
+
+/* ---- K3: Bayesian linear regression (blr.py:27-97) --------------------------------
+ * State on device, float64: S (d x d), S_inv, b = beta * sum(phi_i t_i), m = S b, plus
+ * the psi-space scoring factor R (R^T R = B^T S B) and its split-fp16 image. */
+int sspbo_blr_init(sspbo_ctx* ctx, double alpha);            /* blr.py:27-33: S = I/alpha, m = 0 */
+/* BLR over raw features of any dimension (no SSP space on this ctx): update/predict/get only. */
+int sspbo_blr_init_dim(sspbo_ctx* ctx, int d, double alpha);
+int sspbo_blr_set_beta(sspbo_ctx* ctx, double beta);         /* blr.py:54-59 computed by the host mirror */
+int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_set);
+/* blr.py:60-77: S_inv += beta Phi^T Phi; for each row: Sherman-Morrison on S; m = S b.
+ * phis_dev: k x d float64 (device); ts_host: k float64 (host). */
+int sspbo_blr_update(sspbo_ctx* ctx, const double* phis_dev, const double* ts_host, int k, void* stream);
+/* copies of the posterior (attributes BLR.m (d), BLR.S (d x d), BLR.S_inv (d x d)); any pointer may be NULL */
+int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev, void* stream);
+/* device-to-device adoption of a replicated posterior (multi-GPU broadcast target):
+ * S, S_inv, b, m, R as produced by sspbo_blr_export on another ctx with the same space. */
+int64_t sspbo_blr_export_size(const sspbo_ctx* ctx);          /* number of float64 in the packed state */
+int sspbo_blr_export(sspbo_ctx* ctx, double* packed_dev, void* stream);
+int sspbo_blr_import(sspbo_ctx* ctx, const double* packed_dev, double beta, void* stream);
+/* blr.py:84-97: var = 1/beta + diag(phi S phi^T), mu = m^T phi^T.  phi_dev N x d f64 -> mu (N), var (N) f64 */
+int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi_dev, int64_t N, double* mu_dev, double* var_dev, void* stream);
+
+/* ---- K2: fused encode + acquisition + argmax ---------------------------------------
+ * Composition SSPAgent.eval (agents/ssp_agent.py:125-137) -> score = mu + acq -> np.argmax
+ * (experiments/demo_blr_gif.py:129-136) without materialising phi.
+ *   score_i = m^T phi_i + lam * ( sqrt(1/beta + phi_i^T S phi_i + gamma_t) - sqrt(gamma_t) )
+ * x_dev: N x (n*L) candidates (F32|F64); index0: global index of x_dev[0] (for sharded
+ * candidate sets); outputs mu/var/acq (float32, N each) are optional (NULL to skip);
+ * best_key_dev: one uint64, atomically max-combined with
+ *   key = orderable_u32(score) << 32 | (0xFFFFFFFF - global_index)
+ * so that max(key) = highest score, lowest index on ties (np.argmax).  The caller zeroes
+ * *best_key_dev before the first call of a step; global_index must be < 2^32. */
+int sspbo_score(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, int64_t index0,
+                double lam, double gamma_t, float* mu_dev, float* var_dev, float* acq_dev,
+                unsigned long long* best_key_dev, int engine, void* stream);
+/* host helpers for the packed key */
+void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index);
+unsigned long long sspbo_key_pack(float score, int64_t index);
+/* engine the last sspbo_score call used (SSPBO_ENGINE_SIMT / _UMMA) and kernel launches so far */
+int sspbo_last_engine(const sspbo_ctx* ctx);
+int64_t sspbo_launch_count(const sspbo_ctx* ctx);
+
+/* ---- K4: from-set decode (sspspace.py:352-356) ------------------------------------
+ * unit = q / max(||q||, 1e-6); idx[j] = argmax_i sample_ssps[i] . unit[j], first index on ties.
+ * sample_ssps_dev: M x d f64; queries_dev: q x d f64; idx_out_dev: q int64. */
+int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* sample_ssps_dev, int64_t M, const double* queries_dev,
+                          int q, int64_t* idx_out_dev, void* stream);
+
+/* ---- candidate generators ---------------------------------------------------------
+ * Counter-based uniform(0,1) float32 stream (same integer hash as
+ * oracle/ssp_oracle.py:counter_uniform, bit-exact): rows [start, start+count) of an
+ * (infinite x n) stream.  out_dev: count x n float32. */
+int sspbo_fill_uniform(sspbo_ctx* ctx, uint64_t seed, int64_t start, int64_t count, int n, float* out_dev, void* stream);
+/* Candidate grid in the reference's order (SSPSpace.get_sample_points('grid'),
+ * sspspace.py:488-495: np.meshgrid(indexing='xy') flattened C-order).  axes_dev: the
+ * per-axis linspace values concatenated (sum(counts) float64, computed by the host with
+ * np.linspace so points are bit-identical); rows [start, start+count) -> out_dev (count x n f64). */
+int sspbo_grid_points(sspbo_ctx* ctx, const double* axes_dev, const int* counts_host, int n, int64_t start,
+                      int64_t count, double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSPBO_H */

@@ -1,0 +1,6 @@
+from .agent import Agent
+from .ssp_agent import SSPAgent
+from .ssp_traj_agent import SSPTrajectoryAgent
+from . import domains
+
+__all__ = ["Agent", "SSPAgent", "SSPTrajectoryAgent", "domains"]

@@ -1,0 +1,41 @@
+"""Initial-design samplers (ssp_bayes_opt/agents/domains.py).  Host-side, unseeded Sobol exactly like the
+reference; pass `init_points=(xs, ys)` to `maximize` for reproducible runs."""
+import numpy as np
+from scipy.stats import qmc
+
+
+class Domain:
+    def sample(self, num_points: int = 10, method: str = 'sobol') -> np.ndarray:
+        raise NotImplementedError
+
+
+class BoundedDomain(Domain):
+    """domains.py:24-38"""
+
+    def __init__(self, bounds: np.ndarray):
+        self.bounds = bounds
+        self.data_dim = bounds.shape[0]
+        self.sampler = qmc.Sobol(d=self.data_dim)
+
+    def sample(self, num_points: int = 10, method: str = 'sobol') -> np.ndarray:
+        if method != 'sobol':
+            raise NotImplementedError(f'{method} not implemented')
+        return qmc.scale(self.sampler.random(num_points), self.bounds[:, 0], self.bounds[:, 1])
+
+
+class TrajectoryDomain(Domain):
+    """Flattened (traj_len * spatial_dim) trajectories inside a square box (domains.py:84-106)."""
+
+    def __init__(self, trajectory_length: int, spatial_dim: int, bounds: np.ndarray):
+        self.traj_len = trajectory_length
+        self.spatial_dim = spatial_dim
+        self.domain_bounds = np.array([bounds[:, 0].min() * np.ones(spatial_dim),
+                                       bounds[:, 1].max() * np.ones(spatial_dim)]).T
+        self.sampler = qmc.Sobol(d=spatial_dim)
+
+    def sample(self, num_points: int = 10, method: str = 'sobol') -> np.ndarray:
+        if method != 'sobol':
+            raise NotImplementedError(f'{method} not implemented')
+        u = self.sampler.random(num_points * self.traj_len)
+        pts = qmc.scale(u, self.domain_bounds[:, 0], self.domain_bounds[:, 1])
+        return pts.reshape(num_points, self.traj_len * self.spatial_dim)

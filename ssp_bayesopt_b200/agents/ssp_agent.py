@@ -1,0 +1,150 @@
+"""SSP + BLR agent on the GPU.  Mirrors `ssp_bayes_opt/agents/ssp_agent.py` of the reference.
+
+Hot path: `eval` (ssp_agent.py:125-137) and `best_candidate` call the fused kernel
+(`sspbo_score`: encode -> BLR predict -> MI/UCB bonus -> argmax) and never materialise phi;
+`update` (ssp_agent.py:187-224) encodes x_t and applies the float64 rank-one posterior update on the
+device.  Deviations, documented in DESIGN.md: `decoder_method` defaults to 'from-set' (the reference's
+default 'network-optim' needs TensorFlow); omitting `length_scale` raises instead of fitting the
+sklearn sinc-kernel GP (ssp_agent.py:96-109, out of the hot-path scope).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import blr, sspspace
+from .._lib import ENGINE_AUTO
+from .agent import Agent
+
+
+class SSPAgent(Agent):
+    def __init__(self, init_xs, init_ys, ssp_space, decoder_method='from-set', gamma_c=1.0,
+                 beta_ucb=np.log(2 / 1e-6), var_decay=0., **kwargs):
+        super().__init__()
+        (num_pts, data_dim) = init_xs.shape
+        self.data_dim = data_dim
+        self.init_xs = init_xs
+        self.init_ys = init_ys
+        self.decoder_method = decoder_method
+        self.score_engine = kwargs.pop('score_engine', ENGINE_AUTO)
+
+        self._set_ssp_space(ssp_space=ssp_space, **kwargs)
+        self._set_decoder()
+
+        init_phis = self.encode(init_xs)
+        self.blr = blr.BayesianLinearRegression(self.ssp_dim, engine=self._scoring_engine())
+        self.blr.update(init_phis, np.array(init_ys))
+        self.constraint_ssp = np.zeros((self.ssp_dim, 1))
+
+        self.gamma_t = 0
+        self.gamma_c = gamma_c
+        self.var_weight = beta_ucb
+        self.var_decay = var_decay
+
+    # ------------------------------------------------------------------ construction
+    def _scoring_engine(self):
+        """Device context whose `score` sees candidates in this agent's input layout."""
+        return self.ssp_space.engine
+
+    def _set_ssp_space(self, ssp_space, seed=0, **kwargs):
+        if ssp_space is None:
+            ssp_space = sspspace.HexagonalSSPSpace(self.data_dim, ssp_dim=kwargs.get('ssp_dim', 100),
+                                                   domain_bounds=kwargs.get('domain_bounds', None),
+                                                   length_scale=1, rng=seed)
+        self.ssp_space = ssp_space
+        self.ssp_dim = ssp_space.ssp_dim
+        if 'length_scale' not in kwargs or np.any(np.asarray(kwargs.get('length_scale')) < 0):
+            raise NotImplementedError(
+                "length_scale must be given: the sinc-kernel GP length-scale fit of the reference "
+                "(ssp_agent.py:96-109) is outside the GPU hot-path scope")
+        self.ssp_space.update_lengthscale(kwargs.get('length_scale'))
+
+    def _set_decoder(self):
+        if self.decoder_method in ('network', 'network-optim', 'regression'):
+            raise NotImplementedError(f"decoder_method={self.decoder_method!r} (learned decoders) is out of scope; "
+                                      "use 'from-set' or 'direct-optim'")
+        self.init_samples = self.get_init_samples(self.ssp_space)
+
+    def length_scale(self):
+        return self.ssp_space.length_scale
+
+    def get_init_samples(self, ssp_space):
+        """Decoding set: grid size rule of ssp_agent.py:111-123."""
+        ls = np.asarray(ssp_space.length_scale, dtype=np.float64).reshape(-1)
+        n_ls = [2 * int(np.ceil((b[1] - b[0]) / ls[i])) for i, b in enumerate(ssp_space.domain_bounds)]
+        if (np.prod(n_ls) * ssp_space.ssp_dim > 1e7) or ('optim' not in self.decoder_method):
+            per_dim = np.min([100, int(np.ceil((1e7 / ssp_space.ssp_dim) ** (1 / ssp_space.domain_dim)))])
+            return ssp_space.get_sample_pts_and_ssps(per_dim, 'grid')
+        return ssp_space.get_sample_pts_and_ssps(1, 'length-scale')
+
+    # ------------------------------------------------------------------ hot path
+    def _gamma(self):
+        return float(np.ravel(self.gamma_t)[0])
+
+    def eval(self, xs):
+        """mu (1, n), var (n,), acq (n,) with acq = var_weight (sqrt(var + gamma_t) - sqrt(gamma_t))."""
+        _, (mu, var, acq) = self._scoring_engine().score(xs, self.var_weight, self._gamma(), want_outputs=True,
+                                                         engine=self.score_engine)
+        return (mu.double().cpu().numpy().reshape(1, -1), var.double().cpu().numpy(), acq.double().cpu().numpy())
+
+    def best_candidate(self, xs, index0=0, reset_best=True):
+        """argmax_i mu_i + acq_i over a candidate block (host array or device tensor).  Returns the device
+        key tensor (see sspbo_score); `self._scoring_engine().best()` unpacks it."""
+        key, _ = self._scoring_engine().score(xs, self.var_weight, self._gamma(), index0=index0, want_outputs=False,
+                                              engine=self.score_engine, reset_best=reset_best)
+        return key
+
+    def initial_guess(self):
+        return self.blr.sample()
+
+    def untrusted(self, x, badness=-1):
+        self.constraint_ssp += badness * self.encode(x).reshape(-1, 1)
+
+    def acquisition_func(self):
+        """phi-space objective/gradient pair of ssp_agent.py:156-185, on host copies of (m, S).  This is the
+        reference's L-BFGS route ('next' row f.2 of SURVEY.md section 8); `maximize` here uses `best_candidate`."""
+        margin = 4
+        m, sigma = self.blr.m, self.blr.S
+        gamma, beta_inv, lam = self._gamma(), 1 / float(np.ravel(self.blr.beta)[0]), self.var_weight
+
+        def _clamp(phi):
+            nrm = np.linalg.norm(phi)
+            return margin * phi / nrm if nrm > margin else phi
+
+        def min_func(phi):
+            phi = _clamp(phi)
+            mi = lam * np.sqrt(gamma + beta_inv + phi.T @ sigma @ phi) - np.sqrt(gamma)
+            return -(phi.T @ m + mi).flatten()
+
+        def gradient(phi):
+            phi = _clamp(phi)
+            sig_phi = sigma @ phi
+            return -(m.flatten() + lam * sig_phi / np.sqrt(phi.T @ sig_phi + gamma + beta_inv))
+
+        return min_func, gradient
+
+    def update(self, x_t: np.ndarray, y_t: np.ndarray, sigma_t: float, step_num=0):
+        x_val, y_val = x_t, y_t
+        if len(x_t.shape) < 2:
+            x_val = x_t.reshape(1, x_t.shape[0])
+            y_val = y_t.reshape(1, y_t.shape[0])
+        phi = np.atleast_2d(self.encode(x_val).squeeze())
+        self.blr.update(phi, y_val)
+
+        if isinstance(self.var_decay, (int, float)):
+            self.var_weight = self.var_weight + self.var_decay
+        elif callable(self.var_decay):
+            self.var_weight = self.var_weight + self.var_decay(step_num)
+        else:
+            raise RuntimeError(f'unable to use {self.var_weight}, expected number or callable')
+        if isinstance(self.gamma_c, (int, float)):
+            self.gamma_t = self.gamma_t + self.gamma_c * sigma_t
+        elif callable(self.gamma_c):
+            self.gamma_t = self.gamma_t + self.gamma_c(step_num) * sigma_t
+        else:
+            raise RuntimeError(f'unable to use {self.gamma_c}, expected number or callable')
+
+    def encode(self, x):
+        return self.ssp_space.encode(x)
+
+    def decode(self, ssp):
+        return self.ssp_space.decode(ssp, method=self.decoder_method, samples=self.init_samples)

@@ -1,0 +1,222 @@
+"""BO driver with the reference's surface, acquisition maximised by fused candidate scoring on the GPU.
+
+Mirrors `ssp_bayes_opt/bayesian_optimization.py:21-333`: same constructor, `initialize_agent`,
+`maximize(init_points, n_iter, num_restarts, agent_type, **kwargs)`, attributes `xs ys times full_times
+memory total_time agt`, properties `res`, `max`, the `log_and_plot_f` hook, and the rule that `f` is
+called as `f(x_2d)` when it takes one positional argument, else `f(x_2d, info_str)` (:51-54).
+
+What changed, on purpose: the reference maximises the acquisition with multi-restart
+L-BFGS in phi-space and decodes phi* (:249-282).  Here each step scores a whole candidate set with the fused
+kernel (encode -> BLR-UCB/MI -> argmax) and takes the arg-max candidate; `num_restarts` and `use_jac`
+are accepted and ignored.  Candidate sets (extra kwargs, all optional):
+    acq_candidates      'grid' (default) | 'uniform' | ndarray (N, data_dim)
+    candidates_per_dim  grid resolution per axis (default: the agent's decoding-grid rule)
+    n_candidates        size of the 'uniform' set (counter-based uniform in bounds, float32)
+    candidate_seed      seed of the 'uniform' set
+    candidate_chunk     candidates per kernel launch (default 1<<22)
+Supported agent types: 'ssp-hex', 'ssp-rand', 'ssp-custom' (with ssp_space=...), 'ssp-traj'.  Under
+torch.distributed (one process per GPU) the candidate index range is sharded across ranks.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from typing import Callable
+
+import numpy as np
+
+from . import agents, dist, sspspace
+
+_BO_KW = ('acq_candidates', 'candidates_per_dim', 'n_candidates', 'candidate_seed', 'candidate_chunk')
+
+
+class BayesianOptimization:
+    def __init__(self, f: Callable[..., float] = None, bounds: np.ndarray = None,
+                 log_and_plot_f: Callable[..., float] = None, random_state: int = None,
+                 verbose: bool = False, sampling_seed: int = None):
+        assert f is not None, 'Must specify a callable target function'
+        assert bounds is not None, 'Must specify input bounds'
+        assert bounds.shape[1] == 2, 'bounds must have shape (n_dims, 2)'
+        if random_state is not None:
+            np.random.seed(random_state)
+        if hasattr(f, '__code__') and f.__code__.co_argcount == 1:
+            self.target = lambda x, info=None: f(x)
+        else:
+            self.target = f
+        self.sampling_seed = sampling_seed
+        self.bounds = bounds
+        self.log_and_plot_f = log_and_plot_f
+        self.verbose = verbose
+        self.data_dim = self.bounds.shape[0]
+        self.num_decoding = 10000
+        self.xs = None
+        self.ys = None
+        self.logger = logging.getLogger(__name__)
+
+    # ------------------------------------------------------------------ agent construction
+    def initialize_agent(self, init_points=10, agent_type='ssp-hex', **kwargs):
+        """Sample / adopt the initial design, evaluate the target, build the agent (:67-185)."""
+        kwargs.pop('num_perimeter_samples', 0)
+        if 'traj' in agent_type:
+            domain = agents.domains.TrajectoryDomain(kwargs['traj_len'], kwargs['x_dim'], self.bounds)
+        else:
+            domain = agents.domains.BoundedDomain(self.bounds)
+        if isinstance(init_points, (int, np.integer)):
+            init_xs = domain.sample(int(init_points))
+        else:
+            init_xs = np.copy(init_points[0])
+        n_init = init_xs.shape[0]
+        if isinstance(init_points, tuple) and init_points[1] is not None:
+            init_ys = init_points[1]
+        else:
+            init_ys = np.array([self.target(np.atleast_2d(x), str(i)) for i, x in enumerate(init_xs)]
+                               ).reshape((n_init, -1))
+
+        if agent_type == 'ssp-hex':
+            space = sspspace.HexagonalSSPSpace(self.data_dim, **kwargs)
+            agt = agents.SSPAgent(init_xs, init_ys, space, **kwargs)
+        elif agent_type == 'ssp-rand':
+            space = sspspace.RandomSSPSpace(self.data_dim, **kwargs)
+            agt = agents.SSPAgent(init_xs, init_ys, space, **kwargs)
+        elif agent_type == 'ssp-custom':
+            assert 'ssp_space' in kwargs
+            kw = {k: v for k, v in kwargs.items() if k != 'ssp_space'}
+            kw.setdefault('length_scale', kwargs['ssp_space'].length_scale)
+            agt = agents.SSPAgent(init_xs, init_ys, kwargs['ssp_space'], **kw)
+        elif agent_type == 'ssp-traj':
+            agt = agents.SSPTrajectoryAgent(init_xs, init_ys, **kwargs)
+            init_xs, init_ys = agt.init_xs, agt.init_ys
+        else:
+            raise NotImplementedError(
+                f'{agent_type} agent is not part of the GPU hot path (supported: ssp-hex, ssp-rand, ssp-custom, ssp-traj)')
+        self.logger.info(f'{type(agt).__name__} agent created')
+        return agt, init_xs, init_ys
+
+    # ------------------------------------------------------------------ candidate sets
+    def _build_candidates(self, agt, acq_candidates, candidates_per_dim, n_candidates, candidate_seed):
+        """Returns (kind, payload, total).  Each rank materialises only its shard on its GPU."""
+        eng = agt._scoring_engine()
+        rank, world = dist.rank_world()
+        lo, hi = self.bounds[:, 0], self.bounds[:, 1]
+        if isinstance(acq_candidates, np.ndarray):
+            total = acq_candidates.shape[0]
+            s, e = dist.shard_range(total, rank, world)
+            return dict(total=total, start=s, x=eng.to_device(acq_candidates[s:e]), lookup=None)
+        if isinstance(agt, agents.SSPTrajectoryAgent):
+            if acq_candidates == 'grid':
+                acq_candidates = 'uniform'                           # a grid over L*x_dim axes is not meaningful
+            lo = np.tile(agt.domain_bounds[:, 0], agt.traj_len)
+            hi = np.tile(agt.domain_bounds[:, 1], agt.traj_len)
+        if acq_candidates == 'grid':
+            if candidates_per_dim is None:
+                candidates_per_dim = int(np.min([100, int(np.ceil((1e7 / agt.ssp_dim) ** (1 / self.data_dim)))]))
+            axes = [np.linspace(self.bounds[i, 0], self.bounds[i, 1], int(candidates_per_dim))
+                    for i in range(self.data_dim)]
+            total = int(candidates_per_dim) ** self.data_dim
+            s, e = dist.shard_range(total, rank, world)
+            return dict(total=total, start=s, x=eng.grid_points(axes, s, e - s), lookup=None)
+        if acq_candidates == 'uniform':
+            total = int(n_candidates or 100000)
+            s, e = dist.shard_range(total, rank, world)
+            torch = eng.torch
+            u = eng.fill_uniform(candidate_seed, s, e - s, len(lo))
+            span = torch.as_tensor((hi - lo).astype(np.float32), device=u.device)
+            off = torch.as_tensor(lo.astype(np.float32), device=u.device)
+            u.mul_(span).add_(off)                                   # float32 candidates inside the bounds
+            return dict(total=total, start=s, x=u, lookup=None)
+        raise ValueError(f'unknown acq_candidates={acq_candidates!r}')
+
+    def _select(self, agt, cand, chunk):
+        """One acquisition step: fused scoring of this rank's shard, key all-reduce, x* lookup."""
+        eng = agt._scoring_engine()
+        x, start = cand['x'], cand['start']
+        n_local = x.shape[0]
+        key = None
+        first = True
+        for c0 in range(0, max(n_local, 1), chunk):
+            if n_local == 0:
+                break
+            key = agt.best_candidate(x[c0:c0 + chunk], index0=start + c0, reset_best=first)
+            first = False
+        if key is None:
+            eng._best.zero_()
+            key = eng._best
+        dist.allreduce_best(key)
+        score, gidx = eng.best()
+        # owner of the winning row publishes it (one small broadcast; single-GPU: a D2H copy of one row)
+        rank, world = dist.rank_world()
+        owner_has = start <= gidx < start + n_local
+        torch = eng.torch
+        row = x[gidx - start].to(torch.float64) if owner_has else torch.zeros(x.shape[1], dtype=torch.float64,
+                                                                               device=x.device)
+        if world > 1:
+            import torch.distributed as td
+            td.all_reduce(row, op=td.ReduceOp.SUM)                   # exactly one rank contributes non-zeros
+        return score, gidx, row.cpu().numpy().reshape(1, -1)
+
+    # ------------------------------------------------------------------ BO loop
+    def maximize(self, init_points=10, n_iter: int = 100, num_restarts: int = 5, agent_type='ssp-hex',
+                 save_memory=True, use_jac=True, **kwargs):
+        bo_kw = {k: kwargs.pop(k) for k in _BO_KW if k in kwargs}
+        acq_candidates = bo_kw.get('acq_candidates', 'grid')
+        chunk = int(bo_kw.get('candidate_chunk', 1 << 22))
+        kwargs.setdefault('decoder_method', 'from-set')
+
+        agt, init_xs, init_ys = self.initialize_agent(init_points, agent_type, domain_bounds=self.bounds, **kwargs)
+        self.agt = agt
+        cand = self._build_candidates(agt, acq_candidates, bo_kw.get('candidates_per_dim'),
+                                      bo_kw.get('n_candidates'), int(bo_kw.get('candidate_seed', 0)))
+
+        n0 = init_xs.shape[0]
+        self.times = np.zeros((n_iter,))
+        self.full_times = np.zeros((n_iter,))
+        self.memory = np.zeros((n_iter, 1))
+        self.xs = np.zeros((n_iter + n0, init_xs.shape[1]))
+        self.ys = np.zeros((n_iter + n0,))
+        self.xs[:n0] = init_xs
+        self.ys[:n0] = np.ravel(init_ys)
+        self.acq_values = np.zeros((n_iter,))
+        self.acq_indices = np.zeros((n_iter,), dtype=np.int64)
+        rank, _ = dist.rank_world()
+
+        full_start = time.perf_counter_ns()
+        for t in range(n_iter):
+            start = time.perf_counter_ns()
+            score, gidx, x_t = self._select(agt, cand, chunk)        # synchronises on the 8-byte key
+            self.times[t] = time.perf_counter_ns() - start
+            self.acq_values[t], self.acq_indices[t] = score, gidx
+
+            status = f'{t + n0}'
+            y_t = np.atleast_2d(self.target(x_t, status))
+            if dist.is_distributed():                                 # keep replicas identical even if f is noisy
+                import torch
+                import torch.distributed as td
+                yb = torch.as_tensor(y_t, dtype=torch.float64, device=agt._scoring_engine()._dev())
+                td.broadcast(yb, src=0)
+                y_t = yb.cpu().numpy()
+
+            mu_t, var_t, phi_t = agt.eval(x_t)
+            if self.verbose and rank == 0:
+                print(f'| step {t + n0}\t | {y_t}, {np.sqrt(var_t)}, {phi_t}\t ')
+            update_start = time.perf_counter_ns()
+            agt.update(x_t, y_t, var_t, step_num=t + n0)
+            agt._scoring_engine().torch.cuda.synchronize()
+            self.times[t] += time.perf_counter_ns() - update_start
+            self.full_times[t] = time.perf_counter_ns() - start
+
+            t_now = t + n0
+            self.xs[t_now] = np.copy(x_t)
+            self.ys[t_now] = np.ravel(y_t)[0]
+            if self.log_and_plot_f is not None:
+                self.log_and_plot_f(np.vstack(self.xs[:t_now + 1]), np.vstack(self.ys[:t_now + 1]),
+                                    times=self.times, trial=t_now, memory=self.memory)
+        self.total_time = time.perf_counter_ns() - full_start
+
+    @property
+    def res(self):
+        return [{'target': t, 'params': p} for t, p in zip(self.ys, self.xs)]
+
+    @property
+    def max(self):
+        i = np.argmax(self.ys)
+        return {'target': self.ys[i], 'params': self.xs[i]}

@@ -1,0 +1,770 @@
+// libsspbo.so core: context, SSP space, K1 encode, K3 BLR posterior (float64), K4 from-set
+// decode, candidate generators.  Hand-written CUDA for sm_100a; no CPU fallback anywhere.
+//
+// Reference arithmetic being replaced (ctn-waterloo/ssp-bayesopt, ssp_bayes_opt/):
+//   SSPSpace.encode                sspspace.py:254-276
+//   BayesianLinearRegression.*     blr.py:27-97
+//   SSPSpace.decode('from-set')    sspspace.py:352-356
+//   SSPSpace.get_sample_points     sspspace.py:488-495
+#include "sspbo_internal.cuh"
+#include <math.h>
+#include <new>
+#include <vector>
+
+static const double kTwoPi = 6.283185307179586476925286766559;
+
+// =====================================================================================
+// small device utilities
+// =====================================================================================
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum, result valid in every thread; red must hold >= 32 doubles
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = (l < nw) ? red[l] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// =====================================================================================
+// K1  encode: x -> psi (shared memory) -> phi = B psi   (float64 throughout)
+// =====================================================================================
+// psi of one candidate row (L waypoints of n coordinates) at frequency k: sum of L unit phasors.
+template <typename XT>
+__device__ __forceinline__ void psi_entry(const XT* __restrict__ xrow, const double* __restrict__ A_turns,
+                                          const double* __restrict__ tau_turns, int n, int K, int L, int k,
+                                          double& cs, double& sn) {
+    cs = 0.0; sn = 0.0;
+    const double* Ak = A_turns + (size_t)k * n;
+    for (int j = 0; j < L; ++j) {
+        double t = tau_turns ? tau_turns[(size_t)j * K + k] : 0.0;
+        for (int a = 0; a < n; ++a) t = fma(Ak[a], (double)xrow[j * n + a], t);
+        t -= rint(t);                                   // exact range reduction to [-1/2, 1/2] turns
+        double s, c;
+        sincospi(2.0 * t, &s, &c);
+        cs += c; sn += s;
+    }
+}
+
+constexpr int ENC_CPB = 4;       // candidates per block
+constexpr int ENC_THREADS = 256;
+
+template <typename XT>
+__global__ void __launch_bounds__(ENC_THREADS)
+k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
+         const double2* __restrict__ twiddle, int n, int K, int L, double* __restrict__ phi) {
+    extern __shared__ double psi_s[];                   // ENC_CPB x d
+    const int d = 2 * K + 1;
+    const int nl = n * L;
+    for (int64_t base = (int64_t)blockIdx.x * ENC_CPB; base < N; base += (int64_t)gridDim.x * ENC_CPB) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ENC_CPB * K; i += blockDim.x) {
+            int c = i / K, k = i - c * K;
+            if (base + c < N) {
+                double cs, sn;
+                psi_entry(x + (base + c) * nl, A_turns, tau_turns, n, K, L, k, cs, sn);
+                psi_s[c * d + 1 + k] = cs;
+                psi_s[c * d + 1 + K + k] = sn;
+                if (k == 0) psi_s[c * d] = (double)L;
+            }
+        }
+        __syncthreads();
+        const double inv_d = 1.0 / (double)d;
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            double acc[ENC_CPB];
+#pragma unroll
+            for (int c = 0; c < ENC_CPB; ++c) acc[c] = 0.0;
+            int idx = 0;
+            for (int k = 1; k <= K; ++k) {
+                idx += j; if (idx >= d) idx -= d;       // (j*k) mod d
+                double2 tw = twiddle[idx];
+#pragma unroll
+                for (int c = 0; c < ENC_CPB; ++c)
+                    acc[c] += psi_s[c * d + k] * tw.x - psi_s[c * d + K + k] * tw.y;
+            }
+#pragma unroll
+            for (int c = 0; c < ENC_CPB; ++c)
+                if (base + c < N) phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * acc[c]) * inv_d;
+        }
+    }
+}
+
+// =====================================================================================
+// basis change phi-space <-> psi-space on d-vectors (float64)
+//   out[0] = s0 * sum_j in[j];  out[k] = sk * sum_j in[j] cos(w_jk);  out[K+k] = -sk * sum_j in[j] sin(w_jk)
+// (s0, sk) = (1, 1) maps phi -> psi ;  (1/d, 2/d) maps m -> m' = B^T m.
+// =====================================================================================
+__global__ void k_analysis(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ twiddle,
+                           int K, double s0, double sk) {
+    __shared__ double red[64];
+    const int d = 2 * K + 1;
+    const int k = blockIdx.x;                           // 0..K
+    double c = 0.0, s = 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        int idx = (int)(((long long)j * k) % d);
+        double2 tw = twiddle[idx];
+        double v = in[j];
+        c += v * tw.x; s += v * tw.y;
+    }
+    c = block_sum(c, red);
+    s = block_sum(s, red + 32);
+    if (threadIdx.x == 0) {
+        if (k == 0) out[0] = s0 * c;
+        else { out[k] = sk * c; out[K + k] = -sk * s; }
+    }
+}
+
+// =====================================================================================
+// float64 GEMV / rank-one kernels for the posterior (d <= a few thousand)
+// =====================================================================================
+// y = M x   (row-major d x d): one warp per row
+__global__ void k_gemv_rows(const double* __restrict__ M, const double* __restrict__ x, double* __restrict__ y, int d) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= d) return;
+    const double* r = M + (size_t)row * d;
+    double acc = 0.0;
+    for (int j = threadIdx.x & 31; j < d; j += 32) acc += r[j] * x[j];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) y[row] = acc;
+}
+// y = M^T x : block (32 x 8) handles 32 columns, strides over rows
+__global__ void k_gemv_cols(const double* __restrict__ M, const double* __restrict__ x, double* __restrict__ y, int d) {
+    __shared__ double part[8][33];
+    int col = blockIdx.x * 32 + threadIdx.x;
+    double acc = 0.0;
+    if (col < d)
+        for (int i = threadIdx.y; i < d; i += 8) acc += M[(size_t)i * d + col] * x[i];
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < d) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
+        y[col] = t;
+    }
+}
+// scalars for one observation.  scal[0] = coefS = beta / (1 + beta phi.v)   (Sherman-Morrison, blr.py:64-67)
+//                               scal[1] = kappa = beta / (sqrt(s) (1 + sqrt(s))), s = 1 + beta y.y  (factor update)
+//                               scal[2] = phi . v  (= phi^T S phi before the update, the prior variance term)
+__global__ void k_update_scalars(const double* __restrict__ phi, const double* __restrict__ v, const double* __restrict__ y,
+                                 int d, double beta, double* __restrict__ scal) {
+    __shared__ double red[64];
+    double pv = 0.0, yy = 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) { pv += phi[j] * v[j]; yy += y[j] * y[j]; }
+    pv = block_sum(pv, red);
+    yy = block_sum(yy, red + 32);
+    if (threadIdx.x == 0) {
+        scal[0] = beta / (1.0 + beta * pv);
+        double s = 1.0 + beta * yy, rs = sqrt(s);
+        scal[1] = beta / (rs * (1.0 + rs));
+        scal[2] = pv;
+    }
+}
+// M[i][j] += sign * coef * a[i] * b[j]   (coef read from device memory, or the immediate when coef_dev == nullptr)
+__global__ void k_rank1(double* __restrict__ M, const double* __restrict__ a, const double* __restrict__ b, int d,
+                        const double* __restrict__ coef_dev, double coef_imm) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= d) return;
+    double c = coef_dev ? -(*coef_dev) : coef_imm;
+    M[(size_t)i * d + j] += c * a[i] * b[j];
+}
+__global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, double a, int d) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < d) y[j] += a * x[j];
+}
+__global__ void k_set_diag(double* __restrict__ M, int d, double v0, double v) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < d) M[(size_t)j * d + j] = (j == 0) ? v0 : v;
+}
+
+// refresh of the scoring operands from the float64 masters
+__global__ void k_refresh_operands(const double* __restrict__ R, const double* __restrict__ mp, int d, int dp,
+                                   double r_scale, float* __restrict__ Rt_f32, __half* __restrict__ Rh,
+                                   __half* __restrict__ Rl, float* __restrict__ mp_f32) {
+    __shared__ double tile[32][33];
+    int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    // read R[j][k] coalesced along k
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int j = j0 + r, k = k0 + threadIdx.x;
+        double v = (j < d && k < d) ? R[(size_t)j * d + k] : 0.0;
+        tile[r][threadIdx.x] = v;
+        if (j < dp && k < dp) {
+            double sv = v * r_scale;
+            __half h = __double2half(sv);
+            double rem = sv - (double)__half2float(h);
+            Rh[(size_t)j * dp + k] = h;
+            Rl[(size_t)j * dp + k] = __double2half(rem);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int k = k0 + r, j = j0 + threadIdx.x;
+        if (k < dp && j < dp) Rt_f32[(size_t)k * dp + j] = (float)tile[threadIdx.x][r];
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int i = threadIdx.y * 32 + threadIdx.x; i < dp; i += 256) mp_f32[i] = (i < d) ? (float)mp[i] : 0.f;
+    }
+}
+
+// =====================================================================================
+// BLR.predict on explicit phi (float64): var = 1/beta + phi^T S phi ; mu = m . phi
+// =====================================================================================
+constexpr int PRED_CPB = 4;
+__global__ void __launch_bounds__(256)
+k_predict(const double* __restrict__ phi, int64_t N, const double* __restrict__ S, const double* __restrict__ m, int d,
+          double inv_beta, double* __restrict__ mu, double* __restrict__ var) {
+    extern __shared__ double ph[];                      // PRED_CPB x d
+    __shared__ double red[64];
+    for (int64_t base = (int64_t)blockIdx.x * PRED_CPB; base < N; base += (int64_t)gridDim.x * PRED_CPB) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < PRED_CPB * d; i += blockDim.x) {
+            int c = i / d;
+            ph[i] = (base + c < N) ? phi[(base + c) * d + (i - c * d)] : 0.0;
+        }
+        __syncthreads();
+        double q[PRED_CPB], u[PRED_CPB];
+#pragma unroll
+        for (int c = 0; c < PRED_CPB; ++c) { q[c] = 0.0; u[c] = 0.0; }
+        // blr.py:96: einsum('ij,ij->i', phi, phi @ S.T):  (phi S^T)_j = sum_i phi_i S[j][i]
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            double t[PRED_CPB];
+#pragma unroll
+            for (int c = 0; c < PRED_CPB; ++c) t[c] = 0.0;
+            for (int i = 0; i < d; ++i) {
+                double s = S[(size_t)i * d + j];        // S symmetric to ~1e-13; column read is coalesced
+#pragma unroll
+                for (int c = 0; c < PRED_CPB; ++c) t[c] += ph[c * d + i] * s;
+            }
+            double mj = m[j];
+#pragma unroll
+            for (int c = 0; c < PRED_CPB; ++c) { q[c] += t[c] * ph[c * d + j]; u[c] += mj * ph[c * d + j]; }
+        }
+#pragma unroll
+        for (int c = 0; c < PRED_CPB; ++c) {
+            double qq = block_sum(q[c], red);
+            double uu = block_sum(u[c], red + 32);
+            if (threadIdx.x == 0 && base + c < N) { var[base + c] = inv_beta + qq; mu[base + c] = uu; }
+        }
+    }
+}
+
+// =====================================================================================
+// K4 from-set decode: sims = sample_ssps @ unit^T ; first-index argmax per query
+// =====================================================================================
+__global__ void k_unit_rows(const double* __restrict__ q, double* __restrict__ unit, int d) {
+    __shared__ double red[32];
+    const double* r = q + (size_t)blockIdx.x * d;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s += r[j] * r[j];
+    s = block_sum(s, red);
+    double nrm = fmax(sqrt(s), 1e-6);                   // sspspace.py:352
+    for (int j = threadIdx.x; j < d; j += blockDim.x) unit[(size_t)blockIdx.x * d + j] = r[j] / nrm;
+}
+// one warp per sample row; sims[qi * M + i]
+__global__ void k_sims(const double* __restrict__ ssps, int64_t M, const double* __restrict__ unit, int nq, int d,
+                       double* __restrict__ sims) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const double* r = ssps + row * d;
+    for (int qi = 0; qi < nq; ++qi) {
+        const double* u = unit + (size_t)qi * d;
+        double acc = 0.0;
+        for (int j = threadIdx.x & 31; j < d; j += 32) acc += r[j] * u[j];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) sims[(size_t)qi * M + row] = acc;
+    }
+}
+__device__ __forceinline__ bool better_f64(double v, int64_t i, double bv, int64_t bi) {
+    // np.argmax: first maximum; NaN compares as the maximum
+    bool vn = isnan(v), bn = isnan(bv);
+    if (vn || bn) return vn && (!bn || i < bi);
+    return (v > bv) || (v == bv && i < bi);
+}
+__global__ void k_argmax_rows(const double* __restrict__ sims, int64_t M, int64_t* __restrict__ idx_out) {
+    __shared__ double bv_s[32];
+    __shared__ long long bi_s[32];
+    const double* r = sims + (size_t)blockIdx.x * M;
+    double bv = -INFINITY; int64_t bi = INT64_MAX;
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x)
+        if (better_f64(r[i], i, bv, bi)) { bv = r[i]; bi = i; }
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+        if (better_f64(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { bv_s[w] = bv; bi_s[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        bv = (l < nw) ? bv_s[l] : -INFINITY; bi = (l < nw) ? bi_s[l] : INT64_MAX;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+            if (better_f64(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (l == 0) idx_out[blockIdx.x] = bi;
+    }
+}
+
+// =====================================================================================
+// candidate generators
+// =====================================================================================
+__global__ void k_fill_uniform(uint64_t seed, int64_t first_elem, int64_t count, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = (uint64_t)(first_elem + i) + (seed << 40) + 0x9E3779B97F4A7C15ull;   // splitmix64 finaliser
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        out[i] = (float)(z >> 40) * 5.9604644775390625e-8f;                               // 24 bits * 2^-24
+    }
+}
+struct GridDesc { int n; int counts[16]; int offs[16]; };
+__global__ void k_grid_points(const double* __restrict__ axes, GridDesc g, int64_t start, int64_t count,
+                              double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = start + i;
+        // flattened C-order of a meshgrid('xy') array of shape (N1, N0, N2, ..., N_{n-1})
+        for (int a = g.n - 1; a >= 2; --a) {
+            int ia = (int)(p % g.counts[a]); p /= g.counts[a];
+            out[i * g.n + a] = axes[g.offs[a] + ia];
+        }
+        int i0 = (int)(p % g.counts[0]); p /= g.counts[0];
+        out[i * g.n + 0] = axes[g.offs[0] + i0];
+        if (g.n >= 2) out[i * g.n + 1] = axes[g.offs[1] + (int)p];
+    }
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+template <typename T>
+static int dev_alloc(sspbo_ctx* ctx, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    SSPBO_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    SSPBO_CUDA(ctx, cudaMemset(*p, 0, count * sizeof(T)));
+    return SSPBO_OK;
+}
+template <typename T>
+static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+extern "C" int sspbo_abi_version(void) { return 1; }
+
+extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
+    if (!out) return SSPBO_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SSPBO_ECUDA;
+    sspbo_ctx* ctx = new (std::nothrow) sspbo_ctx();
+    if (!ctx) return SSPBO_EINVAL;
+    ctx->device = device;
+    cudaSetDevice(device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMalloc((void**)&ctx->scal, 16 * sizeof(double)) != cudaSuccess) { delete ctx; return SSPBO_ECUDA; }
+    *out = ctx;
+    return SSPBO_OK;
+}
+
+static void free_blr(sspbo_ctx* ctx) {
+    dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
+    dev_free(&ctx->R); dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
+    dev_free(&ctx->Rh); dev_free(&ctx->Rl);
+    dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
+    ctx->blr_ready = false; ctx->has_beta = false;
+}
+
+extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    sspbo_umma_release(ctx);
+    free_blr(ctx);
+    dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    dev_free(&ctx->twiddle); dev_free(&ctx->scal);
+    delete ctx;
+}
+
+extern "C" const char* sspbo_last_error(const sspbo_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+extern "C" int sspbo_last_engine(const sspbo_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
+extern "C" int64_t sspbo_launch_count(const sspbo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const double* inv_ls, int K, int n) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!A_plus || !inv_ls || K < 1 || n < 1 || n > 16) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set: need K>=1, 1<=n<=16");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (K != ctx->K || !ctx->has_factor) { free_blr(ctx); sspbo_umma_release(ctx); }
+    const int d = 2 * K + 1;
+    std::vector<double> At((size_t)K * n);
+    std::vector<float> Af((size_t)K * n);
+    double mx = 0.0;
+    for (int k = 0; k < K; ++k) {
+        double rs = 0.0;
+        for (int a = 0; a < n; ++a) {
+            double t = A_plus[(size_t)k * n + a] * inv_ls[a] / kTwoPi;
+            At[(size_t)k * n + a] = t; Af[(size_t)k * n + a] = (float)t; rs += fabs(t);
+        }
+        mx = fmax(mx, rs);
+    }
+    std::vector<double2> tw(d);
+    for (int i = 0; i < d; ++i) {
+        // exact-ish twiddles: reduce the angle to the first octant in integer arithmetic via sincospi
+        double frac = 2.0 * (double)i / (double)d;
+        tw[i].x = cospi(frac); tw[i].y = sinpi(frac);
+    }
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->A_turns, (size_t)K * n))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->A_turns_f32, (size_t)K * n))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->twiddle, (size_t)d))) return rc;
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns, At.data(), At.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns_f32, Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "space_set_traj before space_set");
+    if (L < 1 || L > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "traj length must be in [1, 64]");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    ctx->L = L;
+    if (!tau_host) { if (L != 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "tau is required when L > 1"); return SSPBO_OK; }
+    std::vector<double> t((size_t)L * ctx->K);
+    std::vector<float> tf((size_t)L * ctx->K);
+    for (size_t i = 0; i < t.size(); ++i) {
+        double turns = tau_host[i] / kTwoPi;
+        turns -= rint(turns);
+        t[i] = turns; tf[i] = (float)turns;
+    }
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->tau_turns, t.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->tau_turns_f32, t.size()))) return rc;
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->tau_turns, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->tau_turns_f32, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_space_dims(const sspbo_ctx* ctx, int* d, int* K, int* n, int* L) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (d) *d = ctx->d; if (K) *K = ctx->K; if (n) *n = ctx->n; if (L) *L = ctx->L;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, double* phi_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "encode before space_set");
+    if (N < 0 || (N > 0 && (!x || !phi_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: null pointer");
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t smem = (size_t)ENC_CPB * ctx->d * sizeof(double);
+    int64_t blocks64 = (N + ENC_CPB - 1) / ENC_CPB;
+    int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 8 ? blocks64 : (int64_t)ctx->sm_count * 8);
+    if (x_dtype == SSPBO_F32) {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_encode<float><<<blocks, ENC_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
+                                                           ctx->n, ctx->K, ctx->L, phi_out);
+    } else if (x_dtype == SSPBO_F64) {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_encode<double><<<blocks, ENC_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
+                                                            ctx->n, ctx->K, ctx->L, phi_out);
+    } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------ BLR
+static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_blr(ctx);
+    const int dp = sspbo_pad64(d);
+    const size_t dd = (size_t)d * d, dpp = (size_t)dp * dp;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->S, dd)) || (rc = dev_alloc(ctx, &ctx->Sinv, dd)) ||
+        (rc = dev_alloc(ctx, &ctx->b, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->m, (size_t)d)) ||
+        (rc = dev_alloc(ctx, &ctx->v, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->z, (size_t)d)))
+        return rc;
+    if (with_factor) {
+        if ((rc = dev_alloc(ctx, &ctx->R, dd)) || (rc = dev_alloc(ctx, &ctx->mp, (size_t)d)) ||
+            (rc = dev_alloc(ctx, &ctx->Rt_f32, dpp)) || (rc = dev_alloc(ctx, &ctx->mp_f32, (size_t)dp)) ||
+            (rc = dev_alloc(ctx, &ctx->Rh, dpp)) || (rc = dev_alloc(ctx, &ctx->Rl, dpp)) ||
+            (rc = dev_alloc(ctx, &ctx->psi, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->y, (size_t)d)) ||
+            (rc = dev_alloc(ctx, &ctx->phi_tmp, (size_t)d)))
+            return rc;
+    }
+    ctx->alpha = alpha; ctx->has_beta = false; ctx->beta = 0.0; ctx->d = d; ctx->dp = dp;
+    int blocks = (d + 255) / 256;
+    k_set_diag<<<blocks, 256>>>(ctx->S, d, 1.0 / alpha, 1.0 / alpha);                 // blr.py:33 pinv(alpha I)
+    SSPBO_LAUNCH_CHECK(ctx);
+    k_set_diag<<<blocks, 256>>>(ctx->Sinv, d, alpha, alpha);                           // blr.py:30
+    SSPBO_LAUNCH_CHECK(ctx);
+    if (with_factor) {
+        // R0 = sqrt(B^T B / alpha), B^T B = diag(1/d, 2/d, ..., 2/d)
+        k_set_diag<<<blocks, 256>>>(ctx->R, d, sqrt(1.0 / (d * alpha)), sqrt(2.0 / (d * alpha)));
+        SSPBO_LAUNCH_CHECK(ctx);
+        // (I - kappa y y^T) is a contraction, so |R_jk| <= ||R0||_2 for every later R: one fixed power-of-two scale
+        double rmax = sqrt(2.0 / (d * alpha));
+        ctx->r_scale = exp2(floor(log2(1024.0 / rmax)));
+    }
+    ctx->has_factor = with_factor;
+    ctx->blr_ready = true; ctx->operands_dirty = true;
+    SSPBO_CUDA(ctx, cudaDeviceSynchronize());
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_blr_init(sspbo_ctx* ctx, double alpha) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_init before space_set");
+    if (!(alpha > 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "alpha must be positive");
+    return blr_alloc(ctx, 2 * ctx->K + 1, alpha, true);
+}
+
+extern "C" int sspbo_blr_init_dim(sspbo_ctx* ctx, int d, double alpha) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K != 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_init_dim: this ctx has an SSP space; use blr_init");
+    if (d < 1 || d > 16384) SSPBO_FAIL(ctx, SSPBO_EINVAL, "blr_init_dim: d out of range");
+    if (!(alpha > 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "alpha must be positive");
+    return blr_alloc(ctx, d, alpha, false);
+}
+
+extern "C" int sspbo_blr_set_beta(sspbo_ctx* ctx, double beta) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!(beta > 0) || !isfinite(beta)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "beta must be positive and finite");
+    ctx->beta = beta; ctx->has_beta = true;
+    return SSPBO_OK;
+}
+extern "C" int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_set) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (beta) *beta = ctx->beta; if (is_set) *is_set = ctx->has_beta ? 1 : 0;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double* ts_host, int k, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_update before blr_init");
+    if (!ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_update before blr_set_beta");
+    if (k < 0 || (k > 0 && (!phis || !ts_host))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "blr_update: null pointer");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = ctx->d, K = ctx->K;
+    const double beta = ctx->beta;
+    dim3 g1((d + 255) / 256, d);
+    for (int i = 0; i < k; ++i) {
+        const double* phi = phis + (size_t)i * d;
+        // --- phi-space posterior, blr.py:60-70 ---
+        k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, phi, ctx->v, d);                       // v = S phi
+        SSPBO_LAUNCH_CHECK(ctx);
+        k_gemv_cols<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(ctx->S, phi, ctx->z, d);              // z = S^T phi
+        SSPBO_LAUNCH_CHECK(ctx);
+        // --- psi-space factor: psi = D^-1 B^T phi ; y = R psi ---
+        if (ctx->has_factor) {
+            k_analysis<<<K + 1, 128, 0, st>>>(phi, ctx->psi, ctx->twiddle, K, 1.0, 1.0);
+            SSPBO_LAUNCH_CHECK(ctx);
+            k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->R, ctx->psi, ctx->y, d);               // y = R psi
+            SSPBO_LAUNCH_CHECK(ctx);
+        }
+        k_update_scalars<<<1, 256, 0, st>>>(phi, ctx->v, ctx->has_factor ? ctx->y : ctx->v, d, beta, ctx->scal);
+        SSPBO_LAUNCH_CHECK(ctx);
+        k_rank1<<<g1, 256, 0, st>>>(ctx->S, ctx->v, ctx->z, d, ctx->scal + 0, 0.0);              // S -= coef v z^T
+        SSPBO_LAUNCH_CHECK(ctx);
+        k_rank1<<<g1, 256, 0, st>>>(ctx->Sinv, phi, phi, d, nullptr, beta);                      // S_inv += beta phi phi^T
+        SSPBO_LAUNCH_CHECK(ctx);
+        k_axpy<<<(d + 255) / 256, 256, 0, st>>>(ctx->b, phi, beta * ts_host[i], d);              // b += beta t phi
+        SSPBO_LAUNCH_CHECK(ctx);
+        if (ctx->has_factor) {
+            k_gemv_cols<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(ctx->R, ctx->y, ctx->phi_tmp, d); // R^T y
+            SSPBO_LAUNCH_CHECK(ctx);
+            k_rank1<<<g1, 256, 0, st>>>(ctx->R, ctx->y, ctx->phi_tmp, d, ctx->scal + 1, 0.0);    // R -= kappa y (R^T y)^T
+            SSPBO_LAUNCH_CHECK(ctx);
+        }
+    }
+    if (k > 0) {
+        k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, ctx->b, ctx->m, d);                     // m = S b  (blr.py:75)
+        SSPBO_LAUNCH_CHECK(ctx);
+        if (ctx->has_factor) {
+            k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d);   // m' = B^T m
+            SSPBO_LAUNCH_CHECK(ctx);
+        }
+        ctx->operands_dirty = true;
+    }
+    return SSPBO_OK;
+}
+
+int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
+    if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
+    if (!ctx->operands_dirty) return SSPBO_OK;
+    dim3 grid(ctx->dp / 32, ctx->dp / 32);
+    k_refresh_operands<<<grid, dim3(32, 8), 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->dp, ctx->r_scale, ctx->Rt_f32, ctx->Rh,
+                                                     ctx->Rl, ctx->mp_f32);
+    SSPBO_LAUNCH_CHECK(ctx);
+    ctx->operands_dirty = false;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_blr_get(sspbo_ctx* ctx, double* m, double* S, double* Sinv, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_get before blr_init");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = ctx->d;
+    if (m) SSPBO_CUDA(ctx, cudaMemcpyAsync(m, ctx->m, d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (S) SSPBO_CUDA(ctx, cudaMemcpyAsync(S, ctx->S, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (Sinv) SSPBO_CUDA(ctx, cudaMemcpyAsync(Sinv, ctx->Sinv, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return SSPBO_OK;
+}
+
+extern "C" int64_t sspbo_blr_export_size(const sspbo_ctx* ctx) {
+    if (!ctx || !ctx->blr_ready) return 0;
+    int64_t d = ctx->d;
+    return ctx->has_factor ? 3 * d * d + 3 * d : 2 * d * d + 2 * d;
+}
+extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready || !packed) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_export: not initialised / null");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = ctx->d, dd = d * d;
+    const double* src[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->R, ctx->mp};
+    const size_t cnt[6] = {dd, dd, d, d, dd, d};
+    size_t off = 0;
+    for (int i = 0; i < (ctx->has_factor ? 6 : 4); ++i) {
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(packed + off, src[i], cnt[i] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        off += cnt[i];
+    }
+    return SSPBO_OK;
+}
+extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double beta, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready || !packed) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_import: not initialised / null");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = ctx->d, dd = d * d;
+    double* dst[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->R, ctx->mp};
+    const size_t cnt[6] = {dd, dd, d, d, dd, d};
+    size_t off = 0;
+    for (int i = 0; i < (ctx->has_factor ? 6 : 4); ++i) {
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(dst[i], packed + off, cnt[i] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        off += cnt[i];
+    }
+    if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
+    ctx->operands_dirty = true;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, double* mu, double* var, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_predict before blr_init");
+    if (!ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_predict before beta is set (blr.py:96 divides by beta)");
+    if (N < 0 || (N > 0 && (!phi || !mu || !var))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "blr_predict: null pointer");
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t smem = (size_t)PRED_CPB * ctx->d * sizeof(double);
+    SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks64 = (N + PRED_CPB - 1) / PRED_CPB;
+    int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 4 ? blocks64 : (int64_t)ctx->sm_count * 4);
+    k_predict<<<blocks, 256, smem, (cudaStream_t)stream>>>(phi, N, ctx->S, ctx->m, ctx->d, 1.0 / ctx->beta, mu, var);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------ K2 dispatch
+extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, double lam, double gamma_t,
+                           float* mu, float* var, float* acq, unsigned long long* best, int engine, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready || !ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "score: BLR posterior (and beta) must be set first");
+    if (N < 0 || (N > 0 && !x)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: null candidates");
+    if (x_dtype != SSPBO_F32 && x_dtype != SSPBO_F64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown dtype %d", x_dtype);
+    if (index0 < 0 || index0 + N > 0xffffffffLL) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: candidate index must stay below 2^32");
+    if (!(gamma_t >= 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: gamma_t must be >= 0");
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = sspbo_refresh_operands(ctx, st);
+    if (rc) return rc;
+    bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
+    if (engine == SSPBO_ENGINE_UMMA && !umma_ok)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: tcgen05 engine does not cover d=%d L=%d", ctx->d, ctx->L);
+    bool use_umma = (engine == SSPBO_ENGINE_UMMA) || (engine == SSPBO_ENGINE_AUTO && umma_ok && N >= 1024);
+    if (use_umma) {
+        ctx->last_engine = SSPBO_ENGINE_UMMA;
+        return sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+    }
+    ctx->last_engine = SSPBO_ENGINE_SIMT;
+    return sspbo_score_simt_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+}
+
+extern "C" void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index) {
+    unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)(key & 0xffffffffu);
+    if (index) *index = (int64_t)(0xffffffffu - lo);
+    if (score) {
+        unsigned int u;
+        if (hi == 0xffffffffu) u = 0x7fc00000u;                      // NaN
+        else u = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
+        memcpy(score, &u, 4);
+    }
+}
+extern "C" unsigned long long sspbo_key_pack(float score, int64_t index) { return sspbo_pack(score, (unsigned long long)index); }
+
+// ------------------------------------------------------------------------------------ K4
+extern "C" int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* ssps, int64_t M, const double* queries, int q,
+                                     int64_t* idx_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (M < 1 || q < 1 || !ssps || !queries || !idx_out) SSPBO_FAIL(ctx, SSPBO_EINVAL, "from_set: empty set / null pointer");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = ctx->d;
+    if (d < 1) SSPBO_FAIL(ctx, SSPBO_ESTATE, "from_set before space_set");
+    double *unit = nullptr, *sims = nullptr;
+    SSPBO_CUDA(ctx, cudaMallocAsync((void**)&unit, (size_t)q * d * sizeof(double), st));
+    SSPBO_CUDA(ctx, cudaMallocAsync((void**)&sims, (size_t)q * M * sizeof(double), st));
+    k_unit_rows<<<q, 256, 0, st>>>(queries, unit, d);
+    SSPBO_LAUNCH_CHECK(ctx);
+    k_sims<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ssps, M, unit, q, d, sims);
+    SSPBO_LAUNCH_CHECK(ctx);
+    k_argmax_rows<<<q, 1024, 0, st>>>(sims, M, idx_out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    SSPBO_CUDA(ctx, cudaFreeAsync(unit, st));
+    SSPBO_CUDA(ctx, cudaFreeAsync(sims, st));
+    return SSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------ generators
+extern "C" int sspbo_fill_uniform(sspbo_ctx* ctx, uint64_t seed, int64_t start, int64_t count, int n, float* out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (count < 0 || n < 1 || start < 0 || (count > 0 && !out)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "fill_uniform: bad arguments");
+    if (count == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t total = count * n;
+    int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    k_fill_uniform<<<blocks, 256, 0, (cudaStream_t)stream>>>(seed, start * n, total, out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_grid_points(sspbo_ctx* ctx, const double* axes, const int* counts, int n, int64_t start, int64_t count,
+                                 double* out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (n < 1 || n > 16 || !axes || !counts || count < 0 || start < 0 || (count > 0 && !out))
+        SSPBO_FAIL(ctx, SSPBO_EINVAL, "grid_points: bad arguments");
+    if (count == 0) return SSPBO_OK;
+    GridDesc g; g.n = n;
+    int off = 0; double total = 1.0;
+    for (int a = 0; a < n; ++a) {
+        if (counts[a] < 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "grid_points: counts must be >= 1");
+        g.counts[a] = counts[a]; g.offs[a] = off; off += counts[a]; total *= counts[a];
+    }
+    if ((double)(start + count) > total) SSPBO_FAIL(ctx, SSPBO_EINVAL, "grid_points: range exceeds the grid");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    int blocks = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    k_grid_points<<<blocks, 256, 0, (cudaStream_t)stream>>>(axes, g, start, count, out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}

@@ -1,0 +1,110 @@
+// Internal definitions shared by the translation units of libsspbo.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/sspbo.h"
+
+struct sspbo_ctx {
+    int device = 0;
+    int sm_count = 148;
+    mutable char err[512] = {0};
+    int64_t launches = 0;
+    int last_engine = 0;
+
+    // ---- space ----
+    int K = 0, n = 0, d = 0, L = 1;
+    int dp = 0;                      // d padded to a multiple of 64 (operand leading dimension)
+    double* A_turns = nullptr;       // K x n : A+ * inv_ls / (2 pi)  -> theta in turns (float64)
+    float*  A_turns_f32 = nullptr;   // same, float32
+    double* tau_turns = nullptr;     // L x K : trajectory time phases in turns (nullptr when L == 1)
+    float*  tau_turns_f32 = nullptr;
+    double2* twiddle = nullptr;      // d entries (cos, sin)(2 pi i / d), float64
+    double max_turns = 0.0;          // host bound on |theta| in turns per unit |x|_inf (sum_a |A_turns[k][a]|, max over k)
+
+    // ---- BLR (phi-space, float64) ----
+    bool blr_ready = false, has_beta = false;
+    bool has_factor = false;         // psi-space factor maintained (needs a space: d = 2K+1)
+    double alpha = 0.01, beta = 0.0;
+    double *S = nullptr, *Sinv = nullptr, *b = nullptr, *m = nullptr;
+    // ---- scoring state (psi-space) ----
+    double* R = nullptr;             // d x d float64 row-major, R^T R = B^T S B
+    double* mp = nullptr;            // m' = B^T m (d)
+    float*  Rt_f32 = nullptr;        // dp x dp float32, Rt[k*dp + j] = R[j][k]      (SIMT scorer)
+    float*  mp_f32 = nullptr;        // dp
+    __half* Rh = nullptr;            // dp x dp fp16 K-major: Rh[j*dp + k] = hi(R[j][k] * r_scale) (tcgen05 scorer)
+    __half* Rl = nullptr;            //                       lo part
+    double r_scale = 1.0;
+    bool operands_dirty = true;      // Rt_f32 / Rh / Rl / mp_f32 need a refresh from R, m
+    // scratch d-vectors (float64)
+    double *v = nullptr, *psi = nullptr, *y = nullptr, *z = nullptr, *phi_tmp = nullptr;
+    double* scal = nullptr;          // a few device scalars
+    // opaque state of the tcgen05 engine (tensor maps etc.)
+    void* umma = nullptr;
+};
+
+#define SSPBO_FAIL(ctx, code, ...)                                         \
+    do {                                                                   \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);             \
+        return (code);                                                     \
+    } while (0)
+
+#define SSPBO_CUDA(ctx, expr)                                                              \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, \
+                     #expr, cudaGetErrorString(e__));                                      \
+            return SSPBO_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define SSPBO_LAUNCH_CHECK(ctx)                      \
+    do {                                             \
+        (ctx)->launches++;                           \
+        SSPBO_CUDA(ctx, cudaGetLastError());         \
+    } while (0)
+
+static inline int sspbo_pad64(int x) { return (x + 63) / 64 * 64; }
+
+// ---- packed (score, index) key: max(key) == max score, lowest index on ties; NaN ranks highest ----
+__host__ __device__ inline unsigned int sspbo_orderable(float f) {
+#ifdef __CUDA_ARCH__
+    unsigned int u = __float_as_uint(f);
+#else
+    unsigned int u; memcpy(&u, &f, 4);
+#endif
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;      // NaN counts as the maximum (np.argmax)
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline unsigned long long sspbo_pack(float score, unsigned long long idx) {
+    return ((unsigned long long)sspbo_orderable(score) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)idx);
+}
+
+// engines implemented in other translation units
+int sspbo_score_simt_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
+                            float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
+int sspbo_score_umma_supported(const sspbo_ctx* ctx);
+int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
+                            float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
+void sspbo_umma_release(sspbo_ctx* ctx);
+int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st);
+
+// ---- device helpers shared by the scorers: theta (in turns) of frequency k for candidate row x ----
+// fast path: float32 FMA chain (valid when the host bound max_turns*|x| keeps the error below 2^-20 turns)
+// precise path: float64
+template <typename XT>
+__device__ __forceinline__ float sspbo_theta_turns(const XT* __restrict__ x, const float* __restrict__ Af,
+                                                   const double* __restrict__ Ad, int n, bool precise) {
+    if (!precise) {
+        float t = 0.f;
+        for (int a = 0; a < n; ++a) t = fmaf(Af[a], (float)x[a], t);
+        return t - rintf(t);
+    } else {
+        double t = 0.0;
+        for (int a = 0; a < n; ++a) t = fma(Ad[a], (double)x[a], t);
+        return (float)(t - rint(t));
+    }
+}

@@ -1,0 +1,258 @@
+"""One device context of the SSP-BO hot path (a `sspbo_ctx` of libsspbo.so).
+
+PyTorch is used for plumbing only: device buffers, the current CUDA stream and
+(in `dist.py`) the NCCL process group.  All arithmetic is in the hand-written
+kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.SspboError("ssp_bayesopt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    return int(torch.device("cuda", device).index if not isinstance(device, int) else device)
+
+
+class DeviceEngine:
+    """Owns a device context: SSP space tables, the float64 BLR posterior and its scoring factor."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        self.device = require_cuda(device)
+        self.torch = _torch()
+        self._ctx = C.c_void_p()
+        rc = self.lib.sspbo_ctx_create(self.device, C.byref(self._ctx))
+        if rc != 0:
+            raise _lib.SspboError(f"sspbo_ctx_create({self.device}) failed ({rc})")
+        self.d = 0
+        self.K = 0
+        self.n = 0
+        self.L = 1
+        self._best = self.torch.zeros(1, dtype=self.torch.int64, device=self._dev())
+
+    # ------------------------------------------------------------------ plumbing
+    def _dev(self):
+        return self.torch.device("cuda", self.device)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        _lib.check(self.lib, self._ctx, rc, what)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.sspbo_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to_device(self, a, dtype=None):
+        """numpy / torch -> contiguous device tensor (float32 or float64 kept, everything else -> float64)."""
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            t = a
+            if dtype is not None:
+                t = t.to(dtype)
+            elif t.dtype not in (torch.float32, torch.float64):
+                t = t.to(torch.float64)
+            return t.to(self._dev()).contiguous()
+        a = np.asarray(a)
+        if dtype is None:
+            a = a if a.dtype in (np.float32, np.float64) else a.astype(np.float64)
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self._dev())
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self._dev(), dtype)
+
+    @staticmethod
+    def _dtype_code(t):
+        import torch
+        return _lib.F32 if t.dtype == torch.float32 else _lib.F64
+
+    # ------------------------------------------------------------------ space
+    def set_space(self, phase_matrix: np.ndarray, length_scale) -> None:
+        """phase_matrix (d, n) as built by the reference constructors; rows 1..K are A+."""
+        A = np.asarray(phase_matrix, dtype=np.float64)
+        d, n = A.shape
+        if d % 2 != 1 or d < 3:
+            raise ValueError(f"phase matrix must have 2K+1 rows (conjugate symmetric), got {d}")
+        K = (d - 1) // 2
+        a_plus = np.ascontiguousarray(A[1:K + 1])
+        inv_ls = np.ascontiguousarray(1.0 / np.asarray(length_scale, dtype=np.float64).reshape(-1) * np.ones(n))
+        rc = self.lib.sspbo_space_set(self._ctx, a_plus.ctypes.data_as(_lib._pd), inv_ls.ctypes.data_as(_lib._pd), K, n)
+        self._check(rc, "sspbo_space_set")
+        self.d, self.K, self.n, self.L = d, K, n, 1
+
+    def set_traj(self, tau: np.ndarray | None, L: int) -> None:
+        """tau (L, K): phase in radians of timestep j at frequency k."""
+        if tau is None:
+            rc = self.lib.sspbo_space_set_traj(self._ctx, None, 1)
+            L = 1
+        else:
+            tau = np.ascontiguousarray(tau, dtype=np.float64)
+            assert tau.shape == (L, self.K), f"tau must be ({L}, {self.K}), got {tau.shape}"
+            rc = self.lib.sspbo_space_set_traj(self._ctx, tau.ctypes.data_as(_lib._pd), L)
+        self._check(rc, "sspbo_space_set_traj")
+        self.L = L
+
+    # ------------------------------------------------------------------ K1
+    def encode_device(self, x):
+        """x (N, n*L) -> device tensor phi (N, d) float64."""
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        if xt.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        phi = self.torch.empty((N, self.d), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_encode(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N,
+                                   C.c_void_p(phi.data_ptr()), self._stream())
+        self._check(rc, "sspbo_encode")
+        return phi
+
+    def encode(self, x) -> np.ndarray:
+        return self.encode_device(x).cpu().numpy()
+
+    # ------------------------------------------------------------------ K3
+    def blr_init(self, alpha: float, dim: int | None = None) -> None:
+        if self.K:
+            rc = self.lib.sspbo_blr_init(self._ctx, float(alpha))
+        else:
+            rc = self.lib.sspbo_blr_init_dim(self._ctx, int(dim), float(alpha))
+            self.d = int(dim)
+        self._check(rc, "sspbo_blr_init")
+
+    def blr_set_beta(self, beta: float) -> None:
+        self._check(self.lib.sspbo_blr_set_beta(self._ctx, float(beta)), "sspbo_blr_set_beta")
+
+    def blr_beta(self):
+        b, s = C.c_double(), C.c_int()
+        self._check(self.lib.sspbo_blr_get_beta(self._ctx, C.byref(b), C.byref(s)), "sspbo_blr_get_beta")
+        return b.value if s.value else None
+
+    def blr_update(self, phis, ts) -> None:
+        pt = self.to_device(phis, self.torch.float64)
+        ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
+        assert pt.shape[0] == ts.shape[0]
+        rc = self.lib.sspbo_blr_update(self._ctx, C.c_void_p(pt.data_ptr()), ts.ctypes.data_as(_lib._pd), pt.shape[0],
+                                       self._stream())
+        self._check(rc, "sspbo_blr_update")
+
+    def blr_get(self, m=True, S=True, Sinv=False):
+        torch = self.torch
+        d = self.d
+        mt = torch.empty(d, dtype=torch.float64, device=self._dev()) if m else None
+        St = torch.empty((d, d), dtype=torch.float64, device=self._dev()) if S else None
+        Si = torch.empty((d, d), dtype=torch.float64, device=self._dev()) if Sinv else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self.lib.sspbo_blr_get(self._ctx, ptr(mt), ptr(St), ptr(Si), self._stream()), "sspbo_blr_get")
+        return mt, St, Si
+
+    def blr_export(self):
+        n = self.lib.sspbo_blr_export_size(self._ctx)
+        buf = self.torch.empty(n, dtype=self.torch.float64, device=self._dev())
+        self._check(self.lib.sspbo_blr_export(self._ctx, C.c_void_p(buf.data_ptr()), self._stream()), "sspbo_blr_export")
+        return buf
+
+    def blr_import(self, buf, beta) -> None:
+        assert buf.numel() == self.lib.sspbo_blr_export_size(self._ctx)
+        rc = self.lib.sspbo_blr_import(self._ctx, C.c_void_p(buf.data_ptr()), float(beta or 0.0), self._stream())
+        self._check(rc, "sspbo_blr_import")
+
+    def blr_predict(self, phi):
+        pt = self.to_device(phi, self.torch.float64)
+        N = pt.shape[0]
+        mu = self.torch.empty(N, dtype=self.torch.float64, device=self._dev())
+        var = self.torch.empty(N, dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_blr_predict(self._ctx, C.c_void_p(pt.data_ptr()), N, C.c_void_p(mu.data_ptr()),
+                                        C.c_void_p(var.data_ptr()), self._stream())
+        self._check(rc, "sspbo_blr_predict")
+        return mu, var
+
+    # ------------------------------------------------------------------ K2
+    def score(self, x, lam, gamma_t, index0=0, want_outputs=False, engine=_lib.ENGINE_AUTO, reset_best=True):
+        """Fused encode + acquisition + argmax over candidates x (N, n*L), host or device.
+        Returns (best_key_tensor, (mu, var, acq) | None); all device tensors, nothing is synchronised."""
+        torch = self.torch
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        if xt.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        outs = None
+        ptrs = [None, None, None]
+        if want_outputs:
+            outs = tuple(torch.empty(N, dtype=torch.float32, device=self._dev()) for _ in range(3))
+            ptrs = [C.c_void_p(t.data_ptr()) for t in outs]
+        if reset_best:
+            self._best.zero_()
+        rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, int(index0),
+                                  float(lam), float(gamma_t), ptrs[0], ptrs[1], ptrs[2],
+                                  C.c_void_p(self._best.data_ptr()), int(engine), self._stream())
+        self._check(rc, "sspbo_score")
+        return self._best, outs
+
+    def best(self):
+        """(score, index) of the packed key; synchronises."""
+        return _lib.key_unpack(int(self._best.item()))
+
+    def last_engine(self) -> str:
+        return _lib.ENGINE_NAMES.get(self.lib.sspbo_last_engine(self._ctx), "?")
+
+    def launch_count(self) -> int:
+        return int(self.lib.sspbo_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ K4
+    def from_set_argmax(self, sample_ssps, queries):
+        st = self.to_device(sample_ssps, self.torch.float64)
+        qt = self.to_device(queries, self.torch.float64)
+        if qt.dim() == 1:
+            qt = qt.reshape(1, -1)
+        assert st.shape[1] == qt.shape[1], f"Expected {tuple(st.shape)} dim, got {tuple(qt.shape)}"
+        if self.d == 0:
+            raise _lib.SspboError("from_set_argmax before set_space")
+        assert st.shape[1] == self.d
+        idx = self.torch.empty(qt.shape[0], dtype=self.torch.int64, device=self._dev())
+        rc = self.lib.sspbo_from_set_argmax(self._ctx, C.c_void_p(st.data_ptr()), st.shape[0], C.c_void_p(qt.data_ptr()),
+                                            qt.shape[0], C.c_void_p(idx.data_ptr()), self._stream())
+        self._check(rc, "sspbo_from_set_argmax")
+        return idx
+
+    # ------------------------------------------------------------------ generators
+    def fill_uniform(self, seed: int, start: int, count: int, n: int | None = None):
+        n = n or self.n * self.L
+        out = self.torch.empty((count, n), dtype=self.torch.float32, device=self._dev())
+        rc = self.lib.sspbo_fill_uniform(self._ctx, int(seed), int(start), int(count), int(n), C.c_void_p(out.data_ptr()),
+                                         self._stream())
+        self._check(rc, "sspbo_fill_uniform")
+        return out
+
+    def grid_points(self, axes, start=0, count=None):
+        """axes: list of per-axis numpy linspaces.  Rows [start, start+count) in the reference's meshgrid order."""
+        counts = np.array([len(a) for a in axes], dtype=np.int32)
+        total = int(np.prod(counts.astype(np.int64)))
+        count = total - start if count is None else count
+        flat = self.to_device(np.concatenate([np.asarray(a, dtype=np.float64) for a in axes]), self.torch.float64)
+        out = self.torch.empty((count, len(axes)), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_grid_points(self._ctx, C.c_void_p(flat.data_ptr()), counts.ctypes.data_as(_lib._pi), len(axes),
+                                        int(start), int(count), C.c_void_p(out.data_ptr()), self._stream())
+        self._check(rc, "sspbo_grid_points")
+        return out

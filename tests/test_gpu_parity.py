@@ -1,0 +1,376 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the package's reference-shaped API) against the
+numpy oracle and the committed golden fixtures of the live reference.
+
+Tolerances (BASELINE.json north_star): phi and acquisition scores within 1e-4 relative (phi: normwise per
+row); argmax identical wherever the oracle's top-2 relative gap exceeds 1e-4; posterior m, S within 1e-6
+relative (normwise) after 1,000 updates.  Index / integer results (grid order, from-set decode indices,
+the counter-based generator) are bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import ssp_oracle as orc
+from tests.conftest import himmelblau
+
+pytestmark = pytest.mark.gpu
+
+B2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+RTOL_SCORE = 1e-4
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ssp_bayesopt_b200 as p
+    return p
+
+
+def space_from(pkg, A, ls, bounds=None):
+    return pkg.SSPSpace(A.shape[1], A.shape[0], phase_matrix=A, domain_bounds=bounds, length_scale=np.asarray(ls))
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------ K1 encode
+@pytest.mark.parametrize("name,xk", [("hex51", "x2"), ("rand51", "x2"), ("hex151", "x2"), ("rand512", "x2"),
+                                     ("hexsmall", "x15"), ("rand1024", "x6")])
+def test_encode_golden(pkg, golden, name, xk):
+    g = golden("encode.npz")
+    sp = space_from(pkg, g[f"{name}_A"], g[f"{name}_ls"])
+    phi = sp.encode(g[xk])
+    assert phi.dtype == np.float64 and phi.shape == g[f"{name}_phi"].shape
+    np.testing.assert_allclose(phi, g[f"{name}_phi"], rtol=0, atol=2e-13)
+    np.testing.assert_allclose(np.linalg.norm(phi, axis=1), 1.0, atol=1e-12)      # tests/test_ssps.py:31-37
+
+
+def test_encode_edge_cases(pkg, golden):
+    g = golden("encode.npz")
+    sp = space_from(pkg, g["rand51_A"], g["rand51_ls"])
+    assert sp.encode(np.zeros((0, 2))).shape == (0, 51)                            # empty input
+    one = sp.encode(np.array([1.3, -3.4]))                                          # 1-D input -> (1, d)
+    assert one.shape == (1, 51)
+    np.testing.assert_allclose(one, orc.encode(g["rand51_A"], g["rand51_ls"], [[1.3, -3.4]]), atol=2e-13)
+    np.testing.assert_allclose(sp.encode(np.zeros((3, 2)))[:, 0], 1.0, atol=1e-15)  # phi(0) = identity
+    x32 = g["x2"].astype(np.float32)                                                # float32 candidates accepted
+    np.testing.assert_allclose(sp.encode(x32), orc.encode(g["rand51_A"], g["rand51_ls"], x32.astype(np.float64)),
+                               atol=2e-13)
+    with pytest.raises(AssertionError):
+        sp.encode(np.zeros((2, 3)))
+    # ragged batch sizes around the kernel's candidates-per-block
+    for n in (1, 3, 4, 5, 1023):
+        x = np.random.default_rng(n).uniform(-5, 5, (n, 2))
+        np.testing.assert_allclose(sp.encode(x), orc.encode(g["rand51_A"], g["rand51_ls"], x), atol=2e-13)
+
+
+def test_encode_large_random(pkg, golden):
+    g = golden("encode.npz")
+    A, ls = g["rand1024_A"], g["rand1024_ls"]
+    sp = space_from(pkg, A, ls)
+    x = orc.counter_uniform(3, 0, 4096, 6).astype(np.float64)
+    phi, ref = sp.encode(x), orc.encode(A, ls, x)
+    err = np.max(np.abs(phi - ref), axis=1) / np.max(np.abs(ref), axis=1)
+    assert err.max() < 1e-4 and err.max() < 1e-10, err.max()
+
+
+# ------------------------------------------------------------------------------------------ K3 BLR
+@pytest.mark.parametrize("name", ["hex51", "rand51"])
+def test_blr_golden(pkg, golden, name):
+    g, e = golden("blr.npz"), golden("encode.npz")
+    sp = space_from(pkg, e[f"{name}_A"], e[f"{name}_ls"])
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    model.update(sp.encode(g["xs"]), g["ys"])
+    assert model.beta == g[f"{name}_beta"]
+    assert model.m.shape == (sp.ssp_dim, 1) and model.S.shape == (sp.ssp_dim, sp.ssp_dim)
+    assert rel(model.m, g[f"{name}_m0"]) < 1e-11 and rel(model.S, g[f"{name}_S0"]) < 1e-11
+    for i in range(40):
+        model.update(sp.encode(g[f"{name}_xt"][i:i + 1]), g[f"{name}_yt"][i:i + 1])
+    assert rel(model.m, g[f"{name}_m40"]) < 1e-9 and rel(model.S, g[f"{name}_S40"]) < 1e-9
+    mu, var = model.predict(sp.encode(g[f"{name}_xc"]))
+    assert mu.shape == (1, 64) and var.shape == (64,)                               # tests/test_blr.py:28-39
+    np.testing.assert_allclose(mu, g[f"{name}_mu"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(var, g[f"{name}_var"], rtol=1e-8)
+    assert np.all(var > 0)                                                          # tests/test_blr.py:42-52
+    Sinv = model.S_inv
+    np.testing.assert_allclose(Sinv @ model.S, np.eye(sp.ssp_dim), atol=1e-7)
+
+
+def test_blr_single_target_beta_rule(pkg, golden):
+    g, e = golden("blr.npz"), golden("encode.npz")
+    sp = space_from(pkg, e["hex51_A"], e["hex51_ls"])
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    model.update(sp.encode(g["xs"][:1]), g["ys"][:1])
+    assert np.ravel(model.beta)[0] == g["single_beta"]                              # 1/|t| (blr.py:57-58)
+    assert rel(model.S, g["single_S"]) < 1e-11 and rel(model.m, g["single_m"]) < 1e-11
+
+
+def test_blr_1000_updates(pkg, golden):
+    """north star: posterior m and S within 1e-6 relative after 1,000 updates."""
+    g = golden("blr1000.npz")
+    sp = space_from(pkg, g["A"], np.ones(2))
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    phis = sp.encode(g["xt"])
+    model.update(phis[:10], g["yt"][:10])
+    for i in range(10, 1000):
+        model.update(phis[i:i + 1], g["yt"][i:i + 1])
+    assert model.beta == g["beta"]
+    assert rel(model.S, g["S"]) < 1e-6 and rel(model.m, g["m"]) < 1e-6, (rel(model.S, g["S"]), rel(model.m, g["m"]))
+
+
+def test_blr_raw_features_sequential_equals_batch(pkg):
+    """The reference's own invariant (tests/test_blr.py:72-92) on a BLR without an SSP space (even dim)."""
+    rng = np.random.default_rng(4)
+    xs, ys = rng.normal(size=(6, 10)), rng.normal(size=(6, 1))
+    a = pkg.BayesianLinearRegression(10, beta=1.0)
+    b = pkg.BayesianLinearRegression(10, beta=1.0)
+    a.update(xs, ys)
+    for i in range(6):
+        b.update(xs[i:i + 1], ys[i:i + 1])
+    assert np.allclose(a.m, b.m, atol=1e-6) and np.allclose(a.S, b.S, atol=1e-6)
+    ref = orc.BLR(10, beta=1.0)
+    ref.update(xs, ys)
+    assert rel(a.m, ref.m) < 1e-10 and rel(a.S, ref.S) < 1e-10
+    mu, var = a.predict(xs)
+    rmu, rvar = ref.predict(xs)
+    np.testing.assert_allclose(mu, rmu, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(var, rvar, rtol=1e-9)
+    with pytest.raises(AssertionError):
+        a.update(np.zeros((2, 9)), np.zeros((2, 1)))
+    with pytest.raises(AssertionError):
+        a.update(np.zeros((2, 10)), np.zeros(2))
+
+
+# ------------------------------------------------------------------------------------------ K2 fused scorer
+def _replay_agent(pkg, golden, tag, gamma_c):
+    g, b = golden("agent.npz"), golden("blr.npz")
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=B2, length_scale=1.0, rng=0)
+    agt = pkg.SSPAgent(b["xs"], b["ys"], sp, decoder_method="from-set", gamma_c=gamma_c, beta_ucb=10.0,
+                       var_decay=0.25, length_scale=1.0)
+    for i in range(6):
+        x_t = g["xt"][i:i + 1]
+        _, var_t, _ = agt.eval(x_t)
+        agt.update(x_t, np.atleast_2d(himmelblau(x_t)), var_t, step_num=i)
+    return agt, g
+
+
+@pytest.mark.parametrize("tag,gamma_c", [("mi", 1.0), ("ucb", 0.0)])
+def test_agent_eval_golden(pkg, golden, tag, gamma_c):
+    agt, g = _replay_agent(pkg, golden, tag, gamma_c)
+    assert rel(agt.blr.m, g[f"{tag}_m"]) < 1e-7
+    np.testing.assert_allclose(np.ravel(agt.gamma_t)[0], g[f"{tag}_gamma_t"], rtol=1e-5)
+    assert agt.var_weight == g[f"{tag}_var_weight"]
+    mu, var, acq = agt.eval(g["xc"])
+    assert mu.shape == (1, 256) and var.shape == (256,) and acq.shape == (256,)
+    score, ref = mu.ravel() + acq, g[f"{tag}_mu"].ravel() + g[f"{tag}_acq"]
+    np.testing.assert_allclose(score, ref, rtol=RTOL_SCORE)
+    np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=RTOL_SCORE)
+    np.testing.assert_allclose(acq, g[f"{tag}_acq"], rtol=RTOL_SCORE)
+    key = agt.best_candidate(g["xc"])
+    s, idx = agt._scoring_engine().best()
+    assert idx == int(np.argmax(ref)) and abs(s - ref.max()) <= RTOL_SCORE * abs(ref.max())
+    assert np.array_equal(agt.init_samples[1], g[f"{tag}_init_pts"])
+    assert np.array_equal(agt.decode(agt.encode(g["xc"][:3])), g[f"{tag}_decoded"])
+
+
+def _c3_setup(pkg, T, seed=1):
+    """BASELINE config C3 space (Random n=6, ssp_dim=1024 -> d=1023, l=0.25) with T Hartmann-6 observations."""
+    b6 = np.array([[0.0, 1.0]] * 6)
+    sp = pkg.RandomSSPSpace(6, ssp_dim=1024, domain_bounds=b6, length_scale=0.25, rng=0)
+    X = np.random.default_rng(seed).uniform(0, 1, (T, 6))
+    y = orc.hartmann6(X).reshape(-1, 1)
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    phis = sp.encode(X)
+    model.update(phis[:10], y[:10])
+    ref = orc.BLR(sp.ssp_dim)
+    ref.update(orc.encode(sp.phase_matrix, 0.25 * np.ones(6), X[:10]), y[:10])
+    beta = ref.beta
+    S, bvec = ref.S.copy(), beta * (phis[:10].T @ y[:10])
+    for i in range(10, T):                         # O(d^2) float64 restatement of blr.py:63-75 (survey section 7)
+        model.update(phis[i:i + 1], y[i:i + 1])
+        phi = phis[i]
+        v = S @ phi
+        S = S - np.outer(v, v) * (beta / (1 + beta * (phi @ v)))
+        bvec = bvec + beta * phi[:, None] * y[i]
+    ref.S, ref.m = S, S @ bvec
+    return sp, model, ref, X
+
+
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_score_c3_parity(pkg, engine):
+    from ssp_bayesopt_b200 import _lib
+    sp, model, ref, X = _c3_setup(pkg, 60)
+    assert rel(model.S, ref.S) < 1e-9 and rel(model.m, ref.m) < 1e-7
+    N = 8192
+    xc = orc.counter_uniform(0, 0, N, 6)
+    xc[:32] = (X[:32] + 1e-3 * np.random.default_rng(2).normal(size=(32, 6))).astype(np.float32)  # low-variance rows
+    lam, gam = 10.0, 0.0
+    phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
+    ref_score, ref_idx = orc.score_and_argmax(phis, ref, lam, gam)
+    eng = sp.engine
+    code = {"simt": _lib.ENGINE_SIMT, "auto": _lib.ENGINE_AUTO}[engine]
+    _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=code)
+    score = (mu + acq).double().cpu().numpy()
+    err = np.abs(score - ref_score) / np.abs(ref_score)
+    assert err.max() < RTOL_SCORE, err.max()
+    srt = np.sort(ref_score)[::-1]
+    gap = (srt[0] - srt[1]) / abs(srt[0])
+    s, idx = eng.best()
+    if gap > RTOL_SCORE:
+        assert idx == ref_idx, (idx, ref_idx, gap)
+    assert abs(s - ref_score.max()) <= RTOL_SCORE * abs(ref_score.max())
+    # index0 offsets the packed index; shards combine by max
+    eng.score(xc[:4096], lam, gam, index0=1000)
+    k1 = int(eng._best.item())
+    eng.score(xc[4096:], lam, gam, index0=1000 + 4096, reset_best=False)
+    s2, idx2 = eng.best()
+    assert idx2 == idx + 1000 and s2 == s
+    assert (int(eng._best.item()) & 0xFFFFFFFFFFFFFFFF) >= (k1 & 0xFFFFFFFFFFFFFFFF)
+
+
+def test_score_edge_cases(pkg, golden):
+    agt, g = _replay_agent(pkg, golden, "ucb", 0.0)
+    eng = agt._scoring_engine()
+    # ragged sizes around the 16-candidate tile, and the tie-break: duplicated rows -> lowest index
+    x = np.repeat(g["xc"][:1], 37, axis=0)
+    eng.score(x, 10.0, 0.0)
+    assert eng.best()[1] == 0
+    for n in (1, 15, 16, 17, 255):
+        mu, var, acq = agt.eval(g["xc"][:n])
+        assert mu.shape == (1, n)
+        np.testing.assert_allclose(mu.ravel() + acq, (g["ucb_mu"].ravel() + g["ucb_acq"])[:n], rtol=RTOL_SCORE)
+    key, outs = eng.score(np.zeros((0, 2)), 10.0, 0.0, want_outputs=True)          # empty candidate set
+    assert int(key.item()) == 0 and outs[0].numel() == 0
+    with pytest.raises(Exception):
+        eng.score(g["xc"], 10.0, -1.0)                                             # gamma_t < 0
+
+
+# ------------------------------------------------------------------------------------------ K4 + grids
+def test_grid_points_and_from_set_decode(pkg, golden):
+    g = golden("decode.npz")
+    sp = space_from(pkg, g["A"], np.ones(2), g["bounds"])
+    ssps, pts = sp.get_sample_pts_and_ssps(20, "grid")
+    assert np.array_equal(pts, g["pts"])                                           # bit-exact, meshgrid('xy') order
+    np.testing.assert_allclose(ssps, g["ssps"], atol=2e-13)
+    assert np.array_equal(sp.decode(g["queries"], method="from-set", samples=(ssps, pts)), g["decoded"])
+    assert np.array_equal(sp.decode(g["queries"], method="from-set", samples=(g["ssps"], g["pts"])), g["decoded"])
+    sp3 = pkg.RandomSSPSpace(3, ssp_dim=31, domain_bounds=g["bounds3"], length_scale=1.0, rng=1)
+    assert np.array_equal(sp3.get_sample_points(4, "grid"), g["pts3"])             # n >= 3 axis order
+    # shard of a grid == slice of the full grid
+    axes = sp.grid_axes(20, "grid")
+    part = sp.engine.grid_points(axes, 137, 100).cpu().numpy()
+    assert np.array_equal(part, g["pts"][137:237])
+    # ties -> first index; zero query (norm floor 1e-6, sspspace.py:352) -> index 0
+    dup = np.vstack([g["ssps"][5:6]] * 4 + [g["ssps"][:3]])
+    idx = sp.engine.from_set_argmax(dup, g["ssps"][5:6]).cpu().numpy()
+    assert idx[0] == 0
+    assert sp.engine.from_set_argmax(g["ssps"], np.zeros((1, sp.ssp_dim))).cpu().numpy()[0] == 0
+    with pytest.raises(NotImplementedError):
+        sp.decode(g["queries"], method="nope")
+
+
+def test_decode_round_trip_reference_tests(pkg):
+    """tests/test_ssps.py:39-54, :75-80, :92-98 re-run against the GPU path."""
+    b15 = 15 * np.array([[-1.0, 1.0], [-1.0, 1.0]])
+    s = 2 * np.pi / np.sqrt(6)
+    x = np.atleast_2d(np.array([1.3, -3.4]))
+    hexs = pkg.HexagonalSSPSpace(2, ssp_dim=151, scale_min=s - 0.5, scale_max=s + 0.5, domain_bounds=b15, length_scale=1)
+    assert np.isclose(np.inner(hexs.encode(x), hexs.encode(x)), 1)
+    assert np.all(np.isclose(x, hexs.decode(hexs.encode(x), method="from-set", num_samples=300), atol=1e-1))
+    rnd = pkg.RandomSSPSpace(2, ssp_dim=151, domain_bounds=b15, length_scale=1, rng=0)
+    assert np.all(np.isclose(x, rnd.decode(rnd.encode(x), method="from-set", num_samples=300), atol=1e-1))
+    small = pkg.HexagonalSSPSpace(2, ssp_dim=151, scale_min=s - 0.5, scale_max=s + 0.5, domain_bounds=b15,
+                                  length_scale=0.05)
+    assert np.all(np.isclose(x, small.decode(small.encode(x), method="from-set", num_samples=500), atol=1e-2))
+    assert np.all(np.isclose(x, hexs.decode(hexs.encode(x), method="direct-optim"), atol=1e-4))
+
+
+# ------------------------------------------------------------------------------------------ trajectory agent
+def test_trajectory_agent_golden(pkg, golden):
+    g = golden("traj.npz")
+    agt = pkg.SSPTrajectoryAgent(g["trajs"], g["tys"], x_dim=2, traj_len=4, ssp_dim=51, domain_bounds=g["bounds"],
+                                 length_scale=0.7, time_length_scale=1.3, decoder_method="from-set", gamma_c=0.0,
+                                 beta_ucb=5.0)
+    assert np.array_equal(agt.ssp_x_space.phase_matrix, g["Ax"]) and np.array_equal(agt.ssp_t_space.phase_matrix, g["At"])
+    np.testing.assert_allclose(agt.timestep_ssps, g["timestep_ssps"], atol=2e-13)
+    phi = agt.encode(g["xc"])
+    np.testing.assert_allclose(phi, g["phi"], atol=5e-13)
+    assert agt.blr.beta == g["beta"]
+    assert rel(agt.blr.m, g["m"]) < 1e-9 and rel(agt.blr.S, g["S"]) < 1e-9
+    mu, var, acq = agt.eval(g["xc"])
+    np.testing.assert_allclose(mu.ravel() + acq, g["mu"].ravel() + g["acq"], rtol=RTOL_SCORE)
+    np.testing.assert_allclose(var, g["var"], rtol=RTOL_SCORE)
+    assert np.array_equal(agt.decode(phi[:1]), g["decoded"])
+
+
+# ------------------------------------------------------------------------------------------ generators, driver
+def test_fill_uniform_bit_exact(pkg):
+    eng = pkg.DeviceEngine()
+    for seed, start, count, n in ((0, 0, 1000, 6), (7, 123456789, 257, 2), (1, 2 ** 33, 64, 20)):
+        got = eng.fill_uniform(seed, start, count, n).cpu().numpy()
+        assert np.array_equal(got, orc.counter_uniform(seed, start, count, n))
+
+
+def test_maximize_api(pkg):
+    """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
+    bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    f = lambda x: -(x[:, 0] ** 2 + x[:, 1] ** 2)
+    xs0 = np.random.default_rng(0).uniform(-2, 2, (5, 2))
+    for n_iter in (0, 1, 6):
+        opt = pkg.BayesianOptimization(f=f, bounds=bounds)
+        opt.maximize(init_points=(xs0, f(xs0).reshape(-1, 1)), n_iter=n_iter, agent_type="ssp-hex", ssp_dim=151,
+                     length_scale=0.5, decoder_method="from-set", beta_ucb=10.0, gamma_c=0.0)
+        assert opt.xs.shape == (5 + n_iter, 2) and opt.ys.shape == (5 + n_iter,)
+        assert set(opt.max) == {"target", "params"} and len(opt.res) == 5 + n_iter
+        assert opt.times.shape == (n_iter,)
+    # the chosen points are the oracle's argmax over the same 100 x 100 grid, step by step
+    pts = orc.grid_sample_points(bounds, 100)
+    A = opt.agt.ssp_space.phase_matrix
+    ref = orc.BLR(A.shape[0])
+    phis0 = orc.encode(A, 0.5 * np.ones(2), xs0)
+    ref.update(phis0, f(xs0).reshape(-1, 1))
+    grid_phis = orc.encode(A, 0.5 * np.ones(2), pts)
+    for t in range(6):
+        score, idx = orc.score_and_argmax(grid_phis, ref, 10.0, 0.0)
+        srt = np.sort(score)[::-1]
+        if (srt[0] - srt[1]) / abs(srt[0]) > RTOL_SCORE:
+            assert opt.acq_indices[t] == idx
+            assert np.array_equal(opt.xs[5 + t], pts[idx])
+        x_t = opt.xs[5 + t:6 + t]
+        ref.update(orc.encode(A, 0.5 * np.ones(2), x_t), np.atleast_2d(f(x_t)))
+    two_arg = lambda x, info: float(-(x ** 2).sum())
+    opt = pkg.BayesianOptimization(f=two_arg, bounds=bounds)
+    opt.maximize(init_points=3, n_iter=1, agent_type="ssp-rand", ssp_dim=51, length_scale=0.5, rng=0,
+                 acq_candidates="uniform", n_candidates=5000)
+    assert opt.xs.shape == (4, 2) and np.all(np.abs(opt.xs) <= 2)
+
+
+def test_full_size_grid_properties(pkg):
+    """BASELINE config C2 size (1000 x 1000 Branin grid, Hex d=151): size-independent properties of the fused
+    path - sharding invariance of the argmax and agreement of the winner with the oracle on its neighbourhood."""
+    bounds = np.array([[-5.0, 10.0], [0.0, 15.0]])
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=1.0)
+    xs0 = np.random.default_rng(0).uniform(bounds[:, 0], bounds[:, 1], (10, 2))
+    a, b, c, r, s, t = 1, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6., 10., 1 / (8 * np.pi)
+    branin = lambda x: -(a * (x[:, 1] - b * x[:, 0] ** 2 + c * x[:, 0] - r) ** 2 + s * (1 - t) * np.cos(x[:, 0]) + s)
+    agt = pkg.SSPAgent(xs0, branin(xs0).reshape(-1, 1), sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0)
+    eng = sp.engine
+    axes = sp.grid_axes(1000, "grid")
+    grid = eng.grid_points(axes)
+    assert grid.shape == (1000000, 2)
+    agt.best_candidate(grid)
+    s_all, i_all = eng.best()
+    first = True
+    for k in range(4):                                           # 4 ragged shards
+        lo, hi = k * 250007, min(1000000, (k + 1) * 250007)
+        agt.best_candidate(grid[lo:hi], index0=lo, reset_best=first)
+        first = False
+    assert eng.best() == (s_all, i_all)
+    lo = max(0, i_all - 2000)
+    pts = grid[lo:lo + 4000].cpu().numpy()
+    ref = orc.BLR(sp.ssp_dim)
+    ref.update(orc.encode(sp.phase_matrix, np.ones(2), xs0), branin(xs0).reshape(-1, 1))
+    score, _ = orc.score_and_argmax(orc.encode(sp.phase_matrix, np.ones(2), pts), ref, 10.0, 0.0)
+    assert abs(score[i_all - lo] - s_all) <= RTOL_SCORE * abs(s_all)
+    assert score.max() <= s_all * (1 + np.sign(s_all) * RTOL_SCORE) + 1e-12

@@ -1,0 +1,143 @@
+"""CPU-only tests: C-ABI library exports, host-side mirrors of the reference constructors, sharding and the
+packed-key reduction over gloo (world_size 2).  No compute call touches a GPU here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssp_bayesopt_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "sspbo.h")).read()
+    declared = set(re.findall(r"\b(sspbo_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sspbo.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sspbo_abi_version() == 1
+
+
+def test_key_pack_orders_like_argmax():
+    from ssp_bayesopt_b200 import _lib
+    k = _lib.key_pack
+    assert k(1.0, 5) > k(0.5, 0)                       # higher score wins
+    assert k(1.0, 3) > k(1.0, 4)                       # ties: lowest index wins (np.argmax)
+    assert k(-1.0, 0) > k(-2.0, 0) and k(0.0, 9) > k(-0.0, 9) or k(0.0, 9) >= k(-0.0, 9)
+    assert k(float("nan"), 7) > k(float("inf"), 0)     # NaN counts as the maximum
+    assert k(-1e30, 1) > 0
+    s, i = _lib.key_unpack(k(-3.25, 4000000000))
+    assert s == -3.25 and i == 4000000000
+
+
+def test_phase_matrices_bit_identical_to_reference(golden):
+    from ssp_bayesopt_b200 import sspspace
+    g = golden("encode.npz")
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    assert np.array_equal(sspspace.RandomSSPSpace(2, ssp_dim=51, domain_bounds=b2, rng=0).phase_matrix, g["rand51_A"])
+    assert np.array_equal(sspspace.RandomSSPSpace(6, ssp_dim=1024, rng=0).phase_matrix, g["rand1024_A"])
+    hx = sspspace.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=b2, rng=0)
+    assert np.array_equal(hx.phase_matrix, g["hex51_A"]) and hx.ssp_dim == 25
+    assert np.array_equal(sspspace.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=b2).phase_matrix, g["hex151_A"])
+    s = 2 * np.pi / np.sqrt(6)
+    hs = sspspace.HexagonalSSPSpace(2, ssp_dim=151, scale_min=s - 0.5, scale_max=s + 0.5, length_scale=0.05)
+    assert np.array_equal(hs.phase_matrix, g["hexsmall_A"])
+    assert hs.length_scale.shape == (2, 1)
+    hs.update_lengthscale(0.1)
+    assert hs.length_scale.shape == (2,)               # sspspace.py:243-252 quirk kept
+    with pytest.raises(AssertionError):
+        sspspace.SSPSpace(2, 7, phase_matrix=np.zeros((7, 3)))
+
+
+def test_host_algebra_matches_reference(golden):
+    from ssp_bayesopt_b200 import sspspace
+    g = golden("decode.npz")
+    sp = sspspace.SSPSpace(2, g["A"].shape[0], phase_matrix=g["A"], domain_bounds=g["bounds"])
+    np.testing.assert_allclose(sp.bind(g["queries"][0], g["queries"][1]), g["bind"], atol=1e-15)
+    assert np.array_equal(sp.invert(g["queries"]), g["invert"])
+    assert sp.identity().shape == (1, sp.ssp_dim)
+    np.testing.assert_allclose(np.linalg.norm(sp.normalize(3 * g["queries"]), axis=1), 1.0)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ssp_bayesopt_b200 import _lib, sspspace
+    sp = sspspace.RandomSSPSpace(2, ssp_dim=51, rng=0)
+    with pytest.raises(_lib.SspboError):
+        sp.encode(np.zeros((1, 2)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssp_bayesopt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_shard_range_partitions():
+    from ssp_bayesopt_b200.dist import shard_range
+    for total in (0, 1, 7, 1000, 10 ** 8):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as td
+from ssp_bayesopt_b200 import _lib, dist
+td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+r = td.get_rank()
+assert dist.rank_world() == (r, 2) and dist.is_distributed()
+# rank 0 holds a positive score (top bit of the key set), rank 1 a higher one and a tie at a lower index
+cases = [((0.5, 10), (0.75, 2000000)), ((1.0, 9), (1.0, 3)), ((-2.0, 1), (-1.0, 4000000000)), ((float("nan"), 8), (9e9, 0))]
+for c in cases:
+    s, i = c[r]
+    key = _lib.key_pack(s, i)
+    t = torch.tensor([key - (1 << 64) if key >= (1 << 63) else key], dtype=torch.int64)
+    dist.allreduce_best(t)
+    got = _lib.key_unpack(int(t.item()))
+    want = max(_lib.key_pack(*c[0]), _lib.key_pack(*c[1]))
+    assert (int(t.item()) & 0xFFFFFFFFFFFFFFFF) == want, (c, got)
+# sharded argmax == global argmax on a synthetic score vector
+g = torch.Generator().manual_seed(0)
+scores = torch.randn(1001, generator=g)
+s0, s1 = dist.shard_range(1001, r, 2)
+loc = int(torch.argmax(scores[s0:s1])) + s0
+key = _lib.key_pack(float(scores[loc]), loc)
+t = torch.tensor([key - (1 << 64) if key >= (1 << 63) else key], dtype=torch.int64)
+dist.allreduce_best(t)
+assert _lib.key_unpack(int(t.item()))[1] == int(torch.argmax(scores))
+td.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_gloo_world2_key_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
