@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the SSP-BO hot path: fused encode + BLR-UCB + argmax candidates/s at d=1024 (-> 1023).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[2] ("C3"): RandomSSPSpace(n=6, ssp_dim=1024 -> d=1023, K=511), bounds [0,1]^6,
+length_scale 0.25, rng=0; posterior after 10 + 50 Hartmann-6 observations; 1e8 counter-based uniform float32
+candidates per BO step, sharded over 8 GPUs = 1.25e7 candidates per GPU per step (weak scaling: the per-GPU shard
+is fixed, so N GPUs score N * 1.25e7 candidates per step).  One step = score every local candidate with the
+fused kernel, max-reduce the packed (score, index) key over ranks, read the winner, evaluate Hartmann-6 on
+it and apply the float64 rank-one posterior update (so every step sees a new posterior).
+
+`value`   candidates/s, whole job, candidates resident in HBM, device-timed (CUDA events, max over ranks).
+`e2e`     same metric through the public API (`SSPAgent.best_candidate`) from pinned HOST candidates: the
+          H2D copy of the shard and the D2H read of the winner are inside the timed region every step.
+`roofline` tensor-pipe: achieved = candidates * F_alg / kernel time, F_alg = 2 d^2 + 2 d + 2 K n flops
+          (SURVEY.md section 8d), peak = MEASURED_PEAKS.json bf16 dense (sustained, the kernel runs inside a long step).
+`cpu_baseline` / `--impl reference`: the numpy oracle port of the reference path on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_REQ, N_DIM, LS, LAM, GAMMA = 1024, 6, 0.25, 10.0, 0.0
+PER_GPU = 12_500_000
+N_OBS = 60
+METRIC = "fused encode+UCB+argmax candidates/sec at d=1024"
+
+
+def f_alg(d, K, n):
+    return 2.0 * d * d + 2.0 * d + 2.0 * K * n
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1590.0))),
+                    tflops_burst=float(j.get("bf16_tflops", 1590.0)), hbm=float(j.get("hbm_gbs", 6650.0)),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def problem_setup():
+    """Seeded C3 posterior inputs, identical on every rank and for both arms."""
+    from oracle import ssp_oracle as orc          # only for the objective (Hartmann-6) and the shared generator
+    X = np.random.default_rng(1).uniform(0, 1, (N_OBS, N_DIM))
+    y = orc.hartmann6(X).reshape(-1, 1)
+    return X, y, orc
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(sample, chunk, steps=1, warmup=0):
+    """Reference path restated in numpy (oracle/ssp_oracle.py): encode -> predict -> acq -> argmax, chunked so the
+    (d x chunk) complex128 temporary stays small.  Returns (candidates/s, seconds per step, cores)."""
+    X, y, orc = problem_setup()
+    A = orc.random_phase_matrix(N_DIM, D_REQ, rng=0)
+    ls = LS * np.ones(N_DIM)
+    blr = orc.BLR(A.shape[0])
+    blr.update(orc.encode(A, ls, X[:10]), y[:10])
+    S, beta = blr.S.copy(), blr.beta
+    bvec = beta * (orc.encode(A, ls, X[:10]).T @ y[:10])
+    for i in range(10, N_OBS):                     # O(d^2) form of blr.py:63-75 to keep the setup short
+        phi = orc.encode(A, ls, X[i:i + 1])[0]
+        v = S @ phi
+        S = S - np.outer(v, v) * (beta / (1 + beta * (phi @ v)))
+        bvec = bvec + beta * phi[:, None] * y[i]
+    blr.S, blr.m = S, S @ bvec
+    times = []
+    for it in range(warmup + steps):
+        xc = orc.counter_uniform(0, it * sample, sample, N_DIM).astype(np.float64)
+        t0 = time.perf_counter()
+        best, best_i = -np.inf, -1
+        for c0 in range(0, sample, chunk):
+            score, i = orc.score_and_argmax(orc.encode(A, ls, xc[c0:c0 + chunk]), blr, LAM, GAMMA)
+            if score[i] > best:
+                best, best_i = score[i], c0 + i
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    return sample / per_step, per_step, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample, chunk = 20000, 10000
+    rate, per_step, cores = cpu_oracle_rate(sample, chunk, steps=args.steps, warmup=args.warmup)
+    d = 1023
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "candidates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023) Hartmann-6 posterior, uniform candidates",
+                   "candidates_per_step": sample, "note": "bounded sample of the 1.25e7-per-GPU shard"},
+        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} candidates/step in chunks of {chunk}, numpy/OpenBLAS on all host cores "
+                                   "(the reference is pure Python and cannot travel to the GPU box; this is its numpy "
+                                   "restatement, oracle/ssp_oracle.py, pinned to the live reference by tests/golden)"},
+        "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "roofline": None,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_native(args):
+    import torch
+    import torch.distributed as td
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import ssp_bayesopt_b200 as pkg
+    from ssp_bayesopt_b200 import _lib, dist
+
+    X, y, orc = problem_setup()
+    b6 = np.array([[0.0, 1.0]] * N_DIM)
+    sp = pkg.RandomSSPSpace(N_DIM, ssp_dim=D_REQ, domain_bounds=b6, length_scale=LS, rng=0, device=local)
+    agt = pkg.SSPAgent(X, y, sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=LAM, length_scale=LS,
+                       score_engine={"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "umma": _lib.ENGINE_UMMA}[args.engine])
+    eng = agt._scoring_engine()
+    d, K = sp.ssp_dim, (sp.ssp_dim - 1) // 2
+    n_local = args.per_gpu
+    total = n_local * world
+    start = rank * n_local
+    cand = eng.fill_uniform(0, start, n_local)                    # resident shard, 300 MB > L2 (126 MB)
+    chunk = args.chunk
+    torch.cuda.synchronize()
+
+    def select(x_dev):
+        first = True
+        for c0 in range(0, n_local, chunk):
+            agt.best_candidate(x_dev[c0:c0 + chunk], index0=start + c0, reset_best=first)
+            first = False
+        dist.allreduce_best(eng._best)
+        return eng.best()                                         # D2H of the 8-byte key (synchronises)
+
+    def winner_row(gidx):
+        u = orc.counter_uniform(0, gidx, 1, N_DIM)                # any rank can regenerate any candidate
+        return u.astype(np.float64)
+
+    def bo_step(x_dev, kernel_events=None):
+        if kernel_events is not None:
+            kernel_events[0].record()
+        score, gidx = select(x_dev)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        x_t = winner_row(gidx)
+        y_t = np.atleast_2d(orc.hartmann6(x_t))
+        var_t = np.array([0.0])
+        agt.update(x_t, y_t, var_t)                               # encode x_t + float64 rank-one update on device
+        return score, gidx
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        bo_step(cand)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    last = None
+    for i in range(args.steps):
+        last = bo_step(cand, ev[i])
+    t_end.record()
+    barrier()
+    sampler.stop_flag = True
+    launches = eng.launch_count() - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))   # scoring launches + key reduction, per step
+    engine_used = eng.last_engine()
+
+    # ---- end-to-end timing: pinned host candidates -> H2D -> fused score -> D2H key, through the public API ----
+    host = torch.empty((n_local, N_DIM), dtype=torch.float32).pin_memory()
+    host.copy_(cand)
+    e2e_steps = max(1, min(args.steps, 3))
+    staging = torch.empty_like(cand)
+    def e2e_step():
+        staging.copy_(host, non_blocking=True)                    # H2D of this step's candidates
+        return bo_step(staging)
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # max over ranks
+    stats = torch.tensor([ms_total, kernel_ms, e2e_ms], dtype=torch.float64, device=cand.device)
+    if world > 1:
+        td.all_reduce(stats, op=td.ReduceOp.MAX)
+    ms_total, kernel_ms, e2e_ms = [float(v) for v in stats.cpu()]
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_per_step = ms_total / args.steps
+        value = total / (ms_per_step * 1e-3)
+        flops = f_alg(d, K, N_DIM)
+        achieved = n_local * flops / (kernel_ms * 1e-3) / 1e12      # per GPU, TFLOP/s algorithmic
+        cpu_rate, cpu_step, cores = cpu_oracle_rate(20000, 10000, steps=1, warmup=0) if world == 1 else (None, None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x3-split mma / f32 accumulate / f64 phase+posterior" if engine_used == "umma"
+            else "f32 contraction / f64 phase+posterior",
+            "data": "synthetic",
+            "config": {"workload": "C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023,K=511) ls=0.25 rng=0, Hartmann-6 posterior "
+                                   f"after {N_OBS}+step observations, counter-based uniform f32 candidates",
+                       "candidates_per_gpu_per_step": n_local, "candidates_per_step": total, "chunk": chunk,
+                       "engine": engine_used, "parallelism": f"candidate-shard x{world}",
+                       "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands refreshed every step",
+                       "last_winner": {"score": last[0], "index": last[1]}},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "note": f"algorithmic {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
+                                 f"{kernel_ms:.2f} ms scoring time per step per GPU; peak {peaks['source']}"},
+            "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
+                              "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
+                             if cpu_rate else None),
+            "e2e": {"value": total * e2e_steps / (e2e_ms * 1e-3), "unit": "candidates/s",
+                    "h2d_bytes_per_step": int(n_local * N_DIM * 4), "d2h_bytes_per_step": 8,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "umma"])
+    ap.add_argument("--per-gpu", type=int, default=PER_GPU)
+    ap.add_argument("--chunk", type=int, default=1 << 22)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

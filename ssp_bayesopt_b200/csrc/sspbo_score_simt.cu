@@ -99,7 +99,8 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
 #pragma unroll
             for (int s = 0; s < 16; ++s) u += red_mu[tid * 16 + s];
             float var = inv_beta + qq;                                        // blr.py:96
-            float acq = lam * (sqrtf(var + gamma_t) - sqrtf(gamma_t));        // ssp_agent.py:136
+            // ssp_agent.py:136: lam (sqrt(var + gamma) - sqrt(gamma)), written without the float32 cancellation
+            float acq = lam * var / (sqrtf(var + gamma_t) + sqrtf(gamma_t));
             float score = u + acq;
             int64_t gi = base + tid;
             if (mu_out) mu_out[gi] = u;

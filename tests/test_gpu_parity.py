@@ -30,6 +30,17 @@ def space_from(pkg, A, ls, bounds=None):
     return pkg.SSPSpace(A.shape[1], A.shape[0], phase_matrix=A, domain_bounds=bounds, length_scale=np.asarray(ls))
 
 
+def assert_scores_close(mu, acq, ref_mu, ref_acq, rtol=RTOL_SCORE):
+    """score = mu + acq can cancel to ~0 (MI acquisition), so 'within 1e-4 relative' is taken relative to the
+    magnitude of the two terms; acq (always > 0) is additionally checked element-wise."""
+    mu, acq, ref_mu, ref_acq = (np.ravel(a) for a in (mu, acq, ref_mu, ref_acq))
+    scale = np.abs(ref_mu) + np.abs(ref_acq)
+    err = np.abs((mu + acq) - (ref_mu + ref_acq)) / scale
+    assert err.max() < rtol, err.max()
+    np.testing.assert_allclose(acq, ref_acq, rtol=rtol)
+    assert np.max(np.abs(mu - ref_mu) / scale) < rtol
+
+
 def rel(a, b):
     return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
 
@@ -163,13 +174,15 @@ def test_agent_eval_golden(pkg, golden, tag, gamma_c):
     assert agt.var_weight == g[f"{tag}_var_weight"]
     mu, var, acq = agt.eval(g["xc"])
     assert mu.shape == (1, 256) and var.shape == (256,) and acq.shape == (256,)
-    score, ref = mu.ravel() + acq, g[f"{tag}_mu"].ravel() + g[f"{tag}_acq"]
-    np.testing.assert_allclose(score, ref, rtol=RTOL_SCORE)
+    ref = g[f"{tag}_mu"].ravel() + g[f"{tag}_acq"]
+    assert_scores_close(mu, acq, g[f"{tag}_mu"], g[f"{tag}_acq"])
     np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=RTOL_SCORE)
-    np.testing.assert_allclose(acq, g[f"{tag}_acq"], rtol=RTOL_SCORE)
     key = agt.best_candidate(g["xc"])
     s, idx = agt._scoring_engine().best()
-    assert idx == int(np.argmax(ref)) and abs(s - ref.max()) <= RTOL_SCORE * abs(ref.max())
+    srt = np.sort(ref)[::-1]
+    if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+        assert idx == int(np.argmax(ref))
+    assert abs(s - ref.max()) <= RTOL_SCORE * np.max(np.abs(g[f"{tag}_mu"]) + np.abs(g[f"{tag}_acq"]))
     assert np.array_equal(agt.init_samples[1], g[f"{tag}_init_pts"])
     assert np.array_equal(agt.decode(agt.encode(g["xc"][:3])), g[f"{tag}_decoded"])
 
@@ -212,6 +225,9 @@ def test_score_c3_parity(pkg, engine):
     code = {"simt": _lib.ENGINE_SIMT, "auto": _lib.ENGINE_AUTO}[engine]
     _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=code)
     score = (mu + acq).double().cpu().numpy()
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gam)
+    assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+    np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
     err = np.abs(score - ref_score) / np.abs(ref_score)
     assert err.max() < RTOL_SCORE, err.max()
     srt = np.sort(ref_score)[::-1]
@@ -239,7 +255,7 @@ def test_score_edge_cases(pkg, golden):
     for n in (1, 15, 16, 17, 255):
         mu, var, acq = agt.eval(g["xc"][:n])
         assert mu.shape == (1, n)
-        np.testing.assert_allclose(mu.ravel() + acq, (g["ucb_mu"].ravel() + g["ucb_acq"])[:n], rtol=RTOL_SCORE)
+        assert_scores_close(mu, acq, g["ucb_mu"].ravel()[:n], g["ucb_acq"][:n])
     key, outs = eng.score(np.zeros((0, 2)), 10.0, 0.0, want_outputs=True)          # empty candidate set
     assert int(key.item()) == 0 and outs[0].numel() == 0
     with pytest.raises(Exception):
@@ -299,7 +315,7 @@ def test_trajectory_agent_golden(pkg, golden):
     assert agt.blr.beta == g["beta"]
     assert rel(agt.blr.m, g["m"]) < 1e-9 and rel(agt.blr.S, g["S"]) < 1e-9
     mu, var, acq = agt.eval(g["xc"])
-    np.testing.assert_allclose(mu.ravel() + acq, g["mu"].ravel() + g["acq"], rtol=RTOL_SCORE)
+    assert_scores_close(mu, acq, g["mu"], g["acq"])
     np.testing.assert_allclose(var, g["var"], rtol=RTOL_SCORE)
     assert np.array_equal(agt.decode(phi[:1]), g["decoded"])
 
