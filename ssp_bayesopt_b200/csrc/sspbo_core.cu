@@ -186,8 +186,7 @@ __global__ void k_set_diag(double* __restrict__ M, int d, double v0, double v) {
 
 // refresh of the scoring operands from the float64 masters
 __global__ void k_refresh_operands(const double* __restrict__ R, const double* __restrict__ mp, int d, int dp,
-                                   double r_scale, float* __restrict__ Rt_f32, __half* __restrict__ Rh,
-                                   __half* __restrict__ Rl, float* __restrict__ mp_f32) {
+                                   float* __restrict__ Rt_f32, float* __restrict__ mp_f32) {
     __shared__ double tile[32][33];
     int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
     // read R[j][k] coalesced along k
@@ -195,13 +194,6 @@ __global__ void k_refresh_operands(const double* __restrict__ R, const double* _
         int j = j0 + r, k = k0 + threadIdx.x;
         double v = (j < d && k < d) ? R[(size_t)j * d + k] : 0.0;
         tile[r][threadIdx.x] = v;
-        if (j < dp && k < dp) {
-            double sv = v * r_scale;
-            __half h = __double2half(sv);
-            double rem = sv - (double)__half2float(h);
-            Rh[(size_t)j * dp + k] = h;
-            Rl[(size_t)j * dp + k] = __double2half(rem);
-        }
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
@@ -211,6 +203,28 @@ __global__ void k_refresh_operands(const double* __restrict__ R, const double* _
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         for (int i = threadIdx.y * 32 + threadIdx.x; i < dp; i += 256) mp_f32[i] = (i < d) ? (float)mp[i] : 0.f;
     }
+}
+
+// split-fp16 operands of the tcgen05 scorer in operand order (sspbo_internal.cuh)
+__device__ __forceinline__ int psi_index_of_column(int c, int K) {
+    int b = c >> 6, i = c & 63;
+    int f = 32 * b + (i & 31);
+    if (f > K) return -1;
+    if (i < 32) return f;                    // DC (f = 0) or cos_f
+    return f == 0 ? -1 : K + f;              // sin_f ; sin of the DC term is identically zero
+}
+__global__ void k_refresh_umma_operands(const double* __restrict__ R, const double* __restrict__ mp, int d, int K,
+                                        int KC_pad, int NJ_pad, double r_scale, __half* __restrict__ Rh,
+                                        __half* __restrict__ Rl, float* __restrict__ mp_op) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (c >= KC_pad) return;
+    int p = psi_index_of_column(c, K);
+    double v = (p >= 0 && j < d) ? R[(size_t)j * d + p] * r_scale : 0.0;
+    __half h = __double2half(v);
+    Rh[(size_t)j * KC_pad + c] = h;
+    Rl[(size_t)j * KC_pad + c] = __double2half(v - (double)__half2float(h));
+    if (j == 0) mp_op[c] = (p >= 0) ? (float)mp[p] : 0.f;
 }
 
 // =====================================================================================
@@ -375,7 +389,7 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
     dev_free(&ctx->R); dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
-    dev_free(&ctx->Rh); dev_free(&ctx->Rl);
+    dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -386,7 +400,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     sspbo_umma_release(ctx);
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
-    dev_free(&ctx->twiddle); dev_free(&ctx->scal);
+    dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->At_op);
     delete ctx;
 }
 
@@ -425,6 +439,15 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns_f32, Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
     dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    {   // frequency table of the tcgen05 scorer: row f = A_turns of frequency f (f = 0: DC, f > K: padding) -> zeros
+        int kc, bn, nc, nj;
+        sspbo_umma_dims(K, &kc, &bn, &nc, &nj);
+        std::vector<double> op((size_t)(kc / 2) * n, 0.0);
+        for (int f = 1; f <= K; ++f)
+            for (int a = 0; a < n; ++a) op[(size_t)f * n + a] = At[(size_t)(f - 1) * n + a];
+        if ((rc = dev_alloc(ctx, &ctx->At_op, op.size()))) return rc;
+        SSPBO_CUDA(ctx, cudaMemcpy(ctx->At_op, op.data(), op.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
     return SSPBO_OK;
 }
@@ -488,6 +511,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     const int dp = sspbo_pad64(d);
     const size_t dd = (size_t)d * d, dpp = (size_t)dp * dp;
     int rc;
+    if (with_factor) sspbo_umma_dims(ctx->K, &ctx->KC_pad, &ctx->BN, &ctx->n_chunks, &ctx->NJ_pad);
     if ((rc = dev_alloc(ctx, &ctx->S, dd)) || (rc = dev_alloc(ctx, &ctx->Sinv, dd)) ||
         (rc = dev_alloc(ctx, &ctx->b, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->m, (size_t)d)) ||
         (rc = dev_alloc(ctx, &ctx->v, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->z, (size_t)d)))
@@ -495,7 +519,9 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     if (with_factor) {
         if ((rc = dev_alloc(ctx, &ctx->R, dd)) || (rc = dev_alloc(ctx, &ctx->mp, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->Rt_f32, dpp)) || (rc = dev_alloc(ctx, &ctx->mp_f32, (size_t)dp)) ||
-            (rc = dev_alloc(ctx, &ctx->Rh, dpp)) || (rc = dev_alloc(ctx, &ctx->Rl, dpp)) ||
+            (rc = dev_alloc(ctx, &ctx->Rh, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Rl, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->mp_op, (size_t)ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->psi, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->y, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->phi_tmp, (size_t)d)))
             return rc;
@@ -602,8 +628,11 @@ int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     if (!ctx->operands_dirty) return SSPBO_OK;
     dim3 grid(ctx->dp / 32, ctx->dp / 32);
-    k_refresh_operands<<<grid, dim3(32, 8), 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->dp, ctx->r_scale, ctx->Rt_f32, ctx->Rh,
-                                                     ctx->Rl, ctx->mp_f32);
+    k_refresh_operands<<<grid, dim3(32, 8), 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->dp, ctx->Rt_f32, ctx->mp_f32);
+    SSPBO_LAUNCH_CHECK(ctx);
+    dim3 g2((ctx->KC_pad + 255) / 256, ctx->NJ_pad);
+    k_refresh_umma_operands<<<g2, 256, 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->K, ctx->KC_pad, ctx->NJ_pad, ctx->r_scale,
+                                                ctx->Rh, ctx->Rl, ctx->mp_op);
     SSPBO_LAUNCH_CHECK(ctx);
     ctx->operands_dirty = false;
     return SSPBO_OK;

@@ -34,8 +34,14 @@ struct sspbo_ctx {
     double* mp = nullptr;            // m' = B^T m (d)
     float*  Rt_f32 = nullptr;        // dp x dp float32, Rt[k*dp + j] = R[j][k]      (SIMT scorer)
     float*  mp_f32 = nullptr;        // dp
-    __half* Rh = nullptr;            // dp x dp fp16 K-major: Rh[j*dp + k] = hi(R[j][k] * r_scale) (tcgen05 scorer)
-    __half* Rl = nullptr;            //                       lo part
+    // tcgen05 scorer operands, "operand order" (see sspbo_umma_dims): NJ_pad x KC_pad fp16, K-major.
+    //   column c -> block b = c/64, i = c%64, frequency f = 32 b + (i%32) (f = 0 is the DC term);
+    //   i < 32 : cos(theta_f) column, i >= 32 : sin(theta_f) column; f > K and sin(DC) columns are zero.
+    __half* Rh = nullptr;            // hi(R[j][psi_index(c)] * r_scale)
+    __half* Rl = nullptr;            // lo part (value - hi)
+    float*  mp_op = nullptr;         // m' in operand order (KC_pad)
+    double* At_op = nullptr;         // (KC_pad/2) x n float64: A_turns row of frequency f (row 0 and f > K are zero)
+    int KC_pad = 0, BN = 0, n_chunks = 0, NJ_pad = 0;
     double r_scale = 1.0;
     bool operands_dirty = true;      // Rt_f32 / Rh / Rl / mp_f32 need a refresh from R, m
     // scratch d-vectors (float64)
@@ -68,6 +74,17 @@ struct sspbo_ctx {
     } while (0)
 
 static inline int sspbo_pad64(int x) { return (x + 63) / 64 * 64; }
+
+// Operand geometry of the tcgen05 scorer for a space with K positive frequencies (d = 2K+1):
+//   KC_pad   contraction length: (K+1) frequencies in blocks of 32 -> 64 columns (cos|sin) per block
+//   n_chunks / BN  the d output rows j are processed in n_chunks chunks of BN rows (BN % 16 == 0, BN <= 256)
+static inline void sspbo_umma_dims(int K, int* KC_pad, int* BN, int* n_chunks, int* NJ_pad) {
+    int d = 2 * K + 1;
+    int kb = (K + 1 + 31) / 32;
+    int nc = (d + 255) / 256;
+    int bn = ((d + nc - 1) / nc + 15) / 16 * 16;
+    *KC_pad = kb * 64; *BN = bn; *n_chunks = nc; *NJ_pad = nc * bn;
+}
 
 // ---- packed (score, index) key: max(key) == max score, lowest index on ties; NaN ranks highest ----
 __host__ __device__ inline unsigned int sspbo_orderable(float f) {

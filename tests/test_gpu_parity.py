@@ -210,7 +210,7 @@ def _c3_setup(pkg, T, seed=1):
     return sp, model, ref, X
 
 
-@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "umma", "auto"])
 def test_score_c3_parity(pkg, engine):
     from ssp_bayesopt_b200 import _lib
     sp, model, ref, X = _c3_setup(pkg, 60)
@@ -222,8 +222,9 @@ def test_score_c3_parity(pkg, engine):
     phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
     ref_score, ref_idx = orc.score_and_argmax(phis, ref, lam, gam)
     eng = sp.engine
-    code = {"simt": _lib.ENGINE_SIMT, "auto": _lib.ENGINE_AUTO}[engine]
+    code = {"simt": _lib.ENGINE_SIMT, "umma": _lib.ENGINE_UMMA, "auto": _lib.ENGINE_AUTO}[engine]
     _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=code)
+    assert eng.last_engine() == ("simt" if engine == "simt" else "umma")
     score = (mu + acq).double().cpu().numpy()
     ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gam)
     assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
@@ -237,12 +238,51 @@ def test_score_c3_parity(pkg, engine):
         assert idx == ref_idx, (idx, ref_idx, gap)
     assert abs(s - ref_score.max()) <= RTOL_SCORE * abs(ref_score.max())
     # index0 offsets the packed index; shards combine by max
-    eng.score(xc[:4096], lam, gam, index0=1000)
+    eng.score(xc[:4096], lam, gam, index0=1000, engine=code)
     k1 = int(eng._best.item())
-    eng.score(xc[4096:], lam, gam, index0=1000 + 4096, reset_best=False)
+    eng.score(xc[4096:], lam, gam, index0=1000 + 4096, reset_best=False, engine=code)
     s2, idx2 = eng.best()
     assert idx2 == idx + 1000 and s2 == s
     assert (int(eng._best.item()) & 0xFFFFFFFFFFFFFFFF) >= (k1 & 0xFFFFFFFFFFFFFFFF)
+
+
+@pytest.mark.parametrize("kind,ssp_dim,n_dim,N", [("hex", 151, 2, 1000), ("hex", 51, 2, 129), ("rand", 512, 2, 4097),
+                                                  ("rand", 64, 3, 128), ("rand", 300, 6, 77)])
+def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
+    """tcgen05 engine on the other BASELINE shapes (d=151, d=511), odd d, ragged N, float64 candidates, MI gamma."""
+    from ssp_bayesopt_b200 import _lib
+    rng = np.random.default_rng(ssp_dim + N)
+    bounds = np.array([[-3.0, 4.0]] * n_dim)
+    if kind == "hex":
+        sp = pkg.HexagonalSSPSpace(n_dim, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=0.8, rng=0)
+    else:
+        sp = pkg.RandomSSPSpace(n_dim, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=0.8, rng=0)
+    ls = 0.8 * np.ones(n_dim)
+    X = rng.uniform(-3, 4, (25, n_dim))
+    y = np.sin(X.sum(axis=1, keepdims=True))
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    ref = orc.BLR(sp.ssp_dim)
+    for i in range(0, 25, 5):
+        model.update(sp.encode(X[i:i + 5]), y[i:i + 5])
+        ref.update(orc.encode(sp.phase_matrix, ls, X[i:i + 5]), y[i:i + 5])
+    xc = rng.uniform(-3, 4, (N, n_dim))                                   # float64 candidates
+    xc[:5] = X[:5]                                                         # observed points: smallest variance
+    phis = orc.encode(sp.phase_matrix, ls, xc)
+    for lam, gam in ((10.0, 0.0), (3.0, 250.0)):
+        ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gam)
+        ref_score = ref_mu.ravel() + ref_acq
+        eng = sp.engine
+        _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_UMMA)
+        assert eng.last_engine() == "umma"
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        s, idx = eng.best()
+        srt = np.sort(ref_score)[::-1]
+        if N > 1 and (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert idx == int(np.argmax(ref_score))
+        # both engines agree far below the tolerance
+        _, (mu2, var2, acq2) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_SIMT)
+        np.testing.assert_allclose(var.cpu().numpy(), var2.cpu().numpy(), rtol=2e-5)
 
 
 def test_score_edge_cases(pkg, golden):
