@@ -22,11 +22,11 @@ namespace {
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block = one 128-byte swizzle atom of fp16
-constexpr int GEN_WARPS = 8;
+constexpr int GEN_WARPS = 16;                     // 512 threads: (row, quarter) -> 8 frequencies of a k-block each
 constexpr int EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
-constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 256
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 704
+constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 512
 constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB
 constexpr int MAX_N = 8;                                         // domain dimension held in registers
 constexpr uint32_t TMEM_COLS = 512;
@@ -65,6 +65,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 26)) __trap();
+}
+// same, with a short sleep between polls: for roles that wait for a long time (epilogue, producers)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        __nanosleep(100);
+        if (spin > (1u << 24)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -112,7 +119,8 @@ struct Pipe {                            // ring position shared by every role (
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B swizzle; offset arithmetic (not integer casts) keeps the address space known
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_tile_bytes = p.BN * BK * 2;
@@ -120,8 +128,8 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint8_t* tables = smem + (size_t)p.stages * stage_bytes;
     double* At_s = (double*)tables;                                         // (KC_pad/2) x n
     float* mp_s = (float*)(At_s + (size_t)(p.KC_pad / 2) * p.n);            // KC_pad
-    float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][2 halves][128]
-    uint64_t* bars = (uint64_t*)(((uintptr_t)(mu_part + 2 * 2 * BM) + 7) & ~(uintptr_t)7);
+    float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][4 quarters][128]
+    uint64_t* bars = (uint64_t*)(mu_part + 2 * 4 * BM);                     // offset is a multiple of 8 bytes (see table_bytes)
     // barrier map: full_a[s], full_b[s], empty[s] for s < stages ; tmem_full[2] ; tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -157,7 +165,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int c = 0; c < p.n_chunks; ++c)
                     for (int kb = 0; kb < p.n_kb; ++kb) {
-                        mbar_wait(empty_(pipe.stage), pipe.phase ^ 1);
+                        mbar_wait_relaxed(empty_(pipe.stage), pipe.phase ^ 1);
                         uint8_t* st = smem + (size_t)pipe.stage * stage_bytes;
                         mbar_expect_tx(full_b(pipe.stage), 2u * (uint32_t)b_tile_bytes);
                         tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &map_hi, full_b(pipe.stage), kb * BK, c * p.BN);
@@ -211,7 +219,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             float q = 0.f;
             for (int c = 0; c < p.n_chunks; ++c, ++acc_iter) {
                 const int buf = acc_iter & 1;
-                mbar_wait(tmem_full(buf), acc_phase[buf]);
+                mbar_wait_relaxed(tmem_full(buf), acc_phase[buf]);
                 acc_phase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
@@ -227,8 +235,8 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             }
             const long long gi = tile * BM + row;
             if (gi < p.N) {
-                const float* mpart = mu_part + (tile_iter & 1) * 2 * BM;
-                float mu = mpart[row] + mpart[BM + row];
+                const float* mpart = mu_part + (tile_iter & 1) * 4 * BM;
+                float mu = (mpart[row] + mpart[BM + row]) + (mpart[2 * BM + row] + mpart[3 * BM + row]);
                 float var = p.inv_beta + q * p.inv_rscale2;                           // blr.py:96
                 float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
                 float score = mu + acq;
@@ -247,10 +255,13 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     } else {
         // ================================ psi generators ================================
         const int gt = threadIdx.x - WARP_GEN0 * 32;
-        const int row = gt & (BM - 1), half = gt >> 7;                    // half 0: frequencies 0..15 of the block, 1: 16..31
+        const int row = gt & (BM - 1), quarter = gt >> 7;                 // quarter q: frequencies 8q .. 8q+7 of the k-block
         const int n = p.n;
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t sw = (uint32_t)(row & 7);
+        // one 16-byte chunk of cos (chunk q) and one of sin (chunk 4+q) per stage, XOR-swizzled by the row
+        const uint32_t off_cos = row_off + (((uint32_t)quarter ^ sw) << 4);
+        const uint32_t off_sin = row_off + (((uint32_t)(quarter + 4) ^ sw) << 4);
         Pipe pipe;
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
@@ -265,53 +276,48 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             float mu = 0.f;
             for (int c = 0; c < p.n_chunks; ++c)
                 for (int kb = 0; kb < p.n_kb; ++kb) {
-                    mbar_wait(empty_(pipe.stage), pipe.phase ^ 1);
-                    uint8_t* st = smem + (size_t)pipe.stage * stage_bytes;
-                    const double* Ablk = At_s + (size_t)(kb * 32 + half * 16) * n;
-                    const float* mcos = mp_s + kb * BK + half * 16;
-                    const float* msin = mcos + 32;
+                    const double* Ablk = At_s + (size_t)(kb * 32 + quarter * 8) * n;
+                    float cs[8], sn[8];
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {                          // 8 frequencies -> one 16-byte chunk of cos, one of sin
-                        float cs[8], sn[8];
+                    for (int i = 0; i < 8; ++i) {
+                        const double* Af = Ablk + (size_t)i * n;
+                        double t = 0.0;
+#pragma unroll
+                        for (int a = 0; a < MAX_N; ++a)
+                            if (a < n) t = fma(Af[a], x[a], t);
+                        float tr = (float)(t - rint(t));                  // exact reduction to [-1/2, 1/2] turns
+                        float ang = tr * 6.283185307179586f;
+                        cs[i] = __cosf(ang);
+                        sn[i] = __sinf(ang);
+                    }
+                    if (c == 0) {
+                        const float* mcos = mp_s + kb * BK + quarter * 8;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const double* Af = Ablk + (size_t)(g * 8 + i) * n;
-                            double t = 0.0;
-#pragma unroll
-                            for (int a = 0; a < MAX_N; ++a)
-                                if (a < n) t = fma(Af[a], x[a], t);
-                            float tr = (float)(t - rint(t));              // exact reduction to [-1/2, 1/2] turns
-                            float ang = tr * 6.283185307179586f;
-                            cs[i] = __cosf(ang);
-                            sn[i] = __sinf(ang);
+                            mu = fmaf(mcos[i], cs[i], mu);
+                            mu = fmaf(mcos[32 + i], sn[i], mu);
                         }
-                        if (c == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                mu = fmaf(mcos[g * 8 + i], cs[i], mu);
-                                mu = fmaf(msin[g * 8 + i], sn[i], mu);
-                            }
-                        }
-                        uint32_t ch[4], cl[4], sh[4], sl[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            __half2 h = __floats2half2_rn(cs[2 * i], cs[2 * i + 1]);
-                            float2 hf = __half22float2(h);
-                            __half2 l = __floats2half2_rn(cs[2 * i] - hf.x, cs[2 * i + 1] - hf.y);
-                            ch[i] = *reinterpret_cast<uint32_t*>(&h); cl[i] = *reinterpret_cast<uint32_t*>(&l);
-                            h = __floats2half2_rn(sn[2 * i], sn[2 * i + 1]);
-                            hf = __half22float2(h);
-                            l = __floats2half2_rn(sn[2 * i] - hf.x, sn[2 * i + 1] - hf.y);
-                            sh[i] = *reinterpret_cast<uint32_t*>(&h); sl[i] = *reinterpret_cast<uint32_t*>(&l);
-                        }
-                        const uint32_t chunk_cos = (uint32_t)(half * 2 + g), chunk_sin = chunk_cos + 4u;
-                        const uint32_t off_cos = row_off + ((chunk_cos ^ sw) << 4), off_sin = row_off + ((chunk_sin ^ sw) << 4);
-                        *reinterpret_cast<uint4*>(st + off_cos) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-                        *reinterpret_cast<uint4*>(st + off_sin) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-                        *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_cos) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
-                        *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_sin) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
                     }
-                    if (c == 0 && kb == p.n_kb - 1) mu_part[(tile_iter & 1) * 2 * BM + half * BM + row] = mu;
+                    uint32_t ch[4], cl[4], sh[4], sl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __half2 h = __floats2half2_rn(cs[2 * i], cs[2 * i + 1]);
+                        float2 hf = __half22float2(h);
+                        __half2 l = __floats2half2_rn(cs[2 * i] - hf.x, cs[2 * i + 1] - hf.y);
+                        ch[i] = *reinterpret_cast<uint32_t*>(&h); cl[i] = *reinterpret_cast<uint32_t*>(&l);
+                        h = __floats2half2_rn(sn[2 * i], sn[2 * i + 1]);
+                        hf = __half22float2(h);
+                        l = __floats2half2_rn(sn[2 * i] - hf.x, sn[2 * i + 1] - hf.y);
+                        sh[i] = *reinterpret_cast<uint32_t*>(&h); sl[i] = *reinterpret_cast<uint32_t*>(&l);
+                    }
+                    // values are ready in registers before the slot is claimed: the wait overlaps the math above
+                    mbar_wait(empty_(pipe.stage), pipe.phase ^ 1);
+                    uint8_t* st = smem + (size_t)pipe.stage * stage_bytes;
+                    *reinterpret_cast<uint4*>(st + off_cos) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+                    *reinterpret_cast<uint4*>(st + off_sin) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_cos) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_sin) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+                    if (c == 0 && kb == p.n_kb - 1) mu_part[(tile_iter & 1) * 4 * BM + quarter * BM + row] = mu;
                     fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core
                     mbar_arrive(full_a(pipe.stage));
                     pipe.advance(p.stages);
@@ -340,7 +346,7 @@ struct UmmaState {
 
 size_t table_bytes(const sspbo_ctx* ctx) {
     return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(double) + (size_t)ctx->KC_pad * sizeof(float) +
-           2 * 2 * BM * sizeof(float) + 8 + (3 * 4 + 4) * 8 + 16;
+           2 * 4 * BM * sizeof(float) + (3 * 4 + 4) * 8 + 16;
 }
 size_t stage_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)A_TILE_BYTES + 2 * (size_t)ctx->BN * BK * 2; }
 
