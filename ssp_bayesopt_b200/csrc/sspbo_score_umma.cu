@@ -1,18 +1,19 @@
 // K2, tcgen05/TMEM engine: fused encode + BLR acquisition + argmax for sm_100a.
 //
 // Per CTA (persistent, one per SM) and per tile of 128 candidates:
-//   generator warps  theta_f = A_f . x in float64 turns, exact range reduction, MUFU sin/cos -> the psi tile
-//                    (A operand, 128 x 64 per k-block) written straight into 128B-swizzled shared memory as a
-//                    split-fp16 pair (hi, lo); psi never exists in HBM.  The first pass also accumulates
-//                    mu = m' . psi in float32.
-//   TMA warp         streams the matching 64-column slabs of the split-fp16 factor R (hi, lo) from L2.
+//   generator warps  theta_f = A_f . x in float64 turns, exact range reduction, MUFU sin/cos -> the psi k-block
+//                    (A operand, 128 x 64) written straight into 128B-swizzled shared memory as a split-fp16 pair
+//                    (hi, lo); psi never exists in HBM.  Each thread owns 2 candidate rows x 8 frequencies, so one
+//                    shared-memory read of a phase-matrix entry feeds two float64 FMA chains.  The first pass also
+//                    accumulates mu = m' . psi in float32.
+//   TMA warp         streams the 64-column slabs of the split-fp16 factor R (hi, lo) from L2 into the B ring.
 //   MMA warp         one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16, fp16 x fp16 -> fp32 in TMEM):
 //                    Y += psi_hi R_hi^T + psi_hi R_lo^T + psi_lo R_hi^T   (3-term split: ~2^-22 operand precision)
-//   epilogue warps   tcgen05.ld the accumulator chunk, q += sum_j Y_j^2, then var = 1/beta + q / r_scale^2,
+//   epilogue warps   tcgen05.ld the accumulator, q += sum_j Y_j^2, then var = 1/beta + q / r_scale^2,
 //                    acq = lam var / (sqrt(var+gamma) + sqrt(gamma)), score = mu + acq, warp-shuffle argmax.
-// The d output rows are processed in n_chunks chunks of BN rows with two TMEM accumulators (2 x 256 columns) so the
-// epilogue of chunk c overlaps the MMAs of chunk c+1; the psi k-block is regenerated per chunk (it is cheaper than
-// the 3 x MMA time it overlaps with, and 128 x 1024 x 2 x fp16 does not fit on chip).
+// The d output rows are processed in chunks of BN rows, two chunks (= both 256-column TMEM accumulators) per pass
+// over the contraction dimension, so every generated psi k-block is consumed by two MMAs groups before it is
+// regenerated for the next pair of chunks (128 x 1024 x 2 fp16 does not fit on chip).
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
@@ -22,20 +23,23 @@ namespace {
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block = one 128-byte swizzle atom of fp16
-constexpr int GEN_WARPS = 16;                     // 512 threads: (row, quarter) -> 8 frequencies of a k-block each
+constexpr int GEN_WARPS = 8;            // 256 threads: (row pair, quarter) -> 2 rows x 8 frequencies of a k-block each
 constexpr int EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 704
-constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 512
-constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB
-constexpr int MAX_N = 8;                                         // domain dimension held in registers
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
+constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 256
+constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB (one of hi / lo)
+constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
+constexpr int NA = 2;                                            // A ring slots
+constexpr int MAX_NB = 6;                                        // B ring slots (as many as fit)
+constexpr int MAX_N = 8;                                         // domain dimension (compile-time specialised)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;                                    // columns per accumulator buffer
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
     const double* At_op; const float* mp_op;
-    int n, K, KC_pad, BN, n_chunks, n_kb, stages;
+    int K, KC_pad, BN, n_chunks, n_kb, nb;
     float inv_beta, lam, gamma_t, inv_rscale2;
     float *mu, *var, *acq;
     unsigned long long* best;
@@ -66,7 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 26)) __trap();
 }
-// same, with a short sleep between polls: for roles that wait for a long time (epilogue, producers)
+// same, with a short sleep between polls: for roles that wait for a long time (epilogue, TMA producer)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
         __nanosleep(100);
@@ -110,12 +114,22 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct Pipe {                            // ring position shared by every role (all iterate the same sequence)
-    int stage = 0; uint32_t phase = 0;
-    __device__ __forceinline__ void advance(int stages) { if (++stage == stages) { stage = 0; phase ^= 1; } }
+struct Ring {                            // ring position; every role walks the same sequence
+    int slot = 0; uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) { if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 
+// split one float pair into fp16 hi / lo words
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __half2 h = __floats2half2_rn(a, b);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
 // ------------------------------------------------------------------------------------------ kernel
+template <int NDIM>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -124,26 +138,30 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_tile_bytes = p.BN * BK * 2;
-    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-    uint8_t* tables = smem + (size_t)p.stages * stage_bytes;
-    double* At_s = (double*)tables;                                         // (KC_pad/2) x n
-    float* mp_s = (float*)(At_s + (size_t)(p.KC_pad / 2) * p.n);            // KC_pad
+    const int b_slot_bytes = 2 * b_tile_bytes;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + NA * A_SLOT_BYTES;
+    uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
+    double* At_s = (double*)tables;                                         // (KC_pad/2) x NDIM
+    float* mp_s = (float*)(At_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
     float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][4 quarters][128]
-    uint64_t* bars = (uint64_t*)(mu_part + 2 * 4 * BM);                     // offset is a multiple of 8 bytes (see table_bytes)
-    // barrier map: full_a[s], full_b[s], empty[s] for s < stages ; tmem_full[2] ; tmem_empty[2]
+    uint64_t* bars = (uint64_t*)(mu_part + 2 * 4 * BM);
+    // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
-    auto full_a = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
-    auto empty_ = [&](int s) { return bar0 + 8u * (uint32_t)(2 * p.stages + s); };
-    auto tmem_full = [&](int b) { return bar0 + 8u * (uint32_t)(3 * p.stages + b); };
-    auto tmem_empty = [&](int b) { return bar0 + 8u * (uint32_t)(3 * p.stages + 2 + b); };
-    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * p.stages + 4);
+    auto a_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (uint32_t)(NA + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (uint32_t)(2 * NA + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * NA + p.nb + s); };
+    auto tmem_full = [&](int b) { return bar0 + 8u * (uint32_t)(2 * NA + 2 * p.nb + b); };
+    auto tmem_empty = [&](int b) { return bar0 + 8u * (uint32_t)(2 * NA + 2 * p.nb + 2 + b); };
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    for (int i = threadIdx.x; i < (p.KC_pad / 2) * p.n; i += THREADS) At_s[i] = p.At_op[i];
+    for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) At_s[i] = p.At_op[i];
     for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     if (warp == WARP_TMA && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), GEN_THREADS); mbar_init(full_b(s), 1); mbar_init(empty_(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_THREADS); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS * 32); }
         fence_barrier_init();
     }
@@ -157,54 +175,65 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     const long long n_tiles = (p.N + BM - 1) / BM;
+    const int n_pairs = (p.n_chunks + 1) / 2;
+    // accumulator of chunk cc of a pair: with a single chunk per tile the two buffers alternate by tile instead
+    auto acc_of = [&](int tile_iter, int cc) { return p.n_chunks == 1 ? (tile_iter & 1) : cc; };
 
     if (warp == WARP_TMA) {
-        // ================================ TMA producer ================================
+        // ================================ TMA producer (B ring) ================================
         if (lane == 0) {
-            Pipe pipe;
+            Ring rb;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int c = 0; c < p.n_chunks; ++c)
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
-                        mbar_wait_relaxed(empty_(pipe.stage), pipe.phase ^ 1);
-                        uint8_t* st = smem + (size_t)pipe.stage * stage_bytes;
-                        mbar_expect_tx(full_b(pipe.stage), 2u * (uint32_t)b_tile_bytes);
-                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &map_hi, full_b(pipe.stage), kb * BK, c * p.BN);
-                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &map_lo, full_b(pipe.stage), kb * BK, c * p.BN);
-                        pipe.advance(p.stages);
-                    }
+                for (int pr = 0; pr < n_pairs; ++pr)
+                    for (int kb = 0; kb < p.n_kb; ++kb)
+                        for (int cc = 0; cc < 2 && 2 * pr + cc < p.n_chunks; ++cc) {
+                            mbar_wait_relaxed(b_empty(rb.slot), rb.phase ^ 1);
+                            uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
+                            mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
+                            tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, (2 * pr + cc) * p.BN);
+                            tma_load_2d(smem_u32(st + b_tile_bytes), &map_lo, b_full(rb.slot), kb * BK, (2 * pr + cc) * p.BN);
+                            rb.advance(p.nb);
+                        }
         }
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BM, p.BN);
-            Pipe pipe;
+            Ring ra, rb;
             uint32_t acc_phase[2] = {0, 0};
-            int acc_iter = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int c = 0; c < p.n_chunks; ++c, ++acc_iter) {
-                    const int buf = acc_iter & 1;
-                    mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);       // epilogue drained this accumulator
-                    acc_phase[buf] ^= 1;
+            int tile_iter = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
+                for (int pr = 0; pr < n_pairs; ++pr) {
+                    const int ncc = (2 * pr + 1 < p.n_chunks) ? 2 : 1;
+                    for (int cc = 0; cc < ncc; ++cc) {                    // the epilogue must have drained the accumulators
+                        const int buf = acc_of(tile_iter, cc);
+                        mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);
+                        acc_phase[buf] ^= 1;
+                    }
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
                     for (int kb = 0; kb < p.n_kb; ++kb) {
-                        mbar_wait(full_a(pipe.stage), pipe.phase);
-                        mbar_wait(full_b(pipe.stage), pipe.phase);
-                        tc_fence_after();
-                        const uint32_t st = smem_u32(smem + (size_t)pipe.stage * stage_bytes);
-                        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE_BYTES);
-                        const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE_BYTES);
-                        const uint64_t b_lo = make_desc_sw128(st + 2 * A_TILE_BYTES + b_tile_bytes);
+                        mbar_wait(a_full(ra.slot), ra.phase);
+                        const uint32_t sa = smem_u32(a_ring + (size_t)ra.slot * A_SLOT_BYTES);
+                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                        for (int cc = 0; cc < ncc; ++cc) {
+                            mbar_wait(b_full(rb.slot), rb.phase);
+                            tc_fence_after();
+                            const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
+                            const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + b_tile_bytes);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(acc_of(tile_iter, cc) * ACC_COLS);
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk) {
-                            const uint64_t off = (uint64_t)((kk * 32) >> 4);        // 16 fp16 = 32 bytes along K
-                            umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb | kk) != 0);
-                            umma_f16(d_tmem, a_hi + off, b_lo + off, idesc, 1);
-                            umma_f16(d_tmem, a_lo + off, b_hi + off, idesc, 1);
+                            for (int kk = 0; kk < BK / 16; ++kk) {
+                                const uint64_t off = (uint64_t)((kk * 32) >> 4);    // 16 fp16 = 32 bytes along K
+                                umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb | kk) != 0);
+                                umma_f16(d_tmem, a_hi + off, b_lo + off, idesc, 1);
+                                umma_f16(d_tmem, a_lo + off, b_hi + off, idesc, 1);
+                            }
+                            umma_commit(b_empty(rb.slot));                // frees the B slot when these MMAs retire
+                            if (kb == p.n_kb - 1) umma_commit(tmem_full(acc_of(tile_iter, cc)));
+                            rb.advance(p.nb);
                         }
-                        umma_commit(empty_(pipe.stage));                  // frees the stage when these MMAs retire
-                        if (kb == p.n_kb - 1) umma_commit(tmem_full(buf));
-                        pipe.advance(p.stages);
+                        umma_commit(a_empty(ra.slot));                    // frees the A slot
+                        ra.advance(NA);
                     }
                 }
         }
@@ -213,22 +242,28 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         const int quad = warp & 3;                                        // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;
         uint32_t acc_phase[2] = {0, 0};
-        int acc_iter = 0, tile_iter = 0;
+        int tile_iter = 0;
         unsigned long long my_best = 0ull;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             float q = 0.f;
-            for (int c = 0; c < p.n_chunks; ++c, ++acc_iter) {
-                const int buf = acc_iter & 1;
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const int buf = acc_of(tile_iter, c & 1);
                 mbar_wait_relaxed(tmem_full(buf), acc_phase[buf]);
                 acc_phase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-                for (int g = 0; g < p.BN; g += 16) {
-                    uint32_t v[16];
+                for (int g = 0; g < p.BN; g += 32) {                      // BN % 16 == 0
+                    uint32_t v[32];
                     tmem_ld16(taddr + (uint32_t)g, v);
+                    const bool two = g + 16 < p.BN;
+                    if (two) tmem_ld16(taddr + (uint32_t)g + 16u, v + 16);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { float y = __uint_as_float(v[i]); q = fmaf(y, y, q); }
+                    if (two) {
+#pragma unroll
+                        for (int i = 16; i < 32; ++i) { float y = __uint_as_float(v[i]); q = fmaf(y, y, q); }
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(tmem_empty(buf));
@@ -253,74 +288,97 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         }
         if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
     } else {
-        // ================================ psi generators ================================
-        const int gt = threadIdx.x - WARP_GEN0 * 32;
-        const int row = gt & (BM - 1), quarter = gt >> 7;                 // quarter q: frequencies 8q .. 8q+7 of the k-block
-        const int n = p.n;
-        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-        const uint32_t sw = (uint32_t)(row & 7);
-        // one 16-byte chunk of cos (chunk q) and one of sin (chunk 4+q) per stage, XOR-swizzled by the row
+        // ================================ psi generators (A ring) ================================
+        const int gw = warp - WARP_GEN0;                                  // 0..7
+        const int r0 = (gw & 1) * 32 + lane, quarter = gw >> 1;           // rows r0 and r0 + 64; frequencies 8q .. 8q+7
+        const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128);
+        const uint32_t sw = (uint32_t)(r0 & 7);                           // (r0 + 64) & 7 == r0 & 7
+        // one 16-byte chunk of cos (chunk q) and one of sin (chunk 4+q) per row and stage, XOR-swizzled by the row
         const uint32_t off_cos = row_off + (((uint32_t)quarter ^ sw) << 4);
         const uint32_t off_sin = row_off + (((uint32_t)(quarter + 4) ^ sw) << 4);
-        Pipe pipe;
+        constexpr uint32_t ROW1 = 64 * 128;                               // byte offset of row r0 + 64 inside a tile
+        Ring ra;
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            double x[MAX_N];
-            const long long gi = tile * BM + row;
+            double x0[NDIM], x1[NDIM];
+            const long long g0 = tile * BM + r0, g1 = g0 + 64;
 #pragma unroll
-            for (int a = 0; a < MAX_N; ++a) {
-                x[a] = 0.0;
-                if (a < n && gi < p.N)
-                    x[a] = p.x_f64 ? ((const double*)p.x)[gi * n + a] : (double)((const float*)p.x)[gi * n + a];
+            for (int a = 0; a < NDIM; ++a) {
+                x0[a] = 0.0; x1[a] = 0.0;
+                if (g0 < p.N) x0[a] = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                if (g1 < p.N) x1[a] = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
             }
-            float mu = 0.f;
-            for (int c = 0; c < p.n_chunks; ++c)
+            float mu0 = 0.f, mu1 = 0.f;
+            for (int pr = 0; pr < n_pairs; ++pr)
                 for (int kb = 0; kb < p.n_kb; ++kb) {
-                    const double* Ablk = At_s + (size_t)(kb * 32 + quarter * 8) * n;
-                    float cs[8], sn[8];
+                    const double* Ablk = At_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
+                    double t0[8], t1[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const double* Af = Ablk + (size_t)i * n;
-                        double t = 0.0;
+                    for (int i = 0; i < 8; ++i) { t0[i] = 0.0; t1[i] = 0.0; }
 #pragma unroll
-                        for (int a = 0; a < MAX_N; ++a)
-                            if (a < n) t = fma(Af[a], x[a], t);
-                        float tr = (float)(t - rint(t));                  // exact reduction to [-1/2, 1/2] turns
-                        float ang = tr * 6.283185307179586f;
-                        cs[i] = __cosf(ang);
-                        sn[i] = __sinf(ang);
-                    }
-                    if (c == 0) {
-                        const float* mcos = mp_s + kb * BK + quarter * 8;
+                    for (int a = 0; a < NDIM; ++a) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            mu = fmaf(mcos[i], cs[i], mu);
-                            mu = fmaf(mcos[32 + i], sn[i], mu);
+                            const double Afa = Ablk[i * NDIM + a];        // one broadcast read feeds both rows
+                            t0[i] = fma(Afa, x0[a], t0[i]);
+                            t1[i] = fma(Afa, x1[a], t1[i]);
                         }
                     }
-                    uint32_t ch[4], cl[4], sh[4], sl[4];
+                    uint32_t w0[16], w1[16];                              // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
+                    {
+                        float cs[8], sn[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        __half2 h = __floats2half2_rn(cs[2 * i], cs[2 * i + 1]);
-                        float2 hf = __half22float2(h);
-                        __half2 l = __floats2half2_rn(cs[2 * i] - hf.x, cs[2 * i + 1] - hf.y);
-                        ch[i] = *reinterpret_cast<uint32_t*>(&h); cl[i] = *reinterpret_cast<uint32_t*>(&l);
-                        h = __floats2half2_rn(sn[2 * i], sn[2 * i + 1]);
-                        hf = __half22float2(h);
-                        l = __floats2half2_rn(sn[2 * i] - hf.x, sn[2 * i + 1] - hf.y);
-                        sh[i] = *reinterpret_cast<uint32_t*>(&h); sl[i] = *reinterpret_cast<uint32_t*>(&l);
+                        for (int i = 0; i < 8; ++i) {
+                            float ang = (float)(t0[i] - rint(t0[i])) * 6.283185307179586f;   // exact reduction to [-pi, pi]
+                            cs[i] = __cosf(ang); sn[i] = __sinf(ang);
+                        }
+                        if (pr == 0) {
+                            const float* mcos = mp_s + kb * BK + quarter * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { mu0 = fmaf(mcos[i], cs[i], mu0); mu0 = fmaf(mcos[32 + i], sn[i], mu0); }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            split_pair(cs[2 * i], cs[2 * i + 1], w0[i], w0[4 + i]);
+                            split_pair(sn[2 * i], sn[2 * i + 1], w0[8 + i], w0[12 + i]);
+                        }
+                    }
+                    {
+                        float cs[8], sn[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float ang = (float)(t1[i] - rint(t1[i])) * 6.283185307179586f;
+                            cs[i] = __cosf(ang); sn[i] = __sinf(ang);
+                        }
+                        if (pr == 0) {
+                            const float* mcos = mp_s + kb * BK + quarter * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { mu1 = fmaf(mcos[i], cs[i], mu1); mu1 = fmaf(mcos[32 + i], sn[i], mu1); }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            split_pair(cs[2 * i], cs[2 * i + 1], w1[i], w1[4 + i]);
+                            split_pair(sn[2 * i], sn[2 * i + 1], w1[8 + i], w1[12 + i]);
+                        }
                     }
                     // values are ready in registers before the slot is claimed: the wait overlaps the math above
-                    mbar_wait(empty_(pipe.stage), pipe.phase ^ 1);
-                    uint8_t* st = smem + (size_t)pipe.stage * stage_bytes;
-                    *reinterpret_cast<uint4*>(st + off_cos) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-                    *reinterpret_cast<uint4*>(st + off_sin) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_cos) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
-                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_sin) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
-                    if (c == 0 && kb == p.n_kb - 1) mu_part[(tile_iter & 1) * 4 * BM + quarter * BM + row] = mu;
+                    mbar_wait(a_empty(ra.slot), ra.phase ^ 1);
+                    uint8_t* st = a_ring + (size_t)ra.slot * A_SLOT_BYTES;
+                    *reinterpret_cast<uint4*>(st + off_cos) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_cos) = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+                    *reinterpret_cast<uint4*>(st + off_sin) = make_uint4(w0[8], w0[9], w0[10], w0[11]);
+                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_sin) = make_uint4(w0[12], w0[13], w0[14], w0[15]);
+                    *reinterpret_cast<uint4*>(st + ROW1 + off_cos) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                    *reinterpret_cast<uint4*>(st + ROW1 + A_TILE_BYTES + off_cos) = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+                    *reinterpret_cast<uint4*>(st + ROW1 + off_sin) = make_uint4(w1[8], w1[9], w1[10], w1[11]);
+                    *reinterpret_cast<uint4*>(st + ROW1 + A_TILE_BYTES + off_sin) = make_uint4(w1[12], w1[13], w1[14], w1[15]);
+                    if (pr == 0 && kb == p.n_kb - 1) {
+                        float* mpart = mu_part + (tile_iter & 1) * 4 * BM + quarter * BM;
+                        mpart[r0] = mu0; mpart[r0 + 64] = mu1;
+                    }
                     fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core
-                    mbar_arrive(full_a(pipe.stage));
-                    pipe.advance(p.stages);
+                    mbar_arrive(a_full(ra.slot));
+                    ra.advance(NA);
                 }
         }
     }
@@ -341,14 +399,24 @@ struct UmmaState {
     const void* rh = nullptr; const void* rl = nullptr;
     int KC_pad = 0, NJ_pad = 0, BN = 0;
     int max_smem = 0;
-    bool attr_set = false;
+    int attr_set_n = 0;
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
     return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(double) + (size_t)ctx->KC_pad * sizeof(float) +
-           2 * 4 * BM * sizeof(float) + (3 * 4 + 4) * 8 + 16;
+           2 * 4 * BM * sizeof(float) + (2 * NA + 2 * MAX_NB + 4) * 8 + 16;
 }
-size_t stage_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)A_TILE_BYTES + 2 * (size_t)ctx->BN * BK * 2; }
+size_t b_slot_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)ctx->BN * BK * 2; }
+
+typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
+kernel_fn kernel_for(int n) {
+    switch (n) {
+        case 1: return k_score_umma<1>; case 2: return k_score_umma<2>; case 3: return k_score_umma<3>;
+        case 4: return k_score_umma<4>; case 5: return k_score_umma<5>; case 6: return k_score_umma<6>;
+        case 7: return k_score_umma<7>; case 8: return k_score_umma<8>;
+    }
+    return nullptr;
+}
 
 int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
     cuuint64_t gdim[2] = {(cuuint64_t)ctx->KC_pad, (cuuint64_t)ctx->NJ_pad};
@@ -383,7 +451,7 @@ int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    if (table_bytes(ctx) + 2 * stage_bytes_of(ctx) + 1024 > (size_t)max_smem) return 0;
+    if (table_bytes(ctx) + NA * A_SLOT_BYTES + 2 * b_slot_bytes_of(ctx) + 1024 > (size_t)max_smem) return 0;
     return 1;
 }
 
@@ -401,26 +469,28 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
         us->rh = ctx->Rh; us->rl = ctx->Rl; us->KC_pad = ctx->KC_pad; us->NJ_pad = ctx->NJ_pad; us->BN = ctx->BN;
     }
     if (!us->max_smem) cudaDeviceGetAttribute(&us->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    const size_t tb = table_bytes(ctx), sb = stage_bytes_of(ctx);
-    int stages = (int)(((size_t)us->max_smem - 1024 - tb) / sb);
-    if (stages > 4) stages = 4;
-    if (stages < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two stages");
-    const size_t smem = 1024 + (size_t)stages * sb + tb;
-    if (!us->attr_set) {
-        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, us->max_smem));
-        us->attr_set = true;
+    const size_t tb = table_bytes(ctx), sb = b_slot_bytes_of(ctx);
+    int nb = (int)(((size_t)us->max_smem - 1024 - tb - NA * A_SLOT_BYTES) / sb);
+    if (nb > MAX_NB) nb = MAX_NB;
+    if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two B slots");
+    const size_t smem = 1024 + NA * A_SLOT_BYTES + (size_t)nb * sb + tb;
+    kernel_fn kern = kernel_for(ctx->n);
+    if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: domain dimension %d not instantiated", ctx->n);
+    if (us->attr_set_n != ctx->n) {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, us->max_smem));
+        us->attr_set_n = ctx->n;
     }
     Params p;
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
     p.At_op = ctx->At_op; p.mp_op = ctx->mp_op;
-    p.n = ctx->n; p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
-    p.n_kb = ctx->KC_pad / BK; p.stages = stages;
+    p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
+    p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    k_score_umma<<<grid, THREADS, smem, st>>>(us->map_hi, us->map_lo, p);
+    kern<<<grid, THREADS, smem, st>>>(us->map_hi, us->map_lo, p);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }
