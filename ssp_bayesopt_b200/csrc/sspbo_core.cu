@@ -400,7 +400,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     sspbo_umma_release(ctx);
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
-    dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->At_op);
+    dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op);
     delete ctx;
 }
 
@@ -442,11 +442,16 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     {   // frequency table of the tcgen05 scorer: row f = A_turns of frequency f (f = 0: DC, f > K: padding) -> zeros
         int kc, bn, nc, nj;
         sspbo_umma_dims(K, &kc, &bn, &nc, &nj);
-        std::vector<double> op((size_t)(kc / 2) * n, 0.0);
+        std::vector<long long> op((size_t)(kc / 2) * n, 0ll);
+        ctx->umma_range_ok = true;
         for (int f = 1; f <= K; ++f)
-            for (int a = 0; a < n; ++a) op[(size_t)f * n + a] = At[(size_t)(f - 1) * n + a];
-        if ((rc = dev_alloc(ctx, &ctx->At_op, op.size()))) return rc;
-        SSPBO_CUDA(ctx, cudaMemcpy(ctx->At_op, op.data(), op.size() * sizeof(double), cudaMemcpyHostToDevice));
+            for (int a = 0; a < n; ++a) {
+                double t = At[(size_t)(f - 1) * n + a];
+                if (!(fabs(t) < 2147483648.0)) { ctx->umma_range_ok = false; t = 0.0; }
+                op[(size_t)f * n + a] = llrint(t * 4294967296.0);                  // Q31.32 turns per unit of x
+            }
+        if ((rc = dev_alloc(ctx, &ctx->Aq_op, op.size()))) return rc;
+        SSPBO_CUDA(ctx, cudaMemcpy(ctx->Aq_op, op.data(), op.size() * sizeof(long long), cudaMemcpyHostToDevice));
     }
     ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
     return SSPBO_OK;

@@ -22,6 +22,7 @@ struct sspbo_ctx {
     double* tau_turns = nullptr;     // L x K : trajectory time phases in turns (nullptr when L == 1)
     float*  tau_turns_f32 = nullptr;
     double2* twiddle = nullptr;      // d entries (cos, sin)(2 pi i / d), float64
+    bool umma_range_ok = true;       // every |A_turns| < 2^31 (fixed-point phase of the tcgen05 scorer)
     double max_turns = 0.0;          // host bound on |theta| in turns per unit |x|_inf (sum_a |A_turns[k][a]|, max over k)
 
     // ---- BLR (phi-space, float64) ----
@@ -40,7 +41,7 @@ struct sspbo_ctx {
     __half* Rh = nullptr;            // hi(R[j][psi_index(c)] * r_scale)
     __half* Rl = nullptr;            // lo part (value - hi)
     float*  mp_op = nullptr;         // m' in operand order (KC_pad)
-    double* At_op = nullptr;         // (KC_pad/2) x n float64: A_turns row of frequency f (row 0 and f > K are zero)
+    long long* Aq_op = nullptr;      // (KC_pad/2) x n, Q31.32 fixed point: A_turns row of frequency f (row 0 and f > K are zero)
     int KC_pad = 0, BN = 0, n_chunks = 0, NJ_pad = 0;
     double r_scale = 1.0;
     bool operands_dirty = true;      // Rt_f32 / Rh / Rl / mp_f32 need a refresh from R, m

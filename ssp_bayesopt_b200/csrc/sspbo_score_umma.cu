@@ -1,11 +1,13 @@
 // K2, tcgen05/TMEM engine: fused encode + BLR acquisition + argmax for sm_100a.
 //
 // Per CTA (persistent, one per SM) and per tile of 128 candidates:
-//   generator warps  theta_f = A_f . x in float64 turns, exact range reduction, MUFU sin/cos -> the psi k-block
-//                    (A operand, 128 x 64) written straight into 128B-swizzled shared memory as a split-fp16 pair
-//                    (hi, lo); psi never exists in HBM.  Each thread owns 2 candidate rows x 8 frequencies, so one
-//                    shared-memory read of a phase-matrix entry feeds two float64 FMA chains.  The first pass also
-//                    accumulates mu = m' . psi in float32.
+//   generator warps  theta_f = A_f . x in 64-bit fixed point: A and x are Q31.32 integers, the low 64 bits of the
+//                    sum of products are the phase in turns modulo 1 (range reduction is the integer wrap-around,
+//                    exact for any |x| < 2^31; resolution 2^-33 turns per unit of A or x), then MUFU sin/cos -> the
+//                    psi k-block (A operand, 128 x 64) written straight into 128B-swizzled shared memory as a
+//                    split-fp16 pair (hi, lo); psi never exists in HBM.  Each thread owns 2 candidate rows x 8
+//                    frequencies, so one shared-memory read of a phase-matrix entry feeds two multiply-add chains.
+//                    The first pass also accumulates mu = m' . psi in float32.
 //   TMA warp         streams the 64-column slabs of the split-fp16 factor R (hi, lo) from L2 into the B ring.
 //   MMA warp         one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16, fp16 x fp16 -> fp32 in TMEM):
 //                    Y += psi_hi R_hi^T + psi_hi R_lo^T + psi_lo R_hi^T   (3-term split: ~2^-22 operand precision)
@@ -38,7 +40,7 @@ constexpr int ACC_COLS = 256;                                    // columns per 
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
-    const double* At_op; const float* mp_op;
+    const long long* Aq_op; const float* mp_op;
     int K, KC_pad, BN, n_chunks, n_kb, nb;
     float inv_beta, lam, gamma_t, inv_rscale2;
     float *mu, *var, *acq;
@@ -142,8 +144,8 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + NA * A_SLOT_BYTES;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
-    double* At_s = (double*)tables;                                         // (KC_pad/2) x NDIM
-    float* mp_s = (float*)(At_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
+    long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM, Q31.32 turns per unit
+    float* mp_s = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
     float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][4 quarters][128]
     uint64_t* bars = (uint64_t*)(mu_part + 2 * 4 * BM);
     // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
@@ -157,7 +159,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) At_s[i] = p.At_op[i];
+    for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
     for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     if (warp == WARP_TMA && lane == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_THREADS); mbar_init(a_empty(s), 1); }
@@ -300,28 +302,30 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         Ring ra;
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            double x0[NDIM], x1[NDIM];
+            unsigned long long x0[NDIM], x1[NDIM];                       // Q31.32 candidates (two's complement)
             const long long g0 = tile * BM + r0, g1 = g0 + 64;
 #pragma unroll
             for (int a = 0; a < NDIM; ++a) {
-                x0[a] = 0.0; x1[a] = 0.0;
-                if (g0 < p.N) x0[a] = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                if (g1 < p.N) x1[a] = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
+                double v0 = 0.0, v1 = 0.0;
+                if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
+                x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                x1[a] = (unsigned long long)__double2ll_rn(v1 * 4294967296.0);
             }
             float mu0 = 0.f, mu1 = 0.f;
             for (int pr = 0; pr < n_pairs; ++pr)
                 for (int kb = 0; kb < p.n_kb; ++kb) {
-                    const double* Ablk = At_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
-                    double t0[8], t1[8];
+                    const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
+                    unsigned long long t0[8], t1[8];                      // phase in turns, Q0.64, wraps modulo 1
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { t0[i] = 0.0; t1[i] = 0.0; }
+                    for (int i = 0; i < 8; ++i) { t0[i] = 0ull; t1[i] = 0ull; }
 #pragma unroll
                     for (int a = 0; a < NDIM; ++a) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const double Afa = Ablk[i * NDIM + a];        // one broadcast read feeds both rows
-                            t0[i] = fma(Afa, x0[a], t0[i]);
-                            t1[i] = fma(Afa, x1[a], t1[i]);
+                            const unsigned long long Afa = Ablk[i * NDIM + a];   // one broadcast read feeds both rows
+                            t0[i] += Afa * x0[a];
+                            t1[i] += Afa * x1[a];
                         }
                     }
                     uint32_t w0[16], w1[16];                              // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
@@ -329,7 +333,8 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         float cs[8], sn[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float ang = (float)(t0[i] - rint(t0[i])) * 6.283185307179586f;   // exact reduction to [-pi, pi]
+                            // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
+                            float ang = (float)(int)(t0[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
                             cs[i] = __cosf(ang); sn[i] = __sinf(ang);
                         }
                         if (pr == 0) {
@@ -347,7 +352,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         float cs[8], sn[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float ang = (float)(t1[i] - rint(t1[i])) * 6.283185307179586f;
+                            float ang = (float)(int)(t1[i] >> 32) * 1.4629180792671596e-9f;
                             cs[i] = __cosf(ang); sn[i] = __sinf(ang);
                         }
                         if (pr == 0) {
@@ -403,7 +408,7 @@ struct UmmaState {
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
-    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(double) + (size_t)ctx->KC_pad * sizeof(float) +
+    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
            2 * 4 * BM * sizeof(float) + (2 * NA + 2 * MAX_NB + 4) * 8 + 16;
 }
 size_t b_slot_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)ctx->BN * BK * 2; }
@@ -446,7 +451,7 @@ int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
 }  // namespace
 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
-    if (!ctx->has_factor || ctx->L != 1 || ctx->n > MAX_N || ctx->K < 1) return 0;
+    if (!ctx->has_factor || ctx->L != 1 || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok) return 0;
     int major = 0;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
     int max_smem = 0;
@@ -482,7 +487,7 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     }
     Params p;
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
-    p.At_op = ctx->At_op; p.mp_op = ctx->mp_op;
+    p.Aq_op = ctx->Aq_op; p.mp_op = ctx->mp_op;
     p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
     p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
