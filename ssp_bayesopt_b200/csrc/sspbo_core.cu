@@ -101,7 +101,7 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
 // (s0, sk) = (1, 1) maps phi -> psi ;  (1/d, 2/d) maps m -> m' = B^T m.
 // =====================================================================================
 __global__ void k_analysis(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ twiddle,
-                           int K, double s0, double sk) {
+                           int K, double s0, double sk, const int* __restrict__ dest) {
     __shared__ double red[64];
     const int d = 2 * K + 1;
     const int k = blockIdx.x;                           // 0..K
@@ -114,9 +114,9 @@ __global__ void k_analysis(const double* __restrict__ in, double* __restrict__ o
     }
     c = block_sum(c, red);
     s = block_sum(s, red + 32);
-    if (threadIdx.x == 0) {
-        if (k == 0) out[0] = s0 * c;
-        else { out[k] = sk * c; out[K + k] = -sk * s; }
+    if (threadIdx.x == 0) {                 // dest (optional) scatters natural psi indices to permuted ranks
+        if (k == 0) out[dest ? dest[0] : 0] = s0 * c;
+        else { out[dest ? dest[k] : k] = sk * c; out[dest ? dest[K + k] : K + k] = -sk * s; }
     }
 }
 
@@ -149,22 +149,14 @@ __global__ void k_gemv_cols(const double* __restrict__ M, const double* __restri
         y[col] = t;
     }
 }
-// scalars for one observation.  scal[0] = coefS = beta / (1 + beta phi.v)   (Sherman-Morrison, blr.py:64-67)
-//                               scal[1] = kappa = beta / (sqrt(s) (1 + sqrt(s))), s = 1 + beta y.y  (factor update)
-//                               scal[2] = phi . v  (= phi^T S phi before the update, the prior variance term)
-__global__ void k_update_scalars(const double* __restrict__ phi, const double* __restrict__ v, const double* __restrict__ y,
-                                 int d, double beta, double* __restrict__ scal) {
-    __shared__ double red[64];
-    double pv = 0.0, yy = 0.0;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) { pv += phi[j] * v[j]; yy += y[j] * y[j]; }
-    pv = block_sum(pv, red);
-    yy = block_sum(yy, red + 32);
-    if (threadIdx.x == 0) {
-        scal[0] = beta / (1.0 + beta * pv);
-        double s = 1.0 + beta * yy, rs = sqrt(s);
-        scal[1] = beta / (rs * (1.0 + rs));
-        scal[2] = pv;
-    }
+// Sherman-Morrison coefficient of one observation (blr.py:64-67): out[0] = beta / (1 + beta a.b), out[1] = a.b
+__global__ void k_update_scalars(const double* __restrict__ a, const double* __restrict__ b, int d, double beta,
+                                 double* __restrict__ out) {
+    __shared__ double red[32];
+    double ab = 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) ab += a[j] * b[j];
+    ab = block_sum(ab, red);
+    if (threadIdx.x == 0) { out[0] = beta / (1.0 + beta * ab); out[1] = ab; }
 }
 // M[i][j] += sign * coef * a[i] * b[j]   (coef read from device memory, or the immediate when coef_dev == nullptr)
 __global__ void k_rank1(double* __restrict__ M, const double* __restrict__ a, const double* __restrict__ b, int d,
@@ -184,47 +176,117 @@ __global__ void k_set_diag(double* __restrict__ M, int d, double v0, double v) {
     if (j < d) M[(size_t)j * d + j] = (j == 0) ? v0 : v;
 }
 
-// refresh of the scoring operands from the float64 masters
-__global__ void k_refresh_operands(const double* __restrict__ R, const double* __restrict__ mp, int d, int dp,
-                                   float* __restrict__ Rt_f32, float* __restrict__ mp_f32) {
-    __shared__ double tile[32][33];
-    int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-    // read R[j][k] coalesced along k
+// =====================================================================================
+// Blocked right-looking Cholesky (lower, in place, float64) of the permuted psi-space covariance.
+// d^3/3 flops per refresh (3.6e8 at d=1023) in three small kernels per 32-column panel.
+// =====================================================================================
+constexpr int CH_NB = 32;
+// diagonal block: L_kk = chol(A_kk), one CTA of 32x32 threads
+__global__ void k_chol_diag(double* __restrict__ A, int d, int k0) {
+    __shared__ double a[CH_NB][CH_NB + 1];
+    const int nb = min(CH_NB, d - k0);
+    const int r = threadIdx.y, c = threadIdx.x;
+    a[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + r) * d + k0 + c] : (r == c ? 1.0 : 0.0);
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        if (r == k && c == k) a[k][k] = sqrt(fmax(a[k][k], 1e-300));
+        __syncthreads();
+        if (c == k && r > k) a[r][k] /= a[k][k];
+        __syncthreads();
+        if (r > k && c > k && c <= r) a[r][c] -= a[r][k] * a[c][k];
+        __syncthreads();
+    }
+    if (r < nb && c < nb && c <= r) A[(size_t)(k0 + r) * d + k0 + c] = a[r][c];
+}
+// panel below the diagonal block: L_ik = A_ik L_kk^-T, one thread per row
+__global__ void k_chol_trsm(double* __restrict__ A, int d, int k0) {
+    __shared__ double l[CH_NB][CH_NB + 1];
+    const int nb = min(CH_NB, d - k0);
+    for (int i = threadIdx.x; i < CH_NB * CH_NB; i += blockDim.x) {
+        int r = i / CH_NB, c = i % CH_NB;
+        l[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * d + k0 + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= d) return;
+    double x[CH_NB];
+#pragma unroll
+    for (int c = 0; c < CH_NB; ++c) x[c] = (c < nb) ? A[(size_t)row * d + k0 + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CH_NB; ++c) {
+        double acc = x[c];
+#pragma unroll
+        for (int t = 0; t < c; ++t) acc -= x[t] * l[c][t];
+        x[c] = acc / l[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < CH_NB; ++c)
+        if (c < nb) A[(size_t)row * d + k0 + c] = x[c];
+}
+// trailing update (lower tiles only): A_ij -= sum_t L_it L_jt, 32x32 tile per CTA of 32x8 threads
+__global__ void k_chol_syrk(double* __restrict__ A, int d, int k0) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj > ti) return;
+    __shared__ double li[32][CH_NB + 1], lj[32][CH_NB + 1];
+    const int base = k0 + CH_NB;
+    const int i0 = base + ti * 32, j0 = base + tj * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
-        int j = j0 + r, k = k0 + threadIdx.x;
-        double v = (j < d && k < d) ? R[(size_t)j * d + k] : 0.0;
-        tile[r][threadIdx.x] = v;
+        int gi = i0 + r, gj = j0 + r;
+        li[r][threadIdx.x] = (gi < d) ? A[(size_t)gi * d + k0 + threadIdx.x] : 0.0;
+        lj[r][threadIdx.x] = (gj < d) ? A[(size_t)gj * d + k0 + threadIdx.x] : 0.0;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
-        int k = k0 + r, j = j0 + threadIdx.x;
-        if (k < dp && j < dp) Rt_f32[(size_t)k * dp + j] = (float)tile[threadIdx.x][r];
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
-        for (int i = threadIdx.y * 32 + threadIdx.x; i < dp; i += 256) mp_f32[i] = (i < d) ? (float)mp[i] : 0.f;
+        int gi = i0 + r, gj = j0 + threadIdx.x;
+        if (gi < d && gj < d && gj <= gi) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < CH_NB; ++t) acc += li[r][t] * lj[threadIdx.x][t];
+            A[(size_t)gi * d + gj] -= acc;
+        }
     }
 }
 
-// split-fp16 operands of the tcgen05 scorer in operand order (sspbo_internal.cuh)
-__device__ __forceinline__ int psi_index_of_column(int c, int K) {
-    int b = c >> 6, i = c & 63;
-    int f = 32 * b + (i & 31);
-    if (f > K) return -1;
-    if (i < 32) return f;                    // DC (f = 0) or cos_f
-    return f == 0 ? -1 : K + f;              // sin_f ; sin of the DC term is identically zero
+// refresh of the scoring operands from the float64 factor L (lower) and m'
+//   SIMT image : Rt_f32[perm[kk] * dp + j] = L[kk][j]   (row = natural psi index, column = output row j)
+__global__ void k_refresh_operands(const double* __restrict__ L, const double* __restrict__ mp, const int* __restrict__ perm,
+                                   int d, int dp, float* __restrict__ Rt_f32, float* __restrict__ mp_f32) {
+    const int kk = blockIdx.y;
+    const int row = perm[kk];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < dp; j += gridDim.x * blockDim.x)
+        Rt_f32[(size_t)row * dp + j] = (j <= kk) ? (float)L[(size_t)kk * d + j] : 0.f;
+    if (kk == 0)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dp; i += gridDim.x * blockDim.x)
+            mp_f32[i] = (i < d) ? (float)mp[i] : 0.f;
 }
-__global__ void k_refresh_umma_operands(const double* __restrict__ R, const double* __restrict__ mp, int d, int K,
-                                        int KC_pad, int NJ_pad, double r_scale, __half* __restrict__ Rh,
-                                        __half* __restrict__ Rl, float* __restrict__ mp_op) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y;
-    if (c >= KC_pad) return;
-    int p = psi_index_of_column(c, K);
-    double v = (p >= 0 && j < d) ? R[(size_t)j * d + p] * r_scale : 0.0;
-    __half h = __double2half(v);
-    Rh[(size_t)j * KC_pad + c] = h;
-    Rl[(size_t)j * KC_pad + c] = __double2half(v - (double)__half2float(h));
-    if (j == 0) mp_op[c] = (p >= 0) ? (float)mp[p] : 0.f;
+// split-fp16 operands of the tcgen05 scorer in operand order (sspbo_internal.cuh):
+//   Rh/Rl[j * KC_pad + col_of_rank[kk]] = split(L[kk][j] * r_scale) for j <= kk; everything else stays zero
+__global__ void k_refresh_umma_operands(const double* __restrict__ L, const double* __restrict__ mp,
+                                        const int* __restrict__ perm, const int* __restrict__ col_of_rank, int d,
+                                        int KC_pad, double r_scale, __half* __restrict__ Rh, __half* __restrict__ Rl,
+                                        float* __restrict__ mp_op) {
+    __shared__ double tile[32][33];
+    const int kk0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (j0 > kk0 + 31) return;                                  // strictly upper tile of L: structurally zero
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int kk = kk0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (kk < d && j <= kk) ? L[(size_t)kk * d + j] * r_scale : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int j = j0 + r, kk = kk0 + threadIdx.x;
+        if (j < d && kk < d) {
+            double v = tile[threadIdx.x][r];
+            __half h = __double2half(v);
+            size_t o = (size_t)j * KC_pad + col_of_rank[kk];
+            Rh[o] = h;
+            Rl[o] = __double2half(v - (double)__half2float(h));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 0) {                  // m' in operand order (padding columns stay zero)
+        int kk = kk0 + threadIdx.x;
+        if (kk < d) mp_op[col_of_rank[kk]] = (float)mp[perm[kk]];
+    }
 }
 
 // =====================================================================================
@@ -388,7 +450,8 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 
 static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
-    dev_free(&ctx->R); dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
+    dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
+    dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
@@ -522,7 +585,9 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
         (rc = dev_alloc(ctx, &ctx->v, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->z, (size_t)d)))
         return rc;
     if (with_factor) {
-        if ((rc = dev_alloc(ctx, &ctx->R, dd)) || (rc = dev_alloc(ctx, &ctx->mp, (size_t)d)) ||
+        if ((rc = dev_alloc(ctx, &ctx->R, dd)) || (rc = dev_alloc(ctx, &ctx->Sp, dd)) ||
+            (rc = dev_alloc(ctx, &ctx->perm, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->inv_perm, (size_t)d)) ||
+            (rc = dev_alloc(ctx, &ctx->col_of_rank, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->mp, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->Rt_f32, dpp)) || (rc = dev_alloc(ctx, &ctx->mp_f32, (size_t)dp)) ||
             (rc = dev_alloc(ctx, &ctx->Rh, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->Rl, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
@@ -538,12 +603,33 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     k_set_diag<<<blocks, 256>>>(ctx->Sinv, d, alpha, alpha);                           // blr.py:30
     SSPBO_LAUNCH_CHECK(ctx);
     if (with_factor) {
-        // R0 = sqrt(B^T B / alpha), B^T B = diag(1/d, 2/d, ..., 2/d)
-        k_set_diag<<<blocks, 256>>>(ctx->R, d, sqrt(1.0 / (d * alpha)), sqrt(2.0 / (d * alpha)));
+        // permutation of the psi components into operand-column order (cos/sin interleaved per 32-frequency block)
+        {
+            const int K = ctx->K;
+            std::vector<int> perm, col;
+            for (int c = 0; c < ctx->KC_pad; ++c) {
+                int b = c >> 6, i = c & 63, f = 32 * b + (i & 31);
+                int pidx = (f > K) ? -1 : (i < 32 ? f : (f == 0 ? -1 : K + f));
+                if (pidx >= 0) { perm.push_back(pidx); col.push_back(c); }
+            }
+            if ((int)perm.size() != d) SSPBO_FAIL(ctx, SSPBO_EINVAL, "internal: operand permutation has %d of %d entries", (int)perm.size(), d);
+            std::vector<int> inv(d);
+            for (int r = 0; r < d; ++r) inv[perm[r]] = r;
+            SSPBO_CUDA(ctx, cudaMemcpy(ctx->perm, perm.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+            SSPBO_CUDA(ctx, cudaMemcpy(ctx->inv_perm, inv.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+            SSPBO_CUDA(ctx, cudaMemcpy(ctx->col_of_rank, col.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+            for (int ch = 0; ch < 8; ++ch) {
+                int row = ch * ctx->BN;
+                ctx->kb_start[ch] = (ch < ctx->n_chunks && row < d) ? col[row] / 64 : 0;
+            }
+        }
+        // Sp0 = P (B^T B / alpha) P^T, B^T B = diag(1/d, 2/d, ..., 2/d); the DC component keeps rank 0
+        k_set_diag<<<blocks, 256>>>(ctx->Sp, d, 1.0 / (d * alpha), 2.0 / (d * alpha));
         SSPBO_LAUNCH_CHECK(ctx);
-        // (I - kappa y y^T) is a contraction, so |R_jk| <= ||R0||_2 for every later R: one fixed power-of-two scale
+        // Sp only shrinks (in the Loewner order), so |L_ij| <= sqrt(||Sp0||_2) for ever: one fixed power-of-two scale
         double rmax = sqrt(2.0 / (d * alpha));
         ctx->r_scale = exp2(floor(log2(1024.0 / rmax)));
+        ctx->factor_dirty = true;
     }
     ctx->has_factor = with_factor;
     ctx->blr_ready = true; ctx->operands_dirty = true;
@@ -595,14 +681,18 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         SSPBO_LAUNCH_CHECK(ctx);
         k_gemv_cols<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(ctx->S, phi, ctx->z, d);              // z = S^T phi
         SSPBO_LAUNCH_CHECK(ctx);
-        // --- psi-space factor: psi = D^-1 B^T phi ; y = R psi ---
+        k_update_scalars<<<1, 256, 0, st>>>(phi, ctx->v, d, beta, ctx->scal);
+        SSPBO_LAUNCH_CHECK(ctx);
+        // --- psi-space covariance (permuted): psi = D^-1 B^T phi ; y = Sp psi ; Sp -= beta y y^T / (1 + beta psi.y) ---
         if (ctx->has_factor) {
-            k_analysis<<<K + 1, 128, 0, st>>>(phi, ctx->psi, ctx->twiddle, K, 1.0, 1.0);
+            k_analysis<<<K + 1, 128, 0, st>>>(phi, ctx->psi, ctx->twiddle, K, 1.0, 1.0, ctx->inv_perm);
             SSPBO_LAUNCH_CHECK(ctx);
-            k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->R, ctx->psi, ctx->y, d);               // y = R psi
+            k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->Sp, ctx->psi, ctx->y, d);
             SSPBO_LAUNCH_CHECK(ctx);
+            k_update_scalars<<<1, 256, 0, st>>>(ctx->psi, ctx->y, d, beta, ctx->scal + 2);
+            SSPBO_LAUNCH_CHECK(ctx);
+            k_rank1<<<g1, 256, 0, st>>>(ctx->Sp, ctx->y, ctx->y, d, ctx->scal + 2, 0.0);
         }
-        k_update_scalars<<<1, 256, 0, st>>>(phi, ctx->v, ctx->has_factor ? ctx->y : ctx->v, d, beta, ctx->scal);
         SSPBO_LAUNCH_CHECK(ctx);
         k_rank1<<<g1, 256, 0, st>>>(ctx->S, ctx->v, ctx->z, d, ctx->scal + 0, 0.0);              // S -= coef v z^T
         SSPBO_LAUNCH_CHECK(ctx);
@@ -610,21 +700,15 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         SSPBO_LAUNCH_CHECK(ctx);
         k_axpy<<<(d + 255) / 256, 256, 0, st>>>(ctx->b, phi, beta * ts_host[i], d);              // b += beta t phi
         SSPBO_LAUNCH_CHECK(ctx);
-        if (ctx->has_factor) {
-            k_gemv_cols<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(ctx->R, ctx->y, ctx->phi_tmp, d); // R^T y
-            SSPBO_LAUNCH_CHECK(ctx);
-            k_rank1<<<g1, 256, 0, st>>>(ctx->R, ctx->y, ctx->phi_tmp, d, ctx->scal + 1, 0.0);    // R -= kappa y (R^T y)^T
-            SSPBO_LAUNCH_CHECK(ctx);
-        }
     }
     if (k > 0) {
         k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, ctx->b, ctx->m, d);                     // m = S b  (blr.py:75)
         SSPBO_LAUNCH_CHECK(ctx);
         if (ctx->has_factor) {
-            k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d);   // m' = B^T m
+            k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
             SSPBO_LAUNCH_CHECK(ctx);
         }
-        ctx->operands_dirty = true;
+        ctx->operands_dirty = true; ctx->factor_dirty = true;
     }
     return SSPBO_OK;
 }
@@ -632,12 +716,29 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
 int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     if (!ctx->operands_dirty) return SSPBO_OK;
-    dim3 grid(ctx->dp / 32, ctx->dp / 32);
-    k_refresh_operands<<<grid, dim3(32, 8), 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->dp, ctx->Rt_f32, ctx->mp_f32);
+    const int d = ctx->d;
+    if (ctx->factor_dirty) {                                    // L = chol(Sp), blocked, in place on a copy
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->R, ctx->Sp, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (int k0 = 0; k0 < d; k0 += CH_NB) {
+            k_chol_diag<<<1, dim3(CH_NB, CH_NB), 0, st>>>(ctx->R, d, k0);
+            SSPBO_LAUNCH_CHECK(ctx);
+            int rest = d - k0 - CH_NB;
+            if (rest > 0) {
+                k_chol_trsm<<<(rest + 127) / 128, 128, 0, st>>>(ctx->R, d, k0);
+                SSPBO_LAUNCH_CHECK(ctx);
+                int tiles = (rest + 31) / 32;
+                k_chol_syrk<<<dim3(tiles, tiles), dim3(32, 8), 0, st>>>(ctx->R, d, k0);
+                SSPBO_LAUNCH_CHECK(ctx);
+            }
+        }
+        ctx->factor_dirty = false;
+    }
+    k_refresh_operands<<<dim3((ctx->dp + 255) / 256, d), 256, 0, st>>>(ctx->R, ctx->mp, ctx->perm, d, ctx->dp, ctx->Rt_f32,
+                                                                    ctx->mp_f32);
     SSPBO_LAUNCH_CHECK(ctx);
-    dim3 g2((ctx->KC_pad + 255) / 256, ctx->NJ_pad);
-    k_refresh_umma_operands<<<g2, 256, 0, st>>>(ctx->R, ctx->mp, ctx->d, ctx->K, ctx->KC_pad, ctx->NJ_pad, ctx->r_scale,
-                                                ctx->Rh, ctx->Rl, ctx->mp_op);
+    dim3 g2((d + 31) / 32, (d + 31) / 32);
+    k_refresh_umma_operands<<<g2, dim3(32, 8), 0, st>>>(ctx->R, ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->KC_pad,
+                                                        ctx->r_scale, ctx->Rh, ctx->Rl, ctx->mp_op);
     SSPBO_LAUNCH_CHECK(ctx);
     ctx->operands_dirty = false;
     return SSPBO_OK;
@@ -666,7 +767,7 @@ extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d, dd = d * d;
-    const double* src[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->R, ctx->mp};
+    const double* src[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->Sp, ctx->mp};
     const size_t cnt[6] = {dd, dd, d, d, dd, d};
     size_t off = 0;
     for (int i = 0; i < (ctx->has_factor ? 6 : 4); ++i) {
@@ -681,7 +782,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d, dd = d * d;
-    double* dst[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->R, ctx->mp};
+    double* dst[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->Sp, ctx->mp};
     const size_t cnt[6] = {dd, dd, d, d, dd, d};
     size_t off = 0;
     for (int i = 0; i < (ctx->has_factor ? 6 : 4); ++i) {
@@ -689,7 +790,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
         off += cnt[i];
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
-    ctx->operands_dirty = true;
+    ctx->operands_dirty = true; ctx->factor_dirty = true;
     return SSPBO_OK;
 }
 

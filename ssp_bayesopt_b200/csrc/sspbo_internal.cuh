@@ -31,7 +31,16 @@ struct sspbo_ctx {
     double alpha = 0.01, beta = 0.0;
     double *S = nullptr, *Sinv = nullptr, *b = nullptr, *m = nullptr;
     // ---- scoring state (psi-space) ----
-    double* R = nullptr;             // d x d float64 row-major, R^T R = B^T S B
+    // Sp = P (B^T S B) P^T : psi-space covariance with components permuted into operand-column order (perm below).
+    // R holds the LOWER Cholesky factor L of Sp (row-major, only j <= i meaningful); the scoring factor is the upper
+    // triangular L^T:  psi^T Sp psi = |L^T psi|^2, and output row j of the scorer is column j of L.
+    double* Sp = nullptr;            // d x d float64
+    double* R = nullptr;             // d x d float64, L (lower)
+    int* perm = nullptr;             // d : psi natural index of the component with rank r (operand-column order)
+    int* inv_perm = nullptr;         // d : rank of psi natural index
+    int* col_of_rank = nullptr;      // d : operand column of rank r
+    int kb_start[8] = {0};           // first k-block with non-zero factor entries, per output chunk (triangular skip)
+    bool factor_dirty = true;        // L must be recomputed from Sp
     double* mp = nullptr;            // m' = B^T m (d)
     float*  Rt_f32 = nullptr;        // dp x dp float32, Rt[k*dp + j] = R[j][k]      (SIMT scorer)
     float*  mp_f32 = nullptr;        // dp

@@ -15,7 +15,9 @@
 //                    acq = lam var / (sqrt(var+gamma) + sqrt(gamma)), score = mu + acq, warp-shuffle argmax.
 // The d output rows are processed in chunks of BN rows, two chunks (= both 256-column TMEM accumulators) per pass
 // over the contraction dimension, so every generated psi k-block is consumed by two MMAs groups before it is
-// regenerated for the next pair of chunks (128 x 1024 x 2 fp16 does not fit on chip).
+// regenerated for the next pair of chunks (128 x 1024 x 2 fp16 does not fit on chip).  The factor is upper
+// triangular (Cholesky of the permuted psi-space covariance), so chunk c only needs k-blocks >= kb_start[c]:
+// 40 of the 64 (chunk, k-block) MMA groups and 24 of the 32 psi k-blocks at d = 1023.
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
@@ -42,6 +44,7 @@ struct Params {
     const void* x; int x_f64; long long N; long long index0;
     const long long* Aq_op; const float* mp_op;
     int K, KC_pad, BN, n_chunks, n_kb, nb;
+    int kb_start[8];                    // first k-block holding non-zeros of the (upper triangular) factor, per output chunk
     float inv_beta, lam, gamma_t, inv_rscale2;
     float *mu, *var, *acq;
     unsigned long long* best;
@@ -187,8 +190,9 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             Ring rb;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int pr = 0; pr < n_pairs; ++pr)
-                    for (int kb = 0; kb < p.n_kb; ++kb)
+                    for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb)
                         for (int cc = 0; cc < 2 && 2 * pr + cc < p.n_chunks; ++cc) {
+                            if (kb < p.kb_start[2 * pr + cc]) continue;   // zero block of the triangular factor
                             mbar_wait_relaxed(b_empty(rb.slot), rb.phase ^ 1);
                             uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
                             mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
@@ -213,11 +217,13 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         acc_phase[buf] ^= 1;
                     }
                     tc_fence_after();
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                    for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
                         mbar_wait(a_full(ra.slot), ra.phase);
                         const uint32_t sa = smem_u32(a_ring + (size_t)ra.slot * A_SLOT_BYTES);
                         const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
                         for (int cc = 0; cc < ncc; ++cc) {
+                            const int kb_first = p.kb_start[2 * pr + cc];
+                            if (kb < kb_first) continue;                  // zero block of the triangular factor
                             mbar_wait(b_full(rb.slot), rb.phase);
                             tc_fence_after();
                             const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
@@ -226,7 +232,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 #pragma unroll
                             for (int kk = 0; kk < BK / 16; ++kk) {
                                 const uint64_t off = (uint64_t)((kk * 32) >> 4);    // 16 fp16 = 32 bytes along K
-                                umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb | kk) != 0);
+                                umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb != kb_first) || (kk != 0));
                                 umma_f16(d_tmem, a_hi + off, b_lo + off, idesc, 1);
                                 umma_f16(d_tmem, a_lo + off, b_hi + off, idesc, 1);
                             }
@@ -314,7 +320,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             }
             float mu0 = 0.f, mu1 = 0.f;
             for (int pr = 0; pr < n_pairs; ++pr)
-                for (int kb = 0; kb < p.n_kb; ++kb) {
+                for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
                     const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
                     unsigned long long t0[8], t1[8];                      // phase in turns, Q0.64, wraps modulo 1
 #pragma unroll
@@ -451,7 +457,7 @@ int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
 }  // namespace
 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
-    if (!ctx->has_factor || ctx->L != 1 || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok) return 0;
+    if (!ctx->has_factor || ctx->L != 1 || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
     int major = 0;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
     int max_smem = 0;
@@ -490,6 +496,7 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     p.Aq_op = ctx->Aq_op; p.mp_op = ctx->mp_op;
     p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
     p.n_kb = ctx->KC_pad / BK; p.nb = nb;
+    for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
