@@ -270,9 +270,15 @@ def run_native(args):
                        "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands refreshed every step",
                        "last_winner": {"score": last[0], "index": last[1]}},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "frac": achieved / peaks["tflops"],
+                         # dram__bytes_read+write of one k_score_umma launch (chunk of 4,194,304 candidates) from the
+                         # ncu --set full capture summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
+                         "traffic": 108.6e6 if engine_used == "umma" else None,
+                         "launch_candidates": min(chunk, n_local),
                          "note": f"algorithmic {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
-                                 f"{kernel_ms:.2f} ms scoring time per step per GPU; peak {peaks['source']}"},
+                                 f"{kernel_ms:.2f} ms scoring time per step per GPU (all launches of the step); executed "
+                                 "tensor flops = 3 (fp16 split) x ~0.56 (triangular factor) x algorithmic; "
+                                 f"peak {peaks['source']}"},
             "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                               "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
                              if cpu_rate else None),

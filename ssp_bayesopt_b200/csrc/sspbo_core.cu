@@ -618,6 +618,11 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->perm, perm.data(), d * sizeof(int), cudaMemcpyHostToDevice));
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->inv_perm, inv.data(), d * sizeof(int), cudaMemcpyHostToDevice));
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->col_of_rank, col.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+            for (int kb = 0; kb < 32; ++kb) {
+                int cnt = 0;
+                for (int r = 0; r < d; ++r) cnt += (col[r] < 64 * (kb + 1));
+                ctx->nz_rows[kb] = (short)cnt;
+            }
             for (int ch = 0; ch < 8; ++ch) {
                 int row = ch * ctx->BN;
                 ctx->kb_start[ch] = (ch < ctx->n_chunks && row < d) ? col[row] / 64 : 0;

@@ -39,6 +39,7 @@ struct sspbo_ctx {
     int* perm = nullptr;             // d : psi natural index of the component with rank r (operand-column order)
     int* inv_perm = nullptr;         // d : rank of psi natural index
     int* col_of_rank = nullptr;      // d : operand column of rank r
+    short nz_rows[32] = {0};         // components whose operand column is < 64 (kb + 1), per k-block
     int kb_start[8] = {0};           // first k-block with non-zero factor entries, per output chunk (triangular skip)
     bool factor_dirty = true;        // L must be recomputed from Sp
     double* mp = nullptr;            // m' = B^T m (d)

@@ -45,6 +45,7 @@ struct Params {
     const long long* Aq_op; const float* mp_op;
     int K, KC_pad, BN, n_chunks, n_kb, nb;
     int kb_start[8];                    // first k-block holding non-zeros of the (upper triangular) factor, per output chunk
+    short nz_rows[32];                  // factor rows that can be non-zero in k-block kb (= components with column < 64 (kb+1))
     float inv_beta, lam, gamma_t, inv_rscale2;
     float *mu, *var, *acq;
     unsigned long long* best;
@@ -204,7 +205,6 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BM, p.BN);
             Ring ra, rb;
             uint32_t acc_phase[2] = {0, 0};
             int tile_iter = 0;
@@ -229,6 +229,15 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
                             const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + b_tile_bytes);
                             const uint32_t d_tmem = tmem_base + (uint32_t)(acc_of(tile_iter, cc) * ACC_COLS);
+                            // Rows of this chunk beyond the triangle are zero in this k-block: shrink N (multiple of 16).
+                            // The first k-block of a chunk runs at full N with accumulate = 0 so every column is initialised.
+                            int n_eff = p.BN;
+                            if (kb != kb_first) {
+                                int nz = (int)p.nz_rows[kb] - (2 * pr + cc) * p.BN;
+                                nz = (nz + 15) & ~15;
+                                n_eff = nz < p.BN ? nz : p.BN;
+                            }
+                            const uint32_t idesc = make_idesc(BM, n_eff);
 #pragma unroll
                             for (int kk = 0; kk < BK / 16; ++kk) {
                                 const uint64_t off = (uint64_t)((kk * 32) >> 4);    // 16 fp16 = 32 bytes along K
@@ -497,6 +506,7 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
     p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
+    for (int i = 0; i < 32; ++i) p.nz_rows[i] = ctx->nz_rows[i];
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
