@@ -229,10 +229,15 @@ def run_native(args):
     host = torch.empty((n_local, N_DIM), dtype=torch.float32).pin_memory()
     host.copy_(cand)
     e2e_steps = max(1, min(args.steps, 3))
-    staging = torch.empty_like(cand)
     def e2e_step():
-        staging.copy_(host, non_blocking=True)                    # H2D of this step's candidates
-        return bo_step(staging)
+        # public API on HOST candidates: SSPAgent.best_candidate streams the pinned shard to the GPU in chunks
+        # (H2D inside the timed region, overlapped with the scoring), then the 8-byte key is read back
+        agt.best_candidate(host, index0=start)
+        dist.allreduce_best(eng._best)
+        score, gidx = eng.best()
+        x_t = winner_row(gidx)
+        agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))
+        return score, gidx
     e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -89,8 +89,13 @@ class SSPAgent(Agent):
     def best_candidate(self, xs, index0=0, reset_best=True):
         """argmax_i mu_i + acq_i over a candidate block (host array or device tensor).  Returns the device
         key tensor (see sspbo_score); `self._scoring_engine().best()` unpacks it."""
-        key, _ = self._scoring_engine().score(xs, self.var_weight, self._gamma(), index0=index0, want_outputs=False,
-                                              engine=self.score_engine, reset_best=reset_best)
+        eng = self._scoring_engine()
+        on_host = isinstance(xs, np.ndarray) or (hasattr(xs, "is_cuda") and not xs.is_cuda)
+        if on_host and len(xs) >= (1 << 21):                  # large host sets: overlap the H2D copy with the scoring
+            return eng.score_host(xs, self.var_weight, self._gamma(), index0=index0, engine=self.score_engine,
+                                  reset_best=reset_best)
+        key, _ = eng.score(xs, self.var_weight, self._gamma(), index0=index0, want_outputs=False,
+                           engine=self.score_engine, reset_best=reset_best)
         return key
 
     def initial_guess(self):

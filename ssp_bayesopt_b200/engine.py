@@ -210,6 +210,47 @@ class DeviceEngine:
         self._check(rc, "sspbo_score")
         return self._best, outs
 
+    def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 20, reset_best=True):
+        """Fused scoring of candidates that live in HOST memory (numpy or CPU tensor, ideally pinned): the set is
+        streamed through two device staging buffers so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
+        Returns the device key tensor (nothing is synchronised)."""
+        torch = self.torch
+        xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host))
+        if xt.dtype not in (torch.float32, torch.float64):
+            xt = xt.to(torch.float64)
+        xt = xt.contiguous()
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        cols = self.n * self.L
+        if xt.shape[1] != cols:
+            raise AssertionError(f"Expected {cols}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        key = (xt.dtype, cols, chunk)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [torch.empty((chunk, cols), dtype=xt.dtype, device=self._dev()) for _ in range(2)]
+            self._stage_key = key
+            self._copy_stream = torch.cuda.Stream(device=self._dev())
+        compute = torch.cuda.current_stream(self.device)
+        if reset_best:
+            self._best.zero_()
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
+        for i, c0 in enumerate(range(0, N, chunk)):
+            b, n = i & 1, min(chunk, N - c0)
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(done[b])
+                self._stage[b][:n].copy_(xt[c0:c0 + n], non_blocking=True)
+                copied[b].record(self._copy_stream)
+            compute.wait_event(copied[b])
+            rc = self.lib.sspbo_score(self._ctx, C.c_void_p(self._stage[b].data_ptr()), self._dtype_code(xt), n,
+                                      int(index0 + c0), float(lam), float(gamma_t), None, None, None,
+                                      C.c_void_p(self._best.data_ptr()), int(engine), C.c_void_p(compute.cuda_stream))
+            self._check(rc, "sspbo_score")
+            done[b].record(compute)
+        return self._best
+
     def best(self):
         """(score, index) of the packed key; synchronises."""
         return _lib.key_unpack(int(self._best.item()))

@@ -285,6 +285,21 @@ def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
         np.testing.assert_allclose(var.cpu().numpy(), var2.cpu().numpy(), rtol=2e-5)
 
 
+def test_score_host_streaming_matches_resident(pkg, golden):
+    """Host candidates streamed in chunks (H2D overlapped) give the same packed key as device-resident scoring."""
+    import torch
+    agt, g = _replay_agent(pkg, golden, "ucb", 0.0)
+    eng = agt._scoring_engine()
+    x = np.random.default_rng(3).uniform(-5, 5, (50001, 2)).astype(np.float32)
+    eng.score(x, 10.0, 0.0, index0=7)
+    want = int(eng._best.item())
+    for host in (x, torch.from_numpy(x).pin_memory()):
+        eng.score_host(host, 10.0, 0.0, index0=7, chunk=4096)
+        assert int(eng._best.item()) == want
+    eng.score_host(x[:0], 10.0, 0.0)
+    assert int(eng._best.item()) == 0
+
+
 def test_score_edge_cases(pkg, golden):
     agt, g = _replay_agent(pkg, golden, "ucb", 0.0)
     eng = agt._scoring_engine()
