@@ -211,12 +211,6 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
                 for (int pr = 0; pr < n_pairs; ++pr) {
                     const int ncc = (2 * pr + 1 < p.n_chunks) ? 2 : 1;
-                    for (int cc = 0; cc < ncc; ++cc) {                    // the epilogue must have drained the accumulators
-                        const int buf = acc_of(tile_iter, cc);
-                        mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);
-                        acc_phase[buf] ^= 1;
-                    }
-                    tc_fence_after();
                     for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
                         mbar_wait(a_full(ra.slot), ra.phase);
                         const uint32_t sa = smem_u32(a_ring + (size_t)ra.slot * A_SLOT_BYTES);
@@ -224,6 +218,11 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         for (int cc = 0; cc < ncc; ++cc) {
                             const int kb_first = p.kb_start[2 * pr + cc];
                             if (kb < kb_first) continue;                  // zero block of the triangular factor
+                            if (kb == kb_first) {                         // first use of this accumulator in the pair:
+                                const int buf = acc_of(tile_iter, cc);    // the epilogue must have drained it (waited for
+                                mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);   // lazily, so the other accumulator's
+                                acc_phase[buf] ^= 1;                      // epilogue overlaps these MMAs)
+                            }
                             mbar_wait(b_full(rb.slot), rb.phase);
                             tc_fence_after();
                             const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
@@ -269,18 +268,25 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                 acc_phase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-                for (int g = 0; g < p.BN; g += 32) {                      // BN % 16 == 0
-                    uint32_t v[32];
-                    tmem_ld16(taddr + (uint32_t)g, v);
-                    const bool two = g + 16 < p.BN;
-                    if (two) tmem_ld16(taddr + (uint32_t)g + 16u, v + 16);
+                for (int g = 0; g < p.BN; g += 64) {                      // BN % 16 == 0; up to 64 columns in flight
+                    uint32_t v[64];
+                    const int nld = min(4, (p.BN - g) >> 4);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+                        if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
                     tmem_ld_wait();
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { float y = __uint_as_float(v[i]); q = fmaf(y, y, q); }
-                    if (two) {
+                    for (int l = 0; l < 4; ++l)
+                        if (l < nld) {
 #pragma unroll
-                        for (int i = 16; i < 32; ++i) { float y = __uint_as_float(v[i]); q = fmaf(y, y, q); }
-                    }
+                            for (int i = 0; i < 16; i += 4) {
+                                float y0 = __uint_as_float(v[16 * l + i]), y1 = __uint_as_float(v[16 * l + i + 1]);
+                                float y2 = __uint_as_float(v[16 * l + i + 2]), y3 = __uint_as_float(v[16 * l + i + 3]);
+                                q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1); q2 = fmaf(y2, y2, q2); q3 = fmaf(y3, y3, q3);
+                            }
+                        }
+                    q += (q0 + q1) + (q2 + q3);
                 }
                 tc_fence_before();
                 mbar_arrive(tmem_empty(buf));
