@@ -255,6 +255,7 @@ def run_native(args):
     ms_total, kernel_ms, e2e_ms = [float(v) for v in stats.cpu()]
     sampler.join(timeout=2)
 
+    c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
     if rank == 0:
         peaks = load_peaks()
         ms_per_step = ms_total / args.steps
@@ -292,10 +293,28 @@ def run_native(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
+            "bo_step": c2,
         }
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
+
+
+def bo_step_c2(pkg, n_iter=30):
+    """'ms per BO step' of BASELINE config C2 through the public driver: Branin, ssp-hex ssp_dim=151, 1000 x 1000
+    candidate grid, `BayesianOptimization.maximize` (fused scoring of the 1e6 grid + winner read-back + target
+    evaluation + eval(x_t) + float64 posterior update per step)."""
+    bounds = np.array([[-5.0, 10.0], [0.0, 15.0]])
+    a, b, c, r, s, t = 1, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6., 10., 1 / (8 * np.pi)
+    branin = lambda x: -(a * (x[:, 1] - b * x[:, 0] ** 2 + c * x[:, 0] - r) ** 2 + s * (1 - t) * np.cos(x[:, 0]) + s)
+    xs0 = np.random.default_rng(0).uniform(bounds[:, 0], bounds[:, 1], (10, 2))
+    opt = pkg.BayesianOptimization(f=branin, bounds=bounds)
+    opt.maximize(init_points=(xs0, branin(xs0).reshape(-1, 1)), n_iter=n_iter, agent_type="ssp-hex", ssp_dim=151,
+                 length_scale=1.0, beta_ucb=10.0, gamma_c=0.0, candidates_per_dim=1000)
+    ft = opt.full_times[5:] * 1e-6                                  # ns -> ms, skip the first (warm-up) steps
+    return {"config": "C2: Branin 2-D ssp-hex d=151, 1e6-point candidate grid, BayesianOptimization.maximize",
+            "ms_per_bo_step": float(np.mean(ft)), "ms_min": float(np.min(ft)), "steps": int(len(ft)),
+            "candidates_per_s": float(1e6 / (np.mean(opt.times[5:]) * 1e-9)), "best_target": float(opt.max["target"])}
 
 
 def main():
@@ -307,6 +326,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "umma"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--chunk", type=int, default=1 << 22)
+    ap.add_argument("--no-c2", action="store_true", help="skip the config-C2 'ms per BO step' side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

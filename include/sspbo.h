@@ -117,6 +117,12 @@ int64_t sspbo_launch_count(const sspbo_ctx* ctx);
 int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* sample_ssps_dev, int64_t M, const double* queries_dev,
                           int q, int64_t* idx_out_dev, void* stream);
 
+/* ---- K5: binding (sspspace.py:551-560) ------------------------------------------------
+ * Circular convolution out[r] = a[ra] (*) b[rb] over the last axis, float64, evaluated directly in the time
+ * domain (the reference goes through fft/ifft; results agree to ~1e-15).  a_dev: qa x d, b_dev: qb x d with
+ * qa == qb, or either equal to 1 (numpy broadcasting); out_dev: max(qa, qb) x d.  d is the context's ssp_dim. */
+int sspbo_bind(sspbo_ctx* ctx, const double* a_dev, int qa, const double* b_dev, int qb, double* out_dev, void* stream);
+
 /* ---- candidate generators ---------------------------------------------------------
  * Counter-based uniform(0,1) float32 stream (same integer hash as
  * oracle/ssp_oracle.py:counter_uniform, bit-exact): rows [start, start+count) of an

@@ -391,6 +391,29 @@ __global__ void k_argmax_rows(const double* __restrict__ sims, int64_t M, int64_
 }
 
 // =====================================================================================
+// K5 binding: circular convolution out[r][i] = sum_j a[r][j] b[r][(i - j) mod d]   (float64, direct)
+// =====================================================================================
+__global__ void k_bind(const double* __restrict__ a, int qa, const double* __restrict__ b, int qb, int d,
+                       double* __restrict__ out) {
+    extern __shared__ double sh[];                      // a row, then b row
+    double* as = sh; double* bs = sh + d;
+    const int r = blockIdx.y;
+    const double* ar = a + (size_t)(qa == 1 ? 0 : r) * d;
+    const double* br = b + (size_t)(qb == 1 ? 0 : r) * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) { as[j] = ar[j]; bs[j] = br[j]; }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        int k = i;                                       // (i - j) mod d, walked downwards
+        for (int j = 0; j < d; ++j) {
+            acc = fma(as[j], bs[k], acc);
+            k = (k == 0) ? d - 1 : k - 1;
+        }
+        out[(size_t)r * d + i] = acc;
+    }
+}
+
+// =====================================================================================
 // candidate generators
 // =====================================================================================
 __global__ void k_fill_uniform(uint64_t seed, int64_t first_elem, int64_t count, float* __restrict__ out) {
@@ -873,6 +896,22 @@ extern "C" int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* ssps, int64_t
     SSPBO_LAUNCH_CHECK(ctx);
     SSPBO_CUDA(ctx, cudaFreeAsync(unit, st));
     SSPBO_CUDA(ctx, cudaFreeAsync(sims, st));
+    return SSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------ K5
+extern "C" int sspbo_bind(sspbo_ctx* ctx, const double* a, int qa, const double* b, int qb, double* out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    const int d = ctx->d;
+    if (d < 1) SSPBO_FAIL(ctx, SSPBO_ESTATE, "bind before space_set");
+    if (!a || !b || !out || qa < 1 || qb < 1 || (qa != qb && qa != 1 && qb != 1))
+        SSPBO_FAIL(ctx, SSPBO_EINVAL, "bind: row counts %d and %d do not broadcast", qa, qb);
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int q = qa > qb ? qa : qb;
+    size_t smem = 2 * (size_t)d * sizeof(double);
+    SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_bind, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bind<<<dim3((d + 255) / 256, q), 256, smem, (cudaStream_t)stream>>>(a, qa, b, qb, d, out);
+    SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }
 

@@ -277,6 +277,19 @@ class DeviceEngine:
         self._check(rc, "sspbo_from_set_argmax")
         return idx
 
+    # ------------------------------------------------------------------ K5
+    def bind(self, a, b):
+        """Circular convolution of the rows of a (qa, d) and b (qb, d) with numpy broadcasting over rows."""
+        at = self.to_device(np.atleast_2d(a) if not hasattr(a, "is_cuda") else a, self.torch.float64)
+        bt = self.to_device(np.atleast_2d(b) if not hasattr(b, "is_cuda") else b, self.torch.float64)
+        assert at.shape[1] == self.d and bt.shape[1] == self.d, (tuple(at.shape), tuple(bt.shape), self.d)
+        q = max(at.shape[0], bt.shape[0])
+        out = self.torch.empty((q, self.d), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_bind(self._ctx, C.c_void_p(at.data_ptr()), at.shape[0], C.c_void_p(bt.data_ptr()), bt.shape[0],
+                                 C.c_void_p(out.data_ptr()), self._stream())
+        self._check(rc, "sspbo_bind")
+        return out
+
     # ------------------------------------------------------------------ generators
     def fill_uniform(self, seed: int, start: int, count: int, n: int | None = None):
         n = n or self.n * self.L

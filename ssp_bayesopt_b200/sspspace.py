@@ -210,13 +210,14 @@ class SSPSpace:
         return s
 
     def bind(self, *arrays):
-        """Circular convolution (sspspace.py:551-557).  The trajectory encoder on the device never calls this
-        (it sums phasors in the Fourier domain); it is kept for the API and for the tiny (L, d) unbind of
-        SSPTrajectoryAgent.decode."""
-        spec = np.fft.fft(np.atleast_2d(arrays[0]), axis=-1)
+        """Circular convolution (sspspace.py:551-557), on the GPU (`sspbo_bind`, direct float64 convolution; the
+        reference's fft/ifft route agrees to ~1e-15).  The trajectory encoder never calls this (it sums phasors in
+        the Fourier domain); SSPTrajectoryAgent.decode uses it to unbind the L timesteps."""
+        eng = self.engine
+        acc = eng.to_device(np.atleast_2d(arrays[0]), eng.torch.float64)
         for a in arrays[1:]:
-            spec = spec * np.fft.fft(np.atleast_2d(a), axis=-1)
-        return np.fft.ifft(spec, axis=-1).real
+            acc = eng.bind(acc, np.atleast_2d(a))
+        return acc.cpu().numpy()
 
     def invert(self, a):
         a = np.atleast_2d(a)

@@ -339,6 +339,13 @@ def test_grid_points_and_from_set_decode(pkg, golden):
     assert sp.engine.from_set_argmax(g["ssps"], np.zeros((1, sp.ssp_dim))).cpu().numpy()[0] == 0
     with pytest.raises(NotImplementedError):
         sp.decode(g["queries"], method="nope")
+    # K5 binding (sspspace.py:551-557): golden value, broadcasting, identity and inverse
+    np.testing.assert_allclose(sp.bind(g["queries"][0], g["queries"][1]), g["bind"], atol=1e-14)
+    np.testing.assert_allclose(sp.bind(g["queries"], g["queries"][1]), orc.bind(g["queries"], g["queries"][1]), atol=1e-14)
+    np.testing.assert_allclose(sp.bind(g["queries"], sp.identity()), g["queries"], atol=1e-15)
+    np.testing.assert_allclose(sp.bind(g["queries"][:1], sp.invert(g["queries"][:1])), sp.identity(), atol=1e-12)
+    x12 = np.array([[1.0, -2.0], [0.5, 3.0]])
+    np.testing.assert_allclose(sp.bind(sp.encode(x12[:1]), sp.encode(x12[1:])), sp.encode(x12.sum(0, keepdims=True)), atol=1e-12)
 
 
 def test_decode_round_trip_reference_tests(pkg):
