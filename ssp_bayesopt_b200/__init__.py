@@ -10,6 +10,7 @@ from .blr import BayesianLinearRegression
 from .engine import DeviceEngine
 from .sspspace import HexagonalSSPSpace, RandomSSPSpace, SSPSpace
 from .agents import SSPAgent, SSPTrajectoryAgent
+from .batched import BatchedRuns
 
 __all__ = ["BayesianOptimization", "BayesianLinearRegression", "DeviceEngine", "SSPSpace", "HexagonalSSPSpace",
-           "RandomSSPSpace", "SSPAgent", "SSPTrajectoryAgent", "agents", "blr", "dist", "sspspace"]
+           "RandomSSPSpace", "SSPAgent", "SSPTrajectoryAgent", "BatchedRuns", "agents", "blr", "dist", "sspspace"]

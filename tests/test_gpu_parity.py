@@ -452,3 +452,34 @@ def test_full_size_grid_properties(pkg):
     score, _ = orc.score_and_argmax(orc.encode(sp.phase_matrix, np.ones(2), pts), ref, 10.0, 0.0)
     assert abs(score[i_all - lo] - s_all) <= RTOL_SCORE * abs(s_all)
     assert score.max() <= s_all * (1 + np.sign(s_all) * RTOL_SCORE) + 1e-12
+
+
+def test_batched_independent_runs(pkg):
+    """BASELINE config C4 in miniature: independent runs (own space seed, own posterior) stepped in lock-step over a
+    shared Himmelblau grid; every run's picks must equal the oracle's arg-max for that run, step by step."""
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    R, steps, per_dim = 6, 3, 40
+    agents, refs, spaces = [], [], []
+    for r in range(R):
+        sp = pkg.RandomSSPSpace(2, ssp_dim=128, domain_bounds=bounds, length_scale=1.0, rng=r)   # d = 127
+        xs0 = np.random.default_rng(100 + r).uniform(-5, 5, (6, 2))
+        ys0 = himmelblau(xs0).reshape(-1, 1)
+        agents.append(pkg.SSPAgent(xs0, ys0, sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+        ref = orc.BLR(sp.ssp_dim)
+        ref.update(orc.encode(sp.phase_matrix, np.ones(2), xs0), ys0)
+        refs.append(ref)
+        spaces.append(sp)
+    grid = orc.grid_sample_points(bounds, per_dim)
+    runs = pkg.BatchedRuns(agents, grid, n_streams=3)
+    for _ in range(steps):
+        pts, ys, scores = runs.step(himmelblau)
+        for r in range(R):
+            A = spaces[r].phase_matrix
+            score, idx = orc.score_and_argmax(orc.encode(A, np.ones(2), grid), refs[r], 10.0, 0.0)
+            srt = np.sort(score)[::-1]
+            if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+                assert np.array_equal(pts[r], grid[idx]), (r, pts[r], grid[idx])
+            assert abs(scores[r] - score.max()) <= RTOL_SCORE * abs(score.max())
+            refs[r].update(orc.encode(A, np.ones(2), pts[r:r + 1]), np.atleast_2d(ys[r]))
+    for r in range(R):
+        assert rel(agents[r].blr.m, refs[r].m) < 1e-8
