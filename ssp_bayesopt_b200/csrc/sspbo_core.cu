@@ -486,7 +486,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     sspbo_umma_release(ctx);
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
-    dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op);
+    dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
     delete ctx;
 }
 
@@ -524,7 +524,7 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns, At.data(), At.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns_f32, Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op);
     {   // frequency table of the tcgen05 scorer: row f = A_turns of frequency f (f = 0: DC, f > K: padding) -> zeros
         int kc, bn, nc, nj;
         sspbo_umma_dims(K, &kc, &bn, &nc, &nj);
@@ -548,7 +548,7 @@ extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int 
     if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "space_set_traj before space_set");
     if (L < 1 || L > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "traj length must be in [1, 64]");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
-    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op);
     ctx->L = L;
     if (!tau_host) { if (L != 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "tau is required when L > 1"); return SSPBO_OK; }
     std::vector<double> t((size_t)L * ctx->K);
@@ -563,6 +563,21 @@ extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int 
     if ((rc = dev_alloc(ctx, &ctx->tau_turns_f32, t.size()))) return rc;
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->tau_turns, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->tau_turns_f32, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {   // Q0.64 phase offsets in the frequency order of the tcgen05 scorer (f = 0: DC, f > K: padding -> 0)
+        int kc, bn, nc, nj;
+        sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
+        const int nf = kc / 2;
+        std::vector<unsigned long long> tq((size_t)L * nf, 0ull);
+        for (int j = 0; j < L; ++j)
+            for (int f = 1; f <= ctx->K; ++f) {
+                double fr = t[(size_t)j * ctx->K + f - 1];              // in [-1/2, 1/2]
+                fr -= floor(fr);                                       // [0, 1)
+                long double scaled = (long double)fr * 18446744073709551616.0L;
+                tq[(size_t)j * nf + f] = (scaled >= 18446744073709551615.0L) ? 0ull : (unsigned long long)scaled;
+            }
+        if ((rc = dev_alloc(ctx, &ctx->tauq_op, tq.size()))) return rc;
+        SSPBO_CUDA(ctx, cudaMemcpy(ctx->tauq_op, tq.data(), tq.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
     return SSPBO_OK;
 }
 

@@ -43,6 +43,8 @@ constexpr int ACC_COLS = 256;                                    // columns per 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
     const long long* Aq_op; const float* mp_op;
+    // trajectory mode (TRAJ): candidates pre-converted to Q31.32 (N x L x n), per-timestep phase offsets Q0.64 (L x KC_pad/2)
+    const unsigned long long* xq; const unsigned long long* tauq; int L;
     int K, KC_pad, BN, n_chunks, n_kb, nb;
     int kb_start[8];                    // first k-block holding non-zeros of the (upper triangular) factor, per output chunk
     short nz_rows[32];                  // factor rows that can be non-zero in k-block kb (= components with column < 64 (kb+1))
@@ -135,7 +137,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int NDIM>
+template <int NDIM, bool TRAJ>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -325,67 +327,86 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             unsigned long long x0[NDIM], x1[NDIM];                       // Q31.32 candidates (two's complement)
             const long long g0 = tile * BM + r0, g1 = g0 + 64;
+            if constexpr (!TRAJ) {
 #pragma unroll
-            for (int a = 0; a < NDIM; ++a) {
-                double v0 = 0.0, v1 = 0.0;
-                if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
-                x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
-                x1[a] = (unsigned long long)__double2ll_rn(v1 * 4294967296.0);
+                for (int a = 0; a < NDIM; ++a) {
+                    double v0 = 0.0, v1 = 0.0;
+                    if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                    if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
+                    x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                    x1[a] = (unsigned long long)__double2ll_rn(v1 * 4294967296.0);
+                }
             }
             float mu0 = 0.f, mu1 = 0.f;
             for (int pr = 0; pr < n_pairs; ++pr)
                 for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
                     const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
-                    unsigned long long t0[8], t1[8];                      // phase in turns, Q0.64, wraps modulo 1
+                    float cs0[8], sn0[8], cs1[8], sn1[8];
+                    if constexpr (!TRAJ) {
+                        unsigned long long t0[8], t1[8];                  // phase in turns, Q0.64, wraps modulo 1
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { t0[i] = 0ull; t1[i] = 0ull; }
+                        for (int i = 0; i < 8; ++i) { t0[i] = 0ull; t1[i] = 0ull; }
 #pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
+                        for (int a = 0; a < NDIM; ++a) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const unsigned long long Afa = Ablk[i * NDIM + a];   // one broadcast read feeds both rows
-                            t0[i] += Afa * x0[a];
-                            t1[i] += Afa * x1[a];
+                            for (int i = 0; i < 8; ++i) {
+                                const unsigned long long Afa = Ablk[i * NDIM + a];   // one broadcast read feeds both rows
+                                t0[i] += Afa * x0[a];
+                                t1[i] += Afa * x1[a];
+                            }
                         }
-                    }
-                    uint32_t w0[16], w1[16];                              // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
-                    {
-                        float cs[8], sn[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
-                            float ang = (float)(int)(t0[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
-                            cs[i] = __cosf(ang); sn[i] = __sinf(ang);
+                            float a0 = (float)(int)(t0[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
+                            float a1 = (float)(int)(t1[i] >> 32) * 1.4629180792671596e-9f;
+                            cs0[i] = __cosf(a0); sn0[i] = __sinf(a0);
+                            cs1[i] = __cosf(a1); sn1[i] = __sinf(a1);
                         }
-                        if (pr == 0) {
-                            const float* mcos = mp_s + kb * BK + quarter * 8;
+                    } else {
+                        // trajectory: the spectrum is the sum over the L waypoints of unit phasors
+                        // exp(i (theta_f(x_j) + tau_jf))  (agents/ssp_traj_agent.py:145-163 in the Fourier domain)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) { mu0 = fmaf(mcos[i], cs[i], mu0); mu0 = fmaf(mcos[32 + i], sn[i], mu0); }
-                        }
+                        for (int i = 0; i < 8; ++i) { cs0[i] = 0.f; sn0[i] = 0.f; cs1[i] = 0.f; sn1[i] = 0.f; }
+                        const int nf = p.KC_pad >> 1;
+                        for (int j = 0; j < p.L; ++j) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            split_pair(cs[2 * i], cs[2 * i + 1], w0[i], w0[4 + i]);
-                            split_pair(sn[2 * i], sn[2 * i + 1], w0[8 + i], w0[12 + i]);
+                            for (int a = 0; a < NDIM; ++a) {
+                                x0[a] = (g0 < p.N) ? __ldg(p.xq + ((size_t)g0 * p.L + j) * NDIM + a) : 0ull;
+                                x1[a] = (g1 < p.N) ? __ldg(p.xq + ((size_t)g1 * p.L + j) * NDIM + a) : 0ull;
+                            }
+                            const unsigned long long* tq = p.tauq + (size_t)j * nf + kb * 32 + quarter * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                unsigned long long t0 = __ldg(tq + i), t1 = t0;
+#pragma unroll
+                                for (int a = 0; a < NDIM; ++a) {
+                                    const unsigned long long Afa = Ablk[i * NDIM + a];
+                                    t0 += Afa * x0[a];
+                                    t1 += Afa * x1[a];
+                                }
+                                float a0 = (float)(int)(t0 >> 32) * 1.4629180792671596e-9f;
+                                float a1 = (float)(int)(t1 >> 32) * 1.4629180792671596e-9f;
+                                cs0[i] += __cosf(a0); sn0[i] += __sinf(a0);
+                                cs1[i] += __cosf(a1); sn1[i] += __sinf(a1);
+                            }
                         }
                     }
-                    {
-                        float cs[8], sn[8];
+                    if (pr == 0) {
+                        const float* mcos = mp_s + kb * BK + quarter * 8;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float ang = (float)(int)(t1[i] >> 32) * 1.4629180792671596e-9f;
-                            cs[i] = __cosf(ang); sn[i] = __sinf(ang);
+                            mu0 = fmaf(mcos[i], cs0[i], mu0); mu0 = fmaf(mcos[32 + i], sn0[i], mu0);
+                            mu1 = fmaf(mcos[i], cs1[i], mu1); mu1 = fmaf(mcos[32 + i], sn1[i], mu1);
                         }
-                        if (pr == 0) {
-                            const float* mcos = mp_s + kb * BK + quarter * 8;
+                    }
+                    uint32_t w0[16], w1[16];                              // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) { mu1 = fmaf(mcos[i], cs[i], mu1); mu1 = fmaf(mcos[32 + i], sn[i], mu1); }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            split_pair(cs[2 * i], cs[2 * i + 1], w1[i], w1[4 + i]);
-                            split_pair(sn[2 * i], sn[2 * i + 1], w1[8 + i], w1[12 + i]);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        split_pair(cs0[2 * i], cs0[2 * i + 1], w0[i], w0[4 + i]);
+                        split_pair(sn0[2 * i], sn0[2 * i + 1], w0[8 + i], w0[12 + i]);
+                        split_pair(cs1[2 * i], cs1[2 * i + 1], w1[i], w1[4 + i]);
+                        split_pair(sn1[2 * i], sn1[2 * i + 1], w1[8 + i], w1[12 + i]);
                     }
                     // values are ready in registers before the slot is claimed: the wait overlaps the math above
                     mbar_wait(a_empty(ra.slot), ra.phase ^ 1);
@@ -426,6 +447,7 @@ struct UmmaState {
     int KC_pad = 0, NJ_pad = 0, BN = 0;
     int max_smem = 0;
     int attr_set_n = 0;
+    unsigned long long* xq = nullptr; size_t xq_cap = 0;      // scratch of the trajectory mode
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
@@ -435,13 +457,27 @@ size_t table_bytes(const sspbo_ctx* ctx) {
 size_t b_slot_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)ctx->BN * BK * 2; }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
-kernel_fn kernel_for(int n) {
+constexpr int MAX_TRAJ_N = 3;           // waypoint dimension of the trajectory instantiations
+kernel_fn kernel_for(int n, bool traj) {
+    if (traj) {
+        switch (n) {
+            case 1: return k_score_umma<1, true>; case 2: return k_score_umma<2, true>; case 3: return k_score_umma<3, true>;
+        }
+        return nullptr;
+    }
     switch (n) {
-        case 1: return k_score_umma<1>; case 2: return k_score_umma<2>; case 3: return k_score_umma<3>;
-        case 4: return k_score_umma<4>; case 5: return k_score_umma<5>; case 6: return k_score_umma<6>;
-        case 7: return k_score_umma<7>; case 8: return k_score_umma<8>;
+        case 1: return k_score_umma<1, false>; case 2: return k_score_umma<2, false>; case 3: return k_score_umma<3, false>;
+        case 4: return k_score_umma<4, false>; case 5: return k_score_umma<5, false>; case 6: return k_score_umma<6, false>;
+        case 7: return k_score_umma<7, false>; case 8: return k_score_umma<8, false>;
     }
     return nullptr;
+}
+
+// candidates -> Q31.32 two's complement (trajectory mode reads each waypoint once per k-block)
+template <typename XT>
+__global__ void k_to_q32(const XT* __restrict__ x, long long count, unsigned long long* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (unsigned long long)__double2ll_rn((double)x[i] * 4294967296.0);
 }
 
 int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
@@ -472,7 +508,8 @@ int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
 }  // namespace
 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
-    if (!ctx->has_factor || ctx->L != 1 || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
+    if (!ctx->has_factor || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
+    if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
     int major = 0;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
     int max_smem = 0;
@@ -482,7 +519,11 @@ int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
 }
 
 void sspbo_umma_release(sspbo_ctx* ctx) {
-    if (ctx->umma) { delete (UmmaState*)ctx->umma; ctx->umma = nullptr; }
+    if (ctx->umma) {
+        UmmaState* us = (UmmaState*)ctx->umma;
+        if (us->xq) cudaFree(us->xq);
+        delete us; ctx->umma = nullptr;
+    }
 }
 
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
@@ -500,11 +541,13 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two B slots");
     const size_t smem = 1024 + NA * A_SLOT_BYTES + (size_t)nb * sb + tb;
-    kernel_fn kern = kernel_for(ctx->n);
+    const bool traj = ctx->L != 1;
+    kernel_fn kern = kernel_for(ctx->n, traj);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: domain dimension %d not instantiated", ctx->n);
-    if (us->attr_set_n != ctx->n) {
+    const int attr_key = ctx->n + (traj ? 100 : 0);
+    if (us->attr_set_n != attr_key) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, us->max_smem));
-        us->attr_set_n = ctx->n;
+        us->attr_set_n = attr_key;
     }
     Params p;
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
@@ -516,6 +559,20 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
+    p.xq = nullptr; p.tauq = (const unsigned long long*)ctx->tauq_op; p.L = ctx->L;
+    if (traj) {
+        const size_t count = (size_t)N * ctx->L * ctx->n;
+        if (count > us->xq_cap) {
+            if (us->xq) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(us->xq); us->xq = nullptr; us->xq_cap = 0; }
+            SSPBO_CUDA(ctx, cudaMalloc((void**)&us->xq, count * sizeof(unsigned long long)));
+            us->xq_cap = count;
+        }
+        const int cb = (int)((count + 255) / 256 < (size_t)ctx->sm_count * 16 ? (count + 255) / 256 : (size_t)ctx->sm_count * 16);
+        if (x_dtype == SSPBO_F64) k_to_q32<double><<<cb, 256, 0, st>>>((const double*)x, (long long)count, us->xq);
+        else k_to_q32<float><<<cb, 256, 0, st>>>((const float*)x, (long long)count, us->xq);
+        SSPBO_LAUNCH_CHECK(ctx);
+        p.xq = us->xq;
+    }
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     kern<<<grid, THREADS, smem, st>>>(us->map_hi, us->map_lo, p);

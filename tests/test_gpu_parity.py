@@ -382,6 +382,36 @@ def test_trajectory_agent_golden(pkg, golden):
     assert np.array_equal(agt.decode(phi[:1]), g["decoded"])
 
 
+@pytest.mark.parametrize("L,ssp_dim,N", [(4, 51, 300), (10, 200, 1500)])
+def test_trajectory_tcgen05_engine(pkg, L, ssp_dim, N):
+    """BASELINE config C5 shape in miniature: the tcgen05 engine sums L phasors per frequency (trajectory mode)."""
+    from ssp_bayesopt_b200 import _lib
+    bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    rng = np.random.default_rng(L)
+    trajs = rng.uniform(-2, 2, (12, 2 * L))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / L
+    agt = pkg.SSPTrajectoryAgent(trajs, tys, x_dim=2, traj_len=L, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=0.7,
+                                 time_length_scale=1.3, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    Ax, At = agt.ssp_x_space.phase_matrix, agt.ssp_t_space.phase_matrix
+    T = orc.traj_timestep_ssps(At, np.array([1.3]), L)
+    ref = orc.BLR(Ax.shape[0])
+    ref.update(orc.traj_encode(Ax, 0.7 * np.ones(2), T, trajs, L, 2), tys)
+    xc = rng.uniform(-2, 2, (N, 2 * L)).astype(np.float32)
+    xc[:4] = trajs[:4].astype(np.float32)
+    phis = orc.traj_encode(Ax, 0.7 * np.ones(2), T, xc.astype(np.float64), L, 2)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 5.0, 0.0)
+    eng = agt._scoring_engine()
+    for code, name in ((_lib.ENGINE_UMMA, "umma"), (_lib.ENGINE_SIMT, "simt")):
+        _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True, engine=code)
+        assert eng.last_engine() == name
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        ref_score = ref_mu.ravel() + ref_acq
+        srt = np.sort(ref_score)[::-1]
+        if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert eng.best()[1] == int(np.argmax(ref_score))
+
+
 # ------------------------------------------------------------------------------------------ generators, driver
 def test_fill_uniform_bit_exact(pkg):
     eng = pkg.DeviceEngine()
