@@ -180,6 +180,7 @@ def run_native(args):
         for c0 in range(0, n_local, chunk):
             agt.best_candidate(x_dev[c0:c0 + chunk], index0=start + c0, reset_best=first)
             first = False
+        eng.settle()                                              # low-rank pass counters (synchronises; replays if asked)
         dist.allreduce_best(eng._best)
         return eng.best()                                         # D2H of the 8-byte key (synchronises)
 
@@ -233,6 +234,7 @@ def run_native(args):
         # public API on HOST candidates: SSPAgent.best_candidate streams the pinned shard to the GPU in chunks
         # (H2D inside the timed region, overlapped with the scoring), then the 8-byte key is read back
         agt.best_candidate(host, index0=start)
+        eng.settle()
         dist.allreduce_best(eng._best)
         score, gidx = eng.best()
         x_t = winner_row(gidx)

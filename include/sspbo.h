@@ -38,9 +38,13 @@ extern "C" {
 #define SSPBO_F64 1
 
 /* scoring engines for sspbo_score */
-#define SSPBO_ENGINE_AUTO 0     /* tcgen05 when the shape is covered, else SIMT */
+#define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; tcgen05 (low-rank while rank <= 512) when covered; else SIMT */
 #define SSPBO_ENGINE_SIMT 1     /* fp32 CUDA-core kernel (any d)                */
-#define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel               */
+#define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel, full triangular factor        */
+#define SSPBO_ENGINE_EXACT 3    /* float64 quadratic form on the psi-space covariance (small N)  */
+#define SSPBO_ENGINE_UMMA_LR 4  /* tcgen05/TMEM kernel on the low-rank form S = I/alpha - V^T V
+                                   (one row of V per observation, rank <= 512) followed by the
+                                   EXACT engine on the candidates it flags (var < 0.1 / alpha)   */
 
 typedef struct sspbo_ctx sspbo_ctx;
 
@@ -64,6 +68,12 @@ int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus_host, const double* inv
 int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L);
 
 int sspbo_space_dims(const sspbo_ctx* ctx, int* d, int* K, int* n, int* L);
+
+/* Declares a bound on |x| over every candidate coordinate (max |SSPSpace.domain_bounds|).  With it the tcgen05
+ * scorer evaluates theta = A x in 32-bit fixed point (one integer multiply-add per axis) when the worst-case
+ * operand rounding stays below 2^-20 turns; candidates outside the bound are counted (sspbo_score_stats) and
+ * switch the context back to the 64-bit phase path.  0 = unknown (64-bit path). */
+int sspbo_space_set_xbound(sspbo_ctx* ctx, double x_absmax);
 
 /* ---- K1: encode ---------------------------------------------------------------
  * SSPSpace.encode (sspspace.py:254-276): phi = Re IFFT(exp(i A (x/l)^T))^T.
@@ -104,6 +114,16 @@ int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi_dev, int64_t N, double* 
 int sspbo_score(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, int64_t index0,
                 double lam, double gamma_t, float* mu_dev, float* var_dev, float* acq_dev,
                 unsigned long long* best_key_dev, int engine, void* stream);
+/* Counters of the low-rank engine since the last reset (synchronises `stream`): candidates scored, re-scored by the
+ * exact pass, flagged beyond the list capacity, outside the declared |x| bound.  *rerun != 0 means the keys/outputs
+ * accumulated since the last reset must be recomputed (the context has already switched its policy, so simply call
+ * sspbo_score again).  Any pointer may be NULL. */
+int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t* overflow, int64_t* out_of_range,
+                      int* rerun, int reset, void* stream);
+/* state of the low-rank form: rows of V appended since blr_init, whether it is usable, policy switches */
+int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, int* disabled, int* phase32);
+/* policy overrides for SSPBO_ENGINE_AUTO: 1 = enable, 0 = disable, -1 = leave */
+int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled);
 /* host helpers for the packed key */
 void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index);
 unsigned long long sspbo_key_pack(float score, int64_t index);

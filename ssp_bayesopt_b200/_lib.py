@@ -14,8 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsspbo.so")
 
 F32, F64 = 0, 1
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_UMMA = 0, 1, 2
-ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_UMMA: "umma"}
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_UMMA, ENGINE_EXACT, ENGINE_UMMA_LR = 0, 1, 2, 3, 4
+ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_UMMA: "umma", ENGINE_EXACT: "exact",
+                ENGINE_UMMA_LR: "umma-lowrank"}
 
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -29,6 +30,10 @@ SIGNATURES = {
     "sspbo_space_set": (_i, [_vp, _pd, _pd, _i, _i]),
     "sspbo_space_set_traj": (_i, [_vp, _pd, _i]),
     "sspbo_space_dims": (_i, [_vp, _pi, _pi, _pi, _pi]),
+    "sspbo_space_set_xbound": (_i, [_vp, _d]),
+    "sspbo_score_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _pi, _i, _vp]),
+    "sspbo_lowrank_info": (_i, [_vp, _pi, _pi, _pi, _pi]),
+    "sspbo_set_policy": (_i, [_vp, _i, _i]),
     "sspbo_encode": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "sspbo_blr_init": (_i, [_vp, _d]),
     "sspbo_blr_init_dim": (_i, [_vp, _i, _d]),

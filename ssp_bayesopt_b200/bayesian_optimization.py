@@ -141,6 +141,7 @@ class BayesianOptimization:
         if key is None:
             eng._best.zero_()
             key = eng._best
+        eng.settle()                                   # local key final before it is combined across ranks
         dist.allreduce_best(key)
         score, gidx = eng.best()
         # owner of the winning row publishes it (one small broadcast; single-GPU: a D2H copy of one row)

@@ -289,6 +289,138 @@ __global__ void k_refresh_umma_operands(const double* __restrict__ L, const doub
     }
 }
 
+// low-rank scoring operand: row r of V (operand order, split fp16) = y sqrt(coef) r_scale, coef = beta / (1 + beta psi.y)
+__global__ void k_lr_append(const double* __restrict__ y, const double* __restrict__ coef, const int* __restrict__ col_of_rank,
+                            int d, double r_scale, __half* __restrict__ vh_row, __half* __restrict__ vl_row) {
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= d) return;
+    const double v = y[kk] * sqrt(*coef) * r_scale;
+    const __half h = __double2half(v);
+    const int c = col_of_rank[kk];
+    vh_row[c] = h;
+    vl_row[c] = __double2half(v - (double)__half2float(h));
+}
+// m' in operand order (padding columns stay zero)
+__global__ void k_mp_op(const double* __restrict__ mp, const int* __restrict__ perm, const int* __restrict__ col_of_rank,
+                        int d, float* __restrict__ mp_op) {
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk < d) mp_op[col_of_rank[kk]] = (float)mp[perm[kk]];
+}
+
+// =====================================================================================
+// K2 exact engine (float64): var = 1/beta + psi^T Sp psi, mu = m' . psi straight from the float64 psi-space
+// covariance.  No factorisation is needed, so it serves (a) the candidates the low-rank tcgen05 pass flags as too
+// close to the observations for its cancelling form, (b) tiny candidate sets such as eval(x_t) of every BO step.
+//   k_exact_partial : grid (groups, RB); CTA (g, rb) builds psi of EX_G candidates in shared memory and reduces
+//                     rows [rb*d/RB, (rb+1)*d/RB) of Sp against them
+//   k_exact_finish  : sums the RB partials, applies ssp_agent.py:136, writes outputs, max-combines the key
+// =====================================================================================
+constexpr int EX_G = 8, EX_THREADS = 256, EX_RB_MAX = 16;
+
+template <typename XT>
+__global__ void __launch_bounds__(EX_THREADS)
+k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restrict__ list,
+                const unsigned long long* __restrict__ count_ptr, unsigned int cap, const double* __restrict__ A_turns,
+                const double* __restrict__ tau_turns, int n, int K, int L, const int* __restrict__ inv_perm,
+                const int* __restrict__ perm, const double* __restrict__ Sp, const double* __restrict__ mp, int RB,
+                double* __restrict__ part_q, double* __restrict__ part_mu) {
+    extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
+    __shared__ double red[EX_G][EX_THREADS / 32];
+    const int d = 2 * K + 1, nl = n * L;
+    int64_t count = N;
+    if (list) { unsigned long long c = *count_ptr; count = (int64_t)(c < cap ? c : cap); }
+    const int rb = blockIdx.y;
+    const int row0 = (int)((long long)d * rb / RB), row1 = (int)((long long)d * (rb + 1) / RB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * EX_G; base < count; base += (int64_t)gridDim.x * EX_G) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < EX_G * (K + 1); i += blockDim.x) {
+            const int c = i / (K + 1), f = i - c * (K + 1);
+            double cs = 0.0, sn = 0.0;
+            if (base + c < count) {
+                const int64_t row = list ? (int64_t)list[base + c] : base + c;
+                if (f == 0) cs = (double)L;
+                else psi_entry(x + row * nl, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
+            }
+            if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
+            else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
+        }
+        __syncthreads();
+        double q[EX_G];
+#pragma unroll
+        for (int c = 0; c < EX_G; ++c) q[c] = 0.0;
+        for (int i = row0 + warp; i < row1; i += EX_THREADS / 32) {
+            const double* srow = Sp + (size_t)i * d;
+            double acc[EX_G];
+#pragma unroll
+            for (int c = 0; c < EX_G; ++c) acc[c] = 0.0;
+            for (int j = lane; j < d; j += 32) {
+                const double s = srow[j];
+#pragma unroll
+                for (int c = 0; c < EX_G; ++c) acc[c] = fma(s, psi_s[c * d + j], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < EX_G; ++c) q[c] = fma(psi_s[c * d + i], acc[c], q[c]);   // linear in the lane partials
+        }
+#pragma unroll
+        for (int c = 0; c < EX_G; ++c) {
+            const double t = warp_sum(q[c]);
+            if (lane == 0) red[c][warp] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < EX_G && base + threadIdx.x < count) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < EX_THREADS / 32; ++w) t += red[threadIdx.x][w];
+            part_q[(base + threadIdx.x) * RB + rb] = t;
+        }
+        if (rb == 0) {                                   // mu = m' . psi, one warp per candidate
+            if (warp < EX_G && base + warp < count) {
+                double u = 0.0;
+                for (int r = lane; r < d; r += 32) u = fma(mp[perm[r]], psi_s[warp * d + r], u);
+                u = warp_sum(u);
+                if (lane == 0) part_mu[base + warp] = u;
+            }
+        }
+    }
+}
+
+__global__ void k_exact_finish(int64_t N, const unsigned int* __restrict__ list, unsigned long long* __restrict__ stats,
+                               unsigned int cap, int RB, const double* __restrict__ part_q, const double* __restrict__ part_mu,
+                               double inv_beta, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
+                               float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
+    int64_t count = N;
+    if (list) { unsigned long long c = stats[SSPBO_STAT_CUR]; count = (int64_t)(c < cap ? c : cap); }
+    unsigned long long my_best = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        double q = 0.0;
+        for (int r = 0; r < RB; ++r) q += part_q[i * RB + r];
+        const double mu = part_mu[i];
+        const double var = inv_beta + q;                                        // blr.py:96
+        const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
+        const int64_t row = list ? (int64_t)list[i] : i;
+        if (mu_out) mu_out[row] = (float)mu;
+        if (var_out) var_out[row] = (float)var;
+        if (acq_out) acq_out[row] = (float)acq;
+        const unsigned long long key = sspbo_pack((float)(mu + acq), (unsigned long long)(index0 + row));
+        if (key > my_best) my_best = key;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, my_best, o);
+        if (other > my_best) my_best = other;
+    }
+    if ((threadIdx.x & 31) == 0 && my_best && best) atomicMax(best, my_best);
+    if (list) {                                          // single CTA in list mode: fold the per-call counter
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long c = stats[SSPBO_STAT_CUR];
+            stats[SSPBO_STAT_FLAGGED] += (c < cap ? c : cap);
+            stats[SSPBO_STAT_SCORED] += (unsigned long long)N;
+            stats[SSPBO_STAT_CUR] = 0ull;
+        }
+    }
+}
+
 // =====================================================================================
 // BLR.predict on explicit phi (float64): var = 1/beta + phi^T S phi ; mu = m . phi
 // =====================================================================================
@@ -476,6 +608,7 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
+    dev_free(&ctx->Vh); dev_free(&ctx->Vl); ctx->lr_rank = 0; ctx->lr_valid = false;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -487,12 +620,15 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
+    dev_free(&ctx->A32_op); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     delete ctx;
 }
 
 extern "C" const char* sspbo_last_error(const sspbo_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int sspbo_last_engine(const sspbo_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 extern "C" int64_t sspbo_launch_count(const sspbo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int build_p32_tables(sspbo_ctx* ctx);
 
 extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const double* inv_ls, int K, int n) {
     if (!ctx) return SSPBO_EINVAL;
@@ -540,7 +676,58 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
         SSPBO_CUDA(ctx, cudaMemcpy(ctx->Aq_op, op.data(), op.size() * sizeof(long long), cudaMemcpyHostToDevice));
     }
     ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
+    double amax = 0.0;
+    for (size_t i = 0; i < At.size(); ++i) amax = fmax(amax, fabs(At[i]));
+    ctx->a_absmax = amax;
+    ctx->host_A_turns.assign(At.begin(), At.end());
+    ctx->p32_disabled = false;
+    return build_p32_tables(ctx);
+}
+
+// 32-bit fixed-point phase tables of the fast generator: A in Q.fa, x in Q.fx with fa <= 31 - ceil(log2 |A|max),
+// fx <= 31 - ceil(log2 |x|max) and fa + fx = 55; the 64-bit sum of the n products holds the phase in turns at bit 55,
+// so bits [32, 55) (the low 23 bits of the high word) are the top 23 bits of the phase modulo one turn.  Enabled when
+// the worst-case rounding of the two operands plus the 2^-23 truncation stays below 2^-20 turns (6e-6 rad);
+// otherwise the 64-bit path (Q31.32 x Q31.32) is used.
+static int build_p32_tables(sspbo_ctx* ctx) {
+    ctx->p32_ok = false;
+    if (ctx->K == 0 || !(ctx->x_absmax > 0.0) || !(ctx->a_absmax > 0.0)) return SSPBO_OK;
+    int ia = 0, ix = 0;
+    while (ldexp(1.0, ia) <= ctx->a_absmax && ia < 31) ++ia;     // 2^ia > |A|max
+    while (ldexp(1.0, ix) <= ctx->x_absmax && ix < 31) ++ix;     // 2^ix > |x|max
+    // the kernel reads the phase at a fixed position: fa + fx = 55 (bits [32, 55) of the 64-bit sum are its top 23 bits)
+    const int fa_max = 31 - ia, fx_max = 31 - ix;
+    if (fa_max + fx_max < 55) return SSPBO_OK;
+    int fa = -1; double err = 1e300;
+    for (int cand = 55 - fx_max; cand <= fa_max; ++cand) {
+        const double e = ctx->n * (ctx->x_absmax * ldexp(1.0, -(cand + 1)) + ctx->a_absmax * ldexp(1.0, -(55 - cand + 1)));
+        if (e < err) { err = e; fa = cand; }
+    }
+    const int fx = 55 - fa;
+    if (fa < 0 || err + ldexp(1.0, -23) > ldexp(1.0, -20)) return SSPBO_OK;
+    int kc, bn, nc, nj;
+    sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
+    std::vector<int> op((size_t)(kc / 2) * ctx->n, 0);
+    for (int f = 1; f <= ctx->K; ++f)
+        for (int a = 0; a < ctx->n; ++a)
+        {
+            long long q = llrint(ctx->host_A_turns[(size_t)(f - 1) * ctx->n + a] * ldexp(1.0, fa));
+            op[(size_t)f * ctx->n + a] = (int)(q > 2147483647ll ? 2147483647ll : (q < -2147483647ll ? -2147483647ll : q));
+        }
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->A32_op, op.size()))) return rc;
+    SSPBO_CUDA(ctx, cudaMemcpy(ctx->A32_op, op.data(), op.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->p32_fa = fa; ctx->p32_fx = fx; ctx->p32_ok = true;
     return SSPBO_OK;
+}
+
+extern "C" int sspbo_space_set_xbound(sspbo_ctx* ctx, double x_absmax) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!(x_absmax >= 0.0) || !isfinite(x_absmax)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set_xbound: bound must be finite and >= 0");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->x_absmax = x_absmax;
+    ctx->p32_disabled = false;
+    return build_p32_tables(ctx);
 }
 
 extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L) {
@@ -630,6 +817,8 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             (rc = dev_alloc(ctx, &ctx->Rh, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->Rl, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->mp_op, (size_t)ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Vh, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Vl, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->psi, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->y, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->phi_tmp, (size_t)d)))
             return rc;
@@ -675,6 +864,12 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
         ctx->factor_dirty = true;
     }
     ctx->has_factor = with_factor;
+    ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false;
+    if (with_factor && !ctx->stats) {
+        if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
+            (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)SSPBO_FLAG_CAP)))
+            return rc;
+    }
     ctx->blr_ready = true; ctx->operands_dirty = true;
     SSPBO_CUDA(ctx, cudaDeviceSynchronize());
     return SSPBO_OK;
@@ -735,6 +930,16 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
             k_update_scalars<<<1, 256, 0, st>>>(ctx->psi, ctx->y, d, beta, ctx->scal + 2);
             SSPBO_LAUNCH_CHECK(ctx);
             k_rank1<<<g1, 256, 0, st>>>(ctx->Sp, ctx->y, ctx->y, d, ctx->scal + 2, 0.0);
+            if (ctx->lr_valid) {
+                if (ctx->lr_rank >= SSPBO_LR_MAX) ctx->lr_valid = false;        // beyond the low-rank regime
+                else {
+                    SSPBO_LAUNCH_CHECK(ctx);                                    // (the rank-one launch above)
+                    const size_t off = (size_t)ctx->lr_rank * ctx->KC_pad;
+                    k_lr_append<<<(d + 255) / 256, 256, 0, st>>>(ctx->y, ctx->scal + 2, ctx->col_of_rank, d, ctx->r_scale,
+                                                                 ctx->Vh + off, ctx->Vl + off);
+                    ctx->lr_rank++;
+                }
+            }
         }
         SSPBO_LAUNCH_CHECK(ctx);
         k_rank1<<<g1, 256, 0, st>>>(ctx->S, ctx->v, ctx->z, d, ctx->scal + 0, 0.0);              // S -= coef v z^T
@@ -749,6 +954,8 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         SSPBO_LAUNCH_CHECK(ctx);
         if (ctx->has_factor) {
             k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
+            SSPBO_LAUNCH_CHECK(ctx);
+            k_mp_op<<<(d + 255) / 256, 256, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op);
             SSPBO_LAUNCH_CHECK(ctx);
         }
         ctx->operands_dirty = true; ctx->factor_dirty = true;
@@ -834,6 +1041,11 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
     ctx->operands_dirty = true; ctx->factor_dirty = true;
+    ctx->lr_valid = false;                                       // the rows of V do not travel with the packed state
+    if (ctx->has_factor) {
+        k_mp_op<<<((int)d + 255) / 256, 256, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, (int)d, ctx->mp_op);
+        SSPBO_LAUNCH_CHECK(ctx);
+    }
     return SSPBO_OK;
 }
 
@@ -854,6 +1066,48 @@ extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, d
 }
 
 // ------------------------------------------------------------------------------------ K2 dispatch
+int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, bool from_flag_list, int64_t index0,
+                             double lam, double gamma_t, float* mu, float* var, float* acq, unsigned long long* best,
+                             cudaStream_t st) {
+    if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
+    const int d = ctx->d;
+    const int64_t max_rows = from_flag_list ? (int64_t)SSPBO_FLAG_CAP : N;
+    // row blocks: spread a tiny set over the machine, one pass over Sp per group of EX_G candidates otherwise
+    int RB = 1;
+    if (!from_flag_list) {
+        const int64_t groups = (N + EX_G - 1) / EX_G;
+        while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;
+    }
+    const size_t need = (size_t)max_rows * (RB + 1);
+    if (need > ctx->ex_part_cap) {
+        if (ctx->ex_part) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); }
+        int rc = dev_alloc(ctx, &ctx->ex_part, need);
+        if (rc) return rc;
+        ctx->ex_part_cap = need;
+    }
+    double* part_q = ctx->ex_part;
+    double* part_mu = ctx->ex_part + (size_t)max_rows * RB;
+    const size_t smem = (size_t)EX_G * d * sizeof(double);
+    const unsigned int* list = from_flag_list ? ctx->flag_idx : nullptr;
+    const unsigned long long* cnt = from_flag_list ? ctx->stats + SSPBO_STAT_CUR : nullptr;
+    int gx = from_flag_list ? 2 * ctx->sm_count : (int)((N + EX_G - 1) / EX_G < 4 * ctx->sm_count ? (N + EX_G - 1) / EX_G : 4 * ctx->sm_count);
+    if (x_dtype == SSPBO_F32) {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, list, cnt, SSPBO_FLAG_CAP, ctx->A_turns,
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+    } else {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_exact_partial<double><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const double*)x, N, list, cnt, SSPBO_FLAG_CAP, ctx->A_turns,
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+    }
+    SSPBO_LAUNCH_CHECK(ctx);
+    const int fb = from_flag_list ? 1 : (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);
+    k_exact_finish<<<fb, from_flag_list ? 1024 : 256, 0, st>>>(N, list, ctx->stats, SSPBO_FLAG_CAP, RB, part_q, part_mu,
+                                                                1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
 extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, double lam, double gamma_t,
                            float* mu, float* var, float* acq, unsigned long long* best, int engine, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
@@ -862,21 +1116,79 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
     if (x_dtype != SSPBO_F32 && x_dtype != SSPBO_F64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown dtype %d", x_dtype);
     if (index0 < 0 || index0 + N > 0xffffffffLL) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: candidate index must stay below 2^32");
     if (!(gamma_t >= 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: gamma_t must be >= 0");
+    if (engine < SSPBO_ENGINE_AUTO || engine > SSPBO_ENGINE_UMMA_LR) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown engine %d", engine);
     if (N == 0) return SSPBO_OK;
+    if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = sspbo_refresh_operands(ctx, st);
-    if (rc) return rc;
-    bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
+    const bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
+    const bool lr_ok = umma_ok && ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && N < 0xffffffffLL;
     if (engine == SSPBO_ENGINE_UMMA && !umma_ok)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: tcgen05 engine does not cover d=%d L=%d", ctx->d, ctx->L);
-    bool use_umma = (engine == SSPBO_ENGINE_UMMA) || (engine == SSPBO_ENGINE_AUTO && umma_ok && N >= 1024);
-    if (use_umma) {
-        ctx->last_engine = SSPBO_ENGINE_UMMA;
-        return sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+    if (engine == SSPBO_ENGINE_UMMA_LR && !lr_ok)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: low-rank tcgen05 engine needs 1 <= rank <= %d rows appended since blr_init "
+                   "(rank %d, valid %d) and L == 1", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid);
+    if (engine == SSPBO_ENGINE_AUTO) {
+        if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
+        else if (umma_ok && N >= 1024) engine = (lr_ok && !ctx->lr_disabled) ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA;
+        else engine = SSPBO_ENGINE_SIMT;
     }
-    ctx->last_engine = SSPBO_ENGINE_SIMT;
+    ctx->last_engine = engine;
+    if (engine == SSPBO_ENGINE_EXACT)
+        return sspbo_score_exact_launch(ctx, x, x_dtype, N, false, index0, lam, gamma_t, mu, var, acq, best, st);
+    if (engine == SSPBO_ENGINE_UMMA_LR) {
+        int rc = sspbo_score_umma_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+        if (rc) return rc;
+        // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
+        return sspbo_score_exact_launch(ctx, x, x_dtype, N, true, index0, lam, gamma_t, mu, var, acq, best, st);
+    }
+    int rc = sspbo_refresh_operands(ctx, st);
+    if (rc) return rc;
+    if (engine == SSPBO_ENGINE_UMMA)
+        return sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
     return sspbo_score_simt_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+}
+
+/* counters of the low-rank pass since the last reset; synchronises `stream`.  Applies the engine policy: when more
+ * than 1 % of the scored candidates needed the exact pass (or the flag list overflowed) the AUTO engine switches to the
+ * full factor; candidates outside the declared |x| bound switch the generator to the 64-bit phase path.  *rerun is set
+ * when the results accumulated since the last reset must be recomputed (overflow or out-of-range candidates). */
+extern "C" int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t* overflow, int64_t* out_of_range,
+                                 int* rerun, int reset, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (scored) *scored = 0; if (flagged) *flagged = 0; if (overflow) *overflow = 0; if (out_of_range) *out_of_range = 0;
+    if (rerun) *rerun = 0;
+    if (!ctx->stats) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long h[SSPBO_STAT_COUNT];
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (reset) SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, sizeof(h), st));
+    if (scored) *scored = (int64_t)h[SSPBO_STAT_SCORED];
+    if (flagged) *flagged = (int64_t)h[SSPBO_STAT_FLAGGED];
+    if (overflow) *overflow = (int64_t)h[SSPBO_STAT_OVERFLOW];
+    if (out_of_range) *out_of_range = (int64_t)h[SSPBO_STAT_OOR];
+    if (h[SSPBO_STAT_OVERFLOW] > 0 || (h[SSPBO_STAT_SCORED] >= 4096 && h[SSPBO_STAT_FLAGGED] * 100 > h[SSPBO_STAT_SCORED]))
+        ctx->lr_disabled = true;
+    if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
+    if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0) ? 1 : 0;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, int* disabled, int* phase32) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (rank) *rank = ctx->lr_rank;
+    if (valid) *valid = ctx->lr_valid ? 1 : 0;
+    if (disabled) *disabled = ctx->lr_disabled ? 1 : 0;
+    if (phase32) *phase32 = (ctx->p32_ok && !ctx->p32_disabled) ? 1 : 0;
+    return SSPBO_OK;
+}
+extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (lowrank_enabled >= 0) ctx->lr_disabled = !lowrank_enabled;
+    if (phase32_enabled >= 0) ctx->p32_disabled = !phase32_enabled;
+    return SSPBO_OK;
 }
 
 extern "C" void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index) {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "../../include/sspbo.h"
 
 struct sspbo_ctx {
@@ -56,6 +57,27 @@ struct sspbo_ctx {
     int KC_pad = 0, BN = 0, n_chunks = 0, NJ_pad = 0;
     double r_scale = 1.0;
     bool operands_dirty = true;      // Rt_f32 / Rh / Rl / mp_f32 need a refresh from R, m
+    // ---- low-rank scoring state: Sp = Sp0 - V^T V with one row of V per observation (rank = #observations) ----
+    //   psi^T Sp psi = psi^T Sp0 psi - |V psi|^2 ;  row r of V = y sqrt(beta / (1 + beta psi.y)), y = Sp psi (before the update)
+    // Only the split-fp16 image in operand order is kept (SSPBO_LR_MAX x KC_pad, K-major, rows >= lr_rank are zero).
+    __half* Vh = nullptr;
+    __half* Vl = nullptr;
+    int lr_rank = 0;
+    bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)
+    bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead
+    bool p32_disabled = false;       // policy: candidates outside the declared |x| bound were seen
+    // 32-bit fixed-point phase tables (fast generator of the tcgen05 scorer), valid when p32_ok
+    int* A32_op = nullptr;           // (KC_pad/2) x n, Q(31-fa).fa turns per unit
+    bool p32_ok = false;
+    int p32_fa = 0, p32_fx = 0;      // fractional bits of A32_op and of the candidate coordinates
+    double x_absmax = 0.0;           // declared bound on |x| (0 = unknown)
+    double a_absmax = 0.0;           // max |A_turns|
+    std::vector<double> host_A_turns;            // host copy of A_turns (K x n) for rebuilding the tables
+    // exact float64 scorer (flagged candidates of the low-rank pass, tiny candidate sets)
+    unsigned int* flag_idx = nullptr;            // SSPBO_FLAG_CAP local row indices
+    unsigned long long* stats = nullptr;         // device counters, see SSPBO_STAT_*
+    double* ex_part = nullptr;                   // partial quadratic forms / means of the exact scorer
+    size_t ex_part_cap = 0;
     // scratch d-vectors (float64)
     double *v = nullptr, *psi = nullptr, *y = nullptr, *z = nullptr, *phi_tmp = nullptr;
     double* scal = nullptr;          // a few device scalars
@@ -84,6 +106,20 @@ struct sspbo_ctx {
         (ctx)->launches++;                           \
         SSPBO_CUDA(ctx, cudaGetLastError());         \
     } while (0)
+
+constexpr int SSPBO_LR_MAX = 512;               // largest rank scored in low-rank form (two 256-column accumulators)
+// The tensor core accumulates in float32 with truncation: |V psi|^2 carries a relative error of ~2e-5 (measured), i.e.
+// 2e-5 / alpha absolute on the variance.  Candidates whose variance is below this fraction of the prior variance
+// 1/alpha would exceed the 1e-4 tolerance after the subtraction and are re-scored by the exact float64 engine.
+constexpr double SSPBO_LR_FLAG_FRACTION = 0.3;
+constexpr unsigned SSPBO_FLAG_CAP = 1u << 18;    // flagged candidates per sspbo_score call that get the exact pass
+// device counters (unsigned long long each)
+enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (reset by its exact pass)
+       SSPBO_STAT_FLAGGED = 1,   // candidates re-scored exactly since the last reset
+       SSPBO_STAT_OVERFLOW = 2,  // flagged candidates beyond SSPBO_FLAG_CAP (kept their low-rank score)
+       SSPBO_STAT_OOR = 3,       // candidates outside the declared |x| bound of the 32-bit phase path
+       SSPBO_STAT_SCORED = 4,    // candidates scored by the low-rank pass since the last reset
+       SSPBO_STAT_COUNT = 8 };
 
 static inline int sspbo_pad64(int x) { return (x + 63) / 64 * 64; }
 
@@ -118,8 +154,14 @@ int sspbo_score_simt_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx);
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
                             float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
+int sspbo_score_umma_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
+                               float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_umma_release(sspbo_ctx* ctx);
 int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st);
+// exact float64 scorer: rows `list[0..*count)` of x (list == nullptr: rows 0..N-1)
+int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, bool from_flag_list, int64_t index0,
+                             double lam, double gamma_t, float* mu, float* var, float* acq, unsigned long long* best,
+                             cudaStream_t st);
 
 // ---- device helpers shared by the scorers: theta (in turns) of frequency k for candidate row x ----
 // fast path: float32 FMA chain (valid when the host bound max_turns*|x| keeps the error below 2^-20 turns)

@@ -19,6 +19,15 @@
 // triangular (Cholesky of the permuted psi-space covariance), so chunk c only needs k-blocks >= kb_start[c]:
 // 40 of the 64 (chunk, k-block) MMA groups and 24 of the 32 psi k-blocks at d = 1023.
 //
+// Low-rank mode (LR): while the posterior has seen r <= 512 observations since blr_init, Sp = Sp0 - V^T V with one row
+// of V per observation, so  psi^T Sp psi = 1/alpha - |V psi|^2  (psi^T Sp0 psi = |phi|^2 / alpha = 1/alpha exactly).
+// The B operand is then the r x KC image of V (BN = r rounded up to 16, one or two chunks, no triangular structure)
+// and psi is generated once per tile.  The subtraction cancels when a candidate sits on top of the observations
+// (var << 1/alpha): those candidates (var < flag_below) are not scored here but appended to a list that the
+// float64 engine (sspbo_core.cu, k_exact_*) re-scores right after this kernel.
+// Fast phase path (P32): A in Q.fa and x in Q.fx 32-bit fixed point with fa + fx = 55: one IMAD.WIDE per axis
+// accumulates the phase in a 64-bit register whose bits [32, 55) are the top 23 bits of the phase in turns.
+//
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
 #include <cuda.h>
@@ -34,7 +43,7 @@ constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
 constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 256
 constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB (one of hi / lo)
 constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
-constexpr int NA = 2;                                            // A ring slots
+constexpr int NA_MIN = 2, NA_MAX = 4;                            // A ring slots (as many as fit after the B ring)
 constexpr int MAX_NB = 6;                                        // B ring slots (as many as fit)
 constexpr int MAX_N = 8;                                         // domain dimension (compile-time specialised)
 constexpr uint32_t TMEM_COLS = 512;
@@ -51,6 +60,12 @@ struct Params {
     float inv_beta, lam, gamma_t, inv_rscale2;
     float *mu, *var, *acq;
     unsigned long long* best;
+    int na;                             // A ring slots
+    // low-rank mode
+    int lowrank; float prior_var, flag_below;
+    unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
+    // 32-bit fixed-point phase path
+    const int* A32_op; double x_scale;
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -127,6 +142,13 @@ struct Ring {                            // ring position; every role walks the 
     __device__ __forceinline__ void advance(int n) { if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 
+// (a & b) ^ c in one LOP3
+__device__ __forceinline__ uint32_t lop3_and_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // split one float pair into fp16 hi / lo words
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     __half2 h = __floats2half2_rn(a, b);
@@ -137,7 +159,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int NDIM, bool TRAJ>
+template <int NDIM, bool TRAJ, bool P32>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -147,6 +169,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_tile_bytes = p.BN * BK * 2;
     const int b_slot_bytes = 2 * b_tile_bytes;
+    const int NA = p.na;
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + NA * A_SLOT_BYTES;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
@@ -165,7 +188,12 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
+    if constexpr (P32) {
+        int* A32_s = (int*)tables;
+        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) A32_s[i] = p.A32_op[i];
+    } else {
+        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
+    }
     for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     if (warp == WARP_TMA && lane == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_THREADS); mbar_init(a_empty(s), 1); }
@@ -297,14 +325,26 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             if (gi < p.N) {
                 const float* mpart = mu_part + (tile_iter & 1) * 4 * BM;
                 float mu = (mpart[row] + mpart[BM + row]) + (mpart[2 * BM + row] + mpart[3 * BM + row]);
-                float var = p.inv_beta + q * p.inv_rscale2;                           // blr.py:96
-                float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
-                float score = mu + acq;
-                if (p.mu) p.mu[gi] = mu;
-                if (p.var) p.var[gi] = var;
-                if (p.acq) p.acq[gi] = acq;
-                unsigned long long key = sspbo_pack(score, (unsigned long long)(p.index0 + gi));
-                if (key > my_best) my_best = key;
+                float qv = q * p.inv_rscale2;
+                bool flagged = false;
+                if (p.lowrank) {
+                    qv = p.prior_var - qv;                                            // 1/alpha - |V psi|^2
+                    if (p.inv_beta + qv < p.flag_below) {                             // too close to the observations for
+                        const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
+                        if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                        else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
+                    }
+                }
+                if (!flagged) {
+                    float var = p.inv_beta + qv;                                           // blr.py:96
+                    float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
+                    float score = mu + acq;
+                    if (p.mu) p.mu[gi] = mu;
+                    if (p.var) p.var[gi] = var;
+                    if (p.acq) p.acq[gi] = acq;
+                    unsigned long long key = sspbo_pack(score, (unsigned long long)(p.index0 + gi));
+                    if (key > my_best) my_best = key;
+                }
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -326,8 +366,22 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             unsigned long long x0[NDIM], x1[NDIM];                       // Q31.32 candidates (two's complement)
+            int xq0[NDIM], xq1[NDIM];                                     // Q.fx candidates of the 32-bit phase path
             const long long g0 = tile * BM + r0, g1 = g0 + 64;
-            if constexpr (!TRAJ) {
+            if constexpr (P32) {
+                bool oor = false;
+#pragma unroll
+                for (int a = 0; a < NDIM; ++a) {
+                    double v0 = 0.0, v1 = 0.0;
+                    if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                    if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
+                    v0 *= p.x_scale; v1 *= p.x_scale;
+                    oor |= !(fabs(v0) < 2147483647.0) || !(fabs(v1) < 2147483647.0);
+                    xq0[a] = __double2int_rn(v0);
+                    xq1[a] = __double2int_rn(v1);
+                }
+                if (oor && quarter == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);     // outside the declared |x| bound
+            } else if constexpr (!TRAJ) {
 #pragma unroll
                 for (int a = 0; a < NDIM; ++a) {
                     double v0 = 0.0, v1 = 0.0;
@@ -342,7 +396,33 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                 for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
                     const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
                     float cs0[8], sn0[8], cs1[8], sn1[8];
-                    if constexpr (!TRAJ) {
+                    if constexpr (P32) {
+                        const int* A32blk = (const int*)tables + (size_t)(kb * 32 + quarter * 8) * NDIM;
+                        long long t0[8], t1[8];                           // phase in turns at bit 55
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { t0[i] = 0ll; t1[i] = 0ll; }
+#pragma unroll
+                        for (int a = 0; a < NDIM; ++a) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int Afa = A32blk[i * NDIM + a];     // one broadcast read feeds both rows
+                                t0[i] += (long long)Afa * (long long)xq0[a];              // IMAD.WIDE
+                                t1[i] += (long long)Afa * (long long)xq1[a];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            // bits [32, 55) = top 23 bits of the phase mod 1; flipping the top one adds 1/2 turn, and
+                            // with the exponent of 1.0 they are the mantissa of f in [1, 2): (f - 1.5) 2 pi is the
+                            // phase in radians in [-pi, pi).  One LOP3: (hi & 0x7fffff) ^ 0x3fc00000.
+                            const float f0 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t0[i] >> 32), 0x7fffffu, 0x3fc00000u));
+                            const float f1 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t1[i] >> 32), 0x7fffffu, 0x3fc00000u));
+                            const float a0 = fmaf(f0, 6.283185307179586f, -9.42477796076938f);
+                            const float a1 = fmaf(f1, 6.283185307179586f, -9.42477796076938f);
+                            cs0[i] = __cosf(a0); sn0[i] = __sinf(a0);
+                            cs1[i] = __cosf(a1); sn1[i] = __sinf(a1);
+                        }
+                    } else if constexpr (!TRAJ) {
                         unsigned long long t0[8], t1[8];                  // phase in turns, Q0.64, wraps modulo 1
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { t0[i] = 0ull; t1[i] = 0ull; }
@@ -441,34 +521,47 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------ host side
+struct MapSet {                           // tensor maps of one operand pair (hi, lo) and the geometry they were built for
+    CUtensorMap hi, lo;
+    const void* bh = nullptr; const void* bl = nullptr;
+    int KC_pad = 0, rows = 0, BN = 0;
+};
 struct UmmaState {
-    CUtensorMap map_hi, map_lo;
-    const void* rh = nullptr; const void* rl = nullptr;
-    int KC_pad = 0, NJ_pad = 0, BN = 0;
+    MapSet full, lr;
     int max_smem = 0;
-    int attr_set_n = 0;
+    bool attr_set[2][2][MAX_N + 1] = {};  // [traj][p32][n]
     unsigned long long* xq = nullptr; size_t xq_cap = 0;      // scratch of the trajectory mode
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
     return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
-           2 * 4 * BM * sizeof(float) + (2 * NA + 2 * MAX_NB + 4) * 8 + 16;
+           2 * 4 * BM * sizeof(float) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
-size_t b_slot_bytes_of(const sspbo_ctx* ctx) { return 2 * (size_t)ctx->BN * BK * 2; }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
 constexpr int MAX_TRAJ_N = 3;           // waypoint dimension of the trajectory instantiations
-kernel_fn kernel_for(int n, bool traj) {
+kernel_fn kernel_for(int n, bool traj, bool p32) {
     if (traj) {
         switch (n) {
-            case 1: return k_score_umma<1, true>; case 2: return k_score_umma<2, true>; case 3: return k_score_umma<3, true>;
+            case 1: return k_score_umma<1, true, false>; case 2: return k_score_umma<2, true, false>;
+            case 3: return k_score_umma<3, true, false>;
+        }
+        return nullptr;
+    }
+    if (p32) {
+        switch (n) {
+            case 1: return k_score_umma<1, false, true>; case 2: return k_score_umma<2, false, true>;
+            case 3: return k_score_umma<3, false, true>; case 4: return k_score_umma<4, false, true>;
+            case 5: return k_score_umma<5, false, true>; case 6: return k_score_umma<6, false, true>;
+            case 7: return k_score_umma<7, false, true>; case 8: return k_score_umma<8, false, true>;
         }
         return nullptr;
     }
     switch (n) {
-        case 1: return k_score_umma<1, false>; case 2: return k_score_umma<2, false>; case 3: return k_score_umma<3, false>;
-        case 4: return k_score_umma<4, false>; case 5: return k_score_umma<5, false>; case 6: return k_score_umma<6, false>;
-        case 7: return k_score_umma<7, false>; case 8: return k_score_umma<8, false>;
+        case 1: return k_score_umma<1, false, false>; case 2: return k_score_umma<2, false, false>;
+        case 3: return k_score_umma<3, false, false>; case 4: return k_score_umma<4, false, false>;
+        case 5: return k_score_umma<5, false, false>; case 6: return k_score_umma<6, false, false>;
+        case 7: return k_score_umma<7, false, false>; case 8: return k_score_umma<8, false, false>;
     }
     return nullptr;
 }
@@ -480,10 +573,11 @@ __global__ void k_to_q32(const XT* __restrict__ x, long long count, unsigned lon
         out[i] = (unsigned long long)__double2ll_rn((double)x[i] * 4294967296.0);
 }
 
-int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
-    cuuint64_t gdim[2] = {(cuuint64_t)ctx->KC_pad, (cuuint64_t)ctx->NJ_pad};
-    cuuint64_t gstride[1] = {(cuuint64_t)ctx->KC_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)ctx->BN};
+// K-major fp16 operand [rows x KC_pad], box = 64 columns x BN rows, 128-byte swizzle
+int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base, int KC_pad, int rows, int BN) {
+    cuuint64_t gdim[2] = {(cuuint64_t)KC_pad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)KC_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     // resolved through the runtime so libsspbo.so has no link-time dependency on libcuda.so.1 (absent on CPU-only hosts)
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -505,57 +599,68 @@ int make_map(sspbo_ctx* ctx, CUtensorMap* map, const void* base) {
     return SSPBO_OK;
 }
 
-}  // namespace
-
-int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
-    if (!ctx->has_factor || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
-    if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
-    int major = 0;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
-    int max_smem = 0;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    if (table_bytes(ctx) + NA * A_SLOT_BYTES + 2 * b_slot_bytes_of(ctx) + 1024 > (size_t)max_smem) return 0;
-    return 1;
+int ensure_maps(sspbo_ctx* ctx, MapSet* ms, const void* bh, const void* bl, int KC_pad, int rows, int BN) {
+    if (ms->bh == bh && ms->bl == bl && ms->KC_pad == KC_pad && ms->rows == rows && ms->BN == BN) return SSPBO_OK;
+    int rc;
+    if ((rc = make_map(ctx, &ms->hi, bh, KC_pad, rows, BN)) || (rc = make_map(ctx, &ms->lo, bl, KC_pad, rows, BN))) return rc;
+    ms->bh = bh; ms->bl = bl; ms->KC_pad = KC_pad; ms->rows = rows; ms->BN = BN;
+    return SSPBO_OK;
 }
 
-void sspbo_umma_release(sspbo_ctx* ctx) {
-    if (ctx->umma) {
-        UmmaState* us = (UmmaState*)ctx->umma;
-        if (us->xq) cudaFree(us->xq);
-        delete us; ctx->umma = nullptr;
-    }
-}
-
-int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
-                            float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+// shared launch path of the full-factor and the low-rank mode
+int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+           float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
     UmmaState* us = (UmmaState*)ctx->umma;
     if (!us) { us = new UmmaState(); ctx->umma = us; }
-    if (us->rh != ctx->Rh || us->rl != ctx->Rl || us->KC_pad != ctx->KC_pad || us->NJ_pad != ctx->NJ_pad || us->BN != ctx->BN) {
-        int rc;
-        if ((rc = make_map(ctx, &us->map_hi, ctx->Rh)) || (rc = make_map(ctx, &us->map_lo, ctx->Rl))) return rc;
-        us->rh = ctx->Rh; us->rl = ctx->Rl; us->KC_pad = ctx->KC_pad; us->NJ_pad = ctx->NJ_pad; us->BN = ctx->BN;
-    }
     if (!us->max_smem) cudaDeviceGetAttribute(&us->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    const size_t tb = table_bytes(ctx), sb = b_slot_bytes_of(ctx);
-    int nb = (int)(((size_t)us->max_smem - 1024 - tb - NA * A_SLOT_BYTES) / sb);
+    Params p;
+    memset(&p, 0, sizeof(p));
+    MapSet* ms;
+    if (lowrank) {
+        // rank r -> one chunk of BN = ceil16(r) rows, or two chunks of ceil16(r / 2) rows beyond 256
+        const int r = ctx->lr_rank;
+        const int nc = r > 256 ? 2 : 1;
+        const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
+        p.BN = bn; p.n_chunks = nc;
+        for (int i = 0; i < 8; ++i) p.kb_start[i] = 0;
+        for (int i = 0; i < 32; ++i) p.nz_rows[i] = 32767;
+        ms = &us->lr;
+        int rc = ensure_maps(ctx, ms, ctx->Vh, ctx->Vl, ctx->KC_pad, SSPBO_LR_MAX, bn);
+        if (rc) return rc;
+        p.lowrank = 1;
+        p.prior_var = (float)(1.0 / ctx->alpha);
+        p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
+        p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
+    } else {
+        p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
+        for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
+        for (int i = 0; i < 32; ++i) p.nz_rows[i] = ctx->nz_rows[i];
+        ms = &us->full;
+        int rc = ensure_maps(ctx, ms, ctx->Rh, ctx->Rl, ctx->KC_pad, ctx->NJ_pad, ctx->BN);
+        if (rc) return rc;
+        p.stats = ctx->stats;
+    }
+    const size_t tb = table_bytes(ctx), sb = 2 * (size_t)p.BN * BK * 2;
+    const size_t avail = (size_t)us->max_smem - 1024 - tb;
+    int nb = (int)((avail - NA_MIN * A_SLOT_BYTES) / sb);
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two B slots");
-    const size_t smem = 1024 + NA * A_SLOT_BYTES + (size_t)nb * sb + tb;
+    int na = (int)((avail - (size_t)nb * sb) / A_SLOT_BYTES);
+    if (na > NA_MAX) na = NA_MAX;
+    const size_t smem = 1024 + (size_t)na * A_SLOT_BYTES + (size_t)nb * sb + tb;
     const bool traj = ctx->L != 1;
-    kernel_fn kern = kernel_for(ctx->n, traj);
+    const bool p32 = !traj && ctx->p32_ok && !ctx->p32_disabled && ctx->stats;
+    kernel_fn kern = kernel_for(ctx->n, traj, p32);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: domain dimension %d not instantiated", ctx->n);
-    const int attr_key = ctx->n + (traj ? 100 : 0);
-    if (us->attr_set_n != attr_key) {
+    if (!us->attr_set[traj][p32][ctx->n]) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, us->max_smem));
-        us->attr_set_n = attr_key;
+        us->attr_set[traj][p32][ctx->n] = true;
     }
-    Params p;
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
     p.Aq_op = ctx->Aq_op; p.mp_op = ctx->mp_op;
-    p.K = ctx->K; p.KC_pad = ctx->KC_pad; p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
-    p.n_kb = ctx->KC_pad / BK; p.nb = nb;
-    for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
-    for (int i = 0; i < 32; ++i) p.nz_rows[i] = ctx->nz_rows[i];
+    p.A32_op = ctx->A32_op; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
+    p.K = ctx->K; p.KC_pad = ctx->KC_pad;
+    p.n_kb = ctx->KC_pad / BK; p.nb = nb; p.na = na;
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
@@ -575,7 +680,38 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     }
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    kern<<<grid, THREADS, smem, st>>>(us->map_hi, us->map_lo, p);
+    kern<<<grid, THREADS, smem, st>>>(ms->hi, ms->lo, p);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
+}
+
+}  // namespace
+
+int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
+    if (!ctx->has_factor || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
+    if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    if (table_bytes(ctx) + NA_MIN * A_SLOT_BYTES + 2 * (2 * (size_t)ctx->BN * BK * 2) + 1024 > (size_t)max_smem) return 0;
+    return 1;
+}
+
+void sspbo_umma_release(sspbo_ctx* ctx) {
+    if (ctx->umma) {
+        UmmaState* us = (UmmaState*)ctx->umma;
+        if (us->xq) cudaFree(us->xq);
+        delete us; ctx->umma = nullptr;
+    }
+}
+
+int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+                            float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+    return launch(ctx, false, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
+}
+
+int sspbo_score_umma_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+                               float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+    return launch(ctx, true, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
 }

@@ -43,6 +43,7 @@ class DeviceEngine:
         self.n = 0
         self.L = 1
         self._best = self.torch.zeros(1, dtype=self.torch.int64, device=self._dev())
+        self._pending = []           # score calls since the last key reset (replayed if the device asks for a rerun)
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self):
@@ -99,6 +100,10 @@ class DeviceEngine:
         rc = self.lib.sspbo_space_set(self._ctx, a_plus.ctypes.data_as(_lib._pd), inv_ls.ctypes.data_as(_lib._pd), K, n)
         self._check(rc, "sspbo_space_set")
         self.d, self.K, self.n, self.L = d, K, n, 1
+
+    def set_xbound(self, x_absmax: float) -> None:
+        """Declared bound on |x| of every candidate coordinate (max |domain_bounds|); 0 = unknown."""
+        self._check(self.lib.sspbo_space_set_xbound(self._ctx, float(x_absmax)), "sspbo_space_set_xbound")
 
     def set_traj(self, tau: np.ndarray | None, L: int) -> None:
         """tau (L, K): phase in radians of timestep j at frequency k."""
@@ -204,10 +209,17 @@ class DeviceEngine:
             ptrs = [C.c_void_p(t.data_ptr()) for t in outs]
         if reset_best:
             self._best.zero_()
-        rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, int(index0),
-                                  float(lam), float(gamma_t), ptrs[0], ptrs[1], ptrs[2],
-                                  C.c_void_p(self._best.data_ptr()), int(engine), self._stream())
-        self._check(rc, "sspbo_score")
+            self._pending = []
+
+        def call():
+            rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, int(index0),
+                                      float(lam), float(gamma_t), ptrs[0], ptrs[1], ptrs[2],
+                                      C.c_void_p(self._best.data_ptr()), int(engine), self._stream())
+            self._check(rc, "sspbo_score")
+        call()
+        self._pending.append(call)
+        if want_outputs and self._needs_rerun():         # outputs are about to be read: settle them now
+            self._replay()
         return self._best, outs
 
     def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 20, reset_best=True):
@@ -233,6 +245,15 @@ class DeviceEngine:
         compute = torch.cuda.current_stream(self.device)
         if reset_best:
             self._best.zero_()
+            self._pending = []
+        call = lambda: self._score_host_stream(xt, N, lam, gamma_t, index0, engine, chunk)
+        call()
+        self._pending.append(call)
+        return self._best
+
+    def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk):
+        torch = self.torch
+        compute = torch.cuda.current_stream(self.device)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
@@ -251,8 +272,52 @@ class DeviceEngine:
             done[b].record(compute)
         return self._best
 
+    def score_stats(self, reset=True):
+        """Counters of the low-rank engine since the last reset (synchronises): dict(scored, flagged, overflow,
+        out_of_range, rerun).  `rerun` means results since the last reset must be recomputed (policy already switched)."""
+        v = [C.c_int64() for _ in range(4)]
+        rr = C.c_int()
+        rc = self.lib.sspbo_score_stats(self._ctx, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), C.byref(rr),
+                                        1 if reset else 0, self._stream())
+        self._check(rc, "sspbo_score_stats")
+        return dict(scored=v[0].value, flagged=v[1].value, overflow=v[2].value, out_of_range=v[3].value, rerun=bool(rr.value))
+
+    def lowrank_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self._check(self.lib.sspbo_lowrank_info(self._ctx, *[C.byref(x) for x in v]), "sspbo_lowrank_info")
+        return dict(rank=v[0].value, valid=bool(v[1].value), disabled=bool(v[2].value), phase32=bool(v[3].value))
+
+    def set_policy(self, lowrank=None, phase32=None):
+        enc = lambda f: -1 if f is None else int(bool(f))
+        self._check(self.lib.sspbo_set_policy(self._ctx, enc(lowrank), enc(phase32)), "sspbo_set_policy")
+
+    def _needs_rerun(self):
+        return self.score_stats(reset=True)["rerun"]
+
+    def settle(self):
+        """Make the key / outputs of the score calls since the last reset final (synchronises): if the low-rank pass
+        overflowed its flag list or saw candidates outside the declared bound, the calls are replayed with the safe
+        engines.  Call before combining keys across ranks; `best()` calls it."""
+        if self._pending:
+            if self._needs_rerun():
+                self._replay()
+            self._pending = []
+
+    def _replay(self):
+        """Recompute every score call since the last key reset (the context has switched to the safe engines)."""
+        calls, self._pending = self._pending, []
+        self._best.zero_()
+        for c in calls:
+            c()
+        self._pending = calls
+        st = self.score_stats(reset=True)
+        if st["rerun"]:
+            raise _lib.SspboError(f"scoring still asks for a rerun after the policy switch: {st}")
+
     def best(self):
-        """(score, index) of the packed key; synchronises."""
+        """(score, index) of the packed key; synchronises.  If the low-rank pass overflowed its flag list or saw
+        candidates outside the declared bound, the step is recomputed with the safe engines first."""
+        self.settle()
         return _lib.key_unpack(int(self._best.item()))
 
     def last_engine(self) -> str:

@@ -89,6 +89,8 @@ class SSPSpace:
             self._engine_ls = None
         if self._engine_ls is None or not np.array_equal(ls, self._engine_ls):
             self._engine.set_space(self.phase_matrix, ls)
+            if self.domain_bounds is not None:           # lets the scorer use its 32-bit fixed-point phase path
+                self._engine.set_xbound(float(np.max(np.abs(np.asarray(self.domain_bounds, dtype=np.float64)))))
             self._engine_ls = ls.copy()
         return self._engine
 

@@ -210,7 +210,10 @@ def _c3_setup(pkg, T, seed=1):
     return sp, model, ref, X
 
 
-@pytest.mark.parametrize("engine", ["simt", "umma", "auto"])
+ENGINE_LABEL = {"simt": "simt", "umma": "umma", "lowrank": "umma-lowrank", "auto": "umma-lowrank", "exact": "exact"}
+
+
+@pytest.mark.parametrize("engine", ["simt", "umma", "lowrank", "auto", "exact"])
 def test_score_c3_parity(pkg, engine):
     from ssp_bayesopt_b200 import _lib
     sp, model, ref, X = _c3_setup(pkg, 60)
@@ -222,9 +225,10 @@ def test_score_c3_parity(pkg, engine):
     phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
     ref_score, ref_idx = orc.score_and_argmax(phis, ref, lam, gam)
     eng = sp.engine
-    code = {"simt": _lib.ENGINE_SIMT, "umma": _lib.ENGINE_UMMA, "auto": _lib.ENGINE_AUTO}[engine]
+    code = {"simt": _lib.ENGINE_SIMT, "umma": _lib.ENGINE_UMMA, "auto": _lib.ENGINE_AUTO, "lowrank": _lib.ENGINE_UMMA_LR,
+            "exact": _lib.ENGINE_EXACT}[engine]
     _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=code)
-    assert eng.last_engine() == ("simt" if engine == "simt" else "umma")
+    assert eng.last_engine() == ENGINE_LABEL[engine]
     score = (mu + acq).double().cpu().numpy()
     ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gam)
     assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
@@ -283,6 +287,95 @@ def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
         # both engines agree far below the tolerance
         _, (mu2, var2, acq2) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_SIMT)
         np.testing.assert_allclose(var.cpu().numpy(), var2.cpu().numpy(), rtol=2e-5)
+
+
+@pytest.mark.parametrize("T,phase32", [(60, True), (60, False), (260, True), (300, True)])
+def test_score_lowrank_c3(pkg, T, phase32):
+    """Low-rank tcgen05 engine (S = I/alpha - V^T V, one row per observation) on config C3 at ranks 60 / 260 / 300
+    (one and two accumulator chunks), with candidates placed at every distance from the observations so that the
+    remaining prior variance spans (0, 1): the ones below the flag threshold must come back from the exact float64
+    pass, all within the 1e-4 tolerance; both phase paths (32-bit fixed point, Q31.32)."""
+    from ssp_bayesopt_b200 import _lib
+    sp, model, ref, X = _c3_setup(pkg, T)
+    eng = sp.engine
+    info = eng.lowrank_info()
+    assert info["rank"] == T and info["valid"] and info["phase32"]
+    eng.set_policy(phase32=phase32)
+    N = 6000
+    rng = np.random.default_rng(5)
+    xc = orc.counter_uniform(0, 0, N, 6)
+    for j, scale in enumerate((0.0, 1e-4, 1e-3, 3e-3, 1e-2, 2e-2, 4e-2, 8e-2, 0.15)):
+        xc[64 * j:64 * j + 60] = np.clip(X[:60] + scale * rng.normal(size=(60, 6)), 0, 1).astype(np.float32)
+    phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
+    eng.score_stats(reset=True)
+    for lam, gam in ((10.0, 0.0), (4.0, 900.0)):
+        ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gam)
+        ref_score = ref_mu.ravel() + ref_acq
+        _, (mu, var, acq) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_UMMA_LR)
+        assert eng.last_engine() == "umma-lowrank"
+        mu, var, acq = (t.double().cpu().numpy() for t in (mu, var, acq))
+        assert_scores_close(mu, acq, ref_mu, ref_acq)
+        np.testing.assert_allclose(var, ref_var, rtol=RTOL_SCORE)
+        s, idx = eng.best()
+        srt = np.sort(ref_score)[::-1]
+        if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert idx == int(np.argmax(ref_score))
+    # the exact pass was exercised (observed points have var << prior) but stayed a small minority
+    eng.score(xc, 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    st = eng.score_stats(reset=True)
+    assert st["scored"] == N and 60 <= st["flagged"] < N // 4 and st["overflow"] == 0 and st["out_of_range"] == 0, st
+    frac_prior = (ref_var - 1.0 / ref.beta) * 0.01                           # remaining fraction of the prior variance
+    assert frac_prior.min() < 1e-3 and frac_prior.max() > 0.5
+    eng.set_policy(phase32=True)
+
+
+def test_score_lowrank_policy_and_rerun(pkg):
+    """(a) candidates outside the declared bound: the 32-bit phase path reports them and the step is recomputed with
+    the Q31.32 path; (b) more flagged candidates than the list holds: recomputed with the full factor; the AUTO
+    engine then stays on the full factor; (c) import of a packed posterior invalidates the low-rank rows."""
+    from ssp_bayesopt_b200 import _lib
+    bounds = np.array([[-2.0, 2.0]] * 2)
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=0.7, rng=0)
+    ls = 0.7 * np.ones(2)
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-2, 2, (30, 2))
+    y = np.cos(X.sum(axis=1, keepdims=True))
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    ref = orc.BLR(sp.ssp_dim)
+    model.update(sp.encode(X), y)
+    ref.update(orc.encode(sp.phase_matrix, ls, X), y)
+    eng = sp.engine
+    assert eng.lowrank_info() == dict(rank=30, valid=True, disabled=False, phase32=True)
+    # (a)
+    xc = rng.uniform(-2, 2, (5000, 2))
+    xc[100] = [7500.0, -9.25]                                               # far outside the declared |x| <= 2
+    ref_score, ref_idx = orc.score_and_argmax(orc.encode(sp.phase_matrix, ls, xc), ref, 10.0, 0.0)
+    eng.score_stats(reset=True)
+    _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True)
+    score = (mu + acq).double().cpu().numpy()
+    assert np.max(np.abs(score - ref_score) / np.abs(ref_score)) < RTOL_SCORE
+    assert eng.best()[1] == ref_idx
+    assert not eng.lowrank_info()["phase32"]                                 # switched to the 64-bit phase path
+    eng.set_policy(phase32=True)
+    # (b)
+    N = (1 << 18) + 5000
+    xn = np.repeat(X, N // 30 + 1, axis=0)[:N] + 1e-3 * rng.normal(size=(N, 2))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, ls, xn[:3000]), ref, 10.0, 0.0)
+    _, (mu, var, acq) = eng.score(xn, 10.0, 0.0, want_outputs=True)
+    assert eng.last_engine() == "umma" and eng.lowrank_info()["disabled"]
+    assert_scores_close(mu[:3000].double().cpu().numpy(), acq[:3000].double().cpu().numpy(), ref_mu, ref_acq)
+    eng.score(xc[:4096], 10.0, 0.0)
+    assert eng.last_engine() == "umma"
+    eng.set_policy(lowrank=True)
+    eng.score(xc[:4096], 10.0, 0.0)
+    assert eng.last_engine() == "umma-lowrank"
+    # (c)
+    eng.blr_import(eng.blr_export(), model.beta)
+    assert not eng.lowrank_info()["valid"]
+    eng.score(xc[:4096], 10.0, 0.0)
+    assert eng.last_engine() == "umma"
+    with pytest.raises(Exception):
+        eng.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
 
 
 def test_score_host_streaming_matches_resident(pkg, golden):
