@@ -1072,10 +1072,13 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     const int d = ctx->d;
     const int64_t max_rows = from_flag_list ? (int64_t)SSPBO_FLAG_CAP : N;
-    // row blocks: spread a tiny set over the machine, one pass over Sp per group of EX_G candidates otherwise
-    int RB = 1;
+    // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs (64 rows each at d = 1023), so that
+    // a handful of candidates (the usual flagged count, or eval(x_t)) spreads over the machine instead of
+    // streaming all of Sp through one SM
+    int RB = EX_RB_MAX;
     if (!from_flag_list) {
         const int64_t groups = (N + EX_G - 1) / EX_G;
+        RB = 1;
         while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;
     }
     const size_t need = (size_t)max_rows * (RB + 1);
@@ -1090,7 +1093,7 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     const size_t smem = (size_t)EX_G * d * sizeof(double);
     const unsigned int* list = from_flag_list ? ctx->flag_idx : nullptr;
     const unsigned long long* cnt = from_flag_list ? ctx->stats + SSPBO_STAT_CUR : nullptr;
-    int gx = from_flag_list ? 2 * ctx->sm_count : (int)((N + EX_G - 1) / EX_G < 4 * ctx->sm_count ? (N + EX_G - 1) / EX_G : 4 * ctx->sm_count);
+    int gx = from_flag_list ? ctx->sm_count / 2 : (int)((N + EX_G - 1) / EX_G < 4 * ctx->sm_count ? (N + EX_G - 1) / EX_G : 4 * ctx->sm_count);
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, list, cnt, SSPBO_FLAG_CAP, ctx->A_turns,

@@ -112,7 +112,7 @@ constexpr int SSPBO_LR_MAX = 512;               // largest rank scored in low-ra
 // 2e-5 / alpha absolute on the variance.  Candidates whose variance is below this fraction of the prior variance
 // 1/alpha would exceed the 1e-4 tolerance after the subtraction and are re-scored by the exact float64 engine.
 constexpr double SSPBO_LR_FLAG_FRACTION = 0.3;
-constexpr unsigned SSPBO_FLAG_CAP = 1u << 18;    // flagged candidates per sspbo_score call that get the exact pass
+constexpr unsigned SSPBO_FLAG_CAP = 1u << 17;    // flagged candidates per sspbo_score call that get the exact pass
 // device counters (unsigned long long each)
 enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (reset by its exact pass)
        SSPBO_STAT_FLAGGED = 1,   // candidates re-scored exactly since the last reset

@@ -36,11 +36,16 @@ namespace {
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block = one 128-byte swizzle atom of fp16
-constexpr int GEN_WARPS = 8;            // 256 threads: (row pair, quarter) -> 2 rows x 8 frequencies of a k-block each
+#ifndef SSPBO_GEN_ROWS
+#define SSPBO_GEN_ROWS 2
+#endif
+constexpr int GEN_ROWS = SSPBO_GEN_ROWS;   // candidate rows per generator thread (1 or 2)
+constexpr int ROW_GROUPS = 4 / GEN_ROWS;   // generator warps per quarter of a k-block
+constexpr int GEN_WARPS = 4 * ROW_GROUPS;  // thread (row group, quarter) -> GEN_ROWS rows x 8 frequencies of a k-block
 constexpr int EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
-constexpr int GEN_THREADS = 32 * GEN_WARPS;                      // 256
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448 (GEN_ROWS = 2) or 704
+constexpr int GEN_THREADS = 32 * GEN_WARPS;
 constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB (one of hi / lo)
 constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
 constexpr int NA_MIN = 2, NA_MAX = 4;                            // A ring slots (as many as fit after the B ring)
@@ -84,6 +89,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
@@ -354,121 +368,150 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
     } else {
         // ================================ psi generators (A ring) ================================
-        const int gw = warp - WARP_GEN0;                                  // 0..7
-        const int r0 = (gw & 1) * 32 + lane, quarter = gw >> 1;           // rows r0 and r0 + 64; frequencies 8q .. 8q+7
+        // Thread (row group, quarter q) produces frequencies 8q .. 8q+7 of GEN_ROWS rows for every k-block (one
+        // shared-memory read of a phase-matrix entry feeds GEN_ROWS multiply-add chains).  Software pipeline per
+        // k-block: probe the slot's "empty" barrier without blocking, do the math into registers, publish the PREVIOUS
+        // k-block (its shared-memory stores have long completed, so the proxy fence is cheap), then store this one.
+        const int gw = warp - WARP_GEN0;
+        const int r0 = (gw % ROW_GROUPS) * 32 + lane, quarter = gw / ROW_GROUPS;
+        constexpr uint32_t ROW_STEP = 32 * ROW_GROUPS;                    // rows r0, r0 + ROW_STEP, ...; ROW_STEP % 8 == 0
         const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128);
-        const uint32_t sw = (uint32_t)(r0 & 7);                           // (r0 + 64) & 7 == r0 & 7
+        const uint32_t sw = (uint32_t)(r0 & 7);
         // one 16-byte chunk of cos (chunk q) and one of sin (chunk 4+q) per row and stage, XOR-swizzled by the row
         const uint32_t off_cos = row_off + (((uint32_t)quarter ^ sw) << 4);
         const uint32_t off_sin = row_off + (((uint32_t)(quarter + 4) ^ sw) << 4);
-        constexpr uint32_t ROW1 = 64 * 128;                               // byte offset of row r0 + 64 inside a tile
+        const int n_kb = p.n_kb, L = p.L;
+        const long long N = p.N;
         Ring ra;
         int tile_iter = 0;
+        bool pending = false; uint32_t pending_bar = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            unsigned long long x0[NDIM], x1[NDIM];                       // Q31.32 candidates (two's complement)
-            int xq0[NDIM], xq1[NDIM];                                     // Q.fx candidates of the 32-bit phase path
-            const long long g0 = tile * BM + r0, g1 = g0 + 64;
+            unsigned long long x0[GEN_ROWS][NDIM];                        // Q31.32 candidates (two's complement)
+            int xq0[GEN_ROWS][NDIM];                                      // Q.fx candidates of the 32-bit phase path
+            long long g[GEN_ROWS];
+#pragma unroll
+            for (int r = 0; r < GEN_ROWS; ++r) g[r] = tile * BM + r0 + r * ROW_STEP;
             if constexpr (P32) {
                 bool oor = false;
 #pragma unroll
-                for (int a = 0; a < NDIM; ++a) {
-                    double v0 = 0.0, v1 = 0.0;
-                    if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                    if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
-                    v0 *= p.x_scale; v1 *= p.x_scale;
-                    oor |= !(fabs(v0) < 2147483647.0) || !(fabs(v1) < 2147483647.0);
-                    xq0[a] = __double2int_rn(v0);
-                    xq1[a] = __double2int_rn(v1);
-                }
+                for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                    for (int a = 0; a < NDIM; ++a) {
+                        double v0 = 0.0;
+                        if (g[r] < N) v0 = p.x_f64 ? ((const double*)p.x)[g[r] * NDIM + a] : (double)((const float*)p.x)[g[r] * NDIM + a];
+                        v0 *= p.x_scale;
+                        oor |= !(fabs(v0) < 2147483647.0);
+                        xq0[r][a] = __double2int_rn(v0);
+                    }
                 if (oor && quarter == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);     // outside the declared |x| bound
             } else if constexpr (!TRAJ) {
 #pragma unroll
-                for (int a = 0; a < NDIM; ++a) {
-                    double v0 = 0.0, v1 = 0.0;
-                    if (g0 < p.N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                    if (g1 < p.N) v1 = p.x_f64 ? ((const double*)p.x)[g1 * NDIM + a] : (double)((const float*)p.x)[g1 * NDIM + a];
-                    x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
-                    x1[a] = (unsigned long long)__double2ll_rn(v1 * 4294967296.0);
+                for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                    for (int a = 0; a < NDIM; ++a) {
+                        double v0 = 0.0;
+                        if (g[r] < N) v0 = p.x_f64 ? ((const double*)p.x)[g[r] * NDIM + a] : (double)((const float*)p.x)[g[r] * NDIM + a];
+                        x0[r][a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                    }
+            }
+            if constexpr (!TRAJ) {                                        // next tile's rows: pull them towards the SM now
+                if (quarter == 0) {
+#pragma unroll
+                    for (int r = 0; r < GEN_ROWS; ++r) {
+                        const long long gn = g[r] + (long long)gridDim.x * BM;
+                        if (gn < N) {
+                            const char* nx = (const char*)p.x + (size_t)gn * NDIM * (p.x_f64 ? 8 : 4);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                        }
+                    }
                 }
             }
-            float mu0 = 0.f, mu1 = 0.f;
+            float mu0[GEN_ROWS];
+#pragma unroll
+            for (int r = 0; r < GEN_ROWS; ++r) mu0[r] = 0.f;
             for (int pr = 0; pr < n_pairs; ++pr)
-                for (int kb = p.kb_start[2 * pr]; kb < p.n_kb; ++kb) {
-                    const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
-                    float cs0[8], sn0[8], cs1[8], sn1[8];
+                for (int kb = p.kb_start[2 * pr]; kb < n_kb; ++kb) {
+                    const uint32_t empty_bar = a_empty(ra.slot);
+                    const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);         // early, non-blocking probe
+                    float cs[GEN_ROWS][8], sn[GEN_ROWS][8];
                     if constexpr (P32) {
                         const int* A32blk = (const int*)tables + (size_t)(kb * 32 + quarter * 8) * NDIM;
-                        long long t0[8], t1[8];                           // phase in turns at bit 55
+                        long long t[GEN_ROWS][8];                         // phase in turns at bit 55
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { t0[i] = 0ll; t1[i] = 0ll; }
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t[r][i] = 0ll;
 #pragma unroll
                         for (int a = 0; a < NDIM; ++a) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const int Afa = A32blk[i * NDIM + a];     // one broadcast read feeds both rows
-                                t0[i] += (long long)Afa * (long long)xq0[a];              // IMAD.WIDE
-                                t1[i] += (long long)Afa * (long long)xq1[a];
+                                const int Afa = A32blk[i * NDIM + a];     // one broadcast read feeds every row
+#pragma unroll
+                                for (int r = 0; r < GEN_ROWS; ++r) t[r][i] += (long long)Afa * (long long)xq0[r][a];   // IMAD.WIDE
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            // bits [32, 55) = top 23 bits of the phase mod 1; flipping the top one adds 1/2 turn, and
-                            // with the exponent of 1.0 they are the mantissa of f in [1, 2): (f - 1.5) 2 pi is the
-                            // phase in radians in [-pi, pi).  One LOP3: (hi & 0x7fffff) ^ 0x3fc00000.
-                            const float f0 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t0[i] >> 32), 0x7fffffu, 0x3fc00000u));
-                            const float f1 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t1[i] >> 32), 0x7fffffu, 0x3fc00000u));
-                            const float a0 = fmaf(f0, 6.283185307179586f, -9.42477796076938f);
-                            const float a1 = fmaf(f1, 6.283185307179586f, -9.42477796076938f);
-                            cs0[i] = __cosf(a0); sn0[i] = __sinf(a0);
-                            cs1[i] = __cosf(a1); sn1[i] = __sinf(a1);
-                        }
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                // bits [32, 55) = top 23 bits of the phase mod 1; flipping the top one adds 1/2 turn, and
+                                // with the exponent of 1.0 they are the mantissa of f in [1, 2): (f - 1.5) 2 pi is the
+                                // phase in radians in [-pi, pi).  One LOP3: (hi & 0x7fffff) ^ 0x3fc00000.
+                                const float f0 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t[r][i] >> 32), 0x7fffffu, 0x3fc00000u));
+                                const float a0 = fmaf(f0, 6.283185307179586f, -9.42477796076938f);
+                                cs[r][i] = __cosf(a0); sn[r][i] = __sinf(a0);
+                            }
                     } else if constexpr (!TRAJ) {
-                        unsigned long long t0[8], t1[8];                  // phase in turns, Q0.64, wraps modulo 1
+                        const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
+                        unsigned long long t[GEN_ROWS][8];                // phase in turns, Q0.64, wraps modulo 1
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { t0[i] = 0ull; t1[i] = 0ull; }
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t[r][i] = 0ull;
 #pragma unroll
                         for (int a = 0; a < NDIM; ++a) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const unsigned long long Afa = Ablk[i * NDIM + a];   // one broadcast read feeds both rows
-                                t0[i] += Afa * x0[a];
-                                t1[i] += Afa * x1[a];
+                                const unsigned long long Afa = Ablk[i * NDIM + a];
+#pragma unroll
+                                for (int r = 0; r < GEN_ROWS; ++r) t[r][i] += Afa * x0[r][a];
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
-                            float a0 = (float)(int)(t0[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
-                            float a1 = (float)(int)(t1[i] >> 32) * 1.4629180792671596e-9f;
-                            cs0[i] = __cosf(a0); sn0[i] = __sinf(a0);
-                            cs1[i] = __cosf(a1); sn1[i] = __sinf(a1);
-                        }
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
+                                float a0 = (float)(int)(t[r][i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
+                                cs[r][i] = __cosf(a0); sn[r][i] = __sinf(a0);
+                            }
                     } else {
                         // trajectory: the spectrum is the sum over the L waypoints of unit phasors
                         // exp(i (theta_f(x_j) + tau_jf))  (agents/ssp_traj_agent.py:145-163 in the Fourier domain)
+                        const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + quarter * 8) * NDIM;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { cs0[i] = 0.f; sn0[i] = 0.f; cs1[i] = 0.f; sn1[i] = 0.f; }
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { cs[r][i] = 0.f; sn[r][i] = 0.f; }
                         const int nf = p.KC_pad >> 1;
-                        for (int j = 0; j < p.L; ++j) {
+                        for (int j = 0; j < L; ++j) {
 #pragma unroll
-                            for (int a = 0; a < NDIM; ++a) {
-                                x0[a] = (g0 < p.N) ? __ldg(p.xq + ((size_t)g0 * p.L + j) * NDIM + a) : 0ull;
-                                x1[a] = (g1 < p.N) ? __ldg(p.xq + ((size_t)g1 * p.L + j) * NDIM + a) : 0ull;
-                            }
+                            for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                                for (int a = 0; a < NDIM; ++a)
+                                    x0[r][a] = (g[r] < N) ? __ldg(p.xq + ((size_t)g[r] * L + j) * NDIM + a) : 0ull;
                             const unsigned long long* tq = p.tauq + (size_t)j * nf + kb * 32 + quarter * 8;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                unsigned long long t0 = __ldg(tq + i), t1 = t0;
+                                const unsigned long long tau = __ldg(tq + i);
 #pragma unroll
-                                for (int a = 0; a < NDIM; ++a) {
-                                    const unsigned long long Afa = Ablk[i * NDIM + a];
-                                    t0 += Afa * x0[a];
-                                    t1 += Afa * x1[a];
+                                for (int r = 0; r < GEN_ROWS; ++r) {
+                                    unsigned long long t0 = tau;
+#pragma unroll
+                                    for (int a = 0; a < NDIM; ++a) t0 += Ablk[i * NDIM + a] * x0[r][a];
+                                    float a0 = (float)(int)(t0 >> 32) * 1.4629180792671596e-9f;
+                                    cs[r][i] += __cosf(a0); sn[r][i] += __sinf(a0);
                                 }
-                                float a0 = (float)(int)(t0 >> 32) * 1.4629180792671596e-9f;
-                                float a1 = (float)(int)(t1 >> 32) * 1.4629180792671596e-9f;
-                                cs0[i] += __cosf(a0); sn0[i] += __sinf(a0);
-                                cs1[i] += __cosf(a1); sn1[i] += __sinf(a1);
                             }
                         }
                     }
@@ -476,38 +519,43 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         const float* mcos = mp_s + kb * BK + quarter * 8;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            mu0 = fmaf(mcos[i], cs0[i], mu0); mu0 = fmaf(mcos[32 + i], sn0[i], mu0);
-                            mu1 = fmaf(mcos[i], cs1[i], mu1); mu1 = fmaf(mcos[32 + i], sn1[i], mu1);
+                            const float mc = mcos[i], ms = mcos[32 + i];
+#pragma unroll
+                            for (int r = 0; r < GEN_ROWS; ++r) { mu0[r] = fmaf(mc, cs[r][i], mu0[r]); mu0[r] = fmaf(ms, sn[r][i], mu0[r]); }
                         }
                     }
-                    uint32_t w0[16], w1[16];                              // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
+                    uint32_t w[GEN_ROWS][16];                             // [cos hi x4, cos lo x4, sin hi x4, sin lo x4]
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        split_pair(cs0[2 * i], cs0[2 * i + 1], w0[i], w0[4 + i]);
-                        split_pair(sn0[2 * i], sn0[2 * i + 1], w0[8 + i], w0[12 + i]);
-                        split_pair(cs1[2 * i], cs1[2 * i + 1], w1[i], w1[4 + i]);
-                        split_pair(sn1[2 * i], sn1[2 * i + 1], w1[8 + i], w1[12 + i]);
+                    for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            split_pair(cs[r][2 * i], cs[r][2 * i + 1], w[r][i], w[r][4 + i]);
+                            split_pair(sn[r][2 * i], sn[r][2 * i + 1], w[r][8 + i], w[r][12 + i]);
+                        }
+                    if (pending) {                                        // publish the previous k-block
+                        fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core
+                        mbar_arrive(pending_bar);
                     }
-                    // values are ready in registers before the slot is claimed: the wait overlaps the math above
-                    mbar_wait(a_empty(ra.slot), ra.phase ^ 1);
+                    if (!slot_free) mbar_wait(empty_bar, ra.phase ^ 1);
                     uint8_t* st = a_ring + (size_t)ra.slot * A_SLOT_BYTES;
-                    *reinterpret_cast<uint4*>(st + off_cos) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_cos) = make_uint4(w0[4], w0[5], w0[6], w0[7]);
-                    *reinterpret_cast<uint4*>(st + off_sin) = make_uint4(w0[8], w0[9], w0[10], w0[11]);
-                    *reinterpret_cast<uint4*>(st + A_TILE_BYTES + off_sin) = make_uint4(w0[12], w0[13], w0[14], w0[15]);
-                    *reinterpret_cast<uint4*>(st + ROW1 + off_cos) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-                    *reinterpret_cast<uint4*>(st + ROW1 + A_TILE_BYTES + off_cos) = make_uint4(w1[4], w1[5], w1[6], w1[7]);
-                    *reinterpret_cast<uint4*>(st + ROW1 + off_sin) = make_uint4(w1[8], w1[9], w1[10], w1[11]);
-                    *reinterpret_cast<uint4*>(st + ROW1 + A_TILE_BYTES + off_sin) = make_uint4(w1[12], w1[13], w1[14], w1[15]);
-                    if (pr == 0 && kb == p.n_kb - 1) {
-                        float* mpart = mu_part + (tile_iter & 1) * 4 * BM + quarter * BM;
-                        mpart[r0] = mu0; mpart[r0 + 64] = mu1;
+#pragma unroll
+                    for (int r = 0; r < GEN_ROWS; ++r) {
+                        uint8_t* sr = st + r * (ROW_STEP * 128);          // 128 bytes per row inside a tile
+                        *reinterpret_cast<uint4*>(sr + off_cos) = make_uint4(w[r][0], w[r][1], w[r][2], w[r][3]);
+                        *reinterpret_cast<uint4*>(sr + A_TILE_BYTES + off_cos) = make_uint4(w[r][4], w[r][5], w[r][6], w[r][7]);
+                        *reinterpret_cast<uint4*>(sr + off_sin) = make_uint4(w[r][8], w[r][9], w[r][10], w[r][11]);
+                        *reinterpret_cast<uint4*>(sr + A_TILE_BYTES + off_sin) = make_uint4(w[r][12], w[r][13], w[r][14], w[r][15]);
                     }
-                    fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core
-                    mbar_arrive(a_full(ra.slot));
+                    if (pr == 0 && kb == n_kb - 1) {
+                        float* mpart = mu_part + (tile_iter & 1) * 4 * BM + quarter * BM;
+#pragma unroll
+                        for (int r = 0; r < GEN_ROWS; ++r) mpart[r0 + r * ROW_STEP] = mu0[r];
+                    }
+                    pending = true; pending_bar = a_full(ra.slot);
                     ra.advance(NA);
                 }
         }
+        if (pending) { fence_proxy_async(); mbar_arrive(pending_bar); }
     }
 
     // ---- teardown ----
@@ -642,11 +690,14 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
     }
     const size_t tb = table_bytes(ctx), sb = 2 * (size_t)p.BN * BK * 2;
     const size_t avail = (size_t)us->max_smem - 1024 - tb;
-    int nb = (int)((avail - NA_MIN * A_SLOT_BYTES) / sb);
-    if (nb > MAX_NB) nb = MAX_NB;
-    if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two B slots");
-    int na = (int)((avail - (size_t)nb * sb) / A_SLOT_BYTES);
-    if (na > NA_MAX) na = NA_MAX;
+    // a deep A ring first (it decouples the generator warps from each other and from the MMA latency), three B
+    // slots cover the TMA latency, the rest goes to B
+    int na = NA_MAX, nb = 3;
+    while (na > NA_MIN && (size_t)na * A_SLOT_BYTES + (size_t)nb * sb > avail) --na;
+    while (nb > 2 && (size_t)na * A_SLOT_BYTES + (size_t)nb * sb > avail) --nb;
+    if ((size_t)na * A_SLOT_BYTES + (size_t)nb * sb > avail)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "tcgen05 engine: shared memory does not fit two B slots");
+    while (nb < MAX_NB && (size_t)na * A_SLOT_BYTES + (size_t)(nb + 1) * sb <= avail) ++nb;
     const size_t smem = 1024 + (size_t)na * A_SLOT_BYTES + (size_t)nb * sb + tb;
     const bool traj = ctx->L != 1;
     const bool p32 = !traj && ctx->p32_ok && !ctx->p32_disabled && ctx->stats;

@@ -358,7 +358,7 @@ def test_score_lowrank_policy_and_rerun(pkg):
     assert not eng.lowrank_info()["phase32"]                                 # switched to the 64-bit phase path
     eng.set_policy(phase32=True)
     # (b)
-    N = (1 << 18) + 5000
+    N = (1 << 17) + 5000
     xn = np.repeat(X, N // 30 + 1, axis=0)[:N] + 1e-3 * rng.normal(size=(N, 2))
     ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, ls, xn[:3000]), ref, 10.0, 0.0)
     _, (mu, var, acq) = eng.score(xn, 10.0, 0.0, want_outputs=True)
