@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsspbo.so")
+LIB_PATH = os.environ.get("SSPBO_LIB") or os.path.join(_HERE, "lib", "libsspbo.so")   # SSPBO_LIB: kernel-variant experiments
 
 F32, F64 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_UMMA, ENGINE_EXACT, ENGINE_UMMA_LR = 0, 1, 2, 3, 4

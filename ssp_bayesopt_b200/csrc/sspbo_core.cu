@@ -8,6 +8,7 @@
 //   SSPSpace.get_sample_points     sspspace.py:488-495
 #include "sspbo_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -291,10 +292,13 @@ __global__ void k_refresh_umma_operands(const double* __restrict__ L, const doub
 
 // low-rank scoring operand: row r of V (operand order, split fp16) = y sqrt(coef) r_scale, coef = beta / (1 + beta psi.y)
 __global__ void k_lr_append(const double* __restrict__ y, const double* __restrict__ coef, const int* __restrict__ col_of_rank,
-                            int d, double r_scale, __half* __restrict__ vh_row, __half* __restrict__ vl_row) {
+                            int d, double r_scale, __half* __restrict__ vh_row, __half* __restrict__ vl_row,
+                            double* __restrict__ vd_row) {
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= d) return;
-    const double v = y[kk] * sqrt(*coef) * r_scale;
+    const double v0 = y[kk] * sqrt(*coef);
+    vd_row[kk] = v0;                                    // float64 row in rank order (exact pass over flagged candidates)
+    const double v = v0 * r_scale;
     const __half h = __double2half(v);
     const int c = col_of_rank[kk];
     vh_row[c] = h;
@@ -383,6 +387,86 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restr
             }
         }
     }
+}
+
+// Flagged candidates of the low-rank pass, re-scored in float64 in the same low-rank form (no cancellation issue at
+// 1e-16): var = 1/beta + 1/alpha - sum_j (v_j . psi)^2, mu = m' . psi.  One CTA per group of EX_G candidates
+// (persistent over the device-side count), psi in shared memory, one warp per row of V.
+template <typename XT>
+__global__ void __launch_bounds__(EX_THREADS)
+k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
+                unsigned int cap, const double* __restrict__ A_turns, int n, int K, const int* __restrict__ inv_perm,
+                const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
+                double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
+                float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
+    extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
+    __shared__ double red[EX_G + 1][EX_THREADS / 32];
+    const int d = 2 * K + 1;
+    const unsigned long long c0 = *count_ptr;
+    const int64_t count = (int64_t)(c0 < cap ? c0 : cap);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long my_best = 0ull;
+    for (int64_t base = (int64_t)blockIdx.x * EX_G; base < count; base += (int64_t)gridDim.x * EX_G) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < EX_G * (K + 1); i += blockDim.x) {
+            const int c = i / (K + 1), f = i - c * (K + 1);
+            double cs = 0.0, sn = 0.0;
+            if (base + c < count) {
+                if (f == 0) cs = 1.0;
+                else psi_entry(x + (int64_t)list[base + c] * n, A_turns, (const double*)nullptr, n, K, 1, f - 1, cs, sn);
+            }
+            if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
+            else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
+        }
+        __syncthreads();
+        double q[EX_G];
+#pragma unroll
+        for (int c = 0; c < EX_G; ++c) q[c] = 0.0;
+        for (int j = warp; j < r; j += EX_THREADS / 32) {
+            const double* vrow = Vd + (size_t)j * d;
+            double acc[EX_G];
+#pragma unroll
+            for (int c = 0; c < EX_G; ++c) acc[c] = 0.0;
+            for (int k = lane; k < d; k += 32) {
+                const double v = vrow[k];
+#pragma unroll
+                for (int c = 0; c < EX_G; ++c) acc[c] = fma(v, psi_s[c * d + k], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < EX_G; ++c) { const double yj = warp_sum(acc[c]); q[c] = fma(yj, yj, q[c]); }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < EX_G; ++c) red[c][warp] = q[c];
+        }
+        __syncthreads();
+        if (warp < EX_G && base + warp < count) {       // one warp per candidate: mu, then the final scalars
+            double u = 0.0;
+            for (int rk = lane; rk < d; rk += 32) u = fma(mp[perm[rk]], psi_s[warp * d + rk], u);
+            u = warp_sum(u);
+            if (lane == 0) {
+                double qq = 0.0;
+#pragma unroll
+                for (int w = 0; w < EX_THREADS / 32; ++w) qq += red[warp][w];
+                const double var = inv_beta + (prior_var - qq);                         // blr.py:96
+                const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
+                const int64_t row = (int64_t)list[base + warp];
+                if (mu_out) mu_out[row] = (float)u;
+                if (var_out) var_out[row] = (float)var;
+                if (acq_out) acq_out[row] = (float)acq;
+                const unsigned long long key = sspbo_pack((float)(u + acq), (unsigned long long)(index0 + row));
+                if (key > my_best) my_best = key;
+            }
+        }
+    }
+    if (lane == 0 && my_best && best) atomicMax(best, my_best);
+}
+// folds the per-call flag counter into the totals (after the exact pass has consumed it)
+__global__ void k_flag_fold(unsigned long long* __restrict__ stats, unsigned int cap, unsigned long long scored) {
+    const unsigned long long c = stats[SSPBO_STAT_CUR];
+    stats[SSPBO_STAT_FLAGGED] += (c < cap ? c : cap);
+    stats[SSPBO_STAT_SCORED] += scored;
+    stats[SSPBO_STAT_CUR] = 0ull;
 }
 
 __global__ void k_exact_finish(int64_t N, const unsigned int* __restrict__ list, unsigned long long* __restrict__ stats,
@@ -608,7 +692,7 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
-    dev_free(&ctx->Vh); dev_free(&ctx->Vl); ctx->lr_rank = 0; ctx->lr_valid = false;
+    dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); ctx->lr_rank = 0; ctx->lr_valid = false;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -617,6 +701,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     sspbo_umma_release(ctx);
+    sspbo_lr_release(ctx);
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
@@ -819,6 +904,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             (rc = dev_alloc(ctx, &ctx->mp_op, (size_t)ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->Vh, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->Vl, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Vd, (size_t)SSPBO_LR_MAX * d)) ||
             (rc = dev_alloc(ctx, &ctx->psi, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->y, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->phi_tmp, (size_t)d)))
             return rc;
@@ -936,7 +1022,7 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     SSPBO_LAUNCH_CHECK(ctx);                                    // (the rank-one launch above)
                     const size_t off = (size_t)ctx->lr_rank * ctx->KC_pad;
                     k_lr_append<<<(d + 255) / 256, 256, 0, st>>>(ctx->y, ctx->scal + 2, ctx->col_of_rank, d, ctx->r_scale,
-                                                                 ctx->Vh + off, ctx->Vl + off);
+                                                                 ctx->Vh + off, ctx->Vl + off, ctx->Vd + (size_t)ctx->lr_rank * d);
                     ctx->lr_rank++;
                 }
             }
@@ -1071,7 +1157,26 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
                              cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     const int d = ctx->d;
-    const int64_t max_rows = from_flag_list ? (int64_t)SSPBO_FLAG_CAP : N;
+    if (from_flag_list) {                               // flagged by the low-rank pass: float64 low-rank form
+        const size_t smem = (size_t)EX_G * d * sizeof(double);
+        const int gx = 2 * ctx->sm_count;
+        if (x_dtype == SSPBO_F32) {
+            SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_exact_lowrank<float><<<gx, EX_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
+        } else {
+            SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_exact_lowrank<double><<<gx, EX_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
+        }
+        SSPBO_LAUNCH_CHECK(ctx);
+        k_flag_fold<<<1, 1, 0, st>>>(ctx->stats, SSPBO_FLAG_CAP, (unsigned long long)N);
+        SSPBO_LAUNCH_CHECK(ctx);
+        return SSPBO_OK;
+    }
+    const int64_t max_rows = N;
     // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs (64 rows each at d = 1023), so that
     // a handful of candidates (the usual flagged count, or eval(x_t)) spreads over the machine instead of
     // streaming all of Sp through one SM
@@ -1140,9 +1245,13 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
     if (engine == SSPBO_ENGINE_EXACT)
         return sspbo_score_exact_launch(ctx, x, x_dtype, N, false, index0, lam, gamma_t, mu, var, acq, best, st);
     if (engine == SSPBO_ENGINE_UMMA_LR) {
-        int rc = sspbo_score_umma_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+        // ranks up to 256: A operand in tensor memory (sspbo_score_lr.cu); beyond: shared-memory A ring, two 256-column chunks
+        int rc = sspbo_score_lr_supported(ctx)
+                     ? sspbo_score_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st)
+                     : sspbo_score_umma_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
         if (rc) return rc;
         // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
+        { const char* dbg = getenv("SSPBO_DEBUG"); if (dbg && (atoi(dbg) & 4)) return SSPBO_OK; }   // timing experiments only
         return sspbo_score_exact_launch(ctx, x, x_dtype, N, true, index0, lam, gamma_t, mu, var, acq, best, st);
     }
     int rc = sspbo_refresh_operands(ctx, st);

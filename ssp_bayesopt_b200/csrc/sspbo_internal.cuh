@@ -62,6 +62,7 @@ struct sspbo_ctx {
     // Only the split-fp16 image in operand order is kept (SSPBO_LR_MAX x KC_pad, K-major, rows >= lr_rank are zero).
     __half* Vh = nullptr;
     __half* Vl = nullptr;
+    double* Vd = nullptr;            // float64 rows of V in rank order (SSPBO_LR_MAX x d): exact pass over flagged candidates
     int lr_rank = 0;
     bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)
     bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead
@@ -81,8 +82,9 @@ struct sspbo_ctx {
     // scratch d-vectors (float64)
     double *v = nullptr, *psi = nullptr, *y = nullptr, *z = nullptr, *phi_tmp = nullptr;
     double* scal = nullptr;          // a few device scalars
-    // opaque state of the tcgen05 engine (tensor maps etc.)
+    // opaque state of the tcgen05 engines (tensor maps etc.)
     void* umma = nullptr;
+    void* lr_state = nullptr;
 };
 
 #define SSPBO_FAIL(ctx, code, ...)                                         \
@@ -157,6 +159,13 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
 int sspbo_score_umma_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
                                float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_umma_release(sspbo_ctx* ctx);
+// low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
+int sspbo_score_lr_supported(const sspbo_ctx* ctx);
+int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+                          float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
+void sspbo_lr_release(sspbo_ctx* ctx);
+// CUtensorMap (passed as void*) of a K-major fp16 operand [rows x KC_pad], box 64 columns x BN rows, 128-byte swizzle
+int sspbo_make_map_f16(sspbo_ctx* ctx, void* map, const void* base, int KC_pad, int rows, int BN);
 int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st);
 // exact float64 scorer: rows `list[0..*count)` of x (list == nullptr: rows 0..N-1)
 int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, bool from_flag_list, int64_t index0,

@@ -1,0 +1,467 @@
+// K2, low-rank tcgen05 engine: fused encode + BLR acquisition + argmax while the posterior has rank r <= 255.
+//
+//   Sp = Sp0 - V^T V   (one row of V per observation, sspbo_core.cu:k_lr_append), psi^T Sp0 psi = |phi|^2 / alpha = 1 / alpha
+//   var = 1/beta + 1/alpha - |V psi|^2,   mu = m' . psi
+//
+// so the contraction is 128 candidates x 1024 (psi) x r instead of x 1023: at r = 64 sixteen times fewer tensor flops
+// than the dense quadratic form, and the kernel is bound by generating psi.  Everything about psi is therefore kept
+// off shared memory: the generator warps write the split-fp16 psi k-block (A operand) straight into TENSOR MEMORY
+// with tcgen05.st, and tcgen05.mma reads A from TMEM and only the V slab (B operand, TMA-fed) from shared memory.
+//
+// Per CTA (persistent, one per SM), per tile of 128 candidates:
+//   generator warps (8)  thread <-> candidate row (TMEM lane = row, the warp's lane quadrant is warp % 4), 16 of the 32
+//                        frequencies of a k-block each.  theta_f = A_f . x in fixed point (32-bit operands with
+//                        fa + fx = 55 -> one IMAD.WIDE per axis, or Q31.32 x Q31.32), the phase bits become the
+//                        mantissa of a float in [1, 2), MUFU sin/cos, split into fp16 hi/lo, tcgen05.st into the
+//                        A ring (4 slots x 64 columns: 32 hi + 32 lo).  mu = m' . psi accumulates in float32.
+//   TMA warp             streams V_hi / V_lo slabs (64 columns x BN rows) through the B ring.
+//   MMA warp             per k-block and chunk: 4 x 3 tcgen05.mma (M=128, N=BN, K=16): psi_hi V_hi^T + psi_hi V_lo^T +
+//                        psi_lo V_hi^T into a float32 accumulator in TMEM.
+//   epilogue warps (4)   q = sum_j Y_j^2, var = 1/beta + 1/alpha - q, acquisition, packed-key argmax; candidates with
+//                        var < SSPBO_LR_FLAG_FRACTION / alpha are appended to the flag list instead (the exact float64
+//                        engine re-scores them right after this kernel, sspbo_core.cu:k_exact_*).
+// TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,512) A ring.
+// Rank: r_eff = r rows, one chunk of BN = ceil16(r) <= 128 rows (accumulators alternate by tile), or two chunks of
+// <= 128 rows (accumulator = chunk).
+//
+// Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
+#include "sspbo_internal.cuh"
+#include "sspbo_tc.cuh"
+#include <stdlib.h>
+
+namespace {
+using namespace sspbo_tc;
+
+constexpr int BM = 128;                 // candidates per tile (UMMA M)
+constexpr int BK = 64;                  // operand columns per k-block
+constexpr int GEN_WARPS = 8, EPI_WARPS = 4;
+constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
+constexpr int NF = 16;                  // frequencies per generator thread and k-block
+constexpr int NA_MAX = 6;               // A ring slots in TMEM: 4 behind 128-column accumulators, 6 behind 64-column ones
+constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp16 per column)
+constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
+constexpr int MAX_NB = 8;
+constexpr int MAX_N = 8;
+
+struct Params {
+    const void* x; int x_f64; long long N; long long index0;
+    const long long* Aq_op; const int* A32_op; const float* mp_op; double x_scale;
+    int KC_pad, BN, n_chunks, n_kb, nb;
+    int na, acc_cols;                   // A ring slots; columns reserved per accumulator (64 or 128)
+    float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
+    float *mu, *var, *acq;
+    unsigned long long* best;
+    unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
+    int debug;
+};
+
+template <int NDIM, bool P32>
+__global__ void __launch_bounds__(THREADS, 1)
+k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NA = p.na;
+    const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = 2u * ACC_COLS;
+    const int b_tile_bytes = p.BN * BK * 2;
+    const int b_slot_bytes = 2 * b_tile_bytes;
+    uint8_t* b_ring = smem;
+    uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
+    long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM (int32 in the P32 path)
+    float* mp_s = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
+    float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][2 halves][128]
+    uint64_t* bars = (uint64_t*)(mu_part + 2 * 2 * BM);
+    // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
+    const uint32_t bar0 = smem_u32(bars);
+    auto a_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (uint32_t)(NA + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (uint32_t)(2 * NA + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * NA + p.nb + s); };
+    auto tmem_full = [&](int b) { return bar0 + 8u * (uint32_t)(2 * NA + 2 * p.nb + b); };
+    auto tmem_empty = [&](int b) { return bar0 + 8u * (uint32_t)(2 * NA + 2 * p.nb + 2 + b); };
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
+
+    // ---- one-time setup ----
+    if constexpr (P32) {
+        int* A32_s = (int*)tables;
+        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) A32_s[i] = p.A32_op[i];
+    } else {
+        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
+    }
+    for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
+    if (warp == WARP_TMA && lane == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_WARPS); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS * 32); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long n_tiles = (p.N + BM - 1) / BM;
+    const int n_kb = p.n_kb, n_chunks = p.n_chunks;
+    // accumulator of chunk c: with a single chunk per tile the two buffers alternate by tile instead
+    auto acc_of = [&](int tile_iter, int c) { return n_chunks == 1 ? (tile_iter & 1) : c; };
+
+    if (warp == WARP_TMA) {
+        // ================================ TMA producer (B ring) ================================
+        if (lane == 0) {
+            Ring rb;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int kb = 0; kb < n_kb; ++kb)
+                    for (int c = 0; c < n_chunks; ++c) {
+                        mbar_wait_relaxed<400>(b_empty(rb.slot), rb.phase ^ 1);
+                        uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
+                        mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
+                        tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, c * p.BN);
+                        tma_load_2d(smem_u32(st + b_tile_bytes), &map_lo, b_full(rb.slot), kb * BK, c * p.BN);
+                        rb.advance(p.nb);
+                    }
+        }
+    } else if (warp == WARP_MMA) {
+        // ================================ MMA issuer ================================
+        // The whole warp walks the pipeline (warp-uniform control flow keeps ring state and descriptors in uniform
+        // registers); one elected lane issues.  With N <= 128 an MMA retires in 32-64 cycles, so the issue sequence
+        // itself must stay at a few instructions per tcgen05.mma.
+        Ring ra, rb;
+        uint32_t acc_phase[2] = {0, 0};
+        const uint32_t idesc = make_idesc(BM, p.BN);
+        const bool no_mma = (p.debug & 1) != 0;
+        int tile_iter = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
+                tc_fence_after();
+                const uint32_t a_hi = tmem_base + A_RING_COL0 + (uint32_t)(ra.slot * A_SLOT_COLS);
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int buf = acc_of(tile_iter, c);
+                    if (kb == 0) {                                        // first use of this accumulator in the tile: the
+                        mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);   // epilogue must have drained it
+                        acc_phase[buf] ^= 1;
+                    }
+                    mbar_wait(b_full(rb.slot), rb.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
+                    const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + b_tile_bytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+                    if (elect_one()) {
+                        if (!no_mma) {
+                            // kk = 0: the first MMA of a tile overwrites the accumulator
+                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
+                            umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+#pragma unroll
+                            for (int kk = 1; kk < BK / 16; ++kk) {
+                                // 16 fp16 along K = 32 bytes in shared memory (descriptor units of 16 B) = 8 TMEM columns
+                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                            }
+                        }
+                        umma_commit(b_empty(rb.slot));                    // frees the B slot when these MMAs retire
+                        if (kb == n_kb - 1) umma_commit(tmem_full(buf));
+                    }
+                    __syncwarp();
+                    rb.advance(p.nb);
+                }
+                if (elect_one()) umma_commit(a_empty(ra.slot));           // frees the A slot
+                __syncwarp();
+                ra.advance(NA);
+            }
+    } else if (warp < WARP_GEN0) {
+        // ================================ epilogue ================================
+        const int quad = warp & 3;                                        // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;
+        uint32_t acc_phase[2] = {0, 0};
+        int tile_iter = 0;
+        unsigned long long my_best = 0ull;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            float q = 0.f;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int buf = acc_of(tile_iter, c);
+                mbar_wait_relaxed<800>(tmem_full(buf), acc_phase[buf]);
+                acc_phase[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * ACC_COLS;
+                for (int g = 0; g < p.BN; g += 64) {                      // BN % 16 == 0; up to 64 columns in flight
+                    uint32_t v[64];
+                    const int nld = min(4, (p.BN - g) >> 4);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+                        if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
+                    tmem_ld_wait();
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+                        if (l < nld) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float y0 = __uint_as_float(v[16 * l + i]), y1 = __uint_as_float(v[16 * l + i + 1]);
+                                float y2 = __uint_as_float(v[16 * l + i + 2]), y3 = __uint_as_float(v[16 * l + i + 3]);
+                                q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1); q2 = fmaf(y2, y2, q2); q3 = fmaf(y3, y3, q3);
+                            }
+                        }
+                    q += (q0 + q1) + (q2 + q3);
+                }
+                tc_fence_before();
+                mbar_arrive(tmem_empty(buf));
+            }
+            const long long gi = tile * BM + row;
+            if (gi < p.N) {
+                const float* mpart = mu_part + (tile_iter & 1) * 2 * BM;
+                const float mu = mpart[row] + mpart[BM + row];
+                const float rem = p.prior_var - q * p.inv_rscale2;                    // 1/alpha - |V psi|^2
+                const float var = p.inv_beta + rem;                                   // blr.py:96
+                bool flagged = false;
+                if (var < p.flag_below) {                                             // too close to the observations for
+                    const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
+                    if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                    else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
+                }
+                if (!flagged) {
+                    const float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
+                    const float score = mu + acq;
+                    if (p.mu) p.mu[gi] = mu;
+                    if (p.var) p.var[gi] = var;
+                    if (p.acq) p.acq[gi] = acq;
+                    const unsigned long long key = sspbo_pack(score, (unsigned long long)(p.index0 + gi));
+                    if (key > my_best) my_best = key;
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, my_best, o);
+            if (other > my_best) my_best = other;
+        }
+        if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
+    } else {
+        // ================================ psi generators (A ring in tensor memory) ================================
+        // Software pipeline per k-block: probe the slot's "empty" barrier without blocking, do the math into
+        // registers, publish the PREVIOUS k-block (its tcgen05.st have long completed), then store this one.
+        const int gw = warp - WARP_GEN0;                                  // 0..7
+        const int quad = warp & 3, half = gw >> 2;                        // TMEM lane quadrant, frequency half of the k-block
+        const int r0 = quad * 32 + lane;                                  // candidate row of this thread = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + A_RING_COL0;
+        const long long N = p.N;
+        Ring ra;
+        int tile_iter = 0;
+        bool pending = false; uint32_t pending_bar = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            unsigned long long x0[NDIM];                                  // Q31.32 candidate (two's complement)
+            int xq0[NDIM];                                                // Q.fx candidate of the 32-bit phase path
+            const long long g0 = tile * BM + r0;
+            if constexpr (P32) {
+                bool oor = false;
+#pragma unroll
+                for (int a = 0; a < NDIM; ++a) {
+                    double v0 = 0.0;
+                    if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                    v0 *= p.x_scale;
+                    oor |= !(fabs(v0) < 2147483647.0);
+                    xq0[a] = __double2int_rn(v0);
+                }
+                if (oor && half == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);        // outside the declared |x| bound
+            } else {
+#pragma unroll
+                for (int a = 0; a < NDIM; ++a) {
+                    double v0 = 0.0;
+                    if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                    x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                }
+            }
+            {                                                             // next tile's row: pull it towards the SM now
+                const long long gn = g0 + (long long)gridDim.x * BM;
+                if (half == 0 && gn < N) {
+                    const char* nx = (const char*)p.x + (size_t)gn * NDIM * (p.x_f64 ? 8 : 4);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                }
+            }
+            float mu0 = 0.f;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const uint32_t empty_bar = a_empty(ra.slot);
+                const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);             // early, non-blocking probe
+                float cs[NF], sn[NF];
+                if (p.debug & 2) {
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
+                } else if constexpr (P32) {
+                    const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;
+                    long long t[NF];                                      // phase in turns at bit 55
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) t[i] = 0ll;
+#pragma unroll
+                    for (int a = 0; a < NDIM; ++a) {
+#pragma unroll
+                        for (int i = 0; i < NF; ++i) t[i] += (long long)A32blk[i * NDIM + a] * (long long)xq0[a];   // IMAD.WIDE
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        // bits [32, 55) = top 23 bits of the phase mod 1; flipping the top one adds 1/2 turn, and with
+                        // the exponent of 1.0 they are the mantissa of f in [1, 2): (f - 1.5) 2 pi is the phase in
+                        // radians in [-pi, pi).  One LOP3: (hi & 0x7fffff) ^ 0x3fc00000.
+                        const float f0 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t[i] >> 32), 0x7fffffu, 0x3fc00000u));
+                        const float a0 = fmaf(f0, 6.283185307179586f, -9.42477796076938f);
+                        cs[i] = __cosf(a0); sn[i] = __sinf(a0);
+                    }
+                } else {
+                    const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + half * NF) * NDIM;
+                    unsigned long long t[NF];                             // phase in turns, Q0.64, wraps modulo 1
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) t[i] = 0ull;
+#pragma unroll
+                    for (int a = 0; a < NDIM; ++a) {
+#pragma unroll
+                        for (int i = 0; i < NF; ++i) t[i] += Ablk[i * NDIM + a] * x0[a];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
+                        const float a0 = (float)(int)(t[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
+                        cs[i] = __cosf(a0); sn[i] = __sinf(a0);
+                    }
+                }
+                {
+                    const float* mcos = mp_s + kb * BK + half * NF;
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) { mu0 = fmaf(mcos[i], cs[i], mu0); mu0 = fmaf(mcos[32 + i], sn[i], mu0); }
+                }
+                uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
+#pragma unroll
+                for (int i = 0; i < NF / 2; ++i) {
+                    split_pair(cs[2 * i], cs[2 * i + 1], wch[i], wcl[i]);
+                    split_pair(sn[2 * i], sn[2 * i + 1], wsh[i], wsl[i]);
+                }
+                if (pending) {                                            // publish the previous k-block
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pending_bar);
+                }
+                if (!slot_free) mbar_wait(empty_bar, ra.phase ^ 1);
+                tc_fence_after();
+                // operand order inside a k-block: K index i < 32 is cos(f = i), i >= 32 is sin(f = i - 32); two fp16 per
+                // TMEM column, hi part in columns [0, 32), lo part in [32, 64) of the slot
+                const uint32_t slot_addr = lane_addr + (uint32_t)(ra.slot * A_SLOT_COLS) + (uint32_t)(half * (NF / 2));
+                tmem_st8(slot_addr, wch);
+                tmem_st8(slot_addr + 16, wsh);
+                tmem_st8(slot_addr + 32, wcl);
+                tmem_st8(slot_addr + 48, wsl);
+                if (kb == n_kb - 1) mu_part[(tile_iter & 1) * 2 * BM + half * BM + r0] = mu0;
+                pending = true; pending_bar = a_full(ra.slot);
+                ra.advance(NA);
+            }
+        }
+        if (pending) { tmem_st_wait(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(pending_bar); }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct LrState {
+    CUtensorMap hi, lo;
+    const void* bh = nullptr; const void* bl = nullptr;
+    int KC_pad = 0, BN = 0;
+    int max_smem = 0;
+    bool attr_set[2][MAX_N + 1] = {};
+};
+
+size_t table_bytes(const sspbo_ctx* ctx) {
+    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
+           2 * 2 * BM * sizeof(float) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
+}
+
+typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
+kernel_fn kernel_for(int n, bool p32) {
+    if (p32) {
+        switch (n) {
+            case 1: return k_score_lr<1, true>; case 2: return k_score_lr<2, true>; case 3: return k_score_lr<3, true>;
+            case 4: return k_score_lr<4, true>; case 5: return k_score_lr<5, true>; case 6: return k_score_lr<6, true>;
+            case 7: return k_score_lr<7, true>; case 8: return k_score_lr<8, true>;
+        }
+        return nullptr;
+    }
+    switch (n) {
+        case 1: return k_score_lr<1, false>; case 2: return k_score_lr<2, false>; case 3: return k_score_lr<3, false>;
+        case 4: return k_score_lr<4, false>; case 5: return k_score_lr<5, false>; case 6: return k_score_lr<6, false>;
+        case 7: return k_score_lr<7, false>; case 8: return k_score_lr<8, false>;
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+// ranks this engine covers (beyond it the shared-memory-A kernel of sspbo_score_umma.cu takes over)
+int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
+    return ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && ctx->lr_rank <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
+           ctx->umma_range_ok && ctx->stats;
+}
+
+void sspbo_lr_release(sspbo_ctx* ctx) {
+    if (ctx->lr_state) { delete (LrState*)ctx->lr_state; ctx->lr_state = nullptr; }
+}
+
+int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+                          float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+    LrState* ls = (LrState*)ctx->lr_state;
+    if (!ls) { ls = new LrState(); ctx->lr_state = ls; }
+    if (!ls->max_smem) cudaDeviceGetAttribute(&ls->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    Params p;
+    memset(&p, 0, sizeof(p));
+    const int r = ctx->lr_rank;
+    const int nc = r > (int)ACC_COLS_MAX ? 2 : 1;
+    const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
+    if (ls->bh != ctx->Vh || ls->bl != ctx->Vl || ls->KC_pad != ctx->KC_pad || ls->BN != bn) {
+        int rc;
+        if ((rc = sspbo_make_map_f16(ctx, &ls->hi, ctx->Vh, ctx->KC_pad, SSPBO_LR_MAX, bn)) ||
+            (rc = sspbo_make_map_f16(ctx, &ls->lo, ctx->Vl, ctx->KC_pad, SSPBO_LR_MAX, bn)))
+            return rc;
+        ls->bh = ctx->Vh; ls->bl = ctx->Vl; ls->KC_pad = ctx->KC_pad; ls->BN = bn;
+    }
+    const size_t tb = table_bytes(ctx), sb = 2 * (size_t)bn * BK * 2;
+    int nb = (int)(((size_t)ls->max_smem - 1024 - tb) / sb);
+    if (nb > MAX_NB) nb = MAX_NB;
+    if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
+    const size_t smem = 1024 + (size_t)nb * sb + tb;
+    const bool p32 = ctx->p32_ok && !ctx->p32_disabled;
+    kernel_fn kern = kernel_for(ctx->n, p32);
+    if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
+    if (!ls->attr_set[p32][ctx->n]) {
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ls->max_smem));
+        ls->attr_set[p32][ctx->n] = true;
+    }
+    p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
+    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.mp_op = ctx->mp_op; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
+    p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
+    p.acc_cols = bn <= 64 ? 64 : 128;
+    p.na = (int)((TMEM_COLS - 2 * p.acc_cols) / A_SLOT_COLS);
+    if (p.na > NA_MAX) p.na = NA_MAX;
+    { const char* e = getenv("SSPBO_NA"); if (e && atoi(e) >= 2 && atoi(e) <= p.na) p.na = atoi(e); }
+    p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
+    p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
+    p.prior_var = (float)(1.0 / ctx->alpha);
+    p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
+    p.mu = mu; p.var = var; p.acq = acq; p.best = best;
+    p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
+    { const char* dbg = getenv("SSPBO_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    const long long tiles = (N + BM - 1) / BM;
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}

@@ -30,9 +30,11 @@
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
-#include <cuda.h>
+#include "sspbo_tc.cuh"
+#include <stdlib.h>
 
 namespace {
+using namespace sspbo_tc;
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block = one 128-byte swizzle atom of fp16
@@ -71,106 +73,8 @@ struct Params {
     unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
     // 32-bit fixed-point phase path
     const int* A32_op; double x_scale;
+    int debug;                          // SSPBO_DEBUG experiments: 1 = no MMAs issued, 2 = generator skips the phase/sincos math
 };
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// non-blocking probe of a phase
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();
-}
-// same, with a short sleep between polls: for roles that wait for a long time (epilogue, TMA producer)
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        __nanosleep(100);
-        if (spin > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start >> 4 ; [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) ; [32,46) stride byte
-//   offset >> 4 (1024 B between 8-row groups) ; [46,48) version = 1 ; [61,64) layout type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor: D = f32 (bits [4,6) = 1), A = B = f16 (0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-struct Ring {                            // ring position; every role walks the same sequence
-    int slot = 0; uint32_t phase = 0;
-    __device__ __forceinline__ void advance(int n) { if (++slot == n) { slot = 0; phase ^= 1; } }
-};
-
-// (a & b) ^ c in one LOP3
-__device__ __forceinline__ uint32_t lop3_and_xor(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-// split one float pair into fp16 hi / lo words
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-}
 
 // ------------------------------------------------------------------------------------------ kernel
 template <int NDIM, bool TRAJ, bool P32>
@@ -210,7 +114,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     }
     for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     if (warp == WARP_TMA && lane == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_THREADS); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_WARPS); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS * 32); }
         fence_barrier_init();
@@ -282,7 +186,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             }
                             const uint32_t idesc = make_idesc(BM, n_eff);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {
+                            for (int kk = 0; kk < BK / 16 && !(p.debug & 1); ++kk) {
                                 const uint64_t off = (uint64_t)((kk * 32) >> 4);    // 16 fp16 = 32 bytes along K
                                 umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb != kb_first) || (kk != 0));
                                 umma_f16(d_tmem, a_hi + off, b_lo + off, idesc, 1);
@@ -434,7 +338,12 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                     const uint32_t empty_bar = a_empty(ra.slot);
                     const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);         // early, non-blocking probe
                     float cs[GEN_ROWS][8], sn[GEN_ROWS][8];
-                    if constexpr (P32) {
+                    if (p.debug & 2) {
+#pragma unroll
+                        for (int r = 0; r < GEN_ROWS; ++r)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { cs[r][i] = 0.25f * (float)(i + kb); sn[r][i] = 0.125f * (float)(r + kb); }
+                    } else if constexpr (P32) {
                         const int* A32blk = (const int*)tables + (size_t)(kb * 32 + quarter * 8) * NDIM;
                         long long t[GEN_ROWS][8];                         // phase in turns at bit 55
 #pragma unroll
@@ -532,9 +441,10 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             split_pair(cs[r][2 * i], cs[r][2 * i + 1], w[r][i], w[r][4 + i]);
                             split_pair(sn[r][2 * i], sn[r][2 * i + 1], w[r][8 + i], w[r][12 + i]);
                         }
-                    if (pending) {                                        // publish the previous k-block
-                        fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core
-                        mbar_arrive(pending_bar);
+                    if (pending) {                                        // publish the previous k-block: every thread
+                        fence_proxy_async();                              // fences its own stores towards the tensor core,
+                        __syncwarp();                                     // one lane per warp arrives
+                        if (lane == 0) mbar_arrive(pending_bar);
                     }
                     if (!slot_free) mbar_wait(empty_bar, ra.phase ^ 1);
                     uint8_t* st = a_ring + (size_t)ra.slot * A_SLOT_BYTES;
@@ -555,7 +465,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                     ra.advance(NA);
                 }
         }
-        if (pending) { fence_proxy_async(); mbar_arrive(pending_bar); }
+        if (pending) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(pending_bar); }
     }
 
     // ---- teardown ----
@@ -716,6 +626,7 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     p.xq = nullptr; p.tauq = (const unsigned long long*)ctx->tauq_op; p.L = ctx->L;
+    { const char* dbg = getenv("SSPBO_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (traj) {
         const size_t count = (size_t)N * ctx->L * ctx->n;
         if (count > us->xq_cap) {
@@ -737,6 +648,10 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
 }
 
 }  // namespace
+
+int sspbo_make_map_f16(sspbo_ctx* ctx, void* map, const void* base, int KC_pad, int rows, int BN) {
+    return make_map(ctx, (CUtensorMap*)map, base, KC_pad, rows, BN);
+}
 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
     if (!ctx->has_factor || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
