@@ -17,6 +17,9 @@ it and apply the float64 rank-one posterior update (so every step sees a new pos
           H2D copy of the shard and the D2H read of the winner are inside the timed region every step.
 `roofline` tensor-pipe: achieved = candidates * F_alg / kernel time, F_alg = 2 d^2 + 2 d + 2 K n flops
           (SURVEY.md section 8d), peak = MEASURED_PEAKS.json bf16 dense (sustained, the kernel runs inside a long step).
+          While the posterior has rank r <= 512 the scorer uses the low-rank form (2 d r flops instead of 2 d^2), so
+          the algorithmic figure can exceed the dense-form peak; `executed` gives the tensor flops really issued, and
+          `by_rank` the kernel-only rate at other ranks and for the dense (full-factor) engine.
 `cpu_baseline` / `--impl reference`: the numpy oracle port of the reference path on the host cores.
 """
 import argparse
@@ -71,7 +74,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -257,6 +260,8 @@ def run_native(args):
     ms_total, kernel_ms, e2e_ms = [float(v) for v in stats.cpu()]
     sampler.join(timeout=2)
 
+    info = eng.lowrank_info()
+    sweep = rank_sweep(pkg, eng, agt, cand, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
     c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
     if rank == 0:
         peaks = load_peaks()
@@ -268,25 +273,29 @@ def run_native(args):
         line = {
             "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16x3-split mma / f32 accumulate / f64 phase+posterior" if engine_used == "umma"
-            else "f32 contraction / f64 phase+posterior",
+            "vs_baseline": None,
+            "dtype": ("f16x3-split mma / f32 accumulate / fixed-point phase / f64 posterior" if engine_used.startswith("umma")
+                      else "f32 contraction / f64 phase+posterior"),
             "data": "synthetic",
             "config": {"workload": "C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023,K=511) ls=0.25 rng=0, Hartmann-6 posterior "
                                    f"after {N_OBS}+step observations, counter-based uniform f32 candidates",
                        "candidates_per_gpu_per_step": n_local, "candidates_per_step": total, "chunk": chunk,
-                       "engine": engine_used, "parallelism": f"candidate-shard x{world}",
+                       "engine": engine_used, "posterior_rank": info["rank"], "phase32": info["phase32"],
+                       "parallelism": f"candidate-shard x{world}",
                        "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands refreshed every step",
                        "last_winner": {"score": last[0], "index": last[1]}},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"],
                          # dram__bytes_read+write of one k_score_umma launch (chunk of 4,194,304 candidates) from the
                          # ncu --set full capture summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
-                         "traffic": 108.6e6 if engine_used == "umma" else None,
+                         "traffic": 108.6e6 if engine_used.startswith("umma") else None,
                          "launch_candidates": min(chunk, n_local),
-                         "note": f"algorithmic {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
-                                 f"{kernel_ms:.2f} ms scoring time per step per GPU (all launches of the step); executed "
-                                 "tensor flops = 3 (fp16 split) x ~0.56 (triangular factor) x algorithmic; "
-                                 f"peak {peaks['source']}"},
+                         "executed": executed_note(engine_used, info["rank"], d, n_local, kernel_ms, peaks),
+                         "note": f"algorithmic (dense form, SURVEY 8d) {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
+                                 f"{kernel_ms:.2f} ms scoring time per step per GPU (all launches of the step, incl. the key "
+                                 "read-back); frac > 1 means the low-rank form beats the dense-form roofline by doing less "
+                                 f"work, not that the tensor pipe runs above peak; peak {peaks['source']}"},
+            "by_rank": sweep,
             "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                               "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
                              if cpu_rate else None),
@@ -300,6 +309,58 @@ def run_native(args):
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
+
+
+def executed_note(engine, rank, d, n_local, kernel_ms, peaks):
+    """Tensor flops the kernel really issues per candidate (3 split-fp16 MMAs per product)."""
+    kc = 1024
+    if engine == "umma-lowrank":
+        nc = 2 if rank > 128 else 1
+        if rank > 256:
+            nc = 2
+        bn = -(-(-(-rank // nc)) // 16) * 16
+        per_cand = 3 * 2.0 * kc * bn * nc
+        what = f"low-rank: 3 x 2 x {kc} x {nc}x{bn} per candidate"
+    elif engine == "umma":
+        per_cand = 3 * 2.0 * kc * 1024 * 0.56
+        what = "dense triangular factor: 3 x 0.56 x 2 x 1024^2 per candidate"
+    else:
+        return None
+    tf = n_local * per_cand / (kernel_ms * 1e-3) / 1e12
+    return {"tflops": tf, "frac_of_peak": tf / peaks["tflops"], "what": what}
+
+
+def rank_sweep(pkg, eng, agt, cand, orc, n=1 << 22, reps=3):
+    """Kernel-only candidates/s (CUDA events, device-resident candidates, one launch of n candidates) of the low-rank
+    engine at the current and at higher posterior ranks, and of the dense full-factor engine."""
+    import torch
+    from ssp_bayesopt_b200 import _lib
+    x = cand[:n]
+    out = []
+
+    def timed(code):
+        eng.score(x, LAM, GAMMA, engine=code)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.score(x, LAM, GAMMA, engine=code)
+        e1.record()
+        torch.cuda.synchronize()
+        return x.shape[0] * reps / (e0.elapsed_time(e1) * 1e-3)
+
+    rng = np.random.default_rng(7)
+    for target in (None, 128, 250):
+        while target is not None and eng.lowrank_info()["rank"] < target:
+            x_t = rng.uniform(0, 1, (1, N_DIM))
+            agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))
+        r = eng.lowrank_info()["rank"]
+        row = {"rank": r, "lowrank_cand_per_s": timed(_lib.ENGINE_UMMA_LR)}
+        if target in (None, 250):
+            row["dense_cand_per_s"] = timed(_lib.ENGINE_UMMA)
+        eng.score_stats(reset=True)
+        out.append(row)
+    return out
 
 
 def bo_step_c2(pkg, n_iter=30):
@@ -322,13 +383,14 @@ def bo_step_c2(pkg, n_iter=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "umma"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--chunk", type=int, default=1 << 22)
     ap.add_argument("--no-c2", action="store_true", help="skip the config-C2 'ms per BO step' side measurement")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the kernel-only rank sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

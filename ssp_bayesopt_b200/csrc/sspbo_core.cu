@@ -304,11 +304,39 @@ __global__ void k_lr_append(const double* __restrict__ y, const double* __restri
     vh_row[c] = h;
     vl_row[c] = __double2half(v - (double)__half2float(h));
 }
-// m' in operand order (padding columns stay zero)
+// m' in operand order (padding columns stay zero), and as row 0 of the low-rank operand images: the tensor core then
+// delivers mu = m' . psi as output column 0.  Row 0 carries its own power-of-two scale (|m'| max -> [512, 1024)),
+// published in *mscale_out for the epilogue.  One block.
 __global__ void k_mp_op(const double* __restrict__ mp, const int* __restrict__ perm, const int* __restrict__ col_of_rank,
-                        int d, float* __restrict__ mp_op) {
-    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kk < d) mp_op[col_of_rank[kk]] = (float)mp[perm[kk]];
+                        int d, float* __restrict__ mp_op, __half* __restrict__ vh_row0, __half* __restrict__ vl_row0,
+                        float* __restrict__ mscale_out) {
+    __shared__ double red[32];
+    __shared__ double scale_s;
+    double mx = 0.0;
+    for (int kk = threadIdx.x; kk < d; kk += blockDim.x) mx = fmax(mx, fabs(mp[kk]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmax(m, red[w]);
+        const double sc = (m > 0.0 && isfinite(m)) ? exp2(floor(log2(1024.0 / m))) : 1.0;
+        scale_s = sc;
+        *mscale_out = (float)(1.0 / sc);
+    }
+    __syncthreads();
+    const double sc = scale_s;
+    for (int kk = threadIdx.x; kk < d; kk += blockDim.x) {
+        const double m = mp[perm[kk]];
+        const int c = col_of_rank[kk];
+        mp_op[c] = (float)m;
+        if (vh_row0) {
+            const double v = m * sc;
+            const __half h = __double2half(v);
+            vh_row0[c] = h;
+            vl_row0[c] = __double2half(v - (double)__half2float(h));
+        }
+    }
 }
 
 // =====================================================================================
@@ -692,7 +720,7 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
-    dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); ctx->lr_rank = 0; ctx->lr_valid = false;
+    dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); dev_free(&ctx->mscale); ctx->lr_rank = 0; ctx->lr_valid = false;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -902,8 +930,9 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             (rc = dev_alloc(ctx, &ctx->Rh, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->Rl, (size_t)ctx->NJ_pad * ctx->KC_pad)) ||
             (rc = dev_alloc(ctx, &ctx->mp_op, (size_t)ctx->KC_pad)) ||
-            (rc = dev_alloc(ctx, &ctx->Vh, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
-            (rc = dev_alloc(ctx, &ctx->Vl, (size_t)SSPBO_LR_MAX * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Vh, (size_t)(SSPBO_LR_MAX + 1) * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->Vl, (size_t)(SSPBO_LR_MAX + 1) * ctx->KC_pad)) ||
+            (rc = dev_alloc(ctx, &ctx->mscale, (size_t)1)) ||
             (rc = dev_alloc(ctx, &ctx->Vd, (size_t)SSPBO_LR_MAX * d)) ||
             (rc = dev_alloc(ctx, &ctx->psi, (size_t)d)) || (rc = dev_alloc(ctx, &ctx->y, (size_t)d)) ||
             (rc = dev_alloc(ctx, &ctx->phi_tmp, (size_t)d)))
@@ -1020,7 +1049,7 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                 if (ctx->lr_rank >= SSPBO_LR_MAX) ctx->lr_valid = false;        // beyond the low-rank regime
                 else {
                     SSPBO_LAUNCH_CHECK(ctx);                                    // (the rank-one launch above)
-                    const size_t off = (size_t)ctx->lr_rank * ctx->KC_pad;
+                    const size_t off = (size_t)(ctx->lr_rank + 1) * ctx->KC_pad;      // row 0 holds m'
                     k_lr_append<<<(d + 255) / 256, 256, 0, st>>>(ctx->y, ctx->scal + 2, ctx->col_of_rank, d, ctx->r_scale,
                                                                  ctx->Vh + off, ctx->Vl + off, ctx->Vd + (size_t)ctx->lr_rank * d);
                     ctx->lr_rank++;
@@ -1041,7 +1070,7 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         if (ctx->has_factor) {
             k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
             SSPBO_LAUNCH_CHECK(ctx);
-            k_mp_op<<<(d + 255) / 256, 256, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op);
+            k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
             SSPBO_LAUNCH_CHECK(ctx);
         }
         ctx->operands_dirty = true; ctx->factor_dirty = true;
@@ -1129,7 +1158,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     ctx->operands_dirty = true; ctx->factor_dirty = true;
     ctx->lr_valid = false;                                       // the rows of V do not travel with the packed state
     if (ctx->has_factor) {
-        k_mp_op<<<((int)d + 255) / 256, 256, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, (int)d, ctx->mp_op);
+        k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, (int)d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
         SSPBO_LAUNCH_CHECK(ctx);
     }
     return SSPBO_OK;
@@ -1238,7 +1267,9 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
                    "(rank %d, valid %d) and L == 1", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid);
     if (engine == SSPBO_ENGINE_AUTO) {
         if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
-        else if (umma_ok && N >= 1024) engine = (lr_ok && !ctx->lr_disabled) ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA;
+        else if (umma_ok && N >= 1024)                          // low-rank form while it is less tensor work than the
+            engine = (lr_ok && !ctx->lr_disabled && 2 * (ctx->lr_rank + 1) <= ctx->d)   // triangular factor (~0.56 d^2)
+                         ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA;
         else engine = SSPBO_ENGINE_SIMT;
     }
     ctx->last_engine = engine;

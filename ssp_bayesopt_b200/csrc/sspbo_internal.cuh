@@ -59,9 +59,11 @@ struct sspbo_ctx {
     bool operands_dirty = true;      // Rt_f32 / Rh / Rl / mp_f32 need a refresh from R, m
     // ---- low-rank scoring state: Sp = Sp0 - V^T V with one row of V per observation (rank = #observations) ----
     //   psi^T Sp psi = psi^T Sp0 psi - |V psi|^2 ;  row r of V = y sqrt(beta / (1 + beta psi.y)), y = Sp psi (before the update)
-    // Only the split-fp16 image in operand order is kept (SSPBO_LR_MAX x KC_pad, K-major, rows >= lr_rank are zero).
+    // Split-fp16 image in operand order: (SSPBO_LR_MAX + 1) x KC_pad, K-major; row 0 = m' (own scale, see mscale), row j + 1 =
+    // observation j, rows beyond the rank are zero.
     __half* Vh = nullptr;
     __half* Vl = nullptr;
+    float* mscale = nullptr;         // device scalar: 1 / (power-of-two scale of row 0 = m')
     double* Vd = nullptr;            // float64 rows of V in rank order (SSPBO_LR_MAX x d): exact pass over flagged candidates
     int lr_rank = 0;
     bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)

@@ -13,10 +13,11 @@
 //                        frequencies of a k-block each.  theta_f = A_f . x in fixed point (32-bit operands with
 //                        fa + fx = 55 -> one IMAD.WIDE per axis, or Q31.32 x Q31.32), the phase bits become the
 //                        mantissa of a float in [1, 2), MUFU sin/cos, split into fp16 hi/lo, tcgen05.st into the
-//                        A ring (4 slots x 64 columns: 32 hi + 32 lo).  mu = m' . psi accumulates in float32.
+//                        A ring (4-6 slots x 64 columns: 32 hi + 32 lo).
 //   TMA warp             streams V_hi / V_lo slabs (64 columns x BN rows) through the B ring.
 //   MMA warp             per k-block and chunk: 4 x 3 tcgen05.mma (M=128, N=BN, K=16): psi_hi V_hi^T + psi_hi V_lo^T +
 //                        psi_lo V_hi^T into a float32 accumulator in TMEM.
+//   (row 0 of the B operand is m' with its own scale, so output column 0 is mu = m' . psi: no FMA in the generator)
 //   epilogue warps (4)   q = sum_j Y_j^2, var = 1/beta + 1/alpha - q, acquisition, packed-key argmax; candidates with
 //                        var < SSPBO_LR_FLAG_FRACTION / alpha are appended to the flag list instead (the exact float64
 //                        engine re-scores them right after this kernel, sspbo_core.cu:k_exact_*).
@@ -34,10 +35,14 @@ using namespace sspbo_tc;
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block
-constexpr int GEN_WARPS = 8, EPI_WARPS = 4;
+#ifndef SSPBO_LR_NF
+#define SSPBO_LR_NF 16
+#endif
+constexpr int NF = SSPBO_LR_NF;         // frequencies per generator thread and k-block (16 or 8)
+constexpr int PARTS = 32 / NF;          // generator warps per TMEM lane quadrant
+constexpr int GEN_WARPS = 4 * PARTS, EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448
-constexpr int NF = 16;                  // frequencies per generator thread and k-block
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448 (NF = 16) or 704 (NF = 8)
 constexpr int NA_MAX = 6;               // A ring slots in TMEM: 4 behind 128-column accumulators, 6 behind 64-column ones
 constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp16 per column)
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
@@ -46,7 +51,7 @@ constexpr int MAX_N = 8;
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
-    const long long* Aq_op; const int* A32_op; const float* mp_op; double x_scale;
+    const long long* Aq_op; const int* A32_op; const float* mscale; double x_scale;
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols;                   // A ring slots; columns reserved per accumulator (64 or 128)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
@@ -70,9 +75,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint8_t* b_ring = smem;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
     long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM (int32 in the P32 path)
-    float* mp_s = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
-    float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][2 halves][128]
-    uint64_t* bars = (uint64_t*)(mu_part + 2 * 2 * BM);
+    uint64_t* bars = (uint64_t*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);
     // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -85,12 +88,15 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 
     // ---- one-time setup ----
     if constexpr (P32) {
+        // axis-major inside every block of NF frequencies: one LDS.128 feeds four independent multiply-add chains
         int* A32_s = (int*)tables;
-        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) A32_s[i] = p.A32_op[i];
+        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) {
+            const int f = i / NDIM, a = i - f * NDIM;
+            A32_s[((f / NF) * NDIM + a) * NF + (f % NF)] = p.A32_op[i];
+        }
     } else {
         for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
     }
-    for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     if (warp == WARP_TMA && lane == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_WARPS); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
@@ -183,8 +189,9 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         uint32_t acc_phase[2] = {0, 0};
         int tile_iter = 0;
         unsigned long long my_best = 0ull;
+        const float inv_mscale = __ldg(p.mscale);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            float q = 0.f;
+            float q = 0.f, mu_raw = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
                 const int buf = acc_of(tile_iter, c);
                 mbar_wait_relaxed<800>(tmem_full(buf), acc_phase[buf]);
@@ -198,6 +205,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     for (int l = 0; l < 4; ++l)
                         if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
                     tmem_ld_wait();
+                    if (c == 0 && g == 0) { mu_raw = __uint_as_float(v[0]); v[0] = 0u; }   // output row 0 is m' . psi, not a row of V
                     float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
@@ -216,8 +224,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             }
             const long long gi = tile * BM + row;
             if (gi < p.N) {
-                const float* mpart = mu_part + (tile_iter & 1) * 2 * BM;
-                const float mu = mpart[row] + mpart[BM + row];
+                const float mu = mu_raw * inv_mscale;
                 const float rem = p.prior_var - q * p.inv_rscale2;                    // 1/alpha - |V psi|^2
                 const float var = p.inv_beta + rem;                                   // blr.py:96
                 bool flagged = false;
@@ -246,7 +253,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         // ================================ psi generators (A ring in tensor memory) ================================
         // Software pipeline per k-block: probe the slot's "empty" barrier without blocking, do the math into
         // registers, publish the PREVIOUS k-block (its tcgen05.st have long completed), then store this one.
-        const int gw = warp - WARP_GEN0;                                  // 0..7
+        const int gw = warp - WARP_GEN0;
         const int quad = warp & 3, half = gw >> 2;                        // TMEM lane quadrant, frequency half of the k-block
         const int r0 = quad * 32 + lane;                                  // candidate row of this thread = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + A_RING_COL0;
@@ -284,7 +291,6 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
             }
-            float mu0 = 0.f;
             for (int kb = 0; kb < n_kb; ++kb) {
                 const uint32_t empty_bar = a_empty(ra.slot);
                 const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);             // early, non-blocking probe
@@ -293,14 +299,14 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
                 } else if constexpr (P32) {
-                    const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;
+                    const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF]
                     long long t[NF];                                      // phase in turns at bit 55
 #pragma unroll
-                    for (int i = 0; i < NF; ++i) t[i] = 0ll;
+                    for (int i = 0; i < NF; ++i) t[i] = (long long)A32blk[i] * (long long)xq0[0];
 #pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
+                    for (int a = 1; a < NDIM; ++a) {
 #pragma unroll
-                        for (int i = 0; i < NF; ++i) t[i] += (long long)A32blk[i * NDIM + a] * (long long)xq0[a];   // IMAD.WIDE
+                        for (int i = 0; i < NF; ++i) t[i] += (long long)A32blk[a * NF + i] * (long long)xq0[a];   // IMAD.WIDE
                     }
 #pragma unroll
                     for (int i = 0; i < NF; ++i) {
@@ -328,11 +334,6 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                         cs[i] = __cosf(a0); sn[i] = __sinf(a0);
                     }
                 }
-                {
-                    const float* mcos = mp_s + kb * BK + half * NF;
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) { mu0 = fmaf(mcos[i], cs[i], mu0); mu0 = fmaf(mcos[32 + i], sn[i], mu0); }
-                }
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
                 for (int i = 0; i < NF / 2; ++i) {
@@ -350,11 +351,10 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 // operand order inside a k-block: K index i < 32 is cos(f = i), i >= 32 is sin(f = i - 32); two fp16 per
                 // TMEM column, hi part in columns [0, 32), lo part in [32, 64) of the slot
                 const uint32_t slot_addr = lane_addr + (uint32_t)(ra.slot * A_SLOT_COLS) + (uint32_t)(half * (NF / 2));
-                tmem_st8(slot_addr, wch);
-                tmem_st8(slot_addr + 16, wsh);
-                tmem_st8(slot_addr + 32, wcl);
-                tmem_st8(slot_addr + 48, wsl);
-                if (kb == n_kb - 1) mu_part[(tile_iter & 1) * 2 * BM + half * BM + r0] = mu0;
+                tmem_st<NF / 2>(slot_addr, wch);
+                tmem_st<NF / 2>(slot_addr + 16, wsh);
+                tmem_st<NF / 2>(slot_addr + 32, wcl);
+                tmem_st<NF / 2>(slot_addr + 48, wsl);
                 pending = true; pending_bar = a_full(ra.slot);
                 ra.advance(NA);
             }
@@ -382,8 +382,7 @@ struct LrState {
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
-    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
-           2 * 2 * BM * sizeof(float) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
+    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
@@ -408,7 +407,7 @@ kernel_fn kernel_for(int n, bool p32) {
 
 // ranks this engine covers (beyond it the shared-memory-A kernel of sspbo_score_umma.cu takes over)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
-    return ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && ctx->lr_rank <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
+    return ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && ctx->lr_rank + 1 <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
            ctx->umma_range_ok && ctx->stats;
 }
 
@@ -423,13 +422,13 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (!ls->max_smem) cudaDeviceGetAttribute(&ls->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     Params p;
     memset(&p, 0, sizeof(p));
-    const int r = ctx->lr_rank;
+    const int r = ctx->lr_rank + 1;                      // + row 0 (m')
     const int nc = r > (int)ACC_COLS_MAX ? 2 : 1;
     const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
     if (ls->bh != ctx->Vh || ls->bl != ctx->Vl || ls->KC_pad != ctx->KC_pad || ls->BN != bn) {
         int rc;
-        if ((rc = sspbo_make_map_f16(ctx, &ls->hi, ctx->Vh, ctx->KC_pad, SSPBO_LR_MAX, bn)) ||
-            (rc = sspbo_make_map_f16(ctx, &ls->lo, ctx->Vl, ctx->KC_pad, SSPBO_LR_MAX, bn)))
+        if ((rc = sspbo_make_map_f16(ctx, &ls->hi, ctx->Vh, ctx->KC_pad, SSPBO_LR_MAX + 1, bn)) ||
+            (rc = sspbo_make_map_f16(ctx, &ls->lo, ctx->Vl, ctx->KC_pad, SSPBO_LR_MAX + 1, bn)))
             return rc;
         ls->bh = ctx->Vh; ls->bl = ctx->Vl; ls->KC_pad = ctx->KC_pad; ls->BN = bn;
     }
@@ -446,7 +445,7 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
         ls->attr_set[p32][ctx->n] = true;
     }
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
-    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.mp_op = ctx->mp_op; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
+    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.mscale = ctx->mscale; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
     p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     p.acc_cols = bn <= 64 ? 64 : 128;
     p.na = (int)((TMEM_COLS - 2 * p.acc_cols) / A_SLOT_COLS);

@@ -583,7 +583,7 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
         for (int i = 0; i < 8; ++i) p.kb_start[i] = 0;
         for (int i = 0; i < 32; ++i) p.nz_rows[i] = 32767;
         ms = &us->lr;
-        int rc = ensure_maps(ctx, ms, ctx->Vh, ctx->Vl, ctx->KC_pad, SSPBO_LR_MAX, bn);
+        int rc = ensure_maps(ctx, ms, ctx->Vh + ctx->KC_pad, ctx->Vl + ctx->KC_pad, ctx->KC_pad, SSPBO_LR_MAX, bn);   // row 0 is m'
         if (rc) return rc;
         p.lowrank = 1;
         p.prior_var = (float)(1.0 / ctx->alpha);
