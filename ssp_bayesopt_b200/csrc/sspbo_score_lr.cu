@@ -147,6 +147,48 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + A_RING_COL0 + (uint32_t)(ra.slot * A_SLOT_COLS);
+                if (n_chunks == 2) {
+                    // Two chunks: consecutive MMAs alternate between the two accumulators.  Back-to-back MMAs into the
+                    // SAME accumulator serialise on its write-back (~110 cycles each at N <= 128, measured), so the
+                    // interleave nearly doubles the issue rate.
+                    if (kb == 0) {
+                        mbar_wait(tmem_empty(0), acc_phase[0] ^ 1); acc_phase[0] ^= 1;
+                        mbar_wait(tmem_empty(1), acc_phase[1] ^ 1); acc_phase[1] ^= 1;
+                    }
+                    Ring rb1 = rb; rb1.advance(p.nb);
+                    mbar_wait(b_full(rb.slot), rb.phase);
+                    mbar_wait(b_full(rb1.slot), rb1.phase);
+                    tc_fence_after();
+                    const uint32_t sb0 = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
+                    const uint32_t sb1 = smem_u32(b_ring + (size_t)rb1.slot * b_slot_bytes);
+                    const uint64_t b0h = make_desc_sw128(sb0), b0l = make_desc_sw128(sb0 + b_tile_bytes);
+                    const uint64_t b1h = make_desc_sw128(sb1), b1l = make_desc_sw128(sb1 + b_tile_bytes);
+                    const uint32_t d0 = tmem_base, d1 = tmem_base + ACC_COLS;
+                    if (elect_one()) {
+                        if (!no_mma) {
+                            umma_f16_ts(d0, a_hi, b0h, idesc, kb != 0);
+                            umma_f16_ts(d1, a_hi, b1h, idesc, kb != 0);
+                            umma_f16_ts_acc(d0, a_hi, b0l, idesc);
+                            umma_f16_ts_acc(d1, a_hi, b1l, idesc);
+                            umma_f16_ts_acc(d0, a_hi + 32, b0h, idesc);
+                            umma_f16_ts_acc(d1, a_hi + 32, b1h, idesc);
+#pragma unroll
+                            for (int kk = 1; kk < BK / 16; ++kk) {
+                                umma_f16_ts_acc(d0, a_hi + 8 * kk, b0h + 2 * kk, idesc);
+                                umma_f16_ts_acc(d1, a_hi + 8 * kk, b1h + 2 * kk, idesc);
+                                umma_f16_ts_acc(d0, a_hi + 8 * kk, b0l + 2 * kk, idesc);
+                                umma_f16_ts_acc(d1, a_hi + 8 * kk, b1l + 2 * kk, idesc);
+                                umma_f16_ts_acc(d0, a_hi + 32 + 8 * kk, b0h + 2 * kk, idesc);
+                                umma_f16_ts_acc(d1, a_hi + 32 + 8 * kk, b1h + 2 * kk, idesc);
+                            }
+                        }
+                        umma_commit(b_empty(rb.slot));
+                        umma_commit(b_empty(rb1.slot));
+                        if (kb == n_kb - 1) { umma_commit(tmem_full(0)); umma_commit(tmem_full(1)); }
+                    }
+                    __syncwarp();
+                    rb.advance(p.nb); rb.advance(p.nb);
+                } else
                 for (int c = 0; c < n_chunks; ++c) {
                     const int buf = acc_of(tile_iter, c);
                     if (kb == 0) {                                        // first use of this accumulator in the tile: the
