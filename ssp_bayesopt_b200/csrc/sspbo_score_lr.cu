@@ -35,14 +35,14 @@ using namespace sspbo_tc;
 
 constexpr int BM = 128;                 // candidates per tile (UMMA M)
 constexpr int BK = 64;                  // operand columns per k-block
-#ifndef SSPBO_LR_NF
-#define SSPBO_LR_NF 16
+#ifndef SSPBO_LR_GEN_W
+#define SSPBO_LR_GEN_W 3
 #endif
-constexpr int NF = SSPBO_LR_NF;         // frequencies per generator thread and k-block (16 or 8)
-constexpr int PARTS = 32 / NF;          // generator warps per TMEM lane quadrant
-constexpr int GEN_WARPS = 4 * PARTS, EPI_WARPS = 4;
+constexpr int NF = 16;                  // frequencies per generator thread and pass (two passes per k-block)
+constexpr int GEN_W = SSPBO_LR_GEN_W;   // generator warps per TMEM lane quadrant (= per SM sub-partition), k-blocks in rotation
+constexpr int GEN_WARPS = 4 * GEN_W, EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448 (NF = 16) or 704 (NF = 8)
+constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 576 with three generator warps per quadrant
 constexpr int NA_MAX = 6;               // A ring slots in TMEM: 4 behind 128-column accumulators, 6 behind 64-column ones
 constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp16 per column)
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
@@ -98,7 +98,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
     }
     if (warp == WARP_TMA && lane == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), GEN_WARPS); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS * 32); }
         fence_barrier_init();
@@ -293,49 +293,57 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
     } else {
         // ================================ psi generators (A ring in tensor memory) ================================
-        // Software pipeline per k-block: probe the slot's "empty" barrier without blocking, do the math into
-        // registers, publish the PREVIOUS k-block (its tcgen05.st have long completed), then store this one.
+        // GEN_W warps per TMEM lane quadrant (thread <-> candidate row).  Warp j of a quadrant produces the k-blocks
+        // g = j, j + GEN_W, ... of the CTA's k-block sequence (tiles x n_kb), both frequency halves of each, so GEN_W
+        // consecutive k-blocks are in production at once and every scheduler has GEN_W generator warps to hide the
+        // fixed-latency stalls of each other (the instruction stream of one warp issues only every ~4 cycles).
         const int gw = warp - WARP_GEN0;
-        const int quad = warp & 3, half = gw >> 2;                        // TMEM lane quadrant, frequency half of the k-block
+        const int quad = warp & 3, member = gw >> 2;                      // TMEM lane quadrant, position in the rotation
         const int r0 = quad * 32 + lane;                                  // candidate row of this thread = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + A_RING_COL0;
         const long long N = p.N;
-        Ring ra;
-        int tile_iter = 0;
-        bool pending = false; uint32_t pending_bar = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            unsigned long long x0[NDIM];                                  // Q31.32 candidate (two's complement)
-            int xq0[NDIM];                                                // Q.fx candidate of the 32-bit phase path
-            const long long g0 = tile * BM + r0;
-            if constexpr (P32) {
-                bool oor = false;
+        const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long long total_blocks = my_tiles * n_kb;
+        int slot = member % NA;
+        uint32_t phase = (uint32_t)((member / NA) & 1);
+        int kb = member % n_kb;
+        long long tile_iter = member / n_kb, loaded_iter = -1;
+        unsigned long long x0[NDIM];                                      // Q31.32 candidate (two's complement)
+        int xq0[NDIM];                                                    // Q.fx candidate of the 32-bit phase path
+        for (long long g = member; g < total_blocks; g += GEN_W) {
+            if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
+                loaded_iter = tile_iter;
+                const long long g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
+                if constexpr (P32) {
+                    bool oor = false;
 #pragma unroll
-                for (int a = 0; a < NDIM; ++a) {
-                    double v0 = 0.0;
-                    if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                    v0 *= p.x_scale;
-                    oor |= !(fabs(v0) < 2147483647.0);
-                    xq0[a] = __double2int_rn(v0);
-                }
-                if (oor && half == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);        // outside the declared |x| bound
-            } else {
+                    for (int a = 0; a < NDIM; ++a) {
+                        double v0 = 0.0;
+                        if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                        v0 *= p.x_scale;
+                        oor |= !(fabs(v0) < 2147483647.0);
+                        xq0[a] = __double2int_rn(v0);
+                    }
+                    if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
+                } else {
 #pragma unroll
-                for (int a = 0; a < NDIM; ++a) {
-                    double v0 = 0.0;
-                    if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                    x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                    for (int a = 0; a < NDIM; ++a) {
+                        double v0 = 0.0;
+                        if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
+                        x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                    }
                 }
-            }
-            {                                                             // next tile's row: pull it towards the SM now
-                const long long gn = g0 + (long long)gridDim.x * BM;
-                if (half == 0 && gn < N) {
+                const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it towards the SM now
+                if (member == 0 && gn < N) {
                     const char* nx = (const char*)p.x + (size_t)gn * NDIM * (p.x_f64 ? 8 : 4);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
             }
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const uint32_t empty_bar = a_empty(ra.slot);
-                const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);             // early, non-blocking probe
+            const uint32_t empty_bar = a_empty(slot);
+            bool slot_free = mbar_test_wait(empty_bar, phase ^ 1);        // early, non-blocking probe
+            const uint32_t slot_addr = lane_addr + (uint32_t)(slot * A_SLOT_COLS);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
                 if (p.debug & 2) {
 #pragma unroll
@@ -379,29 +387,26 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
                 for (int i = 0; i < NF / 2; ++i) {
-                    split_pair(cs[2 * i], cs[2 * i + 1], wch[i], wcl[i]);
-                    split_pair(sn[2 * i], sn[2 * i + 1], wsh[i], wsl[i]);
+                    split_pair_trunc(cs[2 * i], cs[2 * i + 1], wch[i], wcl[i]);
+                    split_pair_trunc(sn[2 * i], sn[2 * i + 1], wsh[i], wsl[i]);
                 }
-                if (pending) {                                            // publish the previous k-block
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(pending_bar);
-                }
-                if (!slot_free) mbar_wait(empty_bar, ra.phase ^ 1);
+                if (!slot_free) { mbar_wait(empty_bar, phase ^ 1); slot_free = true; }
                 tc_fence_after();
                 // operand order inside a k-block: K index i < 32 is cos(f = i), i >= 32 is sin(f = i - 32); two fp16 per
                 // TMEM column, hi part in columns [0, 32), lo part in [32, 64) of the slot
-                const uint32_t slot_addr = lane_addr + (uint32_t)(ra.slot * A_SLOT_COLS) + (uint32_t)(half * (NF / 2));
-                tmem_st<NF / 2>(slot_addr, wch);
-                tmem_st<NF / 2>(slot_addr + 16, wsh);
-                tmem_st<NF / 2>(slot_addr + 32, wcl);
-                tmem_st<NF / 2>(slot_addr + 48, wsl);
-                pending = true; pending_bar = a_full(ra.slot);
-                ra.advance(NA);
+                const uint32_t sa = slot_addr + (uint32_t)(half * (NF / 2));
+                tmem_st8(sa, wch);
+                tmem_st8(sa + 16, wsh);
+                tmem_st8(sa + 32, wcl);
+                tmem_st8(sa + 48, wsl);
             }
+            tmem_st_wait();                                               // publish the k-block
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(slot));
+            slot += GEN_W; while (slot >= NA) { slot -= NA; phase ^= 1; }
+            kb += GEN_W; while (kb >= n_kb) { kb -= n_kb; ++tile_iter; }
         }
-        if (pending) { tmem_st_wait(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(pending_bar); }
     }
 
     // ---- teardown ----
@@ -479,7 +484,8 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
     const size_t smem = 1024 + (size_t)nb * sb + tb;
-    const bool p32 = ctx->p32_ok && !ctx->p32_disabled;
+    bool p32 = ctx->p32_ok && !ctx->p32_disabled;
+    { const char* dbg = getenv("SSPBO_DEBUG"); if (dbg && (atoi(dbg) & 8)) p32 = false; }     // timing experiments only
     kernel_fn kern = kernel_for(ctx->n, p32);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
     if (!ls->attr_set[p32][ctx->n]) {

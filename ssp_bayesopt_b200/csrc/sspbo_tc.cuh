@@ -100,6 +100,18 @@ __device__ __forceinline__ uint32_t lop3_and_xor(uint32_t a, uint32_t b, uint32_
     return d;
 }
 
+// Split by truncation: hi = a with the low 13 mantissa bits cleared (exactly representable in fp16 for |a| >= 2^-14),
+// lo = a - hi (exact in fp32, < 2^-10 |a|), then rounded to fp16: |a - hi - lo| <= 2^-21 |a|.  Compared with split_pair
+// this trades the two half->float conversions (FMA pipe) for two LOP3 (ALU pipe).
+__device__ __forceinline__ void split_pair_trunc(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const float ha = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+    const float hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+    __half2 h = __floats2half2_rn(ha, hb);
+    __half2 l = __floats2half2_rn(a - ha, b - hb);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
 // split one float pair into fp16 hi / lo words
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     __half2 h = __floats2half2_rn(a, b);
