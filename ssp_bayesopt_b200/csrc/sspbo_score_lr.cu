@@ -21,9 +21,9 @@
 //   epilogue warps (4)   q = sum_j Y_j^2, var = 1/beta + 1/alpha - q, acquisition, packed-key argmax; candidates with
 //                        var < SSPBO_LR_FLAG_FRACTION / alpha are appended to the flag list instead (the exact float64
 //                        engine re-scores them right after this kernel, sspbo_core.cu:k_exact_*).
-// TMEM map (512 columns): [0,128) accumulator 0, [128,256) accumulator 1, [256,512) A ring.
-// Rank: r_eff = r rows, one chunk of BN = ceil16(r) <= 128 rows (accumulators alternate by tile), or two chunks of
-// <= 128 rows (accumulator = chunk).
+// TMEM map (512 columns): accumulator buffer(s) first ([0,128) / [0,256)), the A ring behind them.
+// Rank: r_eff = r + 1 rows (row 0 = m'), one chunk of BN = ceil16(r_eff) <= 256 rows: two accumulator buffers alternating
+// by tile while BN <= 128, a single 256-column accumulator beyond (the epilogue then sits between two tiles).
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
@@ -53,7 +53,7 @@ struct Params {
     const void* x; int x_f64; long long N; long long index0;
     const long long* Aq_op; const int* A32_op; const float* mscale; double x_scale;
     int KC_pad, BN, n_chunks, n_kb, nb;
-    int na, acc_cols;                   // A ring slots; columns reserved per accumulator (64 or 128)
+    int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
     float *mu, *var, *acq;
     unsigned long long* best;
@@ -69,7 +69,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NA = p.na;
-    const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = 2u * ACC_COLS;
+    const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = (uint32_t)(p.n_bufs * p.acc_cols);
     const int b_tile_bytes = p.BN * BK * 2;
     const int b_slot_bytes = 2 * b_tile_bytes;
     uint8_t* b_ring = smem;
@@ -115,7 +115,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     const long long n_tiles = (p.N + BM - 1) / BM;
     const int n_kb = p.n_kb, n_chunks = p.n_chunks;
     // accumulator of chunk c: with a single chunk per tile the two buffers alternate by tile instead
-    auto acc_of = [&](int tile_iter, int c) { return n_chunks == 1 ? (tile_iter & 1) : c; };
+    auto acc_of = [&](int tile_iter, int c) { return n_chunks == 1 ? (tile_iter & (p.n_bufs - 1)) : c; };
 
     if (warp == WARP_TMA) {
         // ================================ TMA producer (B ring) ================================
@@ -147,48 +147,6 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + A_RING_COL0 + (uint32_t)(ra.slot * A_SLOT_COLS);
-                if (n_chunks == 2) {
-                    // Two chunks: consecutive MMAs alternate between the two accumulators.  Back-to-back MMAs into the
-                    // SAME accumulator serialise on its write-back (~110 cycles each at N <= 128, measured), so the
-                    // interleave nearly doubles the issue rate.
-                    if (kb == 0) {
-                        mbar_wait(tmem_empty(0), acc_phase[0] ^ 1); acc_phase[0] ^= 1;
-                        mbar_wait(tmem_empty(1), acc_phase[1] ^ 1); acc_phase[1] ^= 1;
-                    }
-                    Ring rb1 = rb; rb1.advance(p.nb);
-                    mbar_wait(b_full(rb.slot), rb.phase);
-                    mbar_wait(b_full(rb1.slot), rb1.phase);
-                    tc_fence_after();
-                    const uint32_t sb0 = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
-                    const uint32_t sb1 = smem_u32(b_ring + (size_t)rb1.slot * b_slot_bytes);
-                    const uint64_t b0h = make_desc_sw128(sb0), b0l = make_desc_sw128(sb0 + b_tile_bytes);
-                    const uint64_t b1h = make_desc_sw128(sb1), b1l = make_desc_sw128(sb1 + b_tile_bytes);
-                    const uint32_t d0 = tmem_base, d1 = tmem_base + ACC_COLS;
-                    if (elect_one()) {
-                        if (!no_mma) {
-                            umma_f16_ts(d0, a_hi, b0h, idesc, kb != 0);
-                            umma_f16_ts(d1, a_hi, b1h, idesc, kb != 0);
-                            umma_f16_ts_acc(d0, a_hi, b0l, idesc);
-                            umma_f16_ts_acc(d1, a_hi, b1l, idesc);
-                            umma_f16_ts_acc(d0, a_hi + 32, b0h, idesc);
-                            umma_f16_ts_acc(d1, a_hi + 32, b1h, idesc);
-#pragma unroll
-                            for (int kk = 1; kk < BK / 16; ++kk) {
-                                umma_f16_ts_acc(d0, a_hi + 8 * kk, b0h + 2 * kk, idesc);
-                                umma_f16_ts_acc(d1, a_hi + 8 * kk, b1h + 2 * kk, idesc);
-                                umma_f16_ts_acc(d0, a_hi + 8 * kk, b0l + 2 * kk, idesc);
-                                umma_f16_ts_acc(d1, a_hi + 8 * kk, b1l + 2 * kk, idesc);
-                                umma_f16_ts_acc(d0, a_hi + 32 + 8 * kk, b0h + 2 * kk, idesc);
-                                umma_f16_ts_acc(d1, a_hi + 32 + 8 * kk, b1h + 2 * kk, idesc);
-                            }
-                        }
-                        umma_commit(b_empty(rb.slot));
-                        umma_commit(b_empty(rb1.slot));
-                        if (kb == n_kb - 1) { umma_commit(tmem_full(0)); umma_commit(tmem_full(1)); }
-                    }
-                    __syncwarp();
-                    rb.advance(p.nb); rb.advance(p.nb);
-                } else
                 for (int c = 0; c < n_chunks; ++c) {
                     const int buf = acc_of(tile_iter, c);
                     if (kb == 0) {                                        // first use of this accumulator in the tile: the
@@ -470,7 +428,10 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     Params p;
     memset(&p, 0, sizeof(p));
     const int r = ctx->lr_rank + 1;                      // + row 0 (m')
-    const int nc = r > (int)ACC_COLS_MAX ? 2 : 1;
+    // One chunk of BN = ceil16(r) <= 256 rows (a tcgen05.mma costs ~100 cycles or more whatever N is, so the fewest,
+    // widest instructions win): two accumulator buffers alternating by tile while BN <= 128, a single 256-column one
+    // beyond (measured at r = 250: 4.95 ms per 4.19M candidates against 5.26 ms for two interleaved 128-row chunks).
+    const int nc = 1;
     const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
     if (ls->bh != ctx->Vh || ls->bl != ctx->Vl || ls->KC_pad != ctx->KC_pad || ls->BN != bn) {
         int rc;
@@ -495,8 +456,11 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
     p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.mscale = ctx->mscale; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
     p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
-    p.acc_cols = bn <= 64 ? 64 : 128;
-    p.na = (int)((TMEM_COLS - 2 * p.acc_cols) / A_SLOT_COLS);
+    // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
+    if (bn <= 64) { p.acc_cols = 64; p.n_bufs = 2; }
+    else if (bn <= 128) { p.acc_cols = 128; p.n_bufs = 2; }
+    else { p.acc_cols = 256; p.n_bufs = 1; }
+    p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
     if (p.na > NA_MAX) p.na = NA_MAX;
     { const char* e = getenv("SSPBO_NA"); if (e && atoi(e) >= 2 && atoi(e) <= p.na) p.na = atoi(e); }
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
