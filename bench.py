@@ -315,10 +315,10 @@ def executed_note(engine, rank, d, n_local, kernel_ms, peaks):
     """Tensor flops the kernel really issues per candidate (3 split-fp16 MMAs per product)."""
     kc = 1024
     if engine == "umma-lowrank":
-        nc = 2 if rank > 128 else 1
-        if rank > 256:
-            nc = 2
-        bn = -(-(-(-rank // nc)) // 16) * 16
+        r_eff = rank + 1                                   # row 0 of the operand is m'
+        nc = 1 if r_eff <= 256 else 2
+        rows = r_eff if nc == 1 else rank
+        bn = -(-(-(-rows // nc)) // 16) * 16
         per_cand = 3 * 2.0 * kc * bn * nc
         what = f"low-rank: 3 x 2 x {kc} x {nc}x{bn} per candidate"
     elif engine == "umma":

@@ -431,7 +431,8 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
     __shared__ double red[EX_G + 1][EX_THREADS / 32];
     const int d = 2 * K + 1;
     const unsigned long long c0 = *count_ptr;
-    const int64_t count = (int64_t)(c0 < cap ? c0 : cap);
+    if (c0 > cap) return;                               // list overflowed: the host recomputes the call with the dense factor
+    const int64_t count = (int64_t)c0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long my_best = 0ull;
     for (int64_t base = (int64_t)blockIdx.x * EX_G; base < count; base += (int64_t)gridDim.x * EX_G) {

@@ -50,7 +50,9 @@ constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448 (GEN_ROW
 constexpr int GEN_THREADS = 32 * GEN_WARPS;
 constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB (one of hi / lo)
 constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
-constexpr int NA_MIN = 2, NA_MAX = 4;                            // A ring slots (as many as fit after the B ring)
+constexpr int NA_MIN = 2, NA_MAX = 4;
+// tiles of mu in flight (power of two): 8 when a tile has fewer than 8 k-blocks, else 2
+static inline int mu_depth_for(int n_kb) { return n_kb < 8 ? 8 : 2; }                            // A ring slots (as many as fit after the B ring)
 constexpr int MAX_NB = 6;                                        // B ring slots (as many as fit)
 constexpr int MAX_N = 8;                                         // domain dimension (compile-time specialised)
 constexpr uint32_t TMEM_COLS = 512;
@@ -68,6 +70,7 @@ struct Params {
     float *mu, *var, *acq;
     unsigned long long* best;
     int na;                             // A ring slots
+    int mu_depth;                       // tiles of mu in flight between generator and epilogue
     // low-rank mode
     int lowrank; float prior_var, flag_below;
     unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
@@ -93,8 +96,12 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
     long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM, Q31.32 turns per unit
     float* mp_s = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);           // KC_pad
-    float* mu_part = mp_s + p.KC_pad;                                       // [2 tile parities][4 quarters][128]
-    uint64_t* bars = (uint64_t*)(mu_part + 2 * 4 * BM);
+    // mu of a tile travels generator -> epilogue through shared memory.  The generators run up to NA k-blocks ahead of
+    // the MMAs and the MMAs up to two tiles ahead of the epilogue, so with few k-blocks per tile several tiles are in
+    // flight: MU_DEPTH buffers (the generator of tile t + MU_DEPTH can only start after the epilogue of tile t).
+    float* mu_part = mp_s + p.KC_pad;                                       // [MU_DEPTH tiles][4 quarters][128]
+    const int MU_DEPTH = p.mu_depth;
+    uint64_t* bars = (uint64_t*)(mu_part + MU_DEPTH * 4 * BM);
     // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -241,7 +248,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             }
             const long long gi = tile * BM + row;
             if (gi < p.N) {
-                const float* mpart = mu_part + (tile_iter & 1) * 4 * BM;
+                const float* mpart = mu_part + (tile_iter & (MU_DEPTH - 1)) * 4 * BM;
                 float mu = (mpart[row] + mpart[BM + row]) + (mpart[2 * BM + row] + mpart[3 * BM + row]);
                 float qv = q * p.inv_rscale2;
                 bool flagged = false;
@@ -457,7 +464,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         *reinterpret_cast<uint4*>(sr + A_TILE_BYTES + off_sin) = make_uint4(w[r][12], w[r][13], w[r][14], w[r][15]);
                     }
                     if (pr == 0 && kb == n_kb - 1) {
-                        float* mpart = mu_part + (tile_iter & 1) * 4 * BM + quarter * BM;
+                        float* mpart = mu_part + (tile_iter & (MU_DEPTH - 1)) * 4 * BM + quarter * BM;
 #pragma unroll
                         for (int r = 0; r < GEN_ROWS; ++r) mpart[r0 + r * ROW_STEP] = mu0[r];
                     }
@@ -493,7 +500,7 @@ struct UmmaState {
 
 size_t table_bytes(const sspbo_ctx* ctx) {
     return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
-           2 * 4 * BM * sizeof(float) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
+           mu_depth_for(ctx->KC_pad / BK) * 4 * BM * sizeof(float) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
@@ -621,7 +628,7 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
     p.Aq_op = ctx->Aq_op; p.mp_op = ctx->mp_op;
     p.A32_op = ctx->A32_op; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
     p.K = ctx->K; p.KC_pad = ctx->KC_pad;
-    p.n_kb = ctx->KC_pad / BK; p.nb = nb; p.na = na;
+    p.n_kb = ctx->KC_pad / BK; p.nb = nb; p.na = na; p.mu_depth = mu_depth_for(p.n_kb);
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;

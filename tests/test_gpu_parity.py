@@ -287,6 +287,15 @@ def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
         # both engines agree far below the tolerance
         _, (mu2, var2, acq2) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_SIMT)
         np.testing.assert_allclose(var.cpu().numpy(), var2.cpu().numpy(), rtol=2e-5)
+        # low-rank engine (rank 25, one to sixteen k-blocks, both table layouts) + its float64 pass on the observed rows
+        assert eng.lowrank_info()["rank"] == 25 and eng.lowrank_info()["valid"]
+        _, (mu3, var3, acq3) = eng.score(xc, lam, gam, want_outputs=True, engine=_lib.ENGINE_UMMA_LR)
+        assert eng.last_engine() == "umma-lowrank"
+        assert_scores_close(mu3.double().cpu().numpy(), acq3.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var3.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        s3, idx3 = eng.best()
+        if N > 1 and (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert idx3 == int(np.argmax(ref_score))
 
 
 @pytest.mark.parametrize("T,phase32", [(60, True), (60, False), (260, True), (300, True)])
@@ -404,6 +413,16 @@ def test_score_edge_cases(pkg, golden):
         mu, var, acq = agt.eval(g["xc"][:n])
         assert mu.shape == (1, n)
         assert_scores_close(mu, acq, g["ucb_mu"].ravel()[:n], g["ucb_acq"][:n])
+    # many single-k-block tiles per CTA (d = 25): generator, MMA and epilogue are several tiles apart; every engine and
+    # every repetition must give the same winner (regression: mu buffers of tiles in flight)
+    from ssp_bayesopt_b200 import _lib
+    xs = np.random.default_rng(3).uniform(-5, 5, (50001, 2)).astype(np.float32)
+    eng.score(xs, 10.0, 0.0, engine=_lib.ENGINE_SIMT)
+    want_idx = eng.best()[1]
+    for rep in range(12):
+        for code in (_lib.ENGINE_UMMA, _lib.ENGINE_UMMA_LR):
+            eng.score(xs, 10.0, 0.0, engine=code)
+            assert _lib.key_unpack(int(eng._best.item()))[1] == want_idx, (rep, code)
     key, outs = eng.score(np.zeros((0, 2)), 10.0, 0.0, want_outputs=True)          # empty candidate set
     assert int(key.item()) == 0 and outs[0].numel() == 0
     with pytest.raises(Exception):
