@@ -38,12 +38,12 @@ extern "C" {
 #define SSPBO_F64 1
 
 /* scoring engines for sspbo_score */
-#define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; tcgen05 (low-rank while rank <= 512) when covered; else SIMT */
+#define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; tcgen05 (low-rank while rank <= 255) when covered; else SIMT */
 #define SSPBO_ENGINE_SIMT 1     /* fp32 CUDA-core kernel (any d)                */
 #define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel, full triangular factor        */
 #define SSPBO_ENGINE_EXACT 3    /* float64 quadratic form on the psi-space covariance (small N)  */
 #define SSPBO_ENGINE_UMMA_LR 4  /* tcgen05/TMEM kernel on the low-rank form S = I/alpha - V^T V
-                                   (one row of V per observation, rank <= 512) followed by the
+                                   (one row of V per observation, rank <= 255) followed by the
                                    EXACT engine on the candidates it flags (var < 0.1 / alpha)   */
 
 typedef struct sspbo_ctx sspbo_ctx;

@@ -1260,7 +1260,7 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
-    const bool lr_ok = umma_ok && ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && N < 0xffffffffLL;
+    const bool lr_ok = umma_ok && sspbo_score_lr_supported(ctx) && N < 0xffffffffLL;
     if (engine == SSPBO_ENGINE_UMMA && !umma_ok)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: tcgen05 engine does not cover d=%d L=%d", ctx->d, ctx->L);
     if (engine == SSPBO_ENGINE_UMMA_LR && !lr_ok)
@@ -1277,10 +1277,7 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
     if (engine == SSPBO_ENGINE_EXACT)
         return sspbo_score_exact_launch(ctx, x, x_dtype, N, false, index0, lam, gamma_t, mu, var, acq, best, st);
     if (engine == SSPBO_ENGINE_UMMA_LR) {
-        // ranks up to 256: A operand in tensor memory (sspbo_score_lr.cu); beyond: shared-memory A ring, two 256-column chunks
-        int rc = sspbo_score_lr_supported(ctx)
-                     ? sspbo_score_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st)
-                     : sspbo_score_umma_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+        int rc = sspbo_score_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
         if (rc) return rc;
         // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
         { const char* dbg = getenv("SSPBO_DEBUG"); if (dbg && (atoi(dbg) & 4)) return SSPBO_OK; }   // timing experiments only

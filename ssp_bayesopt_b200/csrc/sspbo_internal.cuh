@@ -111,7 +111,7 @@ struct sspbo_ctx {
         SSPBO_CUDA(ctx, cudaGetLastError());         \
     } while (0)
 
-constexpr int SSPBO_LR_MAX = 512;               // largest rank scored in low-rank form (two 256-column accumulators)
+constexpr int SSPBO_LR_MAX = 255;               // largest rank scored in low-rank form (m' + 255 rows = one 256-row MMA operand)
 // The tensor core accumulates in float32 with truncation: |V psi|^2 carries a relative error of ~2e-5 (measured), i.e.
 // 2e-5 / alpha absolute on the variance.  Candidates whose variance is below this fraction of the prior variance
 // 1/alpha would exceed the 1e-4 tolerance after the subtraction and are re-scored by the exact float64 engine.
@@ -158,8 +158,6 @@ int sspbo_score_simt_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx);
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
                             float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
-int sspbo_score_umma_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
-                               float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_umma_release(sspbo_ctx* ctx);
 // low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);

@@ -410,7 +410,7 @@ kernel_fn kernel_for(int n, bool p32) {
 
 }  // namespace
 
-// ranks this engine covers (beyond it the shared-memory-A kernel of sspbo_score_umma.cu takes over)
+// ranks this engine covers (beyond them the dense factor of sspbo_score_umma.cu is as fast)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
     return ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && ctx->lr_rank + 1 <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
            ctx->umma_range_ok && ctx->stats;

@@ -19,12 +19,6 @@
 // triangular (Cholesky of the permuted psi-space covariance), so chunk c only needs k-blocks >= kb_start[c]:
 // 40 of the 64 (chunk, k-block) MMA groups and 24 of the 32 psi k-blocks at d = 1023.
 //
-// Low-rank mode (LR): while the posterior has seen r <= 512 observations since blr_init, Sp = Sp0 - V^T V with one row
-// of V per observation, so  psi^T Sp psi = 1/alpha - |V psi|^2  (psi^T Sp0 psi = |phi|^2 / alpha = 1/alpha exactly).
-// The B operand is then the r x KC image of V (BN = r rounded up to 16, one or two chunks, no triangular structure)
-// and psi is generated once per tile.  The subtraction cancels when a candidate sits on top of the observations
-// (var << 1/alpha): those candidates (var < flag_below) are not scored here but appended to a list that the
-// float64 engine (sspbo_core.cu, k_exact_*) re-scores right after this kernel.
 // Fast phase path (P32): A in Q.fa and x in Q.fx 32-bit fixed point with fa + fx = 55: one IMAD.WIDE per axis
 // accumulates the phase in a 64-bit register whose bits [32, 55) are the top 23 bits of the phase in turns.
 //
@@ -71,9 +65,7 @@ struct Params {
     unsigned long long* best;
     int na;                             // A ring slots
     int mu_depth;                       // tiles of mu in flight between generator and epilogue
-    // low-rank mode
-    int lowrank; float prior_var, flag_below;
-    unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
+    unsigned long long* stats;          // device counters (out-of-bound candidates of the 32-bit phase path)
     // 32-bit fixed-point phase path
     const int* A32_op; double x_scale;
     int debug;                          // SSPBO_DEBUG experiments: 1 = no MMAs issued, 2 = generator skips the phase/sincos math
@@ -250,26 +242,14 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             if (gi < p.N) {
                 const float* mpart = mu_part + (tile_iter & (MU_DEPTH - 1)) * 4 * BM;
                 float mu = (mpart[row] + mpart[BM + row]) + (mpart[2 * BM + row] + mpart[3 * BM + row]);
-                float qv = q * p.inv_rscale2;
-                bool flagged = false;
-                if (p.lowrank) {
-                    qv = p.prior_var - qv;                                            // 1/alpha - |V psi|^2
-                    if (p.inv_beta + qv < p.flag_below) {                             // too close to the observations for
-                        const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
-                        if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
-                        else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
-                    }
-                }
-                if (!flagged) {
-                    float var = p.inv_beta + qv;                                           // blr.py:96
-                    float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
-                    float score = mu + acq;
-                    if (p.mu) p.mu[gi] = mu;
-                    if (p.var) p.var[gi] = var;
-                    if (p.acq) p.acq[gi] = acq;
-                    unsigned long long key = sspbo_pack(score, (unsigned long long)(p.index0 + gi));
-                    if (key > my_best) my_best = key;
-                }
+                float var = p.inv_beta + q * p.inv_rscale2;                           // blr.py:96
+                float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
+                float score = mu + acq;
+                if (p.mu) p.mu[gi] = mu;
+                if (p.var) p.var[gi] = var;
+                if (p.acq) p.acq[gi] = acq;
+                unsigned long long key = sspbo_pack(score, (unsigned long long)(p.index0 + gi));
+                if (key > my_best) my_best = key;
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -492,7 +472,7 @@ struct MapSet {                           // tensor maps of one operand pair (hi
     int KC_pad = 0, rows = 0, BN = 0;
 };
 struct UmmaState {
-    MapSet full, lr;
+    MapSet full;
     int max_smem = 0;
     bool attr_set[2][2][MAX_N + 1] = {};  // [traj][p32][n]
     unsigned long long* xq = nullptr; size_t xq_cap = 0;      // scratch of the trajectory mode
@@ -572,8 +552,7 @@ int ensure_maps(sspbo_ctx* ctx, MapSet* ms, const void* bh, const void* bl, int 
     return SSPBO_OK;
 }
 
-// shared launch path of the full-factor and the low-rank mode
-int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+int launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
            float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
     UmmaState* us = (UmmaState*)ctx->umma;
     if (!us) { us = new UmmaState(); ctx->umma = us; }
@@ -581,22 +560,7 @@ int launch(sspbo_ctx* ctx, bool lowrank, const void* x, int x_dtype, int64_t N, 
     Params p;
     memset(&p, 0, sizeof(p));
     MapSet* ms;
-    if (lowrank) {
-        // rank r -> one chunk of BN = ceil16(r) rows, or two chunks of ceil16(r / 2) rows beyond 256
-        const int r = ctx->lr_rank;
-        const int nc = r > 256 ? 2 : 1;
-        const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
-        p.BN = bn; p.n_chunks = nc;
-        for (int i = 0; i < 8; ++i) p.kb_start[i] = 0;
-        for (int i = 0; i < 32; ++i) p.nz_rows[i] = 32767;
-        ms = &us->lr;
-        int rc = ensure_maps(ctx, ms, ctx->Vh + ctx->KC_pad, ctx->Vl + ctx->KC_pad, ctx->KC_pad, SSPBO_LR_MAX, bn);   // row 0 is m'
-        if (rc) return rc;
-        p.lowrank = 1;
-        p.prior_var = (float)(1.0 / ctx->alpha);
-        p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
-        p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
-    } else {
+    {
         p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
         for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
         for (int i = 0; i < 32; ++i) p.nz_rows[i] = ctx->nz_rows[i];
@@ -681,10 +645,5 @@ void sspbo_umma_release(sspbo_ctx* ctx) {
 
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
                             float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
-    return launch(ctx, false, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
-}
-
-int sspbo_score_umma_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
-                               float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
-    return launch(ctx, true, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
+    return launch(ctx, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
 }

@@ -298,10 +298,10 @@ def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
             assert idx3 == int(np.argmax(ref_score))
 
 
-@pytest.mark.parametrize("T,phase32", [(60, True), (60, False), (260, True), (300, True)])
+@pytest.mark.parametrize("T,phase32", [(60, True), (60, False), (127, True), (250, True)])
 def test_score_lowrank_c3(pkg, T, phase32):
-    """Low-rank tcgen05 engine (S = I/alpha - V^T V, one row per observation) on config C3 at ranks 60 / 260 / 300
-    (one and two accumulator chunks), with candidates placed at every distance from the observations so that the
+    """Low-rank tcgen05 engine (S = I/alpha - V^T V, one row per observation) on config C3 at ranks 60 / 127 / 250
+    (64-, 128- and 256-column accumulators), with candidates placed at every distance from the observations so that the
     remaining prior variance spans (0, 1): the ones below the flag threshold must come back from the exact float64
     pass, all within the 1e-4 tolerance; both phase paths (32-bit fixed point, Q31.32)."""
     from ssp_bayesopt_b200 import _lib
