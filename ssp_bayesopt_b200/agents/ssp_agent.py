@@ -82,9 +82,8 @@ class SSPAgent(Agent):
 
     def eval(self, xs):
         """mu (1, n), var (n,), acq (n,) with acq = var_weight (sqrt(var + gamma_t) - sqrt(gamma_t))."""
-        _, (mu, var, acq) = self._scoring_engine().score(xs, self.var_weight, self._gamma(), want_outputs=True,
-                                                         engine=self.score_engine)
-        return (mu.double().cpu().numpy().reshape(1, -1), var.double().cpu().numpy(), acq.double().cpu().numpy())
+        mu, var, acq = self._scoring_engine().eval_host(xs, self.var_weight, self._gamma(), engine=self.score_engine)
+        return mu.reshape(1, -1), var, acq
 
     def best_candidate(self, xs, index0=0, reset_best=True):
         """argmax_i mu_i + acq_i over a candidate block (host array or device tensor).  Returns the device
@@ -132,7 +131,7 @@ class SSPAgent(Agent):
         if len(x_t.shape) < 2:
             x_val = x_t.reshape(1, x_t.shape[0])
             y_val = y_t.reshape(1, y_t.shape[0])
-        phi = np.atleast_2d(self.encode(x_val).squeeze())
+        phi = self._encode_device(x_val)                   # stays on the device: no host round trip of phi
         self.blr.update(phi, y_val)
 
         if isinstance(self.var_decay, (int, float)):
@@ -150,6 +149,10 @@ class SSPAgent(Agent):
 
     def encode(self, x):
         return self.ssp_space.encode(x)
+
+    def _encode_device(self, x):
+        """(k, n) -> device tensor (k, ssp_dim) float64 in this agent's input layout."""
+        return self._scoring_engine().encode_device(np.atleast_2d(x))
 
     def decode(self, ssp):
         return self.ssp_space.decode(ssp, method=self.decoder_method, samples=self.init_samples)

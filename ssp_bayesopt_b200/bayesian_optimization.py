@@ -101,7 +101,9 @@ class BayesianOptimization:
         if isinstance(acq_candidates, np.ndarray):
             total = acq_candidates.shape[0]
             s, e = dist.shard_range(total, rank, world)
-            return dict(total=total, start=s, x=eng.to_device(acq_candidates[s:e]), lookup=None)
+            host = np.asarray(acq_candidates)
+            return dict(total=total, start=s, x=eng.to_device(acq_candidates[s:e]),
+                        lookup=lambda i: np.asarray(host[i], dtype=np.float64))
         if isinstance(agt, agents.SSPTrajectoryAgent):
             if acq_candidates == 'grid':
                 acq_candidates = 'uniform'                           # a grid over L*x_dim axes is not meaningful
@@ -114,7 +116,20 @@ class BayesianOptimization:
                     for i in range(self.data_dim)]
             total = int(candidates_per_dim) ** self.data_dim
             s, e = dist.shard_range(total, rank, world)
-            return dict(total=total, start=s, x=eng.grid_points(axes, s, e - s), lookup=None)
+            counts = [len(a) for a in axes]
+
+            def grid_row(i):                                         # the reference's meshgrid('xy') order, on the host
+                out = np.empty(len(axes))
+                p = int(i)
+                for a in range(len(axes) - 1, 1, -1):
+                    out[a] = axes[a][p % counts[a]]
+                    p //= counts[a]
+                out[0] = axes[0][p % counts[0]]
+                p //= counts[0]
+                if len(axes) >= 2:
+                    out[1] = axes[1][p]
+                return out
+            return dict(total=total, start=s, x=eng.grid_points(axes, s, e - s), lookup=grid_row)
         if acq_candidates == 'uniform':
             total = int(n_candidates or 100000)
             s, e = dist.shard_range(total, rank, world)
@@ -144,6 +159,8 @@ class BayesianOptimization:
         eng.settle()                                   # local key final before it is combined across ranks
         dist.allreduce_best(key)
         score, gidx = eng.best()
+        if cand.get('lookup') is not None:             # every rank can name the winning row without touching the device
+            return score, gidx, np.asarray(cand['lookup'](gidx), dtype=np.float64).reshape(1, -1)
         # owner of the winning row publishes it (one small broadcast; single-GPU: a D2H copy of one row)
         rank, world = dist.rank_world()
         owner_has = start <= gidx < start + n_local

@@ -44,6 +44,7 @@ class DeviceEngine:
         self.L = 1
         self._best = self.torch.zeros(1, dtype=self.torch.int64, device=self._dev())
         self._pending = []           # score calls since the last key reset (replayed if the device asks for a rerun)
+        self._lr_used = False        # ... and whether any of them ran the low-rank engine
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self):
@@ -210,6 +211,7 @@ class DeviceEngine:
         if reset_best:
             self._best.zero_()
             self._pending = []
+            self._lr_used = False
 
         def call():
             rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, int(index0),
@@ -218,9 +220,39 @@ class DeviceEngine:
             self._check(rc, "sspbo_score")
         call()
         self._pending.append(call)
-        if want_outputs and self._needs_rerun():         # outputs are about to be read: settle them now
+        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR
+        if want_outputs and self._lr_used and self._needs_rerun():   # outputs are about to be read: settle them now
             self._replay()
         return self._best, outs
+
+    def eval_host(self, x, lam, gamma_t, engine=_lib.ENGINE_AUTO):
+        """(mu, var, acq) as float64 numpy arrays with a single device->host copy (SSPAgent.eval)."""
+        torch = self.torch
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        if xt.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        out = torch.empty((3, max(N, 1)), dtype=torch.float32, device=self._dev())
+        ptrs = [C.c_void_p(out[i].data_ptr()) for i in range(3)]
+        self._best.zero_()
+        self._pending = []
+        self._lr_used = False
+
+        def call():
+            rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, 0, float(lam),
+                                      float(gamma_t), ptrs[0], ptrs[1], ptrs[2], C.c_void_p(self._best.data_ptr()),
+                                      int(engine), self._stream())
+            self._check(rc, "sspbo_score")
+        call()
+        self._pending.append(call)
+        if self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR:
+            self._lr_used = True
+            if self._needs_rerun():
+                self._replay()
+        host = out[:, :N].double().cpu().numpy()
+        return host[0], host[1], host[2]
 
     def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 20, reset_best=True):
         """Fused scoring of candidates that live in HOST memory (numpy or CPU tensor, ideally pinned): the set is
@@ -246,9 +278,11 @@ class DeviceEngine:
         if reset_best:
             self._best.zero_()
             self._pending = []
+            self._lr_used = False
         call = lambda: self._score_host_stream(xt, N, lam, gamma_t, index0, engine, chunk)
         call()
         self._pending.append(call)
+        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR
         return self._best
 
     def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk):
@@ -299,7 +333,7 @@ class DeviceEngine:
         overflowed its flag list or saw candidates outside the declared bound, the calls are replayed with the safe
         engines.  Call before combining keys across ranks; `best()` calls it."""
         if self._pending:
-            if self._needs_rerun():
+            if self._lr_used and self._needs_rerun():    # only the low-rank engine can ask for a rerun
                 self._replay()
             self._pending = []
 
