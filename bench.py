@@ -56,34 +56,69 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML (a few microseconds per sample) when available,
+    nvidia-smi otherwise."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag = index, [], False       # samples: (sm_mhz, max_mhz, [4 flags])
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # HwSlowdown, HwThermal, SwThermal, SwPowerCap
+        self.samples.append((float(sm), float(mx), flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.samples.append((float(parts[0]), float(parts[1]), [p.lower().startswith("active") for p in parts[2:6]]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def problem_setup():
@@ -288,7 +323,7 @@ def run_native(args):
                          "frac": achieved / peaks["tflops"],
                          # dram__bytes_read+write of one k_score_umma launch (chunk of 4,194,304 candidates) from the
                          # ncu --set full capture summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
-                         "traffic": 108.6e6 if engine_used.startswith("umma") else None,
+                         "traffic": (105.3e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
                          "launch_candidates": min(chunk, n_local),
                          "executed": executed_note(engine_used, info["rank"], d, n_local, kernel_ms, peaks),
                          "note": f"algorithmic (dense form, SURVEY 8d) {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
@@ -383,7 +418,7 @@ def bo_step_c2(pkg, n_iter=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "umma"])

@@ -124,7 +124,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int kb = 0; kb < n_kb; ++kb)
                     for (int c = 0; c < n_chunks; ++c) {
-                        mbar_wait_relaxed<400>(b_empty(rb.slot), rb.phase ^ 1);
+                        mbar_wait_relaxed<64>(b_empty(rb.slot), rb.phase ^ 1);
                         uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
                         mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
                         tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, c * p.BN);
@@ -194,7 +194,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             float q = 0.f, mu_raw = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
                 const int buf = acc_of(tile_iter, c);
-                mbar_wait_relaxed<800>(tmem_full(buf), acc_phase[buf]);
+                mbar_wait_relaxed<100>(tmem_full(buf), acc_phase[buf]);
                 acc_phase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * ACC_COLS;
