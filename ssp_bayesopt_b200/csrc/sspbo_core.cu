@@ -348,6 +348,7 @@ __global__ void k_mp_op(const double* __restrict__ mp, const int* __restrict__ p
 //   k_exact_finish  : sums the RB partials, applies ssp_agent.py:136, writes outputs, max-combines the key
 // =====================================================================================
 constexpr int EX_G = 8, EX_THREADS = 256, EX_RB_MAX = 16;
+constexpr int EXL_THREADS = 512;    // flagged-candidate pass: few groups in flight, so many warps per group
 
 template <typename XT>
 __global__ void __launch_bounds__(EX_THREADS)
@@ -421,14 +422,14 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restr
 // 1e-16): var = 1/beta + 1/alpha - sum_j (v_j . psi)^2, mu = m' . psi.  One CTA per group of EX_G candidates
 // (persistent over the device-side count), psi in shared memory, one warp per row of V.
 template <typename XT>
-__global__ void __launch_bounds__(EX_THREADS)
+__global__ void __launch_bounds__(EXL_THREADS)
 k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
                 unsigned int cap, const double* __restrict__ A_turns, int n, int K, const int* __restrict__ inv_perm,
                 const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
                 double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                 float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
-    __shared__ double red[EX_G + 1][EX_THREADS / 32];
+    __shared__ double red[EX_G + 1][EXL_THREADS / 32];
     const int d = 2 * K + 1;
     const unsigned long long c0 = *count_ptr;
     if (c0 > cap) return;                               // list overflowed: the host recomputes the call with the dense factor
@@ -451,7 +452,7 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
         double q[EX_G];
 #pragma unroll
         for (int c = 0; c < EX_G; ++c) q[c] = 0.0;
-        for (int j = warp; j < r; j += EX_THREADS / 32) {
+        for (int j = warp; j < r; j += EXL_THREADS / 32) {
             const double* vrow = Vd + (size_t)j * d;
             double acc[EX_G];
 #pragma unroll
@@ -476,7 +477,7 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
             if (lane == 0) {
                 double qq = 0.0;
 #pragma unroll
-                for (int w = 0; w < EX_THREADS / 32; ++w) qq += red[warp][w];
+                for (int w = 0; w < EXL_THREADS / 32; ++w) qq += red[warp][w];
                 const double var = inv_beta + (prior_var - qq);                         // blr.py:96
                 const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
                 const int64_t row = (int64_t)list[base + warp];
@@ -1192,12 +1193,12 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
         const int gx = 2 * ctx->sm_count;
         if (x_dtype == SSPBO_F32) {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_exact_lowrank<float><<<gx, EX_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
+            k_exact_lowrank<float><<<gx, EXL_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
                 SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         } else {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_exact_lowrank<double><<<gx, EX_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
+            k_exact_lowrank<double><<<gx, EXL_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
                 SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         }
