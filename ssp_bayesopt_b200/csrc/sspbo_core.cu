@@ -1281,7 +1281,7 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
         int rc = sspbo_score_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
         if (rc) return rc;
         // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
-        { const char* dbg = getenv("SSPBO_DEBUG"); if (dbg && (atoi(dbg) & 4)) return SSPBO_OK; }   // timing experiments only
+        if (sspbo_debug_env() & 4) return SSPBO_OK;              // timing experiments only (compiled out of product builds)
         return sspbo_score_exact_launch(ctx, x, x_dtype, N, true, index0, lam, gamma_t, mu, var, acq, best, st);
     }
     int rc = sspbo_refresh_operands(ctx, st);

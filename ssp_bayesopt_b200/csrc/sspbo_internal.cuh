@@ -125,6 +125,18 @@ enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (re
        SSPBO_STAT_SCORED = 4,    // candidates scored by the low-rank pass since the last reset
        SSPBO_STAT_COUNT = 8 };
 
+// Timing experiments (tools/kbench.py): built only with -DSSPBO_EXPERIMENTS (`make EXPERIMENTS=1`).  SSPBO_DEBUG bits:
+// 1 = no MMAs issued, 2 = generators skip the phase / sincos math, 4 = skip the float64 pass over flagged candidates,
+// 8 = force the Q31.32 phase path.  In product builds the switches compile to constants.
+#ifdef SSPBO_EXPERIMENTS
+#include <stdlib.h>
+#define SSPBO_DBG_BITS(p) ((p).debug)
+static inline int sspbo_debug_env() { const char* e = getenv("SSPBO_DEBUG"); return e ? atoi(e) : 0; }
+#else
+#define SSPBO_DBG_BITS(p) 0
+static inline int sspbo_debug_env() { return 0; }
+#endif
+
 static inline int sspbo_pad64(int x) { return (x + 63) / 64 * 64; }
 
 // Operand geometry of the tcgen05 scorer for a space with K positive frequencies (d = 2K+1):

@@ -140,7 +140,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         Ring ra, rb;
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t idesc = make_idesc(BM, p.BN);
-        const bool no_mma = (p.debug & 1) != 0;
+        const bool no_mma = (SSPBO_DBG_BITS(p) & 1) != 0;
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -303,7 +303,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
-                if (p.debug & 2) {
+                if (SSPBO_DBG_BITS(p) & 2) {
 #pragma unroll
                     for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
                 } else if constexpr (P32) {
@@ -446,7 +446,7 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
     const size_t smem = 1024 + (size_t)nb * sb + tb;
     bool p32 = ctx->p32_ok && !ctx->p32_disabled;
-    { const char* dbg = getenv("SSPBO_DEBUG"); if (dbg && (atoi(dbg) & 8)) p32 = false; }     // timing experiments only
+    if (sspbo_debug_env() & 8) p32 = false;              // timing experiments only (compiled out of product builds)
     kernel_fn kern = kernel_for(ctx->n, p32);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
     if (!ls->attr_set[p32][ctx->n]) {
@@ -462,14 +462,13 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     else { p.acc_cols = 256; p.n_bufs = 1; }
     p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
     if (p.na > NA_MAX) p.na = NA_MAX;
-    { const char* e = getenv("SSPBO_NA"); if (e && atoi(e) >= 2 && atoi(e) <= p.na) p.na = atoi(e); }
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.prior_var = (float)(1.0 / ctx->alpha);
     p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
-    { const char* dbg = getenv("SSPBO_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.debug = sspbo_debug_env();
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p);

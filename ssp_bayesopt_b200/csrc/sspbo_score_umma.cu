@@ -68,7 +68,7 @@ struct Params {
     unsigned long long* stats;          // device counters (out-of-bound candidates of the 32-bit phase path)
     // 32-bit fixed-point phase path
     const int* A32_op; double x_scale;
-    int debug;                          // SSPBO_DEBUG experiments: 1 = no MMAs issued, 2 = generator skips the phase/sincos math
+    int debug;                          // SSPBO_DEBUG experiments (sspbo_internal.cuh); constant 0 in product builds
 };
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -185,7 +185,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             }
                             const uint32_t idesc = make_idesc(BM, n_eff);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16 && !(p.debug & 1); ++kk) {
+                            for (int kk = 0; kk < BK / 16 && !(SSPBO_DBG_BITS(p) & 1); ++kk) {
                                 const uint64_t off = (uint64_t)((kk * 32) >> 4);    // 16 fp16 = 32 bytes along K
                                 umma_f16(d_tmem, a_hi + off, b_hi + off, idesc, (kb != kb_first) || (kk != 0));
                                 umma_f16(d_tmem, a_hi + off, b_lo + off, idesc, 1);
@@ -325,7 +325,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                     const uint32_t empty_bar = a_empty(ra.slot);
                     const bool slot_free = mbar_test_wait(empty_bar, ra.phase ^ 1);         // early, non-blocking probe
                     float cs[GEN_ROWS][8], sn[GEN_ROWS][8];
-                    if (p.debug & 2) {
+                    if (SSPBO_DBG_BITS(p) & 2) {
 #pragma unroll
                         for (int r = 0; r < GEN_ROWS; ++r)
 #pragma unroll
@@ -597,7 +597,7 @@ int launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     p.xq = nullptr; p.tauq = (const unsigned long long*)ctx->tauq_op; p.L = ctx->L;
-    { const char* dbg = getenv("SSPBO_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.debug = sspbo_debug_env();
     if (traj) {
         const size_t count = (size_t)N * ctx->L * ctx->n;
         if (count > us->xq_cap) {

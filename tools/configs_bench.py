@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Side measurements of BASELINE configs C4 (batched independent runs) and C5 (trajectory agent) at reduced scale."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ssp_bayesopt_b200 as pkg
+from ssp_bayesopt_b200.batched import BatchedRuns
+
+
+def himmelblau(x):
+    return -((x[:, 0] ** 2 + x[:, 1] - 11) ** 2 + (x[:, 0] + x[:, 1] ** 2 - 7) ** 2) / 100.0
+
+
+def c4(runs=128, steps=5):
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    agents = []
+    t0 = time.perf_counter()
+    for r in range(runs):
+        sp = pkg.RandomSSPSpace(2, ssp_dim=512, domain_bounds=b2, length_scale=1.0, rng=r)
+        X = np.random.default_rng(r).uniform(-5, 5, (10, 2))
+        agents.append(pkg.SSPAgent(X, himmelblau(X).reshape(-1, 1), sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+    t_build = time.perf_counter() - t0
+    ax = np.linspace(-5, 5, 100)
+    grid = np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2).astype(np.float32)
+    br = BatchedRuns(agents, grid)
+    br.step(himmelblau)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        br.step(himmelblau)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    eng = agents[0]._scoring_engine()
+    print(f"C4: {runs} runs x {grid.shape[0]} candidates d={eng.d}: {dt * 1e3:.1f} ms per lock-step "
+          f"({runs * grid.shape[0] / dt:.3e} candidate evaluations/s; engine {eng.last_engine()}; set-up {t_build:.1f} s) "
+          f"-> 4096 runs: {dt * 4096 / runs:.2f} s per lock-step")
+
+
+def c5(n=1 << 20, steps=3):
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    L, xd = 10, 2
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-5, 5, (12, L * xd))
+    y = -np.sum(X ** 2, axis=1, keepdims=True) / 100.0
+    agt = pkg.SSPTrajectoryAgent(X, y, x_dim=xd, traj_len=L, domain_bounds=b2, ssp_dim=2048, length_scale=1.0,
+                                 time_length_scale=1.0, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0)
+    eng = agt._scoring_engine()
+    cand = eng.fill_uniform(0, 0, n, L * xd)
+    cand.mul_(10.0).sub_(5.0)
+    agt.best_candidate(cand)
+    eng.best()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        agt.best_candidate(cand)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(f"C5: trajectory L={L} x_dim={xd} d={eng.d}: {n} candidates in {ms:.1f} ms = {n / ms * 1e3:.3e} candidates/s "
+          f"(engine {eng.last_engine()}) -> 1e7 candidates: {1e7 / (n / ms * 1e3):.2f} s")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c4", "c5"]
+    if "c5" in which:
+        c5()
+    if "c4" in which:
+        c4()

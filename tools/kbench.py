@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only timing of the fused scorer on config C3 for several posterior ranks (CUDA events, device-resident
-candidates).  Usage: python tools/kbench.py [--ranks 60,130,260,500] [--n 4194304] [--engines lr,full]"""
+candidates).  The SSPBO_DEBUG switches need a library built with `make -C ssp_bayesopt_b200/csrc EXPERIMENTS=1`.
+Usage: python tools/kbench.py [--ranks 60,130,260,500] [--n 4194304] [--engines lr,full]"""
 import argparse, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
