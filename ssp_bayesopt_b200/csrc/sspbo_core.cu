@@ -735,7 +735,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
-    dev_free(&ctx->A32_op); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
+    dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     delete ctx;
 }
 
@@ -805,8 +805,23 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
 // the worst-case rounding of the two operands plus the 2^-23 truncation stays below 2^-20 turns (6e-6 rad);
 // otherwise the 64-bit path (Q31.32 x Q31.32) is used.
 static int build_p32_tables(sspbo_ctx* ctx) {
-    ctx->p32_ok = false;
+    ctx->p32_ok = false; ctx->pf32_ok = false;
     if (ctx->K == 0 || !(ctx->x_absmax > 0.0) || !(ctx->a_absmax > 0.0)) return SSPBO_OK;
+    {   // float32 path: theta in radians by an FMA chain; partial sums stay below 32 pi (16 turns), so every rounding is
+        // below 2^-18 rad and the MUFU range reduction (an RZ multiply by 1/2pi) adds < 1.2e-5 rad
+        if (ctx->max_turns * ctx->x_absmax <= 16.0) {
+            int kc, bn, nc, nj;
+            sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
+            std::vector<float> op((size_t)(kc / 2) * ctx->n, 0.f);
+            for (int f = 1; f <= ctx->K; ++f)
+                for (int a = 0; a < ctx->n; ++a)
+                    op[(size_t)f * ctx->n + a] = (float)(ctx->host_A_turns[(size_t)(f - 1) * ctx->n + a] * kTwoPi);
+            int rc;
+            if ((rc = dev_alloc(ctx, &ctx->Af_op, op.size()))) return rc;
+            SSPBO_CUDA(ctx, cudaMemcpy(ctx->Af_op, op.data(), op.size() * sizeof(float), cudaMemcpyHostToDevice));
+            ctx->pf32_ok = true;
+        }
+    }
     int ia = 0, ix = 0;
     while (ldexp(1.0, ia) <= ctx->a_absmax && ia < 31) ++ia;     // 2^ia > |A|max
     while (ldexp(1.0, ix) <= ctx->x_absmax && ix < 31) ++ix;     // 2^ix > |x|max
@@ -1323,7 +1338,7 @@ extern "C" int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, i
     if (rank) *rank = ctx->lr_rank;
     if (valid) *valid = ctx->lr_valid ? 1 : 0;
     if (disabled) *disabled = ctx->lr_disabled ? 1 : 0;
-    if (phase32) *phase32 = (ctx->p32_ok && !ctx->p32_disabled) ? 1 : 0;
+    if (phase32) *phase32 = ((ctx->p32_ok || ctx->pf32_ok) && !ctx->p32_disabled) ? 1 : 0;
     return SSPBO_OK;
 }
 extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled) {

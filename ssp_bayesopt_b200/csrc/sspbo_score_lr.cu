@@ -51,7 +51,7 @@ constexpr int MAX_N = 8;
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
-    const long long* Aq_op; const int* A32_op; const float* mscale; double x_scale;
+    const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
@@ -61,7 +61,9 @@ struct Params {
     int debug;
 };
 
-template <int NDIM, bool P32>
+// PH: phase arithmetic of the generator: 0 = Q31.32 x Q31.32 (any range), 1 = 32-bit fixed point (fa + fx = 55),
+// 2 = float32 FMA chain in radians (|theta| <= 16 pi by the declared bounds: rounding < 1e-5 rad)
+template <int NDIM, int PH>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -87,12 +89,13 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    if constexpr (P32) {
+    if constexpr (PH == 1 || PH == 2) {
         // axis-major inside every block of NF frequencies: one LDS.128 feeds four independent multiply-add chains
         int* A32_s = (int*)tables;
+        const int* src = PH == 1 ? p.A32_op : (const int*)p.Af_op;
         for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) {
             const int f = i / NDIM, a = i - f * NDIM;
-            A32_s[((f / NF) * NDIM + a) * NF + (f % NF)] = p.A32_op[i];
+            A32_s[((f / NF) * NDIM + a) * NF + (f % NF)] = src[i];
         }
     } else {
         for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
@@ -272,7 +275,17 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
                 loaded_iter = tile_iter;
                 const long long g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
-                if constexpr (P32) {
+                if constexpr (PH == 2) {
+                    bool oor = false;
+#pragma unroll
+                    for (int a = 0; a < NDIM; ++a) {
+                        float v0 = 0.f;
+                        if (g0 < N) v0 = p.x_f64 ? (float)((const double*)p.x)[g0 * NDIM + a] : ((const float*)p.x)[g0 * NDIM + a];
+                        oor |= !(fabsf(v0) <= p.x_absmax);
+                        xq0[a] = __float_as_int(v0);
+                    }
+                    if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
+                } else if constexpr (PH == 1) {
                     bool oor = false;
 #pragma unroll
                     for (int a = 0; a < NDIM; ++a) {
@@ -306,7 +319,19 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 if (SSPBO_DBG_BITS(p) & 2) {
 #pragma unroll
                     for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
-                } else if constexpr (P32) {
+                } else if constexpr (PH == 2) {
+                    const float* Afblk = (const float*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF], radians per unit
+                    float t[NF];
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) t[i] = Afblk[i] * __int_as_float(xq0[0]);
+#pragma unroll
+                    for (int a = 1; a < NDIM; ++a) {
+#pragma unroll
+                        for (int i = 0; i < NF; ++i) t[i] = fmaf(Afblk[a * NF + i], __int_as_float(xq0[a]), t[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) { cs[i] = __cosf(t[i]); sn[i] = __sinf(t[i]); }   // MUFU reduces the range itself
+                } else if constexpr (PH == 1) {
                     const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF]
                     long long t[NF];                                      // phase in turns at bit 55
 #pragma unroll
@@ -383,7 +408,7 @@ struct LrState {
     const void* bh = nullptr; const void* bl = nullptr;
     int KC_pad = 0, BN = 0;
     int max_smem = 0;
-    bool attr_set[2][MAX_N + 1] = {};
+    bool attr_set[3][MAX_N + 1] = {};
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
@@ -391,21 +416,17 @@ size_t table_bytes(const sspbo_ctx* ctx) {
 }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
-kernel_fn kernel_for(int n, bool p32) {
-    if (p32) {
-        switch (n) {
-            case 1: return k_score_lr<1, true>; case 2: return k_score_lr<2, true>; case 3: return k_score_lr<3, true>;
-            case 4: return k_score_lr<4, true>; case 5: return k_score_lr<5, true>; case 6: return k_score_lr<6, true>;
-            case 7: return k_score_lr<7, true>; case 8: return k_score_lr<8, true>;
-        }
-        return nullptr;
-    }
+template <int PH>
+kernel_fn kernel_for_n(int n) {
     switch (n) {
-        case 1: return k_score_lr<1, false>; case 2: return k_score_lr<2, false>; case 3: return k_score_lr<3, false>;
-        case 4: return k_score_lr<4, false>; case 5: return k_score_lr<5, false>; case 6: return k_score_lr<6, false>;
-        case 7: return k_score_lr<7, false>; case 8: return k_score_lr<8, false>;
+        case 1: return k_score_lr<1, PH>; case 2: return k_score_lr<2, PH>; case 3: return k_score_lr<3, PH>;
+        case 4: return k_score_lr<4, PH>; case 5: return k_score_lr<5, PH>; case 6: return k_score_lr<6, PH>;
+        case 7: return k_score_lr<7, PH>; case 8: return k_score_lr<8, PH>;
     }
     return nullptr;
+}
+kernel_fn kernel_for(int n, int ph) {
+    return ph == 2 ? kernel_for_n<2>(n) : (ph == 1 ? kernel_for_n<1>(n) : kernel_for_n<0>(n));
 }
 
 }  // namespace
@@ -445,16 +466,21 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
     const size_t smem = 1024 + (size_t)nb * sb + tb;
-    bool p32 = ctx->p32_ok && !ctx->p32_disabled;
-    if (sspbo_debug_env() & 8) p32 = false;              // timing experiments only (compiled out of product builds)
-    kernel_fn kern = kernel_for(ctx->n, p32);
+    // phase path: float32 FMA chain when the declared bounds keep |theta| small, 32-bit fixed point when they allow it,
+    // Q31.32 otherwise (or after candidates outside the declared bound were seen)
+    int ph = 0;
+    if (!ctx->p32_disabled) ph = ctx->pf32_ok ? 2 : (ctx->p32_ok ? 1 : 0);
+    if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
+    if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
+    kernel_fn kern = kernel_for(ctx->n, ph);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
-    if (!ls->attr_set[p32][ctx->n]) {
+    if (!ls->attr_set[ph][ctx->n]) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ls->max_smem));
-        ls->attr_set[p32][ctx->n] = true;
+        ls->attr_set[ph][ctx->n] = true;
     }
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
-    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.mscale = ctx->mscale; p.x_scale = p32 ? ldexp(1.0, ctx->p32_fx) : 0.0;
+    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.Af_op = ctx->Af_op; p.mscale = ctx->mscale;
+    p.x_scale = ph == 1 ? ldexp(1.0, ctx->p32_fx) : 0.0; p.x_absmax = (float)(ctx->x_absmax * 1.000001);
     p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
     if (bn <= 64) { p.acc_cols = 64; p.n_bufs = 2; }
