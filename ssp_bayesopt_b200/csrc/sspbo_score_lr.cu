@@ -22,8 +22,10 @@
 //                        var < SSPBO_LR_FLAG_FRACTION / alpha are appended to the flag list instead (the exact float64
 //                        engine re-scores them right after this kernel, sspbo_core.cu:k_exact_*).
 // TMEM map (512 columns): accumulator buffer(s) first ([0,128) / [0,256)), the A ring behind them.
-// Rank: r_eff = r + 1 rows (row 0 = m'), one chunk of BN = ceil16(r_eff) <= 256 rows: two accumulator buffers alternating
-// by tile while BN <= 128, a single 256-column accumulator beyond (the epilogue then sits between two tiles).
+// Rank: r_eff = r + 1 rows (row 0 = m'), one chunk of BN = ceil16(r_eff) <= 256 rows.  BN <= 128: the B slot's hi and lo
+// tiles are read through ONE descriptor as a 2 BN-row operand (two MMAs per K = 16 step instead of three; the accumulator
+// is 2 BN wide and the epilogue adds its halves); two accumulator buffers alternate by tile while BN <= 64, a single
+// 256-column accumulator beyond (the epilogue then sits between two tiles).
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
 #include "sspbo_internal.cuh"
@@ -54,6 +56,7 @@ struct Params {
     const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
+    int merged;                         // BN <= 128: hi|lo tiles of the B slot read as ONE 2 BN-row operand (two MMAs per K step)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
     float *mu, *var, *acq;
     unsigned long long* best;
@@ -142,7 +145,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         // itself must stay at a few instructions per tcgen05.mma.
         Ring ra, rb;
         uint32_t acc_phase[2] = {0, 0};
-        const uint32_t idesc = make_idesc(BM, p.BN);
+        const uint32_t idesc = make_idesc(BM, p.BN), idesc2 = make_idesc(BM, 2 * p.BN);
         const bool no_mma = (SSPBO_DBG_BITS(p) & 1) != 0;
         int tile_iter = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
@@ -163,16 +166,31 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
                     if (elect_one()) {
                         if (!no_mma) {
-                            // kk = 0: the first MMA of a tile overwrites the accumulator
-                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
-                            umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
-                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+                            // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.
+                            // The first MMA of a tile overwrites the accumulator.
+                            if (p.merged) {
+                                // The tcgen05 instruction stream itself is the scarce resource here (~50 cycles of issue
+                                // per instruction, measured), so as few, as wide instructions as possible: the lo tile
+                                // follows the hi tile in the B slot, ONE descriptor with N = 2 BN covers [V_hi; V_lo]:
+                                // accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN) psi_hi V_lo^T; a second MMA
+                                // adds psi_lo V_hi^T to the first half.  The epilogue adds the halves.
+                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
 #pragma unroll
-                            for (int kk = 1; kk < BK / 16; ++kk) {
-                                // 16 fp16 along K = 32 bytes in shared memory (descriptor units of 16 B) = 8 TMEM columns
-                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
-                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
-                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                                for (int kk = 1; kk < BK / 16; ++kk) {
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc2);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                                }
+                            } else {
+                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
+                                umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+#pragma unroll
+                                for (int kk = 1; kk < BK / 16; ++kk) {
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                                }
                             }
                         }
                         umma_commit(b_empty(rb.slot));                    // frees the B slot when these MMAs retire
@@ -201,6 +219,24 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 acc_phase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * ACC_COLS;
+                if (p.merged) {
+                    // columns [0, BN): psi_hi V_hi^T + psi_lo V_hi^T, columns [BN, 2 BN): psi_hi V_lo^T
+                    for (int g = 0; g < p.BN; g += 16) {                  // BN % 16 == 0
+                        uint32_t va[16], vb[16];
+                        tmem_ld16(taddr + (uint32_t)g, va);
+                        tmem_ld16(taddr + (uint32_t)(p.BN + g), vb);
+                        tmem_ld_wait();
+                        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float y0 = __uint_as_float(va[i]) + __uint_as_float(vb[i]);
+                            const float y1 = __uint_as_float(va[i + 1]) + __uint_as_float(vb[i + 1]);
+                            if (i == 0 && g == 0) { mu_raw = y0; y0 = 0.f; }       // output row 0 is m' . psi, not a row of V
+                            q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                        }
+                        q += q0 + q1;
+                    }
+                } else
                 for (int g = 0; g < p.BN; g += 64) {                      // BN % 16 == 0; up to 64 columns in flight
                     uint32_t v[64];
                     const int nld = min(4, (p.BN - g) >> 4);
@@ -483,8 +519,9 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     p.x_scale = ph == 1 ? ldexp(1.0, ctx->p32_fx) : 0.0; p.x_absmax = (float)(ctx->x_absmax * 1.000001);
     p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
     // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
-    if (bn <= 64) { p.acc_cols = 64; p.n_bufs = 2; }
-    else if (bn <= 128) { p.acc_cols = 128; p.n_bufs = 2; }
+    // BN <= 128: merged operand, the accumulator is 2 BN wide
+    p.merged = bn <= 128;
+    if (bn <= 64) { p.acc_cols = 128; p.n_bufs = 2; }
     else { p.acc_cols = 256; p.n_bufs = 1; }
     p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
     if (p.na > NA_MAX) p.na = NA_MAX;
