@@ -128,81 +128,77 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         if (lane == 0) {
             Ring rb;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int kb = 0; kb < n_kb; ++kb)
-                    for (int c = 0; c < n_chunks; ++c) {
-                        mbar_wait_relaxed<64>(b_empty(rb.slot), rb.phase ^ 1);
-                        uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
-                        mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
-                        tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, c * p.BN);
-                        tma_load_2d(smem_u32(st + b_tile_bytes), &map_lo, b_full(rb.slot), kb * BK, c * p.BN);
-                        rb.advance(p.nb);
-                    }
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_relaxed<64>(b_empty(rb.slot), rb.phase ^ 1);
+                    uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
+                    mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
+                    tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, 0);
+                    tma_load_2d(smem_u32(st + b_tile_bytes), &map_lo, b_full(rb.slot), kb * BK, 0);
+                    rb.advance(p.nb);
+                }
         }
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ================================
         // The whole warp walks the pipeline (warp-uniform control flow keeps ring state and descriptors in uniform
-        // registers); one elected lane issues.  With N <= 128 an MMA retires in 32-64 cycles, so the issue sequence
-        // itself must stay at a few instructions per tcgen05.mma.
+        // registers); one elected lane issues.  This loop is the consumer side of every k-block and runs on ONE warp,
+        // so it is kept short: one wait per ring, one fence, one elected section with the MMAs and all commits.
         Ring ra, rb;
         uint32_t acc_phase[2] = {0, 0};
         const uint32_t idesc = make_idesc(BM, p.BN), idesc2 = make_idesc(BM, 2 * p.BN);
         const bool no_mma = (SSPBO_DBG_BITS(p) & 1) != 0;
+        const uint64_t b_desc0 = make_desc_sw128(smem_u32(b_ring));       // slot s: start address + s * slot bytes (16 B units)
+        const uint32_t b_slot_units = (uint32_t)(b_slot_bytes >> 4), b_lo_units = (uint32_t)(b_tile_bytes >> 4);
+        const uint32_t a_ring0 = tmem_base + A_RING_COL0;
+        const bool merged = p.merged != 0;
         int tile_iter = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter)
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            const int buf = tile_iter & (p.n_bufs - 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+            mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);               // the epilogue has drained this accumulator
+            acc_phase[buf] ^= 1;
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
+                mbar_wait(b_full(rb.slot), rb.phase);
                 tc_fence_after();
-                const uint32_t a_hi = tmem_base + A_RING_COL0 + (uint32_t)(ra.slot * A_SLOT_COLS);
-                for (int c = 0; c < n_chunks; ++c) {
-                    const int buf = acc_of(tile_iter, c);
-                    if (kb == 0) {                                        // first use of this accumulator in the tile: the
-                        mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);   // epilogue must have drained it
-                        acc_phase[buf] ^= 1;
-                    }
-                    mbar_wait(b_full(rb.slot), rb.phase);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(b_ring + (size_t)rb.slot * b_slot_bytes);
-                    const uint64_t b_hi = make_desc_sw128(sb), b_lo = make_desc_sw128(sb + b_tile_bytes);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
-                    if (elect_one()) {
-                        if (!no_mma) {
-                            // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.
-                            // The first MMA of a tile overwrites the accumulator.
-                            if (p.merged) {
-                                // The tcgen05 instruction stream itself is the scarce resource here (~50 cycles of issue
-                                // per instruction, measured), so as few, as wide instructions as possible: the lo tile
-                                // follows the hi tile in the B slot, ONE descriptor with N = 2 BN covers [V_hi; V_lo]:
-                                // accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN) psi_hi V_lo^T; a second MMA
-                                // adds psi_lo V_hi^T to the first half.  The epilogue adds the halves.
-                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
-                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+                const uint32_t a_hi = a_ring0 + (uint32_t)(ra.slot * A_SLOT_COLS);
+                const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)rb.slot * b_slot_units);
+                if (elect_one()) {
+                    if (!no_mma) {
+                        // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.
+                        // The first MMA of a tile overwrites the accumulator.
+                        if (merged) {
+                            // The lo tile follows the hi tile in the B slot, so ONE descriptor with N = 2 BN covers
+                            // [V_hi; V_lo]: accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN) psi_hi V_lo^T; a
+                            // second MMA adds psi_lo V_hi^T to the first half.  The epilogue adds the halves.
+                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
 #pragma unroll
-                                for (int kk = 1; kk < BK / 16; ++kk) {
-                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc2);
-                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
-                                }
-                            } else {
-                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
-                                umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
-                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+                            for (int kk = 1; kk < BK / 16; ++kk) {
+                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc2);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                            }
+                        } else {
+                            const uint64_t b_lo = b_hi + b_lo_units;
+                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
+                            umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
 #pragma unroll
-                                for (int kk = 1; kk < BK / 16; ++kk) {
-                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
-                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
-                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
-                                }
+                            for (int kk = 1; kk < BK / 16; ++kk) {
+                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
                             }
                         }
-                        umma_commit(b_empty(rb.slot));                    // frees the B slot when these MMAs retire
-                        if (kb == n_kb - 1) umma_commit(tmem_full(buf));
                     }
-                    __syncwarp();
-                    rb.advance(p.nb);
+                    umma_commit(b_empty(rb.slot));                        // frees the B slot when these MMAs retire
+                    umma_commit(a_empty(ra.slot));                        // ... and the A slot
+                    if (kb == n_kb - 1) umma_commit(tmem_full(buf));
                 }
-                if (elect_one()) umma_commit(a_empty(ra.slot));           // frees the A slot
                 __syncwarp();
+                rb.advance(p.nb);
                 ra.advance(NA);
             }
+        }
     } else if (warp < WARP_GEN0) {
         // ================================ epilogue ================================
         const int quad = warp & 3;                                        // TMEM lane quadrant this warp may read
