@@ -56,6 +56,7 @@ struct Params {
     const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
+    int split_issue;                    // BN > 128: next k-block's barrier waits between the two halves of the MMAs
     int merged;                         // BN <= 128: hi|lo tiles of the B slot read as ONE 2 BN-row operand (two MMAs per K step)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
     float *mu, *var, *acq;
@@ -150,53 +151,128 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         const uint32_t b_slot_units = (uint32_t)(b_slot_bytes >> 4), b_lo_units = (uint32_t)(b_tile_bytes >> 4);
         const uint32_t a_ring0 = tmem_base + A_RING_COL0;
         const bool merged = p.merged != 0;
-        int tile_iter = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            const int buf = tile_iter & (p.n_bufs - 1);
-            const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
-            mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);               // the epilogue has drained this accumulator
-            acc_phase[buf] ^= 1;
-            for (int kb = 0; kb < n_kb; ++kb) {
+        if (p.split_issue) {
+            // Software pipeline: the waits for k-block i + 1 sit BETWEEN the two halves of the MMAs of k-block i, so the
+            // tensor pipe always has queued work while this warp polls barriers (its instruction queue is only a few
+            // MMAs deep: issuing a whole k-block and then waiting would let it run dry).
+            const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const long long total_blocks = my_tiles * n_kb;
+            if (total_blocks > 0) {
                 mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
                 mbar_wait(b_full(rb.slot), rb.phase);
+            }
+            int tile_iter = 0, kb = 0;
+            for (long long g = 0; g < total_blocks; ++g) {
+                const int buf = tile_iter & (p.n_bufs - 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+                if (kb == 0) {
+                    mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);           // the epilogue has drained this accumulator
+                    acc_phase[buf] ^= 1;
+                }
                 tc_fence_after();
                 const uint32_t a_hi = a_ring0 + (uint32_t)(ra.slot * A_SLOT_COLS);
                 const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)rb.slot * b_slot_units);
-                if (elect_one()) {
-                    if (!no_mma) {
-                        // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.
-                        // The first MMA of a tile overwrites the accumulator.
-                        if (merged) {
-                            // The lo tile follows the hi tile in the B slot, so ONE descriptor with N = 2 BN covers
-                            // [V_hi; V_lo]: accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN) psi_hi V_lo^T; a
-                            // second MMA adds psi_lo V_hi^T to the first half.  The epilogue adds the halves.
-                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
-                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
-#pragma unroll
-                            for (int kk = 1; kk < BK / 16; ++kk) {
-                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc2);
-                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
-                            }
-                        } else {
-                            const uint64_t b_lo = b_hi + b_lo_units;
-                            umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
-                            umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
-                            umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
-#pragma unroll
-                            for (int kk = 1; kk < BK / 16; ++kk) {
-                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
-                                umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
-                                umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
-                            }
-                        }
+                const uint64_t b_lo = b_hi + b_lo_units;
+                const uint32_t a_bar = a_empty(ra.slot), b_bar = b_empty(rb.slot);
+                // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.  The first MMA
+                // of a tile overwrites the accumulator.  Merged: the lo tile follows the hi tile in the B slot, so ONE
+                // descriptor with N = 2 BN covers [V_hi; V_lo]: accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN)
+                // psi_hi V_lo^T; a second MMA adds psi_lo V_hi^T to the first half; the epilogue adds the halves.
+                if (elect_one() && !no_mma) {
+                    if (merged) {
+                        umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
+                        umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 8, b_hi + 2, idesc2);
+                        umma_f16_ts_acc(d_tmem, a_hi + 32 + 8, b_hi + 2, idesc);
+                    } else {
+                        umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
+                        umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 8, b_hi + 2, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 8, b_lo + 2, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 32 + 8, b_hi + 2, idesc);
                     }
-                    umma_commit(b_empty(rb.slot));                        // frees the B slot when these MMAs retire
-                    umma_commit(a_empty(ra.slot));                        // ... and the A slot
-                    if (kb == n_kb - 1) umma_commit(tmem_full(buf));
                 }
                 __syncwarp();
                 rb.advance(p.nb);
                 ra.advance(NA);
+                if (g + 1 < total_blocks) {                                   // next k-block's operands, while the pipe works
+                    mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
+                    mbar_wait(b_full(rb.slot), rb.phase);
+                }
+                if (elect_one()) {
+                    if (!no_mma) {
+                        if (merged) {
+                            umma_f16_ts_acc(d_tmem, a_hi + 16, b_hi + 4, idesc2);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32 + 16, b_hi + 4, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 24, b_hi + 6, idesc2);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32 + 24, b_hi + 6, idesc);
+                        } else {
+                            umma_f16_ts_acc(d_tmem, a_hi + 16, b_hi + 4, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 16, b_lo + 4, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32 + 16, b_hi + 4, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 24, b_hi + 6, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 24, b_lo + 6, idesc);
+                            umma_f16_ts_acc(d_tmem, a_hi + 32 + 24, b_hi + 6, idesc);
+                        }
+                    }
+                    umma_commit(b_bar);                                       // frees the B slot when these MMAs retire
+                    umma_commit(a_bar);                                       // ... and the A slot
+                    if (kb == n_kb - 1) umma_commit(tmem_full(buf));
+                }
+                __syncwarp();
+                if (++kb == n_kb) { kb = 0; ++tile_iter; }
+            }
+        } else {
+            // short MMAs (BN <= 128): one elected section per k-block keeps the loop at a minimum of instructions
+            int tile_iter = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+                const int buf = tile_iter & (p.n_bufs - 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+                mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);               // the epilogue has drained this accumulator
+                acc_phase[buf] ^= 1;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
+                    mbar_wait(b_full(rb.slot), rb.phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = a_ring0 + (uint32_t)(ra.slot * A_SLOT_COLS);
+                    const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)rb.slot * b_slot_units);
+                    if (elect_one()) {
+                        if (!no_mma) {
+                            // 16 fp16 along K = 32 bytes in shared memory (2 descriptor units of 16 B) = 8 TMEM columns.
+                            // The first MMA of a tile overwrites the accumulator.
+                            if (merged) {
+                                // The lo tile follows the hi tile in the B slot, so ONE descriptor with N = 2 BN covers
+                                // [V_hi; V_lo]: accumulator columns [0, BN) get psi_hi V_hi^T, [BN, 2 BN) psi_hi V_lo^T; a
+                                // second MMA adds psi_lo V_hi^T to the first half.  The epilogue adds the halves.
+                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc2, kb != 0);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+    #pragma unroll
+                                for (int kk = 1; kk < BK / 16; ++kk) {
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc2);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                                }
+                            } else {
+                                const uint64_t b_lo = b_hi + b_lo_units;
+                                umma_f16_ts(d_tmem, a_hi, b_hi, idesc, kb != 0);
+                                umma_f16_ts_acc(d_tmem, a_hi, b_lo, idesc);
+                                umma_f16_ts_acc(d_tmem, a_hi + 32, b_hi, idesc);
+    #pragma unroll
+                                for (int kk = 1; kk < BK / 16; ++kk) {
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_hi + 2 * kk, idesc);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 8 * kk, b_lo + 2 * kk, idesc);
+                                    umma_f16_ts_acc(d_tmem, a_hi + 32 + 8 * kk, b_hi + 2 * kk, idesc);
+                                }
+                            }
+                        }
+                        umma_commit(b_empty(rb.slot));                        // frees the B slot when these MMAs retire
+                        umma_commit(a_empty(ra.slot));                        // ... and the A slot
+                        if (kb == n_kb - 1) umma_commit(tmem_full(buf));
+                    }
+                    __syncwarp();
+                    rb.advance(p.nb);
+                    ra.advance(NA);
+                }
             }
         }
     } else if (warp < WARP_GEN0) {
@@ -517,6 +593,7 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
     // BN <= 128: merged operand, the accumulator is 2 BN wide
     p.merged = bn <= 128;
+    p.split_issue = bn > 128;
     if (bn <= 64) { p.acc_cols = 128; p.n_bufs = 2; }
     else { p.acc_cols = 256; p.n_bufs = 1; }
     p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
