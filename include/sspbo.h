@@ -122,7 +122,9 @@ int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t
                       int* rerun, int reset, void* stream);
 /* state of the low-rank form: rows of V appended since blr_init, whether it is usable, policy switches */
 int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, int* disabled, int* phase32);
-/* policy overrides for SSPBO_ENGINE_AUTO: 1 = enable, 0 = disable, -1 = leave */
+/* policy overrides: lowrank_enabled 1 = enable, 0 = disable, -1 = leave (SSPBO_ENGINE_AUTO); phase32_enabled selects the
+ * phase arithmetic of the tensor-core scorers: 0 = Q31.32 only, 1 = fastest path the declared bounds allow (float32 FMA
+ * chain, else 32-bit fixed point, else Q31.32), 2 = fixed point only, -1 = leave */
 int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled);
 /* host helpers for the packed key */
 void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index);

@@ -1344,7 +1344,10 @@ extern "C" int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, i
 extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled) {
     if (!ctx) return SSPBO_EINVAL;
     if (lowrank_enabled >= 0) ctx->lr_disabled = !lowrank_enabled;
-    if (phase32_enabled >= 0) ctx->p32_disabled = !phase32_enabled;
+    if (phase32_enabled >= 0) {                          // 0: Q31.32 only; 1: fastest valid path; 2: fixed point only (no float32 chain)
+        ctx->p32_disabled = (phase32_enabled == 0);
+        ctx->pf32_disabled = (phase32_enabled == 2);
+    }
     return SSPBO_OK;
 }
 

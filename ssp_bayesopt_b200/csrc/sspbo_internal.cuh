@@ -73,6 +73,7 @@ struct sspbo_ctx {
     int* A32_op = nullptr;           // (KC_pad/2) x n, Q(31-fa).fa turns per unit
     bool p32_ok = false;
     float* Af_op = nullptr;          // (KC_pad/2) x n float32, radians per unit (float32 phase path)
+    bool pf32_disabled = false;      // policy override: never use the float32 chain
     bool pf32_ok = false;            // declared bounds keep |theta| <= 16 pi: float32 FMA chain is accurate to < 1e-5 rad
     int p32_fa = 0, p32_fx = 0;      // fractional bits of A32_op and of the candidate coordinates
     double x_absmax = 0.0;           // declared bound on |x| (0 = unknown)

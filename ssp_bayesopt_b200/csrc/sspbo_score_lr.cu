@@ -577,7 +577,7 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     // phase path: float32 FMA chain when the declared bounds keep |theta| small, 32-bit fixed point when they allow it,
     // Q31.32 otherwise (or after candidates outside the declared bound were seen)
     int ph = 0;
-    if (!ctx->p32_disabled) ph = ctx->pf32_ok ? 2 : (ctx->p32_ok ? 1 : 0);
+    if (!ctx->p32_disabled) ph = (ctx->pf32_ok && !ctx->pf32_disabled) ? 2 : (ctx->p32_ok ? 1 : 0);
     if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
     if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
     kernel_fn kern = kernel_for(ctx->n, ph);

@@ -322,7 +322,7 @@ class DeviceEngine:
         return dict(rank=v[0].value, valid=bool(v[1].value), disabled=bool(v[2].value), phase32=bool(v[3].value))
 
     def set_policy(self, lowrank=None, phase32=None):
-        enc = lambda f: -1 if f is None else int(bool(f))
+        enc = lambda f: -1 if f is None else int(f)         # phase32: False/0 Q31.32 only, True/1 fastest, 2 fixed point only
         self._check(self.lib.sspbo_set_policy(self._ctx, enc(lowrank), enc(phase32)), "sspbo_set_policy")
 
     def _needs_rerun(self):

@@ -298,12 +298,12 @@ def test_score_umma_shapes(pkg, kind, ssp_dim, n_dim, N):
             assert idx3 == int(np.argmax(ref_score))
 
 
-@pytest.mark.parametrize("T,phase32", [(60, True), (60, False), (127, True), (250, True)])
+@pytest.mark.parametrize("T,phase32", [(60, 1), (60, 0), (60, 2), (127, 1), (250, 1)])
 def test_score_lowrank_c3(pkg, T, phase32):
     """Low-rank tcgen05 engine (S = I/alpha - V^T V, one row per observation) on config C3 at ranks 60 / 127 / 250
     (64-, 128- and 256-column accumulators), with candidates placed at every distance from the observations so that the
     remaining prior variance spans (0, 1): the ones below the flag threshold must come back from the exact float64
-    pass, all within the 1e-4 tolerance; both phase paths (32-bit fixed point, Q31.32)."""
+    pass, all within the 1e-4 tolerance; all three phase paths (float32 chain, 32-bit fixed point, Q31.32)."""
     from ssp_bayesopt_b200 import _lib
     sp, model, ref, X = _c3_setup(pkg, T)
     eng = sp.engine
@@ -335,7 +335,7 @@ def test_score_lowrank_c3(pkg, T, phase32):
     assert st["scored"] == N and 60 <= st["flagged"] < N // 4 and st["overflow"] == 0 and st["out_of_range"] == 0, st
     frac_prior = (ref_var - 1.0 / ref.beta) * 0.01                           # remaining fraction of the prior variance
     assert frac_prior.min() < 1e-3 and frac_prior.max() > 0.5
-    eng.set_policy(phase32=True)
+    eng.set_policy(phase32=1)
 
 
 def test_score_lowrank_policy_and_rerun(pkg):
