@@ -438,7 +438,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                         for (int i = 0; i < NF; ++i) t[i] = fmaf(Afblk[a * NF + i], __int_as_float(xq0[a]), t[i]);
                     }
 #pragma unroll
-                    for (int i = 0; i < NF; ++i) { cs[i] = __cosf(t[i]); sn[i] = __sinf(t[i]); }   // MUFU reduces the range itself
+                    for (int i = 0; i < NF; ++i) __sincosf(t[i], &sn[i], &cs[i]);       // one RZ multiply by 1/2pi, then MUFU.SIN / MUFU.COS (the MUFU reduces the range itself)
                 } else if constexpr (PH == 1) {
                     const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF]
                     long long t[NF];                                      // phase in turns at bit 55
