@@ -424,8 +424,8 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restr
 template <typename XT>
 __global__ void __launch_bounds__(EXL_THREADS)
 k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
-                unsigned int cap, const double* __restrict__ A_turns, int n, int K, const int* __restrict__ inv_perm,
-                const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
+                unsigned int cap, const double* __restrict__ A_turns, const double* __restrict__ tau_turns, int n, int K, int L,
+                const int* __restrict__ inv_perm, const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
                 double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                 float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
@@ -442,8 +442,8 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
             const int c = i / (K + 1), f = i - c * (K + 1);
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
-                if (f == 0) cs = 1.0;
-                else psi_entry(x + (int64_t)list[base + c] * n, A_turns, (const double*)nullptr, n, K, 1, f - 1, cs, sn);
+                if (f == 0) cs = (double)L;
+                else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
             else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
@@ -471,14 +471,21 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
         }
         __syncthreads();
         if (warp < EX_G && base + warp < count) {       // one warp per candidate: mu, then the final scalars
-            double u = 0.0;
-            for (int rk = lane; rk < d; rk += 32) u = fma(mp[perm[rk]], psi_s[warp * d + rk], u);
+            double u = 0.0, ss = 0.0;
+            for (int rk = lane; rk < d; rk += 32) {
+                const double pv = psi_s[warp * d + rk];
+                u = fma(mp[perm[rk]], pv, u);
+                ss = fma(pv, pv, ss);
+            }
             u = warp_sum(u);
+            ss = warp_sum(ss);
             if (lane == 0) {
                 double qq = 0.0;
 #pragma unroll
                 for (int w = 0; w < EXL_THREADS / 32; ++w) qq += red[warp][w];
-                const double var = inv_beta + (prior_var - qq);                         // blr.py:96
+                const double dc = psi_s[warp * d + inv_perm[0]];
+                const double nrm2 = (2.0 * ss - dc * dc) / (double)d;                   // |phi|^2 = psi^T D psi (= 1 when L == 1)
+                const double var = inv_beta + (prior_var * nrm2 - qq);                  // blr.py:96
                 const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
                 const int64_t row = (int64_t)list[base + warp];
                 if (mu_out) mu_out[row] = (float)u;
@@ -775,7 +782,7 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns, At.data(), At.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns_f32, Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->twiddle, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op);
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op); dev_free(&ctx->tauf_op);
     {   // frequency table of the tcgen05 scorer: row f = A_turns of frequency f (f = 0: DC, f > K: padding) -> zeros
         int kc, bn, nc, nj;
         sspbo_umma_dims(K, &kc, &bn, &nc, &nj);
@@ -809,7 +816,7 @@ static int build_p32_tables(sspbo_ctx* ctx) {
     if (ctx->K == 0 || !(ctx->x_absmax > 0.0) || !(ctx->a_absmax > 0.0)) return SSPBO_OK;
     {   // float32 path: theta in radians by an FMA chain; partial sums stay below 32 pi (16 turns), so every rounding is
         // below 2^-18 rad and the MUFU range reduction (an RZ multiply by 1/2pi) adds < 1.2e-5 rad
-        if (ctx->max_turns * ctx->x_absmax <= 16.0) {
+        if (ctx->max_turns * ctx->x_absmax <= 15.5) {           // + half a turn of timestep phase in trajectory mode
             int kc, bn, nc, nj;
             sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
             std::vector<float> op((size_t)(kc / 2) * ctx->n, 0.f);
@@ -865,7 +872,7 @@ extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int 
     if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "space_set_traj before space_set");
     if (L < 1 || L > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "traj length must be in [1, 64]");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
-    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op);
+    dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op); dev_free(&ctx->tauf_op);
     ctx->L = L;
     if (!tau_host) { if (L != 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "tau is required when L > 1"); return SSPBO_OK; }
     std::vector<double> t((size_t)L * ctx->K);
@@ -894,6 +901,11 @@ extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int 
             }
         if ((rc = dev_alloc(ctx, &ctx->tauq_op, tq.size()))) return rc;
         SSPBO_CUDA(ctx, cudaMemcpy(ctx->tauq_op, tq.data(), tq.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        std::vector<float> tfl((size_t)L * nf, 0.f);                      // same, float32 radians in [-pi, pi]
+        for (int j = 0; j < L; ++j)
+            for (int f = 1; f <= ctx->K; ++f) tfl[(size_t)j * nf + f] = (float)(t[(size_t)j * ctx->K + f - 1] * kTwoPi);
+        if ((rc = dev_alloc(ctx, &ctx->tauf_op, tfl.size()))) return rc;
+        SSPBO_CUDA(ctx, cudaMemcpy(ctx->tauf_op, tfl.data(), tfl.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     return SSPBO_OK;
 }
@@ -1209,12 +1221,12 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
         if (x_dtype == SSPBO_F32) {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_exact_lowrank<float><<<gx, EXL_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         } else {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_exact_lowrank<double><<<gx, EXL_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->n, ctx->K, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         }
         SSPBO_LAUNCH_CHECK(ctx);

@@ -52,6 +52,7 @@ struct sspbo_ctx {
     __half* Rh = nullptr;            // hi(R[j][psi_index(c)] * r_scale)
     __half* Rl = nullptr;            // lo part (value - hi)
     float*  mp_op = nullptr;         // m' in operand order (KC_pad)
+    float* tauf_op = nullptr;        // L x (KC_pad/2) float32 radians in [-pi, pi): timestep phase of frequency f (float32 phase path)
     unsigned long long* tauq_op = nullptr;   // L x (KC_pad/2), Q0.64 turns: timestep phase of frequency f (trajectory mode)
     long long* Aq_op = nullptr;      // (KC_pad/2) x n, Q31.32 fixed point: A_turns row of frequency f (row 0 and f > K are zero)
     int KC_pad = 0, BN = 0, n_chunks = 0, NJ_pad = 0;

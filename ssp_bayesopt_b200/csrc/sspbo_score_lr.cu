@@ -49,11 +49,14 @@ constexpr int NA_MAX = 6;               // A ring slots in TMEM: 4 behind 128-co
 constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp16 per column)
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
 constexpr int MAX_NB = 8;
+constexpr int NRM_DEPTH = 8;            // tiles in flight between generator and epilogue (power of two)
 constexpr int MAX_N = 8;
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
     const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
+    // trajectory mode: L waypoints per candidate; per-timestep phase offsets (L x KC_pad/2): Q0.64 turns / float32 radians
+    int L; const unsigned long long* tauq; const float* tauf; float nrm_scale, nrm_offset;   // |phi|^2 = nrm_scale * sum(C^2 + S^2) - nrm_offset
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
     int split_issue;                    // BN > 128: next k-block's barrier waits between the two halves of the MMAs
@@ -67,7 +70,9 @@ struct Params {
 
 // PH: phase arithmetic of the generator: 0 = Q31.32 x Q31.32 (any range), 1 = 32-bit fixed point (fa + fx = 55),
 // 2 = float32 FMA chain in radians (|theta| <= 16 pi by the declared bounds: rounding < 1e-5 rad)
-template <int NDIM, int PH>
+// TRAJ: a candidate is a row of L waypoints; psi sums L unit phasors per frequency (agents/ssp_traj_agent.py:145-163 in
+// the Fourier domain) and |phi|^2 = psi^T D psi is no longer 1: the generators accumulate it for the epilogue.
+template <int NDIM, int PH, bool TRAJ>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -81,7 +86,9 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint8_t* b_ring = smem;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
     long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM (int32 in the P32 path)
-    uint64_t* bars = (uint64_t*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);
+    // |phi|^2 partial sums of the tiles in flight, [NRM_DEPTH tiles][GEN_W warps of a quadrant][128 rows] (trajectory mode)
+    float* nrm_part = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);
+    uint64_t* bars = (uint64_t*)(nrm_part + (TRAJ ? NRM_DEPTH * GEN_W * BM : 0));
     // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -103,6 +110,9 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         }
     } else {
         for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
+    }
+    if constexpr (TRAJ) {
+        for (int i = threadIdx.x; i < NRM_DEPTH * GEN_W * BM; i += THREADS) nrm_part[i] = 0.f;
     }
     if (warp == WARP_TMA && lane == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
@@ -336,10 +346,19 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             const long long gi = tile * BM + row;
             if (gi < p.N) {
                 const float mu = mu_raw * inv_mscale;
-                const float rem = p.prior_var - q * p.inv_rscale2;                    // 1/alpha - |V psi|^2
+                float prior = p.prior_var, flag_below = p.flag_below;
+                if constexpr (TRAJ) {                                                 // |phi|^2 / alpha instead of 1 / alpha
+                    float* np_ = nrm_part + (size_t)(tile_iter & (NRM_DEPTH - 1)) * GEN_W * BM + row;
+                    float ssum = 0.f;
+#pragma unroll
+                    for (int w = 0; w < GEN_W; ++w) { ssum += np_[w * BM]; np_[w * BM] = 0.f; }   // warps without a k-block in a tile write nothing
+                    const float nrm2 = fmaf(p.nrm_scale, ssum, -p.nrm_offset);
+                    prior *= nrm2; flag_below *= nrm2;
+                }
+                const float rem = prior - q * p.inv_rscale2;                          // |phi|^2 / alpha - |V psi|^2
                 const float var = p.inv_beta + rem;                                   // blr.py:96
                 bool flagged = false;
-                if (var < p.flag_below) {                                             // too close to the observations for
+                if (var < flag_below) {                                             // too close to the observations for
                     const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
                     if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
                     else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
@@ -379,10 +398,14 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         long long tile_iter = member / n_kb, loaded_iter = -1;
         unsigned long long x0[NDIM];                                      // Q31.32 candidate (two's complement)
         int xq0[NDIM];                                                    // Q.fx candidate of the 32-bit phase path
+        float nrm_acc = 0.f;                                              // sum of C^2 + S^2 over this warp's k-blocks of the tile
+        long long g0 = 0;
         for (long long g = member; g < total_blocks; g += GEN_W) {
             if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
                 loaded_iter = tile_iter;
-                const long long g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
+                nrm_acc = 0.f;
+                g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
+                if constexpr (!TRAJ) {
                 if constexpr (PH == 2) {
                     bool oor = false;
 #pragma unroll
@@ -417,6 +440,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     const char* nx = (const char*)p.x + (size_t)gn * NDIM * (p.x_f64 ? 8 : 4);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
+                }
             }
             const uint32_t empty_bar = a_empty(slot);
             bool slot_free = mbar_test_wait(empty_bar, phase ^ 1);        // early, non-blocking probe
@@ -424,7 +448,53 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
-                if (SSPBO_DBG_BITS(p) & 2) {
+                if constexpr (TRAJ) {
+                    // sum over the L waypoints of exp(i (A_f . x_j + tau_jf)); waypoints are re-read per k-block (L1 / L2)
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) { cs[i] = 0.f; sn[i] = 0.f; }
+                    const int nf = p.KC_pad >> 1, fbase = kb * 32 + half * NF;
+                    for (int j = 0; j < p.L; ++j) {
+                        if constexpr (PH == 2) {
+                            float xf[NDIM];
+#pragma unroll
+                            for (int a = 0; a < NDIM; ++a) {
+                                const size_t o = ((size_t)g0 * p.L + j) * NDIM + a;
+                                xf[a] = (g0 < N) ? (p.x_f64 ? (float)__ldg((const double*)p.x + o) : __ldg((const float*)p.x + o)) : 0.f;
+                            }
+                            const float* Afblk = (const float*)tables + (size_t)fbase * NDIM;      // [axis][NF]
+                            const float* tf = p.tauf + (size_t)j * nf + fbase;
+#pragma unroll
+                            for (int i = 0; i < NF; ++i) {
+                                float t = __ldg(tf + i);
+#pragma unroll
+                                for (int a = 0; a < NDIM; ++a) t = fmaf(Afblk[a * NF + i], xf[a], t);
+                                float s_, c_;
+                                __sincosf(t, &s_, &c_);
+                                cs[i] += c_; sn[i] += s_;
+                            }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < NDIM; ++a) {
+                                const size_t o = ((size_t)g0 * p.L + j) * NDIM + a;
+                                double v0 = 0.0;
+                                if (g0 < N) v0 = p.x_f64 ? __ldg((const double*)p.x + o) : (double)__ldg((const float*)p.x + o);
+                                x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
+                            }
+                            const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)fbase * NDIM;
+                            const unsigned long long* tq = p.tauq + (size_t)j * nf + fbase;
+#pragma unroll
+                            for (int i = 0; i < NF; ++i) {
+                                unsigned long long t = __ldg(tq + i);
+#pragma unroll
+                                for (int a = 0; a < NDIM; ++a) t += Ablk[i * NDIM + a] * x0[a];
+                                const float a0 = (float)(int)(t >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
+                                cs[i] += __cosf(a0); sn[i] += __sinf(a0);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) nrm_acc = fmaf(cs[i], cs[i], fmaf(sn[i], sn[i], nrm_acc));
+                } else if (SSPBO_DBG_BITS(p) & 2) {
 #pragma unroll
                     for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
                 } else if constexpr (PH == 2) {
@@ -491,6 +561,10 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 tmem_st8(sa + 32, wcl);
                 tmem_st8(sa + 48, wsl);
             }
+            if constexpr (TRAJ) {                                         // this warp's last k-block of the tile: its share of |phi|^2
+                if (kb + GEN_W >= n_kb)
+                    nrm_part[(size_t)(tile_iter & (NRM_DEPTH - 1)) * GEN_W * BM + member * BM + r0] = nrm_acc;
+            }
             tmem_st_wait();                                               // publish the k-block
             tc_fence_before();
             __syncwarp();
@@ -516,24 +590,34 @@ struct LrState {
     const void* bh = nullptr; const void* bl = nullptr;
     int KC_pad = 0, BN = 0;
     int max_smem = 0;
-    bool attr_set[3][MAX_N + 1] = {};
+    bool attr_set[2][3][MAX_N + 1] = {};
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
-    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
+    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (ctx->L != 1 ? NRM_DEPTH * GEN_W * BM * sizeof(float) : 0) +
+           (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
+constexpr int MAX_TRAJ_N = 3;           // waypoint dimension of the trajectory instantiations
 template <int PH>
 kernel_fn kernel_for_n(int n) {
     switch (n) {
-        case 1: return k_score_lr<1, PH>; case 2: return k_score_lr<2, PH>; case 3: return k_score_lr<3, PH>;
-        case 4: return k_score_lr<4, PH>; case 5: return k_score_lr<5, PH>; case 6: return k_score_lr<6, PH>;
-        case 7: return k_score_lr<7, PH>; case 8: return k_score_lr<8, PH>;
+        case 1: return k_score_lr<1, PH, false>; case 2: return k_score_lr<2, PH, false>; case 3: return k_score_lr<3, PH, false>;
+        case 4: return k_score_lr<4, PH, false>; case 5: return k_score_lr<5, PH, false>; case 6: return k_score_lr<6, PH, false>;
+        case 7: return k_score_lr<7, PH, false>; case 8: return k_score_lr<8, PH, false>;
     }
     return nullptr;
 }
-kernel_fn kernel_for(int n, int ph) {
+template <int PH>
+kernel_fn kernel_for_traj(int n) {
+    switch (n) {
+        case 1: return k_score_lr<1, PH, true>; case 2: return k_score_lr<2, PH, true>; case 3: return k_score_lr<3, PH, true>;
+    }
+    return nullptr;
+}
+kernel_fn kernel_for(int n, int ph, bool traj) {
+    if (traj) return ph == 2 ? kernel_for_traj<2>(n) : kernel_for_traj<0>(n);
     return ph == 2 ? kernel_for_n<2>(n) : (ph == 1 ? kernel_for_n<1>(n) : kernel_for_n<0>(n));
 }
 
@@ -541,7 +625,8 @@ kernel_fn kernel_for(int n, int ph) {
 
 // ranks this engine covers (beyond them the dense factor of sspbo_score_umma.cu is as fast)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
-    return ctx->lr_valid && ctx->L == 1 && ctx->lr_rank >= 1 && ctx->lr_rank + 1 <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
+    if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
+    return ctx->lr_valid && ctx->lr_rank >= 1 && ctx->lr_rank + 1 <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
            ctx->umma_range_ok && ctx->stats;
 }
 
@@ -577,14 +662,16 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     // phase path: float32 FMA chain when the declared bounds keep |theta| small, 32-bit fixed point when they allow it,
     // Q31.32 otherwise (or after candidates outside the declared bound were seen)
     int ph = 0;
+    const bool traj = ctx->L != 1;
     if (!ctx->p32_disabled) ph = (ctx->pf32_ok && !ctx->pf32_disabled) ? 2 : (ctx->p32_ok ? 1 : 0);
+    if (traj && ph == 1) ph = 0;                         // trajectories: float32 chain or Q31.32
     if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
     if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
-    kernel_fn kern = kernel_for(ctx->n, ph);
+    kernel_fn kern = kernel_for(ctx->n, ph, traj);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
-    if (!ls->attr_set[ph][ctx->n]) {
+    if (!ls->attr_set[traj][ph][ctx->n]) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ls->max_smem));
-        ls->attr_set[ph][ctx->n] = true;
+        ls->attr_set[traj][ph][ctx->n] = true;
     }
     p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
     p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.Af_op = ctx->Af_op; p.mscale = ctx->mscale;
@@ -604,6 +691,13 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
+    p.L = ctx->L; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
+    {   // |phi|^2 = (1/d) (psi_0^2 + 2 sum_{k>=1} (C_k^2 + S_k^2)); the generators sum C^2 + S^2 over every operand frequency,
+        // including the DC term (= L^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
+        const double d = (double)ctx->d, L2 = (double)ctx->L * ctx->L;
+        const int n_pad = ctx->KC_pad / 2 - 1 - ctx->K;
+        p.nrm_scale = (float)(2.0 / d); p.nrm_offset = (float)(L2 / d * (1.0 + 2.0 * n_pad));
+    }
     p.debug = sspbo_debug_env();
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);

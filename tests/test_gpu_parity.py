@@ -494,7 +494,7 @@ def test_trajectory_agent_golden(pkg, golden):
     assert np.array_equal(agt.decode(phi[:1]), g["decoded"])
 
 
-@pytest.mark.parametrize("L,ssp_dim,N", [(4, 51, 300), (10, 200, 1500)])
+@pytest.mark.parametrize("L,ssp_dim,N", [(4, 51, 300), (10, 200, 1500), (10, 600, 5000)])
 def test_trajectory_tcgen05_engine(pkg, L, ssp_dim, N):
     """BASELINE config C5 shape in miniature: the tcgen05 engine sums L phasors per frequency (trajectory mode)."""
     from ssp_bayesopt_b200 import _lib
@@ -513,7 +513,9 @@ def test_trajectory_tcgen05_engine(pkg, L, ssp_dim, N):
     phis = orc.traj_encode(Ax, 0.7 * np.ones(2), T, xc.astype(np.float64), L, 2)
     ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 5.0, 0.0)
     eng = agt._scoring_engine()
-    for code, name in ((_lib.ENGINE_UMMA, "umma"), (_lib.ENGINE_SIMT, "simt")):
+    for code, name, ph in ((_lib.ENGINE_UMMA, "umma", 1), (_lib.ENGINE_SIMT, "simt", 1),
+                           (_lib.ENGINE_UMMA_LR, "umma-lowrank", 1), (_lib.ENGINE_UMMA_LR, "umma-lowrank", 0)):
+        eng.set_policy(phase32=ph)                    # low-rank trajectory mode: float32 chain and Q31.32 phases
         _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True, engine=code)
         assert eng.last_engine() == name
         assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
