@@ -297,6 +297,7 @@ def run_native(args):
 
     info = eng.lowrank_info()
     sweep = rank_sweep(pkg, eng, agt, cand, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
+    enc = encode_only(eng, cand, load_peaks()) if (rank == 0 and world == 1 and not args.no_sweep) else None
     c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
     if rank == 0:
         peaks = load_peaks()
@@ -331,6 +332,7 @@ def run_native(args):
                                  "read-back); frac > 1 means the low-rank form beats the dense-form roofline by doing less "
                                  f"work, not that the tensor pipe runs above peak; peak {peaks['source']}"},
             "by_rank": sweep,
+            "encode_only": enc,
             "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                               "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
                              if cpu_rate else None),
@@ -396,6 +398,26 @@ def rank_sweep(pkg, eng, agt, cand, orc, n=1 << 22, reps=3):
         eng.score_stats(reset=True)
         out.append(row)
     return out
+
+
+def encode_only(eng, cand, peaks, n=1 << 16, reps=3):
+    """The unfused path: API `encode` (K1) writes phi (N x d float64) to HBM.  Achieved write bandwidth against the
+    measured HBM peak; the kernel is float64 throughout (the API promises 1e-13), so it is FP64-pipe-bound, not HBM-bound."""
+    import torch
+    x = cand[:n]
+    eng.encode_device(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.encode_device(x)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    gbs = n * eng.d * 8 / sec / 1e9
+    return {"kernel": "k_encode (float64 phi to HBM)", "candidates": n, "candidates_per_s": n / sec, "hbm_write_gbs": gbs,
+            "hbm_peak_gbs": peaks["hbm"], "frac_of_hbm_peak": gbs / peaks["hbm"],
+            "note": "2 d K float64 FMA per candidate: bound by the FP64 pipe; the fused scorer never materialises phi"}
 
 
 def bo_step_c2(pkg, n_iter=30):

@@ -534,6 +534,21 @@ def test_fill_uniform_bit_exact(pkg):
         assert np.array_equal(got, orc.counter_uniform(seed, start, count, n))
 
 
+def test_grid_row_lookup_matches_device_grid(pkg):
+    """`maximize` names the winning grid row on the host; it must be the row the device grid holds."""
+    for n, per_dim in ((2, 7), (3, 5)):
+        bounds = np.array([[-1.0, 2.0]] * n)
+        opt = pkg.BayesianOptimization(f=lambda x: -np.sum(x ** 2, axis=1), bounds=bounds)
+        xs0 = np.random.default_rng(n).uniform(-1, 2, (6, n))
+        agt, _, _ = opt.initialize_agent((xs0, -np.sum(xs0 ** 2, axis=1, keepdims=True)), 'ssp-rand', domain_bounds=bounds,
+                                         ssp_dim=33, length_scale=0.9, rng=0)
+        cand = opt._build_candidates(agt, 'grid', per_dim, None, 0)
+        dev = cand['x'].cpu().numpy()
+        assert dev.shape == (per_dim ** n, n)
+        for i in (0, 1, per_dim, per_dim ** n - 1, per_dim ** n // 2 + 1):
+            assert np.array_equal(cand['lookup'](i), dev[i]), (n, i)
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
