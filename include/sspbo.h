@@ -139,6 +139,15 @@ int64_t sspbo_launch_count(const sspbo_ctx* ctx);
 int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* sample_ssps_dev, int64_t M, const double* queries_dev,
                           int q, int64_t* idx_out_dev, void* stream);
 
+/* ---- K4b: direct-optim decode (sspspace.py:358-375) --------------------------------------
+ * For every query row: x* = argmax_x phi(x) . (q / max(||q||, 1e-6)) over the box `bounds_host` (n x 2 float64, row =
+ * [low, high]; NULL = unbounded), started at x0 (q x n, normally the from-set answer).  The reference minimises the
+ * negated objective with scipy's L-BFGS-B and numerical gradients; here the objective, its gradient and its Hessian are
+ * evaluated analytically in the Fourier domain and a projected, damped Newton iteration runs on the device (float64,
+ * one CTA per query).  queries_dev: q x d; x0_dev, x_out_dev: q x n float64. */
+int sspbo_decode_optim(sspbo_ctx* ctx, const double* queries_dev, int q, const double* x0_dev, const double* bounds_host,
+                       double* x_out_dev, void* stream);
+
 /* ---- K5: binding (sspspace.py:551-560) ------------------------------------------------
  * Circular convolution out[r] = a[ra] (*) b[rb] over the last axis, float64, evaluated directly in the time
  * domain (the reference goes through fft/ifft; results agree to ~1e-15).  a_dev: qa x d, b_dev: qb x d with

@@ -191,6 +191,20 @@ class BLR:
 # agent-level composition
 # --------------------------------------------------------------------------
 
+def decode_direct_optim(phase_matrix, length_scale, ssp, x0, bounds=None) -> np.ndarray:
+    """x* = argmin_x -phi(x) . unit(ssp) by scipy L-BFGS-B from x0, per query.  Ref: sspspace.py:352, 358-375
+    (`min_func`, `minimize(..., method='L-BFGS-B', bounds=self.domain_bounds)`, numerical gradients)."""
+    from scipy.optimize import minimize
+    ssp = np.atleast_2d(ssp)
+    unit = ssp / np.maximum(np.linalg.norm(ssp, axis=-1, keepdims=True), 1e-6)
+    out = np.zeros((ssp.shape[0], phase_matrix.shape[1]))
+    for i, u in enumerate(unit):
+        res = minimize(lambda x: -np.inner(encode(phase_matrix, length_scale, np.atleast_2d(x)), np.atleast_2d(u)).flatten(),
+                       np.asarray(x0[i], dtype=np.float64).flatten(), method='L-BFGS-B', bounds=bounds)
+        out[i] = res.x
+    return out
+
+
 def agent_eval(phis, blr: BLR, var_weight, gamma_t):
     """(mu, var, acq) with acq = var_weight (sqrt(var+gamma_t) - sqrt(gamma_t)).
     Ref: ssp_agent.py:133-137."""

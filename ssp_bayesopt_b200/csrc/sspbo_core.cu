@@ -53,7 +53,7 @@ __device__ __forceinline__ void psi_entry(const XT* __restrict__ xrow, const dou
     }
 }
 
-constexpr int ENC_CPB = 4;       // candidates per block
+constexpr int ENC_CPB = 8;       // candidates per block (each twiddle load feeds 2 x ENC_CPB FMAs)
 constexpr int ENC_THREADS = 256;
 
 template <typename XT>
@@ -82,12 +82,13 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c) acc[c] = 0.0;
             int idx = 0;
+#pragma unroll 4
             for (int k = 1; k <= K; ++k) {
                 idx += j; if (idx >= d) idx -= d;       // (j*k) mod d
-                double2 tw = twiddle[idx];
+                const double2 tw = __ldg(twiddle + idx);
 #pragma unroll
                 for (int c = 0; c < ENC_CPB; ++c)
-                    acc[c] += psi_s[c * d + k] * tw.x - psi_s[c * d + K + k] * tw.y;
+                    acc[c] = fma(psi_s[c * d + k], tw.x, fma(-psi_s[c * d + K + k], tw.y, acc[c]));
             }
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c)
@@ -641,6 +642,150 @@ __global__ void k_argmax_rows(const double* __restrict__ sims, int64_t M, int64_
         }
         if (l == 0) idx_out[blockIdx.x] = bi;
     }
+}
+
+// =====================================================================================
+// K4b direct-optim decode (sspspace.py:358-375): for each query, maximise f(x) = phi(x) . unit(query) over x in the domain
+// bounds, starting from x0 (the from-set answer).  The reference runs scipy's L-BFGS-B with numerical gradients on
+// -f; here f, its gradient and its Hessian are analytic in the Fourier domain,
+//   f(x) = u'_0 + sum_k ( c_k cos theta_k(x) + s_k sin theta_k(x) ),  u' = B^T unit(query),  theta_k = 2 pi A_k . x,
+// and a projected, damped Newton iteration (float64, one CTA per query) lands on the same local maximum.
+// =====================================================================================
+constexpr int DO_THREADS = 128, DO_MAXN = 8, DO_NRED = 1 + DO_MAXN + DO_MAXN * (DO_MAXN + 1) / 2;
+
+__global__ void __launch_bounds__(DO_THREADS)
+k_decode_optim(const double* __restrict__ queries, const double* __restrict__ x0, const double* __restrict__ A_turns,
+               const double2* __restrict__ twiddle, const double* __restrict__ bounds, int n, int K, int max_iter,
+               double* __restrict__ x_out) {
+    extern __shared__ double sh[];                      // uc (K), us (K), red (warps x DO_NRED)
+    double* uc = sh; double* us = sh + K; double* red = sh + 2 * K;
+    __shared__ double xs[DO_MAXN], xtrial[DO_MAXN], fgH[DO_NRED], u0_s, nrm_s;
+    __shared__ int done_s;
+    const int d = 2 * K + 1, q = blockIdx.x;
+    const double* qv = queries + (size_t)q * d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = DO_THREADS / 32;
+    // unit(query): norm with the reference's floor (sspspace.py:352)
+    {
+        double ss = 0.0;
+        for (int j = threadIdx.x; j < d; j += DO_THREADS) ss += qv[j] * qv[j];
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < nw; ++w) t += red[w]; nrm_s = fmax(sqrt(t), 1e-6); }
+        __syncthreads();
+    }
+    // u' = B^T unit(query): u'_0 = (1/d) sum_j u_j ; c_k = (2/d) sum_j u_j cos(w_jk) ; s_k = -(2/d) sum_j u_j sin(w_jk)
+    for (int k = threadIdx.x; k <= K; k += DO_THREADS) {
+        double c = 0.0, sn = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double2 tw = twiddle[(int)(((long long)j * k) % d)];
+            c = fma(qv[j], tw.x, c); sn = fma(qv[j], tw.y, sn);
+        }
+        c /= nrm_s; sn /= nrm_s;
+        if (k == 0) u0_s = c / d;
+        else { uc[k - 1] = 2.0 * c / d; us[k - 1] = -2.0 * sn / d; }
+    }
+    if (threadIdx.x < n) { xs[threadIdx.x] = x0[(size_t)q * n + threadIdx.x]; xtrial[threadIdx.x] = xs[threadIdx.x]; }
+    if (threadIdx.x == 0) done_s = 0;
+    __syncthreads();
+
+    const double twopi = 6.283185307179586476925286766559;
+    double f_cur = -1e300, step_scale = 1.0;
+    double delta[DO_MAXN];                              // thread 0: current Newton direction
+    const int nh = n * (n + 1) / 2, nred = 1 + n + nh;
+    for (int it = 0; it < max_iter; ++it) {
+        // ---- f, gradient, Hessian at xtrial (all threads) ----
+        double acc[DO_NRED];
+#pragma unroll
+        for (int i = 0; i < DO_NRED; ++i) acc[i] = 0.0;
+        for (int k = threadIdx.x; k < K; k += DO_THREADS) {
+            const double* Ak = A_turns + (size_t)k * n;
+            double t = 0.0;
+            for (int a = 0; a < n; ++a) t = fma(Ak[a], xtrial[a], t);
+            t -= rint(t);
+            double sv, cv;
+            sincospi(2.0 * t, &sv, &cv);
+            const double val = uc[k] * cv + us[k] * sv;          // contribution to f
+            const double dth = -uc[k] * sv + us[k] * cv;         // d/dtheta
+            acc[0] += val;
+            int h = 1 + n;
+            for (int a = 0; a < n; ++a) {
+                const double wa = twopi * Ak[a];
+                acc[1 + a] = fma(dth, wa, acc[1 + a]);
+                for (int b = 0; b <= a; ++b) { acc[h] = fma(-val * wa, twopi * Ak[b], acc[h]); ++h; }
+            }
+        }
+        for (int i = 0; i < nred; ++i) {
+            const double t = warp_sum(acc[i]);
+            if (lane == 0) red[warp * DO_NRED + i] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < nred; ++i) { double t = 0.0; for (int w = 0; w < nw; ++w) t += red[w * DO_NRED + i]; fgH[i] = t; }
+            const double f_trial = fgH[0] + u0_s;
+            if (f_trial >= f_cur) {                     // accept the trial point, build the next Newton step there
+                f_cur = f_trial; step_scale = 1.0;
+                for (int a = 0; a < n; ++a) xs[a] = xtrial[a];
+                // solve (-H + mu I) delta = g by Cholesky, raising mu until -H + mu I is positive definite
+                double M[DO_MAXN][DO_MAXN], g[DO_MAXN];
+                double hmax = 0.0;
+                for (int i = 0; i < nh; ++i) hmax = fmax(hmax, fabs(fgH[1 + n + i]));
+                // active set: a coordinate sitting on a bound with the gradient pushing outwards stays there, the Newton
+                // system is solved on the free coordinates only
+                bool act[DO_MAXN];
+                for (int a = 0; a < n; ++a) {
+                    g[a] = fgH[1 + a];
+                    act[a] = bounds && ((xs[a] >= bounds[2 * a + 1] && g[a] > 0.0) || (xs[a] <= bounds[2 * a] && g[a] < 0.0));
+                    if (act[a]) g[a] = 0.0;
+                }
+                double mu = 0.0;
+                bool ok = false;
+                for (int attempt = 0; attempt < 40 && !ok; ++attempt) {
+                    int h = 1 + n;
+                    for (int a = 0; a < n; ++a)
+                        for (int b = 0; b <= a; ++b) {
+                            M[a][b] = -fgH[h++];
+                            if (a == b) M[a][b] += mu;
+                            if (act[a] || act[b]) M[a][b] = (a == b) ? 1.0 : 0.0;
+                        }
+                    ok = true;
+                    for (int a = 0; a < n && ok; ++a) {
+                        for (int b = 0; b <= a; ++b) {
+                            double sum = M[a][b];
+                            for (int c = 0; c < b; ++c) sum -= M[a][c] * M[b][c];
+                            if (a == b) { if (sum <= 1e-14 * (hmax + mu)) { ok = false; break; } M[a][a] = sqrt(sum); }
+                            else M[a][b] = sum / M[b][b];
+                        }
+                    }
+                    if (!ok) mu = (mu == 0.0) ? 1e-3 * (hmax + 1e-300) : mu * 4.0;
+                }
+                for (int a = 0; a < n; ++a) {           // forward substitution L y = g
+                    double sum = g[a];
+                    for (int c = 0; c < a; ++c) sum -= M[a][c] * delta[c];
+                    delta[a] = ok ? sum / M[a][a] : 0.0;
+                }
+                for (int a = n - 1; a >= 0; --a) {      // back substitution L^T delta = y
+                    double sum = delta[a];
+                    for (int c = a + 1; c < n; ++c) sum -= M[c][a] * delta[c];
+                    delta[a] = ok ? sum / M[a][a] : g[a] / (hmax + 1e-300);
+                }
+            } else {
+                step_scale *= 0.5;                      // rejected: shorter step from the last accepted point
+            }
+            double moved = 0.0, scale = 0.0;
+            for (int a = 0; a < n; ++a) {
+                double xn = xs[a] + step_scale * delta[a];
+                if (bounds) xn = fmin(fmax(xn, bounds[2 * a]), bounds[2 * a + 1]);
+                moved = fmax(moved, fabs(xn - xs[a]));
+                scale = fmax(scale, fabs(xs[a]));
+                xtrial[a] = xn;
+            }
+            if (moved <= 1e-13 * (1.0 + scale) || step_scale < 1e-12) done_s = 1;
+        }
+        __syncthreads();
+        if (done_s) break;
+    }
+    if (threadIdx.x < n) x_out[(size_t)q * n + threadIdx.x] = xs[threadIdx.x];
 }
 
 // =====================================================================================
@@ -1395,6 +1540,32 @@ extern "C" int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* ssps, int64_t
     SSPBO_LAUNCH_CHECK(ctx);
     SSPBO_CUDA(ctx, cudaFreeAsync(unit, st));
     SSPBO_CUDA(ctx, cudaFreeAsync(sims, st));
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_decode_optim(sspbo_ctx* ctx, const double* queries, int q, const double* x0, const double* bounds_host,
+                                  double* x_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "decode_optim before space_set");
+    if (ctx->L != 1) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "decode_optim: trajectory contexts decode per waypoint through the x space");
+    if (q < 0 || (q > 0 && (!queries || !x0 || !x_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "decode_optim: null pointer");
+    if (ctx->n > DO_MAXN) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "decode_optim: domain dimension %d > %d", ctx->n, DO_MAXN);
+    if (q == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* bounds_dev = nullptr;
+    if (bounds_host) {
+        for (int a = 0; a < ctx->n; ++a)
+            if (!(bounds_host[2 * a] <= bounds_host[2 * a + 1])) SSPBO_FAIL(ctx, SSPBO_EINVAL, "decode_optim: empty bound on axis %d", a);
+        SSPBO_CUDA(ctx, cudaMallocAsync((void**)&bounds_dev, 2 * ctx->n * sizeof(double), st));
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(bounds_dev, bounds_host, 2 * ctx->n * sizeof(double), cudaMemcpyHostToDevice, st));
+        SSPBO_CUDA(ctx, cudaStreamSynchronize(st));     // bounds_host may be a temporary of the caller
+    }
+    const size_t smem = (size_t)(2 * ctx->K + (DO_THREADS / 32) * DO_NRED) * sizeof(double);
+    SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_decode_optim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_decode_optim<<<q, DO_THREADS, smem, st>>>(queries, x0, ctx->A_turns, ctx->twiddle, bounds_dev, ctx->n, ctx->K, 200, x_out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    if (bounds_dev) SSPBO_CUDA(ctx, cudaFreeAsync(bounds_dev, st));
     return SSPBO_OK;
 }
 

@@ -376,6 +376,25 @@ class DeviceEngine:
         self._check(rc, "sspbo_from_set_argmax")
         return idx
 
+    def decode_optim(self, queries, x0, bounds=None):
+        """Direct-optim decode on the device: argmax_x phi(x) . unit(query) from x0 inside `bounds` (n, 2).
+        Returns a device tensor (q, n) float64."""
+        qt = self.to_device(queries, self.torch.float64)
+        if qt.dim() == 1:
+            qt = qt.reshape(1, -1)
+        assert qt.shape[1] == self.d, f"Expected {self.d}-d SSPs, got {tuple(qt.shape)}"
+        xt = self.to_device(np.atleast_2d(x0) if not hasattr(x0, "is_cuda") else x0, self.torch.float64)
+        assert tuple(xt.shape) == (qt.shape[0], self.n), (tuple(xt.shape), qt.shape[0], self.n)
+        out = self.torch.empty_like(xt)
+        bp = None
+        if bounds is not None:
+            b = np.ascontiguousarray(np.asarray(bounds, dtype=np.float64).reshape(self.n, 2))
+            bp = b.ctypes.data_as(_lib._pd)
+        rc = self.lib.sspbo_decode_optim(self._ctx, C.c_void_p(qt.data_ptr()), qt.shape[0], C.c_void_p(xt.data_ptr()), bp,
+                                         C.c_void_p(out.data_ptr()), self._stream())
+        self._check(rc, "sspbo_decode_optim")
+        return out
+
     # ------------------------------------------------------------------ K5
     def bind(self, a, b):
         """Circular convolution of the rows of a (qa, d) and b (qb, d) with numpy broadcasting over rows."""

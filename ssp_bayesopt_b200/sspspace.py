@@ -18,7 +18,6 @@ from __future__ import annotations
 from typing import Optional, Union
 
 import numpy as np
-from scipy.optimize import minimize
 from scipy.special import gammainc
 from scipy.stats import qmc, special_ortho_group
 
@@ -122,10 +121,13 @@ class SSPSpace:
         """sspspace.py:317-397.  'from-set' runs entirely on the GPU; 'direct-optim' seeds scipy's
         L-BFGS-B from the GPU from-set answer and evaluates the objective with the GPU encoder."""
         ssp = np.atleast_2d(ssp)
+        if ssp.shape[0] == 0 and method in ('direct-optim', 'from-set'):
+            return np.zeros((0, self.domain_dim))
         if method in ('direct-optim', 'from-set'):
             if samples is None:
-                sample_ssps, sample_points = self.get_sample_pts_and_ssps(method=sampling_method,
-                                                                          num_points_per_dim=num_samples)
+                # the reference's direct-optim seeds itself from a 'length-scale' decoding set (sspspace.py:366-369)
+                sm = 'length-scale' if method == 'direct-optim' else sampling_method
+                sample_ssps, sample_points = self.get_sample_pts_and_ssps(method=sm, num_points_per_dim=num_samples)
             else:
                 sample_ssps, sample_points = samples
                 assert sample_ssps.shape[1] == ssp.shape[1], f'Expected {sample_ssps.shape} dim, got {ssp.shape}'
@@ -133,16 +135,12 @@ class SSPSpace:
             idx = self.engine.from_set_argmax(sample_ssps, ssp).cpu().numpy()
             return np.asarray(sample_points)[idx, :]
         if method == 'direct-optim':
-            unit = ssp / np.maximum(np.linalg.norm(ssp, axis=-1, keepdims=True), 1e-6)
-            out = np.zeros((ssp.shape[0], self.domain_dim))
-            for i, u in enumerate(unit):
-                x0 = self.decode(np.atleast_2d(u), method='from-set', sampling_method='length-scale',
-                                 num_samples=num_samples, samples=samples)
-                target = np.atleast_2d(u)
-                res = minimize(lambda x: -np.inner(self.encode(np.atleast_2d(x)), target).flatten(),
-                               x0.flatten(), method='L-BFGS-B', bounds=self.domain_bounds)
-                out[i, :] = res.x
-            return out
+            # sspspace.py:358-375: from-set start, then maximise phi(x) . unit(ssp) inside the domain bounds.  Both steps
+            # run on the device (sspbo_from_set_argmax, sspbo_decode_optim); the optimiser is an analytic projected Newton
+            # iteration instead of scipy's L-BFGS-B with numerical gradients, on the same objective from the same start.
+            idx = self.engine.from_set_argmax(sample_ssps, ssp).cpu().numpy()
+            x0 = np.asarray(sample_points, dtype=np.float64)[idx, :]
+            return self.engine.decode_optim(ssp, x0, self.domain_bounds).cpu().numpy()
         if method in ('network', 'network-optim'):
             raise NotImplementedError(
                 f"decoding method {method!r} needs the TensorFlow decoder net, which is outside the hot-path scope")

@@ -476,6 +476,42 @@ def test_decode_round_trip_reference_tests(pkg):
     assert np.all(np.isclose(x, hexs.decode(hexs.encode(x), method="direct-optim"), atol=1e-4))
 
 
+def test_decode_direct_optim_device(pkg):
+    """'direct-optim' decode on the device (analytic projected Newton) against the reference's flow restated with
+    scipy's L-BFGS-B (oracle.decode_direct_optim, sspspace.py:358-375) from the same from-set start, and the
+    reference's own round-trip tests (tests/test_ssps.py:75-90: np.isclose at default tolerance)."""
+    b15 = np.array([[-15.0, 15.0], [-15.0, 15.0]])
+    s = 2 * np.pi / np.sqrt(6)
+    x = np.atleast_2d(np.array([1.3, -3.4]))
+    hexs = pkg.HexagonalSSPSpace(2, ssp_dim=151, scale_min=s - 0.5, scale_max=s + 0.5, domain_bounds=b15, length_scale=1)
+    rnd = pkg.RandomSSPSpace(2, ssp_dim=151, domain_bounds=b15, length_scale=1, rng=0)
+    for sp in (hexs, rnd):
+        assert np.all(np.isclose(x, sp.decode(sp.encode(x), method="direct-optim")))          # rtol 1e-5, atol 1e-8
+    # several queries at once, noisy SSPs (not exactly on the manifold), explicit decoding set
+    rng = np.random.default_rng(9)
+    b4 = np.array([[-4.0, 4.0], [-4.0, 4.0], [-4.0, 4.0]])
+    sp3 = pkg.RandomSSPSpace(3, ssp_dim=201, domain_bounds=b4, length_scale=1.5, rng=1)
+    ls = 1.5 * np.ones(3)
+    xs = rng.uniform(-3.5, 3.5, (12, 3))
+    xs[0] = [4.0, -4.0, 3.9]                                                                    # on / next to the box
+    ssps = orc.encode(sp3.phase_matrix, ls, xs) + 0.02 * rng.normal(size=(12, sp3.ssp_dim))
+    samples = sp3.get_sample_pts_and_ssps(12, "grid")
+    got = sp3.decode(ssps, method="direct-optim", samples=samples)
+    x0 = orc.decode_from_set(ssps, samples[0], samples[1])
+    want = orc.decode_direct_optim(sp3.phase_matrix, ls, ssps, x0, bounds=b4)
+    assert got.shape == (12, 3)
+    # same local maximum: L-BFGS-B with numerical gradients stops within ~1e-5 (1e-4 with an active bound) of it, the
+    # Newton iteration lands on it
+    np.testing.assert_allclose(got, want, atol=2e-4)
+    assert np.median(np.abs(got - want)) < 5e-6
+    unit = ssps / np.linalg.norm(ssps, axis=1, keepdims=True)
+    f_got = np.sum(orc.encode(sp3.phase_matrix, ls, got) * unit, axis=1)
+    f_want = np.sum(orc.encode(sp3.phase_matrix, ls, want) * unit, axis=1)
+    assert np.all(f_got >= f_want - 1e-12)                                                      # never a worse optimum
+    assert np.all(got >= b4[:, 0] - 1e-15) and np.all(got <= b4[:, 1] + 1e-15)
+    assert sp3.decode(np.zeros((0, sp3.ssp_dim)), method="direct-optim", samples=samples).shape == (0, 3)
+
+
 # ------------------------------------------------------------------------------------------ trajectory agent
 def test_trajectory_agent_golden(pkg, golden):
     g = golden("traj.npz")
