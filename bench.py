@@ -415,9 +415,28 @@ def encode_only(eng, cand, peaks, n=1 << 16, reps=3):
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) * 1e-3 / reps
     gbs = n * eng.d * 8 / sec / 1e9
-    return {"kernel": "k_encode (float64 phi to HBM)", "candidates": n, "candidates_per_s": n / sec, "hbm_write_gbs": gbs,
-            "hbm_peak_gbs": peaks["hbm"], "frac_of_hbm_peak": gbs / peaks["hbm"],
-            "note": "2 d K float64 FMA per candidate: bound by the FP64 pipe; the fused scorer never materialises phi"}
+    out = {"f64": {"kernel": "k_encode (float64 phi to HBM)", "candidates": n, "candidates_per_s": n / sec,
+                   "hbm_write_gbs": gbs, "hbm_peak_gbs": peaks["hbm"], "frac_of_hbm_peak": gbs / peaks["hbm"],
+                   "note": "2 d K float64 FMA per candidate: bound by the FP64 pipe; the fused scorer never materialises phi"}}
+    n32 = min(cand.shape[0], 1 << 20)
+    x32 = cand[:n32]
+    eng.encode_f32_device(x32)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        eng.encode_f32_device(x32)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    pitch = eng.lib.sspbo_encode_pitch(eng._ctx)
+    gbs = n32 * pitch * 4 / sec / 1e9
+    tf = n32 * 3 * 2.0 * 1024 * pitch / sec / 1e12
+    out["f32_tensor_core"] = {"kernel": "k_score_umma in encode mode (split-fp16 inverse-DFT basis, float32 phi to HBM)",
+                              "candidates": n32, "candidates_per_s": n32 / sec, "hbm_write_gbs": gbs,
+                              "hbm_peak_gbs": peaks["hbm"], "frac_of_hbm_peak": gbs / peaks["hbm"],
+                              "executed_tflops": tf, "frac_of_tensor_peak": tf / peaks["tflops"],
+                              "note": "tensor-pipe-bound: 3 x 2 x 1024 x 1024 executed flops per candidate"}
+    return out
 
 
 def bo_step_c2(pkg, n_iter=30):

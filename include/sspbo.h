@@ -80,6 +80,13 @@ int sspbo_space_set_xbound(sspbo_ctx* ctx, double x_absmax);
  * x_dev: N x (n*L), dtype SSPBO_F32|SSPBO_F64.  phi_out_dev: N x d float64. */
 int sspbo_encode(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, double* phi_out_dev, void* stream);
 
+/* K1 on the tensor cores, float32 result: phi = psi B^T with the split-fp16 inverse-DFT basis as the MMA operand; psi is
+ * generated on chip as in the scorer.  Error ~1e-6 of max |phi| (inside the 1e-4 the path is specified to), ~50x the
+ * rate of the float64 kernel.  phi_out_dev: N x sspbo_encode_pitch(ctx) float32 (row pitch = d rounded up to the MMA
+ * tiling, columns >= d are zero). */
+int sspbo_encode_pitch(sspbo_ctx* ctx);
+int sspbo_encode_f32(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, float* phi_out_dev, void* stream);
+
 /* ---- K3: Bayesian linear regression (blr.py:27-97) --------------------------------
  * State on device, float64: S (d x d), S_inv, b = beta * sum(phi_i t_i), m = S b, plus
  * the psi-space scoring factor R (R^T R = B^T S B) and its split-fp16 image. */

@@ -97,6 +97,30 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
     }
 }
 
+// Split-fp16 image of the inverse-DFT basis in operand order (B operand of the tensor-core encoder):
+//   phi_j = (1/d) psi_0 + (2/d) sum_f [ cos(theta_f) cos(2 pi j f / d) - sin(theta_f) sin(2 pi j f / d) ]
+// row j, column c <-> (block c/64, frequency f = 32 (c/64) + c%32, cos for c%64 < 32, sin otherwise); padding stays zero.
+__global__ void k_build_basis_operand(const double2* __restrict__ twiddle, int K, int KC_pad, double scale,
+                                      __half* __restrict__ Bh, __half* __restrict__ Bl) {
+    const int d = 2 * K + 1;
+    const int j = blockIdx.x;
+    for (int c = threadIdx.x; c < KC_pad; c += blockDim.x) {
+        const int b = c >> 6, i = c & 63, f = 32 * b + (i & 31);
+        double v = 0.0;
+        if (f <= K) {
+            if (f == 0) v = (i < 32) ? 1.0 / d : 0.0;
+            else {
+                const double2 tw = twiddle[(int)(((long long)j * f) % d)];
+                v = (i < 32) ? 2.0 * tw.x / d : -2.0 * tw.y / d;
+            }
+        }
+        v *= scale;
+        const __half h = __double2half(v);
+        Bh[(size_t)j * KC_pad + c] = h;
+        Bl[(size_t)j * KC_pad + c] = __double2half(v - (double)__half2float(h));
+    }
+}
+
 // =====================================================================================
 // basis change phi-space <-> psi-space on d-vectors (float64)
 //   out[0] = s0 * sum_j in[j];  out[k] = sk * sum_j in[j] cos(w_jk);  out[K+k] = -sk * sum_j in[j] sin(w_jk)
@@ -887,7 +911,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
-    dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
+    dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     delete ctx;
 }
 
@@ -902,6 +926,7 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     if (!A_plus || !inv_ls || K < 1 || n < 1 || n > 16) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set: need K>=1, 1<=n<=16");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     if (K != ctx->K || !ctx->has_factor) { free_blr(ctx); sspbo_umma_release(ctx); }
+    if (K != ctx->K) ctx->enc_K = 0;
     const int d = 2 * K + 1;
     std::vector<double> At((size_t)K * n);
     std::vector<float> Af((size_t)K * n);
@@ -1082,6 +1107,43 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
+}
+
+/* SSPSpace.encode on the tensor cores (float32 result): phi = psi B^T with the split-fp16 inverse-DFT basis as the B
+ * operand of the dense tcgen05 kernel; psi is generated on chip exactly as in the scorer.  Accuracy ~1e-6 of max |phi|
+ * (the float64 sspbo_encode gives 1e-13); the kernel is bound by the tensor pipe (3 x 2 x 1024^2 flops per candidate at
+ * d = 1023), phi is written once: 4 * pitch bytes per candidate.  phi_out_dev: N x pitch float32, pitch = sspbo_encode_pitch. */
+extern "C" int sspbo_encode_pitch(sspbo_ctx* ctx) {
+    if (!ctx || ctx->K == 0) return 0;
+    int kc, bn, nc, nj;
+    sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
+    return nj;
+}
+
+extern "C" int sspbo_encode_f32(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* phi_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "encode_f32 before space_set");
+    if (N < 0 || (N > 0 && (!x || !phi_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode_f32: null pointer");
+    if (x_dtype != SSPBO_F32 && x_dtype != SSPBO_F64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode_f32: unknown dtype %d", x_dtype);
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int kc, bn, nc, nj, rc;
+    sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
+    if (ctx->n > 8 || !ctx->umma_range_ok || nc > 8 || (ctx->L != 1 && (ctx->n > 3 || !ctx->tauq_op)))
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "encode_f32: shape outside the tcgen05 kernel (n=%d, d=%d, L=%d)", ctx->n, ctx->d, ctx->L);
+    if (!ctx->blr_ready || !ctx->has_factor) {           // geometry normally set by blr_init
+        ctx->KC_pad = kc; ctx->BN = bn; ctx->n_chunks = nc; ctx->NJ_pad = nj;
+        if (!ctx->mp_op && (rc = dev_alloc(ctx, &ctx->mp_op, (size_t)kc))) return rc;
+    }
+    if (!ctx->Bh_enc || ctx->enc_K != ctx->K) {
+        if ((rc = dev_alloc(ctx, &ctx->Bh_enc, (size_t)nj * kc)) || (rc = dev_alloc(ctx, &ctx->Bl_enc, (size_t)nj * kc))) return rc;
+        ctx->enc_scale = exp2(floor(log2(1024.0 / (2.0 / ctx->d))));
+        k_build_basis_operand<<<ctx->d, 256, 0, st>>>(ctx->twiddle, ctx->K, kc, ctx->enc_scale, ctx->Bh_enc, ctx->Bl_enc);
+        SSPBO_LAUNCH_CHECK(ctx);
+        ctx->enc_K = ctx->K;
+    }
+    return sspbo_encode_umma_launch(ctx, x, x_dtype, N, phi_out, nj, st);
 }
 
 // ------------------------------------------------------------------------------------ BLR

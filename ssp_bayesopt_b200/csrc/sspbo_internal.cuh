@@ -88,6 +88,8 @@ struct sspbo_ctx {
     // scratch d-vectors (float64)
     double *v = nullptr, *psi = nullptr, *y = nullptr, *z = nullptr, *phi_tmp = nullptr;
     double* scal = nullptr;          // a few device scalars
+    // tensor-core encoder: split-fp16 inverse-DFT basis in operand order (NJ_pad x KC_pad), built lazily
+    __half* Bh_enc = nullptr; __half* Bl_enc = nullptr; double enc_scale = 1.0; int enc_K = 0;
     // opaque state of the tcgen05 engines (tensor maps etc.)
     void* umma = nullptr;
     void* lr_state = nullptr;
@@ -175,6 +177,7 @@ int sspbo_score_umma_supported(const sspbo_ctx* ctx);
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam,
                             float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_umma_release(sspbo_ctx* ctx);
+int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st);
 // low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);
 int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,

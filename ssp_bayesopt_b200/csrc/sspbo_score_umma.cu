@@ -65,6 +65,7 @@ struct Params {
     unsigned long long* best;
     int na;                             // A ring slots
     int mu_depth;                       // tiles of mu in flight between generator and epilogue
+    float* enc_out; int enc_pitch; float enc_inv_scale;   // encode mode: the B operand is the inverse-DFT basis, Y = phi is stored
     unsigned long long* stats;          // device counters (out-of-bound candidates of the 32-bit phase path)
     // 32-bit fixed-point phase path
     const int* A32_op; double x_scale;
@@ -222,6 +223,24 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                     for (int l = 0; l < 4; ++l)
                         if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
                     tmem_ld_wait();
+                    if (p.enc_out) {                                      // encode mode: phi row -> HBM (float32, 64 B per load)
+                        const long long ge = tile * BM + row;
+                        if (ge < p.N) {
+                            float* orow = p.enc_out + (size_t)ge * p.enc_pitch + c * p.BN + g;
+#pragma unroll
+                            for (int l = 0; l < 4; ++l)
+                                if (l < nld) {
+#pragma unroll
+                                    for (int i = 0; i < 16; i += 4)
+                                        *reinterpret_cast<float4*>(orow + 16 * l + i) =
+                                            make_float4(__uint_as_float(v[16 * l + i]) * p.enc_inv_scale,
+                                                        __uint_as_float(v[16 * l + i + 1]) * p.enc_inv_scale,
+                                                        __uint_as_float(v[16 * l + i + 2]) * p.enc_inv_scale,
+                                                        __uint_as_float(v[16 * l + i + 3]) * p.enc_inv_scale);
+                                }
+                        }
+                        continue;
+                    }
                     float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
@@ -239,7 +258,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                 mbar_arrive(tmem_empty(buf));
             }
             const long long gi = tile * BM + row;
-            if (gi < p.N) {
+            if (gi < p.N && !p.enc_out) {
                 const float* mpart = mu_part + (tile_iter & (MU_DEPTH - 1)) * 4 * BM;
                 float mu = (mpart[row] + mpart[BM + row]) + (mpart[2 * BM + row] + mpart[3 * BM + row]);
                 float var = p.inv_beta + q * p.inv_rscale2;                           // blr.py:96
@@ -472,7 +491,7 @@ struct MapSet {                           // tensor maps of one operand pair (hi
     int KC_pad = 0, rows = 0, BN = 0;
 };
 struct UmmaState {
-    MapSet full;
+    MapSet full, enc;
     int max_smem = 0;
     bool attr_set[2][2][MAX_N + 1] = {};  // [traj][p32][n]
     unsigned long long* xq = nullptr; size_t xq_cap = 0;      // scratch of the trajectory mode
@@ -552,7 +571,7 @@ int ensure_maps(sspbo_ctx* ctx, MapSet* ms, const void* bh, const void* bl, int 
     return SSPBO_OK;
 }
 
-int launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+int launch(sspbo_ctx* ctx, float* enc_out, int enc_pitch, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
            float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
     UmmaState* us = (UmmaState*)ctx->umma;
     if (!us) { us = new UmmaState(); ctx->umma = us; }
@@ -560,14 +579,21 @@ int launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0
     Params p;
     memset(&p, 0, sizeof(p));
     MapSet* ms;
-    {
-        p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
+    p.BN = ctx->BN; p.n_chunks = ctx->n_chunks;
+    p.stats = ctx->stats;
+    if (enc_out) {                                       // B operand = inverse-DFT basis (dense: every k-block, every row)
+        for (int i = 0; i < 8; ++i) p.kb_start[i] = 0;
+        for (int i = 0; i < 32; ++i) p.nz_rows[i] = 32767;
+        ms = &us->enc;
+        int rc = ensure_maps(ctx, ms, ctx->Bh_enc, ctx->Bl_enc, ctx->KC_pad, ctx->NJ_pad, ctx->BN);
+        if (rc) return rc;
+        p.enc_out = enc_out; p.enc_pitch = enc_pitch; p.enc_inv_scale = (float)(1.0 / ctx->enc_scale);
+    } else {
         for (int i = 0; i < 8; ++i) p.kb_start[i] = ctx->kb_start[i];
         for (int i = 0; i < 32; ++i) p.nz_rows[i] = ctx->nz_rows[i];
         ms = &us->full;
         int rc = ensure_maps(ctx, ms, ctx->Rh, ctx->Rl, ctx->KC_pad, ctx->NJ_pad, ctx->BN);
         if (rc) return rc;
-        p.stats = ctx->stats;
     }
     const size_t tb = table_bytes(ctx), sb = 2 * (size_t)p.BN * BK * 2;
     const size_t avail = (size_t)us->max_smem - 1024 - tb;
@@ -645,5 +671,10 @@ void sspbo_umma_release(sspbo_ctx* ctx) {
 
 int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
                             float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
-    return launch(ctx, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
+    return launch(ctx, nullptr, 0, x, x_dtype, N, index0, lam, gamma_t, mu, var, acq, best, st);
+}
+
+// K1 on the tensor cores: phi = psi B^T with the split-fp16 inverse-DFT basis as the B operand (float32 out, pitch = NJ_pad)
+int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st) {
+    return launch(ctx, out, pitch, x, x_dtype, N, 0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, st);
 }

@@ -136,6 +136,21 @@ class DeviceEngine:
     def encode(self, x) -> np.ndarray:
         return self.encode_device(x).cpu().numpy()
 
+    def encode_f32_device(self, x):
+        """x (N, n*L) -> device tensor phi (N, d) float32 (a view of an (N, pitch) buffer) from the tensor-core encoder."""
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        if xt.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        pitch = self.lib.sspbo_encode_pitch(self._ctx)
+        buf = self.torch.empty((N, pitch), dtype=self.torch.float32, device=self._dev())
+        rc = self.lib.sspbo_encode_f32(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N,
+                                       C.c_void_p(buf.data_ptr()), self._stream())
+        self._check(rc, "sspbo_encode_f32")
+        return buf[:, :self.d]
+
     # ------------------------------------------------------------------ K3
     def blr_init(self, alpha: float, dim: int | None = None) -> None:
         if self.K:

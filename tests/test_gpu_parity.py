@@ -86,6 +86,33 @@ def test_encode_large_random(pkg, golden):
     assert err.max() < 1e-4 and err.max() < 1e-10, err.max()
 
 
+@pytest.mark.parametrize("name,xk,N", [("rand1024", "x6", 5000), ("hex151", "x2", 1000), ("rand51", "x2", 129)])
+def test_encode_tensor_core_f32(pkg, golden, name, xk, N):
+    """encode(x, dtype=float32): phi = psi B^T on the tensor cores (split-fp16 basis), within the 1e-4 the path is
+    specified to (normwise per row) - in fact ~1e-6 - with and without a BLR on the context, float32 / float64 input."""
+    g = golden("encode.npz")
+    A, ls = g[f"{name}_A"], g[f"{name}_ls"]
+    n = A.shape[1]
+    bounds = np.array([[-6.0, 6.0]] * n)
+    sp = space_from(pkg, A, ls, bounds)
+    rng = np.random.default_rng(N)
+    x = rng.uniform(-5, 5, (N, n)) if n == 2 else orc.counter_uniform(4, 0, N, n).astype(np.float64)
+    ref = orc.encode(A, ls, x)
+    for xin in (x, x.astype(np.float32)):
+        phi = sp.encode(xin, dtype=np.float32)
+        assert phi.dtype == np.float32 and phi.shape == ref.shape
+        r = orc.encode(A, ls, xin.astype(np.float64))
+        err = np.max(np.abs(phi - r), axis=1) / np.max(np.abs(r), axis=1)
+        assert err.max() < 1e-4 and err.max() < 2e-5, err.max()
+    np.testing.assert_allclose(np.linalg.norm(phi, axis=1), 1.0, atol=1e-5)
+    assert sp.encode(np.zeros((0, n)), dtype=np.float32).shape == (0, A.shape[0])
+    # the same context keeps scoring correctly afterwards (the encoder shares the kernel and its operand geometry)
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    model.update(sp.encode(x[:8]), np.sin(x[:8].sum(axis=1, keepdims=True)))
+    phi2 = sp.encode(x[:64], dtype=np.float32)
+    assert np.max(np.abs(phi2 - ref[:64])) < 2e-5 * np.max(np.abs(ref[:64]))
+
+
 # ------------------------------------------------------------------------------------------ K3 BLR
 @pytest.mark.parametrize("name", ["hex51", "rand51"])
 def test_blr_golden(pkg, golden, name):
