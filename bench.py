@@ -322,9 +322,9 @@ def run_native(args):
                        "last_winner": {"score": last[0], "index": last[1]}},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"],
-                         # dram__bytes_read+write of one k_score_umma launch (chunk of 4,194,304 candidates) from the
-                         # ncu --set full capture summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
-                         "traffic": (105.3e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
+                         # dram__bytes_read+write of one scorer launch (chunk of 4,194,304 candidates) from the ncu --set full
+                         # captures summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
+                         "traffic": (108.7e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
                          "launch_candidates": min(chunk, n_local),
                          "executed": executed_note(engine_used, info["rank"], d, n_local, kernel_ms, peaks),
                          "note": f"algorithmic (dense form, SURVEY 8d) {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
