@@ -69,7 +69,7 @@ struct Params {
 };
 
 // PH: phase arithmetic of the generator: 0 = Q31.32 x Q31.32 (any range), 1 = 32-bit fixed point (fa + fx = 55),
-// 2 = float32 FMA chain in radians (|theta| <= 16 pi by the declared bounds: rounding < 1e-5 rad)
+// 2 = float32 FMA chain in radians (|theta| <= 32 pi by the declared bounds: rounding < 2e-5 rad)
 // TRAJ: a candidate is a row of L waypoints; psi sums L unit phasors per frequency (agents/ssp_traj_agent.py:145-163 in
 // the Fourier domain) and |phi|^2 = psi^T D psi is no longer 1: the generators accumulate it for the epilogue.
 template <int NDIM, int PH, bool TRAJ>
