@@ -171,6 +171,18 @@ def main():
         timestep_ssps=agt.timestep_ssps, trajs=trajs, tys=tys, xc=xc, phi=agt.encode(xc), mu=mu, var=var,
         acq=acq, beta=np.float64(agt.blr.beta), m=agt.blr.m, S=agt.blr.S, init_pts=agt.init_samples[1],
         decoded=agt.decode(agt.encode(xc[:1])), bounds=bt)
+    # ---- 7. direct-optim decode (sspspace.py:358-375) with an explicit decoding set ----
+    bo = np.array([[-4.0, 4.0], [-4.0, 4.0], [-4.0, 4.0]])
+    spo = sspspace.RandomSSPSpace(3, ssp_dim=201, domain_bounds=bo, length_scale=1.5, rng=1)
+    rngo = np.random.default_rng(9)
+    xo = rngo.uniform(-3.5, 3.5, (8, 3))
+    xo[0] = [4.0, -4.0, 3.9]
+    ssps_o = spo.encode(xo) + 0.02 * rngo.normal(size=(8, spo.ssp_dim))
+    set_ssps, set_pts = spo.get_sample_pts_and_ssps(12, "grid")
+    dec = spo.decode(ssps_o, method="direct-optim", samples=(set_ssps, set_pts))
+    dec0 = spo.decode(ssps_o, method="from-set", samples=(set_ssps, set_pts))
+    np.savez_compressed(os.path.join(OUT, "decode_optim.npz"), A=spo.phase_matrix, ls=np.ravel(spo.length_scale), bounds=bo,
+                        ssps=ssps_o, set_pts=set_pts, x0=dec0, decoded=dec)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

@@ -6,6 +6,8 @@ row); argmax identical wherever the oracle's top-2 relative gap exceeds 1e-4; po
 relative (normwise) after 1,000 updates.  Index / integer results (grid order, from-set decode indices,
 the counter-based generator) are bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -537,6 +539,11 @@ def test_decode_direct_optim_device(pkg):
     assert np.all(f_got >= f_want - 1e-12)                                                      # never a worse optimum
     assert np.all(got >= b4[:, 0] - 1e-15) and np.all(got <= b4[:, 1] + 1e-15)
     assert sp3.decode(np.zeros((0, sp3.ssp_dim)), method="direct-optim", samples=samples).shape == (0, 3)
+    # and against the live reference's own output (tests/golden/decode_optim.npz)
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode_optim.npz"))
+    spg = space_from(pkg, gd["A"], gd["ls"], gd["bounds"])
+    gs = (orc.encode(gd["A"], gd["ls"], gd["set_pts"]), gd["set_pts"])
+    np.testing.assert_allclose(spg.decode(gd["ssps"], method="direct-optim", samples=gs), gd["decoded"], atol=2e-4)
 
 
 # ------------------------------------------------------------------------------------------ trajectory agent

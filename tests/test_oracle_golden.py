@@ -157,3 +157,15 @@ def test_counter_uniform_is_range_consistent():
     assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
     assert np.array_equal(a[400:500], b)
     assert abs(a.mean() - 0.5) < 0.02
+
+
+def test_decode_direct_optim_matches_reference(golden):
+    """oracle.decode_direct_optim (scipy L-BFGS-B on -phi(x).unit(ssp), sspspace.py:358-375) against the live reference's
+    decode(method='direct-optim') on noisy SSPs, one of them with an active bound."""
+    g = golden("decode_optim.npz")
+    from oracle import ssp_oracle as orc
+    set_ssps = orc.encode(g["A"], g["ls"], g["set_pts"])
+    x0 = orc.decode_from_set(g["ssps"], set_ssps, g["set_pts"])
+    assert np.array_equal(x0, g["x0"])
+    got = orc.decode_direct_optim(g["A"], g["ls"], g["ssps"], x0, bounds=g["bounds"])
+    np.testing.assert_allclose(got, g["decoded"], rtol=0, atol=1e-9)
