@@ -298,6 +298,7 @@ def run_native(args):
     info = eng.lowrank_info()
     sweep = rank_sweep(pkg, eng, agt, cand, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
     enc = encode_only(eng, cand, load_peaks()) if (rank == 0 and world == 1 and not args.no_sweep) else None
+    upd = update_cost(agt, sp, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
     c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
     if rank == 0:
         peaks = load_peaks()
@@ -333,6 +334,7 @@ def run_native(args):
                                  f"work, not that the tensor pipe runs above peak; peak {peaks['source']}"},
             "by_rank": sweep,
             "encode_only": enc,
+            "posterior_update": upd,
             "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                               "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
                              if cpu_rate else None),
@@ -437,6 +439,31 @@ def encode_only(eng, cand, peaks, n=1 << 16, reps=3):
                               "executed_tflops": tf, "frac_of_tensor_peak": tf / peaks["tflops"],
                               "note": "tensor-pipe-bound: 3 x 2 x 1024 x 1024 executed flops per candidate"}
     return out
+
+
+def update_cost(agt, sp, orc, reps=20):
+    """One posterior observation: device float64 rank-one update (encode x_t + K3, about 15 launches) against the
+    reference's expression restated in numpy (blr.py:63-75, O(d^3) as written there), same d."""
+    import torch
+    rng = np.random.default_rng(11)
+    xs = rng.uniform(0, 1, (reps, N_DIM))
+    ys = orc.hartmann6(xs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        agt.update(xs[i:i + 1], np.atleast_2d(ys[i]), np.array([0.0]))
+    torch.cuda.synchronize()
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    ref = orc.BLR(sp.ssp_dim, beta=1.0)
+    phis = orc.encode(sp.phase_matrix, LS * np.ones(N_DIM), xs[:3])
+    ref.update(phis[:1], np.atleast_2d(ys[0]))
+    t0 = time.perf_counter()
+    for i in range(1, 3):
+        ref.update(phis[i:i + 1], np.atleast_2d(ys[i]))
+    cpu_ms = (time.perf_counter() - t0) / 2 * 1e3
+    return {"gpu_ms_per_observation": gpu_ms, "cpu_port_ms_per_observation": cpu_ms, "d": int(sp.ssp_dim),
+            "note": "wall clock incl. host calls; the device update is O(d^2) float64 (S, S_inv, psi-space covariance, one "
+                    "operand row), the reference expression O(d^3)"}
 
 
 def bo_step_c2(pkg, n_iter=30):
