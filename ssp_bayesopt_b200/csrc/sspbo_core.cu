@@ -77,7 +77,9 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
         }
         __syncthreads();
         const double inv_d = 1.0 / (double)d;
-        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        // small batches: gridDim.y blocks share a group of candidates, each takes a slice of the output columns
+        const int j0 = (int)((long long)d * blockIdx.y / gridDim.y), j1 = (int)((long long)d * (blockIdx.y + 1) / gridDim.y);
+        for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             double acc[ENC_CPB];
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c) acc[c] = 0.0;
@@ -1096,13 +1098,16 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     size_t smem = (size_t)ENC_CPB * ctx->d * sizeof(double);
     int64_t blocks64 = (N + ENC_CPB - 1) / ENC_CPB;
     int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 8 ? blocks64 : (int64_t)ctx->sm_count * 8);
+    int slices = 1;                                      // a handful of candidates (e.g. x_t of a BO step): spread the columns
+    while (slices < 16 && (int64_t)blocks * slices < ctx->sm_count && ctx->d / (slices * 2) >= 32) slices *= 2;
+    const dim3 grid(blocks, slices);
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<float><<<blocks, ENC_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
+        k_encode<float><<<grid, ENC_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
                                                            ctx->n, ctx->K, ctx->L, phi_out);
     } else if (x_dtype == SSPBO_F64) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<double><<<blocks, ENC_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
+        k_encode<double><<<grid, ENC_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
                                                             ctx->n, ctx->K, ctx->L, phi_out);
     } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
     SSPBO_LAUNCH_CHECK(ctx);
