@@ -379,16 +379,14 @@ constexpr int EXL_THREADS = 512;    // flagged-candidate pass: few groups in fli
 
 template <typename XT>
 __global__ void __launch_bounds__(EX_THREADS)
-k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restrict__ list,
-                const unsigned long long* __restrict__ count_ptr, unsigned int cap, const double* __restrict__ A_turns,
+k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns,
                 const double* __restrict__ tau_turns, int n, int K, int L, const int* __restrict__ inv_perm,
                 const int* __restrict__ perm, const double* __restrict__ Sp, const double* __restrict__ mp, int RB,
                 double* __restrict__ part_q, double* __restrict__ part_mu) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
     __shared__ double red[EX_G][EX_THREADS / 32];
     const int d = 2 * K + 1, nl = n * L;
-    int64_t count = N;
-    if (list) { unsigned long long c = *count_ptr; count = (int64_t)(c < cap ? c : cap); }
+    const int64_t count = N;
     const int rb = blockIdx.y;
     const int row0 = (int)((long long)d * rb / RB), row1 = (int)((long long)d * (rb + 1) / RB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -398,7 +396,7 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const unsigned int* __restr
             const int c = i / (K + 1), f = i - c * (K + 1);
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
-                const int64_t row = list ? (int64_t)list[base + c] : base + c;
+                const int64_t row = base + c;
                 if (f == 0) cs = (double)L;
                 else psi_entry(x + row * nl, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
             }
@@ -533,12 +531,10 @@ __global__ void k_flag_fold(unsigned long long* __restrict__ stats, unsigned int
     stats[SSPBO_STAT_CUR] = 0ull;
 }
 
-__global__ void k_exact_finish(int64_t N, const unsigned int* __restrict__ list, unsigned long long* __restrict__ stats,
-                               unsigned int cap, int RB, const double* __restrict__ part_q, const double* __restrict__ part_mu,
+__global__ void k_exact_finish(int64_t N, int RB, const double* __restrict__ part_q, const double* __restrict__ part_mu,
                                double inv_beta, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                                float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
-    int64_t count = N;
-    if (list) { unsigned long long c = stats[SSPBO_STAT_CUR]; count = (int64_t)(c < cap ? c : cap); }
+    const int64_t count = N;
     unsigned long long my_best = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         double q = 0.0;
@@ -546,7 +542,7 @@ __global__ void k_exact_finish(int64_t N, const unsigned int* __restrict__ list,
         const double mu = part_mu[i];
         const double var = inv_beta + q;                                        // blr.py:96
         const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
-        const int64_t row = list ? (int64_t)list[i] : i;
+        const int64_t row = i;
         if (mu_out) mu_out[row] = (float)mu;
         if (var_out) var_out[row] = (float)var;
         if (acq_out) acq_out[row] = (float)acq;
@@ -558,15 +554,6 @@ __global__ void k_exact_finish(int64_t N, const unsigned int* __restrict__ list,
         if (other > my_best) my_best = other;
     }
     if ((threadIdx.x & 31) == 0 && my_best && best) atomicMax(best, my_best);
-    if (list) {                                          // single CTA in list mode: fold the per-call counter
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long c = stats[SSPBO_STAT_CUR];
-            stats[SSPBO_STAT_FLAGGED] += (c < cap ? c : cap);
-            stats[SSPBO_STAT_SCORED] += (unsigned long long)N;
-            stats[SSPBO_STAT_CUR] = 0ull;
-        }
-    }
 }
 
 // =====================================================================================
@@ -1446,17 +1433,12 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
         SSPBO_LAUNCH_CHECK(ctx);
         return SSPBO_OK;
     }
-    const int64_t max_rows = N;
-    // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs (64 rows each at d = 1023), so that
-    // a handful of candidates (the usual flagged count, or eval(x_t)) spreads over the machine instead of
-    // streaming all of Sp through one SM
-    int RB = EX_RB_MAX;
-    if (!from_flag_list) {
-        const int64_t groups = (N + EX_G - 1) / EX_G;
-        RB = 1;
-        while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;
-    }
-    const size_t need = (size_t)max_rows * (RB + 1);
+    // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs, so that a handful of candidates (eval(x_t))
+    // spreads over the machine instead of streaming all of Sp through one SM
+    const int64_t groups = (N + EX_G - 1) / EX_G;
+    int RB = 1;
+    while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;
+    const size_t need = (size_t)N * (RB + 1);
     if (need > ctx->ex_part_cap) {
         if (ctx->ex_part) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); }
         int rc = dev_alloc(ctx, &ctx->ex_part, need);
@@ -1464,24 +1446,21 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
         ctx->ex_part_cap = need;
     }
     double* part_q = ctx->ex_part;
-    double* part_mu = ctx->ex_part + (size_t)max_rows * RB;
+    double* part_mu = ctx->ex_part + (size_t)N * RB;
     const size_t smem = (size_t)EX_G * d * sizeof(double);
-    const unsigned int* list = from_flag_list ? ctx->flag_idx : nullptr;
-    const unsigned long long* cnt = from_flag_list ? ctx->stats + SSPBO_STAT_CUR : nullptr;
-    int gx = from_flag_list ? ctx->sm_count / 2 : (int)((N + EX_G - 1) / EX_G < 4 * ctx->sm_count ? (N + EX_G - 1) / EX_G : 4 * ctx->sm_count);
+    const int gx = (int)(groups < 4 * ctx->sm_count ? groups : 4 * ctx->sm_count);
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, list, cnt, SSPBO_FLAG_CAP, ctx->A_turns,
+        k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns,
             ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
     } else {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_exact_partial<double><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const double*)x, N, list, cnt, SSPBO_FLAG_CAP, ctx->A_turns,
+        k_exact_partial<double><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns,
             ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
     }
     SSPBO_LAUNCH_CHECK(ctx);
-    const int fb = from_flag_list ? 1 : (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);
-    k_exact_finish<<<fb, from_flag_list ? 1024 : 256, 0, st>>>(N, list, ctx->stats, SSPBO_FLAG_CAP, RB, part_q, part_mu,
-                                                                1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
+    const int fb = (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);
+    k_exact_finish<<<fb, 256, 0, st>>>(N, RB, part_q, part_mu, 1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }
