@@ -877,6 +877,7 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
     ctx->device = device;
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->cc_major, cudaDevAttrComputeCapabilityMajor, device);
     if (cudaMalloc((void**)&ctx->scal, 16 * sizeof(double)) != cudaSuccess) { delete ctx; return SSPBO_ECUDA; }
     *out = ctx;
     return SSPBO_OK;
@@ -1479,7 +1480,7 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
-    const bool lr_ok = umma_ok && sspbo_score_lr_supported(ctx) && N < 0xffffffffLL;
+    const bool lr_ok = sspbo_score_lr_supported(ctx) && N < 0xffffffffLL;     // covers n <= 16, the dense kernel n <= 8
     if (engine == SSPBO_ENGINE_UMMA && !umma_ok)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: tcgen05 engine does not cover d=%d L=%d", ctx->d, ctx->L);
     if (engine == SSPBO_ENGINE_UMMA_LR && !lr_ok)
@@ -1487,9 +1488,9 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
                    "(rank %d, valid %d) and L == 1", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid);
     if (engine == SSPBO_ENGINE_AUTO) {
         if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
-        else if (umma_ok && N >= 1024)                          // low-rank form while it is less tensor work than the
-            engine = (lr_ok && !ctx->lr_disabled && 2 * (ctx->lr_rank + 1) <= ctx->d)   // triangular factor (~0.56 d^2)
-                         ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA;
+        else if (N >= 1024 && lr_ok && !ctx->lr_disabled && 2 * (ctx->lr_rank + 1) <= ctx->d)
+            engine = SSPBO_ENGINE_UMMA_LR;                      // low-rank form while it is less tensor work than the
+        else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;   // triangular factor (~0.56 d^2)
         else engine = SSPBO_ENGINE_SIMT;
     }
     ctx->last_engine = engine;

@@ -11,6 +11,7 @@
 struct sspbo_ctx {
     int device = 0;
     int sm_count = 148;
+    int cc_major = 0;                // compute capability major (the tcgen05 engines need 10)
     mutable char err[512] = {0};
     int64_t launches = 0;
     int last_engine = 0;

@@ -50,7 +50,7 @@ constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
 constexpr int MAX_NB = 8;
 constexpr int NRM_DEPTH = 8;            // tiles in flight between generator and epilogue (power of two)
-constexpr int MAX_N = 8;
+constexpr int MAX_N = 16;
 
 struct Params {
     const void* x; int x_f64; long long N; long long index0;
@@ -607,6 +607,14 @@ kernel_fn kernel_for_n(int n) {
         case 4: return k_score_lr<4, PH, false>; case 5: return k_score_lr<5, PH, false>; case 6: return k_score_lr<6, PH, false>;
         case 7: return k_score_lr<7, PH, false>; case 8: return k_score_lr<8, PH, false>;
     }
+    if constexpr (PH != 1) {                             // 9 .. 16 dimensions: float32 chain or Q31.32 only
+        switch (n) {
+            case 9: return k_score_lr<9, PH, false>; case 10: return k_score_lr<10, PH, false>;
+            case 11: return k_score_lr<11, PH, false>; case 12: return k_score_lr<12, PH, false>;
+            case 13: return k_score_lr<13, PH, false>; case 14: return k_score_lr<14, PH, false>;
+            case 15: return k_score_lr<15, PH, false>; case 16: return k_score_lr<16, PH, false>;
+        }
+    }
     return nullptr;
 }
 template <int PH>
@@ -626,6 +634,7 @@ kernel_fn kernel_for(int n, int ph, bool traj) {
 // ranks this engine covers (beyond them the dense factor of sspbo_score_umma.cu is as fast)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
     if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
+    if (ctx->cc_major != 10 || !ctx->has_factor) return 0;
     return ctx->lr_valid && ctx->lr_rank >= 1 && ctx->lr_rank + 1 <= 2 * (int)ACC_COLS_MAX && ctx->n <= MAX_N &&
            ctx->umma_range_ok && ctx->stats;
 }
@@ -664,7 +673,7 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     int ph = 0;
     const bool traj = ctx->L != 1;
     if (!ctx->p32_disabled) ph = (ctx->pf32_ok && !ctx->pf32_disabled) ? 2 : (ctx->p32_ok ? 1 : 0);
-    if (traj && ph == 1) ph = 0;                         // trajectories: float32 chain or Q31.32
+    if ((traj || ctx->n > 8) && ph == 1) ph = 0;         // trajectories and n > 8: float32 chain or Q31.32
     if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
     if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
     kernel_fn kern = kernel_for(ctx->n, ph, traj);

@@ -367,6 +367,34 @@ def test_score_lowrank_c3(pkg, T, phase32):
     eng.set_policy(phase32=1)
 
 
+def test_score_lowrank_12d(pkg):
+    """Domains with 9..16 dimensions: the low-rank tcgen05 engine covers them (the dense tcgen05 kernel stops at 8)."""
+    from ssp_bayesopt_b200 import _lib
+    n = 12
+    bounds = np.array([[0.0, 1.0]] * n)
+    sp = pkg.RandomSSPSpace(n, ssp_dim=600, domain_bounds=bounds, length_scale=0.5, rng=2)
+    ls = 0.5 * np.ones(n)
+    rng = np.random.default_rng(21)
+    X = rng.uniform(0, 1, (40, n))
+    y = np.sin(X.sum(axis=1, keepdims=True))
+    model = pkg.BayesianLinearRegression(sp.ssp_dim, engine=sp.engine)
+    ref = orc.BLR(sp.ssp_dim)
+    model.update(sp.encode(X), y)
+    ref.update(orc.encode(sp.phase_matrix, ls, X), y)
+    xc = rng.uniform(0, 1, (3000, n)).astype(np.float32)
+    xc[:8] = X[:8].astype(np.float32)
+    phis = orc.encode(sp.phase_matrix, ls, xc.astype(np.float64))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
+    eng = sp.engine
+    for ph in (1, 0):                                   # float32 chain, Q31.32
+        eng.set_policy(phase32=ph)
+        _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True)
+        assert eng.last_engine() == "umma-lowrank"
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        assert eng.best()[1] == int(np.argmax(ref_mu.ravel() + ref_acq))
+
+
 def test_score_lowrank_policy_and_rerun(pkg):
     """(a) candidates outside the declared bound: the 32-bit phase path reports them and the step is recomputed with
     the Q31.32 path; (b) more flagged candidates than the list holds: recomputed with the full factor; the AUTO
