@@ -101,7 +101,8 @@ int sspbo_blr_update(sspbo_ctx* ctx, const double* phis_dev, const double* ts_ho
 /* copies of the posterior (attributes BLR.m (d), BLR.S (d x d), BLR.S_inv (d x d)); any pointer may be NULL */
 int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev, void* stream);
 /* device-to-device adoption of a replicated posterior (multi-GPU broadcast target):
- * S, S_inv, b, m, R as produced by sspbo_blr_export on another ctx with the same space. */
+ * S, S_inv, b, m, the psi-space covariance, m', and the rows of the low-rank form (so the importing ctx keeps scoring
+ * with the low-rank engine), as produced by sspbo_blr_export on another ctx with the same space and alpha. */
 int64_t sspbo_blr_export_size(const sspbo_ctx* ctx);          /* number of float64 in the packed state */
 int sspbo_blr_export(sspbo_ctx* ctx, double* packed_dev, void* stream);
 int sspbo_blr_import(sspbo_ctx* ctx, const double* packed_dev, double beta, void* stream);

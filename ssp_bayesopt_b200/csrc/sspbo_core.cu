@@ -331,6 +331,19 @@ __global__ void k_lr_append(const double* __restrict__ y, const double* __restri
     vh_row[c] = h;
     vl_row[c] = __double2half(v - (double)__half2float(h));
 }
+// rebuilds the split-fp16 operand rows 1 .. rank from the float64 rows of V (after a posterior import)
+__global__ void k_lr_rebuild(const double* __restrict__ Vd, const int* __restrict__ col_of_rank, int d, int KC_pad, double r_scale,
+                             __half* __restrict__ Vh, __half* __restrict__ Vl) {
+    const int j = blockIdx.y;                           // observation
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= d) return;
+    const double v = Vd[(size_t)j * d + kk] * r_scale;
+    const __half h = __double2half(v);
+    const size_t o = (size_t)(j + 1) * KC_pad + col_of_rank[kk];
+    Vh[o] = h;
+    Vl[o] = __double2half(v - (double)__half2float(h));
+}
+
 // m' in operand order (padding columns stay zero), and as row 0 of the low-rank operand images: the tensor core then
 // delivers mu = m' . psi as output column 0.  Row 0 carries its own power-of-two scale (|m'| max -> [512, 1024)),
 // published in *mscale_out for the epilogue.  One block.
@@ -1350,10 +1363,11 @@ extern "C" int sspbo_blr_get(sspbo_ctx* ctx, double* m, double* S, double* Sinv,
     return SSPBO_OK;
 }
 
+// packed posterior: S, S_inv, b, m [, Sp, m', rank (one float64, -1 = low-rank rows not valid), rows of V (SSPBO_LR_MAX x d)]
 extern "C" int64_t sspbo_blr_export_size(const sspbo_ctx* ctx) {
     if (!ctx || !ctx->blr_ready) return 0;
     int64_t d = ctx->d;
-    return ctx->has_factor ? 3 * d * d + 3 * d : 2 * d * d + 2 * d;
+    return ctx->has_factor ? 3 * d * d + 3 * d + 1 + (int64_t)SSPBO_LR_MAX * d : 2 * d * d + 2 * d;
 }
 extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
@@ -1367,6 +1381,13 @@ extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     for (int i = 0; i < (ctx->has_factor ? 6 : 4); ++i) {
         SSPBO_CUDA(ctx, cudaMemcpyAsync(packed + off, src[i], cnt[i] * sizeof(double), cudaMemcpyDeviceToDevice, st));
         off += cnt[i];
+    }
+    if (ctx->has_factor) {
+        ctx->export_rank = ctx->lr_valid ? (double)ctx->lr_rank : -1.0;
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(packed + off, &ctx->export_rank, sizeof(double), cudaMemcpyHostToDevice, st));
+        SSPBO_CUDA(ctx, cudaStreamSynchronize(st));              // export_rank is a host scalar of the ctx
+        off += 1;
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(packed + off, ctx->Vd, (size_t)SSPBO_LR_MAX * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     return SSPBO_OK;
 }
@@ -1385,8 +1406,22 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
     ctx->operands_dirty = true; ctx->factor_dirty = true;
-    ctx->lr_valid = false;                                       // the rows of V do not travel with the packed state
     if (ctx->has_factor) {
+        double rank = -1.0;                                      // the rows of V travel with the packed state
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+        off += 1;
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->Vd, packed + off, (size_t)SSPBO_LR_MAX * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        const size_t img = (size_t)(SSPBO_LR_MAX + 1) * ctx->KC_pad * sizeof(__half);
+        SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->Vh, 0, img, st));
+        SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->Vl, 0, img, st));
+        ctx->lr_valid = rank >= 0.0 && rank <= (double)SSPBO_LR_MAX;
+        ctx->lr_rank = ctx->lr_valid ? (int)rank : 0;
+        if (ctx->lr_valid && ctx->lr_rank > 0) {
+            k_lr_rebuild<<<dim3(((int)d + 255) / 256, ctx->lr_rank), 256, 0, st>>>(ctx->Vd, ctx->col_of_rank, (int)d, ctx->KC_pad,
+                                                                                    ctx->r_scale, ctx->Vh, ctx->Vl);
+            SSPBO_LAUNCH_CHECK(ctx);
+        }
         k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, (int)d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
         SSPBO_LAUNCH_CHECK(ctx);
     }

@@ -68,6 +68,7 @@ struct sspbo_ctx {
     float* mscale = nullptr;         // device scalar: 1 / (power-of-two scale of row 0 = m')
     double* Vd = nullptr;            // float64 rows of V in rank order (SSPBO_LR_MAX x d): exact pass over flagged candidates
     int lr_rank = 0;
+    double export_rank = -1.0;       // staging scalar of sspbo_blr_export
     bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)
     bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead
     bool p32_disabled = false;       // policy: candidates outside the declared |x| bound were seen

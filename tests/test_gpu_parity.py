@@ -398,7 +398,7 @@ def test_score_lowrank_12d(pkg):
 def test_score_lowrank_policy_and_rerun(pkg):
     """(a) candidates outside the declared bound: the 32-bit phase path reports them and the step is recomputed with
     the Q31.32 path; (b) more flagged candidates than the list holds: recomputed with the full factor; the AUTO
-    engine then stays on the full factor; (c) import of a packed posterior invalidates the low-rank rows."""
+    engine then stays on the full factor; (c) a packed posterior (export / import) carries the low-rank rows."""
     from ssp_bayesopt_b200 import _lib
     bounds = np.array([[-2.0, 2.0]] * 2)
     sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=0.7, rng=0)
@@ -435,13 +435,24 @@ def test_score_lowrank_policy_and_rerun(pkg):
     eng.set_policy(lowrank=True)
     eng.score(xc[:4096], 10.0, 0.0)
     assert eng.last_engine() == "umma-lowrank"
-    # (c)
-    eng.blr_import(eng.blr_export(), model.beta)
-    assert not eng.lowrank_info()["valid"]
-    eng.score(xc[:4096], 10.0, 0.0)
-    assert eng.last_engine() == "umma"
-    with pytest.raises(Exception):
-        eng.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    # (c) a packed posterior carries the low-rank rows: a second context adopts it and scores identically
+    eng.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    want_key = int(eng._best.item())
+    sp2 = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=0.7, rng=0)
+    model2 = pkg.BayesianLinearRegression(sp2.ssp_dim, engine=sp2.engine)
+    sp2.engine.blr_import(eng.blr_export(), model.beta)
+    model2.beta = model.beta                             # the host mirror of the adopting side (blr.py:54-59 would re-estimate it)
+    assert sp2.engine.lowrank_info()["valid"] and sp2.engine.lowrank_info()["rank"] == 30
+    sp2.engine.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    assert int(sp2.engine._best.item()) == want_key
+    assert rel(model2.S, model.S) == 0 and rel(model2.m, model.m) == 0
+    # ... and keeps updating it: one more observation on both, same operand row appended
+    x_new = rng.uniform(-2, 2, (1, 2))
+    for m_, s_ in ((model, sp), (model2, sp2)):
+        m_.update(s_.encode(x_new), np.array([[0.3]]))
+    eng.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    sp2.engine.score(xc[:4096], 10.0, 0.0, engine=_lib.ENGINE_UMMA_LR)
+    assert int(sp2.engine._best.item()) == int(eng._best.item()) and sp2.engine.lowrank_info()["rank"] == 31
 
 
 def test_score_host_streaming_matches_resident(pkg, golden):
