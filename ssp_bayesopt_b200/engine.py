@@ -266,7 +266,7 @@ class DeviceEngine:
             self._lr_used = True
             if self._needs_rerun():
                 self._replay()
-        host = out[:, :N].double().cpu().numpy()
+        host = out[:, :N].cpu().numpy().astype(np.float64)           # one D2H; the widening happens on the host
         return host[0], host[1], host[2]
 
     def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 20, reset_best=True):
