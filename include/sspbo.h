@@ -156,6 +156,17 @@ int sspbo_from_set_argmax(sspbo_ctx* ctx, const double* sample_ssps_dev, int64_t
 int sspbo_decode_optim(sspbo_ctx* ctx, const double* queries_dev, int q, const double* x0_dev, const double* bounds_host,
                        double* x_out_dev, void* stream);
 
+/* ---- K6: phi-space acquisition ascent (agents/ssp_agent.py:156-185, bayesian_optimization.py:249-287) ----------
+ * Maximises g(phi) = m.phi + lam sqrt(gamma_t + 1/beta + phi^T S phi) - sqrt(gamma_t) over the ball |phi| <= margin (the
+ * reference clamps at margin = 4) from R starting points at once.  The reference runs scipy's L-BFGS-B per restart; here
+ * every restart follows the monotone fixed-point step phi <- margin grad g / |grad g| (g is convex, so no step size is
+ * needed and g never decreases) in one cooperative kernel, float64.  A restart stops when its last step moved it by at
+ * most tol * margin, or after max_iter steps.  phi0_dev, phi_out_dev: R x d float64 (starting points outside the ball are
+ * clamped first, like the reference's objective does); val_out_dev: R acquisition values at phi_out; iters_out_dev
+ * (nullable): R step counts.  Works on any context with a posterior (SSP space or sspbo_blr_init_dim). */
+int sspbo_acq_ascent(sspbo_ctx* ctx, const double* phi0_dev, int R, double lam, double gamma_t, double margin, int max_iter,
+                     double tol, double* phi_out_dev, double* val_out_dev, int* iters_out_dev, void* stream);
+
 /* ---- K5: binding (sspspace.py:551-560) ------------------------------------------------
  * Circular convolution out[r] = a[ra] (*) b[rb] over the last axis, float64, evaluated directly in the time
  * domain (the reference goes through fft/ifft; results agree to ~1e-15).  a_dev: qa x d, b_dev: qb x d with

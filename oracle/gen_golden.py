@@ -38,10 +38,46 @@ def himmelblau(x):
              + x[:, 0] + x[:, 1]) / 100
 
 
+def gen_acq_ascent(sspspace, agents):
+    """8. phi-space acquisition search: `acquisition_func` (ssp_agent.py:156-185) and the L-BFGS-B restarts of
+    bayesian_optimization.py:270-280 from `initial_guess()` draws, on an MI agent after 20 sequential updates."""
+    from scipy.optimize import minimize
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    xs = np.random.default_rng(21).uniform(b2[:, 0], b2[:, 1], size=(30, 2))
+    ys = himmelblau(xs).reshape(-1, 1)
+    with quiet:
+        sp = sspspace.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=b2, length_scale=1.0)
+        agt = agents.SSPAgent(xs[:10], ys[:10], sp, decoder_method="from-set", length_scale=1.0)
+        for i in range(10, 30):
+            _, var_t, _ = agt.eval(xs[i:i + 1])
+            agt.update(xs[i:i + 1], ys[i:i + 1], var_t, step_num=i)
+    min_func, gradient = agt.acquisition_func()
+    np.random.seed(3)
+    phi0 = np.stack([agt.initial_guess().flatten() for _ in range(5)])
+    probe = np.random.default_rng(22).normal(size=(4, sp.ssp_dim)) * np.array([[0.05], [0.2], [0.5], [2.0]])
+    sol_x, sol_fun, sol_nit, dec = [], [], [], []
+    for p0 in phi0:
+        soln = minimize(min_func, p0, jac=gradient, method="L-BFGS-B")
+        sol_x.append(soln.x); sol_fun.append(float(np.ravel(soln.fun)[0])); sol_nit.append(soln.nit)
+        dec.append(np.ravel(agt.decode(np.copy(np.atleast_2d(soln.x)))))
+    np.savez_compressed(
+        os.path.join(OUT, "acq_ascent.npz"), A=sp.phase_matrix, ls=np.ravel(sp.length_scale), bounds=b2, xs=xs, ys=ys,
+        m=agt.blr.m, S=agt.blr.S, beta=np.float64(np.ravel(agt.blr.beta)[0]), var_weight=np.float64(agt.var_weight),
+        gamma_t=np.float64(np.ravel(agt.gamma_t)[0]), phi0=phi0, probe=probe,
+        probe_f=np.array([np.ravel(min_func(p))[0] for p in probe]), probe_g=np.stack([gradient(p) for p in probe]),
+        phi0_f=np.array([np.ravel(min_func(p))[0] for p in phi0]),
+        lbfgs_x=np.stack(sol_x), lbfgs_fun=np.array(sol_fun), lbfgs_nit=np.array(sol_nit), lbfgs_decoded=np.stack(dec),
+        init_pts=agt.init_samples[1])
+
+
 def main():
     sspspace, blr, agents = import_reference()
     os.makedirs(OUT, exist_ok=True)
     quiet = contextlib.redirect_stdout(io.StringIO())
+    if "--only-acq-ascent" in sys.argv[1:]:
+        gen_acq_ascent(sspspace, agents)
+        return
 
     # ---- 1. phase matrices + encode, the spaces of the reference's own tests ----
     b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
@@ -183,6 +219,7 @@ def main():
     dec0 = spo.decode(ssps_o, method="from-set", samples=(set_ssps, set_pts))
     np.savez_compressed(os.path.join(OUT, "decode_optim.npz"), A=spo.phase_matrix, ls=np.ravel(spo.length_scale), bounds=bo,
                         ssps=ssps_o, set_pts=set_pts, x0=dec0, decoded=dec)
+    gen_acq_ascent(sspspace, agents)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

@@ -205,6 +205,43 @@ def decode_direct_optim(phase_matrix, length_scale, ssp, x0, bounds=None) -> np.
     return out
 
 
+def acquisition_func(m, S, beta, var_weight, gamma_t, margin=4):
+    """(min_func, gradient) over phi-space.  Ref: ssp_agent.py:156-185 -- phi is pulled back to norm `margin` when it is
+    longer; min_func = -(phi.m + var_weight sqrt(gamma_t + 1/beta + phi^T S phi) - sqrt(gamma_t));
+    gradient = -(m + var_weight S phi / sqrt(phi^T S phi + gamma_t + 1/beta)) at the clamped point."""
+    m = np.asarray(m, dtype=np.float64).reshape(-1, 1)
+    beta_inv = 1.0 / float(np.ravel(beta)[0])
+
+    def _clamp(phi):
+        nrm = np.linalg.norm(phi)
+        return margin * phi / nrm if nrm > margin else phi
+
+    def min_func(phi):
+        phi = _clamp(phi)
+        val = phi.T @ m
+        mi = var_weight * np.sqrt(gamma_t + beta_inv + phi.T @ S @ phi) - np.sqrt(gamma_t)
+        return -(val + mi).flatten()
+
+    def gradient(phi):
+        phi = _clamp(phi)
+        s_phi = S @ phi
+        scale = np.sqrt(phi.T @ s_phi + gamma_t + beta_inv)
+        return -(m.flatten() + var_weight * s_phi / scale)
+
+    return min_func, gradient
+
+
+def maximize_acquisition_lbfgs(min_func, gradient, phi_inits):
+    """One scipy L-BFGS-B run per starting point.  Ref: bayesian_optimization.py:270-287 (`minimize(optim_func,
+    phi_init.flatten(), jac=jac_func, method='L-BFGS-B')`, vals = -soln.fun).  Returns (phis (R, d), vals (R,), nit (R,))."""
+    from scipy.optimize import minimize
+    xs, vals, nit = [], [], []
+    for p0 in np.atleast_2d(phi_inits):
+        soln = minimize(min_func, np.asarray(p0, dtype=np.float64).flatten(), jac=gradient, method='L-BFGS-B')
+        xs.append(soln.x); vals.append(-float(np.ravel(soln.fun)[0])); nit.append(soln.nit)
+    return np.stack(xs), np.array(vals), np.array(nit)
+
+
 def agent_eval(phis, blr: BLR, var_weight, gamma_t):
     """(mu, var, acq) with acq = var_weight (sqrt(var+gamma_t) - sqrt(gamma_t)).
     Ref: ssp_agent.py:133-137."""

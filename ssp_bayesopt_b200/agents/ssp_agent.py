@@ -126,6 +126,23 @@ class SSPAgent(Agent):
 
         return min_func, gradient
 
+    def maximize_acquisition(self, phi_init=None, num_restarts=5, rng=None, max_iter=200, tol=1e-7, margin=4.0):
+        """Device version of the reference's multi-restart phi-space search (bayesian_optimization.py:249-287 over
+        `acquisition_func`): every restart climbs the same objective with the monotone fixed-point step of
+        sspbo_acq_ascent.  phi_init (R, ssp_dim) are the starting points; by default `num_restarts` points drawn
+        uniformly from the domain and encoded on the device (the reference draws from `blr.sample()`, an O(d^3) SVD on
+        the host).  Returns (phi (R, ssp_dim), values (R,)) as numpy float64; values are -min_func(phi)."""
+        eng = self._scoring_engine()
+        if phi_init is None:
+            rng = np.random.default_rng(rng)
+            phi_init = self._encode_device(self._random_inputs(int(num_restarts), rng))
+        phi, val, _ = eng.acq_ascent(phi_init, self.var_weight, self._gamma(), margin=margin, max_iter=max_iter, tol=tol)
+        return phi.cpu().numpy(), val.cpu().numpy()
+
+    def _random_inputs(self, count, rng):
+        b = np.asarray(self.ssp_space.domain_bounds, dtype=np.float64)
+        return rng.uniform(b[:, 0], b[:, 1], size=(count, b.shape[0]))
+
     def update(self, x_t: np.ndarray, y_t: np.ndarray, sigma_t: float, step_num=0):
         x_val, y_val = x_t, y_t
         if len(x_t.shape) < 2:

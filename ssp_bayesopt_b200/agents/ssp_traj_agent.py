@@ -82,6 +82,10 @@ class SSPTrajectoryAgent(SSPAgent):
         x = np.atleast_2d(x)
         return self._traj_engine.encode(x.reshape(x.shape[0], self.traj_len * self.x_dim))
 
+    def _random_inputs(self, count, rng):
+        b = np.tile(np.asarray(self.domain_bounds, dtype=np.float64), (self.traj_len, 1))
+        return rng.uniform(b[:, 0], b[:, 1], size=(count, b.shape[0]))
+
     def decode(self, ssp):
         queries = self.ssp_x_space.bind(self.ssp_t_space.invert(self.timestep_ssps), ssp)
         decoded = self.ssp_x_space.decode(queries, method=self.decoder_method, samples=self.init_samples)

@@ -14,6 +14,11 @@ are accepted and ignored.  Candidate sets (extra kwargs, all optional):
     n_candidates        size of the 'uniform' set (counter-based uniform in bounds, float32)
     candidate_seed      seed of the 'uniform' set
     candidate_chunk     candidates per kernel launch (default 1<<22)
+    acq_optimizer       'candidates' (default) | 'phi-ascent': the reference's own route (:249-287) on the device --
+                        `num_restarts` phi-space climbs of `acquisition_func`'s objective per step
+                        (`SSPAgent.maximize_acquisition`), the best one decoded with the agent's decoder.  Starting
+                        points come from `np.random.default_rng(random_state)`; every rank computes the same step.
+    ascent_iters, ascent_tol   step cap (default 200) and stopping tolerance (default 1e-7) of 'phi-ascent'
 Supported agent types: 'ssp-hex', 'ssp-rand', 'ssp-custom' (with ssp_space=...), 'ssp-traj'.  Under
 torch.distributed (one process per GPU) the candidate index range is sharded across ranks.
 """
@@ -27,7 +32,8 @@ import numpy as np
 
 from . import agents, dist, sspspace
 
-_BO_KW = ('acq_candidates', 'candidates_per_dim', 'n_candidates', 'candidate_seed', 'candidate_chunk')
+_BO_KW = ('acq_candidates', 'candidates_per_dim', 'n_candidates', 'candidate_seed', 'candidate_chunk',
+          'acq_optimizer', 'ascent_iters', 'ascent_tol')
 
 
 class BayesianOptimization:
@@ -39,6 +45,7 @@ class BayesianOptimization:
         assert bounds.shape[1] == 2, 'bounds must have shape (n_dims, 2)'
         if random_state is not None:
             np.random.seed(random_state)
+        self.random_state = random_state
         if hasattr(f, '__code__') and f.__code__.co_argcount == 1:
             self.target = lambda x, info=None: f(x)
         else:
@@ -182,8 +189,14 @@ class BayesianOptimization:
 
         agt, init_xs, init_ys = self.initialize_agent(init_points, agent_type, domain_bounds=self.bounds, **kwargs)
         self.agt = agt
-        cand = self._build_candidates(agt, acq_candidates, bo_kw.get('candidates_per_dim'),
-                                      bo_kw.get('n_candidates'), int(bo_kw.get('candidate_seed', 0)))
+        optimizer = bo_kw.get('acq_optimizer', 'candidates')
+        if optimizer not in ('candidates', 'phi-ascent'):
+            raise ValueError(f'unknown acq_optimizer={optimizer!r}')
+        cand = None
+        if optimizer == 'candidates':
+            cand = self._build_candidates(agt, acq_candidates, bo_kw.get('candidates_per_dim'),
+                                          bo_kw.get('n_candidates'), int(bo_kw.get('candidate_seed', 0)))
+        ascent_rng = np.random.default_rng(self.random_state)
 
         n0 = init_xs.shape[0]
         self.times = np.zeros((n_iter,))
@@ -200,7 +213,15 @@ class BayesianOptimization:
         full_start = time.perf_counter_ns()
         for t in range(n_iter):
             start = time.perf_counter_ns()
-            score, gidx, x_t = self._select(agt, cand, chunk)        # synchronises on the 8-byte key
+            if optimizer == 'candidates':
+                score, gidx, x_t = self._select(agt, cand, chunk)    # synchronises on the 8-byte key
+            else:
+                phis, vals = agt.maximize_acquisition(num_restarts=num_restarts, rng=ascent_rng,
+                                                      max_iter=int(bo_kw.get('ascent_iters', 200)),
+                                                      tol=float(bo_kw.get('ascent_tol', 1e-7)))
+                gidx = int(np.argmax(vals))                          # all restarts (not the reference's vals[:(t+1)] slice)
+                score = vals[gidx]
+                x_t = np.asarray(agt.decode(phis[gidx:gidx + 1]), dtype=np.float64).reshape(1, -1)
             self.times[t] = time.perf_counter_ns() - start
             self.acq_values[t], self.acq_indices[t] = score, gidx
 

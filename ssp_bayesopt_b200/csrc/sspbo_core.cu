@@ -915,6 +915,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
     dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
+    dev_free(&ctx->aa_work);
     delete ctx;
 }
 

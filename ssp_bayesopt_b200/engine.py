@@ -410,6 +410,25 @@ class DeviceEngine:
         self._check(rc, "sspbo_decode_optim")
         return out
 
+    # ------------------------------------------------------------------ K6
+    def acq_ascent(self, phi0, lam, gamma_t, margin=4.0, max_iter=200, tol=1e-7):
+        """Maximise the acquisition in phi-space from the rows of phi0 (R, d), all restarts in one cooperative kernel.
+        Returns device tensors (phi (R, d) float64, values (R,) float64, steps (R,) int32)."""
+        torch = self.torch
+        pt = self.to_device(phi0, torch.float64)
+        if pt.dim() == 1:
+            pt = pt.reshape(1, -1)
+        assert pt.shape[1] == self.d, f"Expected {self.d}-d starting points, got {tuple(pt.shape)}"
+        R = pt.shape[0]
+        out = torch.empty_like(pt)
+        val = torch.empty(R, dtype=torch.float64, device=self._dev())
+        its = torch.empty(R, dtype=torch.int32, device=self._dev())
+        rc = self.lib.sspbo_acq_ascent(self._ctx, C.c_void_p(pt.data_ptr()), R, float(lam), float(gamma_t), float(margin),
+                                       int(max_iter), float(tol), C.c_void_p(out.data_ptr()), C.c_void_p(val.data_ptr()),
+                                       C.c_void_p(its.data_ptr()), self._stream())
+        self._check(rc, "sspbo_acq_ascent")
+        return out, val, its
+
     # ------------------------------------------------------------------ K5
     def bind(self, a, b):
         """Circular convolution of the rows of a (qa, d) and b (qb, d) with numpy broadcasting over rows."""

@@ -658,6 +658,115 @@ def test_grid_row_lookup_matches_device_grid(pkg):
             assert np.array_equal(cand['lookup'](i), dev[i]), (n, i)
 
 
+def _ascent_numpy(m, S, beta, lam, gamma, phi0, margin, max_iter, tol):
+    """float64 numpy statement of the iteration sspbo_acq_ascent runs (phi <- margin grad / |grad|), per restart."""
+    m = np.ravel(m)
+    c = gamma + 1.0 / beta
+    out, vals, its = [], [], []
+    for phi in np.atleast_2d(phi0).astype(np.float64):
+        nrm = np.linalg.norm(phi)
+        phi = margin * phi / nrm if nrm > margin else phi.copy()
+        moved, k = np.inf, 0
+        while True:
+            y = S @ phi
+            s = np.sqrt(c + phi @ y)
+            val = m @ phi + lam * s - np.sqrt(gamma)
+            if moved <= tol * margin or k == max_iter:
+                break
+            g = m + (lam / s) * y
+            new = margin * g / np.linalg.norm(g)
+            moved, phi, k = np.linalg.norm(new - phi), new, k + 1
+        out.append(phi); vals.append(val); its.append(k)
+    return np.stack(out), np.array(vals), np.array(its)
+
+
+def test_acq_ascent_device(pkg, golden):
+    """K6: phi-space acquisition search on the device against the reference's route
+    (oracle.acquisition_func = ssp_agent.py:156-185, L-BFGS-B restarts = bayesian_optimization.py:270-287, pinned by
+    tests/golden/acq_ascent.npz from the live reference)."""
+    g = golden("acq_ascent.npz")
+    sp = space_from(pkg, g["A"], g["ls"], g["bounds"])
+    agt = pkg.SSPAgent(g["xs"][:10], g["ys"][:10], sp, decoder_method="from-set", length_scale=1.0)
+    for i in range(10, 30):
+        _, var_t, _ = agt.eval(g["xs"][i:i + 1])
+        agt.update(g["xs"][i:i + 1], g["ys"][i:i + 1], var_t, step_num=i)
+    lam, gamma = float(agt.var_weight), agt._gamma()
+    assert lam == float(g["var_weight"]) and abs(gamma - float(g["gamma_t"])) <= 1e-4 * float(g["gamma_t"])
+    m, S, beta = agt.blr.m, agt.blr.S, float(np.ravel(agt.blr.beta)[0])
+    assert rel(m, g["m"]) < 1e-7 and rel(S, g["S"]) < 1e-7
+    f_dev, _ = orc.acquisition_func(m, S, beta, lam, gamma)          # the reference's objective on the device's own posterior
+    eng = agt._scoring_engine()
+
+    # (1) from the reference's own starting points: same objective value at the returned phi, never below the reference's
+    #     L-BFGS-B result (which stops at the clamped start), and the iterates of the float64 numpy statement
+    for max_iter, tol in ((0, 0.0), (25, 0.0), (400, 1e-9)):
+        phi, val, its = (t.cpu().numpy() for t in eng.acq_ascent(g["phi0"], lam, gamma, max_iter=max_iter, tol=tol))
+        want_phi, want_val, want_its = _ascent_numpy(m, S, beta, lam, gamma, g["phi0"], 4.0, max_iter, tol)
+        assert phi.shape == g["phi0"].shape and val.shape == (5,)
+        np.testing.assert_allclose(val, [-np.ravel(f_dev(p))[0] for p in phi], rtol=1e-12)
+        np.testing.assert_allclose(val, want_val, rtol=1e-10)
+        np.testing.assert_allclose(phi, want_phi, atol=1e-7 * 4.0)
+        assert np.all(np.linalg.norm(phi, axis=1) <= 4.0 * (1 + 1e-12))
+        if max_iter == 0:
+            np.testing.assert_allclose(val, -g["lbfgs_fun"], rtol=1e-6)     # the reference's result: the clamped start
+            assert np.all(its == 0)
+        else:
+            assert np.all(val >= -g["lbfgs_fun"] * (1 - 1e-9))
+        if tol > 0:
+            assert np.all(np.abs(its - want_its) <= 2) and np.all(its < max_iter)
+    # (2) stationarity of the converged points: phi* = 4 grad / |grad| with the reference's gradient
+    _, grad = orc.acquisition_func(m, S, beta, lam, gamma)
+    for p in phi:
+        gr = -grad(p)
+        np.testing.assert_allclose(p, 4.0 * gr / np.linalg.norm(gr), atol=1e-7)
+    # (3) monotone: more steps never lower the value
+    vals = [eng.acq_ascent(g["phi0"], lam, gamma, max_iter=k, tol=0.0)[1].cpu().numpy() for k in (0, 1, 2, 5, 10, 50)]
+    assert np.all(np.diff(np.stack(vals), axis=0) >= -1e-9 * np.abs(vals[0]))
+    # (4) more restarts than one tile, starting points inside the ball, a single 1-D start
+    rng = np.random.default_rng(5)
+    p0 = rng.normal(size=(19, sp.ssp_dim)) * rng.uniform(0.01, 1.0, size=(19, 1))
+    phi, val, its = (t.cpu().numpy() for t in eng.acq_ascent(p0, lam, gamma, max_iter=60, tol=0.0))
+    want_phi, want_val, _ = _ascent_numpy(m, S, beta, lam, gamma, p0, 4.0, 60, 0.0)
+    np.testing.assert_allclose(val, want_val, rtol=1e-10)
+    np.testing.assert_allclose(phi, want_phi, atol=4e-7)
+    one = eng.acq_ascent(p0[3], lam, gamma, max_iter=60, tol=0.0)
+    np.testing.assert_array_equal(one[0].cpu().numpy()[0], phi[3])
+    # (5) agent / driver surface
+    phis, vals = agt.maximize_acquisition(num_restarts=5, rng=0)
+    assert phis.shape == (5, sp.ssp_dim) and vals.shape == (5,)
+    assert np.all(vals >= -g["lbfgs_fun"].max() - 1e-6)
+    x_star = agt.decode(phis[np.argmax(vals):np.argmax(vals) + 1])
+    assert x_star.shape == (1, 2) and np.all(np.abs(x_star) <= 5)
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    f = lambda x: himmelblau(np.atleast_2d(x))
+    runs = []
+    for _ in range(2):
+        opt = pkg.BayesianOptimization(f=f, bounds=bounds, random_state=4)
+        opt.maximize(init_points=(g["xs"][:10], g["ys"][:10]), n_iter=4, num_restarts=3, agent_type="ssp-hex", ssp_dim=151,
+                     length_scale=1.0, decoder_method="from-set", acq_optimizer="phi-ascent")
+        assert opt.xs.shape == (14, 2) and np.all(np.abs(opt.xs) <= 5)
+        runs.append(opt.xs.copy())
+    assert np.array_equal(runs[0], runs[1])                               # seeded starts, deterministic kernel
+
+
+def test_acq_ascent_raw_feature_posterior(pkg):
+    """The ascent only needs (m, S, beta): a posterior over raw features (sspbo_blr_init_dim), d not a multiple of the
+    warp size, rank-deficient data."""
+    rng = np.random.default_rng(2)
+    d = 77
+    model = pkg.BayesianLinearRegression(d)
+    X = rng.normal(size=(12, d)) / np.sqrt(d)
+    model.update(X, (X[:, :3].sum(axis=1, keepdims=True)))
+    m, S, beta = model.m, model.S, float(np.ravel(model.beta)[0])
+    p0 = rng.normal(size=(3, d))
+    phi, val, its = (t.cpu().numpy() for t in model.engine.acq_ascent(p0, 2.5, 0.3, margin=1.5, max_iter=300, tol=1e-10))
+    want_phi, want_val, want_its = _ascent_numpy(m, S, beta, 2.5, 0.3, p0, 1.5, 300, 1e-10)
+    np.testing.assert_allclose(val, want_val, rtol=1e-10)
+    np.testing.assert_allclose(phi, want_phi, atol=1e-7)
+    f, _ = orc.acquisition_func(m, S, beta, 2.5, 0.3, margin=1.5)
+    np.testing.assert_allclose(val, [-np.ravel(f(p))[0] for p in phi], rtol=1e-12)
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])

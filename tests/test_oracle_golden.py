@@ -169,3 +169,23 @@ def test_decode_direct_optim_matches_reference(golden):
     assert np.array_equal(x0, g["x0"])
     got = orc.decode_direct_optim(g["A"], g["ls"], g["ssps"], x0, bounds=g["bounds"])
     np.testing.assert_allclose(got, g["decoded"], rtol=0, atol=1e-6)   # finite-difference gradients amplify 1e-16 in phi
+
+
+def test_acquisition_func_and_lbfgs_route_match_reference(golden):
+    """oracle.acquisition_func against the live reference's SSPAgent.acquisition_func (ssp_agent.py:156-185) at probe
+    points inside and outside the clamp radius, and the L-BFGS-B restart loop of bayesian_optimization.py:270-287 from the
+    reference's own `initial_guess()` draws (which sit far outside the ball, so the reference stops after 0 steps)."""
+    g = golden("acq_ascent.npz")
+    from oracle import ssp_oracle as orc
+    f, grad = orc.acquisition_func(g["m"], g["S"], g["beta"], float(g["var_weight"]), float(g["gamma_t"]))
+    for p, pf, pg in zip(g["probe"], g["probe_f"], g["probe_g"]):
+        np.testing.assert_allclose(np.ravel(f(p))[0], pf, rtol=1e-12)
+        np.testing.assert_allclose(grad(p), pg, rtol=1e-12, atol=1e-12)
+    for p, pf in zip(g["phi0"], g["phi0_f"]):
+        np.testing.assert_allclose(np.ravel(f(p))[0], pf, rtol=1e-12)
+    xs, vals, nit = orc.maximize_acquisition_lbfgs(f, grad, g["phi0"])
+    np.testing.assert_allclose(vals, -g["lbfgs_fun"], rtol=1e-9)
+    np.testing.assert_array_equal(nit, g["lbfgs_nit"])
+    np.testing.assert_allclose(xs, g["lbfgs_x"], rtol=1e-9, atol=1e-9)
+    set_ssps = orc.encode(g["A"], g["ls"], g["init_pts"])
+    np.testing.assert_array_equal(orc.decode_from_set(xs, set_ssps, g["init_pts"]), g["lbfgs_decoded"])
