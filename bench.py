@@ -299,6 +299,7 @@ def run_native(args):
     sweep = rank_sweep(pkg, eng, agt, cand, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
     enc = encode_only(eng, cand, load_peaks()) if (rank == 0 and world == 1 and not args.no_sweep) else None
     upd = update_cost(agt, sp, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
+    asc = acq_ascent_cost(agt, sp, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
     c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
     if rank == 0:
         peaks = load_peaks()
@@ -335,6 +336,7 @@ def run_native(args):
             "by_rank": sweep,
             "encode_only": enc,
             "posterior_update": upd,
+            "acq_ascent": asc,
             "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                               "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
                              if cpu_rate else None),
@@ -464,6 +466,43 @@ def update_cost(agt, sp, orc, reps=20):
     return {"gpu_ms_per_observation": gpu_ms, "cpu_port_ms_per_observation": cpu_ms, "d": int(sp.ssp_dim),
             "note": "wall clock incl. host calls; the device update is O(d^2) float64 (S, S_inv, psi-space covariance, one "
                     "operand row), the reference expression O(d^3)"}
+
+
+def acq_ascent_cost(agt, sp, orc, restarts=8, steps=100, reps=5):
+    """K6: phi-space acquisition search at the C3 posterior.  Device: `restarts` climbs of `steps`
+    fixed-point steps in one cooperative launch (CUDA events).  CPU: the reference's route restated in the oracle --
+    scipy L-BFGS-B on `acquisition_func` (ssp_agent.py:156-185, bayesian_optimization.py:270-287) per restart, from the
+    same starting points (inside the ball, so L-BFGS-B does iterate)."""
+    import torch
+    eng = agt._scoring_engine()
+    d = int(sp.ssp_dim)
+    rng = np.random.default_rng(12)
+    phi0 = orc.encode(sp.phase_matrix, LS * np.ones(N_DIM), rng.uniform(0, 1, (restarts, N_DIM)))
+    lam, gamma = float(agt.var_weight), agt._gamma()
+    p0 = eng.to_device(phi0, torch.float64)
+    eng.acq_ascent(p0, lam, gamma, max_iter=steps, tol=0.0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        _, val, _ = eng.acq_ascent(p0, lam, gamma, max_iter=steps, tol=0.0)
+    ev[1].record()
+    torch.cuda.synchronize()
+    gpu_ms = ev[0].elapsed_time(ev[1]) / reps
+    _, val_c, its_c = eng.acq_ascent(p0, lam, gamma, max_iter=2000, tol=1e-7)
+    m, S, beta = agt.blr.m, agt.blr.S, float(np.ravel(agt.blr.beta)[0])
+    f, g = orc.acquisition_func(m, S, beta, lam, gamma)
+    t0 = time.perf_counter()
+    _, vals_ref, nit = orc.maximize_acquisition_lbfgs(f, g, phi0[:2])
+    cpu_ms = (time.perf_counter() - t0) / 2 * 1e3
+    return {"d": d, "restarts": restarts, "steps": steps, "gpu_ms_per_call": gpu_ms, "gpu_us_per_step": gpu_ms * 1e3 / steps,
+            "S_bytes_per_step": 8 * d * d, "S_GBps": 8 * d * d * steps / (gpu_ms * 1e-3) / 1e9,
+            "f64_gflops": 2.0 * d * d * restarts * steps / (gpu_ms * 1e-3) / 1e9,
+            "value_after_steps": float(val.max().item()), "value_converged": float(val_c.max().item()),
+            "steps_to_converge_tol1e-7": [int(v) for v in its_c.cpu()],
+            "cpu_port_ms_per_restart": cpu_ms, "cpu_port_value": float(np.max(vals_ref)), "cpu_port_lbfgs_nit": [int(v) for v in nit],
+            "note": "latency-bound: one grid barrier per step; S (float64, d x d) is re-read from L2 every step by all CTAs "
+                    "together; CPU = scipy L-BFGS-B on the oracle's acquisition_func per restart"}
 
 
 def bo_step_c2(pkg, n_iter=30):

@@ -36,6 +36,10 @@ struct AscentParams {
     double lam, c, sqrt_gamma, margin, tol;
 };
 
+// Iterates in shared memory: AA_RT / 2 planes of [d] double2 (restart pairs), so a warp reading 32 consecutive columns of
+// one plane touches 512 contiguous bytes (no bank conflicts); element (column i, restart r):
+__device__ __forceinline__ int aa_at(int d, int i, int r) { return (((r >> 1) * d + i) << 1) | (r & 1); }
+
 __device__ __forceinline__ double aa_warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double sm[];
     const int d = p.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x;
-    double* phi = sm;                                       // [d][AA_RT] iterates, restart-minor
+    double* phi = sm;                                       // iterates, see aa_at()
     double* mv = phi + (size_t)d * AA_RT;                   // [d]
     double* red = mv + d;                                   // [AA_WARPS][2 AA_RT]
     double* tot = red + AA_WARPS * 2 * AA_RT;               // [2 AA_RT]
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
             for (int r = 0; r < AA_RT; ++r) {
                 const int src = r < p.R ? r : p.R - 1;      // unused lanes of the tile shadow the last restart
                 const double v = p.phi0[(size_t)src * d + j];
-                phi[(size_t)j * AA_RT + r] = v;
+                phi[aa_at(d, j, r)] = v;
                 acc[r] = fma(v, v, acc[r]);
                 acc[AA_RT + r] = fma(mj, v, acc[AA_RT + r]);
             }
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
         }
         for (int j = tid; j < d; j += AA_THREADS) {
 #pragma unroll
-            for (int r = 0; r < AA_RT; ++r) phi[(size_t)j * AA_RT + r] *= scale[r];
+            for (int r = 0; r < AA_RT; ++r) phi[aa_at(d, j, r)] *= scale[r];
         }
         if (tid < AA_RT) {
             mphi[tid] = tot[AA_RT + tid] * scale[tid];
@@ -123,18 +127,21 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
             double acc[AA_RT];
 #pragma unroll
             for (int r = 0; r < AA_RT; ++r) acc[r] = 0.0;
-#pragma unroll 2
+#pragma unroll 8
             for (int i = lane; i < d; i += 32) {
                 const double s = __ldg(row + i);
-                const double* ph = phi + (size_t)i * AA_RT;
 #pragma unroll
-                for (int r = 0; r < AA_RT; ++r) acc[r] = fma(s, ph[r], acc[r]);
+                for (int pr = 0; pr < AA_RT / 2; ++pr) {
+                    const double2 v = reinterpret_cast<const double2*>(phi)[pr * d + i];
+                    acc[2 * pr] = fma(s, v.x, acc[2 * pr]);
+                    acc[2 * pr + 1] = fma(s, v.y, acc[2 * pr + 1]);
+                }
             }
             double mine = 0.0;
 #pragma unroll
             for (int r = 0; r < AA_RT; ++r) {
                 acc[r] = aa_warp_sum(acc[r]);
-                pq[r] = fma(phi[(size_t)j * AA_RT + r], acc[r], pq[r]);
+                pq[r] = fma(phi[aa_at(d, j, r)], acc[r], pq[r]);
                 if (lane == r) mine = acc[r];
             }
             if (lane < AA_RT) __stcg(yb + (size_t)j * AA_RT + lane, mine);
@@ -154,9 +161,19 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
         grid.sync();
 
         // ---- every CTA: q_r = phi_r^T S phi_r in CTA order, the value at the current iterate, the stopping rule ----
+        {   // 32 interleaved sub-sums per restart (independent loads), folded in a fixed order
+            const int r = lane & (AA_RT - 1), sub = warp * (32 / AA_RT) + lane / AA_RT;
+            double t = 0.0;
+#pragma unroll 4
+            for (int b = sub; b < G; b += AA_WARPS * (32 / AA_RT)) t += __ldcg(pb + (size_t)b * AA_RT + r);
+#pragma unroll
+            for (int o = AA_RT; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane < AA_RT) red[warp * AA_RT + lane] = t;
+        }
+        __syncthreads();
         if (tid < AA_RT) {
             double q = 0.0;
-            for (int b = 0; b < G; ++b) q += __ldcg(pb + (size_t)b * AA_RT + tid);
+            for (int w = 0; w < AA_WARPS; ++w) q += red[w * AA_RT + tid];
             const double s = sqrt(p.c + q);
             tot[tid] = mphi[tid] + p.lam * s - p.sqrt_gamma;            // acquisition value (ssp_agent.py:167-172)
             coef[tid] = p.lam / s;
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
         if (all_done) {
             if (blockIdx.x == 0) {
                 for (int j = tid; j < d; j += AA_THREADS)
-                    for (int r = 0; r < p.R; ++r) p.phi_out[(size_t)r * d + j] = phi[(size_t)j * AA_RT + r];
+                    for (int r = 0; r < p.R; ++r) p.phi_out[(size_t)r * d + j] = phi[aa_at(d, j, r)];
                 if (tid < p.R) { p.val_out[tid] = tot[tid]; if (p.it_out) p.it_out[tid] = first_it[tid]; }
             }
             break;
@@ -204,8 +221,8 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
 #pragma unroll
                 for (int r = 0; r < AA_RT; ++r) {
                     const double nw = sc[r] * fma(cf[r], __ldcg(yb + (size_t)j * AA_RT + r), mj);
-                    const double df = nw - phi[(size_t)j * AA_RT + r];
-                    phi[(size_t)j * AA_RT + r] = nw;
+                    const double df = nw - phi[aa_at(d, j, r)];
+                    phi[aa_at(d, j, r)] = nw;
                     acc[r] = fma(df, df, acc[r]);
                     acc[AA_RT + r] = fma(mj, nw, acc[AA_RT + r]);
                 }

@@ -1,4 +1,4 @@
-"""Small end-to-end run of every scoring engine, the tensor-core encoder and the device decoder (quick manual check)."""
+"""Small end-to-end run of every scoring engine, the tensor-core encoder, the device decoder and the phi-space ascent (quick manual check)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,3 +18,5 @@ for code in (_lib.ENGINE_UMMA_LR, _lib.ENGINE_UMMA, _lib.ENGINE_SIMT, _lib.ENGIN
     print(eng.last_engine(), eng.best())
 agt.update(xc[:1].astype(np.float64), np.array([[0.1]]), np.array([0.0]))
 print("f32 encode", sp.encode(xc[:300], dtype=np.float32).shape, "decode", sp.decode(sp.encode(xc[:3]), method="direct-optim"))
+phis, vals = agt.maximize_acquisition(num_restarts=3, rng=0)
+print("phi-space ascent", phis.shape, vals, "->", agt.decode(phis[int(np.argmax(vals))][None]))
