@@ -66,6 +66,14 @@ int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus_host, const double* inv
  * (phase of timestep j at frequency k, i.e. A_t[k]*t_j/ls_t).  L=1 with tau=NULL
  * restores the plain space. */
 int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L);
+/* Multi-agent trajectories (SSPMultiAgent.encode, agents/ssp_multi_agent.py:166-186, agents sharing one x space):
+ * phi = unit( sum_i a_i (*) sum_j T_j (*) phi_x(x_ji) ).  Bound tags a_i are unitary, so in the Fourier domain the whole
+ * encoder is again a sum of unit phasors over the L = traj_len * n_agents waypoints (j, i), candidate layout
+ * (traj_len, n_agents, x_dim) flattened, with tau[(j, i)][k] = phase of T_j plus phase of a_i at frequency k.
+ * dc_sign_host (nullable): +1 / -1 per waypoint, the DC coefficient of its tag (a unitary real vector has DC +-1).
+ * normalize != 0: every consumer (encode, score) uses phi / |phi| (ssp_multi_agent.py:186); the dense-factor tcgen05
+ * engine and sspbo_encode_f32 do not form |phi| and report SSPBO_EUNSUPPORTED, AUTO never picks them then. */
+int sspbo_space_set_waypoints(sspbo_ctx* ctx, const double* tau_host, const int* dc_sign_host, int L, int normalize);
 
 int sspbo_space_dims(const sspbo_ctx* ctx, int* d, int* K, int* n, int* L);
 

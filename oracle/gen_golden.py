@@ -71,12 +71,42 @@ def gen_acq_ascent(sspspace, agents):
         init_pts=agt.init_samples[1])
 
 
+def gen_multi_agent(agents):
+    """9. multi-agent trajectory agent (agents/ssp_multi_agent.py): encode (L2-normalised), eval, decode."""
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    bm = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    out = {}
+    for tag, (n_agents, L, ssp_dim, seed) in {"a3": (3, 4, 51, 0), "a2": (2, 5, 120, 4)}.items():
+        xd = 2
+        rng = np.random.default_rng(30 + n_agents)
+        trajs = rng.uniform(-2, 2, size=(12, L * n_agents * xd))
+        tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / (L * n_agents)
+        with quiet:
+            agt = agents.SSPMultiAgent(trajs, tys, n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim,
+                                       domain_bounds=bm, length_scale=0.8, time_length_scale=1.2, seed=seed,
+                                       decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+        xc = rng.uniform(-2, 2, size=(40, L * n_agents * xd))
+        mu, var, acq = agt.eval(xc)
+        out.update({f"{tag}_Ax": agt.ssp_x_spaces[0].phase_matrix, f"{tag}_At": agt.ssp_t_space.phase_matrix,
+                    f"{tag}_ls_x": np.ravel(agt.ssp_x_spaces[0].length_scale), f"{tag}_ls_t": np.ravel(agt.ssp_t_space.length_scale),
+                    f"{tag}_agent_sps": agt.agent_sps, f"{tag}_timestep_ssps": agt.timestep_ssps,
+                    f"{tag}_trajs": trajs, f"{tag}_tys": tys, f"{tag}_xc": xc, f"{tag}_phi": agt.encode(xc),
+                    f"{tag}_mu": mu, f"{tag}_var": var, f"{tag}_acq": acq, f"{tag}_beta": np.float64(np.ravel(agt.blr.beta)[0]),
+                    f"{tag}_m": agt.blr.m, f"{tag}_S": agt.blr.S, f"{tag}_init_pts": agt.init_samples[0][1],
+                    f"{tag}_decoded": agt.decode(agt.encode(xc[:1])), f"{tag}_dims": np.array([n_agents, L, xd, ssp_dim, seed])})
+    out["bounds"] = bm
+    np.savez_compressed(os.path.join(OUT, "multi_agent.npz"), **out)
+
+
 def main():
     sspspace, blr, agents = import_reference()
     os.makedirs(OUT, exist_ok=True)
     quiet = contextlib.redirect_stdout(io.StringIO())
     if "--only-acq-ascent" in sys.argv[1:]:
         gen_acq_ascent(sspspace, agents)
+        return
+    if "--only-multi-agent" in sys.argv[1:]:
+        gen_multi_agent(agents)
         return
 
     # ---- 1. phase matrices + encode, the spaces of the reference's own tests ----
@@ -220,6 +250,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "decode_optim.npz"), A=spo.phase_matrix, ls=np.ravel(spo.length_scale), bounds=bo,
                         ssps=ssps_o, set_pts=set_pts, x0=dec0, decoded=dec)
     gen_acq_ascent(sspspace, agents)
+    gen_multi_agent(agents)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

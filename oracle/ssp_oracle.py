@@ -286,6 +286,48 @@ def traj_decode_from_set(ssp, timestep_ssps, sample_ssps, sample_points):
     return decode_from_set(queries, sample_ssps, sample_points).reshape(-1)
 
 
+def sp_vectors(domain_size, dim, rng) -> np.ndarray:
+    """Unitary tag vectors of SPSpace.  Ref: sspspace.py:55-67, 153-159 (normal draws, column-normalised, then every
+    Fourier coefficient divided by its magnitude)."""
+    if domain_size == 1:
+        v = np.zeros((1, dim))
+        v[:, 0] = 1
+        return v
+    rng = np.random.default_rng(rng) if isinstance(rng, (int, np.integer)) else rng
+    v = rng.normal(size=(domain_size, dim))
+    v /= np.linalg.norm(v, axis=0, keepdims=True)
+    fv = np.fft.fft(v, axis=-1)
+    fv = fv / np.sqrt(fv.real ** 2 + fv.imag ** 2)
+    return np.fft.ifft(fv, axis=-1).real
+
+
+def multi_agent_encode(x_phase_matrix, x_length_scale, timestep_ssps, agent_sps, x, traj_len, n_agents, x_dim):
+    """phi = unit(sum_i bind(a_i, sum_j bind(T_j, phi_x(x_ji)))), input layout (traj_len, n_agents, x_dim).
+    Ref: ssp_multi_agent.py:166-186 (agents sharing one x space)."""
+    x = np.atleast_2d(x)
+    pts = x.reshape(-1, traj_len, n_agents, x_dim)
+    total = np.zeros((x.shape[0], x_phase_matrix.shape[0]))
+    for i in range(n_agents):
+        si = np.zeros_like(total)
+        for j in range(traj_len):
+            si = si + bind(timestep_ssps[j, :], encode(x_phase_matrix, x_length_scale, pts[:, j, i, :]))
+        total = total + bind(agent_sps[i, :], si)
+    return total / np.linalg.norm(total, axis=-1, keepdims=True)
+
+
+def multi_agent_decode_from_set(ssp, timestep_ssps, agent_sps, sample_ssps, sample_points):
+    """Unbind tag and timestep, from-set decode each query.  Ref: ssp_multi_agent.py:195-208."""
+    ssp = np.atleast_2d(ssp)
+    ssp = ssp / np.linalg.norm(ssp, axis=-1, keepdims=True)
+    L, n_agents = timestep_ssps.shape[0], agent_sps.shape[0]
+    out = np.zeros((L, n_agents, sample_points.shape[1]))
+    for i in range(n_agents):
+        sspi = bind(invert(agent_sps[i:i + 1]), ssp)
+        queries = bind(invert(timestep_ssps), sspi)
+        out[:, i, :] = decode_from_set(queries, sample_ssps, sample_points)
+    return out.reshape(-1)
+
+
 # --------------------------------------------------------------------------
 # synthetic candidate generator shared by oracle, tests and the CUDA path
 # --------------------------------------------------------------------------

@@ -19,7 +19,7 @@ are accepted and ignored.  Candidate sets (extra kwargs, all optional):
                         (`SSPAgent.maximize_acquisition`), the best one decoded with the agent's decoder.  Starting
                         points come from `np.random.default_rng(random_state)`; every rank computes the same step.
     ascent_iters, ascent_tol   step cap (default 200) and stopping tolerance (default 1e-7) of 'phi-ascent'
-Supported agent types: 'ssp-hex', 'ssp-rand', 'ssp-custom' (with ssp_space=...), 'ssp-traj'.  Under
+Supported agent types: 'ssp-hex', 'ssp-rand', 'ssp-custom' (with ssp_space=...), 'ssp-traj', 'ssp-multi'.  Under
 torch.distributed (one process per GPU) the candidate index range is sharded across ranks.
 """
 from __future__ import annotations
@@ -66,6 +66,9 @@ class BayesianOptimization:
         kwargs.pop('num_perimeter_samples', 0)
         if 'traj' in agent_type:
             domain = agents.domains.TrajectoryDomain(kwargs['traj_len'], kwargs['x_dim'], self.bounds)
+        elif 'multi' in agent_type:
+            domain = agents.domains.MultiTrajectoryDomain(kwargs['n_agents'], kwargs['traj_len'], kwargs['x_dim'],
+                                                          self.bounds, kwargs.pop('goals', None))
         else:
             domain = agents.domains.BoundedDomain(self.bounds)
         if isinstance(init_points, (int, np.integer)):
@@ -93,9 +96,13 @@ class BayesianOptimization:
         elif agent_type == 'ssp-traj':
             agt = agents.SSPTrajectoryAgent(init_xs, init_ys, **kwargs)
             init_xs, init_ys = agt.init_xs, agt.init_ys
+        elif agent_type == 'ssp-multi':
+            agt = agents.SSPMultiAgent(init_xs, init_ys, **kwargs)
+            init_xs, init_ys = agt.init_xs, agt.init_ys
         else:
             raise NotImplementedError(
-                f'{agent_type} agent is not part of the GPU hot path (supported: ssp-hex, ssp-rand, ssp-custom, ssp-traj)')
+                f'{agent_type} agent is not part of the GPU hot path (supported: ssp-hex, ssp-rand, ssp-custom, ssp-traj, '
+                'ssp-multi)')
         self.logger.info(f'{type(agt).__name__} agent created')
         return agt, init_xs, init_ys
 
@@ -111,11 +118,12 @@ class BayesianOptimization:
             host = np.asarray(acq_candidates)
             return dict(total=total, start=s, x=eng.to_device(acq_candidates[s:e]),
                         lookup=lambda i: np.asarray(host[i], dtype=np.float64))
-        if isinstance(agt, agents.SSPTrajectoryAgent):
+        if isinstance(agt, (agents.SSPTrajectoryAgent, agents.SSPMultiAgent)):
             if acq_candidates == 'grid':
                 acq_candidates = 'uniform'                           # a grid over L*x_dim axes is not meaningful
-            lo = np.tile(agt.domain_bounds[:, 0], agt.traj_len)
-            hi = np.tile(agt.domain_bounds[:, 1], agt.traj_len)
+            waypoints = agt.traj_len * getattr(agt, 'n_agents', 1)
+            box = np.asarray(agt.domain_bounds, dtype=np.float64)[:agt.x_dim]
+            lo, hi = np.tile(box[:, 0], waypoints), np.tile(box[:, 1], waypoints)
         if acq_candidates == 'grid':
             if candidates_per_dim is None:
                 candidates_per_dim = int(np.min([100, int(np.ceil((1e7 / agt.ssp_dim) ** (1 / self.data_dim)))]))

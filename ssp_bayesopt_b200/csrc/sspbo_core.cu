@@ -59,8 +59,9 @@ constexpr int ENC_THREADS = 256;
 template <typename XT>
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
-         const double2* __restrict__ twiddle, int n, int K, int L, double* __restrict__ phi) {
+         const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi) {
     extern __shared__ double psi_s[];                   // ENC_CPB x d
+    __shared__ double scale_s[ENC_CPB];                 // 1 / |phi| per candidate when normalising, else 1
     const int d = 2 * K + 1;
     const int nl = n * L;
     for (int64_t base = (int64_t)blockIdx.x * ENC_CPB; base < N; base += (int64_t)gridDim.x * ENC_CPB) {
@@ -72,11 +73,21 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                 psi_entry(x + (base + c) * nl, A_turns, tau_turns, n, K, L, k, cs, sn);
                 psi_s[c * d + 1 + k] = cs;
                 psi_s[c * d + 1 + K + k] = sn;
-                if (k == 0) psi_s[c * d] = (double)L;
+                if (k == 0) psi_s[c * d] = dc;
             }
         }
         __syncthreads();
         const double inv_d = 1.0 / (double)d;
+        if (normalize) {                                // |phi|^2 = (psi_0^2 + 2 sum_k (C_k^2 + S_k^2)) / d, one warp per candidate
+            const int c = threadIdx.x >> 5;
+            if (c < ENC_CPB && base + c < N) {
+                double ss = 0.0;
+                for (int k = 1 + (threadIdx.x & 31); k < d; k += 32) ss = fma(psi_s[c * d + k], psi_s[c * d + k], ss);
+                ss = warp_sum(ss);
+                if ((threadIdx.x & 31) == 0) scale_s[c] = rsqrt((dc * dc + 2.0 * ss) * inv_d);
+            }
+            __syncthreads();
+        }
         // small batches: gridDim.y blocks share a group of candidates, each takes a slice of the output columns
         const int j0 = (int)((long long)d * blockIdx.y / gridDim.y), j1 = (int)((long long)d * (blockIdx.y + 1) / gridDim.y);
         for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
@@ -94,7 +105,7 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
             }
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c)
-                if (base + c < N) phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * acc[c]) * inv_d;
+                if (base + c < N) phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * acc[c]) * inv_d * (normalize ? scale_s[c] : 1.0);
         }
     }
 }
@@ -393,7 +404,7 @@ constexpr int EXL_THREADS = 512;    // flagged-candidate pass: few groups in fli
 template <typename XT>
 __global__ void __launch_bounds__(EX_THREADS)
 k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns,
-                const double* __restrict__ tau_turns, int n, int K, int L, const int* __restrict__ inv_perm,
+                const double* __restrict__ tau_turns, int n, int K, int L, double dc, const int* __restrict__ inv_perm,
                 const int* __restrict__ perm, const double* __restrict__ Sp, const double* __restrict__ mp, int RB,
                 double* __restrict__ part_q, double* __restrict__ part_mu) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
@@ -410,7 +421,7 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
                 const int64_t row = base + c;
-                if (f == 0) cs = (double)L;
+                if (f == 0) cs = dc;
                 else psi_entry(x + row * nl, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
@@ -445,12 +456,21 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
             for (int w = 0; w < EX_THREADS / 32; ++w) t += red[threadIdx.x][w];
             part_q[(base + threadIdx.x) * RB + rb] = t;
         }
-        if (rb == 0) {                                   // mu = m' . psi, one warp per candidate
+        if (rb == 0) {                                   // mu = m' . psi and |phi|^2 = psi^T D psi, one warp per candidate
             if (warp < EX_G && base + warp < count) {
-                double u = 0.0;
-                for (int r = lane; r < d; r += 32) u = fma(mp[perm[r]], psi_s[warp * d + r], u);
+                double u = 0.0, ss = 0.0;
+                for (int r = lane; r < d; r += 32) {
+                    const double pv = psi_s[warp * d + r];
+                    u = fma(mp[perm[r]], pv, u);
+                    ss = fma(pv, pv, ss);
+                }
                 u = warp_sum(u);
-                if (lane == 0) part_mu[base + warp] = u;
+                ss = warp_sum(ss);
+                if (lane == 0) {
+                    const double p0 = psi_s[warp * d + inv_perm[0]];
+                    part_mu[base + warp] = u;
+                    part_mu[count + base + warp] = (2.0 * ss - p0 * p0) / (double)d;
+                }
             }
         }
     }
@@ -463,7 +483,7 @@ template <typename XT>
 __global__ void __launch_bounds__(EXL_THREADS)
 k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
                 unsigned int cap, const double* __restrict__ A_turns, const double* __restrict__ tau_turns, int n, int K, int L,
-                const int* __restrict__ inv_perm, const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
+                double dc_value, int normalize, const int* __restrict__ inv_perm, const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
                 double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                 float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
@@ -480,7 +500,7 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
             const int c = i / (K + 1), f = i - c * (K + 1);
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
-                if (f == 0) cs = (double)L;
+                if (f == 0) cs = dc_value;
                 else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
@@ -523,7 +543,8 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
                 for (int w = 0; w < EXL_THREADS / 32; ++w) qq += red[warp][w];
                 const double dc = psi_s[warp * d + inv_perm[0]];
                 const double nrm2 = (2.0 * ss - dc * dc) / (double)d;                   // |phi|^2 = psi^T D psi (= 1 when L == 1)
-                const double var = inv_beta + (prior_var * nrm2 - qq);                  // blr.py:96
+                if (normalize) { u *= rsqrt(nrm2); qq /= nrm2; }                        // phi / |phi|
+                const double var = inv_beta + (prior_var * (normalize ? 1.0 : nrm2) - qq);   // blr.py:96
                 const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
                 const int64_t row = (int64_t)list[base + warp];
                 if (mu_out) mu_out[row] = (float)u;
@@ -545,14 +566,15 @@ __global__ void k_flag_fold(unsigned long long* __restrict__ stats, unsigned int
 }
 
 __global__ void k_exact_finish(int64_t N, int RB, const double* __restrict__ part_q, const double* __restrict__ part_mu,
-                               double inv_beta, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
+                               int normalize, double inv_beta, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                                float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     const int64_t count = N;
     unsigned long long my_best = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         double q = 0.0;
         for (int r = 0; r < RB; ++r) q += part_q[i * RB + r];
-        const double mu = part_mu[i];
+        double mu = part_mu[i];
+        if (normalize) { const double nrm2 = part_mu[count + i]; mu *= rsqrt(nrm2); q /= nrm2; }   // phi / |phi|
         const double var = inv_beta + q;                                        // blr.py:96
         const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
         const int64_t row = i;
@@ -1042,13 +1064,29 @@ extern "C" int sspbo_space_set_xbound(sspbo_ctx* ctx, double x_absmax) {
 }
 
 extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int L) {
+    return sspbo_space_set_waypoints(ctx, tau_host, nullptr, L, 0);
+}
+
+extern "C" int sspbo_space_set_waypoints(sspbo_ctx* ctx, const double* tau_host, const int* dc_sign_host, int L, int normalize) {
     if (!ctx) return SSPBO_EINVAL;
     if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "space_set_traj before space_set");
     if (L < 1 || L > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "traj length must be in [1, 64]");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op); dev_free(&ctx->tauf_op);
     ctx->L = L;
-    if (!tau_host) { if (L != 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "tau is required when L > 1"); return SSPBO_OK; }
+    ctx->normalize = normalize != 0;
+    ctx->dc = (double)L;
+    if (dc_sign_host) {
+        ctx->dc = 0.0;
+        for (int j = 0; j < L; ++j) {
+            if (dc_sign_host[j] != 1 && dc_sign_host[j] != -1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "DC signs must be +1 or -1");
+            ctx->dc += dc_sign_host[j];
+        }
+    }
+    if (!tau_host) {
+        if (L != 1 || dc_sign_host) SSPBO_FAIL(ctx, SSPBO_EINVAL, "tau is required when L > 1");
+        return SSPBO_OK;
+    }
     std::vector<double> t((size_t)L * ctx->K);
     std::vector<float> tf((size_t)L * ctx->K);
     for (size_t i = 0; i < t.size(); ++i) {
@@ -1073,11 +1111,15 @@ extern "C" int sspbo_space_set_traj(sspbo_ctx* ctx, const double* tau_host, int 
                 long double scaled = (long double)fr * 18446744073709551616.0L;
                 tq[(size_t)j * nf + f] = (scaled >= 18446744073709551615.0L) ? 0ull : (unsigned long long)scaled;
             }
+        if (dc_sign_host)                                              // DC phasor of waypoint j: +1 (0 turns) or -1 (1/2 turn)
+            for (int j = 0; j < L; ++j) if (dc_sign_host[j] < 0) tq[(size_t)j * nf] = 1ull << 63;
         if ((rc = dev_alloc(ctx, &ctx->tauq_op, tq.size()))) return rc;
         SSPBO_CUDA(ctx, cudaMemcpy(ctx->tauq_op, tq.data(), tq.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
         std::vector<float> tfl((size_t)L * nf, 0.f);                      // same, float32 radians in [-pi, pi]
         for (int j = 0; j < L; ++j)
             for (int f = 1; f <= ctx->K; ++f) tfl[(size_t)j * nf + f] = (float)(t[(size_t)j * ctx->K + f - 1] * kTwoPi);
+        if (dc_sign_host)
+            for (int j = 0; j < L; ++j) if (dc_sign_host[j] < 0) tfl[(size_t)j * nf] = (float)(0.5 * kTwoPi);
         if ((rc = dev_alloc(ctx, &ctx->tauf_op, tfl.size()))) return rc;
         SSPBO_CUDA(ctx, cudaMemcpy(ctx->tauf_op, tfl.data(), tfl.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -1106,11 +1148,11 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_encode<float><<<grid, ENC_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
-                                                           ctx->n, ctx->K, ctx->L, phi_out);
+                                                           ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out);
     } else if (x_dtype == SSPBO_F64) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_encode<double><<<grid, ENC_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
-                                                            ctx->n, ctx->K, ctx->L, phi_out);
+                                                            ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out);
     } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
@@ -1137,7 +1179,7 @@ extern "C" int sspbo_encode_f32(sspbo_ctx* ctx, const void* x, int x_dtype, int6
     cudaStream_t st = (cudaStream_t)stream;
     int kc, bn, nc, nj, rc;
     sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
-    if (ctx->n > 8 || !ctx->umma_range_ok || nc > 8 || (ctx->L != 1 && (ctx->n > 3 || !ctx->tauq_op)))
+    if (ctx->n > 8 || !ctx->umma_range_ok || nc > 8 || (ctx->L != 1 && (ctx->n > 3 || !ctx->tauq_op)) || ctx->normalize)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "encode_f32: shape outside the tcgen05 kernel (n=%d, d=%d, L=%d)", ctx->n, ctx->d, ctx->L);
     if (!ctx->blr_ready || !ctx->has_factor) {           // geometry normally set by blr_init
         ctx->KC_pad = kc; ctx->BN = bn; ctx->n_chunks = nc; ctx->NJ_pad = nj;
@@ -1457,12 +1499,12 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
         if (x_dtype == SSPBO_F32) {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_exact_lowrank<float><<<gx, EXL_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         } else {
             SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_exact_lowrank<double><<<gx, EXL_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
+                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
                 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
         }
         SSPBO_LAUNCH_CHECK(ctx);
@@ -1475,7 +1517,7 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     const int64_t groups = (N + EX_G - 1) / EX_G;
     int RB = 1;
     while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;
-    const size_t need = (size_t)N * (RB + 1);
+    const size_t need = (size_t)N * (RB + 2);                  // partial quadratic forms, mu, |phi|^2
     if (need > ctx->ex_part_cap) {
         if (ctx->ex_part) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); }
         int rc = dev_alloc(ctx, &ctx->ex_part, need);
@@ -1489,15 +1531,15 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns,
-            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
     } else {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_exact_partial<double><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns,
-            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
     }
     SSPBO_LAUNCH_CHECK(ctx);
     const int fb = (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);
-    k_exact_finish<<<fb, 256, 0, st>>>(N, RB, part_q, part_mu, 1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
+    k_exact_finish<<<fb, 256, 0, st>>>(N, RB, part_q, part_mu, ctx->normalize ? 1 : 0, 1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }

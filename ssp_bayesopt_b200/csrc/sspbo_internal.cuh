@@ -92,6 +92,9 @@ struct sspbo_ctx {
     double* scal = nullptr;          // a few device scalars
     // tensor-core encoder: split-fp16 inverse-DFT basis in operand order (NJ_pad x KC_pad), built lazily
     __half* Bh_enc = nullptr; __half* Bl_enc = nullptr; double enc_scale = 1.0; int enc_K = 0;
+    // waypoint sums (L > 1): value of the DC component (L, or sum of the +-1 DC signs of bound tags) and whether phi is
+    // divided by its norm (multi-agent trajectories, agents/ssp_multi_agent.py:166-186)
+    double dc = 1.0; bool normalize = false;
     // workspace of the phi-space acquisition ascent (sspbo_ascent.cu): Y = S Phi and per-CTA partial sums, double-buffered
     double* aa_work = nullptr; size_t aa_cap = 0;
     // opaque state of the tcgen05 engines (tensor maps etc.)

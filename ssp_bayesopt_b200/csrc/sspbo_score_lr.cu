@@ -62,6 +62,7 @@ struct Params {
     int split_issue;                    // BN > 128: next k-block's barrier waits between the two halves of the MMAs
     int merged;                         // BN <= 128: hi|lo tiles of the B slot read as ONE 2 BN-row operand (two MMAs per K step)
     float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
+    int normalize;                      // trajectory mode: score phi / |phi| (multi-agent trajectories)
     float *mu, *var, *acq;
     unsigned long long* best;
     unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
@@ -345,7 +346,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             }
             const long long gi = tile * BM + row;
             if (gi < p.N) {
-                const float mu = mu_raw * inv_mscale;
+                float mu = mu_raw * inv_mscale;
                 float prior = p.prior_var, flag_below = p.flag_below;
                 if constexpr (TRAJ) {                                                 // |phi|^2 / alpha instead of 1 / alpha
                     float* np_ = nrm_part + (size_t)(tile_iter & (NRM_DEPTH - 1)) * GEN_W * BM + row;
@@ -353,7 +354,8 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
                     for (int w = 0; w < GEN_W; ++w) { ssum += np_[w * BM]; np_[w * BM] = 0.f; }   // warps without a k-block in a tile write nothing
                     const float nrm2 = fmaf(p.nrm_scale, ssum, -p.nrm_offset);
-                    prior *= nrm2; flag_below *= nrm2;
+                    if (p.normalize) { const float inv = 1.f / nrm2; mu *= sqrtf(inv); q *= inv; }   // phi / |phi|
+                    else { prior *= nrm2; flag_below *= nrm2; }
                 }
                 const float rem = prior - q * p.inv_rscale2;                          // |phi|^2 / alpha - |V psi|^2
                 const float var = p.inv_beta + rem;                                   // blr.py:96
@@ -702,10 +704,11 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
     p.L = ctx->L; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
     {   // |phi|^2 = (1/d) (psi_0^2 + 2 sum_{k>=1} (C_k^2 + S_k^2)); the generators sum C^2 + S^2 over every operand frequency,
-        // including the DC term (= L^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
+        // including the DC term (= dc^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
         const double d = (double)ctx->d, L2 = (double)ctx->L * ctx->L;
         const int n_pad = ctx->KC_pad / 2 - 1 - ctx->K;
-        p.nrm_scale = (float)(2.0 / d); p.nrm_offset = (float)(L2 / d * (1.0 + 2.0 * n_pad));
+        p.nrm_scale = (float)(2.0 / d); p.nrm_offset = (float)((ctx->dc * ctx->dc + 2.0 * n_pad * L2) / d);
+        p.normalize = ctx->normalize ? 1 : 0;
     }
     p.debug = sspbo_debug_env();
     const long long tiles = (N + BM - 1) / BM;

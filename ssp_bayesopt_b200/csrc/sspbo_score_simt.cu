@@ -14,12 +14,13 @@ template <typename XT>
 __global__ void __launch_bounds__(ST_THREADS)
 k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* __restrict__ A_turns,
              const double* __restrict__ tau_turns, int n, int K, int L, int dp, const float* __restrict__ Rt,
-             const float* __restrict__ mp, float inv_beta, float lam, float gamma_t, float* __restrict__ mu_out,
+             const float* __restrict__ mp, float dc, int normalize, float inv_beta, float lam, float gamma_t, float* __restrict__ mu_out,
              float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     extern __shared__ __align__(16) float smem[];
     float* psiT = smem;                                   // dp x ST_TC, k-major
     float* red = smem + (size_t)dp * ST_TC;               // ST_TC x 8 (warps)  then  ST_TC x 16 (mu slices)
     float* red_mu = red + ST_TC * 8;
+    float* red_n = red_mu + ST_TC * 16;                   // ST_TC x 16 slices of sum_k psi_k^2 (normalised scoring)
     const int d = 2 * K + 1, nl = n * L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned long long my_best = 0ull;
@@ -49,7 +50,7 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
         }
         for (int i = tid; i < ST_TC * (dp - d + 1); i += ST_THREADS) {
             int c = i % ST_TC, r = i / ST_TC;
-            if (r == 0) psiT[c] = (float)L;               // DC term: sum of L unit phasors at frequency 0
+            if (r == 0) psiT[c] = dc;                     // DC term: sum of the waypoints' unit phasors at frequency 0
             else psiT[(d + r - 1) * ST_TC + c] = 0.f;     // padding rows
         }
         __syncthreads();
@@ -86,9 +87,14 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
         }
         {
             int c = tid % ST_TC, slice = tid / ST_TC;     // 16 slices of k
-            float u = 0.f;
-            for (int k = slice; k < d; k += ST_THREADS / ST_TC) u = fmaf(mp[k], psiT[k * ST_TC + c], u);
+            float u = 0.f, ss = 0.f;
+            for (int k = slice; k < d; k += ST_THREADS / ST_TC) {
+                const float pv = psiT[k * ST_TC + c];
+                u = fmaf(mp[k], pv, u);
+                ss = fmaf(pv, pv, ss);
+            }
             red_mu[c * 16 + slice] = u;
+            red_n[c * 16 + slice] = ss;
         }
         __syncthreads();
         // ---- phase 3: acquisition + running argmax ----
@@ -98,6 +104,13 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
             for (int w = 0; w < 8; ++w) qq += red[tid * 8 + w];
 #pragma unroll
             for (int s = 0; s < 16; ++s) u += red_mu[tid * 16 + s];
+            if (normalize) {                                                  // phi / |phi|, |phi|^2 = psi^T D psi
+                float ss = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) ss += red_n[tid * 16 + sl];
+                const float nrm2 = (2.f * ss - dc * dc) / (float)d;
+                u *= rsqrtf(nrm2); qq /= nrm2;
+            }
             float var = inv_beta + qq;                                        // blr.py:96
             // ssp_agent.py:136: lam (sqrt(var + gamma) - sqrt(gamma)), written without the float32 cancellation
             float acq = lam * var / (sqrtf(var + gamma_t) + sqrtf(gamma_t));
@@ -124,19 +137,19 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
 
 int sspbo_score_simt_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
                             float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
-    size_t smem = ((size_t)ctx->dp * ST_TC + ST_TC * 8 + ST_TC * 16) * sizeof(float);
+    size_t smem = ((size_t)ctx->dp * ST_TC + ST_TC * 8 + 2 * ST_TC * 16) * sizeof(float);
     int64_t tiles = (N + ST_TC - 1) / ST_TC;
     int blocks = (int)(tiles < (int64_t)ctx->sm_count * 2 ? tiles : (int64_t)ctx->sm_count * 2);
     float inv_beta = (float)(1.0 / ctx->beta);
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_score_simt<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_simt<float><<<blocks, ST_THREADS, smem, st>>>((const float*)x, N, index0, ctx->A_turns, ctx->tau_turns, ctx->n,
-                                                              ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, inv_beta, lam,
+                                                              ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, (float)ctx->dc, ctx->normalize ? 1 : 0, inv_beta, lam,
                                                               gamma_t, mu, var, acq, best);
     } else {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_score_simt<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_simt<double><<<blocks, ST_THREADS, smem, st>>>((const double*)x, N, index0, ctx->A_turns, ctx->tau_turns, ctx->n,
-                                                               ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, inv_beta, lam,
+                                                               ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, (float)ctx->dc, ctx->normalize ? 1 : 0, inv_beta, lam,
                                                                gamma_t, mu, var, acq, best);
     }
     SSPBO_LAUNCH_CHECK(ctx);

@@ -118,6 +118,21 @@ class DeviceEngine:
         self._check(rc, "sspbo_space_set_traj")
         self.L = L
 
+    def set_waypoints(self, tau: np.ndarray, dc_sign=None, normalize=False) -> None:
+        """Generalised trajectory mode (multi-agent trajectories): tau (L, K) radians per waypoint and frequency,
+        dc_sign (L,) the +-1 DC coefficient of each waypoint's tag, normalize: consumers use phi / |phi|."""
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        L = tau.shape[0]
+        assert tau.shape == (L, self.K), f"tau must be (L, {self.K}), got {tau.shape}"
+        sp = None
+        if dc_sign is not None:
+            sign = np.ascontiguousarray(dc_sign, dtype=np.int32)
+            assert sign.shape == (L,)
+            sp = sign.ctypes.data_as(_lib._pi)
+        rc = self.lib.sspbo_space_set_waypoints(self._ctx, tau.ctypes.data_as(_lib._pd), sp, L, 1 if normalize else 0)
+        self._check(rc, "sspbo_space_set_waypoints")
+        self.L = L
+
     # ------------------------------------------------------------------ K1
     def encode_device(self, x):
         """x (N, n*L) -> device tensor phi (N, d) float64."""
@@ -306,8 +321,14 @@ class DeviceEngine:
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
-        for i, c0 in enumerate(range(0, N, chunk)):
-            b, n = i & 1, min(chunk, N - c0)
+        # short first pieces: the copy of piece 0 is the only one no scoring overlaps, so keep it small
+        pieces, c0, n = [], 0, max(chunk >> 3, 1 << 15)
+        while c0 < N:
+            n = min(n, chunk, N - c0)
+            pieces.append((c0, n))
+            c0, n = c0 + n, n * 2
+        for i, (c0, n) in enumerate(pieces):
+            b = i & 1
             with torch.cuda.stream(self._copy_stream):
                 if i >= 2:
                     self._copy_stream.wait_event(done[b])

@@ -10,8 +10,10 @@ order, so seeded spaces are bit-identical.  `encode`, grid generation and
 `decode(method='from-set')` run on the GPU through libsspbo.so; there is no
 numpy implementation of them in this package.
 
-Not re-hosted (out of the hot-path scope): SPSpace,
-train_decoder_net / 'network' decoders (TensorFlow), Nengo encoder samplers, plotting.
+SPSpace (sspspace.py:14-186) is re-hosted as host numpy only (tag vectors of the multi-agent encoder); its vectors
+enter the device encoder as per-frequency phases.
+Not re-hosted (out of the hot-path scope): train_decoder_net / 'network' decoders
+(TensorFlow), Nengo encoder samplers, plotting.
 """
 from __future__ import annotations
 
@@ -49,6 +51,51 @@ def _rd_sequence(count: int, dim: int, seed: float = 0.5) -> np.ndarray:
         g = (1 + g) ** (1.0 / (dim + 1))
     alpha = np.mod((1.0 / g) ** np.arange(1, dim + 1), 1.0)
     return np.mod(seed + np.outer(np.arange(1, count + 1), alpha), 1.0)
+
+
+class SPSpace:
+    """Random unitary tag vectors for discrete symbols (sspspace.py:14-186), host numpy in the reference's RNG call order.
+    Only the pieces the multi-agent trajectory agent uses: `vectors`, `inverse_vectors`, `make_unitary`, `invert`, `bind`,
+    `identity`."""
+
+    def __init__(self, domain_size: int, dim: int, vectors: Optional[np.ndarray] = None,
+                 rng: Optional[Union[int, np.random.Generator]] = None, **kwargs):
+        self.domain_size = int(domain_size)
+        self.dim = int(dim)
+        self.rng = _get_rng(rng)
+        if self.domain_size == 1:                                   # a single symbol is the identity
+            self.vectors = np.zeros((self.domain_size, self.dim))
+            self.vectors[:, 0] = 1
+        elif vectors is not None:
+            assert vectors.shape[0] == self.domain_size
+            assert vectors.shape[1] == self.dim
+            self.vectors = vectors
+        else:
+            v = self.rng.normal(size=(self.domain_size, self.dim))
+            v /= np.linalg.norm(v, axis=0, keepdims=True)
+            self.vectors = self.make_unitary(v)
+        self.inverse_vectors = self.invert(self.vectors)
+
+    def make_unitary(self, v):
+        fv = np.fft.fft(v, axis=-1)
+        fv = fv / np.sqrt(fv.real ** 2 + fv.imag ** 2)
+        return np.fft.ifft(fv, axis=-1).real
+
+    def identity(self):
+        s = np.zeros((1, self.dim))
+        s[:, 0] = 1
+        return s
+
+    def bind(self, *arrays):
+        arrays = [np.atleast_2d(a) for a in arrays]
+        f = np.fft.fft(arrays[0], axis=-1)
+        for a in arrays[1:]:
+            f = f * np.fft.fft(a, axis=-1)
+        return np.fft.ifft(f, axis=-1).real
+
+    def invert(self, a):
+        a = np.atleast_2d(a)
+        return a[:, -np.arange(self.dim)]
 
 
 class SSPSpace:

@@ -635,6 +635,78 @@ def test_trajectory_tcgen05_engine(pkg, L, ssp_dim, N):
             assert eng.best()[1] == int(np.argmax(ref_score))
 
 
+@pytest.mark.parametrize("tag", ["a3", "a2"])
+def test_multi_agent_golden(pkg, golden, tag):
+    """SSPMultiAgent against the live reference's output (tests/golden/multi_agent.npz):
+    tag vectors, normalised encode, posterior, eval through every engine that forms |phi|, decode."""
+    from ssp_bayesopt_b200 import _lib
+    g = golden("multi_agent.npz")
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g[f"{tag}_dims"])
+    agt = pkg.SSPMultiAgent(g[f"{tag}_trajs"], g[f"{tag}_tys"], n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim,
+                            domain_bounds=g["bounds"], length_scale=0.8, time_length_scale=1.2, seed=seed,
+                            decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    assert np.array_equal(agt.ssp_x_spaces[0].phase_matrix, g[f"{tag}_Ax"])
+    assert np.array_equal(agt.ssp_t_space.phase_matrix, g[f"{tag}_At"])
+    np.testing.assert_allclose(agt.agent_sps, g[f"{tag}_agent_sps"], atol=1e-15)
+    np.testing.assert_allclose(agt.timestep_ssps, g[f"{tag}_timestep_ssps"], atol=2e-13)
+    phi = agt.encode(g[f"{tag}_xc"])
+    np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=5e-13)
+    np.testing.assert_allclose(np.linalg.norm(phi, axis=1), 1.0, atol=1e-13)
+    assert abs(float(np.ravel(agt.blr.beta)[0]) - float(g[f"{tag}_beta"])) <= 1e-12 * float(g[f"{tag}_beta"])
+    assert rel(agt.blr.m, g[f"{tag}_m"]) < 1e-9 and rel(agt.blr.S, g[f"{tag}_S"]) < 1e-9
+    mu, var, acq = agt.eval(g[f"{tag}_xc"])                                   # 40 candidates: exact float64 engine
+    assert_scores_close(mu, acq, g[f"{tag}_mu"], g[f"{tag}_acq"])
+    np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=RTOL_SCORE)
+    eng = agt._scoring_engine()
+    for code, name in ((_lib.ENGINE_SIMT, "simt"), (_lib.ENGINE_UMMA_LR, "umma-lowrank")):
+        _, (mu, var, acq) = eng.score(g[f"{tag}_xc"], 5.0, 0.0, want_outputs=True, engine=code)
+        assert eng.last_engine() == name
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), g[f"{tag}_mu"], g[f"{tag}_acq"])
+        np.testing.assert_allclose(var.double().cpu().numpy(), g[f"{tag}_var"], rtol=RTOL_SCORE)
+    with pytest.raises(_lib.SspboError):                                      # the dense-factor kernel does not form |phi|
+        eng.score(g[f"{tag}_xc"], 5.0, 0.0, engine=_lib.ENGINE_UMMA)
+    assert np.array_equal(agt.decode(phi[:1]), g[f"{tag}_decoded"])
+
+
+def test_multi_agent_tcgen05_and_driver(pkg):
+    """Larger multi-agent candidate sets: AUTO picks the low-rank tcgen05 engine in trajectory mode with normalisation
+    (both phase paths), checked against the oracle restatement of ssp_multi_agent.py:166-186; then the BO driver."""
+    from ssp_bayesopt_b200 import _lib
+    bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    n_agents, L, xd, ssp_dim, N = 3, 6, 2, 300, 3000
+    rng = np.random.default_rng(17)
+    trajs = rng.uniform(-2, 2, (14, L * n_agents * xd))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / (L * n_agents)
+    agt = pkg.SSPMultiAgent(trajs, tys, n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim, domain_bounds=bounds,
+                            length_scale=0.8, time_length_scale=1.2, seed=1, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    Ax, At = agt.ssp_x_spaces[0].phase_matrix, agt.ssp_t_space.phase_matrix
+    T = orc.traj_timestep_ssps(At, np.array([1.2]), L)
+    tags = orc.sp_vectors(n_agents, Ax.shape[0], 1)
+    enc = lambda x: orc.multi_agent_encode(Ax, 0.8 * np.ones(2), T, tags, x, L, n_agents, xd)
+    ref = orc.BLR(Ax.shape[0])
+    ref.update(enc(trajs), tys)
+    xc = rng.uniform(-2, 2, (N, L * n_agents * xd)).astype(np.float32)
+    xc[:4] = trajs[:4].astype(np.float32)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(enc(xc.astype(np.float64)), ref, 5.0, 0.0)
+    ref_score = ref_mu.ravel() + ref_acq
+    eng = agt._scoring_engine()
+    for ph in (1, 0):
+        eng.set_policy(phase32=ph)
+        _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True)
+        assert eng.last_engine() == "umma-lowrank"
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        srt = np.sort(ref_score)[::-1]
+        if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert eng.best()[1] == int(np.argmax(ref_score))
+    f = lambda x: float(-np.sum(np.asarray(x) ** 2) / (L * n_agents))
+    opt = pkg.BayesianOptimization(f=lambda x, info=None: f(x), bounds=bounds)
+    opt.maximize(init_points=(trajs, tys), n_iter=3, agent_type="ssp-multi", n_agents=n_agents, x_dim=xd, traj_len=L,
+                 ssp_dim=ssp_dim, length_scale=0.8, time_length_scale=1.2, seed=1, decoder_method="from-set", gamma_c=0.0,
+                 beta_ucb=5.0, n_candidates=20000)
+    assert opt.xs.shape == (17, L * n_agents * xd) and np.all(np.abs(opt.xs) <= 2)
+
+
 # ------------------------------------------------------------------------------------------ generators, driver
 def test_fill_uniform_bit_exact(pkg):
     eng = pkg.DeviceEngine()

@@ -1,6 +1,7 @@
 """Pin the numpy oracle against outputs of the live reference (tests/golden/*.npz,
 written by oracle/gen_golden.py).  CPU only."""
 import numpy as np
+import pytest
 
 from oracle import ssp_oracle as orc
 
@@ -149,6 +150,32 @@ def test_trajectory_matches_reference(golden):
     ssps = orc.encode(g["Ax"], g["ls_x"], pts)
     dec = orc.traj_decode_from_set(phi[:1], T, ssps, pts)
     assert np.array_equal(dec, g["decoded"])
+
+
+@pytest.mark.parametrize("tag", ["a3", "a2"])
+def test_multi_agent_matches_reference(golden, tag):
+    """oracle.multi_agent_encode / decode / sp_vectors against the live reference's SSPMultiAgent
+    (agents/ssp_multi_agent.py:166-208); the tag vectors include DC coefficients of both signs."""
+    g = golden("multi_agent.npz")
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g[f"{tag}_dims"])
+    d = g[f"{tag}_Ax"].shape[0]
+    tags = orc.sp_vectors(n_agents, d, seed)
+    np.testing.assert_allclose(tags, g[f"{tag}_agent_sps"], atol=1e-15)
+    T = orc.traj_timestep_ssps(g[f"{tag}_At"], g[f"{tag}_ls_t"], L)
+    np.testing.assert_allclose(T, g[f"{tag}_timestep_ssps"], atol=1e-15)
+    phi = orc.multi_agent_encode(g[f"{tag}_Ax"], g[f"{tag}_ls_x"], T, tags, g[f"{tag}_xc"], L, n_agents, xd)
+    np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=1e-14)
+    model = orc.BLR(d)
+    model.update(orc.multi_agent_encode(g[f"{tag}_Ax"], g[f"{tag}_ls_x"], T, tags, g[f"{tag}_trajs"], L, n_agents, xd), g[f"{tag}_tys"])
+    np.testing.assert_allclose(model.m, g[f"{tag}_m"], rtol=1e-9, atol=1e-12)
+    mu, var, acq = orc.agent_eval(phi, model, 5.0, 0.0)
+    np.testing.assert_allclose(mu, g[f"{tag}_mu"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=1e-9)
+    np.testing.assert_allclose(acq, g[f"{tag}_acq"], rtol=1e-9)
+    pts = g[f"{tag}_init_pts"]
+    ssps = orc.encode(g[f"{tag}_Ax"], g[f"{tag}_ls_x"], pts)
+    dec = orc.multi_agent_decode_from_set(phi[:1], T, tags, ssps, pts)
+    assert np.array_equal(dec, g[f"{tag}_decoded"])
 
 
 def test_counter_uniform_is_range_consistent():
