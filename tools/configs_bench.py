@@ -62,8 +62,39 @@ def c5(n=1 << 20, steps=3):
           f"(engine {eng.last_engine()}) -> 1e7 candidates: {1e7 / (n / ms * 1e3):.2f} s")
 
 
+def multi(n=1 << 20, steps=3):
+    """Multi-agent trajectories: 3 agents x 10 timesteps, d = 1945, normalised scoring."""
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    n_agents, L, xd = 3, 10, 2
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-5, 5, (12, L * n_agents * xd))
+    y = -np.sum(X ** 2, axis=1, keepdims=True) / 100.0
+    agt = pkg.SSPMultiAgent(X, y, n_agents=n_agents, x_dim=xd, traj_len=L, domain_bounds=b2, ssp_dim=2048, length_scale=1.0,
+                            time_length_scale=1.0, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0)
+    eng = agt._scoring_engine()
+    cand = eng.fill_uniform(0, 0, n, L * n_agents * xd)
+    cand.mul_(10.0).sub_(5.0)
+    agt.best_candidate(cand)
+    eng.best()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        agt.best_candidate(cand)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t0 = time.perf_counter()
+    phi = agt.encode(cand[:4096].cpu().numpy().astype(np.float64))
+    t_enc = time.perf_counter() - t0
+    print(f"multi-agent {n_agents} x L={L} x_dim={xd} d={eng.d}: {n} candidates in {ms:.1f} ms = {n / ms * 1e3:.3e} candidates/s "
+          f"(engine {eng.last_engine()}, stats {eng.score_stats(reset=False)}); float64 encode of 4096: {t_enc * 1e3:.1f} ms")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c4", "c5"]
+    which = sys.argv[1:] or ["c4", "c5", "multi"]
+    if "multi" in which:
+        multi()
     if "c5" in which:
         c5()
     if "c4" in which:
