@@ -181,6 +181,13 @@ int sspbo_acq_ascent(sspbo_ctx* ctx, const double* phi0_dev, int R, double lam, 
  * qa == qb, or either equal to 1 (numpy broadcasting); out_dev: max(qa, qb) x d.  d is the context's ssp_dim. */
 int sspbo_bind(sspbo_ctx* ctx, const double* a_dev, int qa, const double* b_dev, int qb, double* out_dev, void* stream);
 
+/* ---- length-scale search support (agents/ssp_traj_agent.py:113-143) -----------------------
+ * G = Phi Phi^T of n encoded rows (phi_dev: n x d float64, gram_out_dev: n x n float64).  With the Gram matrix of the
+ * initial design, every fold of the reference's K-fold search is an n x n problem in the BLR's dual form
+ * (mu = k^T (G_tr + alpha/beta I)^-1 t, var = 1/beta + (k** - k^T (G_tr + alpha/beta I)^-1 k) / alpha), which the host
+ * mirror solves; encoding at the trial length scales and this product are the only O(d) steps. */
+int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_dev, void* stream);
+
 /* ---- candidate generators ---------------------------------------------------------
  * Counter-based uniform(0,1) float32 stream (same integer hash as
  * oracle/ssp_oracle.py:counter_uniform, bit-exact): rows [start, start+count) of an

@@ -98,6 +98,43 @@ def gen_multi_agent(agents):
     np.savez_compressed(os.path.join(OUT, "multi_agent.npz"), **out)
 
 
+def gen_lengthscale_cv(agents):
+    """10. K-fold length-scale search of the trajectory agent (ssp_traj_agent.py:113-143): every objective evaluation
+    scipy's L-BFGS-B makes inside the live reference is recorded, together with the result."""
+    from ssp_bayes_opt.agents import ssp_traj_agent as ref_mod
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    bt = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    L, xd = 4, 2
+    rng = np.random.default_rng(40)
+    trajs = rng.uniform(-2, 2, size=(14, L * xd))
+    tys = (np.sin(trajs[:, ::2]).sum(axis=1, keepdims=True) - 0.3 * np.sum(trajs[:, 1::2] ** 2, axis=1, keepdims=True)) / L
+    log = []
+    real_minimize = ref_mod.minimize
+
+    def recording_minimize(fun, *a, **kw):
+        def wrapped(x):
+            v = fun(x)
+            log.append((np.array(x, dtype=np.float64).ravel().copy(), float(v)))
+            return v
+        # the reference passes x0 of shape (2, 1); scipy >= 1.11 rejects that ("'x0' must only have one dimension"), older
+        # releases squeezed it.  Squeeze here so the reference's search runs under the installed scipy.
+        kw["x0"] = np.ravel(kw["x0"])
+        return real_minimize(wrapped, *a, **kw)
+
+    ref_mod.minimize = recording_minimize
+    try:
+        with quiet:
+            agt = agents.SSPTrajectoryAgent(trajs, tys, x_dim=xd, traj_len=L, ssp_dim=51, domain_bounds=bt,
+                                            decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    finally:
+        ref_mod.minimize = real_minimize
+    np.savez_compressed(os.path.join(OUT, "lengthscale_cv.npz"), Ax=agt.ssp_x_space.phase_matrix,
+                        At=agt.ssp_t_space.phase_matrix, trajs=trajs, tys=tys, bounds=bt,
+                        eval_x=np.stack([x for x, _ in log]), eval_f=np.array([f for _, f in log]),
+                        result=np.concatenate([np.ravel(agt.ssp_x_space.length_scale)[:1], np.ravel(agt.ssp_t_space.length_scale)[:1]]),
+                        beta=np.float64(np.ravel(agt.blr.beta)[0]), m=agt.blr.m)
+
+
 def main():
     sspspace, blr, agents = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -107,6 +144,9 @@ def main():
         return
     if "--only-multi-agent" in sys.argv[1:]:
         gen_multi_agent(agents)
+        return
+    if "--only-lengthscale-cv" in sys.argv[1:]:
+        gen_lengthscale_cv(agents)
         return
 
     # ---- 1. phase matrices + encode, the spaces of the reference's own tests ----
@@ -251,6 +291,7 @@ def main():
                         ssps=ssps_o, set_pts=set_pts, x0=dec0, decoded=dec)
     gen_acq_ascent(sspspace, agents)
     gen_multi_agent(agents)
+    gen_lengthscale_cv(agents)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

@@ -286,6 +286,37 @@ def traj_decode_from_set(ssp, timestep_ssps, sample_ssps, sample_points):
     return decode_from_set(queries, sample_ssps, sample_points).reshape(-1)
 
 
+def kfold_indices(n, n_splits):
+    """Contiguous, unshuffled folds of sklearn.model_selection.KFold(n_splits): the first n % n_splits folds get one
+    extra sample.  Yields (train_idx, test_idx).  Ref: ssp_traj_agent.py:121, 127."""
+    sizes = np.full(n_splits, n // n_splits, dtype=int)
+    sizes[:n % n_splits] += 1
+    idx = np.arange(n)
+    start = 0
+    for sz in sizes:
+        test = idx[start:start + sz]
+        yield np.concatenate([idx[:start], idx[start + sz:]]), test
+        start += sz
+
+
+def traj_lengthscale_cv_loss(x_phase_matrix, t_phase_matrix, length_scale, xs, ys, traj_len, x_dim):
+    """Objective of the trajectory agent's length-scale search at length_scale = (ls_x, ls_t): K-fold (min(n, 50) folds)
+    negative predictive log-likelihood of a fresh BLR per fold, timestep SSPs at linspace(0, L, L).
+    Ref: ssp_traj_agent.py:117-137."""
+    ls_x, ls_t = float(length_scale[0]), float(length_scale[1])
+    T = encode(t_phase_matrix, np.array([ls_t]), np.linspace(0, traj_len, traj_len).reshape(-1, 1))
+    phis = traj_encode(x_phase_matrix, ls_x * np.ones(x_dim), T, xs, traj_len, x_dim)
+    errors = []
+    for train, test in kfold_indices(xs.shape[0], min(xs.shape[0], 50)):
+        b = BLR(phis.shape[1])
+        b.update(phis[train], ys[train])
+        mu, var = b.predict(phis[test])
+        diff = ys[test].flatten() - mu.flatten()
+        loss = -0.5 * np.log(var) - np.divide(np.power(diff, 2), var)
+        errors.append(np.sum(-loss))
+    return np.sum(errors)
+
+
 def sp_vectors(domain_size, dim, rng) -> np.ndarray:
     """Unitary tag vectors of SPSpace.  Ref: sspspace.py:55-67, 153-159 (normal draws, column-normalised, then every
     Fourier coefficient divided by its magnitude)."""

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sspbo_from_set_argmax": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "sspbo_decode_optim": (_i, [_vp, _vp, _i, _vp, _pd, _vp, _vp]),
     "sspbo_acq_ascent": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _d, _vp, _vp, _vp, _vp]),
+    "sspbo_gram": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sspbo_bind": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "sspbo_fill_uniform": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "sspbo_grid_points": (_i, [_vp, _vp, _pi, _i, _i64, _i64, _vp, _vp]),

@@ -6,7 +6,11 @@ the device encoder / scorer just sums L phasors per frequency (`sspbo_space_set_
 explicit bind is executed.  Decoding unbinds each timestep and runs the GPU from-set search
 (ssp_traj_agent.py:165-176).
 
-Out of scope (raise): K-fold length-scale search (:113-143) and the sklearn MLP 'regression' decoder (:85-102).
+Omitting `length_scale` runs the reference's K-fold length-scale search (:113-143): scipy's L-BFGS-B
+on the host drives it as in the reference; every objective evaluation encodes the initial design on the device at the
+trial length scales, forms its Gram matrix there (`sspbo_gram`), and solves each fold's BLR in dual form (n x n).
+
+Out of scope (raise): the sklearn MLP 'regression' decoder (:85-102).
 """
 from __future__ import annotations
 
@@ -45,25 +49,68 @@ class SSPTrajectoryAgent(SSPAgent):
         self.ssp_x_space = ssp_x_space
         self.ssp_t_space = ssp_t_space
         self.ssp_space = ssp_x_space
+        # device context that sees whole trajectories: spatial phases + per-timestep phase offsets
+        self._traj_engine = DeviceEngine(self.ssp_x_space._device)
         if 'length_scale' not in kwargs or np.any(np.array(kwargs.get('length_scale')) < 0):
-            raise NotImplementedError(
-                "length_scale / time_length_scale must be given: the K-fold search of the reference "
-                "(ssp_traj_agent.py:113-143) is outside the GPU hot-path scope")
-        self.ssp_x_space.update_lengthscale(kwargs.get('length_scale'))
-        self.ssp_t_space.update_lengthscale(kwargs.get('time_length_scale', 1))
+            optres = self._optimize_lengthscale(self.init_xs, self.init_ys)
+            self.ssp_x_space.update_lengthscale(optres[0])
+            self.ssp_t_space.update_lengthscale(optres[1])
+        else:
+            self.ssp_x_space.update_lengthscale(kwargs.get('length_scale'))
+            self.ssp_t_space.update_lengthscale(kwargs.get('time_length_scale', 1))
 
         timesteps = np.linspace(1, self.traj_len + 1, self.traj_len).reshape(-1, 1)
         self.timestep_ssps = self.ssp_t_space.encode(timesteps)
         self.timestep_inv_ssps = self.ssp_t_space.encode(-timesteps)
+        self._point_engine(timesteps)
 
-        # device context that sees whole trajectories: spatial phases + per-timestep phase offsets
+    def _point_engine(self, timesteps):
+        """(Re)load the trajectory context with the spaces' current length scales and the given timestep values."""
         K = (self.ssp_dim - 1) // 2
         a_t = self.ssp_t_space.phase_matrix[1:K + 1, 0]
         ls_t = float(np.ravel(self.ssp_t_space.length_scale)[0])
-        tau = timesteps * (a_t / ls_t)[None, :]                       # (L, K) radians
-        self._traj_engine = DeviceEngine(self.ssp_x_space._device)
+        tau = np.asarray(timesteps, dtype=np.float64).reshape(-1, 1) * (a_t / ls_t)[None, :]     # (L, K) radians
         self._traj_engine.set_space(self.ssp_x_space.phase_matrix, self.ssp_x_space.length_scale)
         self._traj_engine.set_traj(tau, self.traj_len)
+
+    def _cv_loss(self, length_scale, xs, ys):
+        """Objective of the length-scale search at (ls_x, ls_t) (ssp_traj_agent.py:117-137): negative predictive
+        log-likelihood summed over min(n, 50) contiguous folds, each with a fresh BLR (alpha = 0.01, beta = 1 / var(train
+        targets)), timestep SSPs at linspace(0, L, L).  Encode + Gram matrix on the device, folds in dual form."""
+        ls = np.ravel(length_scale)
+        self.ssp_x_space.update_lengthscale(ls[0])
+        self.ssp_t_space.update_lengthscale(ls[1])
+        self._point_engine(np.linspace(0, self.traj_len, self.traj_len))
+        eng = self._traj_engine
+        G = eng.gram(eng.encode_device(xs)).cpu().numpy()
+        ys = np.asarray(ys, dtype=np.float64).reshape(-1)
+        n, alpha = ys.shape[0], 0.01
+        n_splits = min(n, 50)
+        sizes = np.full(n_splits, n // n_splits, dtype=int)
+        sizes[:n % n_splits] += 1
+        total, start, idx = 0.0, 0, np.arange(n)
+        for sz in sizes:                                              # KFold without shuffling
+            te = idx[start:start + sz]
+            tr = np.concatenate([idx[:start], idx[start + sz:]])
+            start += sz
+            t = ys[tr]
+            beta = 1.0 / np.var(t) if len(t) > 1 else 1.0 / np.abs(t[0])   # blr.py:54-59
+            A = G[np.ix_(tr, tr)] + (alpha / beta) * np.eye(len(tr))
+            k = G[np.ix_(te, tr)]
+            sol = np.linalg.solve(A, np.column_stack([t, k.T]))
+            mu = k @ sol[:, 0]
+            var = 1.0 / beta + (G[te, te] - np.sum(k * sol[:, 1:].T, axis=1)) / alpha
+            diff = ys[te] - mu
+            total += np.sum(0.5 * np.log(var) + diff ** 2 / var)
+        return total
+
+    def _optimize_lengthscale(self, init_trajs, init_ys):
+        from scipy.optimize import minimize
+        xs = np.ascontiguousarray(np.atleast_2d(init_trajs), dtype=np.float64)
+        low = 1 / np.sqrt(xs.shape[0])
+        retval = minimize(lambda ls: self._cv_loss(ls, xs, init_ys), x0=np.array([4., 10.]), method='L-BFGS-B',
+                          bounds=[(low, None), (low, None)])
+        return np.abs(retval.x)
 
     def _scoring_engine(self):
         return self._traj_engine

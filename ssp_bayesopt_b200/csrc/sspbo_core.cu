@@ -860,6 +860,22 @@ __global__ void k_bind(const double* __restrict__ a, int qa, const double* __res
 }
 
 // =====================================================================================
+// Gram matrix G = Phi Phi^T of n encoded rows (float64): the only O(d) work of the K-fold length-scale search
+// (agents/ssp_traj_agent.py:113-143) once every fold's BLR is written in its dual form
+// =====================================================================================
+__global__ void k_gram(const double* __restrict__ phi, int n, int d, double* __restrict__ G) {
+    __shared__ double red[32];
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j > i) return;
+    const double* a = phi + (size_t)i * d;
+    const double* b = phi + (size_t)j * d;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) acc = fma(a[k], b[k], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) { G[(size_t)i * n + j] = acc; G[(size_t)j * n + i] = acc; }
+}
+
+// =====================================================================================
 // candidate generators
 // =====================================================================================
 __global__ void k_fill_uniform(uint64_t seed, int64_t first_elem, int64_t count, float* __restrict__ out) {
@@ -1706,6 +1722,17 @@ extern "C" int sspbo_bind(sspbo_ctx* ctx, const double* a, int qa, const double*
     size_t smem = 2 * (size_t)d * sizeof(double);
     SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_bind, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_bind<<<dim3((d + 255) / 256, q), 256, smem, (cudaStream_t)stream>>>(a, qa, b, qb, d, out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_gram(sspbo_ctx* ctx, const double* phi, int n, double* gram_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->d < 1) SSPBO_FAIL(ctx, SSPBO_ESTATE, "gram before space_set / blr_init_dim");
+    if (n < 0 || n > 65535 || (n > 0 && (!phi || !gram_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "gram: need 0 <= n <= 65535 rows");
+    if (n == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_gram<<<dim3(n, n), 128, 0, (cudaStream_t)stream>>>(phi, n, ctx->d, gram_out);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }

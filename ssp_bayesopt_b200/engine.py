@@ -431,6 +431,15 @@ class DeviceEngine:
         self._check(rc, "sspbo_decode_optim")
         return out
 
+    def gram(self, phi):
+        """G = phi phi^T (n, n) float64 device tensor for n encoded rows (n, d)."""
+        pt = self.to_device(phi, self.torch.float64)
+        assert pt.dim() == 2 and pt.shape[1] == self.d, f"Expected (n, {self.d}) rows, got {tuple(pt.shape)}"
+        out = self.torch.empty((pt.shape[0], pt.shape[0]), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_gram(self._ctx, C.c_void_p(pt.data_ptr()), pt.shape[0], C.c_void_p(out.data_ptr()), self._stream())
+        self._check(rc, "sspbo_gram")
+        return out
+
     # ------------------------------------------------------------------ K6
     def acq_ascent(self, phi0, lam, gamma_t, margin=4.0, max_iter=200, tol=1e-7):
         """Maximise the acquisition in phi-space from the rows of phi0 (R, d), all restarts in one cooperative kernel.

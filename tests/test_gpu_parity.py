@@ -707,6 +707,36 @@ def test_multi_agent_tcgen05_and_driver(pkg):
     assert opt.xs.shape == (17, L * n_agents * xd) and np.all(np.abs(opt.xs) <= 2)
 
 
+def test_trajectory_lengthscale_search(pkg, golden):
+    """Omitted `length_scale`: the K-fold search of ssp_traj_agent.py:113-143 with the encode and
+    the Gram matrix on the device.  Objective against every evaluation recorded inside the live reference; result against
+    the reference's (the valley is flat along the time length scale, so the optimum is compared through the objective)."""
+    g = golden("lengthscale_cv.npz")
+    rng = np.random.default_rng(3)
+    eng = pkg.DeviceEngine()
+    sp = pkg.RandomSSPSpace(2, ssp_dim=64, domain_bounds=g["bounds"], length_scale=1.0, rng=0)
+    phi = sp.encode(rng.uniform(-2, 2, (9, 2)))
+    np.testing.assert_allclose(sp.engine.gram(phi).cpu().numpy(), phi @ phi.T, rtol=0, atol=1e-14)
+    agt = pkg.SSPTrajectoryAgent(g["trajs"], g["tys"], x_dim=2, traj_len=4, ssp_dim=51, domain_bounds=g["bounds"],
+                                 decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    found = np.array([np.ravel(agt.ssp_x_space.length_scale)[0], np.ravel(agt.ssp_t_space.length_scale)[0]])
+    assert np.array_equal(agt.ssp_x_space.phase_matrix, g["Ax"]) and np.array_equal(agt.ssp_t_space.phase_matrix, g["At"])
+    for x, f in list(zip(g["eval_x"], g["eval_f"]))[::5]:
+        np.testing.assert_allclose(agt._cv_loss(x, g["trajs"], g["tys"]), f, rtol=1e-9)
+    f_found = agt._cv_loss(found, g["trajs"], g["tys"])
+    f_ref = agt._cv_loss(g["result"], g["trajs"], g["tys"])
+    np.testing.assert_allclose(f_ref, g["eval_f"].min(), rtol=1e-9)
+    assert f_found <= f_ref + 2e-3 * abs(f_ref)
+    np.testing.assert_allclose(found[0], g["result"][0], rtol=0.1)
+    assert found[1] > 50.0                                             # flat direction: any large time length scale
+    # the agent is usable afterwards with the length scales it found (engine re-pointed at timesteps 1 .. L+1)
+    agt.ssp_x_space.update_lengthscale(found[0]); agt.ssp_t_space.update_lengthscale(found[1])
+    agt._point_engine(np.linspace(1, 5, 4))
+    T = orc.traj_timestep_ssps(g["At"], np.array([found[1]]), 4)
+    want = orc.traj_encode(g["Ax"], found[0] * np.ones(2), T, g["trajs"][:3], 4, 2)
+    np.testing.assert_allclose(agt.encode(g["trajs"][:3]), want, atol=5e-13)
+
+
 # ------------------------------------------------------------------------------------------ generators, driver
 def test_fill_uniform_bit_exact(pkg):
     eng = pkg.DeviceEngine()

@@ -178,6 +178,18 @@ def test_multi_agent_matches_reference(golden, tag):
     assert np.array_equal(dec, g[f"{tag}_decoded"])
 
 
+def test_lengthscale_cv_objective_matches_reference(golden):
+    """oracle.traj_lengthscale_cv_loss against every objective evaluation scipy's L-BFGS-B made inside the live reference's
+    SSPTrajectoryAgent._optimize_lengthscale (ssp_traj_agent.py:113-143), recorded by oracle/gen_golden.py."""
+    g = golden("lengthscale_cv.npz")
+    assert len(g["eval_f"]) > 50
+    for x, f in list(zip(g["eval_x"], g["eval_f"]))[::7]:
+        v = orc.traj_lengthscale_cv_loss(g["Ax"], g["At"], x, g["trajs"], g["tys"], 4, 2)
+        np.testing.assert_allclose(v, f, rtol=1e-11)
+    folds = list(orc.kfold_indices(14, 5))
+    assert [len(te) for _, te in folds] == [3, 3, 3, 3, 2] and np.array_equal(folds[1][1], [3, 4, 5])
+
+
 def test_counter_uniform_is_range_consistent():
     a = orc.counter_uniform(0, 0, 1000, 6)
     b = orc.counter_uniform(0, 400, 100, 6)
