@@ -136,6 +136,15 @@ int sspbo_score(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, int64
  * sspbo_score again).  Any pointer may be NULL. */
 int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t* overflow, int64_t* out_of_range,
                       int* rerun, int reset, void* stream);
+/* sspbo_score_stats plus the read-back of the packed key in the same synchronisation (the one host wait of a selection
+ * step): *key_host = *key_dev.  key_dev / key_host may both be NULL (then this is sspbo_score_stats). */
+int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_dev, unsigned long long* key_host, int64_t* scored,
+                       int64_t* flagged, int64_t* overflow, int64_t* out_of_range, int* rerun, int reset, void* stream);
+/* SSPAgent.eval (agents/ssp_agent.py:125-137) for N <= 64 HOST points (x_t of a BO step): x_host N x (n*L) float64;
+ * mu/var/acq_host N float64 each (float32 precision, like sspbo_score).  Exact float64 engine; one pinned upload, one
+ * pinned read-back, one synchronisation. */
+int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, double lam, double gamma_t, double* mu_host,
+                    double* var_host, double* acq_host, void* stream);
 /* state of the low-rank form: rows of V appended since blr_init, whether it is usable, policy switches */
 int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, int* disabled, int* phase32);
 /* policy overrides: lowrank_enabled 1 = enable, 0 = disable, -1 = leave (SSPBO_ENGINE_AUTO); phase32_enabled selects the

@@ -33,6 +33,9 @@ SIGNATURES = {
     "sspbo_space_dims": (_i, [_vp, _pi, _pi, _pi, _pi]),
     "sspbo_space_set_xbound": (_i, [_vp, _d]),
     "sspbo_score_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _pi, _i, _vp]),
+    "sspbo_score_finish": (_i, [_vp, _vp, C.POINTER(_u64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                _pi, _i, _vp]),
+    "sspbo_eval_host": (_i, [_vp, _pd, _i, _d, _d, _pd, _pd, _pd, _vp]),
     "sspbo_lowrank_info": (_i, [_vp, _pi, _pi, _pi, _pi]),
     "sspbo_set_policy": (_i, [_vp, _i, _i]),
     "sspbo_encode": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),

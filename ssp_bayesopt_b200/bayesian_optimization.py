@@ -171,8 +171,9 @@ class BayesianOptimization:
         if key is None:
             eng._best.zero_()
             key = eng._best
-        eng.settle()                                   # local key final before it is combined across ranks
-        dist.allreduce_best(key)
+        if dist.is_distributed():
+            eng.settle()                               # local key final before it is combined across ranks
+            dist.allreduce_best(key)
         score, gidx = eng.best()
         if cand.get('lookup') is not None:             # every rank can name the winning row without touching the device
             return score, gidx, np.asarray(cand['lookup'](gidx), dtype=np.float64).reshape(1, -1)

@@ -954,6 +954,8 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
     dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     dev_free(&ctx->aa_work);
+    if (ctx->eval_dev) cudaFree(ctx->eval_dev);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
     delete ctx;
 }
 
@@ -1328,8 +1330,25 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
     const int d = ctx->d, K = ctx->K;
     const double beta = ctx->beta;
     dim3 g1((d + 255) / 256, d);
+    bool m_current = false;                              // m, m' already refreshed by the last fused launch
     for (int i = 0; i < k; ++i) {
         const double* phi = phis + (size_t)i * d;
+        if (!ctx->unfused_update) {                      // one cooperative launch per observation
+            __half *vh = nullptr, *vl = nullptr; double* vd = nullptr;
+            bool append = false;
+            if (ctx->has_factor && ctx->lr_valid) {
+                if (ctx->lr_rank >= SSPBO_LR_MAX) ctx->lr_valid = false;
+                else {
+                    const size_t off = (size_t)(ctx->lr_rank + 1) * ctx->KC_pad;
+                    vh = ctx->Vh + off; vl = ctx->Vl + off; vd = ctx->Vd + (size_t)ctx->lr_rank * d; append = true;
+                }
+            }
+            const int rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd, st);
+            if (rc == SSPBO_OK) { if (append) ctx->lr_rank++; m_current = (i == k - 1); continue; }
+            if (rc != SSPBO_EUNSUPPORTED) return rc;
+            // nothing was written: fall through to the unfused kernels, for this and every later observation
+            ctx->unfused_update = true;
+        }
         // --- phi-space posterior, blr.py:60-70 ---
         k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, phi, ctx->v, d);                       // v = S phi
         SSPBO_LAUNCH_CHECK(ctx);
@@ -1366,11 +1385,15 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         SSPBO_LAUNCH_CHECK(ctx);
     }
     if (k > 0) {
-        k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, ctx->b, ctx->m, d);                     // m = S b  (blr.py:75)
-        SSPBO_LAUNCH_CHECK(ctx);
-        if (ctx->has_factor) {
-            k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
+        if (!m_current) {
+            k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, ctx->b, ctx->m, d);                 // m = S b  (blr.py:75)
             SSPBO_LAUNCH_CHECK(ctx);
+        }
+        if (ctx->has_factor) {
+            if (!m_current) {
+                k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
+                SSPBO_LAUNCH_CHECK(ctx);
+            }
             k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
             SSPBO_LAUNCH_CHECK(ctx);
         }
@@ -1608,18 +1631,42 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
  * than 1 % of the scored candidates needed the exact pass (or the flag list overflowed) the AUTO engine switches to the
  * full factor; candidates outside the declared |x| bound switch the generator to the 64-bit phase path.  *rerun is set
  * when the results accumulated since the last reset must be recomputed (overflow or out-of-range candidates). */
+// pinned host staging for the small synchronous read-backs / uploads of a BO step (key + counters, eval of x_t)
+static int host_stage(sspbo_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pin_bytes) return SSPBO_OK;
+    if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; ctx->pin_bytes = 0; }
+    SSPBO_CUDA(ctx, cudaMallocHost(&ctx->pin, bytes));
+    ctx->pin_bytes = bytes;
+    return SSPBO_OK;
+}
+
 extern "C" int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t* overflow, int64_t* out_of_range,
                                  int* rerun, int reset, void* stream) {
+    return sspbo_score_finish(ctx, nullptr, nullptr, scored, flagged, overflow, out_of_range, rerun, reset, stream);
+}
+
+extern "C" int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_dev, unsigned long long* key_host,
+                                  int64_t* scored, int64_t* flagged, int64_t* overflow, int64_t* out_of_range, int* rerun,
+                                  int reset, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
     if (scored) *scored = 0; if (flagged) *flagged = 0; if (overflow) *overflow = 0; if (out_of_range) *out_of_range = 0;
     if (rerun) *rerun = 0;
-    if (!ctx->stats) return SSPBO_OK;
+    if ((key_dev == nullptr) != (key_host == nullptr)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_finish: key_dev and key_host go together");
+    if (!ctx->stats && !key_dev) return SSPBO_OK;
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long h[SSPBO_STAT_COUNT];
-    SSPBO_CUDA(ctx, cudaMemcpyAsync(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost, st));
-    SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
-    if (reset) SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, sizeof(h), st));
+    int rc = host_stage(ctx, 4096);
+    if (rc) return rc;
+    unsigned long long* h = (unsigned long long*)ctx->pin;          // [0, STAT_COUNT): counters, [STAT_COUNT]: key
+    for (int i = 0; i <= SSPBO_STAT_COUNT; ++i) h[i] = 0ull;
+    if (ctx->stats)
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(h, ctx->stats, SSPBO_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (key_dev)
+        SSPBO_CUDA(ctx, cudaMemcpyAsync(h + SSPBO_STAT_COUNT, key_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SSPBO_CUDA(ctx, cudaStreamSynchronize(st));                     // the one synchronisation of a selection step
+    if (key_host) *key_host = h[SSPBO_STAT_COUNT];
+    if (!ctx->stats) return SSPBO_OK;
+    if (reset) SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, SSPBO_STAT_COUNT * sizeof(unsigned long long), st));
     if (scored) *scored = (int64_t)h[SSPBO_STAT_SCORED];
     if (flagged) *flagged = (int64_t)h[SSPBO_STAT_FLAGGED];
     if (overflow) *overflow = (int64_t)h[SSPBO_STAT_OVERFLOW];
@@ -1628,6 +1675,38 @@ extern "C" int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagg
         ctx->lr_disabled = true;
     if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
     if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0) ? 1 : 0;
+    return SSPBO_OK;
+}
+
+/* SSPAgent.eval (agents/ssp_agent.py:125-137) for a handful of HOST points, e.g. x_t of a BO step: one pinned upload, the
+ * exact float64 engine, one pinned read-back, one synchronisation. */
+extern "C" int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, double lam, double gamma_t, double* mu_host,
+                               double* var_host, double* acq_host, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready || !ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "eval_host: BLR posterior (and beta) must be set first");
+    if (N < 0 || N > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "eval_host: 0 <= N <= 64 (larger sets go through sspbo_score)");
+    if (N > 0 && (!x_host || !mu_host || !var_host || !acq_host)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "eval_host: null pointer");
+    if (!(gamma_t >= 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "eval_host: gamma_t must be >= 0");
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nl = (size_t)ctx->n * ctx->L;
+    const size_t xb = 64 * nl * sizeof(double), ob = 3 * 64 * sizeof(float);
+    int rc = host_stage(ctx, xb + ob > 4096 ? xb + ob : 4096);
+    if (rc) return rc;
+    if (!ctx->eval_dev) SSPBO_CUDA(ctx, cudaMalloc(&ctx->eval_dev, 64 * 16 * 64 * sizeof(double) + ob));   // n <= 16, L <= 64
+    double* xd = (double*)ctx->eval_dev;
+    float* od = (float*)((char*)ctx->eval_dev + 64 * 16 * 64 * sizeof(double));
+    double* xp = (double*)ctx->pin;
+    float* op = (float*)((char*)ctx->pin + xb);
+    memcpy(xp, x_host, (size_t)N * nl * sizeof(double));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(xd, xp, (size_t)N * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    ctx->last_engine = SSPBO_ENGINE_EXACT;
+    rc = sspbo_score_exact_launch(ctx, xd, SSPBO_F64, N, false, 0, lam, gamma_t, od, od + 64, od + 128, nullptr, st);
+    if (rc) return rc;
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(op, od, ob, cudaMemcpyDeviceToHost, st));
+    SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < N; ++i) { mu_host[i] = op[i]; var_host[i] = op[64 + i]; acq_host[i] = op[128 + i]; }
     return SSPBO_OK;
 }
 

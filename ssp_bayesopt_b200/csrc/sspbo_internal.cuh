@@ -95,6 +95,10 @@ struct sspbo_ctx {
     // waypoint sums (L > 1): value of the DC component (L, or sum of the +-1 DC signs of bound tags) and whether phi is
     // divided by its norm (multi-agent trajectories, agents/ssp_multi_agent.py:166-186)
     double dc = 1.0; bool normalize = false;
+    bool unfused_update = false;     // posterior updates go through the separate kernels of sspbo_core.cu
+    int fused_update_ok = -1;        // cooperative single-launch posterior update usable on this device (-1: not probed)
+    // pinned host staging and device staging of the small synchronous transfers of a BO step (sspbo_score_finish, sspbo_eval_host)
+    void* pin = nullptr; size_t pin_bytes = 0; void* eval_dev = nullptr;
     // workspace of the phi-space acquisition ascent (sspbo_ascent.cu): Y = S Phi and per-CTA partial sums, double-buffered
     double* aa_work = nullptr; size_t aa_cap = 0;
     // opaque state of the tcgen05 engines (tensor maps etc.)
@@ -185,6 +189,9 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
                             float gamma_t, float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_umma_release(sspbo_ctx* ctx);
 int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st);
+// one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
+int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
+                           double* vd_row, cudaStream_t st);
 // low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);
 int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,

@@ -258,6 +258,17 @@ class DeviceEngine:
     def eval_host(self, x, lam, gamma_t, engine=_lib.ENGINE_AUTO):
         """(mu, var, acq) as float64 numpy arrays with a single device->host copy (SSPAgent.eval)."""
         torch = self.torch
+        if isinstance(x, np.ndarray) and engine in (_lib.ENGINE_AUTO, _lib.ENGINE_EXACT):
+            xh = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+            if 0 < xh.shape[0] <= 64:                     # x_t of a BO step: one C call, one synchronisation
+                if xh.shape[1] != self.n * self.L:
+                    raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xh.shape)}")
+                out = np.empty((3, xh.shape[0]), dtype=np.float64)
+                rc = self.lib.sspbo_eval_host(self._ctx, xh.ctypes.data_as(_lib._pd), xh.shape[0], float(lam), float(gamma_t),
+                                              out[0].ctypes.data_as(_lib._pd), out[1].ctypes.data_as(_lib._pd),
+                                              out[2].ctypes.data_as(_lib._pd), self._stream())
+                self._check(rc, "sspbo_eval_host")
+                return out[0], out[1], out[2]
         xt = self.to_device(x)
         if xt.dim() == 1:
             xt = xt.reshape(1, -1)
@@ -387,8 +398,21 @@ class DeviceEngine:
     def best(self):
         """(score, index) of the packed key; synchronises.  If the low-rank pass overflowed its flag list or saw
         candidates outside the declared bound, the step is recomputed with the safe engines first."""
-        self.settle()
-        return _lib.key_unpack(int(self._best.item()))
+        st, key = self._finish()                          # counters of the low-rank pass and the key in one synchronisation
+        if self._pending and self._lr_used and st["rerun"]:
+            self._replay()
+            _, key = self._finish()
+        self._pending = []
+        return _lib.key_unpack(key)
+
+    def _finish(self):
+        v = [C.c_int64() for _ in range(4)]
+        rr, key = C.c_int(), C.c_uint64()
+        rc = self.lib.sspbo_score_finish(self._ctx, C.c_void_p(self._best.data_ptr()), C.byref(key), C.byref(v[0]),
+                                         C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), C.byref(rr), 1, self._stream())
+        self._check(rc, "sspbo_score_finish")
+        return dict(scored=v[0].value, flagged=v[1].value, overflow=v[2].value, out_of_range=v[3].value,
+                    rerun=bool(rr.value)), int(key.value)
 
     def last_engine(self) -> str:
         return _lib.ENGINE_NAMES.get(self.lib.sspbo_last_engine(self._ctx), "?")
