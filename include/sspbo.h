@@ -106,6 +106,13 @@ int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_set);
 /* blr.py:60-77: S_inv += beta Phi^T Phi; for each row: Sherman-Morrison on S; m = S b.
  * phis_dev: k x d float64 (device); ts_host: k float64 (host). */
 int sspbo_blr_update(sspbo_ctx* ctx, const double* phis_dev, const double* ts_host, int k, void* stream);
+/* SSPAgent.update (agents/ssp_agent.py:187-206) for k <= 64 HOST points: x_host k x (n*L) float64 is staged through pinned
+ * memory, encoded on the device (K1) and applied as k sequential observations (K3); asynchronous. */
+int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const double* ts_host, int k, void* stream);
+/* One BO observation for one HOST point x_t: (*mu_host, *var_host) = BLR predictive mean / variance at phi(x_t) under the
+ * CURRENT posterior (what SSPAgent.eval returns, agents/ssp_agent.py:133-135, float64), then the posterior update with
+ * target t (SSPAgent.update, :187-206).  Both come out of the same cooperative update launch; synchronises once. */
+int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, double* mu_host, double* var_host, void* stream);
 /* copies of the posterior (attributes BLR.m (d), BLR.S (d x d), BLR.S_inv (d x d)); any pointer may be NULL */
 int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev, void* stream);
 /* device-to-device adoption of a replicated posterior (multi-GPU broadcast target):

@@ -46,6 +46,8 @@ SIGNATURES = {
     "sspbo_blr_set_beta": (_i, [_vp, _d]),
     "sspbo_blr_get_beta": (_i, [_vp, _pd, _pi]),
     "sspbo_blr_update": (_i, [_vp, _vp, _pd, _i, _vp]),
+    "sspbo_blr_update_x": (_i, [_vp, _pd, _pd, _i, _vp]),
+    "sspbo_observe": (_i, [_vp, _pd, _d, _pd, _pd, _vp]),
     "sspbo_blr_get": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sspbo_blr_export_size": (_i64, [_vp]),
     "sspbo_blr_export": (_i, [_vp, _vp, _vp]),

@@ -143,14 +143,30 @@ class SSPAgent(Agent):
         b = np.asarray(self.ssp_space.domain_bounds, dtype=np.float64)
         return rng.uniform(b[:, 0], b[:, 1], size=(count, b.shape[0]))
 
+    def observe(self, x_t: np.ndarray, y_t: np.ndarray, step_num=0):
+        """`eval(x_t)` followed by `update(x_t, y_t, var_t, step_num)` for ONE point, as `maximize` calls them back to back
+        (bayesian_optimization.py:299-303): the predictive mean / variance come out of the update launch itself, so the
+        pair costs one device round trip.  Returns what eval returns: mu (1, 1), var (1,), acq (1,)."""
+        x_val = np.asarray(x_t, dtype=np.float64).reshape(1, -1)
+        t = float(np.ravel(y_t)[0])
+        lam, gamma = self.var_weight, self._gamma()
+        mu, var = self._scoring_engine().observe(x_val, t)
+        var_t = np.array([var])
+        acq = lam * (np.sqrt(var_t + gamma) - np.sqrt(gamma))                 # ssp_agent.py:136, with the pre-update lambda, gamma
+        self._step_scalars(var_t, step_num)
+        return np.array([[mu]]), var_t, acq
+
     def update(self, x_t: np.ndarray, y_t: np.ndarray, sigma_t: float, step_num=0):
         x_val, y_val = x_t, y_t
         if len(x_t.shape) < 2:
             x_val = x_t.reshape(1, x_t.shape[0])
             y_val = y_t.reshape(1, y_t.shape[0])
-        phi = self._encode_device(x_val)                   # stays on the device: no host round trip of phi
-        self.blr.update(phi, y_val)
+        x_val = np.asarray(x_val, dtype=np.float64)
+        self.blr.update_points(x_val.reshape(x_val.shape[0], -1), y_val)   # encoded on the device: phi never visits the host
+        self._step_scalars(sigma_t, step_num)
 
+    def _step_scalars(self, sigma_t, step_num):
+        """lambda += var_decay ; gamma_t += gamma_c * sigma_t (ssp_agent.py:208-218)."""
         if isinstance(self.var_decay, (int, float)):
             self.var_weight = self.var_weight + self.var_decay
         elif callable(self.var_decay):

@@ -243,12 +243,11 @@ class BayesianOptimization:
                 td.broadcast(yb, src=0)
                 y_t = yb.cpu().numpy()
 
-            mu_t, var_t, phi_t = agt.eval(x_t)
+            update_start = time.perf_counter_ns()
+            # eval(x_t) under the current posterior, then update(x_t, y_t, var_t) (:299-303): one device round trip
+            mu_t, var_t, phi_t = agt.observe(x_t, y_t, step_num=t + n0)
             if self.verbose and rank == 0:
                 print(f'| step {t + n0}\t | {y_t}, {np.sqrt(var_t)}, {phi_t}\t ')
-            update_start = time.perf_counter_ns()
-            agt.update(x_t, y_t, var_t, step_num=t + n0)
-            agt._scoring_engine().torch.cuda.synchronize()
             self.times[t] += time.perf_counter_ns() - update_start
             self.full_times[t] = time.perf_counter_ns() - start
 

@@ -62,6 +62,18 @@ class BayesianLinearRegression:
             self.engine.blr_set_beta(float(np.ravel(self.beta)[0]))
         self.engine.blr_update(phis, ts)
 
+    def update_points(self, xs: np.ndarray, ts: np.ndarray):
+        """update(encode(xs), ts) for host points of the engine's SSP space without materialising phi on the host (the
+        device encodes them): SSPAgent.update's path.  xs (n, data_dim) float64, ts (n, 1)."""
+        ts = np.asarray(ts, dtype=np.float64)
+        assert len(ts.shape) > 1 and ts.shape[1] == self.output_dim, (
+            f'Expected output shape ({xs.shape[0]}, 1), got {ts.shape}')
+        if self.beta is None:                   # blr.py:54-59
+            var_ts = np.var(ts) if len(ts) > 1 else np.abs(np.copy(ts[0]))
+            self.beta = 1. / var_ts
+            self.engine.blr_set_beta(float(np.ravel(self.beta)[0]))
+        self.engine.blr_update_points(xs, ts)
+
     def predict(self, phi: np.ndarray):
         """mu (1, n), var (n,) for explicit features phi (n, input_dim) (blr.py:84-97)."""
         if self.beta is None:

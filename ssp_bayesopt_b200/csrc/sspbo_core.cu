@@ -955,6 +955,8 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     dev_free(&ctx->aa_work);
     if (ctx->eval_dev) cudaFree(ctx->eval_dev);
+    if (ctx->obs_pin) { cudaFreeHost(ctx->obs_pin); cudaFree(ctx->obs_x); cudaEventDestroy(ctx->obs_event); }
+    dev_free(&ctx->obs_phi); dev_free(&ctx->obs_out);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     delete ctx;
 }
@@ -1343,7 +1345,8 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     vh = ctx->Vh + off; vl = ctx->Vl + off; vd = ctx->Vd + (size_t)ctx->lr_rank * d; append = true;
                 }
             }
-            const int rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd, st);
+            const int rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd,
+                                                  (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr, st);
             if (rc == SSPBO_OK) { if (append) ctx->lr_rank++; m_current = (i == k - 1); continue; }
             if (rc != SSPBO_EUNSUPPORTED) return rc;
             // nothing was written: fall through to the unfused kernels, for this and every later observation
@@ -1707,6 +1710,65 @@ extern "C" int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, doub
     SSPBO_CUDA(ctx, cudaMemcpyAsync(op, od, ob, cudaMemcpyDeviceToHost, st));
     SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
     for (int i = 0; i < N; ++i) { mu_host[i] = op[i]; var_host[i] = op[64 + i]; acq_host[i] = op[128 + i]; }
+    return SSPBO_OK;
+}
+
+/* SSPAgent.update (agents/ssp_agent.py:187-206) for HOST points: encode x_t on the device and apply the posterior update,
+ * in one call and without a synchronisation (x is staged through pinned memory guarded by an event). */
+extern "C" int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const double* ts_host, int k, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_update_x needs an SSP space");
+    if (!ctx->blr_ready || !ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_update_x before blr_init / blr_set_beta");
+    if (k < 0 || k > 64 || (k > 0 && (!x_host || !ts_host))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "blr_update_x: 0 <= k <= 64 points");
+    if (k == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nl = (size_t)ctx->n * ctx->L;
+    if (!ctx->obs_pin) {
+        SSPBO_CUDA(ctx, cudaMallocHost(&ctx->obs_pin, 64 * 16 * 64 * sizeof(double)));
+        SSPBO_CUDA(ctx, cudaMalloc(&ctx->obs_x, 64 * 16 * 64 * sizeof(double)));
+        SSPBO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->obs_event, cudaEventDisableTiming));
+    } else SSPBO_CUDA(ctx, cudaEventSynchronize(ctx->obs_event));       // the previous upload has left the pinned buffer
+    if ((size_t)k * ctx->d > ctx->obs_phi_cap) {
+        if (ctx->obs_phi) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->obs_phi); ctx->obs_phi = nullptr; ctx->obs_phi_cap = 0; }
+        SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->obs_phi, (size_t)64 * ctx->d * sizeof(double)));
+        ctx->obs_phi_cap = (size_t)64 * ctx->d;
+    }
+    memcpy(ctx->obs_pin, x_host, (size_t)k * nl * sizeof(double));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->obs_x, ctx->obs_pin, (size_t)k * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    SSPBO_CUDA(ctx, cudaEventRecord(ctx->obs_event, st));
+    int rc = sspbo_encode(ctx, ctx->obs_x, SSPBO_F64, k, ctx->obs_phi, stream);
+    if (rc) return rc;
+    return sspbo_blr_update(ctx, ctx->obs_phi, ts_host, k, stream);
+}
+
+/* One BO observation: SSPAgent.eval(x_t) (agents/ssp_agent.py:125-137) under the current posterior followed by
+ * SSPAgent.update(x_t, y_t) (:187-206), for one HOST point.  The predictive mean and variance fall out of the update
+ * kernel (mu = m . phi, var = 1/beta + phi^T S phi with v = S phi already formed), so the pair costs one upload, the
+ * encode, one cooperative launch and ONE synchronising read-back of two float64 values. */
+extern "C" int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, double* mu_host, double* var_host, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!x_host || !mu_host || !var_host) SSPBO_FAIL(ctx, SSPBO_EINVAL, "observe: null pointer");
+    if (ctx->K == 0 || !ctx->blr_ready || !ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "observe needs a space and a posterior with beta");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (ctx->unfused_update || ctx->fused_update_ok <= 0) {   // fused kernel unavailable (or not probed yet): the two calls it replaces
+        double acq;
+        if ((rc = sspbo_eval_host(ctx, x_host, 1, 0.0, 0.0, mu_host, var_host, &acq, stream))) return rc;
+        return sspbo_blr_update_x(ctx, x_host, &t, 1, stream);
+    }
+    if (!ctx->obs_out) SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->obs_out, 2 * sizeof(double)));
+    if ((rc = host_stage(ctx, 4096))) return rc;
+    ctx->want_obs = true;
+    rc = sspbo_blr_update_x(ctx, x_host, &t, 1, stream);
+    ctx->want_obs = false;
+    if (rc) return rc;
+    if (ctx->unfused_update) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "observe: fused update unavailable; state was updated, call again for eval");
+    double* h = (double*)ctx->pin + 64;                   // clear of the words sspbo_score_finish uses
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(h, ctx->obs_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+    *mu_host = h[0]; *var_host = h[1];
     return SSPBO_OK;
 }
 

@@ -95,6 +95,10 @@ struct sspbo_ctx {
     // waypoint sums (L > 1): value of the DC component (L, or sum of the +-1 DC signs of bound tags) and whether phi is
     // divided by its norm (multi-agent trajectories, agents/ssp_multi_agent.py:166-186)
     double dc = 1.0; bool normalize = false;
+    // staging of sspbo_blr_update_x: pinned x, device x, device phi rows, event guarding the pinned buffer
+    void* obs_pin = nullptr; void* obs_x = nullptr; double* obs_phi = nullptr; size_t obs_phi_cap = 0; cudaEvent_t obs_event = nullptr;
+    double* obs_out = nullptr;       // device: predictive (mu, var) at the observed point before the update (sspbo_observe)
+    bool want_obs = false;
     bool unfused_update = false;     // posterior updates go through the separate kernels of sspbo_core.cu
     int fused_update_ok = -1;        // cooperative single-launch posterior update usable on this device (-1: not probed)
     // pinned host staging and device staging of the small synchronous transfers of a BO step (sspbo_score_finish, sspbo_eval_host)
@@ -191,7 +195,7 @@ void sspbo_umma_release(sspbo_ctx* ctx);
 int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st);
 // one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
-                           double* vd_row, cudaStream_t st);
+                           double* vd_row, double* obs_out, cudaStream_t st);
 // low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);
 int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,

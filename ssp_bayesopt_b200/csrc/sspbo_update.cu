@@ -32,6 +32,7 @@ struct UpdateParams {
     const double2* twiddle; const int* inv_perm; const int* col_of_rank;
     double *v, *psi, *y;                   // global scratch d-vectors
     __half *vh_row, *vl_row; double* vd_row;   // row of V to append (nullptr: none)
+    double* obs_out;                       // nullable: [0] = m . phi, [1] = 1/beta + phi^T S phi under the posterior BEFORE this update
 };
 
 __device__ __forceinline__ double up_warp_sum(double v) {
@@ -94,6 +95,13 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         bp[j] = fma(p.beta * p.t, f, p.b[j]);                           // blr.py:70: b += beta t phi (read before any CTA writes b)
     }
     __syncthreads();
+    if (p.obs_out && blockIdx.x == 0) {                                  // predictive mean at phi under the old posterior
+        double mu[1] = {0.0};
+        for (int j = tid; j < d; j += UP_THREADS) mu[0] = fma(p.m[j], phi[j], mu[0]);
+        up_block_reduce<1>(mu, red, tot);
+        if (tid == 0) p.obs_out[0] = tot[0];
+        __syncthreads();
+    }
 
     // ---- P0: psi (rank order) and v = S phi ----
     if (p.has_factor)
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
     up_block_reduce<4>(part, red, tot);
     const double coef = p.beta / (1.0 + p.beta * tot[0]);               // blr.py:64-67 (Sherman-Morrison)
     const double coef2 = p.beta / (1.0 + p.beta * tot[1]);
+    if (p.obs_out && blockIdx.x == 0 && tid == 0) p.obs_out[1] = 1.0 / p.beta + tot[0];   // blr.py:96 before the update
     __syncthreads();                                                    // everyone has read psi from vec
     for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.v + j);
     __syncthreads();
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
 // One observation.  Returns SSPBO_EUNSUPPORTED (without touching the state) when the device cannot run it; the caller then
 // falls back to the unfused kernels.
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
-                           double* vd_row, cudaStream_t st) {
+                           double* vd_row, double* obs_out, cudaStream_t st) {
     const int d = ctx->d;
     const size_t smem = ((size_t)4 * d + UP_WARPS * 4 + 4) * sizeof(double);
     if (ctx->fused_update_ok < 0) {                       // probe once
@@ -213,7 +222,7 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
     p.phi = phi; p.S = ctx->S; p.Sinv = ctx->Sinv; p.b = ctx->b; p.m = ctx->m; p.Sp = ctx->Sp; p.mp = ctx->mp;
     p.twiddle = ctx->twiddle; p.inv_perm = ctx->inv_perm; p.col_of_rank = ctx->col_of_rank;
     p.v = ctx->v; p.psi = ctx->psi; p.y = ctx->y;
-    p.vh_row = vh_row; p.vl_row = vl_row; p.vd_row = vd_row;
+    p.vh_row = vh_row; p.vl_row = vl_row; p.vd_row = vd_row; p.obs_out = obs_out;
     int G = (d + UP_WARPS - 1) / UP_WARPS;
     if (G > ctx->sm_count) G = ctx->sm_count;
     void* args[] = {(void*)&p};

@@ -191,6 +191,29 @@ class DeviceEngine:
                                        self._stream())
         self._check(rc, "sspbo_blr_update")
 
+    def blr_update_points(self, xs, ts) -> None:
+        """Encode host points on the device and apply them as observations, one C call, no synchronisation."""
+        xs = np.ascontiguousarray(np.atleast_2d(xs), dtype=np.float64)
+        ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
+        assert xs.shape[0] == ts.shape[0]
+        if xs.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xs.shape)}")
+        for i in range(0, xs.shape[0], 64):
+            rc = self.lib.sspbo_blr_update_x(self._ctx, xs[i:i + 64].ctypes.data_as(_lib._pd), ts[i:i + 64].ctypes.data_as(_lib._pd),
+                                             min(64, xs.shape[0] - i), self._stream())
+            self._check(rc, "sspbo_blr_update_x")
+
+    def observe(self, x, t):
+        """(mu, var) of the BLR at phi(x) under the current posterior, then the posterior update with target t: one C call,
+        one synchronisation (eval(x_t) + update(x_t, y_t) of a BO step)."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        if x.shape[0] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(x.shape)}")
+        mu, var = C.c_double(), C.c_double()
+        rc = self.lib.sspbo_observe(self._ctx, x.ctypes.data_as(_lib._pd), float(t), C.byref(mu), C.byref(var), self._stream())
+        self._check(rc, "sspbo_observe")
+        return mu.value, var.value
+
     def blr_get(self, m=True, S=True, Sinv=False):
         torch = self.torch
         d = self.d

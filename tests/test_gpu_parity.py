@@ -869,6 +869,45 @@ def test_acq_ascent_raw_feature_posterior(pkg):
     np.testing.assert_allclose(val, [-np.ravel(f(p))[0] for p in phi], rtol=1e-12)
 
 
+def test_observe_equals_eval_then_update(pkg, golden):
+    """`SSPAgent.observe` (predictive scalars taken from the fused update launch) against `eval` followed by `update` on a
+    twin agent, MI acquisition so gamma_t depends on the returned variance; also the trajectory and multi-agent contexts."""
+    b = golden("blr.npz")
+    rng = np.random.default_rng(6)
+
+    def twin():
+        sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=B2, length_scale=1.0)
+        return pkg.SSPAgent(b["xs"], b["ys"], sp, decoder_method="from-set", gamma_c=1.0, beta_ucb=10.0, var_decay=0.25,
+                            length_scale=1.0)
+    a1, a2 = twin(), twin()
+    for i in range(8):
+        x_t = rng.uniform(-5, 5, (1, 2))
+        y_t = np.atleast_2d(himmelblau(x_t))
+        mu1, var1, acq1 = a1.eval(x_t)
+        a1.update(x_t, y_t, var1, step_num=i)
+        mu2, var2, acq2 = a2.observe(x_t, y_t, step_num=i)
+        assert mu2.shape == (1, 1) and var2.shape == (1,) and acq2.shape == (1,)
+        np.testing.assert_allclose(mu2, mu1, rtol=1e-5, atol=1e-6 * np.abs(b["ys"]).max())   # eval returns float32-rounded values
+        np.testing.assert_allclose(var2, var1, rtol=1e-5)
+        np.testing.assert_allclose(acq2, acq1, rtol=1e-5)
+    assert a1.var_weight == a2.var_weight
+    np.testing.assert_allclose(np.ravel(a2.gamma_t), np.ravel(a1.gamma_t), rtol=1e-5)
+    assert np.array_equal(a1.blr.m, a2.blr.m) and np.array_equal(a1.blr.S, a2.blr.S)         # same kernels, same order
+    xc = rng.uniform(-5, 5, (2000, 2))
+    k1, k2 = a1.best_candidate(xc), a2.best_candidate(xc)
+    assert a1._scoring_engine().best()[1] == a2._scoring_engine().best()[1]
+    # normalised multi-agent context: mean / variance of the unit-norm phi
+    g = golden("multi_agent.npz")
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g["a2_dims"])
+    agt = pkg.SSPMultiAgent(g["a2_trajs"], g["a2_tys"], n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim,
+                            domain_bounds=g["bounds"], length_scale=0.8, time_length_scale=1.2, seed=seed,
+                            decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    mu, var, acq = agt.observe(g["a2_xc"][:1], np.array([[0.3]]))
+    np.testing.assert_allclose(mu.ravel(), g["a2_mu"].ravel()[:1], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, g["a2_var"][:1], rtol=1e-8)
+    np.testing.assert_allclose(acq, g["a2_acq"][:1], rtol=1e-8)
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
