@@ -53,10 +53,12 @@ __device__ __forceinline__ void psi_entry(const XT* __restrict__ xrow, const dou
     }
 }
 
-constexpr int ENC_CPB = 8;       // candidates per block (each twiddle load feeds 2 x ENC_CPB FMAs)
+// candidates per block: 8 for batches (each twiddle load feeds 16 FMAs), 1 for a handful of points (x_t of a BO step, an
+// initial design): the FP64 pipe is narrow, so FMAs spent on absent candidates of a partly filled group are not free
+constexpr int ENC_CPB_BATCH = 8, ENC_CPB_SMALL = 1, ENC_SMALL_N = 64;
 constexpr int ENC_THREADS = 256;
 
-template <typename XT>
+template <typename XT, int ENC_CPB>
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
          const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi) {
@@ -90,6 +92,40 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
         }
         // small batches: gridDim.y blocks share a group of candidates, each takes a slice of the output columns
         const int j0 = (int)((long long)d * blockIdx.y / gridDim.y), j1 = (int)((long long)d * (blockIdx.y + 1) / gridDim.y);
+        if constexpr (ENC_CPB == 1) {
+            // one candidate per block: when the column slice is narrower than the block, the spare warps split the
+            // frequency sum (k-parts) and the partial sums are folded through shared memory in a fixed order
+            __shared__ double part_s[ENC_THREADS];
+            const int ncol = j1 - j0;
+            const int lanes_per = 32 * ((ncol + 31) / 32);
+            const int kparts = lanes_per >= ENC_THREADS ? 1 : ENC_THREADS / lanes_per;
+            for (int jb = 0; jb < ncol; jb += ENC_THREADS) {            // one trip when ncol <= ENC_THREADS
+                const int part = kparts == 1 ? 0 : threadIdx.x / lanes_per;
+                const int jl = jb + (kparts == 1 ? threadIdx.x : threadIdx.x % lanes_per);
+                double acc = 0.0;
+                if (part < kparts && jl < ncol) {
+                    const int j = j0 + jl;
+                    const int kb = 1 + (int)((long long)K * part / kparts), ke = 1 + (int)((long long)K * (part + 1) / kparts);
+                    int idx = (int)(((long long)j * (kb - 1)) % d);
+#pragma unroll 4
+                    for (int k = kb; k < ke; ++k) {
+                        idx += j; if (idx >= d) idx -= d;   // (j*k) mod d
+                        const double2 tw = __ldg(twiddle + idx);
+                        acc = fma(psi_s[k], tw.x, fma(-psi_s[K + k], tw.y, acc));
+                    }
+                }
+                if (kparts > 1) {
+                    __syncthreads();
+                    part_s[threadIdx.x] = acc;
+                    __syncthreads();
+                    if (part == 0 && jl < ncol)
+                        for (int q = 1; q < kparts; ++q) acc += part_s[q * lanes_per + (threadIdx.x % lanes_per)];
+                }
+                if (part == 0 && jl < ncol)
+                    phi[base * d + j0 + jl] = (psi_s[0] + 2.0 * acc) * inv_d * (normalize ? scale_s[0] : 1.0);
+            }
+            continue;
+        }
         for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             double acc[ENC_CPB];
 #pragma unroll
@@ -1159,21 +1195,25 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     if (N == 0) return SSPBO_OK;
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)ENC_CPB * ctx->d * sizeof(double);
-    int64_t blocks64 = (N + ENC_CPB - 1) / ENC_CPB;
+    const int cpb = N <= ENC_SMALL_N ? ENC_CPB_SMALL : ENC_CPB_BATCH;
+    size_t smem = (size_t)cpb * ctx->d * sizeof(double);
+    int64_t blocks64 = (N + cpb - 1) / cpb;
     int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 8 ? blocks64 : (int64_t)ctx->sm_count * 8);
     int slices = 1;                                      // a handful of candidates (e.g. x_t of a BO step): spread the columns
-    while (slices < 16 && (int64_t)blocks * slices < ctx->sm_count && ctx->d / (slices * 2) >= 32) slices *= 2;
+    while (slices < 16 && (int64_t)blocks * slices < 2 * ctx->sm_count && ctx->d / (slices * 2) >= 32) slices *= 2;
     const dim3 grid(blocks, slices);
+#define SSPBO_ENC_LAUNCH(XT, CPB)                                                                                          \
+    do {                                                                                                                   \
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<XT, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_encode<XT, CPB><<<grid, ENC_THREADS, smem, st>>>((const XT*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,     \
+                                                           ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out); \
+    } while (0)
     if (x_dtype == SSPBO_F32) {
-        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<float><<<grid, ENC_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
-                                                           ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out);
+        if (cpb == ENC_CPB_SMALL) SSPBO_ENC_LAUNCH(float, ENC_CPB_SMALL); else SSPBO_ENC_LAUNCH(float, ENC_CPB_BATCH);
     } else if (x_dtype == SSPBO_F64) {
-        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_encode<double><<<grid, ENC_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,
-                                                            ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out);
+        if (cpb == ENC_CPB_SMALL) SSPBO_ENC_LAUNCH(double, ENC_CPB_SMALL); else SSPBO_ENC_LAUNCH(double, ENC_CPB_BATCH);
     } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
+#undef SSPBO_ENC_LAUNCH
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }
