@@ -204,6 +204,17 @@ int sspbo_bind(sspbo_ctx* ctx, const double* a_dev, int qa, const double* b_dev,
  * mirror solves; encoding at the trial length scales and this product are the only O(d) steps. */
 int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_dev, void* stream);
 
+/* ---- lock-step of many independent runs (BASELINE config C4: 4096 runs, one context each) ---------------------
+ * sspbo_score_batch: for r < R: sspbo_score(ctxs[r], x_dev, ..., lam[r], gamma_t[r], key = keys_dev + r, AUTO engine) on
+ * streams[r % n_streams]; all runs share the candidate set x_dev (N rows) and must share its row width n*L.  keys_dev (R
+ * packed keys) must be zeroed by the caller.  sspbo_update_batch: for r < R: sspbo_blr_update_x(ctxs[r], row r of x_host
+ * (R x n*L float64), ts_host[r]).  Both only enqueue work.  On error the first failing code is returned and *failed
+ * (nullable) is the run index. */
+int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
+                      const double* gamma_t, unsigned long long* keys_dev, void* const* streams, int n_streams, int* failed);
+int sspbo_update_batch(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, void* const* streams,
+                       int n_streams, int* failed);
+
 /* ---- candidate generators ---------------------------------------------------------
  * Counter-based uniform(0,1) float32 stream (same integer hash as
  * oracle/ssp_oracle.py:counter_uniform, bit-exact): rows [start, start+count) of an

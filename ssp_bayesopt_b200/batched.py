@@ -3,13 +3,16 @@
 Each run is an ordinary `SSPAgent` (own SSP space / posterior / scoring factor in its own device context); all
 runs share one candidate set resident on the device.  A lock-step = for every run: fused scoring of the shared
 candidates, arg-max, then (after the host evaluated the objectives) one float64 rank-one posterior update.
-Scoring launches of different runs are issued round-robin on a small pool of CUDA streams so the many small
-kernels overlap; the winners are gathered with ONE device-to-host copy per lock-step.
+The scoring launches of all runs are enqueued by ONE library call (`sspbo_score_batch`: a C loop over the runs' contexts,
+round-robin on a small pool of CUDA streams so the many small kernels overlap), likewise the encode + posterior updates
+(`sspbo_update_batch`); the winners are gathered with ONE device-to-host copy per lock-step.
 
 Runs are independent, so multi-GPU use is plain partitioning of the run list (`dist.shard_range` over run ids),
 with no collective.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -27,6 +30,15 @@ class BatchedRuns:
         self.candidates = eng0.to_device(candidates)            # shared, resident
         self.streams = [self.torch.cuda.Stream(device=self.device) for _ in range(max(1, min(n_streams, len(agents))))]
         self._keys = self.torch.zeros(len(agents), dtype=self.torch.int64, device=self.device)
+        # per-run contexts and streams as C arrays: one library call enqueues a whole lock-step
+        R = len(agents)
+        self._engines = [a._scoring_engine() for a in agents]
+        self._lib = self._engines[0].lib
+        self._ctxs = (C.c_void_p * R)(*[e._ctx.value for e in self._engines])
+        self._cstreams = (C.c_void_p * len(self.streams))(*[st.cuda_stream for st in self.streams])
+        self._width = self._engines[0].n * self._engines[0].L
+        assert all(e.n * e.L == self._width for e in self._engines), "runs must share the candidate row width"
+        assert self.candidates.shape[1] == self._width
 
     def select(self):
         """Arg-max candidate of every run.  Returns (scores (R,), indices (R,), points (R, n))."""
@@ -34,11 +46,19 @@ class BatchedRuns:
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(cur)
-        for r, agt in enumerate(self.agents):
-            st = self.streams[r % len(self.streams)]
-            with torch.cuda.stream(st):
-                key = agt.best_candidate(self.candidates)
-                self._keys[r:r + 1].copy_(key)
+        R = len(self.agents)
+        lam = np.array([a.var_weight for a in self.agents], dtype=np.float64)
+        gam = np.array([a._gamma() for a in self.agents], dtype=np.float64)
+        self._keys.zero_()
+        for s in self.streams:
+            s.wait_stream(cur)                                   # ... and the zeroed keys
+        failed = C.c_int(-1)
+        rc = self._lib.sspbo_score_batch(self._ctxs, R, C.c_void_p(self.candidates.data_ptr()),
+                                         self._engines[0]._dtype_code(self.candidates), self.candidates.shape[0],
+                                         lam.ctypes.data_as(_lib._pd), gam.ctypes.data_as(_lib._pd),
+                                         C.c_void_p(self._keys.data_ptr()), self._cstreams, len(self.streams), C.byref(failed))
+        if rc:
+            _lib.check(self._lib, self._engines[max(failed.value, 0)]._ctx, rc, f"sspbo_score_batch (run {failed.value})")
         for s in self.streams:
             cur.wait_stream(s)
         keys = self._keys.cpu().numpy()                          # one D2H per lock-step
@@ -50,10 +70,27 @@ class BatchedRuns:
 
     def update(self, xs, ys):
         """xs (R, n), ys (R,): one observation per run."""
+        torch = self.torch
+        if all(isinstance(a.gamma_c, (int, float)) and a.gamma_c == 0 for a in self.agents):
+            # pure UCB: gamma_t ignores the predictive variance, so nothing is read back: one library call enqueues every
+            # run's encode + posterior update
+            xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(len(self.agents), self._width)
+            ys = np.ascontiguousarray(ys, dtype=np.float64).reshape(-1)
+            cur = torch.cuda.current_stream(self.device)
+            for s in self.streams:
+                s.wait_stream(cur)
+            failed = C.c_int(-1)
+            rc = self._lib.sspbo_update_batch(self._ctxs, len(self.agents), xs.ctypes.data_as(_lib._pd), ys.ctypes.data_as(_lib._pd),
+                                              self._cstreams, len(self.streams), C.byref(failed))
+            if rc:
+                _lib.check(self._lib, self._engines[max(failed.value, 0)]._ctx, rc, f"sspbo_update_batch (run {failed.value})")
+            for s in self.streams:
+                cur.wait_stream(s)
+            for a in self.agents:
+                a._step_scalars(0.0, 0)
+            return
         for r, agt in enumerate(self.agents):
-            x_t = np.atleast_2d(xs[r])
-            _, var_t, _ = agt.eval(x_t)
-            agt.update(x_t, np.atleast_2d(ys[r]), var_t)
+            agt.observe(np.atleast_2d(xs[r]), np.atleast_2d(ys[r]))   # eval(x_t) + update in one device round trip
 
     def step(self, objective):
         """One lock-step with a vectorised objective f(points (R, n)) -> (R,)."""

@@ -124,8 +124,7 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                 if (part == 0 && jl < ncol)
                     phi[base * d + j0 + jl] = (psi_s[0] + 2.0 * acc) * inv_d * (normalize ? scale_s[0] : 1.0);
             }
-            continue;
-        }
+        } else
         for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             double acc[ENC_CPB];
 #pragma unroll
@@ -1809,6 +1808,34 @@ extern "C" int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, dou
     SSPBO_CUDA(ctx, cudaMemcpyAsync(h, ctx->obs_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
     *mu_host = h[0]; *var_host = h[1];
+    return SSPBO_OK;
+}
+
+/* Lock-step of many independent runs (BASELINE config C4): the per-run calls of a selection / an observation issued from
+ * one C loop over the runs' contexts, round-robin over the caller's streams.  Returns the first non-zero return code;
+ * *failed (nullable) receives the index of that run (its message is in sspbo_last_error of its context). */
+extern "C" int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
+                                 const double* gamma_t, unsigned long long* keys_dev, void* const* streams, int n_streams,
+                                 int* failed) {
+    if (failed) *failed = -1;
+    if (!ctxs || R < 0 || !lam || !gamma_t || !keys_dev || !streams || n_streams < 1) return SSPBO_EINVAL;
+    for (int r = 0; r < R; ++r) {
+        const int rc = sspbo_score(ctxs[r], x_dev, x_dtype, N, 0, lam[r], gamma_t[r], nullptr, nullptr, nullptr, keys_dev + r,
+                                   SSPBO_ENGINE_AUTO, streams[r % n_streams]);
+        if (rc) { if (failed) *failed = r; return rc; }
+    }
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_update_batch(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, void* const* streams,
+                                  int n_streams, int* failed) {
+    if (failed) *failed = -1;
+    if (!ctxs || R < 0 || !x_host || !ts_host || !streams || n_streams < 1) return SSPBO_EINVAL;
+    for (int r = 0; r < R; ++r) {
+        const size_t nl = (size_t)ctxs[r]->n * ctxs[r]->L;
+        const int rc = sspbo_blr_update_x(ctxs[r], x_host + (size_t)r * nl, ts_host + r, 1, streams[r % n_streams]);
+        if (rc) { if (failed) *failed = r; return rc; }
+    }
     return SSPBO_OK;
 }
 

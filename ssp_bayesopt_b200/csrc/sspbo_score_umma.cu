@@ -41,7 +41,6 @@ constexpr int GEN_WARPS = 4 * ROW_GROUPS;  // thread (row group, quarter) -> GEN
 constexpr int EPI_WARPS = 4;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
 constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 448 (GEN_ROWS = 2) or 704
-constexpr int GEN_THREADS = 32 * GEN_WARPS;
 constexpr int A_TILE_BYTES = BM * BK * 2;                        // 16 KiB (one of hi / lo)
 constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
 constexpr int NA_MIN = 2, NA_MAX = 4;
