@@ -80,6 +80,8 @@ class SSPMultiAgent(SSPAgent):
         dc = np.tile(tag_dc, self.traj_len)
         self._traj_engine = DeviceEngine(self.ssp_space._device)
         self._traj_engine.set_space(self.ssp_space.phase_matrix, self.ssp_space.length_scale)
+        if domain_bounds is not None:                    # declared |x| bound: lets the scorer use its fast phase arithmetic
+            self._traj_engine.set_xbound(float(np.max(np.abs(np.asarray(domain_bounds, dtype=np.float64)))))
         self._traj_engine.set_waypoints(tau, dc_sign=dc, normalize=True)
 
     def _scoring_engine(self):

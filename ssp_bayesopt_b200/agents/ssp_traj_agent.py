@@ -71,6 +71,8 @@ class SSPTrajectoryAgent(SSPAgent):
         ls_t = float(np.ravel(self.ssp_t_space.length_scale)[0])
         tau = np.asarray(timesteps, dtype=np.float64).reshape(-1, 1) * (a_t / ls_t)[None, :]     # (L, K) radians
         self._traj_engine.set_space(self.ssp_x_space.phase_matrix, self.ssp_x_space.length_scale)
+        if self.domain_bounds is not None:               # declared |x| bound: lets the scorer use its fast phase arithmetic
+            self._traj_engine.set_xbound(float(np.max(np.abs(np.asarray(self.domain_bounds, dtype=np.float64)))))
         self._traj_engine.set_traj(tau, self.traj_len)
 
     def _cv_loss(self, length_scale, xs, ys):

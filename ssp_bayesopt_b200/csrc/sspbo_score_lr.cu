@@ -463,6 +463,12 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                                 const size_t o = ((size_t)g0 * p.L + j) * NDIM + a;
                                 xf[a] = (g0 < N) ? (p.x_f64 ? (float)__ldg((const double*)p.x + o) : __ldg((const float*)p.x + o)) : 0.f;
                             }
+                            if (kb == 0 && half == 0) {                   // once per row: waypoints outside the declared |x| bound
+                                bool oor = false;
+#pragma unroll
+                                for (int a = 0; a < NDIM; ++a) oor |= !(fabsf(xf[a]) <= p.x_absmax);
+                                if (oor) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);
+                            }
                             const float* Afblk = (const float*)tables + (size_t)fbase * NDIM;      // [axis][NF]
                             const float* tf = p.tauf + (size_t)j * nf + fbase;
 #pragma unroll
