@@ -990,7 +990,8 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     dev_free(&ctx->aa_work);
     if (ctx->eval_dev) cudaFree(ctx->eval_dev);
-    if (ctx->obs_pin) { cudaFreeHost(ctx->obs_pin); cudaFree(ctx->obs_x); cudaEventDestroy(ctx->obs_event); }
+    if (ctx->obs_pin) { cudaFreeHost(ctx->obs_pin); cudaFree(ctx->obs_x); }
+    if (ctx->obs_event) cudaEventDestroy(ctx->obs_event);
     dev_free(&ctx->obs_phi); dev_free(&ctx->obs_out);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     delete ctx;
@@ -1736,9 +1737,13 @@ extern "C" int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, doub
     const size_t xb = 64 * nl * sizeof(double), ob = 3 * 64 * sizeof(float);
     int rc = host_stage(ctx, xb + ob > 4096 ? xb + ob : 4096);
     if (rc) return rc;
-    if (!ctx->eval_dev) SSPBO_CUDA(ctx, cudaMalloc(&ctx->eval_dev, 64 * 16 * 64 * sizeof(double) + ob));   // n <= 16, L <= 64
+    if (xb + ob > ctx->eval_dev_bytes) {                 // sized by the row width (n * L doubles), 64 rows
+        if (ctx->eval_dev) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->eval_dev); ctx->eval_dev = nullptr; ctx->eval_dev_bytes = 0; }
+        SSPBO_CUDA(ctx, cudaMalloc(&ctx->eval_dev, xb + ob));
+        ctx->eval_dev_bytes = xb + ob;
+    }
     double* xd = (double*)ctx->eval_dev;
-    float* od = (float*)((char*)ctx->eval_dev + 64 * 16 * 64 * sizeof(double));
+    float* od = (float*)((char*)ctx->eval_dev + xb);
     double* xp = (double*)ctx->pin;
     float* op = (float*)((char*)ctx->pin + xb);
     memcpy(xp, x_host, (size_t)N * nl * sizeof(double));
@@ -1763,15 +1768,20 @@ extern "C" int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const do
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nl = (size_t)ctx->n * ctx->L;
-    if (!ctx->obs_pin) {
-        SSPBO_CUDA(ctx, cudaMallocHost(&ctx->obs_pin, 64 * 16 * 64 * sizeof(double)));
-        SSPBO_CUDA(ctx, cudaMalloc(&ctx->obs_x, 64 * 16 * 64 * sizeof(double)));
-        SSPBO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->obs_event, cudaEventDisableTiming));
-    } else SSPBO_CUDA(ctx, cudaEventSynchronize(ctx->obs_event));       // the previous upload has left the pinned buffer
+    const size_t stage = 64 * nl * sizeof(double);       // sized by the row width: thousands of contexts may coexist (C4)
+    if (ctx->obs_pin) SSPBO_CUDA(ctx, cudaEventSynchronize(ctx->obs_event));       // the previous upload has left the pinned buffer
+    if (stage > ctx->obs_bytes) {
+        if (ctx->obs_pin) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFreeHost(ctx->obs_pin); cudaFree(ctx->obs_x); ctx->obs_pin = nullptr; ctx->obs_x = nullptr; }
+        else SSPBO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->obs_event, cudaEventDisableTiming));
+        ctx->obs_bytes = 0;
+        SSPBO_CUDA(ctx, cudaMallocHost(&ctx->obs_pin, stage));
+        SSPBO_CUDA(ctx, cudaMalloc(&ctx->obs_x, stage));
+        ctx->obs_bytes = stage;
+    }
     if ((size_t)k * ctx->d > ctx->obs_phi_cap) {
         if (ctx->obs_phi) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->obs_phi); ctx->obs_phi = nullptr; ctx->obs_phi_cap = 0; }
-        SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->obs_phi, (size_t)64 * ctx->d * sizeof(double)));
-        ctx->obs_phi_cap = (size_t)64 * ctx->d;
+        SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->obs_phi, (size_t)k * ctx->d * sizeof(double)));
+        ctx->obs_phi_cap = (size_t)k * ctx->d;
     }
     memcpy(ctx->obs_pin, x_host, (size_t)k * nl * sizeof(double));
     SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->obs_x, ctx->obs_pin, (size_t)k * nl * sizeof(double), cudaMemcpyHostToDevice, st));

@@ -96,13 +96,13 @@ struct sspbo_ctx {
     // divided by its norm (multi-agent trajectories, agents/ssp_multi_agent.py:166-186)
     double dc = 1.0; bool normalize = false;
     // staging of sspbo_blr_update_x: pinned x, device x, device phi rows, event guarding the pinned buffer
-    void* obs_pin = nullptr; void* obs_x = nullptr; double* obs_phi = nullptr; size_t obs_phi_cap = 0; cudaEvent_t obs_event = nullptr;
+    void* obs_pin = nullptr; void* obs_x = nullptr; size_t obs_bytes = 0; double* obs_phi = nullptr; size_t obs_phi_cap = 0; cudaEvent_t obs_event = nullptr;
     double* obs_out = nullptr;       // device: predictive (mu, var) at the observed point before the update (sspbo_observe)
     bool want_obs = false;
     bool unfused_update = false;     // posterior updates go through the separate kernels of sspbo_core.cu
     int fused_update_ok = -1;        // cooperative single-launch posterior update usable on this device (-1: not probed)
     // pinned host staging and device staging of the small synchronous transfers of a BO step (sspbo_score_finish, sspbo_eval_host)
-    void* pin = nullptr; size_t pin_bytes = 0; void* eval_dev = nullptr;
+    void* pin = nullptr; size_t pin_bytes = 0; void* eval_dev = nullptr; size_t eval_dev_bytes = 0;
     // workspace of the phi-space acquisition ascent (sspbo_ascent.cu): Y = S Phi and per-CTA partial sums, double-buffered
     double* aa_work = nullptr; size_t aa_cap = 0;
     // opaque state of the tcgen05 engines (tensor maps etc.)

@@ -12,7 +12,7 @@ def himmelblau(x):
     return -((x[:, 0] ** 2 + x[:, 1] - 11) ** 2 + (x[:, 0] + x[:, 1] ** 2 - 7) ** 2) / 100.0
 
 
-def c4(runs=128, steps=5):
+def c4(runs=int(os.environ.get("C4_RUNS", "128")), steps=5):
     b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
     agents = []
     t0 = time.perf_counter()
