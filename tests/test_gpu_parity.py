@@ -908,6 +908,51 @@ def test_observe_equals_eval_then_update(pkg, golden):
     np.testing.assert_allclose(acq, g["a2_acq"][:1], rtol=1e-8)
 
 
+def test_host_point_entry_points(pkg, golden):
+    """sspbo_eval_host / sspbo_blr_update_x / sspbo_score_finish against the tensor-based calls they shortcut."""
+    import ctypes as C
+    from ssp_bayesopt_b200 import _lib
+    b = golden("blr.npz")
+    rng = np.random.default_rng(8)
+
+    def agent():
+        sp = pkg.RandomSSPSpace(2, ssp_dim=128, domain_bounds=B2, length_scale=1.0, rng=2)
+        return pkg.SSPAgent(b["xs"], b["ys"], sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0, length_scale=1.0)
+    a1, a2 = agent(), agent()
+    e1, e2 = a1._scoring_engine(), a2._scoring_engine()
+    # eval: 64 host points (one C call) == the same points as a device tensor (sspbo_score with outputs), 65 points take the old path
+    x64, x65 = rng.uniform(-5, 5, (64, 2)), rng.uniform(-5, 5, (65, 2))
+    for xs in (x64, x65, x64[:1]):
+        got = e1.eval_host(xs, 10.0, 0.5, engine=_lib.ENGINE_EXACT)
+        _, (mu, var, acq) = e1.score(e1.to_device(xs), 10.0, 0.5, want_outputs=True, engine=_lib.ENGINE_EXACT)
+        for g_, w_ in zip(got, (mu, var, acq)):
+            assert g_.dtype == np.float64 and g_.shape == (len(xs),)
+            np.testing.assert_array_equal(g_, w_.double().cpu().numpy())
+    with pytest.raises(AssertionError):
+        e1.eval_host(np.zeros((3, 5)), 10.0, 0.5)
+    # update from host points (130 of them: three library calls) == update(encode(x), y)
+    xs, ys = rng.uniform(-5, 5, (130, 2)), rng.normal(size=(130, 1))
+    a1.blr.update_points(xs, ys)
+    a2.blr.update(a2.encode(xs), ys)
+    # (the two routes encode with different batch shapes, i.e. different float64 summation orders in K1)
+    assert rel(a1.blr.m, a2.blr.m) < 1e-11 and rel(a1.blr.S, a2.blr.S) < 1e-11
+    assert e1.lowrank_info() == e2.lowrank_info()
+    with pytest.raises(AssertionError):
+        a1.blr.update_points(np.zeros((2, 3)), np.zeros((2, 1)))
+    rc = e1.lib.sspbo_blr_update_x(e1._ctx, xs.ctypes.data_as(_lib._pd), ys.ctypes.data_as(_lib._pd), 65, None)
+    assert rc != 0 and b"64" in e1.lib.sspbo_last_error(e1._ctx)
+    # selection read-back: key and counters in one call
+    xc = rng.uniform(-5, 5, (5000, 2)).astype(np.float32)
+    key = a1.best_candidate(xc)
+    want = int(key.item()) & 0xFFFFFFFFFFFFFFFF
+    st, got = e1._finish()
+    assert got == want and not st["rerun"] and st["scored"] in (0, 5000)      # counters belong to the low-rank engine only
+    assert e1.best() == _lib.key_unpack(want)
+    # empty ascent
+    out = e1.acq_ascent(np.zeros((0, e1.d)), 10.0, 0.5)
+    assert out[0].shape == (0, e1.d) and out[1].shape == (0,)
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
