@@ -106,6 +106,10 @@ int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_set);
 /* blr.py:60-77: S_inv += beta Phi^T Phi; for each row: Sherman-Morrison on S; m = S b.
  * phis_dev: k x d float64 (device); ts_host: k float64 (host). */
 int sspbo_blr_update(sspbo_ctx* ctx, const double* phis_dev, const double* ts_host, int k, void* stream);
+/* Posterior update path: fused != 0 (default) = one cooperative launch per observation (sspbo_update.cu) where the device
+ * supports it, 0 = the separate GEMV / rank-one kernels (sspbo_core.cu; also the automatic fallback). */
+int sspbo_set_update_path(sspbo_ctx* ctx, int fused);
+
 /* SSPAgent.update (agents/ssp_agent.py:187-206) for k <= 64 HOST points: x_host k x (n*L) float64 is staged through pinned
  * memory, encoded on the device (K1) and applied as k sequential observations (K3); asynchronous. */
 int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const double* ts_host, int k, void* stream);

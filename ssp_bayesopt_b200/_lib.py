@@ -48,6 +48,7 @@ SIGNATURES = {
     "sspbo_blr_update": (_i, [_vp, _vp, _pd, _i, _vp]),
     "sspbo_blr_update_x": (_i, [_vp, _pd, _pd, _i, _vp]),
     "sspbo_observe": (_i, [_vp, _pd, _d, _pd, _pd, _vp]),
+    "sspbo_set_update_path": (_i, [_vp, _i]),
     "sspbo_blr_get": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sspbo_blr_export_size": (_i64, [_vp]),
     "sspbo_blr_export": (_i, [_vp, _vp, _vp]),

@@ -1867,6 +1867,12 @@ extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32
     return SSPBO_OK;
 }
 
+extern "C" int sspbo_set_update_path(sspbo_ctx* ctx, int fused) {
+    if (!ctx) return SSPBO_EINVAL;
+    ctx->unfused_update = !fused;
+    return SSPBO_OK;
+}
+
 extern "C" void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index) {
     unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)(key & 0xffffffffu);
     if (index) *index = (int64_t)(0xffffffffu - lo);

@@ -908,6 +908,41 @@ def test_observe_equals_eval_then_update(pkg, golden):
     np.testing.assert_allclose(acq, g["a2_acq"][:1], rtol=1e-8)
 
 
+def test_update_paths_agree(pkg, golden):
+    """The single-launch posterior update against the separate-kernel path it replaces (kept as the fallback), on an SSP
+    context (psi-space covariance, low-rank rows, scoring afterwards) and on a raw-feature context."""
+    b = golden("blr.npz")
+    rng = np.random.default_rng(12)
+    agents = []
+    for fused in (1, 0):
+        sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=B2, length_scale=1.0)
+        assert sp.engine.lib.sspbo_set_update_path(sp.engine._ctx, fused) == 0
+        agents.append(pkg.SSPAgent(b["xs"], b["ys"], sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+    xs, ys = rng.uniform(-5, 5, (30, 2)), rng.normal(size=(30, 1))
+    for a in agents:
+        for i in range(30):
+            a.update(xs[i:i + 1], ys[i:i + 1], 0.0)
+    a1, a0 = agents
+    assert rel(a1.blr.m, a0.blr.m) < 1e-11 and rel(a1.blr.S, a0.blr.S) < 1e-11 and rel(a1.blr.S_inv, a0.blr.S_inv) < 1e-12
+    assert a1._scoring_engine().lowrank_info() == a0._scoring_engine().lowrank_info()
+    xc = rng.uniform(-5, 5, (3000, 2)).astype(np.float32)
+    outs = []
+    for a in agents:
+        _, (mu, var, acq) = a._scoring_engine().score(xc, 10.0, 0.0, want_outputs=True)
+        assert a._scoring_engine().last_engine() == "umma-lowrank"
+        outs.append((mu.cpu().numpy(), var.cpu().numpy()))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-5)
+    models = []
+    for fused in (1, 0):
+        m = pkg.BayesianLinearRegression(77)
+        m.engine.lib.sspbo_set_update_path(m.engine._ctx, fused)
+        X = np.random.default_rng(2).normal(size=(12, 77))
+        m.update(X, X[:, :1])
+        models.append(m)
+    assert rel(models[0].m, models[1].m) < 1e-11 and rel(models[0].S, models[1].S) < 1e-11
+
+
 def test_host_point_entry_points(pkg, golden):
     """sspbo_eval_host / sspbo_blr_update_x / sspbo_score_finish against the tensor-based calls they shortcut."""
     import ctypes as C
