@@ -20,6 +20,7 @@ class SSPAgent(Agent):
     def __init__(self, init_xs, init_ys, ssp_space, decoder_method='from-set', gamma_c=1.0,
                  beta_ucb=np.log(2 / 1e-6), var_decay=0., **kwargs):
         super().__init__()
+        self._init_samples, self._init_samples_of = None, None
         (num_pts, data_dim) = init_xs.shape
         self.data_dim = data_dim
         self.init_xs = init_xs
@@ -62,7 +63,20 @@ class SSPAgent(Agent):
         if self.decoder_method in ('network', 'network-optim', 'regression'):
             raise NotImplementedError(f"decoder_method={self.decoder_method!r} (learned decoders) is out of scope; "
                                       "use 'from-set' or 'direct-optim'")
-        self.init_samples = self.get_init_samples(self.ssp_space)
+        self._init_samples_of = lambda: self.get_init_samples(self.ssp_space)   # built on first use (see init_samples)
+
+    @property
+    def init_samples(self):
+        """Decoding set (sample SSPs, sample points) of ssp_agent.py:86-91.  The reference builds it in the constructor;
+        here it is built on first use, because it is M x ssp_dim float64 (41 MB at M = 1e4, d = 511) and runs that pick
+        their points straight from a candidate set never decode (thousands of agents coexist in config C4)."""
+        if self._init_samples is None and self._init_samples_of is not None:
+            self._init_samples = self._init_samples_of()
+        return self._init_samples
+
+    @init_samples.setter
+    def init_samples(self, value):
+        self._init_samples = value
 
     def length_scale(self):
         return self.ssp_space.length_scale

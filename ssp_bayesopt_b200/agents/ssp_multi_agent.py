@@ -91,7 +91,7 @@ class SSPMultiAgent(SSPAgent):
         if self.decoder_method in ('regression', 'network', 'network-optim'):
             raise NotImplementedError(f"decoder_method={self.decoder_method!r} (learned decoders) is out of scope; "
                                       "use 'from-set' or 'direct-optim'")
-        self.init_samples = [self.get_init_samples(self.ssp_x_spaces[0])] * self.n_agents
+        self._init_samples_of = lambda: [self.get_init_samples(self.ssp_x_spaces[0])] * self.n_agents
 
     def length_scale(self):
         return np.array([sp.length_scale for sp in self.ssp_x_spaces] + [self.ssp_t_space.length_scale])

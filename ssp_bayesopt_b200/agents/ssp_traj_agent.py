@@ -121,7 +121,7 @@ class SSPTrajectoryAgent(SSPAgent):
         if self.decoder_method in ('regression', 'network', 'network-optim'):
             raise NotImplementedError(f"decoder_method={self.decoder_method!r} (learned decoders) is out of scope; "
                                       "use 'from-set' or 'direct-optim'")
-        self.init_samples = self.get_init_samples(self.ssp_x_space)
+        self._init_samples_of = lambda: self.get_init_samples(self.ssp_x_space)
 
     def length_scale(self):
         return np.array([self.ssp_x_space.length_scale, self.ssp_t_space.length_scale])
