@@ -326,7 +326,7 @@ def run_native(args):
                          "frac": achieved / peaks["tflops"],
                          # dram__bytes_read+write of one scorer launch (chunk of 4,194,304 candidates) from the ncu --set full
                          # captures summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
-                         "traffic": (108.7e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
+                         "traffic": (106.1e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
                          "launch_candidates": min(chunk, n_local),
                          "executed": executed_note(engine_used, info["rank"], d, n_local, kernel_ms, peaks),
                          "note": f"algorithmic (dense form, SURVEY 8d) {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
