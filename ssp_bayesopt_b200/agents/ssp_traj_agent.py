@@ -21,6 +21,33 @@ from ..engine import DeviceEngine
 from .ssp_agent import SSPAgent
 
 
+def cv_loss_from_gram(G, ys, alpha=0.01, max_splits=50):
+    """K-fold negative predictive log-likelihood of ssp_traj_agent.py:121-137 from the Gram matrix G = Phi Phi^T of the
+    encoded design: min(n, 50) contiguous folds (KFold without shuffling), per fold a fresh BLR with prior precision
+    alpha and beta = 1 / var(train targets) (blr.py:54-59), written in its dual form
+        mu = k^T (G_tr + (alpha/beta) I)^-1 t ,   var = 1/beta + (k** - k^T (G_tr + (alpha/beta) I)^-1 k) / alpha."""
+    ys = np.asarray(ys, dtype=np.float64).reshape(-1)
+    n = ys.shape[0]
+    n_splits = min(n, max_splits)
+    sizes = np.full(n_splits, n // n_splits, dtype=int)
+    sizes[:n % n_splits] += 1
+    total, start, idx = 0.0, 0, np.arange(n)
+    for sz in sizes:
+        te = idx[start:start + sz]
+        tr = np.concatenate([idx[:start], idx[start + sz:]])
+        start += sz
+        t = ys[tr]
+        beta = 1.0 / np.var(t) if len(t) > 1 else 1.0 / np.abs(t[0])
+        A = G[np.ix_(tr, tr)] + (alpha / beta) * np.eye(len(tr))
+        k = G[np.ix_(te, tr)]
+        sol = np.linalg.solve(A, np.column_stack([t, k.T]))
+        mu = k @ sol[:, 0]
+        var = 1.0 / beta + (G[te, te] - np.sum(k * sol[:, 1:].T, axis=1)) / alpha
+        diff = ys[te] - mu
+        total += np.sum(0.5 * np.log(var) + diff ** 2 / var)
+    return total
+
+
 class SSPTrajectoryAgent(SSPAgent):
     def __init__(self, init_xs, init_ys, **kwargs):
         super().__init__(init_xs, init_ys, None, **kwargs)
@@ -85,26 +112,7 @@ class SSPTrajectoryAgent(SSPAgent):
         self._point_engine(np.linspace(0, self.traj_len, self.traj_len))
         eng = self._traj_engine
         G = eng.gram(eng.encode_device(xs)).cpu().numpy()
-        ys = np.asarray(ys, dtype=np.float64).reshape(-1)
-        n, alpha = ys.shape[0], 0.01
-        n_splits = min(n, 50)
-        sizes = np.full(n_splits, n // n_splits, dtype=int)
-        sizes[:n % n_splits] += 1
-        total, start, idx = 0.0, 0, np.arange(n)
-        for sz in sizes:                                              # KFold without shuffling
-            te = idx[start:start + sz]
-            tr = np.concatenate([idx[:start], idx[start + sz:]])
-            start += sz
-            t = ys[tr]
-            beta = 1.0 / np.var(t) if len(t) > 1 else 1.0 / np.abs(t[0])   # blr.py:54-59
-            A = G[np.ix_(tr, tr)] + (alpha / beta) * np.eye(len(tr))
-            k = G[np.ix_(te, tr)]
-            sol = np.linalg.solve(A, np.column_stack([t, k.T]))
-            mu = k @ sol[:, 0]
-            var = 1.0 / beta + (G[te, te] - np.sum(k * sol[:, 1:].T, axis=1)) / alpha
-            diff = ys[te] - mu
-            total += np.sum(0.5 * np.log(var) + diff ** 2 / var)
-        return total
+        return cv_loss_from_gram(G, ys)
 
     def _optimize_lengthscale(self, init_trajs, init_ys):
         from scipy.optimize import minimize

@@ -140,3 +140,22 @@ def test_gloo_world2_key_allreduce(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+def test_cv_loss_dual_form_matches_reference_evaluations():
+    """Host half of the trajectory agent's length-scale search: the dual-form K-fold loss computed from a Gram matrix (here
+    formed from the oracle's phi on the CPU; the product forms it on the device) against the objective values scipy
+    evaluated inside the live reference (tests/golden/lengthscale_cv.npz)."""
+    import os
+    from oracle import ssp_oracle as orc
+    from ssp_bayesopt_b200.agents.ssp_traj_agent import cv_loss_from_gram
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lengthscale_cv.npz"))
+    L, xd = 4, 2
+    for x, f in list(zip(g["eval_x"], g["eval_f"]))[::6]:
+        T = orc.encode(g["At"], np.array([x[1]]), np.linspace(0, L, L).reshape(-1, 1))
+        phi = orc.traj_encode(g["Ax"], x[0] * np.ones(xd), T, g["trajs"], L, xd)
+        np.testing.assert_allclose(cv_loss_from_gram(phi @ phi.T, g["tys"]), f, rtol=1e-9)
+    # fold sizes of KFold(n_splits=min(n, 50)) for n > 50: 57 points -> 7 folds of 2, 43 of 1
+    rng = np.random.default_rng(0)
+    phi = rng.normal(size=(57, 9))
+    assert np.isfinite(cv_loss_from_gram(phi @ phi.T, rng.normal(size=57)))
