@@ -19,6 +19,25 @@ from ..engine import DeviceEngine
 from .ssp_agent import SSPAgent
 
 
+def waypoint_phase_table(timesteps, t_phase_matrix, t_length_scale, agent_sps):
+    """Phase offsets of the waypoints (timestep j, agent i), in the candidate layout (traj_len, n_agents, x_dim):
+    tau[(j, i), k] = A_t[k] t_j / l_t + angle(FFT(a_i))[k] for the K positive frequencies (radians), and the +-1 DC
+    coefficient of each waypoint's tag (a unitary real vector has a DC coefficient of +1 or -1).  With them
+    sum_i a_i (*) sum_j T_j (*) phi_x(x_ji) has the spectrum sum_(j,i) exp(i (A x_ji / l + tau[(j, i)])) per frequency and
+    sum_(j,i) dc[(j, i)] at DC."""
+    timesteps = np.asarray(timesteps, dtype=np.float64).reshape(-1, 1)
+    agent_sps = np.atleast_2d(agent_sps)
+    K = (agent_sps.shape[1] - 1) // 2
+    a_t = np.asarray(t_phase_matrix)[1:K + 1, 0]
+    ls_t = float(np.ravel(t_length_scale)[0])
+    tau_t = timesteps * (a_t / ls_t)[None, :]                                   # (L, K)
+    spec = np.fft.fft(agent_sps, axis=-1)
+    tag_phase = np.angle(spec[:, 1:K + 1])                                      # (n_agents, K)
+    tag_dc = np.where(spec[:, 0].real < 0, -1, 1).astype(np.int32)
+    tau = (tau_t[:, None, :] + tag_phase[None, :, :]).reshape(timesteps.shape[0] * agent_sps.shape[0], K)
+    return tau, np.tile(tag_dc, timesteps.shape[0])
+
+
 class SSPMultiAgent(SSPAgent):
     def __init__(self, init_xs, init_ys, **kwargs):
         super().__init__(init_xs, init_ys, None, **kwargs)
@@ -69,15 +88,7 @@ class SSPMultiAgent(SSPAgent):
 
         # device context that sees whole multi-agent trajectories: one phase-offset row per (timestep, agent) waypoint,
         # in the candidate layout (traj_len, n_agents, x_dim)
-        K = (self.ssp_dim - 1) // 2
-        a_t = self.ssp_t_space.phase_matrix[1:K + 1, 0]
-        ls_t = float(np.ravel(self.ssp_t_space.length_scale)[0])
-        tau_t = timesteps * (a_t / ls_t)[None, :]                               # (L, K) radians
-        spec = np.fft.fft(self.agent_sps, axis=-1)
-        tag_phase = np.angle(spec[:, 1:K + 1])                                  # (n_agents, K)
-        tag_dc = np.where(spec[:, 0].real < 0, -1, 1).astype(np.int32)          # unitary real vector: DC = +-1
-        tau = (tau_t[:, None, :] + tag_phase[None, :, :]).reshape(self.traj_len * n_agents, K)
-        dc = np.tile(tag_dc, self.traj_len)
+        tau, dc = waypoint_phase_table(timesteps, self.ssp_t_space.phase_matrix, self.ssp_t_space.length_scale, self.agent_sps)
         self._traj_engine = DeviceEngine(self.ssp_space._device)
         self._traj_engine.set_space(self.ssp_space.phase_matrix, self.ssp_space.length_scale)
         if domain_bounds is not None:                    # declared |x| bound: lets the scorer use its fast phase arithmetic

@@ -159,3 +159,29 @@ def test_cv_loss_dual_form_matches_reference_evaluations():
     rng = np.random.default_rng(0)
     phi = rng.normal(size=(57, 9))
     assert np.isfinite(cv_loss_from_gram(phi @ phi.T, rng.normal(size=57)))
+
+
+@pytest.mark.parametrize("tag", ["a3", "a2"])
+def test_multi_agent_phase_table_reproduces_reference_encoding(tag):
+    """Host half of the multi-agent encoder: tag vectors (SPSpace mirror) and the waypoint phase table handed to the device.
+    Summing unit phasors with those offsets and synthesising phi on the CPU must give the live reference's encode
+    (tests/golden/multi_agent.npz) - the device kernels evaluate exactly this sum."""
+    import os
+    import ssp_bayesopt_b200 as pkg
+    from ssp_bayesopt_b200.agents.ssp_multi_agent import waypoint_phase_table
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multi_agent.npz"))
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g[f"{tag}_dims"])
+    Ax, d = g[f"{tag}_Ax"], g[f"{tag}_Ax"].shape[0]
+    K = (d - 1) // 2
+    tags = pkg.SPSpace(n_agents, d, rng=seed)
+    np.testing.assert_allclose(tags.vectors, g[f"{tag}_agent_sps"], atol=1e-15)
+    np.testing.assert_allclose(tags.bind(tags.vectors, tags.inverse_vectors), np.tile(tags.identity(), (n_agents, 1)), atol=1e-12)
+    tau, dc = waypoint_phase_table(np.linspace(1, L + 1, L), g[f"{tag}_At"], g[f"{tag}_ls_t"], tags.vectors)
+    assert tau.shape == (L * n_agents, K) and set(np.unique(dc)) <= {-1, 1}
+    x = g[f"{tag}_xc"].reshape(-1, L * n_agents, xd)                      # waypoints in (timestep, agent) order
+    theta = np.einsum("kn,cwn->cwk", Ax[1:K + 1] / g[f"{tag}_ls_x"], x) + tau[None]
+    spec = np.exp(1j * theta).sum(axis=1)                                 # (candidates, K)
+    j = np.arange(d)[:, None] * np.arange(1, K + 1)[None, :] * (2 * np.pi / d)
+    phi = (dc.sum() + 2 * (spec.real @ np.cos(j).T - spec.imag @ np.sin(j).T)) / d
+    phi /= np.linalg.norm(phi, axis=1, keepdims=True)
+    np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=1e-13)
