@@ -135,6 +135,31 @@ def gen_lengthscale_cv(agents):
                         beta=np.float64(np.ravel(agt.blr.beta)[0]), m=agt.blr.m)
 
 
+def gen_lengthscale_gp(sspspace, agents):
+    """11. length scale of SSPAgent when none is given: sklearn GP with the reference's sinc kernel
+    (agents/ssp_agent.py:96-109, agents/kernels/sinc_kernel.py), on two small designs."""
+    from ssp_bayes_opt.agents.kernels.sinc_kernel import SincKernel
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    out = {"bounds": b2}
+    for tag, n, seed in (("a", 12, 50), ("b", 25, 51)):
+        xs = np.random.default_rng(seed).uniform(b2[:, 0], b2[:, 1], size=(n, 2))
+        ys = himmelblau(xs).reshape(-1, 1)
+        with quiet:
+            sp = sspspace.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=b2, length_scale=1.0)
+            agt = agents.SSPAgent(xs, ys, sp, decoder_method="from-set")
+        out[f"{tag}_xs"], out[f"{tag}_ys"] = xs, ys
+        out[f"{tag}_length_scale"] = np.ravel(agt.ssp_space.length_scale)
+        out[f"{tag}_m"] = agt.blr.m
+    # kernel values and the gradient the reference hands to sklearn, at two length scales
+    X = np.random.default_rng(52).uniform(-2, 2, size=(6, 2))
+    for i, ls in enumerate((1.0, 0.37)):
+        K, dK = SincKernel(length_scale=ls)(X, eval_gradient=True)
+        out[f"k{i}_ls"], out[f"k{i}_K"], out[f"k{i}_dK"] = np.float64(ls), K, dK
+    out["k_X"] = X
+    np.savez_compressed(os.path.join(OUT, "lengthscale_gp.npz"), **out)
+
+
 def main():
     sspspace, blr, agents = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -144,6 +169,9 @@ def main():
         return
     if "--only-multi-agent" in sys.argv[1:]:
         gen_multi_agent(agents)
+        return
+    if "--only-lengthscale-gp" in sys.argv[1:]:
+        gen_lengthscale_gp(sspspace, agents)
         return
     if "--only-lengthscale-cv" in sys.argv[1:]:
         gen_lengthscale_cv(agents)
@@ -292,6 +320,7 @@ def main():
     gen_acq_ascent(sspspace, agents)
     gen_multi_agent(agents)
     gen_lengthscale_cv(agents)
+    gen_lengthscale_gp(sspspace, agents)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

@@ -4,8 +4,8 @@ Hot path: `eval` (ssp_agent.py:125-137) and `best_candidate` call the fused kern
 (`sspbo_score`: encode -> BLR predict -> MI/UCB bonus -> argmax) and never materialise phi;
 `update` (ssp_agent.py:187-224) encodes x_t and applies the float64 rank-one posterior update on the
 device.  Deviations, documented in DESIGN.md: `decoder_method` defaults to 'from-set' (the reference's
-default 'network-optim' needs TensorFlow); omitting `length_scale` raises instead of fitting the
-sklearn sinc-kernel GP (ssp_agent.py:96-109, out of the hot-path scope).
+default 'network-optim' needs TensorFlow).  Omitting `length_scale` fits the sinc-kernel GP of the reference on the
+host (ssp_agent.py:96-109; `agents/kernels/sinc_kernel.py`).
 """
 from __future__ import annotations
 
@@ -54,10 +54,9 @@ class SSPAgent(Agent):
         self.ssp_space = ssp_space
         self.ssp_dim = ssp_space.ssp_dim
         if 'length_scale' not in kwargs or np.any(np.asarray(kwargs.get('length_scale')) < 0):
-            raise NotImplementedError(
-                "length_scale must be given: the sinc-kernel GP length-scale fit of the reference "
-                "(ssp_agent.py:96-109) is outside the GPU hot-path scope")
-        self.ssp_space.update_lengthscale(kwargs.get('length_scale'))
+            self.ssp_space.update_lengthscale(self._optimize_lengthscale(self.init_xs, self.init_ys))
+        else:
+            self.ssp_space.update_lengthscale(kwargs.get('length_scale'))
 
     def _set_decoder(self):
         if self.decoder_method in ('network', 'network-optim', 'regression'):
@@ -80,6 +79,17 @@ class SSPAgent(Agent):
 
     def length_scale(self):
         return self.ssp_space.length_scale
+
+    def _optimize_lengthscale(self, init_xs, init_ys):
+        """Length scale when the caller gives none (ssp_agent.py:96-109): scikit-learn GP with the sinc kernel on the
+        initial design, 20 optimiser restarts, random_state 0.  Host-side set-up on a handful of points."""
+        from sklearn.gaussian_process import GaussianProcessRegressor
+        from .kernels import SincKernel
+        fit_gp = GaussianProcessRegressor(
+            kernel=SincKernel(length_scale=1., length_scale_bounds=(1 / np.sqrt(init_xs.shape[0] + 1), 1e5)),
+            alpha=1e-6, normalize_y=True, n_restarts_optimizer=20, random_state=0)
+        fit_gp.fit(init_xs, init_ys)
+        return np.exp(fit_gp.kernel_.theta)
 
     def get_init_samples(self, ssp_space):
         """Decoding set: grid size rule of ssp_agent.py:111-123."""

@@ -707,6 +707,17 @@ def test_multi_agent_tcgen05_and_driver(pkg):
     assert opt.xs.shape == (17, L * n_agents * xd) and np.all(np.abs(opt.xs) <= 2)
 
 
+def test_agent_without_length_scale(pkg, golden):
+    """SSPAgent with no `length_scale`: the sinc-kernel GP fit on the host picks it (ssp_agent.py:96-109), then the usual
+    device path; length scale and posterior mean against the live reference."""
+    g = golden("lengthscale_gp.npz")
+    for tag in ("a", "b"):
+        sp = pkg.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=g["bounds"], length_scale=1.0)
+        agt = pkg.SSPAgent(g[f"{tag}_xs"], g[f"{tag}_ys"], sp, decoder_method="from-set")
+        np.testing.assert_allclose(np.ravel(agt.ssp_space.length_scale), g[f"{tag}_length_scale"], rtol=1e-6)
+        assert rel(agt.blr.m, g[f"{tag}_m"]) < 1e-5
+
+
 def test_trajectory_lengthscale_search(pkg, golden):
     """Omitted `length_scale`: the K-fold search of ssp_traj_agent.py:113-143 with the encode and
     the Gram matrix on the device.  Objective against every evaluation recorded inside the live reference; result against

@@ -185,3 +185,21 @@ def test_multi_agent_phase_table_reproduces_reference_encoding(tag):
     phi = (dc.sum() + 2 * (spec.real @ np.cos(j).T - spec.imag @ np.sin(j).T)) / d
     phi /= np.linalg.norm(phi, axis=1, keepdims=True)
     np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=1e-13)
+
+
+def test_sinc_kernel_and_gp_length_scale_match_reference():
+    """SincKernel (values and the hyper-parameter gradient handed to scikit-learn) and the GP length-scale fit of
+    SSPAgent._optimize_lengthscale against the live reference (tests/golden/lengthscale_gp.npz).  Host-only."""
+    import os
+    from ssp_bayesopt_b200.agents.kernels import SincKernel
+    from ssp_bayesopt_b200.agents.ssp_agent import SSPAgent
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lengthscale_gp.npz"))
+    for i in (0, 1):
+        K, dK = SincKernel(length_scale=float(g[f"k{i}_ls"]))(g["k_X"], eval_gradient=True)
+        np.testing.assert_allclose(K, g[f"k{i}_K"], atol=1e-15)
+        np.testing.assert_allclose(dK, g[f"k{i}_dK"], atol=1e-14)
+    Ka, dKa = SincKernel(length_scale=np.array([1.0, 0.5]))(g["k_X"], eval_gradient=True)
+    assert dKa.shape == (6, 6, 2) and np.allclose(np.diag(Ka), 1.0)
+    for tag in ("a", "b"):
+        ls = SSPAgent._optimize_lengthscale(None, g[f"{tag}_xs"], g[f"{tag}_ys"])
+        np.testing.assert_allclose(ls, g[f"{tag}_length_scale"][:1], rtol=1e-6)
