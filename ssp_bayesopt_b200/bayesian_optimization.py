@@ -18,7 +18,7 @@ are accepted and ignored.  Candidate sets (extra kwargs, all optional):
                         `num_restarts` phi-space climbs of `acquisition_func`'s objective per step
                         (`SSPAgent.maximize_acquisition`), the best one decoded with the agent's decoder.  Starting
                         points come from `np.random.default_rng(random_state)`; every rank computes the same step.
-    ascent_iters, ascent_tol   step cap (default 200) and stopping tolerance (default 1e-7) of 'phi-ascent'
+    ascent_iters, ascent_tol   step cap (default 200) and stopping tolerance (default 1e-5: far below the resolution of the decoding grid) of 'phi-ascent'
 Supported agent types: 'ssp-hex', 'ssp-rand', 'ssp-custom' (with ssp_space=...), 'ssp-traj', 'ssp-multi'.  Under
 torch.distributed (one process per GPU) the candidate index range is sharded across ranks.
 """
@@ -227,7 +227,7 @@ class BayesianOptimization:
             else:
                 phis, vals = agt.maximize_acquisition(num_restarts=num_restarts, rng=ascent_rng,
                                                       max_iter=int(bo_kw.get('ascent_iters', 200)),
-                                                      tol=float(bo_kw.get('ascent_tol', 1e-7)))
+                                                      tol=float(bo_kw.get('ascent_tol', 1e-5)))
                 gidx = int(np.argmax(vals))                          # all restarts (not the reference's vals[:(t+1)] slice)
                 score = vals[gidx]
                 x_t = np.asarray(agt.decode(phis[gidx:gidx + 1]), dtype=np.float64).reshape(1, -1)
