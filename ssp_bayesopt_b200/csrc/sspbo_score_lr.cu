@@ -710,6 +710,8 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (bn > 64 && 4 * bn + 3 * A_SLOT_COLS <= (int)TMEM_COLS) { p.merged = 1; p.acc_cols = 2 * bn; p.n_bufs = 2; }
     p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
     if (p.na > NA_MAX) p.na = NA_MAX;
+    if (p.na < GEN_W)                                     // every generator warp of a quadrant owns a slot of the rotation
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: %d A slots for %d generator warps per quadrant", p.na, GEN_W);
     p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
     p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
     p.prior_var = (float)(1.0 / ctx->alpha);
