@@ -1648,9 +1648,11 @@ extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N
                    "(rank %d, valid %d) and L == 1", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid);
     if (engine == SSPBO_ENGINE_AUTO) {
         if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
-        else if (N >= 1024 && lr_ok && !ctx->lr_disabled && 2 * (ctx->lr_rank + 1) <= ctx->d)
-            engine = SSPBO_ENGINE_UMMA_LR;                      // low-rank form while it is less tensor work than the
-        else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;   // triangular factor (~0.56 d^2)
+        else if (N >= 1024 && lr_ok && !ctx->lr_disabled &&
+                 2 * (ctx->lr_rank + 1) <= (ctx->d >= 128 ? 3 : 1) * ctx->d)
+            engine = SSPBO_ENGINE_UMMA_LR;                      // low-rank form while it is cheaper than the triangular factor:
+        else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;   // measured crossover at rank ~ 1.5 d for d = 151 (tools/
+                                                                     // rank_crossover.py), never below rank 256 for d >= 511
         else engine = SSPBO_ENGINE_SIMT;
     }
     ctx->last_engine = engine;
