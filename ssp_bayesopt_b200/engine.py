@@ -318,7 +318,7 @@ class DeviceEngine:
         host = out[:, :N].cpu().numpy().astype(np.float64)           # one D2H; the widening happens on the host
         return host[0], host[1], host[2]
 
-    def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 20, reset_best=True):
+    def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 21, reset_best=True):
         """Fused scoring of candidates that live in HOST memory (numpy or CPU tensor, ideally pinned): the set is
         streamed through two device staging buffers so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
         Returns the device key tensor (nothing is synchronised)."""
