@@ -999,6 +999,35 @@ def test_host_point_entry_points(pkg, golden):
     assert out[0].shape == (0, e1.d) and out[1].shape == (0,)
 
 
+def _build_c_abi_smoke(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "ssp_bayesopt_b200", "lib")
+    exe = str(tmp_path / "c_abi_smoke")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["gcc", "-std=c99", "-Wall", "-I" + os.path.join(root, "include"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(root, "tests", "c_abi_smoke.c"), "-L" + libdir, "-lsspbo", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    done = subprocess.run(cmd, capture_output=True, text=True)
+    assert done.returncode == 0, done.stderr
+    return exe
+
+
+def test_c_abi_from_plain_c(pkg, tmp_path):
+    """The drop-in boundary used from a plain C program (tests/c_abi_smoke.c, gcc, no Python / torch in the process): one BO
+    step through sspbo.h; every scoring engine must name the same winner and observe == eval_host."""
+    import subprocess
+    exe = _build_c_abi_smoke(tmp_path)
+    done = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert done.returncode == 0, done.stdout + done.stderr
+    lines = [l for l in done.stdout.splitlines() if l.startswith("engine ")]
+    assert len(lines) == 4 and done.stdout.strip().endswith("c abi ok"), done.stdout
+    idx = {l.split("index ")[1].split()[0] for l in lines}
+    scores = [float(l.split("score ")[1].split()[0]) for l in lines]
+    assert len(idx) == 1, done.stdout
+    assert max(scores) - min(scores) <= RTOL_SCORE * abs(scores[0]), done.stdout
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])

@@ -203,3 +203,18 @@ def test_sinc_kernel_and_gp_length_scale_match_reference():
     for tag in ("a", "b"):
         ls = SSPAgent._optimize_lengthscale(None, g[f"{tag}_xs"], g[f"{tag}_ys"])
         np.testing.assert_allclose(ls, g[f"{tag}_length_scale"][:1], rtol=1e-6)
+
+
+def test_c_abi_links_from_plain_c(tmp_path):
+    """tests/c_abi_smoke.c compiles as C99 against include/sspbo.h and links against the built library with gcc (running it
+    needs a GPU: tests/test_gpu_parity.py::test_c_abi_from_plain_c)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "ssp_bayesopt_b200", "lib", "libsspbo.so")
+    if not os.path.exists(lib):
+        pytest.skip("libsspbo.so not built")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(root, "tests", "c_abi_smoke.c"), "-L" + os.path.dirname(lib), "-lsspbo", "-L" + os.path.join(cuda, "lib64"),
+           "-lcudart", "-lm", "-o", str(tmp_path / "c_abi_smoke")]
+    done = subprocess.run(cmd, capture_output=True, text=True)
+    assert done.returncode == 0, done.stderr
