@@ -318,7 +318,8 @@ class DeviceEngine:
         host = out[:, :N].cpu().numpy().astype(np.float64)           # one D2H; the widening happens on the host
         return host[0], host[1], host[2]
 
-    def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 21, reset_best=True):
+    def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 21, reset_best=True,
+                   first_piece=None, growth=1.5):
         """Fused scoring of candidates that live in HOST memory (numpy or CPU tensor, ideally pinned): the set is
         streamed through two device staging buffers so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
         Returns the device key tensor (nothing is synchronised)."""
@@ -343,24 +344,25 @@ class DeviceEngine:
             self._best.zero_()
             self._pending = []
             self._lr_used = False
-        call = lambda: self._score_host_stream(xt, N, lam, gamma_t, index0, engine, chunk)
+        call = lambda: self._score_host_stream(xt, N, lam, gamma_t, index0, engine, chunk, first_piece, growth)
         call()
         self._pending.append(call)
         self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR
         return self._best
 
-    def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk):
+    def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk, first_piece=None, growth=1.5):
         torch = self.torch
         compute = torch.cuda.current_stream(self.device)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
-        # short first pieces: the copy of piece 0 is the only one no scoring overlaps, so keep it small
-        pieces, c0, n = [], 0, max(chunk >> 3, 1 << 15)
+        # short first piece: its copy is the only one no scoring overlaps; the following ones grow by 1.5x, about the ratio
+        # of link to scoring rate at d = 1023, so the copy of piece i + 1 fits under the scoring of piece i
+        pieces, c0, n = [], 0, int(first_piece or max(chunk >> 2, 1 << 15))
         while c0 < N:
             n = min(n, chunk, N - c0)
             pieces.append((c0, n))
-            c0, n = c0 + n, n * 2
+            c0, n = c0 + n, int(n * growth)
         for i, (c0, n) in enumerate(pieces):
             b = i & 1
             with torch.cuda.stream(self._copy_stream):

@@ -37,9 +37,9 @@ def resident(chunk):
     return f
 
 
-def streamed(chunk):
+def streamed(chunk, first=None, growth=2.0):
     def f():
-        eng.score_host(host, agt.var_weight, 0.0, chunk=chunk)
+        eng.score_host(host, agt.var_weight, 0.0, chunk=chunk, first_piece=first, growth=growth)
         eng.best()
     return f
 
@@ -48,3 +48,6 @@ for chunk in (1 << 22, 1 << 21, 1 << 20):
     print(f"resident, launches of {chunk:8d}: {timed(resident(chunk)):.2f} ms")
 for chunk in (1 << 22, 1 << 21, 1 << 20, 1 << 19):
     print(f"streamed, pieces up to {chunk:8d}: {timed(streamed(chunk)):.2f} ms")
+for chunk, first, growth in ((1 << 21, 1 << 19, 1.5), (1 << 22, 1 << 19, 1.5), (1 << 22, 1 << 20, 1.4), (3 << 20, 1 << 19, 1.6),
+                             (1 << 21, 1 << 20, 1.4), (1 << 22, 1 << 18, 1.5)):
+    print(f"streamed, pieces up to {chunk:8d}, first {first:8d}, growth {growth}: {timed(streamed(chunk, first, growth)):.2f} ms")
