@@ -218,3 +218,25 @@ def test_c_abi_links_from_plain_c(tmp_path):
            "-lcudart", "-lm", "-o", str(tmp_path / "c_abi_smoke")]
     done = subprocess.run(cmd, capture_output=True, text=True)
     assert done.returncode == 0, done.stderr
+
+
+def test_bayesian_optimization_surface_without_device():
+    """Constructor contract of bayesian_optimization.py:22-66 and the `res` / `max` views (:324-333); no device needed."""
+    import ssp_bayesopt_b200 as pkg
+    bounds = np.array([[-1.0, 1.0], [0.0, 2.0]])
+    with pytest.raises(AssertionError):
+        pkg.BayesianOptimization(f=None, bounds=bounds)
+    with pytest.raises(AssertionError):
+        pkg.BayesianOptimization(f=lambda x: 0.0, bounds=None)
+    with pytest.raises(AssertionError):
+        pkg.BayesianOptimization(f=lambda x: 0.0, bounds=np.zeros((2, 3)))
+    one = pkg.BayesianOptimization(f=lambda x: float(np.sum(x)), bounds=bounds)
+    two = pkg.BayesianOptimization(f=lambda x, info: float(np.sum(x)) + len(info), bounds=bounds)
+    assert one.target(np.ones((1, 2)), "ignored") == 2.0          # one positional argument: f(x)
+    assert two.target(np.ones((1, 2)), "ab") == 4.0               # otherwise f(x, info_str)
+    assert one.data_dim == 2 and one.xs is None and one.ys is None
+    one.xs, one.ys = np.array([[0.0, 1.0], [0.5, 0.5]]), np.array([1.0, 3.0])
+    assert one.max["target"] == 3.0 and np.array_equal(one.max["params"], one.xs[1])
+    assert [r["target"] for r in one.res] == [1.0, 3.0]
+    with pytest.raises(NotImplementedError):
+        one.initialize_agent(init_points=(one.xs, one.ys.reshape(-1, 1)), agent_type="gp")
