@@ -240,3 +240,29 @@ def test_bayesian_optimization_surface_without_device():
     assert [r["target"] for r in one.res] == [1.0, 3.0]
     with pytest.raises(NotImplementedError):
         one.initialize_agent(init_points=(one.xs, one.ys.reshape(-1, 1)), agent_type="gp")
+
+
+def test_domains_and_tag_space_shapes():
+    """Initial-design samplers (agents/domains.py) and SPSpace corner cases, host only."""
+    import ssp_bayesopt_b200 as pkg
+    from ssp_bayesopt_b200.agents import domains
+    b = np.array([[-2.0, 3.0], [0.0, 1.0]])
+    pts = domains.BoundedDomain(b).sample(8)
+    assert pts.shape == (8, 2) and np.all(pts >= b[:, 0]) and np.all(pts <= b[:, 1])
+    tr = domains.TrajectoryDomain(5, 2, b).sample(4)
+    assert tr.shape == (4, 10) and tr.min() >= -2.0 and tr.max() <= 3.0          # square box: [min low, max high]
+    np.random.seed(0)
+    goals = [np.array([1.0, 1.0]), np.array([-1.0, 0.5])]
+    mt = domains.MultiTrajectoryDomain(3, 4, 2, b, goals).sample(8)
+    assert mt.shape == (8, 4 * 2 * 3)
+    last = mt.reshape(8, 4, 2, 3)[:, -1]                                           # last waypoints sit within 0.1 of a goal
+    for i in range(3):
+        assert np.all(np.abs(last[:, :, i] - goals[(2 * i + 1) % 2]) <= 0.1 + 1e-12)
+    with pytest.raises(NotImplementedError):
+        domains.BoundedDomain(b).sample(4, method="grid")
+    one = pkg.SPSpace(1, 9)
+    assert np.array_equal(one.vectors, one.identity()) and np.array_equal(one.inverse_vectors, one.identity())
+    given = pkg.SPSpace(2, 9, vectors=np.eye(2, 9))
+    assert np.array_equal(given.vectors, np.eye(2, 9))
+    tags = pkg.SPSpace(4, 33, rng=np.random.default_rng(3))
+    assert np.allclose(np.abs(np.fft.fft(tags.vectors, axis=-1)), 1.0)             # unitary
