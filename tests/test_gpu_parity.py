@@ -367,6 +367,42 @@ def test_score_lowrank_c3(pkg, T, phase32):
     eng.set_policy(phase32=1)
 
 
+@pytest.mark.parametrize("T", [100, 140, 210])
+def test_score_lowrank_beyond_half_rank_small_space(pkg, T):
+    """AUTO keeps the low-rank engine up to rank 1.5 d for d >= 128: hex d = 151 (3 k-blocks per tile) at ranks above d / 2,
+    between d / 2 and d, and above d (rows of V then are linearly dependent, the form stays exact) - accumulator layouts
+    of 112, 144 and 224 rows.  Scores against the oracle on random candidates and on candidates near the observations."""
+    bounds = np.array([[-5.0, 10.0], [0.0, 15.0]])
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=1.0)
+    rng = np.random.default_rng(T)
+    X = rng.uniform(bounds[:, 0], bounds[:, 1], (T, 2))
+    y = np.sin(0.4 * X[:, :1]) + np.cos(0.3 * X[:, 1:])
+    agt = pkg.SSPAgent(X[:10], y[:10], sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0)
+    ref = orc.BLR(sp.ssp_dim)
+    ref.update(orc.encode(sp.phase_matrix, np.ones(2), X[:10]), y[:10])
+    for i in range(10, T):
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0)
+        ref.update(orc.encode(sp.phase_matrix, np.ones(2), X[i:i + 1]), y[i:i + 1])
+    eng = agt._scoring_engine()
+    assert eng.lowrank_info()["rank"] == T and eng.lowrank_info()["valid"]
+    N = 5000
+    xc = rng.uniform(bounds[:, 0], bounds[:, 1], (N, 2))
+    xc[:40] = X[:40] + 0.02 * rng.normal(size=(40, 2))
+    xc = np.clip(xc, bounds[:, 0], bounds[:, 1]).astype(np.float32)
+    phis = orc.encode(sp.phase_matrix, np.ones(2), xc.astype(np.float64))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
+    eng.score_stats(reset=True)
+    _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True)              # AUTO
+    assert eng.last_engine() == "umma-lowrank"
+    mu, var, acq = (t.double().cpu().numpy() for t in (mu, var, acq))
+    assert_scores_close(mu, acq, ref_mu, ref_acq)
+    np.testing.assert_allclose(var, ref_var, rtol=RTOL_SCORE)
+    ref_score = ref_mu.ravel() + ref_acq
+    srt = np.sort(ref_score)[::-1]
+    if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+        assert eng.best()[1] == int(np.argmax(ref_score))
+
+
 def test_score_lowrank_12d(pkg):
     """Domains with 9..16 dimensions: the low-rank tcgen05 engine covers them (the dense tcgen05 kernel stops at 8)."""
     from ssp_bayesopt_b200 import _lib
