@@ -266,3 +266,32 @@ def test_domains_and_tag_space_shapes():
     assert np.array_equal(given.vectors, np.eye(2, 9))
     tags = pkg.SPSpace(4, 33, rng=np.random.default_rng(3))
     assert np.allclose(np.abs(np.fft.fft(tags.vectors, axis=-1)), 1.0)             # unitary
+
+
+def test_sinc_kernel_reference_properties():
+    """The reference's own kernel tests (tests/test_sinc_kernel.py:8-68) against this package's SincKernel."""
+    from ssp_bayesopt_b200.agents.kernels import SincKernel
+    from ssp_bayesopt_b200.agents.kernels.sinc_kernel import _sinc_prime
+    xs = np.linspace(-1, 1, 10000)
+    assert np.allclose(np.diff(np.sinc(xs)) / np.diff(xs), _sinc_prime(xs)[1:], atol=1e-3)      # :8-11
+    k = SincKernel()
+    a, b = np.random.default_rng(0).random((100, 2)), np.random.default_rng(1).random((40, 2))
+    assert k(a, b).shape == (100, 40)                                                           # :14-19
+    K = k(a, a)
+    assert np.allclose(K, K.T) and np.allclose(np.diag(K), 1.0)                                 # :22-34
+    pts = np.array([[0.0, 0.0], [0.5, 0.5]])
+    K, dK = k(pts, eval_gradient=True)
+    assert dK.shape == (2, 2, 1)                                                                # :37-41
+    u = pts[:, None, :] - pts[None, :, :]
+    expected = (_sinc_prime(u)[:, :, 0] * np.sinc(u)[:, :, 1] * (-u[:, :, 0])
+                + np.sinc(u)[:, :, 0] * _sinc_prime(u)[:, :, 1] * (-u[:, :, 1]))
+    assert np.allclose(expected.flatten(), dK.flatten())                                        # :44-53
+    with pytest.raises(ValueError):
+        k(a, b, eval_gradient=True)
+    from sklearn.datasets import load_iris                                                      # :56-68
+    from sklearn.gaussian_process import GaussianProcessClassifier
+    from sklearn.gaussian_process.kernels import RBF
+    X, y = load_iris(return_X_y=True)
+    sinc_score = GaussianProcessClassifier(kernel=SincKernel(), random_state=0).fit(X, y).score(X, y)
+    rbf_score = GaussianProcessClassifier(kernel=1.0 * RBF(1.0), random_state=0).fit(X, y).score(X, y)
+    assert np.allclose(sinc_score, rbf_score, atol=2e-2), (rbf_score, sinc_score)
