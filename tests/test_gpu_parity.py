@@ -1064,6 +1064,55 @@ def test_c_abi_from_plain_c(pkg, tmp_path):
     assert max(scores) - min(scores) <= RTOL_SCORE * abs(scores[0]), done.stdout
 
 
+def test_agents_shape_contract(pkg):
+    """The reference's per-agent smoke tests (tests/test_agents.py:40-70 SSPAgent, :162-200 trajectory, :207-246 multi-agent),
+    same constructor calls and assertions, against the GPU agents."""
+    rng = np.random.default_rng(0)
+    xs = rng.uniform(B2[:, 0], B2[:, 1], size=(8, 2))
+    ys = (-(xs[:, 0] ** 2 + xs[:, 1] - 11) ** 2 - (xs[:, 0] + xs[:, 1] ** 2 - 7) ** 2).reshape(-1, 1)
+    space = pkg.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=B2, length_scale=1.0, rng=0)
+    agt = pkg.SSPAgent(xs, ys, space, decoder_method="from-set", length_scale=1.0)
+    mu, var, phi = agt.eval(xs)
+    assert mu.shape[-1] == 8 and var.shape[-1] == 8
+    min_func, jac = agt.acquisition_func()
+    assert callable(min_func) and callable(jac)
+    assert np.ravel(min_func(agt.encode(xs[:1]).ravel())).shape == (1,) and jac(agt.encode(xs[:1]).ravel()).shape == (agt.ssp_dim,)
+    x_new, y_new = xs[:1] + 0.1, ys[:1]
+    mu, var, _ = agt.eval(x_new)
+    agt.update(x_new, y_new, float(var.flat[0]), step_num=1)
+    x = np.array([[1.0, -2.0]])
+    assert agt.decode(space.encode(x)).shape == x.shape
+    assert agt.encode(xs).shape == (8, agt.ssp_dim)
+
+    rng = np.random.default_rng(1)
+    txs = rng.uniform(-5, 5, size=(5, 3, 2)).reshape(5, -1)
+    tys = rng.uniform(-1, 0, size=(5, 1))
+    tagt = pkg.SSPTrajectoryAgent(txs, tys, x_dim=2, traj_len=3, domain_bounds=B2, decoder_method="from-set", length_scale=1.0,
+                                  ssp_dim=51)
+    assert tagt.encode(txs).shape == (5, tagt.ssp_dim)
+    assert tagt.eval(txs)[0].shape[-1] == 5
+    assert callable(tagt.acquisition_func()[0])
+    rng = np.random.default_rng(99)
+    x_new, y_new = rng.uniform(-5, 5, size=(1, 6)), rng.uniform(-1, 0, size=(1, 1))
+    mu, var, _ = tagt.eval(x_new)
+    tagt.update(x_new, y_new, float(var.flat[0]), step_num=1)
+    assert tagt.decode(tagt.encode(x_new)).shape == (6,)
+
+    rng = np.random.default_rng(2)
+    mxs = rng.uniform(-5, 5, size=(5, 3 * 2 * 2))
+    mys = rng.uniform(-1, 0, size=(5, 1))
+    magt = pkg.SSPMultiAgent(mxs, mys, n_agents=2, x_dim=2, traj_len=3, domain_bounds=B2, decoder_method="from-set",
+                             length_scale=1.0, ssp_dim=51)
+    assert magt.encode(mxs).shape == (5, magt.ssp_dim)
+    assert magt.eval(mxs)[0].shape[-1] == 5
+    assert callable(magt.acquisition_func()[0])
+    rng = np.random.default_rng(99)
+    x_new, y_new = rng.uniform(-5, 5, size=(1, 12)), rng.uniform(-1, 0, size=(1, 1))
+    mu, var, _ = magt.eval(x_new)
+    magt.update(x_new, y_new, float(var.flat[0]), step_num=1)
+    assert magt.decode(magt.encode(x_new)).shape == (12,)
+
+
 def test_maximize_api(pkg):
     """tests/test_bayesian_optimization.py:14-47 shape contract + README-style run (config C1, reduced)."""
     bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
