@@ -15,7 +15,8 @@
  *     row-major; *_host are host pointers.  `stream` is a cudaStream_t passed as
  *     void* (NULL = legacy default stream).  All device work is stream-ordered
  *     and asynchronous unless the function returns a host value.
- *   - one ctx per device; a ctx is not thread-safe; distinct ctxs are independent.
+ *   - one ctx per (space, posterior) on one device - any number of them may share a device (independent runs,
+ *     sspbo_score_batch); a ctx is not thread-safe; distinct ctxs are independent.
  *   - psi-space: d = 2K+1, psi = [DC, cos(theta_1..K), sin(theta_1..K)],
  *     phi = B psi with B the real inverse-DFT matrix.
  */
