@@ -12,7 +12,7 @@
 //
 // One cooperative persistent kernel per tile of AA_RT restarts: every CTA keeps all iterates and m in shared memory, owns
 // a slice of the rows of S (S stays L2-resident: 8.4 MB at d = 1023), publishes its rows of Y = S Phi and its partial
-// phi.y sums, and after ONE grid barrier per iteration every CTA rebuilds the full update redundantly and bit-identically
+// phi.y, m.y and y.y sums (they give phi^T S phi and |grad g|^2 = |m|^2 + 2 c m.y + c^2 y.y without another pass over Y), and after ONE grid barrier per iteration every CTA rebuilds the full update redundantly and bit-identically
 // (fixed summation orders), so the stopping decision is uniform without a second barrier.  Y and the partials are
 // double-buffered across iterations.
 #include "sspbo_internal.cuh"
@@ -71,21 +71,24 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
     const int d = p.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x;
     double* phi = sm;                                       // iterates, see aa_at()
     double* mv = phi + (size_t)d * AA_RT;                   // [d]
-    double* red = mv + d;                                   // [AA_WARPS][2 AA_RT]
-    double* tot = red + AA_WARPS * 2 * AA_RT;               // [2 AA_RT]
-    double* mphi = tot + 2 * AA_RT;                         // [AA_RT]  m . phi_r of the current iterates
+    double* red = mv + d;                                   // [AA_WARPS][3 AA_RT]
+    double* tot = red + AA_WARPS * 3 * AA_RT;               // [3 AA_RT]
+    double* mphi = tot + 3 * AA_RT;                         // [AA_RT]  m . phi_r of the current iterates
     double* moved = mphi + AA_RT;                           // [AA_RT]  |phi_r - previous phi_r|
     double* coef = moved + AA_RT;                           // [AA_RT]  lam / sqrt(c + q_r)
+    double* gscale = coef + AA_RT;                          // [AA_RT]  margin / |grad g(phi_r)|
+    double* mm_s = gscale + AA_RT;                          // [1]      m . m
     __shared__ int first_it[AA_RT];
 
     // ---- load m and the starting points; `_clamp` of ssp_agent.py:160-163 pulls them into the ball ----
     {
-        double acc[2 * AA_RT];
+        double acc[2 * AA_RT + 1];
 #pragma unroll
-        for (int v = 0; v < 2 * AA_RT; ++v) acc[v] = 0.0;
+        for (int v = 0; v < 2 * AA_RT + 1; ++v) acc[v] = 0.0;
         for (int j = tid; j < d; j += AA_THREADS) {
             const double mj = p.m[j];
             mv[j] = mj;
+            acc[2 * AA_RT] = fma(mj, mj, acc[2 * AA_RT]);
 #pragma unroll
             for (int r = 0; r < AA_RT; ++r) {
                 const int src = r < p.R ? r : p.R - 1;      // unused lanes of the tile shadow the last restart
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
                 acc[AA_RT + r] = fma(mj, v, acc[AA_RT + r]);
             }
         }
-        aa_block_reduce<2 * AA_RT>(acc, red, tot);
+        aa_block_reduce<2 * AA_RT + 1>(acc, red, tot);
         double scale[AA_RT];
 #pragma unroll
         for (int r = 0; r < AA_RT; ++r) {
@@ -111,17 +114,18 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
             moved[tid] = INFINITY;
             first_it[tid] = -1;
         }
+        if (tid == 0) mm_s[0] = tot[2 * AA_RT];
         __syncthreads();
     }
 
     for (int k = 0;; ++k) {
         double* yb = p.ybuf + (size_t)(k & 1) * d * AA_RT;
-        double* pb = p.part + (size_t)(k & 1) * G * AA_RT;
+        double* pb = p.part + (size_t)(k & 1) * G * 3 * AA_RT;   // per CTA: phi.y, m.y, y.y of its rows, per restart
 
         // ---- my rows of Y = S Phi, one warp per row, and the partial phi_r . y_r over those rows ----
-        double pq[AA_RT];
+        double pq[AA_RT], pmy[AA_RT], pyy[AA_RT];
 #pragma unroll
-        for (int r = 0; r < AA_RT; ++r) pq[r] = 0.0;
+        for (int r = 0; r < AA_RT; ++r) { pq[r] = 0.0; pmy[r] = 0.0; pyy[r] = 0.0; }
         for (int j = blockIdx.x * AA_WARPS + warp; j < d; j += G * AA_WARPS) {
             const double* __restrict__ row = p.S + (size_t)j * d;
             double acc[AA_RT];
@@ -142,6 +146,8 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
             for (int r = 0; r < AA_RT; ++r) {
                 acc[r] = aa_warp_sum(acc[r]);
                 pq[r] = fma(phi[aa_at(d, j, r)], acc[r], pq[r]);
+                pmy[r] = fma(mv[j], acc[r], pmy[r]);
+                pyy[r] = fma(acc[r], acc[r], pyy[r]);
                 if (lane == r) mine = acc[r];
             }
             if (lane < AA_RT) __stcg(yb + (size_t)j * AA_RT + lane, mine);
@@ -149,13 +155,17 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
         __syncthreads();
         if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < AA_RT; ++r) red[warp * AA_RT + r] = pq[r];
+            for (int r = 0; r < AA_RT; ++r) {
+                red[warp * 3 * AA_RT + r] = pq[r];
+                red[warp * 3 * AA_RT + AA_RT + r] = pmy[r];
+                red[warp * 3 * AA_RT + 2 * AA_RT + r] = pyy[r];
+            }
         }
         __syncthreads();
-        if (tid < AA_RT) {
+        if (tid < 3 * AA_RT) {
             double t = 0.0;
-            for (int w = 0; w < AA_WARPS; ++w) t += red[w * AA_RT + tid];
-            __stcg(pb + (size_t)blockIdx.x * AA_RT + tid, t);
+            for (int w = 0; w < AA_WARPS; ++w) t += red[w * 3 * AA_RT + tid];
+            __stcg(pb + (size_t)blockIdx.x * 3 * AA_RT + tid, t);
         }
 
         grid.sync();
@@ -163,20 +173,33 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
         // ---- every CTA: q_r = phi_r^T S phi_r in CTA order, the value at the current iterate, the stopping rule ----
         {   // 32 interleaved sub-sums per restart (independent loads), folded in a fixed order
             const int r = lane & (AA_RT - 1), sub = warp * (32 / AA_RT) + lane / AA_RT;
-            double t = 0.0;
-#pragma unroll 4
-            for (int b = sub; b < G; b += AA_WARPS * (32 / AA_RT)) t += __ldcg(pb + (size_t)b * AA_RT + r);
+            double t[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int b = sub; b < G; b += AA_WARPS * (32 / AA_RT)) {
 #pragma unroll
-            for (int o = AA_RT; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane < AA_RT) red[warp * AA_RT + lane] = t;
+                for (int v = 0; v < 3; ++v) t[v] += __ldcg(pb + (size_t)b * 3 * AA_RT + v * AA_RT + r);
+            }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+#pragma unroll
+                for (int o = AA_RT; o < 32; o <<= 1) t[v] += __shfl_xor_sync(0xffffffffu, t[v], o);
+                if (lane < AA_RT) red[warp * 3 * AA_RT + v * AA_RT + lane] = t[v];
+            }
         }
         __syncthreads();
         if (tid < AA_RT) {
-            double q = 0.0;
-            for (int w = 0; w < AA_WARPS; ++w) q += red[w * AA_RT + tid];
+            double q = 0.0, my = 0.0, yy = 0.0;
+            for (int w = 0; w < AA_WARPS; ++w) {
+                q += red[w * 3 * AA_RT + tid];
+                my += red[w * 3 * AA_RT + AA_RT + tid];
+                yy += red[w * 3 * AA_RT + 2 * AA_RT + tid];
+            }
             const double s = sqrt(p.c + q);
+            const double cfv = p.lam / s;
             tot[tid] = mphi[tid] + p.lam * s - p.sqrt_gamma;            // acquisition value (ssp_agent.py:167-172)
-            coef[tid] = p.lam / s;
+            coef[tid] = cfv;
+            // |grad g|^2 = |m + cf y|^2 from the same partial sums: no separate pass over Y for the norm
+            gscale[tid] = p.margin / sqrt(fma(cfv, fma(cfv, yy, 2.0 * my), mm_s[0]));
             if (first_it[tid] < 0 && (moved[tid] <= p.tol * p.margin || k == p.max_iter)) first_it[tid] = k;
         }
         __syncthreads();
@@ -191,27 +214,10 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
             break;
         }
 
-        // ---- phi+ = margin grad / |grad|, grad_j = m_j + coef_r y_jr (two passes over Y: norm first) ----
-        double cf[AA_RT];
+        // ---- phi+ = margin grad / |grad|, grad_j = m_j + coef_r y_jr (one pass over Y) ----
+        double cf[AA_RT], sc[AA_RT];
 #pragma unroll
-        for (int r = 0; r < AA_RT; ++r) cf[r] = coef[r];
-        {
-            double gg[AA_RT];
-#pragma unroll
-            for (int r = 0; r < AA_RT; ++r) gg[r] = 0.0;
-            for (int j = tid; j < d; j += AA_THREADS) {
-                const double mj = mv[j];
-#pragma unroll
-                for (int r = 0; r < AA_RT; ++r) {
-                    const double g = fma(cf[r], __ldcg(yb + (size_t)j * AA_RT + r), mj);
-                    gg[r] = fma(g, g, gg[r]);
-                }
-            }
-            aa_block_reduce<AA_RT>(gg, red, tot);
-        }
-        double sc[AA_RT];
-#pragma unroll
-        for (int r = 0; r < AA_RT; ++r) sc[r] = p.margin / sqrt(tot[r]);
+        for (int r = 0; r < AA_RT; ++r) { cf[r] = coef[r]; sc[r] = gscale[r]; }
         {
             double acc[2 * AA_RT];
 #pragma unroll
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(AA_THREADS, 1) k_acq_ascent(const AscentParams
 }
 
 static size_t ascent_smem(int d) {
-    return ((size_t)d * AA_RT + d + AA_WARPS * 2 * AA_RT + 2 * AA_RT + 3 * AA_RT) * sizeof(double);
+    return ((size_t)d * AA_RT + d + AA_WARPS * 3 * AA_RT + 3 * AA_RT + 4 * AA_RT + 1) * sizeof(double);
 }
 
 }  // namespace
@@ -260,7 +266,7 @@ extern "C" int sspbo_acq_ascent(sspbo_ctx* ctx, const double* phi0, int R, doubl
     SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_acq_ascent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int G = (d + AA_WARPS - 1) / AA_WARPS;
     if (G > ctx->sm_count) G = ctx->sm_count;
-    const size_t need = 2 * ((size_t)d * AA_RT + (size_t)G * AA_RT);
+    const size_t need = 2 * ((size_t)d * AA_RT + (size_t)G * 3 * AA_RT);
     if (need > ctx->aa_cap) {
         if (ctx->aa_work) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->aa_work); ctx->aa_work = nullptr; ctx->aa_cap = 0; }
         SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->aa_work, need * sizeof(double)));
