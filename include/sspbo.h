@@ -39,13 +39,23 @@ extern "C" {
 #define SSPBO_F64 1
 
 /* scoring engines for sspbo_score */
-#define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; tcgen05 (low-rank while rank <= 255) when covered; else SIMT */
+#define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; N >= 1024: the tensor-memory tcgen05 engines, low-rank form (UMMA_LR) or
+                                   factor form (UMMA_F8), whichever passes fewer operand rows x k-blocks per tile (low rank
+                                   needs rank <= 511 and at most 1 % of flagged candidates); else SIMT */
 #define SSPBO_ENGINE_SIMT 1     /* fp32 CUDA-core kernel (any d)                */
-#define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel, full triangular factor        */
+#define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel, full triangular factor, psi staged in shared memory */
 #define SSPBO_ENGINE_EXACT 3    /* float64 quadratic form on the psi-space covariance (small N)  */
-#define SSPBO_ENGINE_UMMA_LR 4  /* tcgen05/TMEM kernel on the low-rank form S = I/alpha - V^T V
-                                   (one row of V per observation, rank <= 255) followed by the
-                                   EXACT engine on the candidates it flags (var < 0.1 / alpha)   */
+#define SSPBO_ENGINE_UMMA_LR 4  /* tcgen05 kernels with psi in tensor memory on the low-rank form S = I/alpha - V^T V
+                                   (one row of V per observation, rank <= 511: split-fp16 operands up to 96 rows,
+                                   fp16 + e4m3 operands beyond, see sspbo_set_operand_format) followed by a float64
+                                   pass over the candidates it flags (var < 0.3 / alpha)          */
+#define SSPBO_ENGINE_UMMA_F8 5  /* same kernel family on the triangular factor of the psi-space covariance
+                                   (var = 1/beta + |R psi|^2, any rank): fp16 + e4m3 operands, d + 1 operand rows in
+                                   chunks of <= 256, each chunk skipping the k-blocks before its first non-zero */
+
+/* candidate sets generated inside the scorer (sspbo_score_generated) */
+#define SSPBO_CAND_UNIFORM 1    /* counter-based uniform(0,1) float32 stream of sspbo_fill_uniform */
+#define SSPBO_CAND_GRID 2       /* grid of sspbo_grid_points (SSPSpace.get_sample_points('grid')) */
 
 typedef struct sspbo_ctx sspbo_ctx;
 
@@ -142,6 +152,18 @@ int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi_dev, int64_t N, double* 
 int sspbo_score(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, int64_t index0,
                 double lam, double gamma_t, float* mu_dev, float* var_dev, float* acq_dev,
                 unsigned long long* best_key_dev, int engine, void* stream);
+/* The same scoring over a candidate set GENERATED inside the kernel: rows [index0, index0 + N) of the counter-based
+ * uniform stream (kind SSPBO_CAND_UNIFORM, `seed`; axes/counts ignored) or of the n-D grid in the reference's order
+ * (kind SSPBO_CAND_GRID; axes_dev / counts_host as for sspbo_grid_points, i.e. the host's np.linspace values, so the
+ * winning row is bit-identical to SSPSpace.get_sample_points('grid')[index], sspspace.py:488-495).  No HBM or PCIe byte
+ * per candidate is read; keys carry the global row index.  The tensor-memory engines generate the rows in their
+ * generator warps; any other engine gets them written to a scratch buffer first.  Not for trajectory contexts. */
+int sspbo_score_generated(sspbo_ctx* ctx, int kind, uint64_t seed, const double* axes_dev, const int* counts_host,
+                          int64_t N, int64_t index0, double lam, double gamma_t, float* mu_dev, float* var_dev,
+                          float* acq_dev, unsigned long long* best_key_dev, int engine, void* stream);
+/* Operand format of SSPBO_ENGINE_UMMA_LR: -1 = by rank (default), 0 = split fp16 only (three fp16 products per K step,
+ * rank <= 255), 1 = fp16 + e4m3 (one fp16 and one e4m3 product per K step) at every rank. */
+int sspbo_set_operand_format(sspbo_ctx* ctx, int format);
 /* Counters of the low-rank engine since the last reset (synchronises `stream`): candidates scored, re-scored by the
  * exact pass, flagged beyond the list capacity, outside the declared |x| bound.  *rerun != 0 means the keys/outputs
  * accumulated since the last reset must be recomputed (the context has already switched its policy, so simply call
@@ -166,7 +188,7 @@ int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled);
 /* host helpers for the packed key */
 void sspbo_key_unpack(unsigned long long key, float* score, int64_t* index);
 unsigned long long sspbo_key_pack(float score, int64_t index);
-/* engine the last sspbo_score call used (SSPBO_ENGINE_SIMT / _UMMA) and kernel launches so far */
+/* engine the last sspbo_score call used (an SSPBO_ENGINE_* code other than AUTO) and kernel launches so far */
 int sspbo_last_engine(const sspbo_ctx* ctx);
 int64_t sspbo_launch_count(const sspbo_ctx* ctx);
 

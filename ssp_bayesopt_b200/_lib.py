@@ -14,9 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSPBO_LIB") or os.path.join(_HERE, "lib", "libsspbo.so")   # SSPBO_LIB: kernel-variant experiments
 
 F32, F64 = 0, 1
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_UMMA, ENGINE_EXACT, ENGINE_UMMA_LR = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_UMMA, ENGINE_EXACT, ENGINE_UMMA_LR, ENGINE_UMMA_F8 = 0, 1, 2, 3, 4, 5
 ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_UMMA: "umma", ENGINE_EXACT: "exact",
-                ENGINE_UMMA_LR: "umma-lowrank"}
+                ENGINE_UMMA_LR: "umma-lowrank", ENGINE_UMMA_F8: "umma-factor-f8"}
+CAND_UNIFORM, CAND_GRID = 1, 2
 
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -55,6 +56,8 @@ SIGNATURES = {
     "sspbo_blr_import": (_i, [_vp, _vp, _d, _vp]),
     "sspbo_blr_predict": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sspbo_score": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sspbo_score_generated": (_i, [_vp, _i, _u64, _vp, _pi, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sspbo_set_operand_format": (_i, [_vp, _i]),
     "sspbo_key_unpack": (None, [_u64, C.POINTER(C.c_float), C.POINTER(_i64)]),
     "sspbo_key_pack": (_u64, [C.c_float, _i64]),
     "sspbo_last_engine": (_i, [_vp]),

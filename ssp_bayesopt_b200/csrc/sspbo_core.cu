@@ -6,7 +6,7 @@
 //   BayesianLinearRegression.*     blr.py:27-97
 //   SSPSpace.decode('from-set')    sspspace.py:352-356
 //   SSPSpace.get_sample_points     sspspace.py:488-495
-#include "sspbo_internal.cuh"
+#include "sspbo_lr_common.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <new>
@@ -514,15 +514,19 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
 // Flagged candidates of the low-rank pass, re-scored in float64 in the same low-rank form (no cancellation issue at
 // 1e-16): var = 1/beta + 1/alpha - sum_j (v_j . psi)^2, mu = m' . psi.  One CTA per group of EX_G candidates
 // (persistent over the device-side count), psi in shared memory, one warp per row of V.
-template <typename XT>
+// FULL: the same pass with the float64 psi-space covariance itself, var = 1/beta + psi^T Sp psi (d rows of length d instead
+// of the r rows of V): for posteriors whose low-rank rows are not available (rank > SSPBO_LR_MAX, imported state), flagged by
+// the factor form of the fp16 + e4m3 scorer.  `Vd` then points at Sp and `r` is d.
+template <typename XT, bool FULL>
 __global__ void __launch_bounds__(EXL_THREADS)
-k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
+k_exact_lowrank(const XT* __restrict__ x, const sspbo_lr::CandDesc cand, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
                 unsigned int cap, const double* __restrict__ A_turns, const double* __restrict__ tau_turns, int n, int K, int L,
                 double dc_value, int normalize, const int* __restrict__ inv_perm, const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
                 double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
                 float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
     __shared__ double red[EX_G + 1][EXL_THREADS / 32];
+    __shared__ double xs_gen[EX_G][sspbo_lr::MAX_N];   // rows of a generated candidate set (cand.mode != 0, L == 1)
     const int d = 2 * K + 1;
     const unsigned long long c0 = *count_ptr;
     if (c0 > cap) return;                               // list overflowed: the host recomputes the call with the dense factor
@@ -531,11 +535,17 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
     unsigned long long my_best = 0ull;
     for (int64_t base = (int64_t)blockIdx.x * EX_G; base < count; base += (int64_t)gridDim.x * EX_G) {
         __syncthreads();
+        if (cand.mode != 0) {
+            if (threadIdx.x < EX_G && base + threadIdx.x < count)
+                sspbo_lr::cand_row_rt(cand, n, index0 + (int64_t)list[base + threadIdx.x], xs_gen[threadIdx.x]);
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < EX_G * (K + 1); i += blockDim.x) {
             const int c = i / (K + 1), f = i - c * (K + 1);
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
                 if (f == 0) cs = dc_value;
+                else if (cand.mode != 0) psi_entry(xs_gen[c], A_turns, tau_turns, n, K, L, f - 1, cs, sn);
                 else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
@@ -556,7 +566,10 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
                 for (int c = 0; c < EX_G; ++c) acc[c] = fma(v, psi_s[c * d + k], acc[c]);
             }
 #pragma unroll
-            for (int c = 0; c < EX_G; ++c) { const double yj = warp_sum(acc[c]); q[c] = fma(yj, yj, q[c]); }
+            for (int c = 0; c < EX_G; ++c) {
+                const double yj = warp_sum(acc[c]);
+                q[c] = FULL ? fma(psi_s[c * d + j], yj, q[c]) : fma(yj, yj, q[c]);     // psi_j (Sp psi)_j  /  (v_j . psi)^2
+            }
         }
         if (lane == 0) {
 #pragma unroll
@@ -579,7 +592,7 @@ k_exact_lowrank(const XT* __restrict__ x, const unsigned int* __restrict__ list,
                 const double dc = psi_s[warp * d + inv_perm[0]];
                 const double nrm2 = (2.0 * ss - dc * dc) / (double)d;                   // |phi|^2 = psi^T D psi (= 1 when L == 1)
                 if (normalize) { u *= rsqrt(nrm2); qq /= nrm2; }                        // phi / |phi|
-                const double var = inv_beta + (prior_var * (normalize ? 1.0 : nrm2) - qq);   // blr.py:96
+                const double var = FULL ? inv_beta + qq : inv_beta + (prior_var * (normalize ? 1.0 : nrm2) - qq);   // blr.py:96
                 const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
                 const int64_t row = (int64_t)list[base + warp];
                 if (mu_out) mu_out[row] = (float)u;
@@ -970,6 +983,7 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 }
 
 static void free_blr(sspbo_ctx* ctx) {
+    sspbo_f8_release(ctx);
     dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
@@ -989,6 +1003,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
     dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     dev_free(&ctx->aa_work);
+    if (ctx->gen_rows) cudaFree(ctx->gen_rows);
     if (ctx->eval_dev) cudaFree(ctx->eval_dev);
     if (ctx->obs_pin) { cudaFreeHost(ctx->obs_pin); cudaFree(ctx->obs_x); }
     if (ctx->obs_event) cudaEventDestroy(ctx->obs_event);
@@ -1305,6 +1320,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->perm, perm.data(), d * sizeof(int), cudaMemcpyHostToDevice));
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->inv_perm, inv.data(), d * sizeof(int), cudaMemcpyHostToDevice));
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->col_of_rank, col.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+            ctx->host_col_of_rank = col;
             for (int kb = 0; kb < 32; ++kb) {
                 int cnt = 0;
                 for (int r = 0; r < d; ++r) cnt += (col[r] < 64 * (kb + 1));
@@ -1330,7 +1346,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
             (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)SSPBO_FLAG_CAP)))
             return rc;
     }
-    ctx->blr_ready = true; ctx->operands_dirty = true;
+    ctx->blr_ready = true; ctx->operands_dirty = true; ctx->f8_factor_dirty = true;
     SSPBO_CUDA(ctx, cudaDeviceSynchronize());
     return SSPBO_OK;
 }
@@ -1439,15 +1455,15 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
             }
             k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
             SSPBO_LAUNCH_CHECK(ctx);
+            ctx->v8_row0_dirty = true;
         }
-        ctx->operands_dirty = true; ctx->factor_dirty = true;
+        ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
     }
     return SSPBO_OK;
 }
 
-int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
+int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
-    if (!ctx->operands_dirty) return SSPBO_OK;
     const int d = ctx->d;
     if (ctx->factor_dirty) {                                    // L = chol(Sp), blocked, in place on a copy
         SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->R, ctx->Sp, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1465,6 +1481,15 @@ int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
         }
         ctx->factor_dirty = false;
     }
+    return SSPBO_OK;
+}
+
+int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st) {
+    if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
+    if (!ctx->operands_dirty) return SSPBO_OK;
+    const int d = ctx->d;
+    int rc = sspbo_refresh_factor(ctx, st);
+    if (rc) return rc;
     k_refresh_operands<<<dim3((ctx->dp + 255) / 256, d), 256, 0, st>>>(ctx->R, ctx->mp, ctx->perm, d, ctx->dp, ctx->Rt_f32,
                                                                     ctx->mp_f32);
     SSPBO_LAUNCH_CHECK(ctx);
@@ -1530,7 +1555,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
         off += cnt[i];
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
-    ctx->operands_dirty = true; ctx->factor_dirty = true;
+    ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
     if (ctx->has_factor) {
         double rank = -1.0;                                      // the rows of V travel with the packed state
         SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1540,6 +1565,8 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
         const size_t img = (size_t)(SSPBO_LR_MAX + 1) * ctx->KC_pad * sizeof(__half);
         SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->Vh, 0, img, st));
         SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->Vl, 0, img, st));
+        if (ctx->V8) SSPBO_CUDA(ctx, cudaMemsetAsync(ctx->V8, 0, 2 * img, st));
+        ctx->v8_rank = 0; ctx->v8_row0_dirty = true;
         ctx->lr_valid = rank >= 0.0 && rank <= (double)SSPBO_LR_MAX;
         ctx->lr_rank = ctx->lr_valid ? (int)rank : 0;
         if (ctx->lr_valid && ctx->lr_rank > 0) {
@@ -1570,29 +1597,42 @@ extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, d
 }
 
 // ------------------------------------------------------------------------------------ K2 dispatch
+// float64 pass over the candidates a tensor pass flagged (device-side list and count): the low-rank form over the rows of V
+// while they are valid, else the quadratic form with the psi-space covariance
+static int score_flagged_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t N, int64_t index0, double lam, double gamma_t,
+                                float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+    const int d = ctx->d;
+    const size_t smem = (size_t)EX_G * d * sizeof(double);
+    const int gx = 2 * ctx->sm_count;
+    const bool full = !ctx->lr_valid;
+    const double* rows = full ? ctx->Sp : ctx->Vd;
+    const int r = full ? d : ctx->lr_rank;
+#define SSPBO_FLAGGED_LAUNCH(XT, FULL)                                                                                             \
+    do {                                                                                                                           \
+        SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<XT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_exact_lowrank<XT, FULL><<<gx, EXL_THREADS, smem, st>>>((const XT*)cand.x, cand, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR, \
+            SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm,   \
+            ctx->perm, rows, r, ctx->mp, 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);             \
+    } while (0)
+    if (cand.x_f64) { if (full) SSPBO_FLAGGED_LAUNCH(double, true); else SSPBO_FLAGGED_LAUNCH(double, false); }
+    else { if (full) SSPBO_FLAGGED_LAUNCH(float, true); else SSPBO_FLAGGED_LAUNCH(float, false); }
+#undef SSPBO_FLAGGED_LAUNCH
+    SSPBO_LAUNCH_CHECK(ctx);
+    k_flag_fold<<<1, 1, 0, st>>>(ctx->stats, SSPBO_FLAG_CAP, (unsigned long long)N);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
 int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, bool from_flag_list, int64_t index0,
                              double lam, double gamma_t, float* mu, float* var, float* acq, unsigned long long* best,
                              cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     const int d = ctx->d;
-    if (from_flag_list) {                               // flagged by the low-rank pass: float64 low-rank form
-        const size_t smem = (size_t)EX_G * d * sizeof(double);
-        const int gx = 2 * ctx->sm_count;
-        if (x_dtype == SSPBO_F32) {
-            SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_exact_lowrank<float><<<gx, EXL_THREADS, smem, st>>>((const float*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
-                1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
-        } else {
-            SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_exact_lowrank<double><<<gx, EXL_THREADS, smem, st>>>((const double*)x, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR,
-                SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm, ctx->perm, ctx->Vd, ctx->lr_rank, ctx->mp,
-                1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);
-        }
-        SSPBO_LAUNCH_CHECK(ctx);
-        k_flag_fold<<<1, 1, 0, st>>>(ctx->stats, SSPBO_FLAG_CAP, (unsigned long long)N);
-        SSPBO_LAUNCH_CHECK(ctx);
-        return SSPBO_OK;
+    if (from_flag_list) {
+        sspbo_lr::CandDesc cand;
+        memset(&cand, 0, sizeof(cand));
+        cand.x = x; cand.x_f64 = (x_dtype == SSPBO_F64);
+        return score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
     }
     // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs, so that a handful of candidates (eval(x_t))
     // spreads over the machine instead of streaming all of Sp through one SM
@@ -1626,50 +1666,141 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     return SSPBO_OK;
 }
 
-extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, double lam, double gamma_t,
-                           float* mu, float* var, float* acq, unsigned long long* best, int engine, void* stream) {
-    if (!ctx) return SSPBO_EINVAL;
+// rows [index0, index0 + N) of a generated candidate set written out for the engines that read explicit rows
+static int materialise_rows(sspbo_ctx* ctx, sspbo_lr::CandDesc* cand, int64_t N, int64_t index0, cudaStream_t st) {
+    const int n = ctx->n;
+    const size_t bytes = (size_t)N * n * (cand->mode == 1 ? sizeof(float) : sizeof(double));
+    if (bytes > ctx->gen_rows_bytes) {
+        if (ctx->gen_rows) { SSPBO_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->gen_rows); ctx->gen_rows = nullptr; ctx->gen_rows_bytes = 0; }
+        SSPBO_CUDA(ctx, cudaMalloc(&ctx->gen_rows, bytes));
+        ctx->gen_rows_bytes = bytes;
+    }
+    const int64_t total = N * n;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    if (cand->mode == 1) {
+        k_fill_uniform<<<blocks, 256, 0, st>>>(cand->seed, index0 * n, total, (float*)ctx->gen_rows);
+        cand->x_f64 = 0;
+    } else {
+        GridDesc g; g.n = n;
+        for (int a = 0; a < n; ++a) { g.counts[a] = (int)cand->counts[a]; g.offs[a] = cand->offs[a]; }
+        k_grid_points<<<blocks, 256, 0, st>>>(cand->axes, g, index0, N, (double*)ctx->gen_rows);
+        cand->x_f64 = 1;
+    }
+    SSPBO_LAUNCH_CHECK(ctx);
+    cand->x = ctx->gen_rows; cand->mode = 0;
+    return SSPBO_OK;
+}
+
+static int score_dispatch(sspbo_ctx* ctx, sspbo_lr::CandDesc cand, int64_t N, int64_t index0, double lam, double gamma_t,
+                          float* mu, float* var, float* acq, unsigned long long* best, int engine, cudaStream_t st) {
     if (!ctx->blr_ready || !ctx->has_beta) SSPBO_FAIL(ctx, SSPBO_ESTATE, "score: BLR posterior (and beta) must be set first");
-    if (N < 0 || (N > 0 && !x)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: null candidates");
-    if (x_dtype != SSPBO_F32 && x_dtype != SSPBO_F64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown dtype %d", x_dtype);
     if (index0 < 0 || index0 + N > 0xffffffffLL) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: candidate index must stay below 2^32");
     if (!(gamma_t >= 0)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: gamma_t must be >= 0");
-    if (engine < SSPBO_ENGINE_AUTO || engine > SSPBO_ENGINE_UMMA_LR) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown engine %d", engine);
+    if (engine < SSPBO_ENGINE_AUTO || engine > SSPBO_ENGINE_UMMA_F8) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown engine %d", engine);
     if (N == 0) return SSPBO_OK;
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
-    const bool lr_ok = sspbo_score_lr_supported(ctx) && N < 0xffffffffLL;     // covers n <= 16, the dense kernel n <= 8
+    // low-rank form: split-fp16 operands (one chunk, rank <= 255) and / or fp16 + e4m3 operands (rank <= 511)
+    const bool lr16_ok = sspbo_score_lr_supported(ctx) && ctx->operand_format != 1;
+    const bool lr8_ok = sspbo_score_f8_supported(ctx, 0) && ctx->operand_format != 0;
+    const bool lr_ok = lr16_ok || lr8_ok;
+    const bool f8_ok = sspbo_score_f8_supported(ctx, 1) != 0;
     if (engine == SSPBO_ENGINE_UMMA && !umma_ok)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: tcgen05 engine does not cover d=%d L=%d", ctx->d, ctx->L);
     if (engine == SSPBO_ENGINE_UMMA_LR && !lr_ok)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: low-rank tcgen05 engine needs 1 <= rank <= %d rows appended since blr_init "
-                   "(rank %d, valid %d) and L == 1", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid);
+                   "(rank %d, valid %d, operand format %d)", SSPBO_LR_MAX, ctx->lr_rank, (int)ctx->lr_valid, ctx->operand_format);
+    if (engine == SSPBO_ENGINE_UMMA_F8 && !f8_ok)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score: factor-form tcgen05 engine does not cover d=%d n=%d L=%d", ctx->d, ctx->n, ctx->L);
     if (engine == SSPBO_ENGINE_AUTO) {
+        const bool lr_wanted = lr_ok && !ctx->lr_disabled;
         if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
-        else if (N >= 1024 && lr_ok && !ctx->lr_disabled &&
-                 2 * (ctx->lr_rank + 1) <= (ctx->d >= 128 ? 3 : 1) * ctx->d)
-            engine = SSPBO_ENGINE_UMMA_LR;                      // low-rank form while it is cheaper than the triangular factor:
-        else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;   // measured crossover at rank ~ 1.5 d for d = 151 (tools/
-                                                                     // rank_crossover.py), never below rank 256 for d >= 511
+        else if (N >= 1024 && f8_ok && !ctx->f8_disabled)       // whichever form passes fewer operand rows x k-blocks per tile
+            engine = (lr_wanted && sspbo_f8_cost(ctx, 0) <= sspbo_f8_cost(ctx, 1)) ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA_F8;
+        else if (N >= 1024 && lr_wanted && 2 * (ctx->lr_rank + 1) <= (ctx->d >= 128 ? 3 : 1) * ctx->d)
+            engine = SSPBO_ENGINE_UMMA_LR;
+        else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;
         else engine = SSPBO_ENGINE_SIMT;
     }
     ctx->last_engine = engine;
+    if (cand.mode != 0 && engine != SSPBO_ENGINE_UMMA_LR && engine != SSPBO_ENGINE_UMMA_F8) {
+        int rc = materialise_rows(ctx, &cand, N, index0, st);
+        if (rc) return rc;
+    }
+    const void* x = cand.x;
+    const int x_dtype = cand.x_f64 ? SSPBO_F64 : SSPBO_F32;
     if (engine == SSPBO_ENGINE_EXACT)
         return sspbo_score_exact_launch(ctx, x, x_dtype, N, false, index0, lam, gamma_t, mu, var, acq, best, st);
     if (engine == SSPBO_ENGINE_UMMA_LR) {
-        int rc = sspbo_score_lr_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+        // operand format: split fp16 while the kernel is bound by generating psi, fp16 + e4m3 once the tensor pipe binds
+        const int bn = (ctx->lr_rank + 1 + 15) / 16 * 16;
+        const bool use16 = lr16_ok && (!lr8_ok || ctx->operand_format == 0 || bn <= SSPBO_F8_MIN_BN - 16);
+        int rc = use16 ? sspbo_score_lr_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st)
+                       : sspbo_score_f8_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, 0, st);
         if (rc) return rc;
         // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
         if (sspbo_debug_env() & 4) return SSPBO_OK;              // timing experiments only (compiled out of product builds)
-        return sspbo_score_exact_launch(ctx, x, x_dtype, N, true, index0, lam, gamma_t, mu, var, acq, best, st);
+        return score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
+    }
+    if (engine == SSPBO_ENGINE_UMMA_F8) {
+        int rc = sspbo_score_f8_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, 1, st);
+        if (rc) return rc;
+        // float64 pass over the candidates whose variance is a small fraction of the prior's (SSPBO_F8_FLAG_FRACTION)
+        return score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
     }
     int rc = sspbo_refresh_operands(ctx, st);
     if (rc) return rc;
     if (engine == SSPBO_ENGINE_UMMA)
         return sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
     return sspbo_score_simt_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+}
+
+extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, double lam, double gamma_t,
+                           float* mu, float* var, float* acq, unsigned long long* best, int engine, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (N < 0 || (N > 0 && !x)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: null candidates");
+    if (x_dtype != SSPBO_F32 && x_dtype != SSPBO_F64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score: unknown dtype %d", x_dtype);
+    sspbo_lr::CandDesc cand;
+    memset(&cand, 0, sizeof(cand));
+    cand.x = x; cand.x_f64 = (x_dtype == SSPBO_F64);
+    return score_dispatch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, engine, (cudaStream_t)stream);
+}
+
+/* Fused scoring of a candidate set that is GENERATED inside the kernel (no HBM or PCIe byte per candidate): rows
+ * [index0, index0 + N) of the counter-based uniform stream of sspbo_fill_uniform (kind SSPBO_CAND_UNIFORM, `seed`), or of
+ * the grid of sspbo_grid_points (kind SSPBO_CAND_GRID: axes_dev / counts_host as there; SSPSpace.get_sample_points('grid'),
+ * sspspace.py:488-495).  Keys carry the global row index.  Engines that read explicit rows get them written to a scratch
+ * buffer first. */
+extern "C" int sspbo_score_generated(sspbo_ctx* ctx, int kind, uint64_t seed, const double* axes_dev, const int* counts_host,
+                                     int64_t N, int64_t index0, double lam, double gamma_t, float* mu, float* var, float* acq,
+                                     unsigned long long* best, int engine, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "score_generated before space_set");
+    if (ctx->L != 1) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "score_generated: trajectory contexts take explicit candidate rows");
+    if (N < 0 || index0 < 0) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_generated: negative range");
+    sspbo_lr::CandDesc cand;
+    memset(&cand, 0, sizeof(cand));
+    if (kind == SSPBO_CAND_UNIFORM) {
+        cand.mode = 1; cand.seed = seed;
+    } else if (kind == SSPBO_CAND_GRID) {
+        if (!axes_dev || !counts_host) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_generated: grid needs axes and counts");
+        cand.mode = 2; cand.axes = axes_dev;
+        int off = 0; double total = 1.0;
+        for (int a = 0; a < ctx->n; ++a) {
+            if (counts_host[a] < 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_generated: counts must be >= 1");
+            cand.counts[a] = (unsigned int)counts_host[a]; cand.offs[a] = off; off += counts_host[a]; total *= counts_host[a];
+        }
+        if ((double)(index0 + N) > total) SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_generated: range exceeds the grid");
+    } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "score_generated: unknown kind %d", kind);
+    return score_dispatch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, engine, (cudaStream_t)stream);
+}
+
+extern "C" int sspbo_set_operand_format(sspbo_ctx* ctx, int format) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (format < -1 || format > 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "operand format: -1 (by rank), 0 (split fp16) or 1 (fp16 + e4m3)");
+    ctx->operand_format = format;
+    return SSPBO_OK;
 }
 
 /* counters of the low-rank pass since the last reset; synchronises `stream`.  Applies the engine policy: when more
@@ -1716,6 +1847,9 @@ extern "C" int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_
     if (flagged) *flagged = (int64_t)h[SSPBO_STAT_FLAGGED];
     if (overflow) *overflow = (int64_t)h[SSPBO_STAT_OVERFLOW];
     if (out_of_range) *out_of_range = (int64_t)h[SSPBO_STAT_OOR];
+    // more flagged candidates than the list holds: the low-rank form gives way to the factor form, and that one (whose own
+    // flags then overflowed as well) to the engines that never flag
+    if (h[SSPBO_STAT_OVERFLOW] > 0 && (ctx->lr_disabled || !ctx->lr_valid)) ctx->f8_disabled = true;
     if (h[SSPBO_STAT_OVERFLOW] > 0 || (h[SSPBO_STAT_SCORED] >= 4096 && h[SSPBO_STAT_FLAGGED] * 100 > h[SSPBO_STAT_SCORED]))
         ctx->lr_disabled = true;
     if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
@@ -1861,7 +1995,7 @@ extern "C" int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, i
 }
 extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled) {
     if (!ctx) return SSPBO_EINVAL;
-    if (lowrank_enabled >= 0) ctx->lr_disabled = !lowrank_enabled;
+    if (lowrank_enabled >= 0) { ctx->lr_disabled = !lowrank_enabled; if (lowrank_enabled) ctx->f8_disabled = false; }
     if (phase32_enabled >= 0) {                          // 0: Q31.32 only; 1: fastest valid path; 2: fixed point only (no float32 chain)
         ctx->p32_disabled = (phase32_enabled == 0);
         ctx->pf32_disabled = (phase32_enabled == 2);

@@ -71,6 +71,7 @@ struct sspbo_ctx {
     double export_rank = -1.0;       // staging scalar of sspbo_blr_export
     bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)
     bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead
+    bool f8_disabled = false;        // policy: the factor form's own flag list overflowed, AUTO uses the engines that never flag
     bool p32_disabled = false;       // policy: candidates outside the declared |x| bound were seen
     // 32-bit fixed-point phase tables (fast generator of the tcgen05 scorer), valid when p32_ok
     int* A32_op = nullptr;           // (KC_pad/2) x n, Q(31-fa).fa turns per unit
@@ -108,6 +109,15 @@ struct sspbo_ctx {
     // opaque state of the tcgen05 engines (tensor maps etc.)
     void* umma = nullptr;
     void* lr_state = nullptr;
+    void* f8_state = nullptr;
+    // fp16 + e4m3 operand format (sspbo_score_f8.cu), built lazily: V8 = e4m3 companion of (Vh, Vl), rows 1 .. v8_rank
+    // current; (Fh, F8) = images of [m'; L^T] for the factor form
+    uint8_t* V8 = nullptr; int v8_rank = 0; bool v8_row0_dirty = true;
+    __half* Fh = nullptr; uint8_t* F8 = nullptr; bool f8_factor_dirty = true;
+    int operand_format = -1;         // policy: -1 = by rank, 0 = split fp16 only (rank <= 255), 1 = fp16 + e4m3 whenever usable
+    std::vector<int> host_col_of_rank;           // host copy of col_of_rank (chunk geometry of the factor form)
+    // scratch rows for generated candidate sets scored by an engine that reads explicit rows
+    void* gen_rows = nullptr; size_t gen_rows_bytes = 0;
 };
 
 #define SSPBO_FAIL(ctx, code, ...)                                         \
@@ -132,11 +142,18 @@ struct sspbo_ctx {
         SSPBO_CUDA(ctx, cudaGetLastError());         \
     } while (0)
 
-constexpr int SSPBO_LR_MAX = 255;               // largest rank scored in low-rank form (m' + 255 rows = one 256-row MMA operand)
+constexpr int SSPBO_LR_MAX = 511;               // largest rank scored in low-rank form (m' + 511 rows = two 256-row MMA operands)
 // The tensor core accumulates in float32 with truncation: |V psi|^2 carries a relative error of ~2e-5 (measured), i.e.
 // 2e-5 / alpha absolute on the variance.  Candidates whose variance is below this fraction of the prior variance
 // 1/alpha would exceed the 1e-4 tolerance after the subtraction and are re-scored by the exact float64 engine.
 constexpr double SSPBO_LR_FLAG_FRACTION = 0.3;
+// operand rows (BN, a multiple of 16) from which the low-rank form runs with fp16 + e4m3 operands (sspbo_score_f8.cu): below,
+// the kernel is bound by generating psi and the split-fp16 format (cheaper to generate) is as fast
+constexpr int SSPBO_F8_MIN_BN = 112;
+// Factor form with fp16 + e4m3 operands: the e4m3 corrections leave ~2^-15 of the LARGEST products in |R psi|^2, which
+// reaches 1e-4 of the sum for candidates almost on top of an observation; candidates whose variance is below this fraction
+// of the prior variance |phi|^2 / alpha are re-scored by the float64 pass (measured on B200: 1.3e-4 at 0.3 % of the prior).
+constexpr double SSPBO_F8_FLAG_FRACTION = 0.1;
 constexpr unsigned SSPBO_FLAG_CAP = 1u << 17;    // flagged candidates per sspbo_score call that get the exact pass
 // device counters (unsigned long long each)
 enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (reset by its exact pass)
@@ -196,11 +213,14 @@ int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
 // one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
                            double* vd_row, double* obs_out, cudaStream_t st);
-// low-rank engine with the A operand in tensor memory (sspbo_score_lr.cu), ranks 1 .. 256
+// low-rank engines with the A operand in tensor memory: prototypes in sspbo_lr_common.cuh (they take a candidate descriptor)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);
-int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
-                          float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
 void sspbo_lr_release(sspbo_ctx* ctx);
+void sspbo_f8_release(sspbo_ctx* ctx);
+int sspbo_score_f8_supported(const sspbo_ctx* ctx, int form);
+double sspbo_f8_cost(const sspbo_ctx* ctx, int form);
+// L = chol(Sp) into ctx->R when the psi-space covariance changed since the last factorisation
+int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st);
 // CUtensorMap (passed as void*) of a K-major fp16 operand [rows x KC_pad], box 64 columns x BN rows, 128-byte swizzle
 int sspbo_make_map_f16(sspbo_ctx* ctx, void* map, const void* base, int KC_pad, int rows, int BN);
 int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st);

@@ -28,46 +28,12 @@
 // 256-column accumulator beyond (the epilogue then sits between two tiles).
 //
 // Replaces SSPAgent.eval (agents/ssp_agent.py:125-137) + np.argmax (experiments/demo_blr_gif.py:129-136).
-#include "sspbo_internal.cuh"
-#include "sspbo_tc.cuh"
+#include "sspbo_lr_common.cuh"
 #include <stdlib.h>
 
 namespace {
 using namespace sspbo_tc;
-
-constexpr int BM = 128;                 // candidates per tile (UMMA M)
-constexpr int BK = 64;                  // operand columns per k-block
-#ifndef SSPBO_LR_GEN_W
-#define SSPBO_LR_GEN_W 3
-#endif
-constexpr int NF = 16;                  // frequencies per generator thread and pass (two passes per k-block)
-constexpr int GEN_W = SSPBO_LR_GEN_W;   // generator warps per TMEM lane quadrant (= per SM sub-partition), k-blocks in rotation
-constexpr int GEN_WARPS = 4 * GEN_W, EPI_WARPS = 4;
-constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_GEN0 = WARP_EPI0 + EPI_WARPS;
-constexpr int THREADS = 32 * (WARP_GEN0 + GEN_WARPS);            // 576 with three generator warps per quadrant
-constexpr int NA_MAX = 6;               // A ring slots in TMEM: 4 behind 128-column accumulators, 6 behind 64-column ones
-constexpr int A_SLOT_COLS = 64;         // 32 columns hi + 32 columns lo (two fp16 per column)
-constexpr uint32_t TMEM_COLS = 512, ACC_COLS_MAX = 128;
-constexpr int MAX_NB = 8;
-constexpr int NRM_DEPTH = 8;            // tiles in flight between generator and epilogue (power of two)
-constexpr int MAX_N = 16;
-
-struct Params {
-    const void* x; int x_f64; long long N; long long index0;
-    const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
-    // trajectory mode: L waypoints per candidate; per-timestep phase offsets (L x KC_pad/2): Q0.64 turns / float32 radians
-    int L; const unsigned long long* tauq; const float* tauf; float nrm_scale, nrm_offset;   // |phi|^2 = nrm_scale * sum(C^2 + S^2) - nrm_offset
-    int KC_pad, BN, n_chunks, n_kb, nb;
-    int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating by tile (1 or 2)
-    int split_issue;                    // BN > 128: next k-block's barrier waits between the two halves of the MMAs
-    int merged;                         // BN <= 128: hi|lo tiles of the B slot read as ONE 2 BN-row operand (two MMAs per K step)
-    float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
-    int normalize;                      // trajectory mode: score phi / |phi| (multi-agent trajectories)
-    float *mu, *var, *acq;
-    unsigned long long* best;
-    unsigned int* flag_idx; unsigned long long* stats; unsigned int flag_cap;
-    int debug;
-};
+using namespace sspbo_lr;
 
 // PH: phase arithmetic of the generator: 0 = Q31.32 x Q31.32 (any range), 1 = 32-bit fixed point (fa + fx = 55),
 // 2 = float32 FMA chain in radians (|theta| <= 32 pi by the declared bounds: rounding < 2e-5 rad)
@@ -101,17 +67,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    if constexpr (PH == 1 || PH == 2) {
-        // axis-major inside every block of NF frequencies: one LDS.128 feeds four independent multiply-add chains
-        int* A32_s = (int*)tables;
-        const int* src = PH == 1 ? p.A32_op : (const int*)p.Af_op;
-        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) {
-            const int f = i / NDIM, a = i - f * NDIM;
-            A32_s[((f / NF) * NDIM + a) * NF + (f % NF)] = src[i];
-        }
-    } else {
-        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += THREADS) Aq_s[i] = p.Aq_op[i];
-    }
+    load_tables<NDIM, PH>(p, tables, THREADS);
     if constexpr (TRAJ) {
         for (int i = threadIdx.x; i < NRM_DEPTH * GEN_W * BM; i += THREADS) nrm_part[i] = 0.f;
     }
@@ -408,38 +364,11 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 nrm_acc = 0.f;
                 g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
                 if constexpr (!TRAJ) {
-                if constexpr (PH == 2) {
-                    bool oor = false;
-#pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
-                        float v0 = 0.f;
-                        if (g0 < N) v0 = p.x_f64 ? (float)((const double*)p.x)[g0 * NDIM + a] : ((const float*)p.x)[g0 * NDIM + a];
-                        oor |= !(fabsf(v0) <= p.x_absmax);
-                        xq0[a] = __float_as_int(v0);
-                    }
-                    if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
-                } else if constexpr (PH == 1) {
-                    bool oor = false;
-#pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
-                        double v0 = 0.0;
-                        if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                        v0 *= p.x_scale;
-                        oor |= !(fabs(v0) < 2147483647.0);
-                        xq0[a] = __double2int_rn(v0);
-                    }
-                    if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
-                } else {
-#pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
-                        double v0 = 0.0;
-                        if (g0 < N) v0 = p.x_f64 ? ((const double*)p.x)[g0 * NDIM + a] : (double)((const float*)p.x)[g0 * NDIM + a];
-                        x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
-                    }
-                }
+                const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0);
+                if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
                 const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it towards the SM now
-                if (member == 0 && gn < N) {
-                    const char* nx = (const char*)p.x + (size_t)gn * NDIM * (p.x_f64 ? 8 : 4);
+                if (member == 0 && gn < N && p.cand.mode == 0) {
+                    const char* nx = (const char*)p.cand.x + (size_t)gn * NDIM * (p.cand.x_f64 ? 8 : 4);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
                 }
@@ -450,109 +379,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
-                if constexpr (TRAJ) {
-                    // sum over the L waypoints of exp(i (A_f . x_j + tau_jf)); waypoints are re-read per k-block (L1 / L2)
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) { cs[i] = 0.f; sn[i] = 0.f; }
-                    const int nf = p.KC_pad >> 1, fbase = kb * 32 + half * NF;
-                    for (int j = 0; j < p.L; ++j) {
-                        if constexpr (PH == 2) {
-                            float xf[NDIM];
-#pragma unroll
-                            for (int a = 0; a < NDIM; ++a) {
-                                const size_t o = ((size_t)g0 * p.L + j) * NDIM + a;
-                                xf[a] = (g0 < N) ? (p.x_f64 ? (float)__ldg((const double*)p.x + o) : __ldg((const float*)p.x + o)) : 0.f;
-                            }
-                            if (kb == 0 && half == 0) {                   // once per row: waypoints outside the declared |x| bound
-                                bool oor = false;
-#pragma unroll
-                                for (int a = 0; a < NDIM; ++a) oor |= !(fabsf(xf[a]) <= p.x_absmax);
-                                if (oor) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);
-                            }
-                            const float* Afblk = (const float*)tables + (size_t)fbase * NDIM;      // [axis][NF]
-                            const float* tf = p.tauf + (size_t)j * nf + fbase;
-#pragma unroll
-                            for (int i = 0; i < NF; ++i) {
-                                float t = __ldg(tf + i);
-#pragma unroll
-                                for (int a = 0; a < NDIM; ++a) t = fmaf(Afblk[a * NF + i], xf[a], t);
-                                float s_, c_;
-                                __sincosf(t, &s_, &c_);
-                                cs[i] += c_; sn[i] += s_;
-                            }
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < NDIM; ++a) {
-                                const size_t o = ((size_t)g0 * p.L + j) * NDIM + a;
-                                double v0 = 0.0;
-                                if (g0 < N) v0 = p.x_f64 ? __ldg((const double*)p.x + o) : (double)__ldg((const float*)p.x + o);
-                                x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
-                            }
-                            const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)fbase * NDIM;
-                            const unsigned long long* tq = p.tauq + (size_t)j * nf + fbase;
-#pragma unroll
-                            for (int i = 0; i < NF; ++i) {
-                                unsigned long long t = __ldg(tq + i);
-#pragma unroll
-                                for (int a = 0; a < NDIM; ++a) t += Ablk[i * NDIM + a] * x0[a];
-                                const float a0 = (float)(int)(t >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
-                                cs[i] += __cosf(a0); sn[i] += __sinf(a0);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) nrm_acc = fmaf(cs[i], cs[i], fmaf(sn[i], sn[i], nrm_acc));
-                } else if (SSPBO_DBG_BITS(p) & 2) {
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
-                } else if constexpr (PH == 2) {
-                    const float* Afblk = (const float*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF], radians per unit
-                    float t[NF];
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) t[i] = Afblk[i] * __int_as_float(xq0[0]);
-#pragma unroll
-                    for (int a = 1; a < NDIM; ++a) {
-#pragma unroll
-                        for (int i = 0; i < NF; ++i) t[i] = fmaf(Afblk[a * NF + i], __int_as_float(xq0[a]), t[i]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) __sincosf(t[i], &sn[i], &cs[i]);       // one RZ multiply by 1/2pi, then MUFU.SIN / MUFU.COS (the MUFU reduces the range itself)
-                } else if constexpr (PH == 1) {
-                    const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF]
-                    long long t[NF];                                      // phase in turns at bit 55
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) t[i] = (long long)A32blk[i] * (long long)xq0[0];
-#pragma unroll
-                    for (int a = 1; a < NDIM; ++a) {
-#pragma unroll
-                        for (int i = 0; i < NF; ++i) t[i] += (long long)A32blk[a * NF + i] * (long long)xq0[a];   // IMAD.WIDE
-                    }
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) {
-                        // bits [32, 55) = top 23 bits of the phase mod 1; flipping the top one adds 1/2 turn, and with
-                        // the exponent of 1.0 they are the mantissa of f in [1, 2): (f - 1.5) 2 pi is the phase in
-                        // radians in [-pi, pi).  One LOP3: (hi & 0x7fffff) ^ 0x3fc00000.
-                        const float f0 = __uint_as_float(lop3_and_xor((unsigned int)((unsigned long long)t[i] >> 32), 0x7fffffu, 0x3fc00000u));
-                        const float a0 = fmaf(f0, 6.283185307179586f, -9.42477796076938f);
-                        cs[i] = __cosf(a0); sn[i] = __sinf(a0);
-                    }
-                } else {
-                    const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)(kb * 32 + half * NF) * NDIM;
-                    unsigned long long t[NF];                             // phase in turns, Q0.64, wraps modulo 1
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) t[i] = 0ull;
-#pragma unroll
-                    for (int a = 0; a < NDIM; ++a) {
-#pragma unroll
-                        for (int i = 0; i < NF; ++i) t[i] += Ablk[i * NDIM + a] * x0[a];
-                    }
-#pragma unroll
-                    for (int i = 0; i < NF; ++i) {
-                        // top 32 bits as a signed fraction of a turn in [-1/2, 1/2) -> radians in [-pi, pi)
-                        const float a0 = (float)(int)(t[i] >> 32) * 1.4629180792671596e-9f;   // 2 pi / 2^32
-                        cs[i] = __cosf(a0); sn[i] = __sinf(a0);
-                    }
-                }
+                gen_half<NDIM, PH, TRAJ>(p, tables, g0, kb, half, x0, xq0, cs, sn, nrm_acc);
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
                 for (int i = 0; i < NF / 2; ++i) {
@@ -607,7 +434,6 @@ size_t table_bytes(const sspbo_ctx* ctx) {
 }
 
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
-constexpr int MAX_TRAJ_N = 3;           // waypoint dimension of the trajectory instantiations
 template <int PH>
 kernel_fn kernel_for_n(int n) {
     switch (n) {
@@ -639,7 +465,7 @@ kernel_fn kernel_for(int n, int ph, bool traj) {
 
 }  // namespace
 
-// ranks this engine covers (beyond them the dense factor of sspbo_score_umma.cu is as fast)
+// ranks this engine covers in its own operand format: one chunk of <= 256 rows
 int sspbo_score_lr_supported(const sspbo_ctx* ctx) {
     if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
     if (ctx->cc_major != 10 || !ctx->has_factor) return 0;
@@ -651,13 +477,50 @@ void sspbo_lr_release(sspbo_ctx* ctx) {
     if (ctx->lr_state) { delete (LrState*)ctx->lr_state; ctx->lr_state = nullptr; }
 }
 
-int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, float lam, float gamma_t,
+// phase path: float32 FMA chain when the declared bounds keep |theta| small, 32-bit fixed point when they allow it,
+// Q31.32 otherwise (or after candidates outside the declared bound were seen)
+int sspbo_lr_phase_path(const sspbo_ctx* ctx) {
+    int ph = 0;
+    const bool traj = ctx->L != 1;
+    if (!ctx->p32_disabled) ph = (ctx->pf32_ok && !ctx->pf32_disabled) ? 2 : (ctx->p32_ok ? 1 : 0);
+    if ((traj || ctx->n > 8) && ph == 1) ph = 0;         // trajectories and n > 8: float32 chain or Q31.32
+    if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
+    if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
+    return ph;
+}
+
+// the launch parameters that do not depend on the operand format
+void sspbo_lr_fill_common(const sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
+                          float* mu, float* var, float* acq, unsigned long long* best, int ph, Params* pp) {
+    Params& p = *pp;
+    memset(&p, 0, sizeof(p));
+    p.cand = cand; p.N = N; p.index0 = index0;
+    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.Af_op = ctx->Af_op; p.mscale = ctx->mscale;
+    p.x_scale = ph == 1 ? ldexp(1.0, ctx->p32_fx) : 0.0; p.x_absmax = (float)(ctx->x_absmax * 1.000001);
+    p.KC_pad = ctx->KC_pad; p.n_kb = ctx->KC_pad / BK;
+    p.n_chunks = 1; p.bpt = p.n_kb;
+    p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
+    p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
+    p.prior_var = (float)(1.0 / ctx->alpha);
+    p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
+    p.mu = mu; p.var = var; p.acq = acq; p.best = best;
+    p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
+    p.L = ctx->L; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
+    {   // |phi|^2 = (1/d) (psi_0^2 + 2 sum_{k>=1} (C_k^2 + S_k^2)); the generators sum C^2 + S^2 over every operand frequency,
+        // including the DC term (= dc^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
+        const double d = (double)ctx->d, L2 = (double)ctx->L * ctx->L;
+        const int n_pad = ctx->KC_pad / 2 - 1 - ctx->K;
+        p.nrm_scale = (float)(2.0 / d); p.nrm_offset = (float)((ctx->dc * ctx->dc + 2.0 * n_pad * L2) / d);
+        p.normalize = ctx->normalize ? 1 : 0;
+    }
+    p.debug = sspbo_debug_env();
+}
+
+int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
                           float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
     LrState* ls = (LrState*)ctx->lr_state;
     if (!ls) { ls = new LrState(); ctx->lr_state = ls; }
     if (!ls->max_smem) cudaDeviceGetAttribute(&ls->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    Params p;
-    memset(&p, 0, sizeof(p));
     const int r = ctx->lr_rank + 1;                      // + row 0 (m')
     // One chunk of BN = ceil16(r) <= 256 rows (a tcgen05.mma costs ~100 cycles or more whatever N is, so the fewest,
     // widest instructions win): two accumulator buffers alternating by tile while BN <= 128, a single 256-column one
@@ -676,24 +539,18 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
     const size_t smem = 1024 + (size_t)nb * sb + tb;
-    // phase path: float32 FMA chain when the declared bounds keep |theta| small, 32-bit fixed point when they allow it,
-    // Q31.32 otherwise (or after candidates outside the declared bound were seen)
-    int ph = 0;
+    const int ph = sspbo_lr_phase_path(ctx);
     const bool traj = ctx->L != 1;
-    if (!ctx->p32_disabled) ph = (ctx->pf32_ok && !ctx->pf32_disabled) ? 2 : (ctx->p32_ok ? 1 : 0);
-    if ((traj || ctx->n > 8) && ph == 1) ph = 0;         // trajectories and n > 8: float32 chain or Q31.32
-    if (sspbo_debug_env() & 8) ph = 0;                   // timing experiments only (compiled out of product builds)
-    if (sspbo_debug_env() & 16) ph = ctx->p32_ok ? 1 : 0;
+    if (traj && cand.mode != 0) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: generated candidates need L == 1");
     kernel_fn kern = kernel_for(ctx->n, ph, traj);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: domain dimension %d not instantiated", ctx->n);
     if (!ls->attr_set[traj][ph][ctx->n]) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ls->max_smem));
         ls->attr_set[traj][ph][ctx->n] = true;
     }
-    p.x = x; p.x_f64 = (x_dtype == SSPBO_F64); p.N = N; p.index0 = index0;
-    p.Aq_op = ctx->Aq_op; p.A32_op = ctx->A32_op; p.Af_op = ctx->Af_op; p.mscale = ctx->mscale;
-    p.x_scale = ph == 1 ? ldexp(1.0, ctx->p32_fx) : 0.0; p.x_absmax = (float)(ctx->x_absmax * 1.000001);
-    p.KC_pad = ctx->KC_pad; p.BN = bn; p.n_chunks = nc; p.n_kb = ctx->KC_pad / BK; p.nb = nb;
+    Params p;
+    sspbo_lr_fill_common(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, ph, &p);
+    p.BN = bn; p.nb = nb;
     // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
     // BN <= 128: merged operand, the accumulator is 2 BN wide
     p.merged = bn <= 128;
@@ -712,21 +569,6 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N,
     if (p.na > NA_MAX) p.na = NA_MAX;
     if (p.na < GEN_W)                                     // every generator warp of a quadrant owns a slot of the rotation
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: %d A slots for %d generator warps per quadrant", p.na, GEN_W);
-    p.inv_beta = (float)(1.0 / ctx->beta); p.lam = lam; p.gamma_t = gamma_t;
-    p.inv_rscale2 = (float)(1.0 / (ctx->r_scale * ctx->r_scale));
-    p.prior_var = (float)(1.0 / ctx->alpha);
-    p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
-    p.mu = mu; p.var = var; p.acq = acq; p.best = best;
-    p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
-    p.L = ctx->L; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
-    {   // |phi|^2 = (1/d) (psi_0^2 + 2 sum_{k>=1} (C_k^2 + S_k^2)); the generators sum C^2 + S^2 over every operand frequency,
-        // including the DC term (= dc^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
-        const double d = (double)ctx->d, L2 = (double)ctx->L * ctx->L;
-        const int n_pad = ctx->KC_pad / 2 - 1 - ctx->K;
-        p.nrm_scale = (float)(2.0 / d); p.nrm_offset = (float)((ctx->dc * ctx->dc + 2.0 * n_pad * L2) / d);
-        p.normalize = ctx->normalize ? 1 : 0;
-    }
-    p.debug = sspbo_debug_env();
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p);

@@ -13,6 +13,10 @@ import numpy as np
 from . import _lib
 
 
+# engines whose fast phase path may ask for a recomputation (candidates outside the declared |x| bound, flag-list overflow)
+_RERUN_ENGINES = (_lib.ENGINE_UMMA_LR, _lib.ENGINE_UMMA_F8)
+
+
 def _torch():
     import torch
     return torch
@@ -273,10 +277,60 @@ class DeviceEngine:
             self._check(rc, "sspbo_score")
         call()
         self._pending.append(call)
-        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR
+        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) in _RERUN_ENGINES
         if want_outputs and self._lr_used and self._needs_rerun():   # outputs are about to be read: settle them now
             self._replay()
         return self._best, outs
+
+    def score_generated(self, kind, N, lam, gamma_t, index0=0, seed=0, axes=None, want_outputs=False,
+                        engine=_lib.ENGINE_AUTO, reset_best=True):
+        """Fused scoring of rows [index0, index0 + N) of a candidate set generated inside the kernel: kind 'uniform'
+        (counter-based uniform(0, 1) stream, `seed`) or 'grid' (`axes`: per-axis numpy arrays, reference meshgrid order).
+        No candidate byte is read from HBM or the host.  Returns (best_key_tensor, (mu, var, acq) | None)."""
+        torch = self.torch
+        outs, ptrs = None, [None, None, None]
+        if want_outputs:
+            outs = tuple(torch.empty(N, dtype=torch.float32, device=self._dev()) for _ in range(3))
+            ptrs = [C.c_void_p(t.data_ptr()) for t in outs]
+        if kind == "uniform":
+            code, ax_ptr, cnt_ptr, keep = _lib.CAND_UNIFORM, None, None, None
+        elif kind == "grid":
+            counts = np.array([len(a) for a in axes], dtype=np.int32)
+            assert len(axes) == self.n, f"Expected {self.n} axes, got {len(axes)}"
+            flat = self._grid_axes_device(axes)
+            code, ax_ptr, cnt_ptr, keep = _lib.CAND_GRID, C.c_void_p(flat.data_ptr()), counts.ctypes.data_as(_lib._pi), (flat, counts)
+        else:
+            raise ValueError(f"unknown generated candidate kind {kind!r}")
+        if reset_best:
+            self._best.zero_()
+            self._pending = []
+            self._lr_used = False
+
+        def call():
+            rc = self.lib.sspbo_score_generated(self._ctx, code, int(seed), ax_ptr, cnt_ptr, int(N), int(index0), float(lam),
+                                                float(gamma_t), ptrs[0], ptrs[1], ptrs[2], C.c_void_p(self._best.data_ptr()),
+                                                int(engine), self._stream())
+            self._check(rc, "sspbo_score_generated")
+        call()
+        self._pending.append(call)
+        self._gen_keep = keep
+        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) in _RERUN_ENGINES
+        if want_outputs and self._lr_used and self._needs_rerun():
+            self._replay()
+        return self._best, outs
+
+    def _grid_axes_device(self, axes):
+        """per-axis values concatenated on the device; cached while the same arrays are passed"""
+        key = tuple((id(a), len(a)) for a in axes)
+        cached = getattr(self, "_axes_cache", None)
+        if cached is None or cached[0] != key:
+            flat = self.to_device(np.concatenate([np.asarray(a, dtype=np.float64) for a in axes]), self.torch.float64)
+            self._axes_cache = (key, flat, list(axes))
+        return self._axes_cache[1]
+
+    def set_operand_format(self, fmt):
+        """Operand format of the low-rank tensor-memory engine: None / -1 by rank, 0 split fp16, 1 fp16 + e4m3."""
+        self._check(self.lib.sspbo_set_operand_format(self._ctx, -1 if fmt is None else int(fmt)), "sspbo_set_operand_format")
 
     def eval_host(self, x, lam, gamma_t, engine=_lib.ENGINE_AUTO):
         """(mu, var, acq) as float64 numpy arrays with a single device->host copy (SSPAgent.eval)."""
@@ -311,7 +365,7 @@ class DeviceEngine:
             self._check(rc, "sspbo_score")
         call()
         self._pending.append(call)
-        if self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR:
+        if self.lib.sspbo_last_engine(self._ctx) in _RERUN_ENGINES:
             self._lr_used = True
             if self._needs_rerun():
                 self._replay()
@@ -347,7 +401,7 @@ class DeviceEngine:
         call = lambda: self._score_host_stream(xt, N, lam, gamma_t, index0, engine, chunk, first_piece, growth)
         call()
         self._pending.append(call)
-        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) == _lib.ENGINE_UMMA_LR
+        self._lr_used = self._lr_used or self.lib.sspbo_last_engine(self._ctx) in _RERUN_ENGINES
         return self._best
 
     def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk, first_piece=None, growth=1.5):
@@ -410,15 +464,20 @@ class DeviceEngine:
             self._pending = []
 
     def _replay(self):
-        """Recompute every score call since the last key reset (the context has switched to the safe engines)."""
+        """Recompute every score call since the last key reset (the context has switched to a safer engine: low-rank form ->
+        factor form -> the engines that never flag; fast phase path -> Q31.32)."""
         calls, self._pending = self._pending, []
-        self._best.zero_()
-        for c in calls:
-            c()
+        st = None
+        for _ in range(3):
+            self._best.zero_()
+            for c in calls:
+                c()
+            st = self.score_stats(reset=True)
+            if not st["rerun"]:
+                break
         self._pending = calls
-        st = self.score_stats(reset=True)
         if st["rerun"]:
-            raise _lib.SspboError(f"scoring still asks for a rerun after the policy switch: {st}")
+            raise _lib.SspboError(f"scoring still asks for a rerun after the policy switches: {st}")
 
     def best(self):
         """(score, index) of the packed key; synchronises.  If the low-rank pass overflowed its flag list or saw
