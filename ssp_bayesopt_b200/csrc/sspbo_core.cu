@@ -435,6 +435,7 @@ __global__ void k_mp_op(const double* __restrict__ mp, const int* __restrict__ p
 // =====================================================================================
 constexpr int EX_G = 8, EX_THREADS = 256, EX_RB_MAX = 16;
 constexpr int EXL_THREADS = 512;    // flagged-candidate pass: few groups in flight, so many warps per group
+constexpr int EXL_JB = 4;           // rows of V per warp and pass (register blocking against the shared-memory reads of psi)
 
 template <typename XT>
 __global__ void __launch_bounds__(EX_THREADS)
@@ -555,20 +556,37 @@ k_exact_lowrank(const XT* __restrict__ x, const sspbo_lr::CandDesc cand, const u
         double q[EX_G];
 #pragma unroll
         for (int c = 0; c < EX_G; ++c) q[c] = 0.0;
-        for (int j = warp; j < r; j += EXL_THREADS / 32) {
-            const double* vrow = Vd + (size_t)j * d;
-            double acc[EX_G];
+        // EXL_JB rows per warp and pass: every psi value read from shared memory feeds EXL_JB FMAs (one row per pass is
+        // bound by the shared-memory operand traffic, 8 B per FMA: ~16 FMA/clk/SM)
+        for (int j0 = warp * EXL_JB; j0 < r; j0 += (EXL_THREADS / 32) * EXL_JB) {
+            const double* vrow[EXL_JB];
 #pragma unroll
-            for (int c = 0; c < EX_G; ++c) acc[c] = 0.0;
+            for (int jj = 0; jj < EXL_JB; ++jj) vrow[jj] = Vd + (size_t)min(j0 + jj, r - 1) * d;
+            double acc[EXL_JB][EX_G];
+#pragma unroll
+            for (int jj = 0; jj < EXL_JB; ++jj)
+#pragma unroll
+                for (int c = 0; c < EX_G; ++c) acc[jj][c] = 0.0;
             for (int k = lane; k < d; k += 32) {
-                const double v = vrow[k];
+                double v[EXL_JB], ps[EX_G];
 #pragma unroll
-                for (int c = 0; c < EX_G; ++c) acc[c] = fma(v, psi_s[c * d + k], acc[c]);
+                for (int jj = 0; jj < EXL_JB; ++jj) v[jj] = vrow[jj][k];
+#pragma unroll
+                for (int c = 0; c < EX_G; ++c) ps[c] = psi_s[c * d + k];
+#pragma unroll
+                for (int jj = 0; jj < EXL_JB; ++jj)
+#pragma unroll
+                    for (int c = 0; c < EX_G; ++c) acc[jj][c] = fma(v[jj], ps[c], acc[jj][c]);
             }
 #pragma unroll
-            for (int c = 0; c < EX_G; ++c) {
-                const double yj = warp_sum(acc[c]);
-                q[c] = FULL ? fma(psi_s[c * d + j], yj, q[c]) : fma(yj, yj, q[c]);     // psi_j (Sp psi)_j  /  (v_j . psi)^2
+            for (int jj = 0; jj < EXL_JB; ++jj) {
+                if (j0 + jj < r) {                                                      // warp-uniform
+#pragma unroll
+                    for (int c = 0; c < EX_G; ++c) {
+                        const double yj = warp_sum(acc[jj][c]);
+                        q[c] = FULL ? fma(psi_s[c * d + j0 + jj], yj, q[c]) : fma(yj, yj, q[c]);   // psi_j (Sp psi)_j  /  (v_j . psi)^2
+                    }
+                }
             }
         }
         if (lane == 0) {
@@ -1340,7 +1358,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
         ctx->factor_dirty = true;
     }
     ctx->has_factor = with_factor;
-    ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false;
+    ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false; ctx->lr_flag_frac = 0.0;
     if (with_factor && !ctx->stats) {
         if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
             (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)SSPBO_FLAG_CAP)))
@@ -1702,7 +1720,7 @@ static int score_dispatch(sspbo_ctx* ctx, sspbo_lr::CandDesc cand, int64_t N, in
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool umma_ok = sspbo_score_umma_supported(ctx) != 0;
     // low-rank form: split-fp16 operands (one chunk, rank <= 255) and / or fp16 + e4m3 operands (rank <= 511)
-    const bool lr16_ok = sspbo_score_lr_supported(ctx) && ctx->operand_format != 1;
+    const bool lr16_ok = sspbo_score_lr_supported(ctx) && ctx->operand_format < 1;
     const bool lr8_ok = sspbo_score_f8_supported(ctx, 0) && ctx->operand_format != 0;
     const bool lr_ok = lr16_ok || lr8_ok;
     const bool f8_ok = sspbo_score_f8_supported(ctx, 1) != 0;
@@ -1798,7 +1816,8 @@ extern "C" int sspbo_score_generated(sspbo_ctx* ctx, int kind, uint64_t seed, co
 
 extern "C" int sspbo_set_operand_format(sspbo_ctx* ctx, int format) {
     if (!ctx) return SSPBO_EINVAL;
-    if (format < -1 || format > 1) SSPBO_FAIL(ctx, SSPBO_EINVAL, "operand format: -1 (by rank), 0 (split fp16) or 1 (fp16 + e4m3)");
+    if (format < -1 || format > 2)
+        SSPBO_FAIL(ctx, SSPBO_EINVAL, "operand format: -1 (by rank), 0 (split fp16), 1 (fp16 + e4m3, single CTAs) or 2 (fp16 + e4m3, CTA pairs)");
     ctx->operand_format = format;
     return SSPBO_OK;
 }
@@ -1853,6 +1872,8 @@ extern "C" int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_
     if (h[SSPBO_STAT_OVERFLOW] > 0 || (h[SSPBO_STAT_SCORED] >= 4096 && h[SSPBO_STAT_FLAGGED] * 100 > h[SSPBO_STAT_SCORED]))
         ctx->lr_disabled = true;
     if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
+    if (ctx->last_engine == SSPBO_ENGINE_UMMA_LR && h[SSPBO_STAT_SCORED] >= 4096)
+        ctx->lr_flag_frac = (double)h[SSPBO_STAT_FLAGGED] / (double)h[SSPBO_STAT_SCORED];
     if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0) ? 1 : 0;
     return SSPBO_OK;
 }

@@ -114,7 +114,8 @@ struct sspbo_ctx {
     // current; (Fh, F8) = images of [m'; L^T] for the factor form
     uint8_t* V8 = nullptr; int v8_rank = 0; bool v8_row0_dirty = true;
     __half* Fh = nullptr; uint8_t* F8 = nullptr; bool f8_factor_dirty = true;
-    int operand_format = -1;         // policy: -1 = by rank, 0 = split fp16 only (rank <= 255), 1 = fp16 + e4m3 whenever usable
+    double lr_flag_frac = 0.0;       // flagged / scored of the last read-back of a low-rank pass (cost model of ENGINE_AUTO)
+    int operand_format = -1;         // policy: -1 = by rank, 0 = split fp16 only (rank <= 255), 1 / 2 = fp16 + e4m3 whenever usable (single CTAs / CTA pairs)
     std::vector<int> host_col_of_rank;           // host copy of col_of_rank (chunk geometry of the factor form)
     // scratch rows for generated candidate sets scored by an engine that reads explicit rows
     void* gen_rows = nullptr; size_t gen_rows_bytes = 0;
@@ -148,8 +149,10 @@ constexpr int SSPBO_LR_MAX = 511;               // largest rank scored in low-ra
 // 1/alpha would exceed the 1e-4 tolerance after the subtraction and are re-scored by the exact float64 engine.
 constexpr double SSPBO_LR_FLAG_FRACTION = 0.3;
 // operand rows (BN, a multiple of 16) from which the low-rank form runs with fp16 + e4m3 operands (sspbo_score_f8.cu): below,
-// the kernel is bound by generating psi and the split-fp16 format (cheaper to generate) is as fast
-constexpr int SSPBO_F8_MIN_BN = 112;
+// the kernel is bound by generating psi and the split-fp16 format (cheaper to generate, two MMAs per K step through the
+// merged hi|lo operand up to 128 rows) is faster: measured on C3, rank 100 / 127: 1.57 / 1.47e9 against 1.33 / 1.35e9
+// candidates/s; from 144 rows on the split format needs three MMAs per K step and loses (rank 128: 1.27 against 1.32e9)
+constexpr int SSPBO_F8_MIN_BN = 144;
 // Factor form with fp16 + e4m3 operands: the e4m3 corrections leave ~2^-15 of the LARGEST products in |R psi|^2, which
 // reaches 1e-4 of the sum for candidates almost on top of an observation; candidates whose variance is below this fraction
 // of the prior variance |phi|^2 / alpha are re-scored by the float64 pass (measured on B200: 1.3e-4 at 0.3 % of the prior).

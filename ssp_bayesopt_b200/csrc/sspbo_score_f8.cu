@@ -55,7 +55,13 @@ __device__ __forceinline__ void split_pair_f8(float a, float b, uint32_t& hi, ui
     l8 = e4m3x2_of_half2(*reinterpret_cast<uint32_t*>(&l));
 }
 
-template <int NDIM, int PH, bool TRAJ>
+// PAIR: two CTAs of a cluster (one TPC) share every MMA through cta_group::2: a tile is 256 candidates, 128 per CTA (each its
+// own generators, A ring and accumulator in its own tensor memory); each CTA streams only HALF of the operand rows of B into
+// its shared memory and the tensor cores of both SMs read both halves.  At 256 operand rows a single CTA has to pull 64 KB
+// per k-block from L2 and the MMA warp ends up waiting for B (ncu: profiles/r2_f8_r255_*); the pair pulls 32 KB per SM.  The
+// even CTA issues the MMAs; its a_full / b_full / tmem_empty barriers collect the arrivals of both CTAs, and every commit
+// is multicast to the a_empty / b_empty / tmem_full barriers of both.
+template <int NDIM, int PH, bool TRAJ, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_8, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,7 +70,10 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NA = NA_F8;
     const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = (uint32_t)(p.n_bufs * p.acc_cols);
-    const int b_tile_bytes = p.BN * BK * 2;                                 // fp16 tile: 64 K x 2 B; e4m3 tile: 128 K x 1 B
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr int TILE_M = PAIR ? 2 * BM : BM;                              // candidates per tile
+    const int bn_cta = PAIR ? p.BN / 2 : p.BN;                              // operand rows this CTA holds in shared memory
+    const int b_tile_bytes = bn_cta * BK * 2;                               // fp16 tile: 64 K x 2 B; e4m3 tile: 128 K x 1 B
     const int b_slot_bytes = 2 * b_tile_bytes;
     uint8_t* b_ring = smem;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
@@ -88,23 +97,30 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     for (int i = threadIdx.x; i < p.KC_pad; i += THREADS) mp_s[i] = p.mp_op[i];
     for (int i = threadIdx.x; i < (TRAJ ? 2 : 1) * NRM_DEPTH * GEN_W * BM; i += THREADS) mu_part[i] = 0.f;
     if (warp == WARP_TMA && lane == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), PAIR ? 8 : 4); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS * 32); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS * 32); }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();          // the partner's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long n_tiles = (p.N + BM - 1) / BM;
+    const long long n_tiles = (p.N + TILE_M - 1) / TILE_M;
     const int n_kb = p.n_kb, n_chunks = p.n_chunks, bpt = p.bpt;
-    const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile walkers: a single CTA, or the pair (both CTAs walk the same tiles, 128 rows each)
+    const long long walker = PAIR ? blockIdx.x >> 1 : blockIdx.x, n_walkers = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const long long my_tiles = (n_tiles > walker) ? (n_tiles - walker + n_walkers - 1) / n_walkers : 0;
     const long long total_blocks = my_tiles * bpt;
     const uint32_t buf_mask = (uint32_t)(p.n_bufs - 1);
 
@@ -117,29 +133,85 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     for (int kb = p.kb0[c]; kb < n_kb; ++kb) {
                         mbar_wait_relaxed<64>(b_empty(rb.slot), rb.phase ^ 1);
                         uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
-                        mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
-                        tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, p.b_row0 + c * p.BN);
-                        tma_load_2d(smem_u32(st + b_tile_bytes), &map_8, b_full(rb.slot), kb * 2 * BK, p.b_row0 + c * p.BN);
+                        if constexpr (PAIR) {                             // my half of the chunk's rows; bytes of both halves land on the even CTA's barrier
+                            if (cta_rank == 0) mbar_expect_tx(b_full(rb.slot), 2u * (uint32_t)b_slot_bytes);
+                            const int row = p.b_row0 + c * p.BN + (int)cta_rank * bn_cta;
+                            tma_load_2d_pair(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, row);
+                            tma_load_2d_pair(smem_u32(st + b_tile_bytes), &map_8, b_full(rb.slot), kb * 2 * BK, row);
+                        } else {
+                            mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
+                            tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, p.b_row0 + c * p.BN);
+                            tma_load_2d(smem_u32(st + b_tile_bytes), &map_8, b_full(rb.slot), kb * 2 * BK, p.b_row0 + c * p.BN);
+                        }
                         rb.advance(p.nb);
                     }
         }
-    } else if (warp == WARP_MMA) {
-        // ================================ MMA issuer ================================
+    } else if (warp == WARP_MMA && cta_rank == 0) {
+        // ================================ MMA issuer (the even CTA of a pair) ================================
         // Warp-uniform walk over the CTA's k-block sequence (tiles x chunks x k-blocks); the waits for k-block i + 1 sit
         // between the two halves of the MMAs of k-block i, so the tensor pipe has queued work while this warp polls.
         Ring ra, rb;
         uint32_t acc_phase[2] = {0, 0};
-        const uint32_t idesc = make_idesc(BM, p.BN);
+        const uint32_t idesc = make_idesc(TILE_M, p.BN);
         const bool no_mma = (SSPBO_DBG_BITS(p) & 1) != 0;
         const uint64_t b_desc0 = make_desc_sw128(smem_u32(b_ring));       // slot s: start address + s * slot bytes (16 B units)
         const uint32_t b_slot_units = (uint32_t)(b_slot_bytes >> 4), b_8_units = (uint32_t)(b_tile_bytes >> 4);
         const uint32_t a_ring0 = tmem_base + A_RING_COL0;
-        if (total_blocks > 0) {
+        if (total_blocks > 0 && p.split_issue) {
             mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
             mbar_wait(b_full(rb.slot), rb.phase);
         }
         int c = 0, kb = p.kb0[0];
         uint32_t cc = 0;                                                  // running chunk counter: accumulator buffer = cc & mask
+        if (!p.split_issue) {
+            // One thread walks the sequence: wait for the operands of a k-block, issue its eight MMAs and the commits.  With
+            // 200+ operand rows the MMAs of one k-block keep the tensor pipe busy for ~1000 cycles, longer than this loop
+            // takes, so nothing is gained by interleaving the waits with the issue (the loop below), and its second elected
+            // section, reconvergence points and register -> uniform-register moves are all on the critical path of the
+            // generator -> MMA -> free-slot cycle.
+            if (lane == 0) {
+                uint32_t sa = 0, pa = 0, sb = 0, pb = 0, accph = 0;
+                int kb_first = kb;
+                for (uint32_t g = 0, gn = (uint32_t)total_blocks; g < gn; ++g) {
+                    const uint32_t buf = cc & buf_mask;
+                    const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                    const bool first = kb == kb_first, last = kb == n_kb - 1;
+                    if (first) {
+                        mbar_wait(tmem_empty(buf), ((accph >> buf) & 1u) ^ 1u);
+                        accph ^= 1u << buf;
+                    }
+                    mbar_wait(a_full((int)sa), pa);
+                    mbar_wait(b_full((int)sb), pb);
+                    tc_fence_after();
+                    const uint32_t a_hi = a_ring0 + sa * (uint32_t)A_SLOT_COLS, a_8 = a_hi + 32;
+                    const uint64_t b_hi = b_desc0 + (uint64_t)(sb * b_slot_units);
+                    const uint64_t b_8 = b_hi + b_8_units;
+                    if constexpr (PAIR) {
+                        umma_f16_ts_pair(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) umma_f16_ts_pair(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f8_ts_pair(d_tmem, a_8 + 8 * k, b_8 + 2 * k, idesc, 1u);
+                        umma_commit_pair(b_empty((int)sb));
+                        umma_commit_pair(a_empty((int)sa));
+                        if (last) umma_commit_pair(tmem_full(buf));
+                    } else {
+                        umma_f16_ts(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) umma_f16_ts_acc(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f8_ts_acc(d_tmem, a_8 + 8 * k, b_8 + 2 * k, idesc);
+                        umma_commit(b_empty((int)sb));
+                        umma_commit(a_empty((int)sa));
+                        if (last) umma_commit(tmem_full(buf));
+                    }
+                    if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; }
+                    if (++sb == (uint32_t)p.nb) { sb = 0; pb ^= 1u; }
+                    if (++kb == n_kb) { ++cc; if (++c == n_chunks) c = 0; kb = kb_first = p.kb0[c]; }
+                }
+            }
+            __syncwarp();
+        } else
         for (long long g = 0; g < total_blocks; ++g) {
             const uint32_t buf = cc & buf_mask;
             const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
@@ -156,10 +228,17 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             const uint64_t b_8 = b_hi + b_8_units;
             const uint32_t a_bar = a_empty(ra.slot), b_bar = b_empty(rb.slot);
             if (elect_one() && !no_mma) {
-                umma_f16_ts(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);  // the first MMA of a chunk overwrites the accumulator
-                umma_f16_ts_acc(d_tmem, a_hi + 8, b_hi + 2, idesc);
-                umma_f8_ts_acc(d_tmem, a_8, b_8, idesc);
-                umma_f8_ts_acc(d_tmem, a_8 + 8, b_8 + 2, idesc);
+                if constexpr (PAIR) {
+                    umma_f16_ts_pair(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+                    umma_f16_ts_pair(d_tmem, a_hi + 8, b_hi + 2, idesc, 1u);
+                    umma_f8_ts_pair(d_tmem, a_8, b_8, idesc, 1u);
+                    umma_f8_ts_pair(d_tmem, a_8 + 8, b_8 + 2, idesc, 1u);
+                } else {
+                    umma_f16_ts(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);  // the first MMA of a chunk overwrites the accumulator
+                    umma_f16_ts_acc(d_tmem, a_hi + 8, b_hi + 2, idesc);
+                    umma_f8_ts_acc(d_tmem, a_8, b_8, idesc);
+                    umma_f8_ts_acc(d_tmem, a_8 + 8, b_8 + 2, idesc);
+                }
             }
             __syncwarp();
             rb.advance(p.nb);
@@ -169,20 +248,32 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 mbar_wait(b_full(rb.slot), rb.phase);
             }
             if (elect_one()) {
-                if (!no_mma) {
-                    umma_f16_ts_acc(d_tmem, a_hi + 16, b_hi + 4, idesc);
-                    umma_f16_ts_acc(d_tmem, a_hi + 24, b_hi + 6, idesc);
-                    umma_f8_ts_acc(d_tmem, a_8 + 16, b_8 + 4, idesc);
-                    umma_f8_ts_acc(d_tmem, a_8 + 24, b_8 + 6, idesc);
+                if constexpr (PAIR) {
+                    if (!no_mma) {
+                        umma_f16_ts_pair(d_tmem, a_hi + 16, b_hi + 4, idesc, 1u);
+                        umma_f16_ts_pair(d_tmem, a_hi + 24, b_hi + 6, idesc, 1u);
+                        umma_f8_ts_pair(d_tmem, a_8 + 16, b_8 + 4, idesc, 1u);
+                        umma_f8_ts_pair(d_tmem, a_8 + 24, b_8 + 6, idesc, 1u);
+                    }
+                    umma_commit_pair(b_bar);                              // both CTAs' B slots, A slots, accumulators
+                    umma_commit_pair(a_bar);
+                    if (last) umma_commit_pair(tmem_full(buf));
+                } else {
+                    if (!no_mma) {
+                        umma_f16_ts_acc(d_tmem, a_hi + 16, b_hi + 4, idesc);
+                        umma_f16_ts_acc(d_tmem, a_hi + 24, b_hi + 6, idesc);
+                        umma_f8_ts_acc(d_tmem, a_8 + 16, b_8 + 4, idesc);
+                        umma_f8_ts_acc(d_tmem, a_8 + 24, b_8 + 6, idesc);
+                    }
+                    umma_commit(b_bar);                                   // frees the B slot when these MMAs retire
+                    umma_commit(a_bar);                                   // ... and the A slot
+                    if (last) umma_commit(tmem_full(buf));
                 }
-                umma_commit(b_bar);                                       // frees the B slot when these MMAs retire
-                umma_commit(a_bar);                                       // ... and the A slot
-                if (last) umma_commit(tmem_full(buf));
             }
             __syncwarp();
             if (++kb == n_kb) { ++cc; if (++c == n_chunks) c = 0; kb = p.kb0[c]; }
         }
-    } else if (warp < WARP_GEN0) {
+    } else if (warp >= WARP_EPI0 && warp < WARP_GEN0) {
         // ================================ epilogue ================================
         const int quad = warp & 3;                                        // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;
@@ -190,7 +281,7 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         uint32_t cc = 0;
         unsigned long long my_best = 0ull;
         for (long long t = 0; t < my_tiles; ++t) {
-            const long long tile = blockIdx.x + t * gridDim.x;
+            const long long tile = walker + t * n_walkers;
             float q = 0.f;
             for (int c = 0; c < n_chunks; ++c, ++cc) {
                 const uint32_t buf = cc & buf_mask;
@@ -219,9 +310,10 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     q += (q0 + q1) + (q2 + q3);
                 }
                 tc_fence_before();
-                mbar_arrive(tmem_empty(buf));
+                if constexpr (PAIR) { __syncwarp(); if (lane == 0) mbar_arrive_leader(tmem_empty(buf)); }
+                else mbar_arrive(tmem_empty(buf));
             }
-            const long long gi = tile * BM + row;
+            const long long gi = tile * TILE_M + (long long)cta_rank * BM + row;
             float mu = 0.f;
             {   // the generators' shares of mu = m' . psi (warps without a k-block in chunk 0 of a tile write nothing)
                 float* mp_ = mu_part + (size_t)(t & (NRM_DEPTH - 1)) * GEN_W * BM + row;
@@ -268,7 +360,7 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             if (other > my_best) my_best = other;
         }
         if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
-    } else {
+    } else if (warp >= WARP_GEN0) {
         // ================================ psi generators (A ring in tensor memory) ================================
         // GEN_W warps per TMEM lane quadrant (thread <-> candidate row); warp j of a quadrant produces the k-blocks
         // g = j, j + GEN_W, ... of the CTA's k-block sequence.  psi is regenerated for every chunk of a tile.
@@ -288,11 +380,11 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
                 loaded_iter = tile_iter;
                 nrm_acc = 0.f; mu_acc = 0.f;
-                g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
+                g0 = (walker + tile_iter * n_walkers) * TILE_M + (long long)cta_rank * BM + r0;
                 if constexpr (!TRAJ) {
                     const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0);
                     if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
-                    const long long gn = g0 + (long long)gridDim.x * BM; // next tile's row: pull it towards the SM now
+                    const long long gn = g0 + n_walkers * TILE_M;       // next tile's row: pull it towards the SM now
                     if (member == 0 && gn < p.N && p.cand.mode == 0) {
                         const char* nx = (const char*)p.cand.x + (size_t)gn * NDIM * (p.cand.x_f64 ? 8 : 4);
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
@@ -355,7 +447,7 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             tmem_st_wait();                                               // publish the k-block
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(slot));
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(a_full(slot)); else mbar_arrive(a_full(slot)); }
             slot += GEN_W; while (slot >= NA) { slot -= NA; phase ^= 1; }
             pos += GEN_W; while (pos >= bpt) { pos -= bpt; ++tile_iter; }
         }
@@ -363,11 +455,12 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 
     // ---- teardown ----
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();          // the partner has finished with my barriers and tensor memory
     if (warp == WARP_MMA) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -423,9 +516,9 @@ struct MapPair {
     int KC_pad = 0, BN = 0, rows = 0;
 };
 struct F8State {
-    MapPair lr, fac;
+    MapPair lr[2], fac[2];                                                // [single CTA, CTA pair (boxes of BN / 2 rows)]
     int max_smem = 0;
-    bool attr_set[2][3][MAX_N + 1] = {};
+    bool attr_set[2][2][3][MAX_N + 1] = {};
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
@@ -436,33 +529,38 @@ size_t table_bytes(const sspbo_ctx* ctx) {
 typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
 // instantiated for the domain dimensions the 1-chunk engine does not already serve well: every n <= 8 with the two 32-bit
 // phase paths, plus Q31.32 as the any-range fallback; trajectories with waypoints of up to 3 dimensions
-template <int PH>
+template <int PH, bool PAIR>
 kernel_fn kernel_for_n(int n) {
     switch (n) {
-        case 1: return k_score_f8<1, PH, false>; case 2: return k_score_f8<2, PH, false>; case 3: return k_score_f8<3, PH, false>;
-        case 4: return k_score_f8<4, PH, false>; case 5: return k_score_f8<5, PH, false>; case 6: return k_score_f8<6, PH, false>;
-        case 7: return k_score_f8<7, PH, false>; case 8: return k_score_f8<8, PH, false>;
+        case 1: return k_score_f8<1, PH, false, PAIR>; case 2: return k_score_f8<2, PH, false, PAIR>;
+        case 3: return k_score_f8<3, PH, false, PAIR>; case 4: return k_score_f8<4, PH, false, PAIR>;
+        case 5: return k_score_f8<5, PH, false, PAIR>; case 6: return k_score_f8<6, PH, false, PAIR>;
+        case 7: return k_score_f8<7, PH, false, PAIR>; case 8: return k_score_f8<8, PH, false, PAIR>;
     }
-    if constexpr (PH != 1) {
+    if constexpr (PH != 1 && !PAIR) {
         switch (n) {
-            case 9: return k_score_f8<9, PH, false>; case 10: return k_score_f8<10, PH, false>;
-            case 11: return k_score_f8<11, PH, false>; case 12: return k_score_f8<12, PH, false>;
-            case 13: return k_score_f8<13, PH, false>; case 14: return k_score_f8<14, PH, false>;
-            case 15: return k_score_f8<15, PH, false>; case 16: return k_score_f8<16, PH, false>;
+            case 9: return k_score_f8<9, PH, false, false>; case 10: return k_score_f8<10, PH, false, false>;
+            case 11: return k_score_f8<11, PH, false, false>; case 12: return k_score_f8<12, PH, false, false>;
+            case 13: return k_score_f8<13, PH, false, false>; case 14: return k_score_f8<14, PH, false, false>;
+            case 15: return k_score_f8<15, PH, false, false>; case 16: return k_score_f8<16, PH, false, false>;
         }
     }
     return nullptr;
 }
-template <int PH>
+template <int PH, bool PAIR>
 kernel_fn kernel_for_traj(int n) {
     switch (n) {
-        case 1: return k_score_f8<1, PH, true>; case 2: return k_score_f8<2, PH, true>; case 3: return k_score_f8<3, PH, true>;
+        case 1: return k_score_f8<1, PH, true, PAIR>; case 2: return k_score_f8<2, PH, true, PAIR>; case 3: return k_score_f8<3, PH, true, PAIR>;
     }
     return nullptr;
 }
-kernel_fn kernel_for(int n, int ph, bool traj) {
-    if (traj) return ph == 2 ? kernel_for_traj<2>(n) : kernel_for_traj<0>(n);
-    return ph == 2 ? kernel_for_n<2>(n) : (ph == 1 ? kernel_for_n<1>(n) : kernel_for_n<0>(n));
+template <bool PAIR>
+kernel_fn kernel_for_p(int n, int ph, bool traj) {
+    if (traj) return ph == 2 ? kernel_for_traj<2, PAIR>(n) : kernel_for_traj<0, PAIR>(n);
+    return ph == 2 ? kernel_for_n<2, PAIR>(n) : (ph == 1 ? kernel_for_n<1, PAIR>(n) : kernel_for_n<0, PAIR>(n));
+}
+kernel_fn kernel_for(int n, int ph, bool traj, bool pair) {
+    return pair ? kernel_for_p<true>(n, ph, traj) : kernel_for_p<false>(n, ph, traj);
 }
 
 int make_map_u8(sspbo_ctx* ctx, CUtensorMap* map, const void* base, int KC_pad, int rows, int BN) {
@@ -489,12 +587,25 @@ int make_map_u8(sspbo_ctx* ctx, CUtensorMap* map, const void* base, int KC_pad, 
     return SSPBO_OK;
 }
 
+// BN here = rows of one TMA box (the chunk's rows, or half of them when a CTA pair shares the chunk)
 int ensure_maps(sspbo_ctx* ctx, MapPair* mp, const void* bh, const void* b8, int KC_pad, int rows, int BN) {
     if (mp->bh == bh && mp->b8p == b8 && mp->KC_pad == KC_pad && mp->rows == rows && mp->BN == BN) return SSPBO_OK;
     int rc;
     if ((rc = sspbo_make_map_f16(ctx, &mp->hi, bh, KC_pad, rows, BN)) || (rc = make_map_u8(ctx, &mp->b8, b8, KC_pad, rows, BN))) return rc;
     mp->bh = bh; mp->b8p = b8; mp->KC_pad = KC_pad; mp->rows = rows; mp->BN = BN;
     return SSPBO_OK;
+}
+
+// CTA pairs pay off once a single CTA would wait for its B operand (BN > 128); operand format 1 keeps single CTAs, 2 pairs
+// wherever the shape allows (BN / 2 a multiple of 8 rows, the candidate set at least a few tiles per pair)
+bool want_pair(const sspbo_ctx* ctx, int bn, int64_t N) {
+    if (ctx->n > 8 || bn % 16 != 0 || ctx->sm_count < 2) return false;
+    if (ctx->operand_format == 1) return false;
+    // measured on C3 (tools/pair_check.py): never faster than single CTAs with the one-thread issue loop -- at 256 operand rows
+    // both sit at the rate the generators deliver psi (0.92-0.98e9 candidates/s), below that the pair's cross-CTA barriers cost
+    // 5-15 % -- so the pair is only run on request
+    (void)N;
+    return ctx->operand_format == 2;
 }
 
 // chunks of the factor-form operand: d rows in n_chunks chunks of BN rows
@@ -530,7 +641,9 @@ double sspbo_f8_cost(const sspbo_ctx* ctx, int form) {
     if (form == 0) {
         const int rows = ctx->lr_rank, nc = (rows + 255) / 256;
         const int bn = ((rows + nc - 1) / nc + 15) / 16 * 16;
-        return (double)nc * bn * n_kb;
+        // plus the float64 pass over the flagged candidates: one of its candidate-rows costs ~36 tensor-pass candidate-rows
+        // (measured at rank 511, 1.4 % flagged: 4.3 ms of 12.9 ms per 4.19M candidates)
+        return (double)nc * bn * n_kb * (1.0 + 36.0 * ctx->lr_flag_frac);
     }
     int bn, nc;
     factor_geometry(ctx, &bn, &nc);
@@ -551,9 +664,11 @@ int sspbo_score_f8_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
     Params p;
     sspbo_lr_fill_common(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, ph, &p);
     p.form = form; p.mp_op = ctx->mp_op;
+
     if (form == 1) p.flag_below = (float)(SSPBO_F8_FLAG_FRACTION / ctx->alpha);
     MapPair* mp;
     int rc;
+    bool pair = false;
     if (form == 0) {
         const int rows = ctx->lr_rank;                                    // rows 1 .. rank of the images (row 0 holds m')
         const int nc = (rows + 255) / 256;
@@ -569,8 +684,9 @@ int sspbo_score_f8_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
             SSPBO_LAUNCH_CHECK(ctx);
             ctx->v8_rank = ctx->lr_rank;
         }
-        mp = &fs->lr;
-        if ((rc = ensure_maps(ctx, mp, ctx->Vh, ctx->V8, KC, SSPBO_LR_MAX + 1, bn))) return rc;
+        pair = want_pair(ctx, bn, N);
+        mp = &fs->lr[pair];
+        if ((rc = ensure_maps(ctx, mp, ctx->Vh, ctx->V8, KC, SSPBO_LR_MAX + 1, pair ? bn / 2 : bn))) return rc;
         p.BN = bn; p.n_chunks = nc;
         for (int c = 0; c < nc; ++c) { p.kb0[c] = 0; p.pos0[c] = c * n_kb; }
         p.bpt = nc * n_kb;
@@ -594,8 +710,9 @@ int sspbo_score_f8_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
             SSPBO_LAUNCH_CHECK(ctx);
             ctx->f8_factor_dirty = false;
         }
-        mp = &fs->fac;
-        if ((rc = ensure_maps(ctx, mp, ctx->Fh, ctx->F8, KC, (int)rows, bn))) return rc;
+        pair = want_pair(ctx, bn, N);
+        mp = &fs->fac[pair];
+        if ((rc = ensure_maps(ctx, mp, ctx->Fh, ctx->F8, KC, (int)rows, pair ? bn / 2 : bn))) return rc;
         p.BN = bn; p.n_chunks = nc;
         int pos = 0;
         for (int c = 0; c < nc; ++c) {
@@ -605,21 +722,39 @@ int sspbo_score_f8_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
         }
         p.bpt = pos;
     }
-    const size_t tb = table_bytes(ctx), sb = 2 * (size_t)p.BN * BK * 2;
+    // MMA issue loop: the interleaved one while a k-block's MMAs are short (measured on C3: BN = 208 1.22e9 against 1.10e9
+    // candidates/s; BN = 256 0.84e9 against 0.92e9; factor form at d = 1023 0.33-0.44e9 against 0.40-0.48e9)
+    { static const int split_env = getenv("SSPBO_F8_SPLIT_ISSUE") ? atoi(getenv("SSPBO_F8_SPLIT_ISSUE")) : -1;
+      p.split_issue = split_env >= 0 ? split_env : (p.BN < 240 ? 1 : 0); }
+    const size_t tb = table_bytes(ctx), sb = 2 * (size_t)(pair ? p.BN / 2 : p.BN) * BK * 2;
     int nb = (int)(((size_t)fs->max_smem - 1024 - tb) / sb);
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "fp16+e4m3 tcgen05 engine: shared memory does not fit two B slots");
     p.nb = nb;
     const size_t smem = 1024 + (size_t)nb * sb + tb;
-    kernel_fn kern = kernel_for(ctx->n, ph, traj);
+    kernel_fn kern = kernel_for(ctx->n, ph, traj, pair);
     if (!kern) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "fp16+e4m3 tcgen05 engine: domain dimension %d not instantiated", ctx->n);
-    if (!fs->attr_set[traj][ph][ctx->n]) {
+    if (!fs->attr_set[pair][traj][ph][ctx->n]) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fs->max_smem));
-        fs->attr_set[traj][ph][ctx->n] = true;
+        fs->attr_set[pair][traj][ph][ctx->n] = true;
     }
     // TMEM: accumulator buffer(s) of BN columns first (two while BN <= 128), the four A slots behind them
     if (p.BN <= 128) { p.acc_cols = 128; p.n_bufs = 2; } else { p.acc_cols = 256; p.n_bufs = 1; }
     p.na = NA_F8;
+    if (pair) {
+        // clusters of two CTAs (one TPC): tiles of 256 candidates, one pair per two SMs
+        const long long tiles = (N + 2 * BM - 1) / (2 * BM);
+        const int pairs = (int)(tiles < ctx->sm_count / 2 ? tiles : ctx->sm_count / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SSPBO_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, mp->hi, mp->b8, p));
+        ++ctx->launches;
+        return SSPBO_OK;
+    }
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     kern<<<grid, THREADS, smem, st>>>(mp->hi, mp->b8, p);
