@@ -6,27 +6,38 @@
         bench.py --gpus N --steps K --warmup W
 
 Workload = BASELINE.json configs[2] ("C3"): RandomSSPSpace(n=6, ssp_dim=1024 -> d=1023, K=511), bounds [0,1]^6,
-length_scale 0.25, rng=0; posterior after 10 + 50 Hartmann-6 observations; 1e8 counter-based uniform float32
-candidates per BO step, sharded over 8 GPUs = 1.25e7 candidates per GPU per step (weak scaling: the per-GPU shard
-is fixed, so N GPUs score N * 1.25e7 candidates per step).  One step = score every local candidate with the
-fused kernel, max-reduce the packed (score, index) key over ranks, read the winner, evaluate Hartmann-6 on
-it and apply the float64 rank-one posterior update (so every step sees a new posterior).
+length_scale 0.25, rng=0; posterior after 10 + 50 Hartmann-6 observations (rank r = 10 + t, t = 50); 1e8
+counter-based uniform float32 candidates per BO step, sharded over 8 GPUs = 1.25e7 candidates per GPU per step (weak
+scaling: the per-GPU shard is fixed, so N GPUs score N * 1.25e7 candidates per step).  One step = score every local
+candidate with the fused kernel, max-reduce the packed (score, index) key over ranks, read the winner, evaluate Hartmann-6
+on it, apply the float64 rank-one posterior update -- and then put the rank-60 posterior back (a device-to-device import of
+the saved state, inside the timed step), so that the posterior rank, which the kernel's rate depends on, is the same in
+every step whatever --steps is.  `by_rank` gives the kernel-only rate at ranks 10 ... 1000 (full rank).
 
 `value`   candidates/s, whole job, candidates resident in HBM, device-timed (CUDA events, max over ranks).
-`e2e`     same metric through the public API (`SSPAgent.best_candidate`) from pinned HOST candidates: the
-          H2D copy of the shard and the D2H read of the winner are inside the timed region every step.
-`roofline` tensor-pipe: achieved = candidates * F_alg / kernel time, F_alg = 2 d^2 + 2 d + 2 K n flops
-          (SURVEY.md section 8d), peak = MEASURED_PEAKS.json bf16 dense (sustained, the kernel runs inside a long step).
-          While the posterior has rank r <= 512 the scorer uses the low-rank form (2 d r flops instead of 2 d^2), so
-          the algorithmic figure can exceed the dense-form peak; `executed` gives the tensor flops really issued, and
-          `by_rank` the kernel-only rate at other ranks and for the dense (full-factor) engine.
-`cpu_baseline` / `--impl reference`: the numpy oracle port of the reference path on the host cores.
+`e2e`     same metric through the public API (`SSPAgent.best_candidate`) from pinned HOST candidates: the H2D copy of the
+          shard and the D2H read of the winner are inside the timed region every step (all --steps of them).
+`roofline` the dominant kernel (the tcgen05 scorer): `achieved` = tensor flops it really issues per launch (3 split-fp16
+          products x 2 x 1024 x BN per candidate; BN = operand rows) / its average launch duration, measured with CUDA events on
+          the launching stream inside the timed region (sspbo_set_timing); `peak` = MEASURED_PEAKS.json sustained bf16.  The
+          dense-form algorithmic figure of SURVEY.md 8d (2 d^2 + 2 d + 2 K n flops per candidate) is kept under
+          `algorithmic_dense`: the low-rank form does less work than that, so it is not a utilisation figure.  `traffic` =
+          dram bytes per launch from the committed ncu capture (profiles/r2_roofline_traffic.json), null when absent.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (oracle/_ref, copied by oracle/build_ref.py) --
+          SSPAgent.eval + argmax over chunks -- on the host cores; the numpy oracle port when that copy is absent.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
+
+if "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
+
+import argparse
+import contextlib
+import json
+import subprocess
 import threading
 import time
 
@@ -39,6 +50,8 @@ D_REQ, N_DIM, LS, LAM, GAMMA = 1024, 6, 0.25, 10.0, 0.0
 PER_GPU = 12_500_000
 N_OBS = 60
 METRIC = "fused encode+UCB+argmax candidates/sec at d=1024"
+WORKLOAD = ("C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023,K=511) ls=0.25 rng=0, Hartmann-6 posterior after 10+50 "
+            "observations (rank 60, restored every step), counter-based uniform f32 candidates")
 
 
 def f_alg(d, K, n):
@@ -130,55 +143,135 @@ def problem_setup():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(sample, chunk, steps=1, warmup=0):
-    """Reference path restated in numpy (oracle/ssp_oracle.py): encode -> predict -> acq -> argmax, chunked so the
-    (d x chunk) complex128 temporary stays small.  Returns (candidates/s, seconds per step, cores)."""
-    X, y, orc = problem_setup()
-    A = orc.random_phase_matrix(N_DIM, D_REQ, rng=0)
-    ls = LS * np.ones(N_DIM)
-    blr = orc.BLR(A.shape[0])
-    blr.update(orc.encode(A, ls, X[:10]), y[:10])
-    S, beta = blr.S.copy(), blr.beta
-    bvec = beta * (orc.encode(A, ls, X[:10]).T @ y[:10])
-    for i in range(10, N_OBS):                     # O(d^2) form of blr.py:63-75 to keep the setup short
-        phi = orc.encode(A, ls, X[i:i + 1])[0]
-        v = S @ phi
-        S = S - np.outer(v, v) * (beta / (1 + beta * (phi @ v)))
-        bvec = bvec + beta * phi[:, None] * y[i]
-    blr.S, blr.m = S, S @ bvec
-    times = []
-    for it in range(warmup + steps):
-        xc = orc.counter_uniform(0, it * sample, sample, N_DIM).astype(np.float64)
+def blas_info():
+    """threadpoolctl view of the BLAS / OpenMP pools numpy runs on (BASELINE.md section 3 asks for it next to the number)."""
+    try:
+        from threadpoolctl import threadpool_info
+        return [{k: i.get(k) for k in ("user_api", "internal_api", "version", "num_threads", "threading_layer")}
+                for i in threadpool_info()]
+    except Exception as e:                                   # pragma: no cover
+        return [{"error": str(e)}]
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
+class CpuArm:
+    """The reference path on the host: C3 posterior after N_OBS observations, then per step `eval(X_chunk)` -> score ->
+    running argmax over chunks of the candidate sample.  kind "reference": the unmodified package from oracle/_ref
+    (SSPAgent.eval, agents/ssp_agent.py:125-137; posterior built by its own BLR.update); kind "port": oracle/ssp_oracle.py."""
+
+    def __init__(self):
+        from oracle import ref_loader
+        X, y, orc = problem_setup()
+        self.orc = orc
+        self.ref = ref_loader.load()
+        b6 = np.array([[0.0, 1.0]] * N_DIM)
+        if self.ref is not None:
+            self.kind = "reference"
+            with contextlib.redirect_stdout(sys.stderr):
+                sp = self.ref.sspspace.RandomSSPSpace(N_DIM, ssp_dim=D_REQ, domain_bounds=b6, length_scale=LS, rng=0)
+                self.agt = self.ref.agents.SSPAgent(X[:10], y[:10], sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=LAM,
+                                                    length_scale=LS)
+                # the remaining observations through the reference's own update (agents/ssp_agent.py:187-224 -> blr.py:39-82,
+                # O(d^3) per observation as written there: ~30 ms each at d = 1023)
+                for i in range(10, N_OBS):
+                    self.agt.update(X[i:i + 1], y[i:i + 1], 0.0, step_num=i)
+            self.d = sp.ssp_dim
+        else:
+            self.kind = "port"
+            A = orc.random_phase_matrix(N_DIM, D_REQ, rng=0)
+            ls = LS * np.ones(N_DIM)
+            blr = orc.BLR(A.shape[0])
+            blr.update(orc.encode(A, ls, X[:10]), y[:10])
+            S, beta = blr.S.copy(), blr.beta
+            bvec = beta * (orc.encode(A, ls, X[:10]).T @ y[:10])
+            for i in range(10, N_OBS):                     # O(d^2) form of blr.py:63-75 to keep the setup short
+                phi = orc.encode(A, ls, X[i:i + 1])[0]
+                v = S @ phi
+                S = S - np.outer(v, v) * (beta / (1 + beta * (phi @ v)))
+                bvec = bvec + beta * phi[:, None] * y[i]
+            blr.S, blr.m = S, S @ bvec
+            self.A, self.ls, self.blr, self.d = A, ls, blr, A.shape[0]
+
+    def scores(self, xc):
+        """score = mu + acq of rows xc (float64), the quantity the fused kernel arg-maxes"""
+        if self.kind == "reference":
+            mu, var, acq = self.agt.eval(xc)
+            return np.ravel(mu) + np.ravel(acq)
+        score, _ = self.orc.score_and_argmax(self.orc.encode(self.A, self.ls, xc), self.blr, LAM, GAMMA)
+        return score
+
+    def step(self, start, sample, chunk):
+        """one pass over rows [start, start + sample) of the counter-based candidate stream; returns (seconds, score, index)"""
+        xc = self.orc.counter_uniform(0, start, sample, N_DIM).astype(np.float64)
         t0 = time.perf_counter()
         best, best_i = -np.inf, -1
         for c0 in range(0, sample, chunk):
-            score, i = orc.score_and_argmax(orc.encode(A, ls, xc[c0:c0 + chunk]), blr, LAM, GAMMA)
-            if score[i] > best:
-                best, best_i = score[i], c0 + i
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    per_step = float(np.mean(times))
-    return sample / per_step, per_step, os.cpu_count()
+            sc = self.scores(xc[c0:c0 + chunk])
+            i = int(np.argmax(sc))
+            if sc[i] > best:
+                best, best_i = float(sc[i]), start + c0 + i
+        return time.perf_counter() - t0, best, best_i
+
+    def rate(self, sample, chunk, steps=1, warmup=0):
+        times = []
+        for it in range(warmup + steps):
+            dt, _, _ = self.step(it * sample, sample, chunk)
+            if it >= warmup:
+                times.append(dt)
+        per_step = float(np.mean(times))
+        return sample / per_step, per_step
+
+    def describe(self, sample, chunk, threads):
+        what = ("the unmodified reference package (oracle/_ref: SSPAgent.eval + np.argmax, agents/ssp_agent.py:125-137, "
+                "sspspace.py:254-276, blr.py:84-97)" if self.kind == "reference" else
+                "oracle/ssp_oracle.py, the numpy float64 restatement pinned to the live reference by tests/golden "
+                "(oracle/_ref is absent)")
+        return f"{sample} candidates/step of the C3 shard in chunks of {chunk}, {what}, numpy/OpenBLAS with {threads} threads"
+
+
+def one_thread_rate(arm, sample, chunk):
+    """the same pass with the BLAS pool limited to one thread (encode is mostly single-threaded)"""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            return arm.rate(sample, chunk, steps=1, warmup=0)[0]
+    except Exception:
+        return None
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample, chunk = 20000, 10000
-    rate, per_step, cores = cpu_oracle_rate(sample, chunk, steps=args.steps, warmup=args.warmup)
-    d = 1023
+    cores = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)                     # torchrun's OMP_NUM_THREADS=1 must not shrink the BLAS pool
+    except Exception:
+        pass
+    arm = CpuArm()
+    sample, chunk = args.cpu_sample, 10000
+    rate, per_step = arm.rate(sample, chunk, steps=args.steps, warmup=args.warmup)
+    threads = max([i.get("num_threads") or 1 for i in blas_info()] + [1])
+    one = one_thread_rate(arm, min(sample, 20000), chunk)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "candidates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023) Hartmann-6 posterior, uniform candidates",
-                   "candidates_per_step": sample, "note": "bounded sample of the 1.25e7-per-GPU shard"},
-        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} candidates/step in chunks of {chunk}, numpy/OpenBLAS on all host cores "
-                                   "(the reference is pure Python and cannot travel to the GPU box; this is its numpy "
-                                   "restatement, oracle/ssp_oracle.py, pinned to the live reference by tests/golden)"},
+        "config": {"workload": WORKLOAD, "candidates_per_step": sample, "posterior_rank": N_OBS,
+                   "note": "bounded sample of the 1.25e7-per-GPU shard, same seeds / phase matrix / posterior / candidate stream"},
+        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": threads, "kind": arm.kind,
+                         "sample": arm.describe(sample, chunk, threads), "host_cores": cores, "cpu_model": cpu_model(),
+                         "threadpool_info": blas_info(), "one_thread_value": one},
         "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "roofline": None,
@@ -187,6 +280,38 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def executed_flops_per_candidate(engine, rank, d):
+    """Tensor flops the scorer really issues per candidate, in fp16-MMA equivalents (an e4m3 MMA of twice the K counts as one
+    fp16 MMA: same tensor-pipe time).  Returns (flops, description)."""
+    kc = ((d + 63) // 64) * 64
+    n_kb = kc // 64
+    if engine == "umma-lowrank":
+        bn16 = -(-(rank + 1) // 16) * 16
+        if bn16 <= 128:                                      # split fp16, merged hi|lo operand: N = 2 BN and N = BN MMAs per K step
+            return 3 * 2.0 * kc * bn16, f"low rank, split fp16: 3 x 2 x {kc} x {bn16}"
+        nc = -(-rank // 256)
+        bn = -(-(-(-rank // nc)) // 16) * 16
+        return 2 * 2.0 * kc * bn * nc, f"low rank, fp16 + e4m3: (1 + 2 x 1/2) x 2 x {kc} x {nc}x{bn}"
+    if engine == "umma-factor-f8":
+        nc = -(-d // 256)
+        bn = -(-(-(-d // nc)) // 16) * 16
+        blocks = sum(n_kb - (c * bn) // 64 for c in range(nc))     # chunk c starts at factor column ~c*bn (upper bound on the skip)
+        return 2 * 2.0 * 64 * bn * blocks, f"triangular factor, fp16 + e4m3: 2 x 2 x 64 x {bn} x {blocks} (chunk, k-block) pairs"
+    if engine == "umma":
+        return 3 * 2.0 * kc * 1024 * 0.56, "dense triangular factor, split fp16: 3 x 0.56 x 2 x 1024^2"
+    return None, None
+
+
+def committed_traffic():
+    """dram bytes per scorer launch from the committed ncu --set full capture of this round (written by
+    profiles/raw_metrics.py --json), or None"""
+    p = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def run_native(args):
     import torch
     import torch.distributed as td
@@ -202,8 +327,10 @@ def run_native(args):
     X, y, orc = problem_setup()
     b6 = np.array([[0.0, 1.0]] * N_DIM)
     sp = pkg.RandomSSPSpace(N_DIM, ssp_dim=D_REQ, domain_bounds=b6, length_scale=LS, rng=0, device=local)
-    agt = pkg.SSPAgent(X, y, sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=LAM, length_scale=LS,
+    # 10 initial observations (they fix beta, blr.py:54-59), then 50 sequential ones: the same construction as the CPU arm
+    agt = pkg.SSPAgent(X[:10], y[:10], sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=LAM, length_scale=LS,
                        score_engine={"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "umma": _lib.ENGINE_UMMA}[args.engine])
+    agt.update(X[10:], y[10:], 0.0)
     eng = agt._scoring_engine()
     d, K = sp.ssp_dim, (sp.ssp_dim - 1) // 2
     n_local = args.per_gpu
@@ -211,6 +338,7 @@ def run_native(args):
     start = rank * n_local
     cand = eng.fill_uniform(0, start, n_local)                    # resident shard, 300 MB > L2 (126 MB)
     chunk = args.chunk
+    saved, beta0 = eng.blr_export(), eng.blr_beta()               # the rank-N_OBS posterior every step starts from
     torch.cuda.synchronize()
 
     def select(x_dev):
@@ -226,16 +354,14 @@ def run_native(args):
         u = orc.counter_uniform(0, gidx, 1, N_DIM)                # any rank can regenerate any candidate
         return u.astype(np.float64)
 
-    def bo_step(x_dev, kernel_events=None):
-        if kernel_events is not None:
-            kernel_events[0].record()
-        score, gidx = select(x_dev)
-        if kernel_events is not None:
-            kernel_events[1].record()
+    def observe_and_restore(gidx):
         x_t = winner_row(gidx)
-        y_t = np.atleast_2d(orc.hartmann6(x_t))
-        var_t = np.array([0.0])
-        agt.update(x_t, y_t, var_t)                               # encode x_t + float64 rank-one update on device
+        agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))   # encode x_t + float64 rank-one update on device
+        eng.blr_import(saved, beta0)                              # back to rank N_OBS: every step scores the same posterior
+
+    def bo_step(x_dev):
+        score, gidx = select(x_dev)
+        observe_and_restore(gidx)
         return score, gidx
 
     def barrier():
@@ -247,27 +373,30 @@ def run_native(args):
     for _ in range(args.warmup):
         bo_step(cand)
     barrier()
+    eng.score_stats(reset=True)
+    eng.set_timing(True)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     last = None
     for i in range(args.steps):
-        last = bo_step(cand, ev[i])
+        last = bo_step(cand)
     t_end.record()
     barrier()
     sampler.stop_flag = True
     launches = eng.launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))   # scoring launches + key reduction, per step
+    ktime = eng.timing_read(reset=True)                           # CUDA events around every scorer launch of the timed region
+    eng.set_timing(False)
     engine_used = eng.last_engine()
+    info = eng.lowrank_info()
 
     # ---- end-to-end timing: pinned host candidates -> H2D -> fused score -> D2H key, through the public API ----
     host = torch.empty((n_local, N_DIM), dtype=torch.float32).pin_memory()
     host.copy_(cand)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps
     def e2e_step():
         # public API on HOST candidates: SSPAgent.best_candidate streams the pinned shard to the GPU in chunks
         # (H2D inside the timed region, overlapped with the scoring), then the 8-byte key is read back
@@ -275,132 +404,207 @@ def run_native(args):
         eng.settle()
         dist.allreduce_best(eng._best)
         score, gidx = eng.best()
-        x_t = winner_row(gidx)
-        agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))
+        observe_and_restore(gidx)
         return score, gidx
     e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(e2e_steps):
-        e2e_step()
+        last_e2e = e2e_step()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
 
+    # ---- the same step with the candidate set described instead of shipped (counter-based stream generated in the kernel) ----
+    def gen_step():
+        eng.score_generated("uniform", n_local, float(agt.var_weight), agt._gamma(), index0=start, seed=0)
+        eng.settle()
+        dist.allreduce_best(eng._best)
+        score, gidx = eng.best()
+        observe_and_restore(gidx)
+        return score, gidx
+    gen_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        last_gen = gen_step()
+    g1.record()
+    barrier()
+    gen_ms = g0.elapsed_time(g1)
+
     # max over ranks
-    stats = torch.tensor([ms_total, kernel_ms, e2e_ms], dtype=torch.float64, device=cand.device)
+    stats = torch.tensor([ms_total, ktime["scorer_ms"], ktime["flagged_ms"], e2e_ms, gen_ms], dtype=torch.float64, device=cand.device)
     if world > 1:
         td.all_reduce(stats, op=td.ReduceOp.MAX)
-    ms_total, kernel_ms, e2e_ms = [float(v) for v in stats.cpu()]
+    ms_total, scorer_ms, flagged_ms, e2e_ms, gen_ms = [float(v) for v in stats.cpu()]
     sampler.join(timeout=2)
 
-    info = eng.lowrank_info()
-    sweep = rank_sweep(pkg, eng, agt, cand, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
-    enc = encode_only(eng, cand, load_peaks()) if (rank == 0 and world == 1 and not args.no_sweep) else None
-    upd = update_cost(agt, sp, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
-    asc = acq_ascent_cost(agt, sp, orc) if (rank == 0 and world == 1 and not args.no_sweep) else None
-    c2 = bo_step_c2(pkg) if (rank == 0 and world == 1 and not args.no_c2) else None
+    solo = world == 1 and rank == 0
+    sweep = rank_sweep(pkg, sp, cand, orc, X, y, world, td if world > 1 else None) if not args.no_sweep else None
+    enc = encode_only(eng, cand, load_peaks()) if (solo and not args.no_sweep) else None
+    upd = update_cost(agt, sp, orc) if (solo and not args.no_sweep) else None
+    asc = acq_ascent_cost(agt, sp, orc) if (solo and not args.no_sweep) else None
+    c2 = bo_step_c2(pkg) if (solo and not args.no_c2) else None
+    side = side_configs() if (solo and not args.no_side) else None
     if rank == 0:
         peaks = load_peaks()
         ms_per_step = ms_total / args.steps
         value = total / (ms_per_step * 1e-3)
-        flops = f_alg(d, K, N_DIM)
-        achieved = n_local * flops / (kernel_ms * 1e-3) / 1e12      # per GPU, TFLOP/s algorithmic
-        cpu_rate, cpu_step, cores = cpu_oracle_rate(20000, 10000, steps=1, warmup=0) if world == 1 else (None, None, None)
+        calls = max(int(ktime["calls"]), 1)
+        launch_ms = scorer_ms / calls                             # average duration of one scorer launch (CUDA events)
+        launch_cands = n_local * args.steps / calls
+        ex_flops, ex_what = executed_flops_per_candidate(engine_used, info["rank"], d)
+        achieved = launch_cands * ex_flops / (launch_ms * 1e-3) / 1e12 if ex_flops else None
+        alg = f_alg(d, K, N_DIM)
+        alg_tf = launch_cands * alg / (launch_ms * 1e-3) / 1e12
+        traffic = committed_traffic()
+        # parity of the winners of the last steps with the CPU arm (outside every timed region)
+        check, cpu = None, None
+        if world == 1:
+            arm = CpuArm()
+            cpu_rate, cpu_step = arm.rate(args.cpu_sample, 10000, steps=1, warmup=0)
+            threads = max([i.get("num_threads") or 1 for i in blas_info()] + [1])
+            cpu = {"value": cpu_rate, "unit": "candidates/s", "cores": threads, "kind": arm.kind,
+                   "sample": arm.describe(args.cpu_sample, 10000, threads), "host_cores": os.cpu_count(), "cpu_model": cpu_model(),
+                   "one_thread_value": one_thread_rate(arm, 20000, 10000)}
+            check = winner_check(arm, orc, [("resident", last), ("e2e", last_e2e), ("generated", last_gen)], n_local)
         line = {
             "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": ("f16x3-split mma / f32 accumulate / fixed-point phase / f64 posterior" if engine_used.startswith("umma")
-                      else "f32 contraction / f64 phase+posterior"),
+            "dtype": ("f16 hi/lo split (+ e4m3 corrections above 128 operand rows) mma / f32 accumulate / fixed-point phase / "
+                      "f64 posterior" if engine_used.startswith("umma") else "f32 contraction / f64 phase+posterior"),
             "data": "synthetic",
-            "config": {"workload": "C3: RandomSSPSpace n=6 ssp_dim=1024 (d=1023,K=511) ls=0.25 rng=0, Hartmann-6 posterior "
-                                   f"after {N_OBS}+step observations, counter-based uniform f32 candidates",
+            "config": {"workload": WORKLOAD,
                        "candidates_per_gpu_per_step": n_local, "candidates_per_step": total, "chunk": chunk,
                        "engine": engine_used, "posterior_rank": info["rank"], "phase32": info["phase32"],
                        "parallelism": f"candidate-shard x{world}",
-                       "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands refreshed every step",
+                       "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands rewritten every step",
                        "last_winner": {"score": last[0], "index": last[1]}},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"],
-                         # dram__bytes_read+write of one scorer launch (chunk of 4,194,304 candidates) from the ncu --set full
-                         # captures summarised in profiles/ (algorithmic bytes: 4*n per candidate = 100.7 MB)
-                         "traffic": (106.1e6 if engine_used == "umma-lowrank" else 108.6e6) if engine_used.startswith("umma") else None,
-                         "launch_candidates": min(chunk, n_local),
-                         "executed": executed_note(engine_used, info["rank"], d, n_local, kernel_ms, peaks),
-                         "note": f"algorithmic (dense form, SURVEY 8d) {flops / 1e6:.3f} MFLOP/candidate x {n_local} candidates / "
-                                 f"{kernel_ms:.2f} ms scoring time per step per GPU (all launches of the step, incl. the key "
-                                 "read-back); frac > 1 means the low-rank form beats the dense-form roofline by doing less "
-                                 f"work, not that the tensor pipe runs above peak; peak {peaks['source']}"},
+                         "frac": (achieved / peaks["tflops"]) if achieved else None,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": (traffic or {}).get("source"),
+                         "kernel": {"umma-lowrank": "k_score_lr<6,2,0> / k_score_f8<6,2,0,0>", "umma-factor-f8": "k_score_f8<6,2,0,0>",
+                                    "umma": "k_score_umma"}.get(engine_used, engine_used),
+                         "launch_candidates": launch_cands, "launch_ms": launch_ms, "launches_timed": calls,
+                         "flagged_pass_ms_per_launch": flagged_ms / calls,
+                         "executed_flops_per_candidate": ex_flops, "executed_what": ex_what,
+                         "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if achieved else None,
+                         "algorithmic_dense": {"flops_per_candidate": alg, "tflops": alg_tf, "frac": alg_tf / peaks["tflops"],
+                                               "note": "SURVEY 8d dense-form work / launch time; above 1 because the low-rank form "
+                                                       "does less work, not a utilisation figure"},
+                         "binding": (traffic or {}).get("binding"),
+                         "note": f"achieved = tensor flops issued per launch / average launch duration over {calls} launches "
+                                 f"(CUDA events on the launching stream); peak {peaks['source']}"},
             "by_rank": sweep,
             "encode_only": enc,
             "posterior_update": upd,
             "acq_ascent": asc,
-            "cpu_baseline": ({"value": cpu_rate, "unit": "candidates/s", "cores": cores, "kind": "port",
-                              "sample": "20000 candidates in chunks of 10000, oracle/ssp_oracle.py (numpy float64, OpenBLAS)"}
-                             if cpu_rate else None),
+            "cpu_baseline": cpu,
             "e2e": {"value": total * e2e_steps / (e2e_ms * 1e-3), "unit": "candidates/s",
                     "h2d_bytes_per_step": int(n_local * N_DIM * 4), "d2h_bytes_per_step": 8,
                     "steps": e2e_steps},
+            "e2e_generated": {"value": total * args.steps / (gen_ms * 1e-3), "unit": "candidates/s", "steps": args.steps,
+                              "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                              "note": "candidate descriptor (counter-based uniform stream, seed, start) instead of candidate rows: "
+                                      "x is generated inside the scorer, bit-identical to the resident rows"},
+            "winner_check": check,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "bo_step": c2,
+            "side": side,
         }
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
 
 
-def executed_note(engine, rank, d, n_local, kernel_ms, peaks):
-    """Tensor flops the kernel really issues per candidate (3 split-fp16 MMAs per product)."""
-    kc = 1024
-    if engine == "umma-lowrank":
-        r_eff = rank + 1                                   # row 0 of the operand is m'
-        nc = 1 if r_eff <= 256 else 2
-        rows = r_eff if nc == 1 else rank
-        bn = -(-(-(-rows // nc)) // 16) * 16
-        per_cand = 3 * 2.0 * kc * bn * nc
-        what = f"low-rank: 3 x 2 x {kc} x {nc}x{bn} per candidate"
-    elif engine == "umma":
-        per_cand = 3 * 2.0 * kc * 1024 * 0.56
-        what = "dense triangular factor: 3 x 0.56 x 2 x 1024^2 per candidate"
-    else:
-        return None
-    tf = n_local * per_cand / (kernel_ms * 1e-3) / 1e12
-    return {"tflops": tf, "frac_of_peak": tf / peaks["tflops"], "what": what}
+def winner_check(arm, orc, winners, n_local):
+    """Each winner (score, global index) re-scored by the CPU arm: the score within 1e-4 relative, and no row of a CPU-scored
+    sample of the same shard beats it by more than that.  Outside every timed region."""
+    out = {"checker": arm.kind, "tolerance": 1e-4, "ok": True, "winners": []}
+    sample = orc.counter_uniform(0, 0, 20000, N_DIM).astype(np.float64)
+    smax = float(np.max(arm.scores(sample)))
+    for name, (score, gidx) in winners:
+        ref = float(arm.scores(orc.counter_uniform(0, gidx, 1, N_DIM).astype(np.float64))[0])
+        rel = abs(score - ref) / abs(ref)
+        ok = rel <= 1e-4 and ref >= smax - 1e-4 * abs(smax) and 0 <= gidx < n_local
+        out["winners"].append({"run": name, "index": int(gidx), "score": float(score), "cpu_score": ref, "rel_err": rel,
+                               "cpu_sample_max": smax, "ok": bool(ok)})
+        out["ok"] = bool(out["ok"] and ok)
+    return out
 
 
-def rank_sweep(pkg, eng, agt, cand, orc, n=1 << 22, reps=3):
-    """Kernel-only candidates/s (CUDA events, device-resident candidates, one launch of n candidates) of the low-rank
-    engine at the current and at higher posterior ranks, and of the dense full-factor engine."""
+def side_configs():
+    """Driver-visible lines for the other BASELINE configs (C4 batched runs, C5 trajectories) and the multi-agent encoder."""
+    out = {}
+    with contextlib.redirect_stdout(sys.stderr):
+        from tools import configs_bench as cb
+        for name, fn, kw in (("c5", cb.c5, {}), ("multi_agent", cb.multi, {}), ("c4", cb.c4, {"runs": 256, "steps": 3})):
+            try:
+                out[name] = fn(**kw)
+            except Exception as e:                               # a side line must not take the headline down
+                out[name] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def rank_sweep(pkg, sp_unused, cand, orc, X, y, world, td, n=1 << 22, reps=3,
+               ranks=(10, 60, 127, 128, 255, 256, 512, 1000)):
+    """Kernel-only candidates/s per GPU (CUDA events, device-resident candidates, one launch of n candidates, float64 pass over
+    the flagged candidates included) of the engine ENGINE_AUTO picks at fixed posterior ranks, up to the full-rank posterior
+    after 1000 observations.  With several ranks of a job every rank runs the sweep at the same time and the slowest counts."""
     import torch
     from ssp_bayesopt_b200 import _lib
+    local = cand.device.index
+    b6 = np.array([[0.0, 1.0]] * N_DIM)
+    sp = pkg.RandomSSPSpace(N_DIM, ssp_dim=D_REQ, domain_bounds=b6, length_scale=LS, rng=0, device=local)
+    rng = np.random.default_rng(7)
+    Xs = np.concatenate([X, rng.uniform(0, 1, (max(ranks) - X.shape[0], N_DIM))])
+    ys = np.concatenate([y, orc.hartmann6(Xs[X.shape[0]:]).reshape(-1, 1)])
+    agt = pkg.SSPAgent(Xs[:10], ys[:10], sp, decoder_method="from-set", gamma_c=0.0, beta_ucb=LAM, length_scale=LS)
+    eng = agt._scoring_engine()
     x = cand[:n]
-    out = []
-
-    def timed(code):
-        eng.score(x, LAM, GAMMA, engine=code)
+    d = sp.ssp_dim
+    peaks = load_peaks()
+    out, done = [], 10
+    for r in ranks:
+        if r > done:
+            agt.update(Xs[done:r], ys[done:r], 0.0)
+            done = r
+        eng.set_policy(lowrank=True)
+        eng.score_stats(reset=True)
+        eng.score(x, LAM, GAMMA)                                  # warm-up (operand images, tensor maps)
+        eng.best()
+        if td is not None:
+            td.barrier()
         torch.cuda.synchronize()
+        eng.set_timing(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            eng.score(x, LAM, GAMMA, engine=code)
+            eng.score(x, LAM, GAMMA)
         e1.record()
         torch.cuda.synchronize()
-        return x.shape[0] * reps / (e0.elapsed_time(e1) * 1e-3)
-
-    rng = np.random.default_rng(7)
-    for target in (None, 128, 250):
-        while target is not None and eng.lowrank_info()["rank"] < target:
-            x_t = rng.uniform(0, 1, (1, N_DIM))
-            agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))
-        r = eng.lowrank_info()["rank"]
-        row = {"rank": r, "lowrank_cand_per_s": timed(_lib.ENGINE_UMMA_LR)}
-        if target in (None, 250):
-            row["dense_cand_per_s"] = timed(_lib.ENGINE_UMMA)
-        eng.score_stats(reset=True)
-        out.append(row)
+        kt = eng.timing_read(reset=True)
+        eng.set_timing(False)
+        st = eng.score_stats(reset=True)
+        rate = x.shape[0] * reps / (e0.elapsed_time(e1) * 1e-3)
+        if td is not None:
+            t = torch.tensor([rate], dtype=torch.float64, device=cand.device)
+            td.all_reduce(t, op=td.ReduceOp.MIN)
+            rate = float(t.item())
+        name = eng.last_engine()
+        lr_rank = eng.lowrank_info()["rank"] if eng.lowrank_info()["valid"] else None
+        fl, what = executed_flops_per_candidate(name, r if lr_rank is None else lr_rank, d)
+        tf = x.shape[0] * reps * fl / (kt["scorer_ms"] * 1e-3) / 1e12 if (fl and kt["scorer_ms"] > 0) else None
+        out.append({"rank": r, "engine": name, "cand_per_s_per_gpu": rate, "cand_per_s_job": rate * world,
+                    "flagged_fraction": st["flagged"] / max(st["scored"], 1),
+                    "scorer_ms_per_launch": kt["scorer_ms"] / max(kt["calls"], 1),
+                    "flagged_pass_ms_per_launch": kt["flagged_ms"] / max(kt["calls"], 1),
+                    "executed_tflops": tf, "frac_of_tensor_peak": (tf / peaks["tflops"]) if tf else None, "executed_what": what})
     return out
 
 
@@ -542,7 +746,7 @@ def bo_step_c2(pkg, n_iter=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "umma"])
@@ -550,6 +754,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 22)
     ap.add_argument("--no-c2", action="store_true", help="skip the config-C2 'ms per BO step' side measurement")
     ap.add_argument("--no-sweep", action="store_true", help="skip the kernel-only rank sweep")
+    ap.add_argument("--no-side", action="store_true", help="skip the side lines of configs C4 / C5 / multi-agent")
+    ap.add_argument("--cpu-sample", type=int, default=100000, help="candidates per step of the CPU arm (BASELINE.md 3: >= 1e5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -191,6 +191,12 @@ unsigned long long sspbo_key_pack(float score, int64_t index);
 /* engine the last sspbo_score call used (an SSPBO_ENGINE_* code other than AUTO) and kernel launches so far */
 int sspbo_last_engine(const sspbo_ctx* ctx);
 int64_t sspbo_launch_count(const sspbo_ctx* ctx);
+/* Measurement aid (bench.py's roofline figure; no reference counterpart): with timing enabled every sspbo_score /
+ * sspbo_score_generated call records CUDA events on its stream before the scorer kernel, after it and after the float64 pass
+ * over flagged candidates.  sspbo_timing_read synchronises the stream and returns the summed durations (ms) and the number of
+ * calls since the last reset (at most 4096 calls are kept). */
+int sspbo_set_timing(sspbo_ctx* ctx, int enable);
+int sspbo_timing_read(sspbo_ctx* ctx, double* scorer_ms, double* flagged_ms, int64_t* calls, int reset, void* stream);
 
 /* ---- K4: from-set decode (sspspace.py:352-356) ------------------------------------
  * unit = q / max(||q||, 1e-6); idx[j] = argmax_i sample_ssps[i] . unit[j], first index on ties.

@@ -62,6 +62,8 @@ SIGNATURES = {
     "sspbo_key_pack": (_u64, [C.c_float, _i64]),
     "sspbo_last_engine": (_i, [_vp]),
     "sspbo_launch_count": (_i64, [_vp]),
+    "sspbo_set_timing": (_i, [_vp, _i]),
+    "sspbo_timing_read": (_i, [_vp, _pd, _pd, C.POINTER(_i64), _i, _vp]),
     "sspbo_from_set_argmax": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "sspbo_decode_optim": (_i, [_vp, _vp, _i, _vp, _pd, _vp, _vp]),
     "sspbo_acq_ascent": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _d, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,8 @@
 #include <new>
 #include <vector>
 
+static void timing_release(sspbo_ctx* ctx);
+
 static const double kTwoPi = 6.283185307179586476925286766559;
 
 // =====================================================================================
@@ -1002,6 +1004,7 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 
 static void free_blr(sspbo_ctx* ctx) {
     sspbo_f8_release(ctx);
+    timing_release(ctx);
     dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
@@ -1033,6 +1036,46 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
 extern "C" const char* sspbo_last_error(const sspbo_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int sspbo_last_engine(const sspbo_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 extern "C" int64_t sspbo_launch_count(const sspbo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- kernel timing (bench.py's roofline figure: per-launch duration of the dominant kernel, measured on its stream) ----
+static const int TIMING_MAX_CALLS = 4096;
+static void timing_release(sspbo_ctx* ctx) {
+    auto* ev = (std::vector<cudaEvent_t>*)ctx->timing_events;
+    if (ev) { for (cudaEvent_t e : *ev) cudaEventDestroy(e); delete ev; }
+    ctx->timing_events = nullptr; ctx->timing_used = 0;
+}
+// event `which` (0 before the scorer kernel, 1 after it, 2 after the flagged pass) of the score call in flight
+static void timing_mark(sspbo_ctx* ctx, int which, cudaStream_t st) {
+    if (!ctx->timing || ctx->timing_used >= TIMING_MAX_CALLS) return;
+    auto* ev = (std::vector<cudaEvent_t>*)ctx->timing_events;
+    if (!ev) { ev = new std::vector<cudaEvent_t>(); ctx->timing_events = ev; }
+    const size_t idx = (size_t)ctx->timing_used * 3 + which;
+    while (ev->size() <= idx) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; ev->push_back(e); }
+    cudaEventRecord((*ev)[idx], st);
+    if (which == 2) ++ctx->timing_used;
+}
+extern "C" int sspbo_set_timing(sspbo_ctx* ctx, int enable) {
+    if (!ctx) return SSPBO_EINVAL;
+    ctx->timing = enable != 0; ctx->timing_used = 0;
+    return SSPBO_OK;
+}
+extern "C" int sspbo_timing_read(sspbo_ctx* ctx, double* scorer_ms, double* flagged_ms, int64_t* calls, int reset, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    double a = 0.0, b = 0.0;
+    auto* ev = (std::vector<cudaEvent_t>*)ctx->timing_events;
+    SSPBO_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < ctx->timing_used && ev; ++i) {
+        float t0 = 0.f, t1 = 0.f;
+        SSPBO_CUDA(ctx, cudaEventElapsedTime(&t0, (*ev)[3 * i], (*ev)[3 * i + 1]));
+        SSPBO_CUDA(ctx, cudaEventElapsedTime(&t1, (*ev)[3 * i + 1], (*ev)[3 * i + 2]));
+        a += t0; b += t1;
+    }
+    if (scorer_ms) *scorer_ms = a;
+    if (flagged_ms) *flagged_ms = b;
+    if (calls) *calls = ctx->timing_used;
+    if (reset) ctx->timing_used = 0;
+    return SSPBO_OK;
+}
 
 static int build_p32_tables(sspbo_ctx* ctx);
 
@@ -1754,24 +1797,37 @@ static int score_dispatch(sspbo_ctx* ctx, sspbo_lr::CandDesc cand, int64_t N, in
         // operand format: split fp16 while the kernel is bound by generating psi, fp16 + e4m3 once the tensor pipe binds
         const int bn = (ctx->lr_rank + 1 + 15) / 16 * 16;
         const bool use16 = lr16_ok && (!lr8_ok || ctx->operand_format == 0 || bn <= SSPBO_F8_MIN_BN - 16);
+        timing_mark(ctx, 0, st);
         int rc = use16 ? sspbo_score_lr_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st)
                        : sspbo_score_f8_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, 0, st);
         if (rc) return rc;
+        timing_mark(ctx, 1, st);
         // exact pass over the candidates the low-rank pass flagged (device-side count; usually none)
-        if (sspbo_debug_env() & 4) return SSPBO_OK;              // timing experiments only (compiled out of product builds)
-        return score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
+        if (!(sspbo_debug_env() & 4))                            // (switch for timing experiments, compiled out of product builds)
+            rc = score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
+        timing_mark(ctx, 2, st);
+        return rc;
     }
     if (engine == SSPBO_ENGINE_UMMA_F8) {
+        timing_mark(ctx, 0, st);
         int rc = sspbo_score_f8_launch(ctx, cand, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, 1, st);
         if (rc) return rc;
+        timing_mark(ctx, 1, st);
         // float64 pass over the candidates whose variance is a small fraction of the prior's (SSPBO_F8_FLAG_FRACTION)
-        return score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
+        rc = score_flagged_launch(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, st);
+        timing_mark(ctx, 2, st);
+        return rc;
     }
     int rc = sspbo_refresh_operands(ctx, st);
     if (rc) return rc;
+    timing_mark(ctx, 0, st);
     if (engine == SSPBO_ENGINE_UMMA)
-        return sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
-    return sspbo_score_simt_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+        rc = sspbo_score_umma_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+    else
+        rc = sspbo_score_simt_launch(ctx, x, x_dtype, N, index0, (float)lam, (float)gamma_t, mu, var, acq, best, st);
+    timing_mark(ctx, 1, st);
+    timing_mark(ctx, 2, st);
+    return rc;
 }
 
 extern "C" int sspbo_score(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, int64_t index0, double lam, double gamma_t,

@@ -15,6 +15,11 @@ struct sspbo_ctx {
     mutable char err[512] = {0};
     int64_t launches = 0;
     int last_engine = 0;
+    // kernel timing on request (sspbo_set_timing): CUDA events on the launching stream around the scorer kernel and around
+    // the float64 pass over flagged candidates of every sspbo_score call; read and summed by sspbo_timing_read
+    bool timing = false;
+    void* timing_events = nullptr;   // std::vector<cudaEvent_t>, three per call: before scorer, after scorer, after flagged pass
+    int timing_used = 0;
 
     // ---- space ----
     int K = 0, n = 0, d = 0, L = 1;

@@ -504,6 +504,17 @@ class DeviceEngine:
     def launch_count(self) -> int:
         return int(self.lib.sspbo_launch_count(self._ctx))
 
+    def set_timing(self, enable: bool) -> None:
+        """CUDA events around the scorer kernel and the float64 pass over flagged candidates of every score call."""
+        self._check(self.lib.sspbo_set_timing(self._ctx, 1 if enable else 0), "sspbo_set_timing")
+
+    def timing_read(self, reset=True):
+        """dict(scorer_ms, flagged_ms, calls) summed over the score calls since the last reset (synchronises)."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        rc = self.lib.sspbo_timing_read(self._ctx, C.byref(a), C.byref(b), C.byref(n), 1 if reset else 0, self._stream())
+        self._check(rc, "sspbo_timing_read")
+        return dict(scorer_ms=a.value, flagged_ms=b.value, calls=n.value)
+
     # ------------------------------------------------------------------ K4
     def from_set_argmax(self, sample_ssps, queries):
         st = self.to_device(sample_ssps, self.torch.float64)

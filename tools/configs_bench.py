@@ -35,6 +35,10 @@ def c4(runs=int(os.environ.get("C4_RUNS", "128")), steps=5):
     print(f"C4: {runs} runs x {grid.shape[0]} candidates d={eng.d}: {dt * 1e3:.1f} ms per lock-step "
           f"({runs * grid.shape[0] / dt:.3e} candidate evaluations/s; engine {eng.last_engine()}; set-up {t_build:.1f} s) "
           f"-> 4096 runs: {dt * 4096 / runs:.2f} s per lock-step")
+    return {"workload": f"C4: {runs} independent BLR-UCB runs (Himmelblau 2-D, ssp-rand ssp_dim=512 -> d={eng.d}), shared 100x100 grid, "
+                        "stepped in lock-step (BatchedRuns)", "runs": runs, "candidates_per_run": int(grid.shape[0]), "steps": steps,
+            "ms_per_lockstep": dt * 1e3, "candidate_evaluations_per_s": runs * grid.shape[0] / dt, "engine": eng.last_engine(),
+            "setup_s": t_build, "extrapolated_s_per_4096_run_lockstep": dt * 4096 / runs}
 
 
 def c5(n=1 << 20, steps=3):
@@ -60,6 +64,9 @@ def c5(n=1 << 20, steps=3):
     ms = e0.elapsed_time(e1) / steps
     print(f"C5: trajectory L={L} x_dim={xd} d={eng.d}: {n} candidates in {ms:.1f} ms = {n / ms * 1e3:.3e} candidates/s "
           f"(engine {eng.last_engine()}) -> 1e7 candidates: {1e7 / (n / ms * 1e3):.2f} s")
+    return {"workload": f"C5: SSPTrajectoryAgent L={L} x_dim={xd} ssp_dim=2048 -> d={eng.d}, uniform trajectories, rank-12 posterior",
+            "candidates": n, "steps": steps, "ms_per_pass": ms, "candidates_per_s": n / ms * 1e3, "engine": eng.last_engine(),
+            "s_per_1e7_candidates": 1e7 / (n / ms * 1e3)}
 
 
 def multi(n=1 << 20, steps=3):
@@ -89,6 +96,9 @@ def multi(n=1 << 20, steps=3):
     t_enc = time.perf_counter() - t0
     print(f"multi-agent {n_agents} x L={L} x_dim={xd} d={eng.d}: {n} candidates in {ms:.1f} ms = {n / ms * 1e3:.3e} candidates/s "
           f"(engine {eng.last_engine()}, stats {eng.score_stats(reset=False)}); float64 encode of 4096: {t_enc * 1e3:.1f} ms")
+    return {"workload": f"multi-agent trajectories: SSPMultiAgent {n_agents} agents x L={L} x_dim={xd} ssp_dim=2048 -> d={eng.d}, "
+                        "normalised scoring", "candidates": n, "steps": steps, "ms_per_pass": ms,
+            "candidates_per_s": n / ms * 1e3, "engine": eng.last_engine(), "f64_encode_ms_per_4096": t_enc * 1e3}
 
 
 if __name__ == "__main__":
