@@ -40,14 +40,16 @@ extern "C" {
 
 /* scoring engines for sspbo_score */
 #define SSPBO_ENGINE_AUTO 0     /* N <= 64: EXACT; N >= 1024: the tensor-memory tcgen05 engines, low-rank form (UMMA_LR) or
-                                   factor form (UMMA_F8), whichever passes fewer operand rows x k-blocks per tile (low rank
-                                   needs rank <= 511 and at most 1 % of flagged candidates); else SIMT */
+                                   factor form (UMMA_F8), whichever costs less per tile: operand rows x k-blocks, plus, for
+                                   the low-rank form, the float64 pass over the share of candidates it flagged at the last
+                                   read-back (low rank needs rank <= 511 and at most 1 % of flagged candidates; a factor form
+                                   whose own flag list overflows hands over to UMMA, which never flags); else SIMT */
 #define SSPBO_ENGINE_SIMT 1     /* fp32 CUDA-core kernel (any d)                */
 #define SSPBO_ENGINE_UMMA 2     /* tcgen05/TMEM split-fp16 kernel, full triangular factor, psi staged in shared memory */
 #define SSPBO_ENGINE_EXACT 3    /* float64 quadratic form on the psi-space covariance (small N)  */
 #define SSPBO_ENGINE_UMMA_LR 4  /* tcgen05 kernels with psi in tensor memory on the low-rank form S = I/alpha - V^T V
-                                   (one row of V per observation, rank <= 511: split-fp16 operands up to 96 rows,
-                                   fp16 + e4m3 operands beyond, see sspbo_set_operand_format) followed by a float64
+                                   (one row of V per observation, rank <= 511: split-fp16 operands up to 128 operand
+                                   rows, fp16 + e4m3 operands beyond, see sspbo_set_operand_format) followed by a float64
                                    pass over the candidates it flags (var < 0.3 / alpha)          */
 #define SSPBO_ENGINE_UMMA_F8 5  /* same kernel family on the triangular factor of the psi-space covariance
                                    (var = 1/beta + |R psi|^2, any rank): fp16 + e4m3 operands, d + 1 operand rows in
@@ -148,7 +150,9 @@ int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi_dev, int64_t N, double* 
  * best_key_dev: one uint64, atomically max-combined with
  *   key = orderable_u32(score) << 32 | (0xFFFFFFFF - global_index)
  * so that max(key) = highest score, lowest index on ties (np.argmax).  The caller zeroes
- * *best_key_dev before the first call of a step; global_index must be < 2^32. */
+ * *best_key_dev before the first call of a step; global_index must be < 2^32 (index0 + N above that is refused with
+ * SSPBO_EINVAL).  Larger candidate sets are scored shard by shard with indices local to the shard and the shards' keys are
+ * combined as (key, shard start) pairs: ssp_bayesopt_b200/dist.py:allgather_best, 16 bytes per rank. */
 int sspbo_score(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, int64_t index0,
                 double lam, double gamma_t, float* mu_dev, float* var_dev, float* acq_dev,
                 unsigned long long* best_key_dev, int engine, void* stream);
@@ -162,7 +166,9 @@ int sspbo_score_generated(sspbo_ctx* ctx, int kind, uint64_t seed, const double*
                           int64_t N, int64_t index0, double lam, double gamma_t, float* mu_dev, float* var_dev,
                           float* acq_dev, unsigned long long* best_key_dev, int engine, void* stream);
 /* Operand format of SSPBO_ENGINE_UMMA_LR: -1 = by rank (default), 0 = split fp16 only (three fp16 products per K step,
- * rank <= 255), 1 = fp16 + e4m3 (one fp16 and one e4m3 product per K step) at every rank. */
+ * rank <= 255), 1 = fp16 + e4m3 (one fp16 and one e4m3 product per K step) at every rank, 2 = the same with CTA pairs
+ * (tcgen05 cta_group::2: tiles of 256 candidates, each CTA of a cluster of two streams half of the operand rows; results are
+ * bit-identical to format 1; n <= 8; also applies to SSPBO_ENGINE_UMMA_F8). */
 int sspbo_set_operand_format(sspbo_ctx* ctx, int format);
 /* Counters of the low-rank engine since the last reset (synchronises `stream`): candidates scored, re-scored by the
  * exact pass, flagged beyond the list capacity, outside the declared |x| bound.  *rerun != 0 means the keys/outputs
@@ -175,7 +181,7 @@ int sspbo_score_stats(sspbo_ctx* ctx, int64_t* scored, int64_t* flagged, int64_t
 int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_dev, unsigned long long* key_host, int64_t* scored,
                        int64_t* flagged, int64_t* overflow, int64_t* out_of_range, int* rerun, int reset, void* stream);
 /* SSPAgent.eval (agents/ssp_agent.py:125-137) for N <= 64 HOST points (x_t of a BO step): x_host N x (n*L) float64;
- * mu/var/acq_host N float64 each (float32 precision, like sspbo_score).  Exact float64 engine; one pinned upload, one
+ * mu/var/acq_host N float64 each, float64 precision like the reference's eval.  Exact float64 engine; one pinned upload, one
  * pinned read-back, one synchronisation. */
 int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, double lam, double gamma_t, double* mu_host,
                     double* var_host, double* acq_host, void* stream);
@@ -245,6 +251,11 @@ int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_de
  * (nullable) is the run index. */
 int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
                       const double* gamma_t, unsigned long long* keys_dev, void* const* streams, int n_streams, int* failed);
+/* After sspbo_score_batch, on the same streams: status_dev[r] = bit 0 (the flag list of run r's tensor pass overflowed) |
+ * bit 1 (candidates outside the declared |x| bound met the fast phase path); non-zero means the key of run r must be
+ * recomputed with the safe engines (sspbo_set_policy(ctx, 0, 0), then sspbo_score).  Clears the runs' counters. */
+int sspbo_score_batch_status(sspbo_ctx* const* ctxs, int R, unsigned long long* status_dev, void* const* streams,
+                             int n_streams, int* failed);
 int sspbo_update_batch(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, void* const* streams,
                        int n_streams, int* failed);
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sspbo_acq_ascent": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _d, _vp, _vp, _vp, _vp]),
     "sspbo_gram": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sspbo_score_batch": (_i, [C.POINTER(_vp), _i, _vp, _i, _i64, _pd, _pd, _vp, C.POINTER(_vp), _i, _pi]),
+    "sspbo_score_batch_status": (_i, [C.POINTER(_vp), _i, _vp, C.POINTER(_vp), _i, _pi]),
     "sspbo_update_batch": (_i, [C.POINTER(_vp), _i, _pd, _pd, C.POINTER(_vp), _i, _pi]),
     "sspbo_bind": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "sspbo_fill_uniform": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),

@@ -43,8 +43,26 @@ class SSPAgent(Agent):
 
     # ------------------------------------------------------------------ construction
     def _scoring_engine(self):
-        """Device context whose `score` sees candidates in this agent's input layout."""
-        return self.ssp_space.engine
+        """Device context whose `score` sees candidates in this agent's input layout and which holds this agent's posterior.
+        The first agent over an SSPSpace uses the space's own context; an agent built over a space whose context already
+        hosts another live agent's posterior gets a private context programmed from the same phase matrix (in the reference
+        every agent owns an independent BLR and sharing a space is legal: 'ssp-custom', lists of agents)."""
+        space_eng = self.ssp_space.engine
+        if getattr(self, '_own_engine', None) is None:
+            owner = space_eng._blr_owner() if space_eng._blr_owner is not None else None
+            mine = getattr(self, 'blr', None)
+            if owner is None or owner is mine:
+                return space_eng
+            from ..engine import DeviceEngine
+            self._own_engine = DeviceEngine(self.ssp_space._device)
+            self._own_engine_ls = None
+        ls = np.asarray(self.ssp_space.length_scale, dtype=np.float64).reshape(-1)
+        if self._own_engine_ls is None or not np.array_equal(ls, self._own_engine_ls):
+            self._own_engine.set_space(self.ssp_space.phase_matrix, ls)
+            if self.ssp_space.domain_bounds is not None:
+                self._own_engine.set_xbound(float(np.max(np.abs(np.asarray(self.ssp_space.domain_bounds, dtype=np.float64)))))
+            self._own_engine_ls = ls.copy()
+        return self._own_engine
 
     def _set_ssp_space(self, ssp_space, seed=0, **kwargs):
         if ssp_space is None:

@@ -29,7 +29,8 @@ class BatchedRuns:
         self.device = eng0._dev()
         self.candidates = eng0.to_device(candidates)            # shared, resident
         self.streams = [self.torch.cuda.Stream(device=self.device) for _ in range(max(1, min(n_streams, len(agents))))]
-        self._keys = self.torch.zeros(len(agents), dtype=self.torch.int64, device=self.device)
+        self._keys = self.torch.zeros(2 * len(agents), dtype=self.torch.int64, device=self.device)   # R keys, R status words
+        self._step_num = 0
         # per-run contexts and streams as C arrays: one library call enqueues a whole lock-step
         R = len(agents)
         self._engines = [a._scoring_engine() for a in agents]
@@ -51,7 +52,7 @@ class BatchedRuns:
         gam = np.array([a._gamma() for a in self.agents], dtype=np.float64)
         self._keys.zero_()
         for s in self.streams:
-            s.wait_stream(cur)                                   # ... and the zeroed keys
+            s.wait_stream(cur)                                   # ... and the zeroed keys / status words
         failed = C.c_int(-1)
         rc = self._lib.sspbo_score_batch(self._ctxs, R, C.c_void_p(self.candidates.data_ptr()),
                                          self._engines[0]._dtype_code(self.candidates), self.candidates.shape[0],
@@ -59,9 +60,21 @@ class BatchedRuns:
                                          C.c_void_p(self._keys.data_ptr()), self._cstreams, len(self.streams), C.byref(failed))
         if rc:
             _lib.check(self._lib, self._engines[max(failed.value, 0)]._ctx, rc, f"sspbo_score_batch (run {failed.value})")
+        # the 'rerun' protocol of DeviceEngine.best(): per-run overflow / out-of-bound flags, gathered next to the keys
+        rc = self._lib.sspbo_score_batch_status(self._ctxs, R, C.c_void_p(self._keys.data_ptr() + 8 * R), self._cstreams,
+                                                len(self.streams), C.byref(failed))
+        if rc:
+            _lib.check(self._lib, self._engines[max(failed.value, 0)]._ctx, rc, f"sspbo_score_batch_status (run {failed.value})")
         for s in self.streams:
             cur.wait_stream(s)
-        keys = self._keys.cpu().numpy()                          # one D2H per lock-step
+        both = self._keys.cpu().numpy()                          # one D2H per lock-step: keys and status words
+        keys, status = both[:R].copy(), both[R:]
+        for r in np.nonzero(status)[0]:                          # rare: recompute that run with the engines that never flag
+            eng = self._engines[r]
+            eng.set_policy(lowrank=False if status[r] & 1 else None, phase32=False if status[r] & 2 else None)
+            eng.score(self.candidates, float(lam[r]), float(gam[r]))
+            score, idx_r = eng.best()
+            keys[r] = np.array(_lib.key_pack(score, idx_r), dtype=np.uint64).astype(np.int64)
         unpacked = [_lib.key_unpack(int(k)) for k in keys]
         scores = np.array([u[0] for u in unpacked])
         idx = np.array([u[1] for u in unpacked], dtype=np.int64)
@@ -87,10 +100,12 @@ class BatchedRuns:
             for s in self.streams:
                 cur.wait_stream(s)
             for a in self.agents:
-                a._step_scalars(0.0, 0)
+                a._step_scalars(0.0, self._step_num)
+            self._step_num += 1
             return
         for r, agt in enumerate(self.agents):
-            agt.observe(np.atleast_2d(xs[r]), np.atleast_2d(ys[r]))   # eval(x_t) + update in one device round trip
+            agt.observe(np.atleast_2d(xs[r]), np.atleast_2d(ys[r]), step_num=self._step_num)   # eval(x_t) + update in one device round trip
+        self._step_num += 1
 
     def step(self, objective):
         """One lock-step with a vectorised objective f(points (R, n)) -> (R,)."""

@@ -63,7 +63,7 @@ class BayesianOptimization:
     # ------------------------------------------------------------------ agent construction
     def initialize_agent(self, init_points=10, agent_type='ssp-hex', **kwargs):
         """Sample / adopt the initial design, evaluate the target, build the agent (:67-185)."""
-        kwargs.pop('num_perimeter_samples', 0)
+        num_perimeter_samples = kwargs.pop('num_perimeter_samples', 0)
         if 'traj' in agent_type:
             domain = agents.domains.TrajectoryDomain(kwargs['traj_len'], kwargs['x_dim'], self.bounds)
         elif 'multi' in agent_type:
@@ -81,6 +81,14 @@ class BayesianOptimization:
         else:
             init_ys = np.array([self.target(np.atleast_2d(x), str(i)) for i, x in enumerate(init_xs)]
                                ).reshape((n_init, -1))
+        if dist.is_distributed():
+            # the posterior is replicated, never reconciled: every rank must start from rank 0's initial design (the
+            # domains' Sobol samplers are unseeded, agents/domains.py:30) and, below, from its perimeter draws
+            import torch.distributed as td
+            box = [init_xs, init_ys]
+            td.broadcast_object_list(box, src=0)
+            init_xs, init_ys = box
+            n_init = init_xs.shape[0]
 
         if agent_type == 'ssp-hex':
             space = sspspace.HexagonalSSPSpace(self.data_dim, **kwargs)
@@ -103,6 +111,18 @@ class BayesianOptimization:
             raise NotImplementedError(
                 f'{agent_type} agent is not part of the GPU hot path (supported: ssp-hex, ssp-rand, ssp-custom, ssp-traj, '
                 'ssp-multi)')
+        if num_perimeter_samples > 0:                                # corners of the box as zero-valued prior samples (:173-182)
+            perimeter_xs = []
+            for _ in range(num_perimeter_samples):
+                idxs = np.random.choice(self.bounds.shape[1], size=(self.bounds.shape[0],))
+                perimeter_xs.append([self.bounds[r, c] for r, c in enumerate(idxs)])
+            perimeter_xs = np.atleast_2d(np.squeeze(perimeter_xs))
+            if dist.is_distributed():
+                import torch.distributed as td
+                box = [perimeter_xs]
+                td.broadcast_object_list(box, src=0)
+                perimeter_xs = box[0]
+            agt.update(perimeter_xs, np.zeros((perimeter_xs.shape[0], 1)), 0, 0)
         self.logger.info(f'{type(agt).__name__} agent created')
         return agt, init_xs, init_ys
 

@@ -12,8 +12,11 @@ the host from the copied posterior.
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
+from . import _lib
 from .engine import DeviceEngine
 
 
@@ -29,7 +32,14 @@ class BayesianLinearRegression:
             engine.blr_init(alpha, dim=size_in)
         else:                                   # BLR over an SSP space: also maintains the scoring factor
             assert engine.d == size_in, f"engine encodes {engine.d}-d SSPs, BLR asked for {size_in}"
+            owner = engine._blr_owner() if engine._blr_owner is not None else None
+            if owner is not None and owner is not self:
+                # a device context holds ONE posterior: initialising a second BLR on it would silently wipe the first one's
+                # m / S / V and leave both models updating the same state (in the reference every BLR is independent)
+                raise _lib.SspboError("this DeviceEngine already hosts the posterior of a live BayesianLinearRegression; "
+                                      "give every BLR its own engine (SSPAgent does so for agents that share an SSPSpace)")
             engine.blr_init(alpha)
+        engine._blr_owner = weakref.ref(self)
         self.engine = engine
         self.beta = beta
         if beta is not None:

@@ -635,7 +635,8 @@ __global__ void k_flag_fold(unsigned long long* __restrict__ stats, unsigned int
 
 __global__ void k_exact_finish(int64_t N, int RB, const double* __restrict__ part_q, const double* __restrict__ part_mu,
                                int normalize, double inv_beta, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
-                               float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
+                               float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best,
+                               double* __restrict__ out64) {
     const int64_t count = N;
     unsigned long long my_best = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
@@ -646,6 +647,7 @@ __global__ void k_exact_finish(int64_t N, int RB, const double* __restrict__ par
         const double var = inv_beta + q;                                        // blr.py:96
         const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
         const int64_t row = i;
+        if (out64) { out64[row] = mu; out64[64 + row] = var; out64[128 + row] = acq; }   // sspbo_eval_host: float64 as the reference returns
         if (mu_out) mu_out[row] = (float)mu;
         if (var_out) var_out[row] = (float)var;
         if (acq_out) acq_out[row] = (float)acq;
@@ -1722,7 +1724,8 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     }
     SSPBO_LAUNCH_CHECK(ctx);
     const int fb = (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);
-    k_exact_finish<<<fb, 256, 0, st>>>(N, RB, part_q, part_mu, ctx->normalize ? 1 : 0, 1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best);
+    k_exact_finish<<<fb, 256, 0, st>>>(N, RB, part_q, part_mu, ctx->normalize ? 1 : 0, 1.0 / ctx->beta, lam, gamma_t, index0, mu, var, acq, best,
+                                         ctx->exact_out64);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }
@@ -1947,7 +1950,7 @@ extern "C" int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, doub
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nl = (size_t)ctx->n * ctx->L;
-    const size_t xb = 64 * nl * sizeof(double), ob = 3 * 64 * sizeof(float);
+    const size_t xb = 64 * nl * sizeof(double), ob = 3 * 64 * sizeof(double);
     int rc = host_stage(ctx, xb + ob > 4096 ? xb + ob : 4096);
     if (rc) return rc;
     if (xb + ob > ctx->eval_dev_bytes) {                 // sized by the row width (n * L doubles), 64 rows
@@ -1956,13 +1959,15 @@ extern "C" int sspbo_eval_host(sspbo_ctx* ctx, const double* x_host, int N, doub
         ctx->eval_dev_bytes = xb + ob;
     }
     double* xd = (double*)ctx->eval_dev;
-    float* od = (float*)((char*)ctx->eval_dev + xb);
+    double* od = (double*)((char*)ctx->eval_dev + xb);
     double* xp = (double*)ctx->pin;
-    float* op = (float*)((char*)ctx->pin + xb);
+    double* op = (double*)((char*)ctx->pin + xb);
     memcpy(xp, x_host, (size_t)N * nl * sizeof(double));
     SSPBO_CUDA(ctx, cudaMemcpyAsync(xd, xp, (size_t)N * nl * sizeof(double), cudaMemcpyHostToDevice, st));
     ctx->last_engine = SSPBO_ENGINE_EXACT;
-    rc = sspbo_score_exact_launch(ctx, xd, SSPBO_F64, N, false, 0, lam, gamma_t, od, od + 64, od + 128, nullptr, st);
+    ctx->exact_out64 = od;                               // float64 mu / var / acq straight from the float64 engine
+    rc = sspbo_score_exact_launch(ctx, xd, SSPBO_F64, N, false, 0, lam, gamma_t, nullptr, nullptr, nullptr, nullptr, st);
+    ctx->exact_out64 = nullptr;
     if (rc) return rc;
     SSPBO_CUDA(ctx, cudaMemcpyAsync(op, od, ob, cudaMemcpyDeviceToHost, st));
     SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
@@ -2050,6 +2055,28 @@ extern "C" int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_de
     return SSPBO_OK;
 }
 
+// bit 0: the flag list of the run's low-rank / factor pass overflowed, bit 1: candidates outside the declared |x| bound; the
+// counters are cleared for the next lock-step
+__global__ void k_batch_status(unsigned long long* __restrict__ stats, unsigned long long* __restrict__ out) {
+    *out = (stats[SSPBO_STAT_OVERFLOW] ? 1ull : 0ull) | (stats[SSPBO_STAT_OOR] ? 2ull : 0ull);
+    for (int i = 0; i < SSPBO_STAT_COUNT; ++i) stats[i] = 0ull;
+}
+
+extern "C" int sspbo_score_batch_status(sspbo_ctx* const* ctxs, int R, unsigned long long* status_dev, void* const* streams,
+                                        int n_streams, int* failed) {
+    if (failed) *failed = -1;
+    if (!ctxs || R < 0 || !status_dev || !streams || n_streams < 1) return SSPBO_EINVAL;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* ctx = ctxs[r];
+        cudaStream_t st = (cudaStream_t)streams[r % n_streams];
+        if (!ctx->stats) { if (cudaMemsetAsync(status_dev + r, 0, sizeof(unsigned long long), st) != cudaSuccess) { if (failed) *failed = r; return SSPBO_ECUDA; } continue; }
+        k_batch_status<<<1, 1, 0, st>>>(ctx->stats, status_dev + r);
+        if (cudaGetLastError() != cudaSuccess) { if (failed) *failed = r; return SSPBO_ECUDA; }
+        ++ctx->launches;
+    }
+    return SSPBO_OK;
+}
+
 extern "C" int sspbo_update_batch(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, void* const* streams,
                                   int n_streams, int* failed) {
     if (failed) *failed = -1;
@@ -2072,7 +2099,7 @@ extern "C" int sspbo_lowrank_info(const sspbo_ctx* ctx, int* rank, int* valid, i
 }
 extern "C" int sspbo_set_policy(sspbo_ctx* ctx, int lowrank_enabled, int phase32_enabled) {
     if (!ctx) return SSPBO_EINVAL;
-    if (lowrank_enabled >= 0) { ctx->lr_disabled = !lowrank_enabled; if (lowrank_enabled) ctx->f8_disabled = false; }
+    if (lowrank_enabled >= 0) { ctx->lr_disabled = !lowrank_enabled; if (lowrank_enabled) { ctx->f8_disabled = false; ctx->lr_flag_frac = 0.0; } }
     if (phase32_enabled >= 0) {                          // 0: Q31.32 only; 1: fastest valid path; 2: fixed point only (no float32 chain)
         ctx->p32_disabled = (phase32_enabled == 0);
         ctx->pf32_disabled = (phase32_enabled == 2);

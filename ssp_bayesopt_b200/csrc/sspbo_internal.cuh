@@ -119,6 +119,7 @@ struct sspbo_ctx {
     // current; (Fh, F8) = images of [m'; L^T] for the factor form
     uint8_t* V8 = nullptr; int v8_rank = 0; bool v8_row0_dirty = true;
     __half* Fh = nullptr; uint8_t* F8 = nullptr; bool f8_factor_dirty = true;
+    double* exact_out64 = nullptr;   // set by sspbo_eval_host around its exact-engine launch: 3 x 64 float64 outputs
     double lr_flag_frac = 0.0;       // flagged / scored of the last read-back of a low-rank pass (cost model of ENGINE_AUTO)
     int operand_format = -1;         // policy: -1 = by rank, 0 = split fp16 only (rank <= 255), 1 / 2 = fp16 + e4m3 whenever usable (single CTAs / CTA pairs)
     std::vector<int> host_col_of_rank;           // host copy of col_of_rank (chunk geometry of the factor form)

@@ -123,16 +123,20 @@ __device__ __forceinline__ void cand_row_rt(const CandDesc& c, int n, long long 
 }
 
 // The candidate of a generator thread in the form its phase path wants it (PH 2: float32, PH 1: Q.fx integers, PH 0: Q31.32).
-// Returns true when a coordinate is outside the declared |x| bound of the fast phase paths.
+// Returns true when a coordinate is outside the declared |x| bound of the fast phase paths.  `is_nan`: a coordinate is NaN --
+// the reference's encode then yields a NaN row, its score is NaN and np.argmax treats NaN as the maximum; the integer phase
+// paths would silently turn NaN into 0, so the generators poison psi of such a row instead (gen_half's caller).
 template <int NDIM, int PH>
-__device__ __forceinline__ bool load_candidate(const Params& p, long long g0, unsigned long long (&x0)[NDIM], int (&xq0)[NDIM]) {
+__device__ __forceinline__ bool load_candidate(const Params& p, long long g0, unsigned long long (&x0)[NDIM], int (&xq0)[NDIM],
+                                               bool& is_nan) {
     bool oor = false;
+    is_nan = false;
     const bool valid = g0 < p.N;
     if constexpr (PH == 2) {
         float v[NDIM];
         cand_row<NDIM, float>(p.cand, p.index0 + g0, g0, valid, v);
 #pragma unroll
-        for (int a = 0; a < NDIM; ++a) { oor |= !(fabsf(v[a]) <= p.x_absmax); xq0[a] = __float_as_int(v[a]); }
+        for (int a = 0; a < NDIM; ++a) { is_nan |= v[a] != v[a]; oor |= fabsf(v[a]) > p.x_absmax; xq0[a] = __float_as_int(v[a]); }
     } else {
         double v[NDIM];
         cand_row<NDIM, double>(p.cand, p.index0 + g0, g0, valid, v);
@@ -140,12 +144,13 @@ __device__ __forceinline__ bool load_candidate(const Params& p, long long g0, un
 #pragma unroll
             for (int a = 0; a < NDIM; ++a) {
                 const double s = v[a] * p.x_scale;
-                oor |= !(fabs(s) < 2147483647.0);
+                is_nan |= v[a] != v[a];
+                oor |= fabs(s) >= 2147483647.0;
                 xq0[a] = __double2int_rn(s);
             }
         } else {
 #pragma unroll
-            for (int a = 0; a < NDIM; ++a) x0[a] = (unsigned long long)__double2ll_rn(v[a] * 4294967296.0);
+            for (int a = 0; a < NDIM; ++a) { is_nan |= v[a] != v[a]; x0[a] = (unsigned long long)__double2ll_rn(v[a] * 4294967296.0); }
         }
     }
     return oor;

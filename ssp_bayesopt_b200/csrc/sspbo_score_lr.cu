@@ -358,13 +358,14 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         int xq0[NDIM];                                                    // Q.fx candidate of the 32-bit phase path
         float nrm_acc = 0.f;                                              // sum of C^2 + S^2 over this warp's k-blocks of the tile
         long long g0 = 0;
+        bool row_nan = false;                                             // a coordinate of this row is NaN: its score must be NaN (np.argmax semantics)
         for (long long g = member; g < total_blocks; g += GEN_W) {
             if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
                 loaded_iter = tile_iter;
                 nrm_acc = 0.f;
                 g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
                 if constexpr (!TRAJ) {
-                const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0);
+                const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0, row_nan);
                 if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
                 const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it towards the SM now
                 if (member == 0 && gn < N && p.cand.mode == 0) {
@@ -380,6 +381,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
                 gen_half<NDIM, PH, TRAJ>(p, tables, g0, kb, half, x0, xq0, cs, sn, nrm_acc);
+                if (!TRAJ && row_nan) cs[0] = __int_as_float(0x7fc00000);      // poisons mu and |V psi|^2 of the row through the MMA
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
                 for (int i = 0; i < NF / 2; ++i) {

@@ -44,6 +44,37 @@ def allreduce_best(key_tensor):
     return key_tensor
 
 
+def allgather_best(key_tensor, shard_start: int):
+    """Winner over ranks when the GLOBAL candidate index does not fit the key's 32 index bits (more than 2^32 candidates per
+    step): every rank scores its shard with indices local to the shard (index0 = 0, shard < 2^32 rows) and the ranks exchange
+    (local key, shard start) pairs -- 16 bytes per rank, SURVEY.md section 8e -- instead of max-reducing one key.
+    Returns (score, global_index) with np.argmax's tie-break (lowest global index).  `key_tensor` is left untouched."""
+    from . import _lib
+    import torch
+    if not is_distributed():
+        s, i = _lib.key_unpack(int(key_tensor.item()))
+        return s, shard_start + i
+    import torch.distributed as td
+    world = td.get_world_size()
+    mine = torch.stack([key_tensor.reshape(()).to(torch.int64),
+                        torch.tensor(int(shard_start), dtype=torch.int64, device=key_tensor.device)])
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    td.all_gather(parts, mine)
+    best = None
+    for part in parts:
+        key, start = part.cpu().tolist()
+        key &= 0xFFFFFFFFFFFFFFFF
+        if key == 0:                                          # a rank without candidates
+            continue
+        _, i = _lib.key_unpack(key)
+        cand = (key >> 32, -(start + i))                      # orderable score bits (NaN counts as the maximum), then lowest global index
+        if best is None or cand > best:
+            best = (cand[0], cand[1], key)
+    if best is None:
+        return float("-inf"), -1
+    return _lib.key_unpack(best[2])[0], -best[1]
+
+
 def broadcast_posterior(engine, beta, src=0):
     """Replace every rank's posterior with rank `src`'s."""
     if not is_distributed():

@@ -47,6 +47,7 @@ class DeviceEngine:
         self.n = 0
         self.L = 1
         self._best = self.torch.zeros(1, dtype=self.torch.int64, device=self._dev())
+        self._blr_owner = None       # weakref to the BayesianLinearRegression whose posterior lives in this context
         self._pending = []           # score calls since the last key reset (replayed if the device asks for a rerun)
         self._lr_used = False        # ... and whether any of them ran the low-rank engine
 

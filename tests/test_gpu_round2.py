@@ -1,0 +1,278 @@
+"""GPU parity tests added in round 2: the BASELINE configs at their real shapes (C5: d = 1945, L = 10; C4: d = 511 / 487), the
+NaN-candidate policy of the fused scorer, the CTA-pair (cta_group::2) variant of the fp16 + e4m3 scorer, agents sharing one
+SSPSpace, float64 eval, the lock-step rerun protocol and the kernel-timing entry points.  Oracle = oracle/ssp_oracle.py (numpy
+float64, pinned to the live reference by tests/golden); the unmodified reference from oracle/_ref is used as well where present.
+Tolerances as everywhere: scores / variances within 1e-4 relative, argmax identical where the top-2 gap exceeds it."""
+import numpy as np
+import pytest
+
+from oracle import ssp_oracle as orc
+from tests.test_gpu_parity import RTOL_SCORE, _c3_setup, assert_scores_close, pkg, rel  # noqa: F401  (pkg is a fixture)
+from tests.test_gpu_f8 import _mixed_candidates
+
+pytestmark = pytest.mark.gpu
+
+
+def himmelblau(x):
+    return -((x[:, 0] ** 2 + x[:, 1] - 11) ** 2 + (x[:, 0] + x[:, 1] ** 2 - 7) ** 2) / 100.0
+
+
+# ------------------------------------------------------------------------------------------ C5 at its real shape
+def test_c5_trajectory_real_shape(pkg):
+    """BASELINE config C5: SSPTrajectoryAgent, 10 waypoints, x_dim = 2, ssp_dim = 2048 -> d = 1945 (KC_pad = 1984, 31
+    k-blocks), 1e4 uniform trajectories, every engine that takes trajectories (ssp_traj_agent.py:145-176)."""
+    from ssp_bayesopt_b200 import _lib
+    L, xd, N = 10, 2, 10000
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    rng = np.random.default_rng(5)
+    trajs = rng.uniform(-5, 5, (14, L * xd))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / 100.0
+    agt = pkg.SSPTrajectoryAgent(trajs, tys, x_dim=xd, traj_len=L, ssp_dim=2048, domain_bounds=bounds, length_scale=1.0,
+                                 time_length_scale=1.0, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0)
+    Ax, At = agt.ssp_x_space.phase_matrix, agt.ssp_t_space.phase_matrix
+    assert Ax.shape[0] == 1945
+    T = orc.traj_timestep_ssps(At, np.array([1.0]), L)
+    ref = orc.BLR(Ax.shape[0])
+    ref.update(orc.traj_encode(Ax, np.ones(xd), T, trajs, L, xd), tys)
+    assert rel(agt.blr.m, ref.m) < 1e-8
+    xc = rng.uniform(-5, 5, (N, L * xd)).astype(np.float32)
+    xc[:6] = trajs[:6].astype(np.float32)                       # on top of observations
+    xc[6:12] = (trajs[:6] + 0.02 * rng.normal(size=(6, L * xd))).astype(np.float32)
+    phis = orc.traj_encode(Ax, np.ones(xd), T, xc.astype(np.float64), L, xd)
+    # K1 at this size: encode of the first rows
+    np.testing.assert_allclose(agt.encode(xc[:64].astype(np.float64)), phis[:64], atol=2e-12)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
+    ref_score = ref_mu.ravel() + ref_acq
+    srt = np.sort(ref_score)[::-1]
+    eng = agt._scoring_engine()
+    for code, name, fmt in ((_lib.ENGINE_UMMA_LR, "umma-lowrank", 0), (_lib.ENGINE_UMMA_LR, "umma-lowrank", 1),
+                            (_lib.ENGINE_UMMA_F8, "umma-factor-f8", None), (_lib.ENGINE_UMMA, "umma", None),
+                            (_lib.ENGINE_SIMT, "simt", None), (_lib.ENGINE_AUTO, "umma-lowrank", None)):
+        eng.set_operand_format(fmt)
+        _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True, engine=code)
+        assert eng.last_engine() == name, (name, eng.last_engine())
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        s, idx = eng.best()
+        if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert idx == int(np.argmax(ref_score)), (name, idx)
+        assert abs(s - ref_score.max()) <= RTOL_SCORE * abs(ref_score.max())
+    eng.set_operand_format(None)
+    # decode of the winner: unbind every timestep, from-set (ssp_traj_agent.py:165-176)
+    dec = agt.decode(phis[int(np.argmax(ref_score))][None, :])
+    assert dec.shape == (L * xd,) or dec.shape == (1, L * xd)
+
+
+# ------------------------------------------------------------------------------------------ C4 at its real dimensions
+@pytest.mark.parametrize("kind,d_expect", [("rand", 511), ("hex", 487)])
+def test_c4_batched_runs_real_dimension(pkg, kind, d_expect):
+    """BASELINE config C4: independent Himmelblau runs at ssp_dim = 512 (-> d = 511 random / 487 hexagonal) over the shared
+    100 x 100 grid, stepped in lock-step; every run's pick equals the oracle's arg-max for that run, step by step."""
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    R, steps = 5, 3
+    agents, refs, spaces = [], [], []
+    for r in range(R):
+        if kind == "rand":
+            sp = pkg.RandomSSPSpace(2, ssp_dim=512, domain_bounds=bounds, length_scale=1.0, rng=r)
+        else:
+            sp = pkg.HexagonalSSPSpace(2, ssp_dim=512, domain_bounds=bounds, length_scale=1.0 + 0.1 * r)
+        assert sp.ssp_dim == d_expect
+        xs0 = np.random.default_rng(200 + r).uniform(-5, 5, (10, 2))
+        ys0 = himmelblau(xs0).reshape(-1, 1)
+        agents.append(pkg.SSPAgent(xs0, ys0, sp, gamma_c=0.0, beta_ucb=10.0, length_scale=np.asarray(sp.length_scale).ravel()[0]))
+        ref = orc.BLR(sp.ssp_dim)
+        ref.update(orc.encode(sp.phase_matrix, np.asarray(sp.length_scale).ravel(), xs0), ys0)
+        refs.append(ref)
+        spaces.append(sp)
+    grid = orc.grid_sample_points(bounds, 100)
+    runs = pkg.BatchedRuns(agents, grid, n_streams=4)
+    for _ in range(steps):
+        pts, ys, scores = runs.step(himmelblau)
+        for r in range(R):
+            A, ls = spaces[r].phase_matrix, np.asarray(spaces[r].length_scale).ravel()
+            score, idx = orc.score_and_argmax(orc.encode(A, ls, grid), refs[r], 10.0, 0.0)
+            srt = np.sort(score)[::-1]
+            if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+                assert np.array_equal(pts[r], grid[idx]), (r, pts[r], grid[idx])
+            assert abs(scores[r] - score.max()) <= RTOL_SCORE * abs(score.max())
+            refs[r].update(orc.encode(A, ls, pts[r:r + 1]), np.atleast_2d(ys[r]))
+    for r in range(R):
+        assert rel(agents[r].blr.m, refs[r].m) < 1e-8
+
+
+def test_batched_runs_rerun_protocol(pkg):
+    """A lock-step whose candidates leave the declared |x| bound: the per-run status words (sspbo_score_batch_status) make
+    BatchedRuns recompute those runs with the any-range phase path, as DeviceEngine.best() does for single runs."""
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    R = 3
+    agents, refs, spaces = [], [], []
+    for r in range(R):
+        sp = pkg.RandomSSPSpace(2, ssp_dim=128, domain_bounds=bounds, length_scale=1.0, rng=r)
+        xs0 = np.random.default_rng(300 + r).uniform(-5, 5, (8, 2))
+        ys0 = himmelblau(xs0).reshape(-1, 1)
+        agents.append(pkg.SSPAgent(xs0, ys0, sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+        ref = orc.BLR(sp.ssp_dim)
+        ref.update(orc.encode(sp.phase_matrix, np.ones(2), xs0), ys0)
+        refs.append(ref)
+        spaces.append(sp)
+    cand = np.random.default_rng(9).uniform(-5, 5, (3000, 2))
+    cand[17] = [40.0, -33.0]                                    # far outside the declared bound
+    runs = pkg.BatchedRuns(agents, cand, n_streams=2)
+    scores, idx, pts = runs.select()
+    for r in range(R):
+        score, i = orc.score_and_argmax(orc.encode(spaces[r].phase_matrix, np.ones(2), cand), refs[r], 10.0, 0.0)
+        assert abs(scores[r] - score.max()) <= RTOL_SCORE * abs(score.max())
+        srt = np.sort(score)[::-1]
+        if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+            assert idx[r] == i
+        assert not agents[r]._scoring_engine().lowrank_info()["phase32"]     # the policy switched to the any-range path
+
+
+# ------------------------------------------------------------------------------------------ NaN candidates
+@pytest.mark.parametrize("engine", ["lowrank", "lowrank-f8", "factor-f8", "exact", "simt", "auto"])
+def test_score_nan_candidate_counts_as_maximum(pkg, engine):
+    """np.argmax returns the first NaN (sspspace.py:356): a candidate with a NaN coordinate encodes to a
+    NaN row in the reference, its score is NaN and it wins.  The integer phase paths of the generators would turn NaN into
+    0, so the generators poison psi of such rows; the key orders NaN above every number."""
+    from ssp_bayesopt_b200 import _lib
+    sp, model, ref, X = _c3_setup(pkg, 40)
+    eng = sp.engine
+    xc = orc.counter_uniform(0, 0, 3000, 6)
+    xc[1234, 3] = np.nan
+    xc[2500, 0] = np.nan
+    code, fmt, ph = {"lowrank": (_lib.ENGINE_UMMA_LR, 0, 1), "lowrank-f8": (_lib.ENGINE_UMMA_LR, 1, 2),
+                     "factor-f8": (_lib.ENGINE_UMMA_F8, None, 1), "exact": (_lib.ENGINE_EXACT, None, 1),
+                     "simt": (_lib.ENGINE_SIMT, None, 1), "auto": (_lib.ENGINE_AUTO, None, 1)}[engine]
+    eng.set_operand_format(fmt)
+    eng.set_policy(phase32=ph)
+    eng.score_stats(reset=True)
+    _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True, engine=code)
+    s, idx = eng.best()
+    assert np.isnan(s) and idx == 1234, (s, idx)
+    out = (mu + acq).double().cpu().numpy()
+    assert np.isnan(out[1234]) and np.isnan(out[2500])
+    fin = np.delete(np.arange(3000), [1234, 2500])
+    phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc[fin].astype(np.float64))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
+    assert_scores_close(mu.double().cpu().numpy()[fin], acq.double().cpu().numpy()[fin], ref_mu, ref_acq)
+    assert eng.score_stats(reset=True)["out_of_range"] == 0      # NaN is not an out-of-bound candidate: no recomputation
+    eng.set_operand_format(None)
+    eng.set_policy(phase32=1)
+
+
+# ------------------------------------------------------------------------------------------ CTA pairs
+@pytest.mark.parametrize("T,form", [(200, "lr"), (255, "lr"), (400, "lr"), (60, "factor")])
+def test_cta_pair_variant_matches_single(pkg, T, form):
+    """tcgen05 cta_group::2 variant of the fp16 + e4m3 scorer (operand format 2: tiles of 256 candidates, each CTA of a
+    cluster of two holds half of the operand rows): against the oracle, and bit-identical to the single-CTA kernel."""
+    from ssp_bayesopt_b200 import _lib
+    sp, model, ref, X = _c3_setup(pkg, T)
+    eng = sp.engine
+    xc = _mixed_candidates(X, 5000 + 77)                       # ragged: the last pair tile is partly empty
+    code, label = (_lib.ENGINE_UMMA_LR, "umma-lowrank") if form == "lr" else (_lib.ENGINE_UMMA_F8, "umma-factor-f8")
+    phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
+    outs = {}
+    for fmt in (1, 2):
+        eng.set_operand_format(fmt)
+        eng.score_stats(reset=True)
+        _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True, engine=code)
+        assert eng.last_engine() == label
+        outs[fmt] = [t.double().cpu().numpy() for t in (mu, var, acq)] + [eng.best()]
+        assert_scores_close(outs[fmt][0], outs[fmt][2], ref_mu, ref_acq)
+        np.testing.assert_allclose(outs[fmt][1], ref_var, rtol=RTOL_SCORE)
+    for a, b in zip(outs[1][:3], outs[2][:3]):
+        assert np.array_equal(a, b)
+    assert outs[1][3] == outs[2][3]
+    eng.set_operand_format(None)
+
+
+# ------------------------------------------------------------------------------------------ host-layer fixes
+def test_agents_sharing_a_space_keep_independent_posteriors(pkg):
+    """In the reference every agent owns its BLR and sharing an SSPSpace is legal ('ssp-custom', lists of agents).  Here a
+    device context holds one posterior: the second agent over a space gets its own context, and a second raw BLR on an
+    engine that hosts a live one is refused."""
+    from ssp_bayesopt_b200 import _lib
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=151, domain_bounds=bounds, length_scale=1.0)
+    rng = np.random.default_rng(0)
+    xa, xb = rng.uniform(-5, 5, (8, 2)), rng.uniform(-5, 5, (9, 2))
+    ya, yb = himmelblau(xa).reshape(-1, 1), (himmelblau(xb) * 3 + 1).reshape(-1, 1)
+    a = pkg.SSPAgent(xa, ya, sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0)
+    b = pkg.SSPAgent(xb, yb, sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0)
+    assert a._scoring_engine() is not b._scoring_engine()
+    refs = []
+    for xs, ys in ((xa, ya), (xb, yb)):
+        ref = orc.BLR(sp.ssp_dim)
+        ref.update(orc.encode(sp.phase_matrix, np.ones(2), xs), ys)
+        refs.append(ref)
+    x_t = np.array([[1.0, -2.0]])
+    b.update(x_t, np.array([[0.5]]), 0.0)
+    refs[1].update(orc.encode(sp.phase_matrix, np.ones(2), x_t), np.array([[0.5]]))
+    assert rel(a.blr.m, refs[0].m) < 1e-9 and rel(b.blr.m, refs[1].m) < 1e-9
+    assert rel(a.blr.S, refs[0].S) < 1e-9 and rel(b.blr.S, refs[1].S) < 1e-9
+    grid = orc.grid_sample_points(bounds, 40)
+    for agt, ref in ((a, refs[0]), (b, refs[1])):
+        mu, var, acq = agt.eval(grid)
+        ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, np.ones(2), grid), ref, 10.0, 0.0)
+        assert_scores_close(mu.ravel(), acq, ref_mu, ref_acq)
+    with pytest.raises(_lib.SspboError):
+        pkg.BayesianLinearRegression(sp.ssp_dim, engine=a._scoring_engine())
+
+
+def test_eval_small_sets_is_float64(pkg, golden):
+    """SSPAgent.eval on a handful of points (x_t of a BO step) returns float64-accurate mu / var / acq like the reference, so
+    eval -> update(x_t, y_t, var_t) accumulates an exact gamma_t (ssp_agent.py:125-137, 217-218)."""
+    sp, model, ref, X = _c3_setup(pkg, 30)
+    eng = sp.engine
+    xs = np.random.default_rng(4).uniform(0, 1, (7, 6))
+    mu, var, acq = eng.eval_host(xs, 10.0, 2.5)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xs), ref, 10.0, 2.5)
+    np.testing.assert_allclose(mu, ref_mu.ravel(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, ref_var, rtol=1e-9)
+    np.testing.assert_allclose(acq, ref_acq, rtol=1e-8)
+
+
+def test_kernel_timing_entry_points(pkg):
+    """sspbo_set_timing / sspbo_timing_read: CUDA events around the scorer kernel and the flagged pass of every score call."""
+    sp, model, ref, X = _c3_setup(pkg, 20)
+    eng = sp.engine
+    xc = eng.fill_uniform(0, 0, 1 << 16)
+    eng.score(xc, 10.0, 0.0)
+    eng.set_timing(True)
+    for _ in range(3):
+        eng.score(xc, 10.0, 0.0)
+    t = eng.timing_read(reset=True)
+    assert t["calls"] == 3 and t["scorer_ms"] > 0 and t["flagged_ms"] >= 0
+    assert eng.timing_read()["calls"] == 0
+    eng.set_timing(False)
+    eng.score(xc, 10.0, 0.0)
+    assert eng.timing_read()["calls"] == 0
+
+
+def test_reference_copy_agrees_with_gpu_when_present(pkg):
+    """oracle/_ref (the unmodified reference, copied by oracle/build_ref.py): SSPAgent.eval of the live code against the fused
+    scorer on config C3's space at rank 25.  Skipped where the copy is absent."""
+    from oracle import ref_loader
+    refpkg = ref_loader.load()
+    if refpkg is None:
+        pytest.skip("oracle/_ref not built")
+    import contextlib, io
+    b6 = np.array([[0.0, 1.0]] * 6)
+    X = np.random.default_rng(1).uniform(0, 1, (25, 6))
+    y = orc.hartmann6(X).reshape(-1, 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rsp = refpkg.sspspace.RandomSSPSpace(6, ssp_dim=1024, domain_bounds=b6, length_scale=0.25, rng=0)
+        ragt = refpkg.agents.SSPAgent(X[:10], y[:10], rsp, decoder_method="from-set", gamma_c=0.0, beta_ucb=10.0, length_scale=0.25)
+        for i in range(10, 25):
+            ragt.update(X[i:i + 1], y[i:i + 1], 0.0, step_num=i)
+    sp = pkg.RandomSSPSpace(6, ssp_dim=1024, domain_bounds=b6, length_scale=0.25, rng=0)
+    assert np.array_equal(sp.phase_matrix, rsp.phase_matrix)
+    agt = pkg.SSPAgent(X[:10], y[:10], sp, gamma_c=0.0, beta_ucb=10.0, length_scale=0.25)
+    agt.update(X[10:], y[10:], 0.0)
+    assert rel(agt.blr.m, ragt.blr.m) < 1e-7 and rel(agt.blr.S, ragt.blr.S) < 1e-7
+    xc = orc.counter_uniform(0, 0, 4000, 6)
+    rmu, rvar, racq = ragt.eval(xc.astype(np.float64))
+    mu, var, acq = agt.eval(xc)
+    assert_scores_close(mu.ravel(), acq, rmu, racq)
+    np.testing.assert_allclose(var, rvar, rtol=RTOL_SCORE)

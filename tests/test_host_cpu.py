@@ -120,6 +120,18 @@ key = _lib.key_pack(float(scores[loc]), loc)
 t = torch.tensor([key - (1 << 64) if key >= (1 << 63) else key], dtype=torch.int64)
 dist.allreduce_best(t)
 assert _lib.key_unpack(int(t.item()))[1] == int(torch.argmax(scores))
+# more than 2^32 candidates: shard-local indices + (key, shard start) pairs (SURVEY.md 8e)
+starts = [0, 5_000_000_000]
+for c, want in [(((0.5, 10), (0.75, 7)), (0.75, 5_000_000_007)), (((1.0, 4_000_000_000), (1.0, 3)), (1.0, 4_000_000_000)),
+                (((float("nan"), 8), (9e9, 0)), None)]:
+    s, i = c[r]
+    key = _lib.key_pack(s, i)
+    t = torch.tensor([key - (1 << 64) if key >= (1 << 63) else key], dtype=torch.int64)
+    got = dist.allgather_best(t, starts[r])
+    if want is None:
+        assert got[0] != got[0] and got[1] == 8, got          # NaN wins, as in np.argmax
+    else:
+        assert got == want, (got, want)
 td.destroy_process_group()
 print("ok", r)
 '''
