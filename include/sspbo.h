@@ -100,6 +100,18 @@ int sspbo_space_set_xbound(sspbo_ctx* ctx, double x_absmax);
  * SSPSpace.encode (sspspace.py:254-276): phi = Re IFFT(exp(i A (x/l)^T))^T.
  * x_dev: N x (n*L), dtype SSPBO_F32|SSPBO_F64.  phi_out_dev: N x d float64. */
 int sspbo_encode(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, double* phi_out_dev, void* stream);
+/* SSPSpace.encode_and_deriv (sspspace.py:278-306): phi_out_dev N x d float64 and grad_out_dev, n planes of N x d float64,
+ * grad[a][s][j] = d phi_j(x_s) / d x_a = Re IDFT_k( i (A_ka / l_a) exp(i A_k . x_s / l) )_j (the reference's expression at
+ * :303-304 multiplies a (d, n) by a (d, N) matrix and raises for n != d; this is the derivative its docstring describes,
+ * the one SSPSpace.decode('direct-optim') needs).  Plain spaces only. */
+int sspbo_encode_deriv(sspbo_ctx* ctx, const void* x_dev, int x_dtype, int64_t N, double* phi_out_dev, double* grad_out_dev,
+                       void* stream);
+/* Feature map of the reference's random-Fourier-feature baseline agent (agents/rff_agent.py:153-156):
+ * phi_out_dev[s][j] = scale * cos(W_j . x_s + B_j), W_dev m x n, B_dev m float64, x_dev N x n (F32 | F64), phi_out_dev N x m
+ * float64.  The BLR over these features is a raw-feature context (sspbo_blr_init_dim / sspbo_blr_update / sspbo_blr_predict);
+ * ctx only names the device. */
+int sspbo_rff_encode(sspbo_ctx* ctx, const double* W_dev, const double* B_dev, int m, int n, double scale, const void* x_dev,
+                     int x_dtype, int64_t N, double* phi_out_dev, void* stream);
 
 /* K1 on the tensor cores, float32 result: phi = psi B^T with the split-fp16 inverse-DFT basis as the MMA operand; psi is
  * generated on chip as in the scorer.  Error ~1e-6 of max |phi| (inside the 1e-4 the path is specified to), ~50x the

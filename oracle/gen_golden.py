@@ -160,6 +160,38 @@ def gen_lengthscale_gp(sspspace, agents):
     np.savez_compressed(os.path.join(OUT, "lengthscale_gp.npz"), **out)
 
 
+def gen_rff(agents):
+    """9. Random-Fourier-feature baseline agent (agents/rff_agent.py): features drawn from numpy's global generator after
+    np.random.seed(7), both kernel types; encode, eval (MI acquisition), five sequential updates, the x-space objective."""
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    rng = np.random.default_rng(31)
+    xs = rng.uniform(b2[:, 0], b2[:, 1], size=(17, 2))
+    ys = himmelblau(xs).reshape(-1, 1)
+    xq = rng.uniform(b2[:, 0], b2[:, 1], size=(40, 2))
+    out = dict(xs=xs, ys=ys, xq=xq)
+    for kt in ("rbf", "matern"):
+        np.random.seed(7)
+        with quiet:
+            agt = agents.RFFAgent(xs[:12], ys[:12], ssp_dim=96, kernel_type=kt, gamma_c=1.0, beta_ucb=5.0, var_decay=0.25)
+        out[f"{kt}_W"], out[f"{kt}_B"], out[f"{kt}_scale"] = agt.W, agt.B, agt.sqrt_2_alpha_over_m
+        out[f"{kt}_phi"] = agt.encode(xq)
+        mu, var, acq = agt.eval(xq)
+        out[f"{kt}_mu0"], out[f"{kt}_var0"], out[f"{kt}_acq0"] = mu, var, acq
+        for i in range(12, 17):
+            _, var_t, _ = agt.eval(xs[i:i + 1])
+            agt.update(xs[i:i + 1], ys[i:i + 1], var_t, step_num=i)
+        mu, var, acq = agt.eval(xq)
+        out[f"{kt}_mu1"], out[f"{kt}_var1"], out[f"{kt}_acq1"] = mu, var, acq
+        out[f"{kt}_m"], out[f"{kt}_S"], out[f"{kt}_beta"] = agt.blr.m, agt.blr.S, agt.blr.beta
+        out[f"{kt}_gamma"], out[f"{kt}_lam"] = np.ravel(agt.gamma_t), agt.var_weight
+        f, g = agt.acquisition_func()
+        out[f"{kt}_obj"] = np.array([f(x) for x in xq[:8]]).ravel()
+        out[f"{kt}_grad"] = np.array([g(x) for x in xq[:8]])
+    np.savez_compressed(os.path.join(OUT, "rff.npz"), **out)
+    print("rff.npz written")
+
+
 def main():
     sspspace, blr, agents = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -321,6 +353,7 @@ def main():
     gen_multi_agent(agents)
     gen_lengthscale_cv(agents)
     gen_lengthscale_gp(sspspace, agents)
+    gen_rff(agents)
     print("golden fixtures written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KiB")

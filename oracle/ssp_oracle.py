@@ -95,6 +95,20 @@ def encode(phase_matrix: np.ndarray, length_scale, x) -> np.ndarray:
     return np.fft.ifft(spectrum, axis=0).real.T
 
 
+def encode_and_deriv(phase_matrix: np.ndarray, length_scale, x):
+    """(phi (N, d), grad (N, d, n)): grad[s, j, a] = d phi_j / d x_a = Re ifft_k( i (A_ka / l_a) exp(i A_k . x_s / l) )_j.
+    Ref: sspspace.py:278-306 (`encode_and_deriv`).  The reference's own expression at :303-304,
+    `(phase_matrix @ ls_mat) @ exp(...)`, multiplies (d, n) by (d, N) and raises for n != d; this restates the derivative its
+    docstring describes (the derivative of `encode`, :275), checked against central differences of `encode` in the tests."""
+    x = np.atleast_2d(x)
+    ls = np.asarray(length_scale, dtype=np.float64).reshape(-1) * np.ones(phase_matrix.shape[1])
+    z = np.exp(1.j * phase_matrix @ (x / ls).T)                                  # (d, N)
+    phi = np.fft.ifft(z, axis=0).real.T
+    w = phase_matrix / ls                                                        # (d, n)
+    grad = np.stack([np.fft.ifft(1.j * w[:, a:a + 1] * z, axis=0).real.T for a in range(phase_matrix.shape[1])], axis=2)
+    return phi, grad
+
+
 def encode_closed_form(phase_matrix: np.ndarray, length_scale, x) -> np.ndarray:
     """Independent cross-check of `encode`: with A+ the K
     positive-frequency rows, phi_j = (1 + 2 sum_k cos(theta_k + 2 pi j k / d)) / d.
@@ -362,6 +376,13 @@ def multi_agent_decode_from_set(ssp, timestep_ssps, agent_sps, sample_ssps, samp
 # --------------------------------------------------------------------------
 # synthetic candidate generator shared by oracle, tests and the CUDA path
 # --------------------------------------------------------------------------
+
+def rff_encode(W, B, scale, x) -> np.ndarray:
+    """Random-Fourier-feature map: scale * cos(W x^T + B)^T, (N, m).  Ref: agents/rff_agent.py:153-156 (`encode`);
+    scale = sqrt(2 alpha / m) (:64-65), W (m, n) and B (m, 1) drawn at :66-73."""
+    x = np.atleast_2d(x)
+    return scale * np.cos(np.dot(W, x.T) + np.reshape(B, (-1, 1))).T
+
 
 def counter_uniform(seed: int, start: int, count: int, n: int) -> np.ndarray:
     """Counter-based uniform(0,1) float32 candidates: element (i, a) of the

@@ -9,8 +9,8 @@ from .bayesian_optimization import BayesianOptimization
 from .blr import BayesianLinearRegression
 from .engine import DeviceEngine
 from .sspspace import HexagonalSSPSpace, RandomSSPSpace, SPSpace, SSPSpace
-from .agents import SSPAgent, SSPMultiAgent, SSPTrajectoryAgent
+from .agents import RFFAgent, SSPAgent, SSPMultiAgent, SSPTrajectoryAgent
 from .batched import BatchedRuns
 
 __all__ = ["BayesianOptimization", "BayesianLinearRegression", "DeviceEngine", "SSPSpace", "HexagonalSSPSpace",
-           "RandomSSPSpace", "SPSpace", "SSPAgent", "SSPTrajectoryAgent", "SSPMultiAgent", "BatchedRuns", "agents", "blr", "dist", "sspspace"]
+           "RandomSSPSpace", "SPSpace", "SSPAgent", "SSPTrajectoryAgent", "SSPMultiAgent", "RFFAgent", "BatchedRuns", "agents", "blr", "dist", "sspspace"]

@@ -40,6 +40,8 @@ SIGNATURES = {
     "sspbo_lowrank_info": (_i, [_vp, _pi, _pi, _pi, _pi]),
     "sspbo_set_policy": (_i, [_vp, _i, _i]),
     "sspbo_encode": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "sspbo_encode_deriv": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "sspbo_rff_encode": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _vp, _vp]),
     "sspbo_encode_pitch": (_i, [_vp]),
     "sspbo_encode_f32": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "sspbo_blr_init": (_i, [_vp, _d]),

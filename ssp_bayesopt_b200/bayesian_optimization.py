@@ -101,6 +101,8 @@ class BayesianOptimization:
             kw = {k: v for k, v in kwargs.items() if k != 'ssp_space'}
             kw.setdefault('length_scale', kwargs['ssp_space'].length_scale)
             agt = agents.SSPAgent(init_xs, init_ys, kwargs['ssp_space'], **kw)
+        elif 'rff' in agent_type:                                    # random-Fourier-feature baseline (:152-153), features + BLR on the GPU
+            agt = agents.RFFAgent(init_xs, init_ys, **{k: v for k, v in kwargs.items() if k != 'domain_bounds'})
         elif agent_type == 'ssp-traj':
             agt = agents.SSPTrajectoryAgent(init_xs, init_ys, **kwargs)
             init_xs, init_ys = agt.init_xs, agt.init_ys
@@ -110,7 +112,7 @@ class BayesianOptimization:
         else:
             raise NotImplementedError(
                 f'{agent_type} agent is not part of the GPU hot path (supported: ssp-hex, ssp-rand, ssp-custom, ssp-traj, '
-                'ssp-multi)')
+                'ssp-multi, rff-*)')
         if num_perimeter_samples > 0:                                # corners of the box as zero-valued prior samples (:173-182)
             perimeter_xs = []
             for _ in range(num_perimeter_samples):
@@ -219,7 +221,9 @@ class BayesianOptimization:
         agt, init_xs, init_ys = self.initialize_agent(init_points, agent_type, domain_bounds=self.bounds, **kwargs)
         self.agt = agt
         optimizer = bo_kw.get('acq_optimizer', 'candidates')
-        if optimizer not in ('candidates', 'phi-ascent'):
+        if isinstance(agt, agents.RFFAgent):
+            optimizer = 'x-lbfgs'                                    # the reference's route for this agent (:252-262)
+        if optimizer not in ('candidates', 'phi-ascent', 'x-lbfgs'):
             raise ValueError(f'unknown acq_optimizer={optimizer!r}')
         cand = None
         if optimizer == 'candidates':
@@ -244,6 +248,18 @@ class BayesianOptimization:
             start = time.perf_counter_ns()
             if optimizer == 'candidates':
                 score, gidx, x_t = self._select(agt, cand, chunk)    # synchronises on the 8-byte key
+            elif optimizer == 'x-lbfgs':
+                # multi-restart L-BFGS-B in x on the agent's own objective / gradient (host closures over copies of m, S), as
+                # the reference does for its GP / RFF agents; eval and update of the chosen point run on the device
+                from scipy.optimize import minimize
+                optim_func, jac_func = agt.acquisition_func()
+                vals, solns = np.zeros(num_restarts), np.zeros((num_restarts, init_xs.shape[1]))
+                for r in range(num_restarts):
+                    x_init = np.random.uniform(low=self.bounds[:, 0], high=self.bounds[:, 1], size=(self.bounds.shape[0],))
+                    soln = minimize(optim_func, x_init, jac=jac_func if use_jac else None, method='L-BFGS-B', bounds=self.bounds)
+                    vals[r], solns[r] = -float(np.ravel(soln.fun)[0]), soln.x
+                gidx = int(np.argmax(vals))
+                score, x_t = vals[gidx], np.atleast_2d(solns[gidx])
             else:
                 phis, vals = agt.maximize_acquisition(num_restarts=num_restarts, rng=ascent_rng,
                                                       max_iter=int(bo_kw.get('ascent_iters', 200)),
@@ -265,7 +281,11 @@ class BayesianOptimization:
 
             update_start = time.perf_counter_ns()
             # eval(x_t) under the current posterior, then update(x_t, y_t, var_t) (:299-303): one device round trip
-            mu_t, var_t, phi_t = agt.observe(x_t, y_t, step_num=t + n0)
+            if hasattr(agt, 'observe'):
+                mu_t, var_t, phi_t = agt.observe(x_t, y_t, step_num=t + n0)
+            else:
+                mu_t, var_t, phi_t = agt.eval(x_t)
+                agt.update(x_t, y_t, var_t, step_num=t + n0)
             if self.verbose and rank == 0:
                 print(f'| step {t + n0}\t | {y_t}, {np.sqrt(var_t)}, {phi_t}\t ')
             self.times[t] += time.perf_counter_ns() - update_start

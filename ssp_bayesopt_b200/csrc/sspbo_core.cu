@@ -63,7 +63,10 @@ constexpr int ENC_THREADS = 256;
 template <typename XT, int ENC_CPB>
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
-         const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi) {
+         const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi,
+         int deriv_axis) {
+    // deriv_axis >= 0 (L == 1): d phi / d x_a instead of phi -- the spectrum exp(i theta_k) becomes i w_ka exp(i theta_k),
+    // w_ka = A+_ka / l_a, i.e. (cos, sin) -> (-w sin, w cos) and no DC term (sspspace.py:300-305)
     extern __shared__ double psi_s[];                   // ENC_CPB x d
     __shared__ double scale_s[ENC_CPB];                 // 1 / |phi| per candidate when normalising, else 1
     const int d = 2 * K + 1;
@@ -75,9 +78,14 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
             if (base + c < N) {
                 double cs, sn;
                 psi_entry(x + (base + c) * nl, A_turns, tau_turns, n, K, L, k, cs, sn);
+                if (deriv_axis >= 0) {
+                    const double w = 6.283185307179586476925286766559 * A_turns[(size_t)k * n + deriv_axis];
+                    const double c0 = cs;
+                    cs = -w * sn; sn = w * c0;
+                }
                 psi_s[c * d + 1 + k] = cs;
                 psi_s[c * d + 1 + K + k] = sn;
-                if (k == 0) psi_s[c * d] = dc;
+                if (k == 0) psi_s[c * d] = deriv_axis >= 0 ? 0.0 : dc;
             }
         }
         __syncthreads();
@@ -1266,11 +1274,32 @@ extern "C" int sspbo_space_dims(const sspbo_ctx* ctx, int* d, int* K, int* n, in
     return SSPBO_OK;
 }
 
+static int encode_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, double* phi_out, int deriv_axis, void* stream);
+
 extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, double* phi_out, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
     if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "encode before space_set");
     if (N < 0 || (N > 0 && (!x || !phi_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: null pointer");
     if (N == 0) return SSPBO_OK;
+    return encode_launch(ctx, x, x_dtype, N, phi_out, -1, stream);
+}
+
+/* SSPSpace.encode_and_deriv (sspspace.py:278-306): phi (N x d) and grad, n planes of N x d with
+ * grad[a][s][j] = d phi_j(x_s) / d x_a = Re IDFT_k( i (A_ka / l_a) exp(i A_k . x_s / l) )_j.  Plain spaces only (L == 1). */
+extern "C" int sspbo_encode_deriv(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, double* phi_out, double* grad_out,
+                                  void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "encode_deriv before space_set");
+    if (ctx->L != 1 || ctx->normalize) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "encode_deriv: plain SSP spaces only (no trajectory mode)");
+    if (N < 0 || (N > 0 && (!x || !phi_out || !grad_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode_deriv: null pointer");
+    if (N == 0) return SSPBO_OK;
+    int rc = encode_launch(ctx, x, x_dtype, N, phi_out, -1, stream);
+    for (int a = 0; a < ctx->n && !rc; ++a)
+        rc = encode_launch(ctx, x, x_dtype, N, grad_out + (size_t)a * N * ctx->d, a, stream);
+    return rc;
+}
+
+static int encode_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, double* phi_out, int deriv_axis, void* stream) {
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int cpb = N <= ENC_SMALL_N ? ENC_CPB_SMALL : ENC_CPB_BATCH;
@@ -1284,7 +1313,8 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
     do {                                                                                                                   \
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<XT, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         k_encode<XT, CPB><<<grid, ENC_THREADS, smem, st>>>((const XT*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,     \
-                                                           ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out); \
+                                                           ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out, \
+                                                           deriv_axis);                                                   \
     } while (0)
     if (x_dtype == SSPBO_F32) {
         if (cpb == ENC_CPB_SMALL) SSPBO_ENC_LAUNCH(float, ENC_CPB_SMALL); else SSPBO_ENC_LAUNCH(float, ENC_CPB_BATCH);
@@ -1292,6 +1322,36 @@ extern "C" int sspbo_encode(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
         if (cpb == ENC_CPB_SMALL) SSPBO_ENC_LAUNCH(double, ENC_CPB_SMALL); else SSPBO_ENC_LAUNCH(double, ENC_CPB_BATCH);
     } else SSPBO_FAIL(ctx, SSPBO_EINVAL, "encode: unknown dtype %d", x_dtype);
 #undef SSPBO_ENC_LAUNCH
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+/* Random-Fourier-feature map of agents/rff_agent.py:153-156: phi[s][j] = scale cos(W_j . x_s + B_j), scale = sqrt(2 alpha / m)
+ * (float64 throughout; the BLR over these features is a raw-feature context, sspbo_blr_init_dim).  One thread per output. */
+template <typename XT>
+__global__ void k_rff_encode(const XT* __restrict__ x, int64_t N, int n, const double* __restrict__ W, const double* __restrict__ B,
+                             int m, double scale, double* __restrict__ phi) {
+    const int64_t total = N * m;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / m;
+        const int j = (int)(i - row * m);
+        double t = B[j];
+        for (int a = 0; a < n; ++a) t = fma(W[(size_t)j * n + a], (double)x[row * n + a], t);
+        phi[i] = scale * cos(t);
+    }
+}
+
+extern "C" int sspbo_rff_encode(sspbo_ctx* ctx, const double* W_dev, const double* B_dev, int m, int n, double scale, const void* x,
+                                int x_dtype, int64_t N, double* phi_out, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (m < 1 || n < 1 || N < 0 || !W_dev || !B_dev || (N > 0 && (!x || !phi_out))) SSPBO_FAIL(ctx, SSPBO_EINVAL, "rff_encode: bad argument");
+    if (N == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t total = N * m;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    if (x_dtype == SSPBO_F32) k_rff_encode<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, N, n, W_dev, B_dev, m, scale, phi_out);
+    else if (x_dtype == SSPBO_F64) k_rff_encode<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)x, N, n, W_dev, B_dev, m, scale, phi_out);
+    else SSPBO_FAIL(ctx, SSPBO_EINVAL, "rff_encode: unknown dtype %d", x_dtype);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
 }

@@ -156,6 +156,36 @@ class DeviceEngine:
     def encode(self, x) -> np.ndarray:
         return self.encode_device(x).cpu().numpy()
 
+    def encode_and_deriv_device(self, x):
+        """x (N, n) -> (phi (N, d), grad (N, d, n)) float64 device tensors: grad[s, j, a] = d phi_j(x_s) / d x_a."""
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        if xt.shape[1] != self.n * self.L:
+            raise AssertionError(f"Expected {self.n * self.L}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        phi = self.torch.empty((N, self.d), dtype=self.torch.float64, device=self._dev())
+        grad = self.torch.empty((self.n, N, self.d), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_encode_deriv(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N,
+                                         C.c_void_p(phi.data_ptr()), C.c_void_p(grad.data_ptr()), self._stream())
+        self._check(rc, "sspbo_encode_deriv")
+        return phi, grad.permute(1, 2, 0)
+
+    def rff_encode_device(self, W, B, scale, x):
+        """scale * cos(x W^T + B): W (m, n), B (m,) device float64 tensors, x (N, n) -> (N, m) float64 device tensor."""
+        xt = self.to_device(x)
+        if xt.dim() == 1:
+            xt = xt.reshape(1, -1)
+        m, n = W.shape
+        if xt.shape[1] != n:
+            raise AssertionError(f"Expected {n}-d data, got {tuple(xt.shape)}")
+        N = xt.shape[0]
+        phi = self.torch.empty((N, m), dtype=self.torch.float64, device=self._dev())
+        rc = self.lib.sspbo_rff_encode(self._ctx, C.c_void_p(W.data_ptr()), C.c_void_p(B.data_ptr()), int(m), int(n), float(scale),
+                                       C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, C.c_void_p(phi.data_ptr()), self._stream())
+        self._check(rc, "sspbo_rff_encode")
+        return phi
+
     def encode_f32_device(self, x):
         """x (N, n*L) -> device tensor phi (N, d) float32 (a view of an (N, pitch) buffer) from the tensor-core encoder."""
         xt = self.to_device(x)

@@ -160,6 +160,16 @@ class SSPSpace:
             return self.engine.encode_f32_device(x).cpu().numpy()
         return self.engine.encode(x)
 
+
+    def encode_and_deriv(self, x):
+        """(num_samples, domain_dim) -> (ssp (num_samples, ssp_dim), grad (num_samples, ssp_dim, domain_dim)) float64
+        (sspspace.py:278-306), on the GPU.  grad[s, j, a] = d phi_j(x_s) / d x_a = Re IFFT(i (A[:, a] / l_a) exp(i A x_s / l)).
+        The reference's expression (:303-304) multiplies a (ssp_dim, domain_dim) by a (ssp_dim, num_samples) matrix and
+        raises unless they happen to agree; this is the derivative its docstring describes."""
+        x = np.atleast_2d(x)
+        assert x.shape[1] == self.domain_dim, f'Expected {self.domain_dim}-d data, got {x.shape}'
+        phi, grad = self.engine.encode_and_deriv_device(np.ascontiguousarray(x, dtype=np.float64))
+        return phi.cpu().numpy(), grad.contiguous().cpu().numpy()
     def encode_fourier(self, x):
         """exp(i A x / l) (sspspace.py:308-315): host numpy; not on the device path (diagnostic helper)."""
         x = np.atleast_2d(x)

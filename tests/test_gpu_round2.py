@@ -276,3 +276,76 @@ def test_reference_copy_agrees_with_gpu_when_present(pkg):
     mu, var, acq = agt.eval(xc)
     assert_scores_close(mu.ravel(), acq, rmu, racq)
     np.testing.assert_allclose(var, rvar, rtol=RTOL_SCORE)
+
+
+# ------------------------------------------------------------------------------------------ encode_and_deriv
+@pytest.mark.parametrize("kind,ssp_dim,n", [("hex", 151, 2), ("rand", 1024, 6), ("rand", 64, 3)])
+def test_encode_and_deriv(pkg, kind, ssp_dim, n):
+    """SSPSpace.encode_and_deriv (sspspace.py:278-306) on the device against the oracle's float64 statement."""
+    bounds = np.array([[-4.0, 4.0]] * n)
+    ls = np.linspace(0.6, 1.4, n)
+    sp = (pkg.HexagonalSSPSpace(n, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=1.0) if kind == "hex"
+          else pkg.RandomSSPSpace(n, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=1.0, rng=3))
+    sp.update_lengthscale(ls)
+    for N in (1, 7, 300):
+        x = np.random.default_rng(N).uniform(-4, 4, (N, n))
+        phi, grad = sp.encode_and_deriv(x)
+        rphi, rgrad = orc.encode_and_deriv(sp.phase_matrix, ls, x)
+        assert phi.shape == (N, sp.ssp_dim) and grad.shape == (N, sp.ssp_dim, n)
+        np.testing.assert_allclose(phi, rphi, atol=2e-13)
+        np.testing.assert_allclose(grad, rgrad, atol=2e-12 * max(1.0, np.max(np.abs(rgrad))))
+    with pytest.raises(AssertionError):
+        sp.encode_and_deriv(np.zeros((2, n + 1)))
+
+
+# ------------------------------------------------------------------------------------------ RFF baseline agent
+@pytest.mark.parametrize("kt", ["rbf", "matern"])
+def test_rff_agent_golden(pkg, golden, kt):
+    """agents/rff_agent.py on the GPU (feature map + float64 BLR) against the live-reference fixture: the constructor draws
+    the reference's features (same sklearn fit, same numpy draws), and with the fixture's features adopted exactly, encode /
+    eval / five updates / the x-space objective and gradient agree."""
+    g = golden("rff.npz")
+    xs, ys, xq = g["xs"], g["ys"], g["xq"]
+    np.random.seed(7)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        a0 = pkg.RFFAgent(xs[:12], ys[:12], ssp_dim=96, kernel_type=kt, gamma_c=1.0, beta_ucb=5.0, var_decay=0.25)
+    np.testing.assert_allclose(a0.W, g[f"{kt}_W"], rtol=1e-4, atol=1e-7)       # the GP fit may differ in the last digits across hosts
+    np.testing.assert_allclose(a0.B, g[f"{kt}_B"], rtol=0, atol=0)
+    np.testing.assert_allclose(a0.sqrt_2_alpha_over_m, float(g[f"{kt}_scale"]), rtol=1e-4)
+    agt = pkg.RFFAgent(xs[:12], ys[:12], ssp_dim=96, kernel_type=kt, gamma_c=1.0, beta_ucb=5.0, var_decay=0.25,
+                       features=(g[f"{kt}_W"], g[f"{kt}_B"], float(g[f"{kt}_scale"])))
+    np.testing.assert_allclose(agt.encode(xq), g[f"{kt}_phi"], rtol=0, atol=2e-14)
+    mu, var, acq = agt.eval(xq)
+    assert mu.shape == (1, 40) and var.shape == (40,) and acq.shape == (40,)
+    np.testing.assert_allclose(mu, g[f"{kt}_mu0"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(var, g[f"{kt}_var0"], rtol=1e-8)
+    np.testing.assert_allclose(acq, g[f"{kt}_acq0"], rtol=1e-8)
+    for i in range(12, 17):
+        _, var_t, _ = agt.eval(xs[i:i + 1])
+        agt.update(xs[i:i + 1], ys[i:i + 1], var_t, step_num=i)
+    mu, var, acq = agt.eval(xq)
+    np.testing.assert_allclose(mu, g[f"{kt}_mu1"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, g[f"{kt}_var1"], rtol=1e-7)
+    np.testing.assert_allclose(acq, g[f"{kt}_acq1"], rtol=1e-7)
+    assert rel(agt.blr.m, g[f"{kt}_m"]) < 1e-8 and rel(agt.blr.S, g[f"{kt}_S"]) < 1e-8
+    assert np.isclose(agt.var_weight, float(g[f"{kt}_lam"])) and np.allclose(np.ravel(agt.gamma_t), g[f"{kt}_gamma"], rtol=1e-8)
+    f, grad = agt.acquisition_func()
+    np.testing.assert_allclose(np.array([f(x) for x in xq[:8]]).ravel(), g[f"{kt}_obj"], rtol=1e-7)
+    np.testing.assert_allclose(np.array([grad(x) for x in xq[:8]]), g[f"{kt}_grad"], rtol=1e-6, atol=1e-8)
+
+
+def test_rff_maximize_route(pkg):
+    """maximize(agent_type='rff-rbf'): the reference's x-space L-BFGS-B route (bayesian_optimization.py:252-262) with the
+    agent's features and posterior on the device."""
+    import contextlib, io
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    f = lambda x: float(himmelblau(np.atleast_2d(x))[0])
+    xs0 = np.random.default_rng(2).uniform(-5, 5, (10, 2))
+    ys0 = himmelblau(xs0).reshape(-1, 1)
+    opt = pkg.BayesianOptimization(f=f, bounds=bounds, random_state=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt.maximize(init_points=(xs0, ys0), n_iter=4, num_restarts=3, agent_type="rff-rbf", ssp_dim=64, gamma_c=1.0)
+    assert opt.xs.shape == (14, 2) and opt.ys.shape == (14,)
+    assert np.all(opt.xs[10:] >= -5) and np.all(opt.xs[10:] <= 5)
+    assert isinstance(opt.agt, pkg.RFFAgent) and np.isfinite(opt.max["target"])

@@ -132,6 +132,22 @@ for c, want in [(((0.5, 10), (0.75, 7)), (0.75, 5_000_000_007)), (((1.0, 4_000_0
         assert got[0] != got[0] and got[1] == 8, got          # NaN wins, as in np.argmax
     else:
         assert got == want, (got, want)
+# maximize(init_points=<int>) under torch.distributed: every rank must build its agent from rank 0's initial design (the
+# Sobol samplers are unseeded) -- agent and space construction stubbed out, this is the host logic only
+import numpy as np
+from ssp_bayesopt_b200 import bayesian_optimization as bo
+seen = {}
+class _Agent:
+    def __init__(self, xs, ys, space, **kw): seen["xs"], seen["ys"] = np.array(xs), np.array(ys)
+    def update(self, xs, ys, s, n): seen["perimeter"] = np.array(xs)
+bo.agents.SSPAgent = _Agent
+bo.sspspace.HexagonalSSPSpace = lambda *a, **k: None
+opt = bo.BayesianOptimization(f=lambda x: float(-np.sum(x ** 2)) + r, bounds=np.array([[-2.0, 2.0], [-1.0, 3.0]]))
+opt.initialize_agent(init_points=6, agent_type="ssp-hex", num_perimeter_samples=3)
+mine = torch.from_numpy(np.concatenate([seen["xs"].ravel(), seen["ys"].ravel(), seen["perimeter"].ravel()]))
+both = [torch.empty_like(mine) for _ in range(2)]
+td.all_gather(both, mine)
+assert torch.equal(both[0], both[1]) and seen["xs"].shape == (6, 2) and seen["perimeter"].shape == (3, 2)
 td.destroy_process_group()
 print("ok", r)
 '''

@@ -228,3 +228,29 @@ def test_acquisition_func_and_lbfgs_route_match_reference(golden):
     np.testing.assert_allclose(xs, g["lbfgs_x"], rtol=1e-9, atol=1e-9)
     set_ssps = orc.encode(g["A"], g["ls"], g["init_pts"])
     np.testing.assert_array_equal(orc.decode_from_set(xs, set_ssps, g["init_pts"]), g["lbfgs_decoded"])
+
+
+def test_rff_features_and_blr_golden(golden):
+    """agents/rff_agent.py: the feature map and the BLR over it (MI acquisition, additive var_decay), live-reference fixture."""
+    g = golden("rff.npz")
+    for kt in ("rbf", "matern"):
+        W, B, c = g[f"{kt}_W"], g[f"{kt}_B"], float(g[f"{kt}_scale"])
+        np.testing.assert_allclose(orc.rff_encode(W, B, c, g["xq"]), g[f"{kt}_phi"], rtol=0, atol=1e-15)
+        blr = orc.BLR(W.shape[0])
+        blr.update(orc.rff_encode(W, B, c, g["xs"][:12]), g["ys"][:12])
+        mu, var, acq = orc.agent_eval(orc.rff_encode(W, B, c, g["xq"]), blr, 5.0, 0.0)
+        np.testing.assert_allclose(mu, g[f"{kt}_mu0"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(var, g[f"{kt}_var0"], rtol=1e-9)
+        np.testing.assert_allclose(acq, g[f"{kt}_acq0"], rtol=1e-9)
+        lam, gamma = 5.0, 0.0
+        for i in range(12, 17):
+            phi = orc.rff_encode(W, B, c, g["xs"][i:i + 1])
+            _, var_t, _ = orc.agent_eval(phi, blr, lam, gamma)
+            blr.update(phi, g["ys"][i:i + 1])
+            lam, gamma = orc.agent_update_scalars(lam, gamma, 0.25, 1.0, var_t)
+        assert np.isclose(lam, float(g[f"{kt}_lam"])) and np.allclose(gamma, g[f"{kt}_gamma"], rtol=1e-9)
+        mu, var, acq = orc.agent_eval(orc.rff_encode(W, B, c, g["xq"]), blr, lam, float(np.ravel(gamma)[0]))
+        np.testing.assert_allclose(mu, g[f"{kt}_mu1"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(var, g[f"{kt}_var1"], rtol=1e-8)
+        np.testing.assert_allclose(acq, g[f"{kt}_acq1"], rtol=1e-8)
+        assert np.max(np.abs(blr.m - g[f"{kt}_m"])) <= 1e-9 * np.max(np.abs(g[f"{kt}_m"]))

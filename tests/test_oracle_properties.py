@@ -88,3 +88,20 @@ def test_argmax_conventions():
     score, idx = orc.score_and_argmax(np.vstack([phis, phis]), model, 1.0, 0.0)
     assert idx == 0 and np.allclose(score, score[0])
     assert int(np.argmax(np.array([1.0, np.nan, 5.0]))) == 1
+
+
+def test_encode_and_deriv_is_the_derivative_of_encode():
+    """oracle.encode_and_deriv (sspspace.py:278-306, the derivative its docstring describes) against central differences of
+    `encode`, hexagonal and random spaces, per-axis length scales."""
+    rng = np.random.default_rng(3)
+    for A, n in ((orc.hex_phase_matrix(2, 51), 2), (orc.random_phase_matrix(3, 64, rng=1), 3)):
+        x = rng.uniform(-3, 3, (6, n))
+        ls = rng.uniform(0.5, 2.0, n)
+        phi, grad = orc.encode_and_deriv(A, ls, x)
+        assert grad.shape == (6, A.shape[0], n)
+        np.testing.assert_allclose(phi, orc.encode(A, ls, x), atol=1e-15)
+        h = 1e-6
+        for a in range(n):
+            e = np.zeros(n); e[a] = h
+            fd = (orc.encode(A, ls, x + e) - orc.encode(A, ls, x - e)) / (2 * h)
+            np.testing.assert_allclose(grad[:, :, a], fd, atol=5e-9)
