@@ -67,7 +67,7 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform: role branches and the MMA issuer loop stay on the uniform datapath
     constexpr int NA = NA_F8;
     const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = (uint32_t)(p.n_bufs * p.acc_cols);
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;

@@ -45,7 +45,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform: role branches and the MMA issuer loop stay on the uniform datapath
     const int NA = p.na;
     const uint32_t ACC_COLS = (uint32_t)p.acc_cols, A_RING_COL0 = (uint32_t)(p.n_bufs * p.acc_cols);
     const int b_tile_bytes = p.BN * BK * 2;
@@ -196,11 +196,11 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
                 const int buf = tile_iter & (p.n_bufs - 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
-                mbar_wait(tmem_empty(buf), acc_phase[buf] ^ 1);               // the epilogue has drained this accumulator
+                mbar_wait_inline(tmem_empty(buf), acc_phase[buf] ^ 1);        // the epilogue has drained this accumulator
                 acc_phase[buf] ^= 1;
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
-                    mbar_wait(b_full(rb.slot), rb.phase);
+                    mbar_wait_inline(a_full(ra.slot), ra.phase);
+                    mbar_wait_inline(b_full(rb.slot), rb.phase);
                     tc_fence_after();
                     const uint32_t a_hi = a_ring0 + (uint32_t)(ra.slot * A_SLOT_COLS);
                     const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)rb.slot * b_slot_units);

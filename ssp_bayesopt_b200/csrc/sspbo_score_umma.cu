@@ -79,7 +79,7 @@ k_score_umma(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     // 1024-byte alignment for the 128B swizzle; offset arithmetic (not integer casts) keeps the address space known
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform: role branches and the MMA issuer loop stay on the uniform datapath
     const int b_tile_bytes = p.BN * BK * 2;
     const int b_slot_bytes = 2 * b_tile_bytes;
     const int NA = p.na;

@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 20)) __trap();
 }
+// Wait whose spin loop lives INSIDE the asm block: the compiler sees straight-line code, so a warp-uniform caller keeps its
+// loop state (ring slots, descriptors) in uniform registers and the tcgen05.mma operands need no register -> uniform-register
+// moves on the way (the C++ loops above look divergent to the compiler, and every operand of the MMA issue then travels
+// through an R2UR: ~25 dependent instructions per MMA on the one warp every k-block has to pass).  Unbounded: only for the
+// MMA issuer, whose partners keep the bounded waits and trap on a protocol bug.
+__device__ __forceinline__ void mbar_wait_inline(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra WAIT_DONE;\n\t"
+                 "bra WAIT_LOOP;\n\t"
+                 "WAIT_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
 // same, with a sleep between polls: for roles that wait for a long time (epilogue, TMA producer) and must not take
 // issue slots from the generator warps that share their scheduler
 template <int NS = 100>

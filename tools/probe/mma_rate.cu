@@ -46,11 +46,17 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long* out, int iters) {
         int slot = 0;
         for (int N = 256; N >= 64; N >>= 1) {
             const uint32_t idesc = make_idesc(128, N);
-            for (int kind = 0; kind < 4; ++kind) {
+            for (int kind = 0; kind < 6; ++kind) {
+                if (kind >= 4 && N == 256) { out[slot++] = 0; continue; }      // two / four accumulators need N <= 128 / 64 columns each
+                if (kind == 5 && N == 128) { out[slot++] = 0; continue; }
                 long long t0 = clock64();
                 for (int i = 0; i < iters; ++i) {
                     const uint32_t a = tmem + 256 + 8 * (i & 3);
-                    if (kind == 0) umma_f16_ts(tmem, a, db + 2 * (i & 3), idesc, 1);
+                    // kinds 4, 5: consecutive MMAs accumulate into DIFFERENT accumulators (2 or 4 of them): is the floor of
+                    // ~106 cycles per MMA at N <= 128 the latency of the accumulate chain?
+                    if (kind == 4) umma_f16_ts(tmem + (uint32_t)N * (i & 1), a, db + 2 * (i & 3), idesc, 1);
+                    else if (kind == 5) umma_f16_ts(tmem + (uint32_t)N * (i & 3), a, db + 2 * (i & 3), idesc, 1);
+                    else if (kind == 0) umma_f16_ts(tmem, a, db + 2 * (i & 3), idesc, 1);
                     else if (kind == 1) umma_f8_ts(tmem, a, db + 2 * (i & 3), idesc, 1);
                     else if (kind == 2) umma_f16(tmem, da + 2 * (i & 3), db + 2 * (i & 3), idesc, 1);
                     else umma_f8_ss(tmem, da + 2 * (i & 3), db + 2 * (i & 3), idesc, 1);
@@ -75,9 +81,10 @@ int main() {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 2; }
     long long h[64]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[4] = {"f16 K=16 A:tmem", "e4m3 K=32 A:tmem", "f16 K=16 A:smem", "e4m3 K=32 A:smem"};
+    const char* names[6] = {"f16 K=16 A:tmem", "e4m3 K=32 A:tmem", "f16 K=16 A:smem", "e4m3 K=32 A:smem",
+                            "f16 A:tmem, 2 accumulators in turn", "f16 A:tmem, 4 accumulators in turn"};
     int s = 0;
     for (int N = 256; N >= 64; N >>= 1)
-        for (int k = 0; k < 4; ++k, ++s) printf("N=%3d %-18s %.1f cycles per MMA\n", N, names[k], (double)h[s] / iters);
+        for (int k = 0; k < 6; ++k, ++s) if (h[s]) printf("N=%3d %-36s %.1f cycles per MMA\n", N, names[k], (double)h[s] / iters);
     return 0;
 }
