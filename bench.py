@@ -604,7 +604,8 @@ def rank_sweep(pkg, sp_unused, cand, orc, X, y, world, td, n=1 << 22, reps=3,
                     "flagged_fraction": st["flagged"] / max(st["scored"], 1),
                     "scorer_ms_per_launch": kt["scorer_ms"] / max(kt["calls"], 1),
                     "flagged_pass_ms_per_launch": kt["flagged_ms"] / max(kt["calls"], 1),
-                    "executed_tflops": tf, "frac_of_tensor_peak": (tf / peaks["tflops"]) if tf else None, "executed_what": what})
+                    "executed_tflops": tf, "frac_of_tensor_peak": (tf / peaks["tflops_burst"]) if tf else None,
+                    "tensor_peak": "burst bf16 (kernel timed alone)", "executed_what": what})
     return out
 
 

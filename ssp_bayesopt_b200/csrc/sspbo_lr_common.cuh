@@ -224,16 +224,27 @@ __device__ __forceinline__ void gen_half(const Params& p, const uint8_t* tables,
         for (int i = 0; i < NF; ++i) { cs[i] = 0.25f * (float)(i + kb); sn[i] = 0.125f * (float)kb; }
     } else if constexpr (PH == 2) {
         const float* Afblk = (const float*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF], radians per unit
-        float t[NF];
+        // two frequencies per FFMA2: the chain costs NDIM / 2 issue slots per frequency instead of NDIM
+        const f32x2* A2 = (const f32x2*)Afblk;
+        f32x2 t2[NF / 2];
+        {
+            const f32x2 xx = f2_pack(__int_as_float(xq0[0]), __int_as_float(xq0[0]));
 #pragma unroll
-        for (int i = 0; i < NF; ++i) t[i] = Afblk[i] * __int_as_float(xq0[0]);
-#pragma unroll
-        for (int a = 1; a < NDIM; ++a) {
-#pragma unroll
-            for (int i = 0; i < NF; ++i) t[i] = fmaf(Afblk[a * NF + i], __int_as_float(xq0[a]), t[i]);
+            for (int i = 0; i < NF / 2; ++i) t2[i] = f2_mul(A2[i], xx);
         }
 #pragma unroll
-        for (int i = 0; i < NF; ++i) __sincosf(t[i], &sn[i], &cs[i]);       // one RZ multiply by 1/2pi, then MUFU.SIN / MUFU.COS (the MUFU reduces the range itself)
+        for (int a = 1; a < NDIM; ++a) {
+            const f32x2 xx = f2_pack(__int_as_float(xq0[a]), __int_as_float(xq0[a]));
+#pragma unroll
+            for (int i = 0; i < NF / 2; ++i) t2[i] = f2_fma(A2[a * (NF / 2) + i], xx, t2[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NF / 2; ++i) {
+            float t0, t1;
+            f2_unpack(t2[i], t0, t1);
+            __sincosf(t0, &sn[2 * i], &cs[2 * i]);                          // one RZ multiply by 1/2pi, then MUFU.SIN / MUFU.COS (the MUFU reduces the range itself)
+            __sincosf(t1, &sn[2 * i + 1], &cs[2 * i + 1]);
+        }
     } else if constexpr (PH == 1) {
         const int* A32blk = (const int*)tables + (size_t)(kb * 32 + half * NF) * NDIM;   // [axis][NF]
         long long t[NF];                                      // phase in turns at bit 55

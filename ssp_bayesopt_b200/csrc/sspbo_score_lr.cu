@@ -385,8 +385,8 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
                 for (int i = 0; i < NF / 2; ++i) {
-                    split_pair_trunc(cs[2 * i], cs[2 * i + 1], wch[i], wcl[i]);
-                    split_pair_trunc(sn[2 * i], sn[2 * i + 1], wsh[i], wsl[i]);
+                    split_pair_trunc2(cs[2 * i], cs[2 * i + 1], wch[i], wcl[i]);
+                    split_pair_trunc2(sn[2 * i], sn[2 * i + 1], wsh[i], wsl[i]);
                 }
                 if (!slot_free) { mbar_wait(empty_bar, phase ^ 1); slot_free = true; }
                 tc_fence_after();

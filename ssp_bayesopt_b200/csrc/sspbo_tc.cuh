@@ -102,6 +102,15 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- packed float32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 do two float32 operations per issue slot; the generators are
+// bound by issue slots, not by the FP32 lanes) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 struct Ring {                            // ring position; every role walks the same sequence
     int slot = 0; uint32_t phase = 0;
     __device__ __forceinline__ void advance(int n) { if (++slot == n) { slot = 0; phase ^= 1; } }
@@ -122,6 +131,18 @@ __device__ __forceinline__ void split_pair_trunc(float a, float b, uint32_t& hi,
     const float hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
     __half2 h = __floats2half2_rn(ha, hb);
     __half2 l = __floats2half2_rn(a - ha, b - hb);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// split_pair_trunc with the subtraction done on the pair (one FADD2 instead of two FADD)
+__device__ __forceinline__ void split_pair_trunc2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const float ha = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+    const float hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+    __half2 h = __floats2half2_rn(ha, hb);
+    float la, lb;
+    f2_unpack(f2_sub(f2_pack(a, b), f2_pack(ha, hb)), la, lb);
+    __half2 l = __floats2half2_rn(la, lb);
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
