@@ -367,10 +367,10 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 if constexpr (!TRAJ) {
                 const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0, row_nan);
                 if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
-                const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it towards the SM now
-                if (member == 0 && gn < N && p.cand.mode == 0) {
+                const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it into L1 now (with few k-blocks
+                if (gn < N && p.cand.mode == 0) {                         // per tile every warp loads a row per k-block or two)
                     const char* nx = (const char*)p.cand.x + (size_t)gn * NDIM * (p.cand.x_f64 ? 8 : 4);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
                 }
                 }
             }
@@ -553,20 +553,28 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
     Params p;
     sspbo_lr_fill_common(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, ph, &p);
     p.BN = bn; p.nb = nb;
-    // TMEM: accumulators first, the A ring behind them (4 slots, 6 when the accumulators take 128 columns only)
-    // BN <= 128: merged operand, the accumulator is 2 BN wide
-    p.merged = bn <= 128;
+    // TMEM: accumulators first, the A ring behind them.  BN <= 128: three BN-wide MMAs per K step (hi hi, hi lo, lo hi) into
+    // ONE BN-wide accumulator, two of which alternate by tile, so the epilogue of a tile overlaps the MMAs of the next one
+    // and reads BN columns.  (Round 1 merged the hi|lo tiles into one 2 BN-row operand to issue two MMAs per K step instead
+    // of three: the issue cost ~100 cycles per MMA then.  With the issuer's loop on the uniform datapath the issue is cheap,
+    // the tensor-pipe time of the two layouts is the same, and the merged one pays a 2 BN-wide accumulator and an epilogue
+    // that adds the halves: measured after the change, d = 1023 ranks 10..127: +1..3 % unmerged; d = 151 rank 70: 0.107 ->
+    // 0.100 ms per 1e6 candidates.  SSPBO_LR_MERGED=1 brings the merged layout back for comparison.)
+    // BN > 128: one 256-column accumulator, the waits of the next k-block between the two halves of the MMAs.
+    p.merged = 0;
     p.split_issue = bn > 128;
-    if (bn <= 64) { p.acc_cols = 128; p.n_bufs = 2; }
+    if (bn <= 64) { p.acc_cols = 64; p.n_bufs = 2; }
+    else if (bn <= 128) { p.acc_cols = 128; p.n_bufs = 2; }
     else { p.acc_cols = 256; p.n_bufs = 1; }
-    // Few k-blocks per tile (d <= 383): the drain of the single 2 BN-wide accumulator between tiles costs more than the
-    // third MMA per K step, so accumulate hi|lo products into ONE BN-wide accumulator and alternate two of them by tile
-    // (measured at d = 151, rank 70: 0.148 -> 0.125 ms per 1e6 candidates; at d = 1023 the two layouts are within 2 %)
-    if (bn > 64 && bn <= 128 && p.n_kb <= 6) { p.merged = 0; p.acc_cols = 128; p.n_bufs = 2; }
-    // BN = 80: two merged accumulators (2 x 160 columns) still leave three A slots in the 512 columns of tensor memory, so the
-    // epilogue of a tile overlaps the MMAs of the next one (d = 1023, rank 70-79: 2.17 -> 2.09 ms per 4.19M candidates;
-    // d = 151: 0.125 -> 0.120 ms per 1e6)
-    if (bn > 64 && 4 * bn + 3 * A_SLOT_COLS <= (int)TMEM_COLS) { p.merged = 1; p.acc_cols = 2 * bn; p.n_bufs = 2; }
+    {
+        static const int merged_env = getenv("SSPBO_LR_MERGED") ? atoi(getenv("SSPBO_LR_MERGED")) : -1;
+        if (merged_env == 1 && bn <= 128) {
+            p.merged = 1;
+            if (bn <= 64) { p.acc_cols = 128; p.n_bufs = 2; }
+            else if (4 * bn + 3 * A_SLOT_COLS <= (int)TMEM_COLS) { p.acc_cols = 2 * bn; p.n_bufs = 2; }
+            else { p.acc_cols = 256; p.n_bufs = 1; }
+        }
+    }
     p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
     if (p.na > NA_MAX) p.na = NA_MAX;
     if (p.na < GEN_W)                                     // every generator warp of a quadrant owns a slot of the rotation

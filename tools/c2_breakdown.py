@@ -49,3 +49,14 @@ torch.cuda.synchronize(); ev[0].record()
 for i in range(10): agt.update(xs[i:i+1], np.atleast_2d(branin(xs[i:i+1])), np.array([0.0]))
 ev[1].record(); torch.cuda.synchronize()
 print("update GPU ms per call", ev[0].elapsed_time(ev[1]) / 10)
+# kernel-level split of the scoring call (library events) and of the generated-grid route
+eng.set_timing(True)
+for _ in range(10): agt.best_candidate(cand['x'], index0=0, reset_best=True)
+print("timing (10 calls, resident grid):", eng.timing_read())
+axes = [np.linspace(bounds[i, 0], bounds[i, 1], 1000) for i in range(2)]
+for _ in range(3): eng.score_generated("grid", 1000000, 10.0, 0.0, axes=axes)
+eng.timing_read()
+torch.cuda.synchronize(); ev[0].record()
+for _ in range(10): eng.score_generated("grid", 1000000, 10.0, 0.0, axes=axes)
+ev[1].record(); torch.cuda.synchronize()
+print("generated-grid score GPU ms per call", ev[0].elapsed_time(ev[1]) / 10, "timing:", eng.timing_read())
