@@ -44,15 +44,26 @@ __device__ __forceinline__ uint32_t e4m3x2_of_half2(uint32_t h2) {
     return (uint32_t)r;
 }
 
-// Operand words of one pair of values (a, b): fp16 hi pair, e4m3 pair of the values, e4m3 pair of the scaled remainders
+// float32 pair -> e4m3 pair (first operand -> low byte), one rounding
+__device__ __forceinline__ uint32_t e4m3x2_of_floats(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return (uint32_t)r;
+}
+
+// Operand words of one pair of values (a, b): fp16 hi pair, e4m3 pair of the values, e4m3 pair of the scaled remainders.
+// Seven issue slots per pair: two LOP3, FADD2, F2FP, FMUL2 and the two float32 -> e4m3x2 conversions (the remainders used to
+// travel through half2: one conversion and one HMUL2 more, and a second rounding).
 __device__ __forceinline__ void split_pair_f8(float a, float b, uint32_t& hi, uint32_t& v8, uint32_t& l8) {
     const float ha = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
     const float hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
     __half2 h = __floats2half2_rn(ha, hb);
-    __half2 l = __hmul2(__floats2half2_rn(a - ha, b - hb), __float2half2_rn((float)(1 << F8_SHIFT)));
     hi = *reinterpret_cast<uint32_t*>(&h);
-    v8 = e4m3x2_of_half2(hi);
-    l8 = e4m3x2_of_half2(*reinterpret_cast<uint32_t*>(&l));
+    float la, lb;
+    const float sc = (float)(1 << F8_SHIFT);
+    f2_unpack(f2_mul(f2_sub(f2_pack(a, b), f2_pack(ha, hb)), f2_pack(sc, sc)), la, lb);
+    v8 = e4m3x2_of_floats(a, b);
+    l8 = e4m3x2_of_floats(la, lb);
 }
 
 // PAIR: two CTAs of a cluster (one TPC) share every MMA through cta_group::2: a tile is 256 candidates, 128 per CTA (each its
@@ -296,17 +307,21 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     for (int l = 0; l < 4; ++l)
                         if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
                     tmem_ld_wait();
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                    // sum of squares on packed pairs (FFMA2): the drain of a 256-column accumulator holds up the next tile's MMAs,
+                    // and these warps share their schedulers with the generators
+                    f32x2 q01 = 0ull, q23 = 0ull;
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
                         if (l < nld) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
-                                float y0 = __uint_as_float(v[16 * l + i]), y1 = __uint_as_float(v[16 * l + i + 1]);
-                                float y2 = __uint_as_float(v[16 * l + i + 2]), y3 = __uint_as_float(v[16 * l + i + 3]);
-                                q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1); q2 = fmaf(y2, y2, q2); q3 = fmaf(y3, y3, q3);
+                                const f32x2 y01 = f2_pack(__uint_as_float(v[16 * l + i]), __uint_as_float(v[16 * l + i + 1]));
+                                const f32x2 y23 = f2_pack(__uint_as_float(v[16 * l + i + 2]), __uint_as_float(v[16 * l + i + 3]));
+                                q01 = f2_fma(y01, y01, q01); q23 = f2_fma(y23, y23, q23);
                             }
                         }
+                    float q0, q1, q2, q3;
+                    f2_unpack(q01, q0, q1); f2_unpack(q23, q2, q3);
                     q += (q0 + q1) + (q2 + q3);
                 }
                 tc_fence_before();
@@ -406,11 +421,16 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 gen_half<NDIM, PH, TRAJ>(p, tables, g0, kb, half, x0, xq0, cs, sn, nrm_blk);
                 if (!TRAJ && row_nan) cs[0] = __int_as_float(0x7fc00000);      // poisons mu and |V psi|^2 of the row through the MMA
                 if (c == 0) {                                             // mu = m' . psi in float32 (m' in operand order: cos | sin per k-block)
-                    const float* mc = mp_s + kb * BK + half * NF;
-                    float m0 = 0.f, m1 = 0.f;
+                    const f32x2* mc2 = (const f32x2*)(mp_s + kb * BK + half * NF);      // two frequencies per FFMA2
+                    f32x2 m0 = 0ull, m1 = 0ull;
 #pragma unroll
-                    for (int i = 0; i < NF; ++i) { m0 = fmaf(cs[i], mc[i], m0); m1 = fmaf(sn[i], mc[32 + i], m1); }
-                    mu_acc += m0 + m1;
+                    for (int i = 0; i < NF / 2; ++i) {
+                        m0 = f2_fma(f2_pack(cs[2 * i], cs[2 * i + 1]), mc2[i], m0);
+                        m1 = f2_fma(f2_pack(sn[2 * i], sn[2 * i + 1]), mc2[16 + i], m1);
+                    }
+                    float a0, a1, b0, b1;
+                    f2_unpack(m0, a0, a1); f2_unpack(m1, b0, b1);
+                    mu_acc += (a0 + a1) + (b0 + b1);
                 }
                 // fp16 hi pairs (8 columns each) and e4m3 quadruples (4 columns each): values, then scaled remainders
                 uint32_t wch[NF / 2], wsh[NF / 2], wc8[NF / 4], ws8[NF / 4], wcl[NF / 4], wsl[NF / 4];

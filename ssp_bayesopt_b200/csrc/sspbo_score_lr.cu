@@ -284,17 +284,21 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                         if (l < nld) tmem_ld16(taddr + (uint32_t)(g + 16 * l), v + 16 * l);
                     tmem_ld_wait();
                     if (c == 0 && g == 0) { mu_raw = __uint_as_float(v[0]); v[0] = 0u; }   // output row 0 is m' . psi, not a row of V
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                    // sum of squares on packed pairs (FFMA2): the drain of a 256-column accumulator holds up the next tile's MMAs,
+                    // and these warps share their schedulers with the generators
+                    f32x2 q01 = 0ull, q23 = 0ull;
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
                         if (l < nld) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
-                                float y0 = __uint_as_float(v[16 * l + i]), y1 = __uint_as_float(v[16 * l + i + 1]);
-                                float y2 = __uint_as_float(v[16 * l + i + 2]), y3 = __uint_as_float(v[16 * l + i + 3]);
-                                q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1); q2 = fmaf(y2, y2, q2); q3 = fmaf(y3, y3, q3);
+                                const f32x2 y01 = f2_pack(__uint_as_float(v[16 * l + i]), __uint_as_float(v[16 * l + i + 1]));
+                                const f32x2 y23 = f2_pack(__uint_as_float(v[16 * l + i + 2]), __uint_as_float(v[16 * l + i + 3]));
+                                q01 = f2_fma(y01, y01, q01); q23 = f2_fma(y23, y23, q23);
                             }
                         }
+                    float q0, q1, q2, q3;
+                    f2_unpack(q01, q0, q1); f2_unpack(q23, q2, q3);
                     q += (q0 + q1) + (q2 + q3);
                 }
                 tc_fence_before();
