@@ -543,7 +543,7 @@ def side_configs():
     out = {}
     with contextlib.redirect_stdout(sys.stderr):
         from tools import configs_bench as cb
-        for name, fn, kw in (("c5", cb.c5, {}), ("multi_agent", cb.multi, {}), ("c4", cb.c4, {"runs": 256, "steps": 3})):
+        for name, fn, kw in (("c5", cb.c5, {}), ("multi_agent", cb.multi, {}), ("c4", cb.c4, {"runs": 4096, "steps": 3})):
             try:
                 out[name] = fn(**kw)
             except Exception as e:                               # a side line must not take the headline down

@@ -256,11 +256,16 @@ int sspbo_bind(sspbo_ctx* ctx, const double* a_dev, int qa, const double* b_dev,
 int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_dev, void* stream);
 
 /* ---- lock-step of many independent runs (BASELINE config C4: 4096 runs, one context each) ---------------------
- * sspbo_score_batch: for r < R: sspbo_score(ctxs[r], x_dev, ..., lam[r], gamma_t[r], key = keys_dev + r, AUTO engine) on
- * streams[r % n_streams]; all runs share the candidate set x_dev (N rows) and must share its row width n*L.  keys_dev (R
- * packed keys) must be zeroed by the caller.  sspbo_update_batch: for r < R: sspbo_blr_update_x(ctxs[r], row r of x_host
- * (R x n*L float64), ts_host[r]).  Both only enqueue work.  On error the first failing code is returned and *failed
- * (nullable) is the run index. */
+ * sspbo_score_batch: for r < R: sspbo_score(ctxs[r], x_dev, ..., lam[r], gamma_t[r], key = keys_dev + r, AUTO engine); all
+ * runs share the candidate set x_dev (N rows) and must share its row width n*L.  keys_dev (R packed keys) must be zeroed by
+ * the caller.  sspbo_update_batch: for r < R: sspbo_blr_update_x(ctxs[r], row r of x_host (R x n*L float64), ts_host[r]).
+ * Both only enqueue work.  The caller orders every stream of `streams` after the work that precedes the call and waits for
+ * all of them afterwards.  Runs that share a layout (plain SSP spaces of one dimension n <= 4 and table size, the same
+ * posterior rank <= 127 as in a lock-step, the float32 phase path) are served by GROUPED kernels on streams[0]: one launch of
+ * the fused scorer over (run, tile), one of the float64 pass over (run, flagged group), one for the status words; and one
+ * launch for all updates (a thread-block cluster per run encodes the run's point, applies the float64 rank-one update and
+ * refreshes the run's scoring operands).  Otherwise the per-run calls go to streams[r % n_streams].  On error the first
+ * failing code is returned and *failed (nullable) is the run index. */
 int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
                       const double* gamma_t, unsigned long long* keys_dev, void* const* streams, int n_streams, int* failed);
 /* After sspbo_score_batch, on the same streams: status_dev[r] = bit 0 (the flag list of run r's tensor pass overflowed) |

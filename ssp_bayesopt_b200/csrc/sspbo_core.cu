@@ -528,13 +528,31 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
 // FULL: the same pass with the float64 psi-space covariance itself, var = 1/beta + psi^T Sp psi (d rows of length d instead
 // of the r rows of V): for posteriors whose low-rank rows are not available (rank > SSPBO_LR_MAX, imported state), flagged by
 // the factor form of the fp16 + e4m3 scorer.  `Vd` then points at Sp and `r` is d.
+// Everything one float64 pass needs (one context): k_exact_lowrank takes it by value, k_exact_lowrank_runs reads one per run
+struct ExactArgs {
+    const void* x; sspbo_lr::CandDesc cand; const unsigned int* list; const unsigned long long* count_ptr; unsigned int cap;
+    const double *A_turns, *tau_turns; int n, K, L; double dc_value; int normalize;
+    const int *inv_perm, *perm; const double* Vd; int r; const double* mp;
+    double inv_beta, prior_var, lam, gamma_t; int64_t index0;
+    float *mu_out, *var_out, *acq_out; unsigned long long* best;
+};
+
+// groups cta, cta + ncta, ... of the flag list
 template <typename XT, bool FULL>
-__global__ void __launch_bounds__(EXL_THREADS)
-k_exact_lowrank(const XT* __restrict__ x, const sspbo_lr::CandDesc cand, const unsigned int* __restrict__ list, const unsigned long long* __restrict__ count_ptr,
-                unsigned int cap, const double* __restrict__ A_turns, const double* __restrict__ tau_turns, int n, int K, int L,
-                double dc_value, int normalize, const int* __restrict__ inv_perm, const int* __restrict__ perm, const double* __restrict__ Vd, int r, const double* __restrict__ mp,
-                double inv_beta, double prior_var, double lam, double gamma_t, int64_t index0, float* __restrict__ mu_out,
-                float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
+__device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta, int ncta) {
+    const XT* __restrict__ x = (const XT*)ea.x;
+    const sspbo_lr::CandDesc& cand = ea.cand;
+    const unsigned int* __restrict__ list = ea.list;
+    const unsigned int cap = ea.cap;
+    const double* __restrict__ A_turns = ea.A_turns; const double* __restrict__ tau_turns = ea.tau_turns;
+    const int n = ea.n, K = ea.K, L = ea.L, normalize = ea.normalize, r = ea.r;
+    const double dc_value = ea.dc_value, inv_beta = ea.inv_beta, prior_var = ea.prior_var, lam = ea.lam, gamma_t = ea.gamma_t;
+    const int* __restrict__ inv_perm = ea.inv_perm; const int* __restrict__ perm = ea.perm;
+    const double* __restrict__ Vd = ea.Vd; const double* __restrict__ mp = ea.mp;
+    const int64_t index0 = ea.index0;
+    float* __restrict__ mu_out = ea.mu_out; float* __restrict__ var_out = ea.var_out; float* __restrict__ acq_out = ea.acq_out;
+    unsigned long long* __restrict__ best = ea.best;
+    const unsigned long long* __restrict__ count_ptr = ea.count_ptr;
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
     __shared__ double red[EX_G + 1][EXL_THREADS / 32];
     __shared__ double xs_gen[EX_G][sspbo_lr::MAX_N];   // rows of a generated candidate set (cand.mode != 0, L == 1)
@@ -544,7 +562,7 @@ k_exact_lowrank(const XT* __restrict__ x, const sspbo_lr::CandDesc cand, const u
     const int64_t count = (int64_t)c0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long my_best = 0ull;
-    for (int64_t base = (int64_t)blockIdx.x * EX_G; base < count; base += (int64_t)gridDim.x * EX_G) {
+    for (int64_t base = (int64_t)cta * EX_G; base < count; base += (int64_t)ncta * EX_G) {
         __syncthreads();
         if (cand.mode != 0) {
             if (threadIdx.x < EX_G && base + threadIdx.x < count)
@@ -632,6 +650,31 @@ k_exact_lowrank(const XT* __restrict__ x, const sspbo_lr::CandDesc cand, const u
         }
     }
     if (lane == 0 && my_best && best) atomicMax(best, my_best);
+}
+
+template <typename XT, bool FULL>
+__global__ void __launch_bounds__(EXL_THREADS) k_exact_lowrank(const ExactArgs ea) {
+    exact_lowrank_body<XT, FULL>(ea, blockIdx.x, gridDim.x);
+}
+
+// Lock-step of many independent runs (BASELINE config C4): the float64 pass of EVERY run in one launch -- CTA b walks the
+// flag lists of runs b, b + gridDim.x, ... (a run flags a handful of candidates: its own observations) -- followed, per run,
+// by the counter fold of k_flag_fold and the status word of k_batch_status.
+// work items (run, part): the groups of a run's flag list are dealt to `parts` CTAs, so a few hundred runs still fill the machine
+template <typename XT>
+__global__ void __launch_bounds__(EXL_THREADS) k_exact_lowrank_runs(const ExactArgs* __restrict__ runs, int R, int parts) {
+    for (int item = blockIdx.x; item < R * parts; item += gridDim.x) {
+        __syncthreads();
+        exact_lowrank_body<XT, false>(runs[item / parts], item % parts, parts);
+    }
+}
+// ... and then, one thread per run, the status word of k_batch_status and the counters cleared for the next lock-step
+__global__ void k_batch_status_runs(const ExactArgs* __restrict__ runs, int R, unsigned long long* __restrict__ status) {
+    const int run = blockIdx.x * blockDim.x + threadIdx.x;
+    if (run >= R) return;
+    unsigned long long* st = const_cast<unsigned long long*>(runs[run].count_ptr) - SSPBO_STAT_CUR;
+    status[run] = ((st[SSPBO_STAT_OVERFLOW] || st[SSPBO_STAT_CUR] > runs[run].cap) ? 1ull : 0ull) | (st[SSPBO_STAT_OOR] ? 2ull : 0ull);
+    for (int i = 0; i < SSPBO_STAT_COUNT; ++i) st[i] = 0ull;
 }
 // folds the per-call flag counter into the totals (after the exact pass has consumed it)
 __global__ void k_flag_fold(unsigned long long* __restrict__ stats, unsigned int cap, unsigned long long scored) {
@@ -1015,6 +1058,8 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 static void free_blr(sspbo_ctx* ctx) {
     sspbo_f8_release(ctx);
     timing_release(ctx);
+    if (ctx->batch_pin) { cudaFreeHost(ctx->batch_pin); cudaFree(ctx->batch_dev); cudaEventDestroy(ctx->batch_event); ctx->batch_pin = nullptr; ctx->batch_dev = nullptr; }
+    if (ctx->sbatch_pin) { cudaFreeHost(ctx->sbatch_pin); cudaFree(ctx->sbatch_dev); cudaEventDestroy(ctx->sbatch_event); ctx->sbatch_pin = nullptr; ctx->sbatch_dev = nullptr; }
     dev_free(&ctx->S); dev_free(&ctx->Sinv); dev_free(&ctx->b); dev_free(&ctx->m);
     dev_free(&ctx->R); dev_free(&ctx->Sp); dev_free(&ctx->perm); dev_free(&ctx->inv_perm); dev_free(&ctx->col_of_rank);
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
@@ -1032,7 +1077,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
-    dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
+    dev_free(&ctx->A32_op); dev_free(&ctx->Af_op); dev_free(&ctx->Af_gen); dev_free(&ctx->Bh_enc); dev_free(&ctx->Bl_enc); dev_free(&ctx->flag_idx); dev_free(&ctx->stats); dev_free(&ctx->ex_part);
     dev_free(&ctx->aa_work);
     if (ctx->gen_rows) cudaFree(ctx->gen_rows);
     if (ctx->eval_dev) cudaFree(ctx->eval_dev);
@@ -1164,6 +1209,15 @@ static int build_p32_tables(sspbo_ctx* ctx) {
             int rc;
             if ((rc = dev_alloc(ctx, &ctx->Af_op, op.size()))) return rc;
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->Af_op, op.data(), op.size() * sizeof(float), cudaMemcpyHostToDevice));
+            // the same table in the layout the generators read (axis-major inside every block of 16 frequencies): the grouped
+            // scorer of many runs reads it from global memory instead of staging one table per launch in shared memory
+            std::vector<float> gen(op.size(), 0.f);
+            const int NFq = 16;
+            for (int f = 0; f < kc / 2; ++f)
+                for (int a = 0; a < ctx->n; ++a)
+                    gen[((size_t)(f / NFq) * ctx->n + a) * NFq + (f % NFq)] = op[(size_t)f * ctx->n + a];
+            if ((rc = dev_alloc(ctx, &ctx->Af_gen, gen.size()))) return rc;
+            SSPBO_CUDA(ctx, cudaMemcpy(ctx->Af_gen, gen.data(), gen.size() * sizeof(float), cudaMemcpyHostToDevice));
             ctx->pf32_ok = true;
         }
     }
@@ -1722,6 +1776,16 @@ extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, d
 // ------------------------------------------------------------------------------------ K2 dispatch
 // float64 pass over the candidates a tensor pass flagged (device-side list and count): the low-rank form over the rows of V
 // while they are valid, else the quadratic form with the psi-space covariance
+static void fill_exact_args(const sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t index0, double lam, double gamma_t,
+                            float* mu, float* var, float* acq, unsigned long long* best, bool full, ExactArgs* ea) {
+    ea->x = cand.x; ea->cand = cand; ea->list = ctx->flag_idx; ea->count_ptr = ctx->stats + SSPBO_STAT_CUR; ea->cap = SSPBO_FLAG_CAP;
+    ea->A_turns = ctx->A_turns; ea->tau_turns = ctx->tau_turns; ea->n = ctx->n; ea->K = ctx->K; ea->L = ctx->L;
+    ea->dc_value = ctx->dc; ea->normalize = ctx->normalize ? 1 : 0; ea->inv_perm = ctx->inv_perm; ea->perm = ctx->perm;
+    ea->Vd = full ? ctx->Sp : ctx->Vd; ea->r = full ? ctx->d : ctx->lr_rank; ea->mp = ctx->mp;
+    ea->inv_beta = 1.0 / ctx->beta; ea->prior_var = 1.0 / ctx->alpha; ea->lam = lam; ea->gamma_t = gamma_t; ea->index0 = index0;
+    ea->mu_out = mu; ea->var_out = var; ea->acq_out = acq; ea->best = best;
+}
+
 static int score_flagged_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t N, int64_t index0, double lam, double gamma_t,
                                 float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
     const int d = ctx->d;
@@ -1730,12 +1794,12 @@ static int score_flagged_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, 
     const bool full = !ctx->lr_valid;
     const double* rows = full ? ctx->Sp : ctx->Vd;
     const int r = full ? d : ctx->lr_rank;
+    ExactArgs ea;
+    fill_exact_args(ctx, cand, index0, lam, gamma_t, mu, var, acq, best, full, &ea);
 #define SSPBO_FLAGGED_LAUNCH(XT, FULL)                                                                                             \
     do {                                                                                                                           \
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_lowrank<XT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_exact_lowrank<XT, FULL><<<gx, EXL_THREADS, smem, st>>>((const XT*)cand.x, cand, ctx->flag_idx, ctx->stats + SSPBO_STAT_CUR, \
-            SSPBO_FLAG_CAP, ctx->A_turns, ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, ctx->inv_perm,   \
-            ctx->perm, rows, r, ctx->mp, 1.0 / ctx->beta, 1.0 / ctx->alpha, lam, gamma_t, index0, mu, var, acq, best);             \
+        k_exact_lowrank<XT, FULL><<<gx, EXL_THREADS, smem, st>>>(ea);                                                              \
     } while (0)
     if (cand.x_f64) { if (full) SSPBO_FLAGGED_LAUNCH(double, true); else SSPBO_FLAGGED_LAUNCH(double, false); }
     else { if (full) SSPBO_FLAGGED_LAUNCH(float, true); else SSPBO_FLAGGED_LAUNCH(float, false); }
@@ -2102,11 +2166,74 @@ extern "C" int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, dou
 /* Lock-step of many independent runs (BASELINE config C4): the per-run calls of a selection / an observation issued from
  * one C loop over the runs' contexts, round-robin over the caller's streams.  Returns the first non-zero return code;
  * *failed (nullable) receives the index of that run (its message is in sspbo_last_error of its context). */
+// parameter blocks of the grouped launches: RunScore[R] | ExactArgs[R] | status[R], pinned staging + device copy owned by the
+// first context of the batch
+static int score_batch_grouped(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
+                               const double* gamma_t, unsigned long long* keys_dev, cudaStream_t st, int* failed) {
+    sspbo_ctx* c0 = ctxs[0];
+    if (!c0) return SSPBO_EINVAL;
+    const size_t off_ex = (size_t)R * sizeof(sspbo_lr::RunScore);
+    const size_t off_st = off_ex + (size_t)R * sizeof(ExactArgs);
+    const size_t bytes = off_st + (size_t)R * sizeof(unsigned long long);
+    SSPBO_CUDA(c0, cudaSetDevice(c0->device));
+    if (c0->sbatch_pin) SSPBO_CUDA(c0, cudaEventSynchronize(c0->sbatch_event));
+    if (bytes > c0->sbatch_bytes) {
+        if (c0->sbatch_pin) { SSPBO_CUDA(c0, cudaStreamSynchronize(st)); cudaFreeHost(c0->sbatch_pin); cudaFree(c0->sbatch_dev); c0->sbatch_pin = nullptr; c0->sbatch_dev = nullptr; }
+        else SSPBO_CUDA(c0, cudaEventCreateWithFlags(&c0->sbatch_event, cudaEventDisableTiming));
+        c0->sbatch_bytes = 0;
+        SSPBO_CUDA(c0, cudaMallocHost(&c0->sbatch_pin, bytes));
+        SSPBO_CUDA(c0, cudaMalloc(&c0->sbatch_dev, bytes));
+        c0->sbatch_bytes = bytes;
+    }
+    sspbo_lr::RunScore* hs = (sspbo_lr::RunScore*)c0->sbatch_pin;
+    ExactArgs* he = (ExactArgs*)((char*)c0->sbatch_pin + off_ex);
+    int rc = sspbo_score_lr_runs_prepare(ctxs, R, N, lam, gamma_t, keys_dev, hs);
+    if (rc) return rc;                                                  // EUNSUPPORTED: nothing enqueued
+    sspbo_lr::CandDesc cand;
+    memset(&cand, 0, sizeof(cand));
+    cand.x = x_dev; cand.x_f64 = (x_dtype == SSPBO_F64);
+    for (int r = 0; r < R; ++r)
+        fill_exact_args(ctxs[r], cand, 0, lam[r], gamma_t[r], nullptr, nullptr, nullptr, keys_dev + r, false, he + r);
+    SSPBO_CUDA(c0, cudaMemcpyAsync(c0->sbatch_dev, c0->sbatch_pin, off_st, cudaMemcpyHostToDevice, st));
+    SSPBO_CUDA(c0, cudaEventRecord(c0->sbatch_event, st));
+    rc = sspbo_score_lr_runs_launch(ctxs, R, cand, N, (const sspbo_lr::RunScore*)c0->sbatch_dev, st);
+    if (rc) { if (failed) *failed = 0; return rc; }
+    int d_max = 0;
+    for (int r = 0; r < R; ++r) d_max = ctxs[r]->d > d_max ? ctxs[r]->d : d_max;
+    const size_t smem = (size_t)EX_G * d_max * sizeof(double);
+    int parts = (4 * c0->sm_count) / R;
+    parts = parts < 1 ? 1 : (parts > 16 ? 16 : parts);
+    const int items = R * parts;
+    const int gx = items < 4 * c0->sm_count ? items : 4 * c0->sm_count;
+    const ExactArgs* de = (const ExactArgs*)((const char*)c0->sbatch_dev + off_ex);
+    unsigned long long* dst = (unsigned long long*)((char*)c0->sbatch_dev + off_st);
+    if (cand.x_f64) {
+        SSPBO_CUDA(c0, cudaFuncSetAttribute(k_exact_lowrank_runs<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_exact_lowrank_runs<double><<<gx, EXL_THREADS, smem, st>>>(de, R, parts);
+    } else {
+        SSPBO_CUDA(c0, cudaFuncSetAttribute(k_exact_lowrank_runs<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_exact_lowrank_runs<float><<<gx, EXL_THREADS, smem, st>>>(de, R, parts);
+    }
+    SSPBO_LAUNCH_CHECK(c0);
+    k_batch_status_runs<<<(R + 255) / 256, 256, 0, st>>>(de, R, dst);
+    SSPBO_LAUNCH_CHECK(c0);
+    c0->batch_status_valid = R;
+    return SSPBO_OK;
+}
+
 extern "C" int sspbo_score_batch(sspbo_ctx* const* ctxs, int R, const void* x_dev, int x_dtype, int64_t N, const double* lam,
                                  const double* gamma_t, unsigned long long* keys_dev, void* const* streams, int n_streams,
                                  int* failed) {
     if (failed) *failed = -1;
     if (!ctxs || R < 0 || !lam || !gamma_t || !keys_dev || !streams || n_streams < 1) return SSPBO_EINVAL;
+    if (R >= 1 && ctxs[0]) ctxs[0]->batch_status_valid = 0;
+    if (R >= 2 && x_dev && (x_dtype == SSPBO_F32 || x_dtype == SSPBO_F64)) {
+        // Runs that share a layout (lock-step: same rank): ONE launch of the grouped scorer and ONE of the grouped float64 pass,
+        // which also leaves every run's status word (read by sspbo_score_batch_status); both on streams[0], which the caller
+        // has ordered after the work before the lock-step.
+        const int rc = score_batch_grouped(ctxs, R, x_dev, x_dtype, N, lam, gamma_t, keys_dev, (cudaStream_t)streams[0], failed);
+        if (rc != SSPBO_EUNSUPPORTED) return rc;
+    }
     for (int r = 0; r < R; ++r) {
         const int rc = sspbo_score(ctxs[r], x_dev, x_dtype, N, 0, lam[r], gamma_t[r], nullptr, nullptr, nullptr, keys_dev + r,
                                    SSPBO_ENGINE_AUTO, streams[r % n_streams]);
@@ -2126,6 +2253,14 @@ extern "C" int sspbo_score_batch_status(sspbo_ctx* const* ctxs, int R, unsigned 
                                         int n_streams, int* failed) {
     if (failed) *failed = -1;
     if (!ctxs || R < 0 || !status_dev || !streams || n_streams < 1) return SSPBO_EINVAL;
+    if (R >= 1 && ctxs[0] && ctxs[0]->batch_status_valid == R) {          // the grouped float64 pass already produced the status words
+        sspbo_ctx* c0 = ctxs[0];
+        const size_t off_st = (size_t)R * (sizeof(sspbo_lr::RunScore) + sizeof(ExactArgs));
+        if (cudaMemcpyAsync(status_dev, (const char*)c0->sbatch_dev + off_st, (size_t)R * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)streams[0]) != cudaSuccess) { if (failed) *failed = 0; return SSPBO_ECUDA; }
+        c0->batch_status_valid = 0;
+        return SSPBO_OK;
+    }
     for (int r = 0; r < R; ++r) {
         sspbo_ctx* ctx = ctxs[r];
         cudaStream_t st = (cudaStream_t)streams[r % n_streams];
@@ -2141,6 +2276,12 @@ extern "C" int sspbo_update_batch(sspbo_ctx* const* ctxs, int R, const double* x
                                   int n_streams, int* failed) {
     if (failed) *failed = -1;
     if (!ctxs || R < 0 || !x_host || !ts_host || !streams || n_streams < 1) return SSPBO_EINVAL;
+    if (R >= 2) {
+        // plain SSP-space runs: every run's encode + update + operand refresh in ONE launch (a cluster per run); the caller has
+        // ordered all `streams` after the work that precedes the lock-step, the launch goes to streams[0]
+        const int rc = sspbo_blr_update_runs(ctxs, R, x_host, ts_host, (cudaStream_t)streams[0], failed);
+        if (rc != SSPBO_EUNSUPPORTED) return rc;
+    }
     for (int r = 0; r < R; ++r) {
         const size_t nl = (size_t)ctxs[r]->n * ctxs[r]->L;
         const int rc = sspbo_blr_update_x(ctxs[r], x_host + (size_t)r * nl, ts_host + r, 1, streams[r % n_streams]);

@@ -81,6 +81,7 @@ struct sspbo_ctx {
     // 32-bit fixed-point phase tables (fast generator of the tcgen05 scorer), valid when p32_ok
     int* A32_op = nullptr;           // (KC_pad/2) x n, Q(31-fa).fa turns per unit
     bool p32_ok = false;
+    float* Af_gen = nullptr;         // Af_op in the generators' layout ([block of 16 frequencies][axis][16]), for the grouped scorer
     float* Af_op = nullptr;          // (KC_pad/2) x n float32, radians per unit (float32 phase path)
     bool pf32_disabled = false;      // policy override: never use the float32 chain
     bool pf32_ok = false;            // declared bounds keep |theta| <= 16 pi: float32 FMA chain is accurate to < 1e-5 rad
@@ -119,6 +120,11 @@ struct sspbo_ctx {
     // current; (Fh, F8) = images of [m'; L^T] for the factor form
     uint8_t* V8 = nullptr; int v8_rank = 0; bool v8_row0_dirty = true;
     __half* Fh = nullptr; uint8_t* F8 = nullptr; bool f8_factor_dirty = true;
+    // parameter block + points of sspbo_update_batch's single launch (owned by the first context of the batch)
+    void* batch_pin = nullptr; void* batch_dev = nullptr; size_t batch_bytes = 0; cudaEvent_t batch_event = nullptr;
+    // ... and of sspbo_score_batch's two grouped launches (RunScore[R] | ExactArgs[R] | status[R])
+    void* sbatch_pin = nullptr; void* sbatch_dev = nullptr; size_t sbatch_bytes = 0; cudaEvent_t sbatch_event = nullptr;
+    int batch_status_valid = 0;      // runs whose status words the grouped float64 pass left in sbatch_dev
     double* exact_out64 = nullptr;   // set by sspbo_eval_host around its exact-engine launch: 3 x 64 float64 outputs
     double lr_flag_frac = 0.0;       // flagged / scored of the last read-back of a low-rank pass (cost model of ENGINE_AUTO)
     int operand_format = -1;         // policy: -1 = by rank, 0 = split fp16 only (rank <= 255), 1 / 2 = fp16 + e4m3 whenever usable (single CTAs / CTA pairs)
@@ -220,6 +226,7 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
 void sspbo_umma_release(sspbo_ctx* ctx);
 int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st);
 // one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
+int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed);
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
                            double* vd_row, double* obs_out, cudaStream_t st);
 // low-rank engines with the A operand in tensor memory: prototypes in sspbo_lr_common.cuh (they take a candidate descriptor)

@@ -66,6 +66,17 @@ struct Params {
     int debug;
 };
 
+// Grouped scoring of many independent runs in one launch (BASELINE config C4: thousands of runs, one posterior each, a shared
+// candidate set): what differs from run to run.  CTA b scores ALL tiles of runs b, b + gridDim.x, ...; the operand images
+// come through the run's own tensor maps (in global memory), the frequency table is read from global memory.
+struct alignas(64) RunScore {
+    CUtensorMap map_hi, map_lo;
+    const float* tab;                   // generator frequency table of the run's space (ctx->Af_gen)
+    const float* mscale;
+    float inv_beta, lam, gamma_t, inv_rscale2, prior_var, flag_below;
+    unsigned long long* best; unsigned int* flag_idx; unsigned long long* stats;
+};
+
 // splitmix64 finaliser of the counter-based candidate stream (sspbo_core.cu:k_fill_uniform, oracle counter_uniform)
 __host__ __device__ __forceinline__ float counter_uniform_f32(unsigned long long seed, unsigned long long elem) {
     unsigned long long z = elem + (seed << 40) + 0x9E3779B97F4A7C15ull;
@@ -318,5 +329,9 @@ int sspbo_lr_phase_path(const sspbo_ctx* ctx);
 // split-fp16 operands, one chunk (rank <= 255); fp16 + e4m3 operands, form 0 = low rank (rank <= 511), 1 = triangular factor
 int sspbo_score_lr_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
                           float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st);
+int sspbo_score_lr_runs_prepare(sspbo_ctx* const* ctxs, int R, int64_t N, const double* lam, const double* gamma_t,
+                                unsigned long long* keys_dev, sspbo_lr::RunScore* runs_host);
+int sspbo_score_lr_runs_launch(sspbo_ctx* const* ctxs, int R, const sspbo_lr::CandDesc& cand, int64_t N, const sspbo_lr::RunScore* runs_dev,
+                               cudaStream_t st);
 int sspbo_score_f8_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
                           float* mu, float* var, float* acq, unsigned long long* best, int form, cudaStream_t st);

@@ -39,9 +39,13 @@ using namespace sspbo_lr;
 // 2 = float32 FMA chain in radians (|theta| <= 32 pi by the declared bounds: rounding < 2e-5 rad)
 // TRAJ: a candidate is a row of L waypoints; psi sums L unit phasors per frequency (agents/ssp_traj_agent.py:145-163 in
 // the Fourier domain) and |phi|^2 = psi^T D psi is no longer 1: the generators accumulate it for the epilogue.
-template <int NDIM, int PH, bool TRAJ>
+// GROUPED: one launch scores the shared candidate set for `n_runs` independent runs (RunScore, one per run): CTA b takes all
+// tiles of runs b, b + gridDim.x, ...; the pipeline state (rings, barrier phases, accumulators) simply runs on from one run
+// into the next.  The per-run launches of config C4 cost ~5 us of host time each, several times what the kernel needs.
+template <int NDIM, int PH, bool TRAJ, bool GROUPED = false>
 __global__ void __launch_bounds__(THREADS, 1)
-k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
+k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p,
+           const RunScore* __restrict__ runs, const int n_runs) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -67,7 +71,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NA + 2 * p.nb + 4);
 
     // ---- one-time setup ----
-    load_tables<NDIM, PH>(p, tables, THREADS);
+    if constexpr (!GROUPED) load_tables<NDIM, PH>(p, tables, THREADS);
     if constexpr (TRAJ) {
         for (int i = threadIdx.x; i < NRM_DEPTH * GEN_W * BM; i += THREADS) nrm_part[i] = 0.f;
     }
@@ -88,6 +92,12 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 
     const long long n_tiles = (p.N + BM - 1) / BM;
     const int n_kb = p.n_kb, n_chunks = p.n_chunks;
+    // this CTA's tile sequence: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the one candidate set, or every tile of its runs
+    const long long my_units = GROUPED ? ((n_runs > (int)blockIdx.x) ? (n_runs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0)
+                                       : ((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    const long long my_tiles_all = GROUPED ? my_units * n_tiles : my_units;
+    auto run_of = [&](long long tile_iter) { return GROUPED ? (int)(blockIdx.x + (tile_iter / n_tiles) * gridDim.x) : 0; };
+    auto tile_of = [&](long long tile_iter) { return GROUPED ? tile_iter % n_tiles : (long long)blockIdx.x + tile_iter * gridDim.x; };
     // accumulator of chunk c: with a single chunk per tile the two buffers alternate by tile instead
     auto acc_of = [&](int tile_iter, int c) { return n_chunks == 1 ? (tile_iter & (p.n_bufs - 1)) : c; };
 
@@ -95,15 +105,18 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         // ================================ TMA producer (B ring) ================================
         if (lane == 0) {
             Ring rb;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (long long ti = 0; ti < my_tiles_all; ++ti) {
+                const CUtensorMap* mh = GROUPED ? &runs[run_of(ti)].map_hi : &map_hi;
+                const CUtensorMap* ml = GROUPED ? &runs[run_of(ti)].map_lo : &map_lo;
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait_relaxed<64>(b_empty(rb.slot), rb.phase ^ 1);
                     uint8_t* st = b_ring + (size_t)rb.slot * b_slot_bytes;
                     mbar_expect_tx(b_full(rb.slot), (uint32_t)b_slot_bytes);
-                    tma_load_2d(smem_u32(st), &map_hi, b_full(rb.slot), kb * BK, 0);
-                    tma_load_2d(smem_u32(st + b_tile_bytes), &map_lo, b_full(rb.slot), kb * BK, 0);
+                    tma_load_2d(smem_u32(st), mh, b_full(rb.slot), kb * BK, 0);
+                    tma_load_2d(smem_u32(st + b_tile_bytes), ml, b_full(rb.slot), kb * BK, 0);
                     rb.advance(p.nb);
                 }
+            }
         }
     } else if (warp == WARP_MMA) {
         // ================================ MMA issuer ================================
@@ -122,8 +135,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             // Software pipeline: the waits for k-block i + 1 sit BETWEEN the two halves of the MMAs of k-block i, so the
             // tensor pipe always has queued work while this warp polls barriers (its instruction queue is only a few
             // MMAs deep: issuing a whole k-block and then waiting would let it run dry).
-            const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-            const long long total_blocks = my_tiles * n_kb;
+            const long long total_blocks = my_tiles_all * n_kb;
             if (total_blocks > 0) {
                 mbar_wait_relaxed<40>(a_full(ra.slot), ra.phase);
                 mbar_wait(b_full(rb.slot), rb.phase);
@@ -192,8 +204,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             }
         } else {
             // short MMAs (BN <= 128): one elected section per k-block keeps the loop at a minimum of instructions
-            int tile_iter = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            for (int tile_iter = 0; tile_iter < (int)my_tiles_all; ++tile_iter) {
                 const int buf = tile_iter & (p.n_bufs - 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
                 mbar_wait_inline(tmem_empty(buf), acc_phase[buf] ^ 1);        // the epilogue has drained this accumulator
@@ -247,10 +258,34 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         const int quad = warp & 3;                                        // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;
         uint32_t acc_phase[2] = {0, 0};
-        int tile_iter = 0;
         unsigned long long my_best = 0ull;
-        const float inv_mscale = __ldg(p.mscale);
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+        float inv_mscale = GROUPED ? 0.f : __ldg(p.mscale);
+        // what the epilogue takes from the run (GROUPED) or from the launch parameters
+        float e_inv_beta = p.inv_beta, e_lam = p.lam, e_gamma = p.gamma_t, e_inv_rs2 = p.inv_rscale2, e_prior = p.prior_var,
+              e_flag_below = p.flag_below;
+        unsigned long long* e_best = p.best; unsigned int* e_flag_idx = p.flag_idx; unsigned long long* e_stats = p.stats;
+        int cur_run = -1;
+        for (int tile_iter = 0; tile_iter < (int)my_tiles_all; ++tile_iter) {
+            const long long tile = tile_of(tile_iter);
+            if constexpr (GROUPED) {
+                const int run = run_of(tile_iter);
+                if (run != cur_run) {                                       // first tile of a run: publish the last run's key, load this run's scalars
+                    if (cur_run >= 0) {
+                        for (int o = 16; o > 0; o >>= 1) {
+                            unsigned long long other = __shfl_xor_sync(0xffffffffu, my_best, o);
+                            if (other > my_best) my_best = other;
+                        }
+                        if (lane == 0 && my_best && e_best) atomicMax(e_best, my_best);
+                        my_best = 0ull;
+                    }
+                    cur_run = run;
+                    const RunScore& rs = runs[run];
+                    inv_mscale = __ldg(rs.mscale);
+                    e_inv_beta = rs.inv_beta; e_lam = rs.lam; e_gamma = rs.gamma_t; e_inv_rs2 = rs.inv_rscale2;
+                    e_prior = rs.prior_var; e_flag_below = rs.flag_below;
+                    e_best = rs.best; e_flag_idx = rs.flag_idx; e_stats = rs.stats;
+                }
+            }
             float q = 0.f, mu_raw = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
                 const int buf = acc_of(tile_iter, c);
@@ -307,7 +342,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             const long long gi = tile * BM + row;
             if (gi < p.N) {
                 float mu = mu_raw * inv_mscale;
-                float prior = p.prior_var, flag_below = p.flag_below;
+                float prior = e_prior, flag_below = e_flag_below;
                 if constexpr (TRAJ) {                                                 // |phi|^2 / alpha instead of 1 / alpha
                     float* np_ = nrm_part + (size_t)(tile_iter & (NRM_DEPTH - 1)) * GEN_W * BM + row;
                     float ssum = 0.f;
@@ -317,16 +352,16 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     if (p.normalize) { const float inv = 1.f / nrm2; mu *= sqrtf(inv); q *= inv; }   // phi / |phi|
                     else { prior *= nrm2; flag_below *= nrm2; }
                 }
-                const float rem = prior - q * p.inv_rscale2;                          // |phi|^2 / alpha - |V psi|^2
-                const float var = p.inv_beta + rem;                                   // blr.py:96
+                const float rem = prior - q * e_inv_rs2;                              // |phi|^2 / alpha - |V psi|^2
+                const float var = e_inv_beta + rem;                                   // blr.py:96
                 bool flagged = false;
                 if (var < flag_below) {                                             // too close to the observations for
-                    const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
-                    if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
-                    else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
+                    const unsigned long long slot = atomicAdd(e_stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
+                    if (slot < (unsigned long long)p.flag_cap) { e_flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                    else atomicAdd(e_stats + SSPBO_STAT_OVERFLOW, 1ull);
                 }
                 if (!flagged) {
-                    const float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t)); // ssp_agent.py:136, cancellation-free
+                    const float acq = e_lam * var / (sqrtf(var + e_gamma) + sqrtf(e_gamma));     // ssp_agent.py:136, cancellation-free
                     const float score = mu + acq;
                     if (p.mu) p.mu[gi] = mu;
                     if (p.var) p.var[gi] = var;
@@ -340,7 +375,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             unsigned long long other = __shfl_xor_sync(0xffffffffu, my_best, o);
             if (other > my_best) my_best = other;
         }
-        if (lane == 0 && my_best && p.best) atomicMax(p.best, my_best);
+        if (lane == 0 && my_best && e_best) atomicMax(e_best, my_best);
     } else {
         // ================================ psi generators (A ring in tensor memory) ================================
         // GEN_W warps per TMEM lane quadrant (thread <-> candidate row).  Warp j of a quadrant produces the k-blocks
@@ -352,8 +387,9 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
         const int r0 = quad * 32 + lane;                                  // candidate row of this thread = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + A_RING_COL0;
         const long long N = p.N;
-        const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const long long total_blocks = my_tiles * n_kb;
+        const long long total_blocks = my_tiles_all * n_kb;
+        const uint8_t* gen_tab = tables;                                  // GROUPED: the run's table in global memory
+        unsigned long long* oor_stats = p.stats;
         int slot = member % NA;
         uint32_t phase = (uint32_t)((member / NA) & 1);
         int kb = member % n_kb;
@@ -367,11 +403,12 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
             if (tile_iter != loaded_iter) {                               // first k-block of a tile for this warp: its row
                 loaded_iter = tile_iter;
                 nrm_acc = 0.f;
-                g0 = (blockIdx.x + tile_iter * gridDim.x) * BM + r0;
+                g0 = tile_of(tile_iter) * BM + r0;
+                if constexpr (GROUPED) { const RunScore& rs = runs[run_of(tile_iter)]; gen_tab = (const uint8_t*)rs.tab; oor_stats = rs.stats; }
                 if constexpr (!TRAJ) {
                 const bool oor = load_candidate<NDIM, PH>(p, g0, x0, xq0, row_nan);
-                if (oor && member == 0) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
-                const long long gn = g0 + (long long)gridDim.x * BM;     // next tile's row: pull it into L1 now (with few k-blocks
+                if (oor && member == 0) atomicAdd(oor_stats + SSPBO_STAT_OOR, 1ull);  // outside the declared |x| bound
+                const long long gn = GROUPED ? tile_of(tile_iter + 1) * BM + r0 : g0 + (long long)gridDim.x * BM;   // next tile's row: pull it into L1 now (with few k-blocks
                 if (gn < N && p.cand.mode == 0) {                         // per tile every warp loads a row per k-block or two)
                     const char* nx = (const char*)p.cand.x + (size_t)gn * NDIM * (p.cand.x_f64 ? 8 : 4);
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
@@ -384,7 +421,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float cs[NF], sn[NF];
-                gen_half<NDIM, PH, TRAJ>(p, tables, g0, kb, half, x0, xq0, cs, sn, nrm_acc);
+                gen_half<NDIM, PH, TRAJ>(p, gen_tab, g0, kb, half, x0, xq0, cs, sn, nrm_acc);
                 if (!TRAJ && row_nan) cs[0] = __int_as_float(0x7fc00000);      // poisons mu and |V psi|^2 of the row through the MMA
                 uint32_t wch[NF / 2], wcl[NF / 2], wsh[NF / 2], wsl[NF / 2];     // cos hi / cos lo / sin hi / sin lo, fp16 pairs
 #pragma unroll
@@ -432,6 +469,7 @@ struct LrState {
     int KC_pad = 0, BN = 0;
     int max_smem = 0;
     bool attr_set[2][3][MAX_N + 1] = {};
+    bool runs_attr_set[MAX_N + 1] = {};
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
@@ -439,7 +477,7 @@ size_t table_bytes(const sspbo_ctx* ctx) {
            (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
 
-typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params);
+typedef void (*kernel_fn)(const CUtensorMap, const CUtensorMap, const Params, const RunScore*, const int);
 template <int PH>
 kernel_fn kernel_for_n(int n) {
     switch (n) {
@@ -467,6 +505,14 @@ kernel_fn kernel_for_traj(int n) {
 kernel_fn kernel_for(int n, int ph, bool traj) {
     if (traj) return ph == 2 ? kernel_for_traj<2>(n) : kernel_for_traj<0>(n);
     return ph == 2 ? kernel_for_n<2>(n) : (ph == 1 ? kernel_for_n<1>(n) : kernel_for_n<0>(n));
+}
+// grouped scoring of many runs: float32 phase chain, up to 4 domain dimensions
+kernel_fn kernel_for_runs(int n) {
+    switch (n) {
+        case 1: return k_score_lr<1, 2, false, true>; case 2: return k_score_lr<2, 2, false, true>;
+        case 3: return k_score_lr<3, 2, false, true>; case 4: return k_score_lr<4, 2, false, true>;
+    }
+    return nullptr;
 }
 
 }  // namespace
@@ -522,17 +568,11 @@ void sspbo_lr_fill_common(const sspbo_ctx* ctx, const CandDesc& cand, int64_t N,
     p.debug = sspbo_debug_env();
 }
 
-int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
-                          float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+// tensor maps of the context's operand images for chunks of bn rows (rebuilt when the images or bn changed)
+static int lr_ensure_maps(sspbo_ctx* ctx, int bn, LrState** out) {
     LrState* ls = (LrState*)ctx->lr_state;
     if (!ls) { ls = new LrState(); ctx->lr_state = ls; }
     if (!ls->max_smem) cudaDeviceGetAttribute(&ls->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    const int r = ctx->lr_rank + 1;                      // + row 0 (m')
-    // One chunk of BN = ceil16(r) <= 256 rows (a tcgen05.mma costs ~100 cycles or more whatever N is, so the fewest,
-    // widest instructions win): two accumulator buffers alternating by tile while BN <= 128, a single 256-column one
-    // beyond (measured at r = 250: 4.95 ms per 4.19M candidates against 5.26 ms for two interleaved 128-row chunks).
-    const int nc = 1;
-    const int bn = ((r + nc - 1) / nc + 15) / 16 * 16;
     if (ls->bh != ctx->Vh || ls->bl != ctx->Vl || ls->KC_pad != ctx->KC_pad || ls->BN != bn) {
         int rc;
         if ((rc = sspbo_make_map_f16(ctx, &ls->hi, ctx->Vh, ctx->KC_pad, SSPBO_LR_MAX + 1, bn)) ||
@@ -540,11 +580,54 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
             return rc;
         ls->bh = ctx->Vh; ls->bl = ctx->Vl; ls->KC_pad = ctx->KC_pad; ls->BN = bn;
     }
+    *out = ls;
+    return SSPBO_OK;
+}
+
+// layout of one launch for chunks of bn operand rows: B ring depth, shared memory, accumulators and A ring in tensor memory
+static int lr_configure(sspbo_ctx* ctx, const LrState* ls, int bn, Params* p, size_t* smem_out) {
     const size_t tb = table_bytes(ctx), sb = 2 * (size_t)bn * BK * 2;
     int nb = (int)(((size_t)ls->max_smem - 1024 - tb) / sb);
     if (nb > MAX_NB) nb = MAX_NB;
     if (nb < 2) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: shared memory does not fit two B slots");
-    const size_t smem = 1024 + (size_t)nb * sb + tb;
+    *smem_out = 1024 + (size_t)nb * sb + tb;
+    p->BN = bn; p->nb = nb;
+    // TMEM: accumulators first, the A ring behind them.  BN <= 128: three BN-wide MMAs per K step (hi hi, hi lo, lo hi) into
+    // ONE BN-wide accumulator, two of which alternate by tile, so the epilogue of a tile overlaps the MMAs of the next one
+    // and reads BN columns.  (Round 1 merged the hi|lo tiles into one 2 BN-row operand to issue two MMAs per K step instead
+    // of three: the issue cost ~100 cycles per MMA then.  With the issuer's loop on the uniform datapath the issue is cheap,
+    // the tensor-pipe time of the two layouts is the same, and the merged one pays a 2 BN-wide accumulator and an epilogue
+    // that adds the halves: measured after the change, d = 1023 ranks 10..127: +1..3 % unmerged; d = 151 rank 70: 0.107 ->
+    // 0.100 ms per 1e6 candidates.  SSPBO_LR_MERGED=1 brings the merged layout back for comparison.)
+    // BN > 128: one 256-column accumulator, the waits of the next k-block between the two halves of the MMAs.
+    p->merged = 0;
+    p->split_issue = bn > 128;
+    if (bn <= 64) { p->acc_cols = 64; p->n_bufs = 2; }
+    else if (bn <= 128) { p->acc_cols = 128; p->n_bufs = 2; }
+    else { p->acc_cols = 256; p->n_bufs = 1; }
+    {
+        static const int merged_env = getenv("SSPBO_LR_MERGED") ? atoi(getenv("SSPBO_LR_MERGED")) : -1;
+        if (merged_env == 1 && bn <= 128) {
+            p->merged = 1;
+            if (bn <= 64) { p->acc_cols = 128; p->n_bufs = 2; }
+            else if (4 * bn + 3 * A_SLOT_COLS <= (int)TMEM_COLS) { p->acc_cols = 2 * bn; p->n_bufs = 2; }
+            else { p->acc_cols = 256; p->n_bufs = 1; }
+        }
+    }
+    p->na = (int)((TMEM_COLS - p->n_bufs * p->acc_cols) / A_SLOT_COLS);
+    if (p->na > NA_MAX) p->na = NA_MAX;
+    if (p->na < GEN_W)                                    // every generator warp of a quadrant owns a slot of the rotation
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: %d A slots for %d generator warps per quadrant", p->na, GEN_W);
+    return SSPBO_OK;
+}
+
+int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64_t index0, float lam, float gamma_t,
+                          float* mu, float* var, float* acq, unsigned long long* best, cudaStream_t st) {
+    // One chunk of BN = ceil16(rank + 1) <= 256 rows (row 0 of the operand is m')
+    const int bn = (ctx->lr_rank + 1 + 15) / 16 * 16;
+    LrState* ls;
+    int rc = lr_ensure_maps(ctx, bn, &ls);
+    if (rc) return rc;
     const int ph = sspbo_lr_phase_path(ctx);
     const bool traj = ctx->L != 1;
     if (traj && cand.mode != 0) SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: generated candidates need L == 1");
@@ -556,36 +639,66 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
     }
     Params p;
     sspbo_lr_fill_common(ctx, cand, N, index0, lam, gamma_t, mu, var, acq, best, ph, &p);
-    p.BN = bn; p.nb = nb;
-    // TMEM: accumulators first, the A ring behind them.  BN <= 128: three BN-wide MMAs per K step (hi hi, hi lo, lo hi) into
-    // ONE BN-wide accumulator, two of which alternate by tile, so the epilogue of a tile overlaps the MMAs of the next one
-    // and reads BN columns.  (Round 1 merged the hi|lo tiles into one 2 BN-row operand to issue two MMAs per K step instead
-    // of three: the issue cost ~100 cycles per MMA then.  With the issuer's loop on the uniform datapath the issue is cheap,
-    // the tensor-pipe time of the two layouts is the same, and the merged one pays a 2 BN-wide accumulator and an epilogue
-    // that adds the halves: measured after the change, d = 1023 ranks 10..127: +1..3 % unmerged; d = 151 rank 70: 0.107 ->
-    // 0.100 ms per 1e6 candidates.  SSPBO_LR_MERGED=1 brings the merged layout back for comparison.)
-    // BN > 128: one 256-column accumulator, the waits of the next k-block between the two halves of the MMAs.
-    p.merged = 0;
-    p.split_issue = bn > 128;
-    if (bn <= 64) { p.acc_cols = 64; p.n_bufs = 2; }
-    else if (bn <= 128) { p.acc_cols = 128; p.n_bufs = 2; }
-    else { p.acc_cols = 256; p.n_bufs = 1; }
-    {
-        static const int merged_env = getenv("SSPBO_LR_MERGED") ? atoi(getenv("SSPBO_LR_MERGED")) : -1;
-        if (merged_env == 1 && bn <= 128) {
-            p.merged = 1;
-            if (bn <= 64) { p.acc_cols = 128; p.n_bufs = 2; }
-            else if (4 * bn + 3 * A_SLOT_COLS <= (int)TMEM_COLS) { p.acc_cols = 2 * bn; p.n_bufs = 2; }
-            else { p.acc_cols = 256; p.n_bufs = 1; }
-        }
-    }
-    p.na = (int)((TMEM_COLS - p.n_bufs * p.acc_cols) / A_SLOT_COLS);
-    if (p.na > NA_MAX) p.na = NA_MAX;
-    if (p.na < GEN_W)                                     // every generator warp of a quadrant owns a slot of the rotation
-        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "low-rank tcgen05 engine: %d A slots for %d generator warps per quadrant", p.na, GEN_W);
+    size_t smem;
+    if ((rc = lr_configure(ctx, ls, bn, &p, &smem))) return rc;
     const long long tiles = (N + BM - 1) / BM;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p);
+    kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p, nullptr, 0);
     SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
+
+// Grouped scoring of R independent runs over one explicit candidate set: fills runs_host[r] (the caller uploads the array to
+// runs_dev and has it resident when the launch executes) and enqueues ONE launch.  SSPBO_EUNSUPPORTED, with nothing enqueued,
+// when the runs do not share a layout (same rank, table size and |x| bound; split-fp16 operands, i.e. rank <= 127; float32
+// phase chain; n <= 4; plain spaces).
+int sspbo_score_lr_runs_prepare(sspbo_ctx* const* ctxs, int R, int64_t N, const double* lam, const double* gamma_t,
+                                unsigned long long* keys_dev, RunScore* runs_host) {
+    sspbo_ctx* c0 = ctxs[0];
+    const int bn = (c0->lr_rank + 1 + 15) / 16 * 16;
+    if (bn > 128 || N < 1024) return SSPBO_EUNSUPPORTED;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        if (!c || !sspbo_score_lr_supported(c) || c->lr_disabled || c->operand_format >= 1 || c->L != 1 || c->normalize ||
+            sspbo_lr_phase_path(c) != 2 || !c->Af_gen || c->n != c0->n || c->n > 4 || c->KC_pad != c0->KC_pad ||
+            c->lr_rank != c0->lr_rank || c->x_absmax != c0->x_absmax || c->device != c0->device || !c->has_beta || !c->blr_ready)
+            return SSPBO_EUNSUPPORTED;
+    }
+    if (!kernel_for_runs(c0->n)) return SSPBO_EUNSUPPORTED;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        LrState* ls;
+        int rc = lr_ensure_maps(c, bn, &ls);
+        if (rc) return rc;
+        RunScore& rs = runs_host[r];
+        rs.map_hi = ls->hi; rs.map_lo = ls->lo;
+        rs.tab = c->Af_gen; rs.mscale = c->mscale;
+        rs.inv_beta = (float)(1.0 / c->beta); rs.lam = (float)lam[r]; rs.gamma_t = (float)gamma_t[r];
+        rs.inv_rscale2 = (float)(1.0 / (c->r_scale * c->r_scale));
+        rs.prior_var = (float)(1.0 / c->alpha); rs.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / c->alpha);
+        rs.best = keys_dev + r; rs.flag_idx = c->flag_idx; rs.stats = c->stats;
+    }
+    return SSPBO_OK;
+}
+
+int sspbo_score_lr_runs_launch(sspbo_ctx* const* ctxs, int R, const CandDesc& cand, int64_t N, const RunScore* runs_dev, cudaStream_t st) {
+    sspbo_ctx* c0 = ctxs[0];
+    const int bn = (c0->lr_rank + 1 + 15) / 16 * 16;
+    LrState* ls;
+    int rc = lr_ensure_maps(c0, bn, &ls);
+    if (rc) return rc;
+    kernel_fn kern = kernel_for_runs(c0->n);
+    if (!ls->runs_attr_set[c0->n]) {
+        SSPBO_CUDA(c0, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ls->max_smem));
+        ls->runs_attr_set[c0->n] = true;
+    }
+    Params p;
+    sspbo_lr_fill_common(c0, cand, N, 0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, 2, &p);
+    size_t smem;
+    if ((rc = lr_configure(c0, ls, bn, &p, &smem))) return rc;
+    const int grid = R < c0->sm_count ? R : c0->sm_count;
+    kern<<<grid, THREADS, smem, st>>>(ls->hi, ls->lo, p, runs_dev, R);
+    SSPBO_LAUNCH_CHECK(c0);
+    for (int r = 0; r < R; ++r) ctxs[r]->last_engine = SSPBO_ENGINE_UMMA_LR;
     return SSPBO_OK;
 }

@@ -77,11 +77,27 @@ __device__ __forceinline__ void up_analysis(const double* in, int d, int K, cons
     }
 }
 
-__global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const UpdateParams p) {
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) double sm[];
+// The CTAs that share one update: the whole cooperative grid (one observation per launch), or one thread-block cluster per
+// run of a batch of independent runs (k_blr_update_runs: BASELINE config C4)
+struct GridTeam {
+    cg::grid_group g = cg::this_grid();
+    __device__ __forceinline__ int rank() const { return blockIdx.x; }
+    __device__ __forceinline__ int size() const { return gridDim.x; }
+    __device__ __forceinline__ void sync() { g.sync(); }
+};
+struct ClusterTeam {
+    cg::cluster_group c = cg::this_cluster();
+    __device__ __forceinline__ int rank() const { return (int)c.block_rank(); }
+    __device__ __forceinline__ int size() const { return (int)c.num_blocks(); }
+    __device__ __forceinline__ void sync() { __threadfence(); c.sync(); }     // global-memory scratch (v, psi, y, m) crosses CTAs
+};
+
+// psi_from_x: psi (rank order, global) was already written by the caller from the point itself, so P0 skips the analysis DFT
+template <typename Team>
+__device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& team, double* sm, bool psi_given) {
     const int d = p.d, K = p.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gw = blockIdx.x * UP_WARPS + warp, nw = gridDim.x * UP_WARPS;
+    const int cta = team.rank(), ncta = team.size();
+    const int gw = cta * UP_WARPS + warp, nw = ncta * UP_WARPS;
     double* phi = sm;                 // d
     double* vec = phi + d;            // d : psi, later v
     double* yv = vec + d;             // d : y
@@ -90,12 +106,12 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
     double* tot = red + UP_WARPS * 4; // 4
 
     for (int j = tid; j < d; j += UP_THREADS) {
-        const double f = p.phi[j];
+        const double f = __ldcg(p.phi + j);                             // (written by the other CTAs of the cluster in the batched kernel)
         phi[j] = f;
         bp[j] = fma(p.beta * p.t, f, p.b[j]);                           // blr.py:70: b += beta t phi (read before any CTA writes b)
     }
     __syncthreads();
-    if (p.obs_out && blockIdx.x == 0) {                                  // predictive mean at phi under the old posterior
+    if (p.obs_out && cta == 0) {                                         // predictive mean at phi under the old posterior
         double mu[1] = {0.0};
         for (int j = tid; j < d; j += UP_THREADS) mu[0] = fma(p.m[j], phi[j], mu[0]);
         up_block_reduce<1>(mu, red, tot);
@@ -104,7 +120,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
     }
 
     // ---- P0: psi (rank order) and v = S phi ----
-    if (p.has_factor)
+    if (p.has_factor && !psi_given)
         up_analysis(phi, d, K, p.twiddle, gw, nw, lane, [&](int k, double c, double s) {
             if (k == 0) __stcg(p.psi + p.inv_perm[0], c);
             else { __stcg(p.psi + p.inv_perm[k], c); __stcg(p.psi + p.inv_perm[K + k], -s); }
@@ -112,11 +128,12 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
     for (int i = gw; i < d; i += nw) {
         const double* row = p.S + (size_t)i * d;
         double acc = 0.0;
-        for (int j = lane; j < d; j += 32) acc = fma(row[j], phi[j], acc);
+#pragma unroll 4
+        for (int j = lane; j < d; j += 32) acc = fma(row[j], phi[j], acc);       // (several 256-byte requests per warp in flight)
         acc = up_warp_sum(acc);
         if (lane == 0) __stcg(p.v + i, acc);
     }
-    grid.sync();
+    team.sync();
 
     // ---- P1: y = Sp psi ----
     if (p.has_factor) {
@@ -125,11 +142,12 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         for (int i = gw; i < d; i += nw) {
             const double* row = p.Sp + (size_t)i * d;
             double acc = 0.0;
+#pragma unroll 4
             for (int j = lane; j < d; j += 32) acc = fma(row[j], vec[j], acc);
             acc = up_warp_sum(acc);
             if (lane == 0) __stcg(p.y + i, acc);
         }
-        grid.sync();
+        team.sync();
     }
 
     // ---- P2: scalars (identical in every CTA), rank-one updates of my rows, b, the row of V, m = S b ----
@@ -146,7 +164,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
     up_block_reduce<4>(part, red, tot);
     const double coef = p.beta / (1.0 + p.beta * tot[0]);               // blr.py:64-67 (Sherman-Morrison)
     const double coef2 = p.beta / (1.0 + p.beta * tot[1]);
-    if (p.obs_out && blockIdx.x == 0 && tid == 0) p.obs_out[1] = 1.0 / p.beta + tot[0];   // blr.py:96 before the update
+    if (p.obs_out && cta == 0 && tid == 0) p.obs_out[1] = 1.0 / p.beta + tot[0];   // blr.py:96 before the update
     __syncthreads();                                                    // everyone has read psi from vec
     for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.v + j);
     __syncthreads();
@@ -155,6 +173,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         double* irow = p.Sinv + (size_t)i * d;
         const double cv = coef * vec[i], bphi = p.beta * phi[i];
         double acc = 0.0;
+#pragma unroll 4
         for (int j = lane; j < d; j += 32) {
             const double s = fma(-cv, vec[j], srow[j]);
             srow[j] = s;
@@ -164,6 +183,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         if (p.has_factor) {
             double* prow = p.Sp + (size_t)i * d;
             const double cy = coef2 * yv[i];
+#pragma unroll 4
             for (int j = lane; j < d; j += 32) prow[j] = fma(-cy, yv[j], prow[j]);
         }
         if (p.finalize) {
@@ -172,7 +192,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         }
     }
     {   // b and the appended row of V: slices by global thread
-        const int gt = blockIdx.x * UP_THREADS + tid, nt = gridDim.x * UP_THREADS;
+        const int gt = cta * UP_THREADS + tid, nt = ncta * UP_THREADS;
         const double sq = sqrt(coef2);
         for (int j = gt; j < d; j += nt) {
             p.b[j] = bp[j];
@@ -188,7 +208,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         }
     }
     if (!p.finalize || !p.has_factor) return;
-    grid.sync();
+    team.sync();
 
     // ---- P3: m' = B^T m (natural psi order) ----
     for (int j = tid; j < d; j += UP_THREADS) bp[j] = __ldcg(p.m + j);
@@ -198,6 +218,88 @@ __global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const Update
         if (k == 0) p.mp[0] = s0 * c;
         else { p.mp[k] = sk * c; p.mp[K + k] = -sk * s; }
     });
+}
+
+__global__ void __launch_bounds__(UP_THREADS, 1) k_blr_update_fused(const UpdateParams p) {
+    extern __shared__ __align__(16) double sm[];
+    GridTeam team;
+    blr_update_body(p, team, sm, false);
+}
+
+// ---- one observation for each of many independent runs in ONE launch (BASELINE config C4) ----
+// One thread-block cluster per run.  The cluster encodes the run's point itself -- psi from the phases (float64 sincospi),
+// phi = B psi by the synthesis sum, every CTA a slice of the components -- applies the update above with cluster barriers in
+// place of grid barriers, and finishes with the operand-order copy of m' that the scorer reads (k_mp_op of the per-run path).
+// The per-run path costs a point upload, k_encode, a cooperative launch (which wants the whole machine, so runs serialise)
+// and k_mp_op per run: 48 us of kernel time per run at d = 511 (ncu), 70 % of a lock-step of config C4.
+struct RunUpdate {
+    UpdateParams up;
+    const double* x;                      // this run's point (n float64, device)
+    const double* A_turns; int n; double dc;
+    double* phi_out;                      // d float64 scratch of the run (= up.phi)
+    const int* perm; float* mp_op; __half *vh0, *vl0; float* mscale;     // tail: m' in operand order, row 0 of the operand images
+};
+
+__global__ void __launch_bounds__(UP_THREADS, 4) k_blr_update_runs(const RunUpdate* __restrict__ runs) {
+    extern __shared__ __align__(16) double sm[];
+    ClusterTeam team;
+    const int run = blockIdx.x / team.size();
+    const RunUpdate& r = runs[run];
+    const UpdateParams& p = r.up;
+    const int d = p.d, K = p.K, tid = threadIdx.x;
+    const int cta = team.rank(), ncta = team.size();
+    // psi in natural order [dc, cos_1..K, sin_1..K] (every CTA computes all of it: K sincospi)
+    double* psi_n = sm;                   // d doubles; the body reuses this memory afterwards
+    for (int k = tid; k < K; k += UP_THREADS) {
+        double t = 0.0;
+        for (int a = 0; a < r.n; ++a) t = fma(r.A_turns[(size_t)k * r.n + a], r.x[a], t);
+        t -= rint(t);
+        double sn, cs;
+        sincospi(2.0 * t, &sn, &cs);
+        psi_n[1 + k] = cs; psi_n[1 + K + k] = sn;
+    }
+    if (tid == 0) psi_n[0] = r.dc;
+    __syncthreads();
+    if (p.has_factor && cta == 0)
+        for (int k = tid; k < d; k += UP_THREADS) __stcg(p.psi + p.inv_perm[k], psi_n[k]);
+    // phi_j = (psi_0 + 2 sum_k (C_k cos(2 pi j k / d) - S_k sin(2 pi j k / d))) / d for my slice of j (sspspace.py:275)
+    const int j0 = (int)((long long)d * cta / ncta), j1 = (int)((long long)d * (cta + 1) / ncta);
+    for (int j = j0 + tid; j < j1; j += UP_THREADS) {
+        double acc = 0.0;
+        int idx = 0;
+        for (int k = 1; k <= K; ++k) {
+            idx += j; if (idx >= d) idx -= d;
+            const double2 tw = __ldg(p.twiddle + idx);
+            acc = fma(psi_n[k], tw.x, fma(-psi_n[K + k], tw.y, acc));
+        }
+        __stcg(r.phi_out + j, (psi_n[0] + 2.0 * acc) / (double)d);
+    }
+    team.sync();
+    blr_update_body(p, team, sm, true);
+    if (!p.finalize || !p.has_factor) return;
+    team.sync();                                                         // m' complete
+    if (cta != 0) return;
+    // tail (k_mp_op): m' scaled by a power of two into row 0 of the operand images, and in operand order as float32
+    double* red = sm;
+    double mx = 0.0;
+    for (int k = tid; k < d; k += UP_THREADS) mx = fmax(mx, fabs(__ldcg(p.mp + k)));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    double m_all = 0.0;
+    for (int w = 0; w < UP_WARPS; ++w) m_all = fmax(m_all, red[w]);
+    const double sc = (m_all > 0.0 && isfinite(m_all)) ? exp2(floor(log2(1024.0 / m_all))) : 1.0;
+    if (tid == 0) *r.mscale = (float)(1.0 / sc);
+    for (int kk = tid; kk < d; kk += UP_THREADS) {
+        const double m = __ldcg(p.mp + r.perm[kk]);
+        const int c = p.col_of_rank[kk];
+        r.mp_op[c] = (float)m;
+        const double v = m * sc;
+        const __half h = __double2half(v);
+        r.vh0[c] = h;
+        r.vl0[c] = __double2half(v - (double)__half2float(h));
+    }
 }
 
 }  // namespace
@@ -228,5 +330,89 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
     void* args[] = {(void*)&p};
     SSPBO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_blr_update_fused, dim3(G), dim3(UP_THREADS), args, smem, st));
     ctx->launches++;
+    return SSPBO_OK;
+}
+
+// One observation for each of R independent runs (one context each, all on one device) in one launch.  Returns
+// SSPBO_EUNSUPPORTED -- nothing enqueued, no state touched -- when a run is not a plain SSP-space posterior with the fused
+// update available (trajectory / normalised contexts, raw-feature BLRs); the caller then takes the per-run path.
+int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed) {
+    if (R <= 0) return SSPBO_OK;
+    sspbo_ctx* c0 = ctxs[0];
+    int d_max = 0, n_max = 0;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        if (!c || c->K == 0 || !c->blr_ready || !c->has_beta || c->L != 1 || c->normalize || !c->has_factor || c->unfused_update ||
+            c->device != c0->device || c->n != c0->n)
+            return SSPBO_EUNSUPPORTED;
+        d_max = c->d > d_max ? c->d : d_max;
+        n_max = c->n > n_max ? c->n : n_max;
+    }
+    int cluster_ok = 0;
+    cudaDeviceGetAttribute(&cluster_ok, cudaDevAttrClusterLaunch, c0->device);
+    const size_t smem = ((size_t)4 * d_max + UP_WARPS * 4 + 4) * sizeof(double);
+    if (!cluster_ok || smem > 200 * 1024) return SSPBO_EUNSUPPORTED;
+    SSPBO_CUDA(c0, cudaSetDevice(c0->device));
+    // parameter block and points: pinned staging + device copy, owned by the first context
+    const size_t bytes = (size_t)R * sizeof(RunUpdate) + (size_t)R * n_max * sizeof(double);
+    if (c0->batch_pin) SSPBO_CUDA(c0, cudaEventSynchronize(c0->batch_event));   // the previous upload has left the pinned buffer
+    if (bytes > c0->batch_bytes) {
+        if (c0->batch_pin) { SSPBO_CUDA(c0, cudaStreamSynchronize(st)); cudaFreeHost(c0->batch_pin); cudaFree(c0->batch_dev); c0->batch_pin = nullptr; c0->batch_dev = nullptr; }
+        else SSPBO_CUDA(c0, cudaEventCreateWithFlags(&c0->batch_event, cudaEventDisableTiming));
+        c0->batch_bytes = 0;
+        SSPBO_CUDA(c0, cudaMallocHost(&c0->batch_pin, bytes));
+        SSPBO_CUDA(c0, cudaMalloc(&c0->batch_dev, bytes));
+        c0->batch_bytes = bytes;
+    }
+    RunUpdate* hp = (RunUpdate*)c0->batch_pin;
+    double* hx = (double*)((char*)c0->batch_pin + (size_t)R * sizeof(RunUpdate));
+    const RunUpdate* dp = (const RunUpdate*)c0->batch_dev;
+    const double* dx = (const double*)((const char*)c0->batch_dev + (size_t)R * sizeof(RunUpdate));
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        const int d = c->d;
+        if ((size_t)d > c->obs_phi_cap) {
+            if (c->obs_phi) { SSPBO_CUDA(c, cudaStreamSynchronize(st)); cudaFree(c->obs_phi); c->obs_phi = nullptr; c->obs_phi_cap = 0; }
+            if (cudaMalloc((void**)&c->obs_phi, (size_t)d * sizeof(double)) != cudaSuccess) { if (failed) *failed = r; SSPBO_FAIL(c, SSPBO_ECUDA, "update_batch: out of device memory"); }
+            c->obs_phi_cap = (size_t)d;
+        }
+        RunUpdate& u = hp[r];
+        UpdateParams& p = u.up;
+        p.d = d; p.K = c->K; p.has_factor = 1; p.finalize = 1;
+        p.beta = c->beta; p.t = ts_host[r]; p.r_scale = c->r_scale;
+        p.phi = c->obs_phi; p.S = c->S; p.Sinv = c->Sinv; p.b = c->b; p.m = c->m; p.Sp = c->Sp; p.mp = c->mp;
+        p.twiddle = c->twiddle; p.inv_perm = c->inv_perm; p.col_of_rank = c->col_of_rank;
+        p.v = c->v; p.psi = c->psi; p.y = c->y;
+        p.vh_row = nullptr; p.vl_row = nullptr; p.vd_row = nullptr; p.obs_out = nullptr;
+        if (c->lr_valid) {                                                 // the row of V this observation appends
+            if (c->lr_rank >= SSPBO_LR_MAX) c->lr_valid = false;
+            else {
+                const size_t off = (size_t)(c->lr_rank + 1) * c->KC_pad;
+                p.vh_row = c->Vh + off; p.vl_row = c->Vl + off; p.vd_row = c->Vd + (size_t)c->lr_rank * d;
+            }
+        }
+        u.x = dx + (size_t)r * n_max; u.A_turns = c->A_turns; u.n = c->n; u.dc = c->dc; u.phi_out = c->obs_phi;
+        u.perm = c->perm; u.mp_op = c->mp_op; u.vh0 = c->Vh; u.vl0 = c->Vl; u.mscale = c->mscale;
+        for (int a = 0; a < c->n; ++a) hx[(size_t)r * n_max + a] = x_host[(size_t)r * c->n + a];
+    }
+    SSPBO_CUDA(c0, cudaMemcpyAsync(c0->batch_dev, c0->batch_pin, bytes, cudaMemcpyHostToDevice, st));
+    SSPBO_CUDA(c0, cudaEventRecord(c0->batch_event, st));
+    // clusters of 4 CTAs (8 from d = 768 on): one run per cluster, as many clusters in flight as the machine holds
+    const int G = d_max >= 768 ? 8 : 4;
+    SSPBO_CUDA(c0, cudaFuncSetAttribute(k_blr_update_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(R * G)); cfg.blockDim = dim3(UP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SSPBO_CUDA(c0, cudaLaunchKernelEx(&cfg, k_blr_update_runs, dp));
+    c0->launches++;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        if (hp[r].up.vd_row) c->lr_rank++;
+        c->v8_row0_dirty = true;
+        c->operands_dirty = true; c->factor_dirty = true; c->f8_factor_dirty = true;
+    }
     return SSPBO_OK;
 }

@@ -349,3 +349,36 @@ def test_rff_maximize_route(pkg):
     assert opt.xs.shape == (14, 2) and opt.ys.shape == (14,)
     assert np.all(opt.xs[10:] >= -5) and np.all(opt.xs[10:] <= 5)
     assert isinstance(opt.agt, pkg.RFFAgent) and np.isfinite(opt.max["target"])
+
+
+def test_batched_runs_use_grouped_kernels(pkg):
+    """Config C4: a lock-step of R runs that share a layout is three launches for the selection (grouped scorer over (run,
+    tile), grouped float64 pass, status words) and one for all updates -- not several launches per run -- and gives what the
+    per-run path gives (posterior and picks compared run by run with independently stepped agents)."""
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    R, steps = 7, 4
+    def make():
+        out = []
+        for r in range(R):
+            sp = pkg.RandomSSPSpace(2, ssp_dim=256, domain_bounds=bounds, length_scale=1.0, rng=r)
+            xs0 = np.random.default_rng(400 + r).uniform(-5, 5, (6, 2))
+            out.append(pkg.SSPAgent(xs0, himmelblau(xs0).reshape(-1, 1), sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+        return out
+    grid = orc.grid_sample_points(bounds, 50)
+    a_batch, a_single = make(), make()
+    runs = pkg.BatchedRuns(a_batch, grid, n_streams=3)
+    engines = [a._scoring_engine() for a in a_batch]
+    for _ in range(steps):
+        before = sum(e.launch_count() for e in engines)
+        pts, ys, scores = runs.step(himmelblau)
+        launched = sum(e.launch_count() for e in engines) - before
+        assert launched <= 5, launched                          # 4 grouped launches (+ slack), not ~7 per run
+        for r, agt in enumerate(a_single):                      # the per-run route on independent agents
+            agt.best_candidate(grid)
+            s, idx = agt._scoring_engine().best()
+            assert abs(s - scores[r]) <= 1e-6 * abs(s)
+            assert np.array_equal(grid[idx], pts[r])
+            agt.update(grid[idx:idx + 1], np.atleast_2d(himmelblau(grid[idx:idx + 1])), 0.0)
+    for a, b in zip(a_batch, a_single):
+        assert rel(a.blr.m, b.blr.m) < 1e-10 and rel(a.blr.S, b.blr.S) < 1e-10
+        assert a._scoring_engine().lowrank_info() == b._scoring_engine().lowrank_info()

@@ -12,7 +12,9 @@ def himmelblau(x):
     return -((x[:, 0] ** 2 + x[:, 1] - 11) ** 2 + (x[:, 0] + x[:, 1] ** 2 - 7) ** 2) / 100.0
 
 
-def c4(runs=int(os.environ.get("C4_RUNS", "128")), steps=5):
+def c4(runs=int(os.environ.get("C4_RUNS", "4096")), steps=5):
+    """BASELINE config C4: `runs` independent BLR-UCB runs (Himmelblau 2-D, ssp-rand ssp_dim=512 -> d=511, own space seed and
+    posterior each) over a shared 100 x 100 grid, stepped in lock-step through BatchedRuns (grouped kernels)."""
     b2 = np.array([[-5.0, 5.0], [-5.0, 5.0]])
     agents = []
     t0 = time.perf_counter()
@@ -26,19 +28,27 @@ def c4(runs=int(os.environ.get("C4_RUNS", "128")), steps=5):
     br = BatchedRuns(agents, grid)
     br.step(himmelblau)
     torch.cuda.synchronize()
+    t_sel = t_upd = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
-        br.step(himmelblau)
-    torch.cuda.synchronize()
+        ta = time.perf_counter()
+        scores, idx, pts = br.select()
+        tb = time.perf_counter()
+        ys = himmelblau(pts)
+        tc = time.perf_counter()
+        br.update(pts, ys)
+        torch.cuda.synchronize()
+        t_sel += tb - ta; t_upd += time.perf_counter() - tc
     dt = (time.perf_counter() - t0) / steps
     eng = agents[0]._scoring_engine()
     print(f"C4: {runs} runs x {grid.shape[0]} candidates d={eng.d}: {dt * 1e3:.1f} ms per lock-step "
-          f"({runs * grid.shape[0] / dt:.3e} candidate evaluations/s; engine {eng.last_engine()}; set-up {t_build:.1f} s) "
-          f"-> 4096 runs: {dt * 4096 / runs:.2f} s per lock-step")
+          f"({runs * grid.shape[0] / dt:.3e} candidate evaluations/s; selection {t_sel / steps * 1e3:.1f} ms, updates "
+          f"{t_upd / steps * 1e3:.1f} ms; engine {eng.last_engine()}; set-up {t_build:.1f} s)")
     return {"workload": f"C4: {runs} independent BLR-UCB runs (Himmelblau 2-D, ssp-rand ssp_dim=512 -> d={eng.d}), shared 100x100 grid, "
-                        "stepped in lock-step (BatchedRuns)", "runs": runs, "candidates_per_run": int(grid.shape[0]), "steps": steps,
-            "ms_per_lockstep": dt * 1e3, "candidate_evaluations_per_s": runs * grid.shape[0] / dt, "engine": eng.last_engine(),
-            "setup_s": t_build, "extrapolated_s_per_4096_run_lockstep": dt * 4096 / runs}
+                        "stepped in lock-step (BatchedRuns, grouped kernels)", "runs": runs, "candidates_per_run": int(grid.shape[0]),
+            "steps": steps, "ms_per_lockstep": dt * 1e3, "selection_ms": t_sel / steps * 1e3, "updates_ms": t_upd / steps * 1e3,
+            "candidate_evaluations_per_s": runs * grid.shape[0] / dt, "engine": eng.last_engine(),
+            "posterior_rank": eng.lowrank_info()["rank"], "setup_s": t_build}
 
 
 def c5(n=1 << 20, steps=3):
