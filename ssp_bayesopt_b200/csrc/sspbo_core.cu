@@ -562,8 +562,31 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
     const int64_t count = (int64_t)c0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long my_best = 0ull;
+    // arg-max only (no per-candidate outputs): a flagged candidate whose score bound cannot beat the best key so far is skipped
+    const bool prune = best != nullptr && !mu_out && !var_out && !acq_out;
+    __shared__ int keep_s;
     for (int64_t base = (int64_t)cta * EX_G; base < count; base += (int64_t)ncta * EX_G) {
         __syncthreads();
+        if (prune) {
+            if (threadIdx.x == 0) {
+                const unsigned int ob = (unsigned int)(*(volatile unsigned long long*)best >> 32);     // orderable bits of the best score
+                int keep = 0;
+                if (ob != 0xffffffffu) {                                                             // (NaN already won)
+                    const float bs = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+                    for (int c = 0; c < EX_G && base + c < count; ++c) {
+                        const float ub = __uint_as_float(list[cap + base + c]);
+                        if (!(ub + 1e-3f * (fabsf(ub) + fabsf(bs)) < bs) || ob == 0u) ++keep;
+                    }
+                }
+                keep_s = keep;
+                if (keep) atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)keep);
+            }
+            __syncthreads();
+            if (keep_s == 0) continue;
+        } else if (threadIdx.x == 0) {
+            const int64_t nhere = count - base < EX_G ? count - base : EX_G;
+            atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)nhere);
+        }
         if (cand.mode != 0) {
             if (threadIdx.x < EX_G && base + threadIdx.x < count)
                 sspbo_lr::cand_row_rt(cand, n, index0 + (int64_t)list[base + threadIdx.x], xs_gen[threadIdx.x]);
@@ -1520,7 +1543,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false; ctx->lr_flag_frac = 0.0;
     if (with_factor && !ctx->stats) {
         if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
-            (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)SSPBO_FLAG_CAP)))
+            (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)2 * SSPBO_FLAG_CAP)))
             return rc;
     }
     ctx->blr_ready = true; ctx->operands_dirty = true; ctx->f8_factor_dirty = true;
@@ -2052,11 +2075,11 @@ extern "C" int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_
     // more flagged candidates than the list holds: the low-rank form gives way to the factor form, and that one (whose own
     // flags then overflowed as well) to the engines that never flag
     if (h[SSPBO_STAT_OVERFLOW] > 0 && (ctx->lr_disabled || !ctx->lr_valid)) ctx->f8_disabled = true;
-    if (h[SSPBO_STAT_OVERFLOW] > 0 || (h[SSPBO_STAT_SCORED] >= 4096 && h[SSPBO_STAT_FLAGGED] * 100 > h[SSPBO_STAT_SCORED]))
+    if (h[SSPBO_STAT_OVERFLOW] > 0 || (h[SSPBO_STAT_SCORED] >= 4096 && h[SSPBO_STAT_RESCORED] * 100 > h[SSPBO_STAT_SCORED]))
         ctx->lr_disabled = true;
     if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
-    if (ctx->last_engine == SSPBO_ENGINE_UMMA_LR && h[SSPBO_STAT_SCORED] >= 4096)
-        ctx->lr_flag_frac = (double)h[SSPBO_STAT_FLAGGED] / (double)h[SSPBO_STAT_SCORED];
+    if (ctx->last_engine == SSPBO_ENGINE_UMMA_LR && h[SSPBO_STAT_SCORED] >= 4096)       // what the float64 pass really costs
+        ctx->lr_flag_frac = (double)h[SSPBO_STAT_RESCORED] / (double)h[SSPBO_STAT_SCORED];
     if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0) ? 1 : 0;
     return SSPBO_OK;
 }

@@ -90,7 +90,7 @@ struct sspbo_ctx {
     double a_absmax = 0.0;           // max |A_turns|
     std::vector<double> host_A_turns;            // host copy of A_turns (K x n) for rebuilding the tables
     // exact float64 scorer (flagged candidates of the low-rank pass, tiny candidate sets)
-    unsigned int* flag_idx = nullptr;            // SSPBO_FLAG_CAP local row indices
+    unsigned int* flag_idx = nullptr;            // SSPBO_FLAG_CAP local row indices, then SSPBO_FLAG_CAP float32 score bounds
     unsigned long long* stats = nullptr;         // device counters, see SSPBO_STAT_*
     double* ex_part = nullptr;                   // partial quadratic forms / means of the exact scorer
     size_t ex_part_cap = 0;
@@ -176,6 +176,7 @@ enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (re
        SSPBO_STAT_OVERFLOW = 2,  // flagged candidates beyond SSPBO_FLAG_CAP (kept their low-rank score)
        SSPBO_STAT_OOR = 3,       // candidates outside the declared |x| bound of the 32-bit phase path
        SSPBO_STAT_SCORED = 4,    // candidates scored by the low-rank pass since the last reset
+       SSPBO_STAT_RESCORED = 5,  // flagged candidates the float64 pass really re-scored (the others could not win the arg-max)
        SSPBO_STAT_COUNT = 8 };
 
 // Timing experiments (tools/kbench.py): built only with -DSSPBO_EXPERIMENTS (`make EXPERIMENTS=1`).  SSPBO_DEBUG bits:

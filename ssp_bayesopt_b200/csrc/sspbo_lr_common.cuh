@@ -311,6 +311,18 @@ __device__ __forceinline__ void load_tables(const Params& p, uint8_t* tables, in
     }
 }
 
+// Upper bound of the true score of a candidate the tensor pass flags (its variance is too small for the pass's own accuracy):
+// the approximate mean plus the acquisition at an inflated variance.  The error of the pass on the variance is ~2e-5 of the
+// prior variance (float32 accumulation inside the tensor core; e4m3 corrections in factor form: ~3e-5); 1e-4 of it is added.
+// The float64 pass skips a flagged candidate whose bound, with a further 1e-3 relative margin, stays below the best key found
+// so far: a candidate close to the observations has little variance left and rarely competes for the arg-max, and its float64
+// re-score costs as much as ~36 tensor-pass candidates per operand row.  Stored behind the index list (flag_idx[cap + slot]).
+__device__ __forceinline__ float flagged_score_bound(float mu, float var, float prior, float lam, float gamma_t) {
+    if (!(lam >= 0.f)) return __int_as_float(0x7f800000);                 // (a negative weight would need a lower bound: no pruning)
+    const float v = fmaxf(var, 0.f) + 1e-4f * prior;
+    return mu + lam * v / (sqrtf(v + gamma_t) + sqrtf(gamma_t));
+}
+
 // acquisition of one scored candidate: packs the key, writes the optional outputs
 __device__ __forceinline__ unsigned long long finish_candidate(const Params& p, long long gi, float mu, float var) {
     const float acq = p.lam * var / (sqrtf(var + p.gamma_t) + sqrtf(p.gamma_t));   // ssp_agent.py:136, cancellation-free

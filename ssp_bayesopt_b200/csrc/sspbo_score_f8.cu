@@ -353,14 +353,20 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                     var = p.inv_beta + (prior - q);                                   // blr.py:96 with S = I/alpha - V^T V
                     if (var < flag_below) {                                         // too close to the observations for
                         const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
-                        if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                        if (slot < (unsigned long long)p.flag_cap) {
+                            p.flag_idx[slot] = (unsigned int)gi; flagged = true;
+                            p.flag_idx[p.flag_cap + slot] = __float_as_uint(flagged_score_bound(mu, var, prior, p.lam, p.gamma_t));
+                        }
                         else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
                     }
                 } else {
                     var = p.inv_beta + q;                                             // blr.py:96 with psi^T Sp psi = |R psi|^2
                     if (var < flag_below) {                                         // nearly on top of an observation: the e4m3
                         const unsigned long long slot = atomicAdd(p.stats + SSPBO_STAT_CUR, 1ull);   // corrections are too coarse
-                        if (slot < (unsigned long long)p.flag_cap) { p.flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                        if (slot < (unsigned long long)p.flag_cap) {
+                            p.flag_idx[slot] = (unsigned int)gi; flagged = true;
+                            p.flag_idx[p.flag_cap + slot] = __float_as_uint(flagged_score_bound(mu, var, prior, p.lam, p.gamma_t));
+                        }
                         else atomicAdd(p.stats + SSPBO_STAT_OVERFLOW, 1ull);
                     }
                 }

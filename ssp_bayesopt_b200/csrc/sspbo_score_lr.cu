@@ -357,7 +357,10 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
                 bool flagged = false;
                 if (var < flag_below) {                                             // too close to the observations for
                     const unsigned long long slot = atomicAdd(e_stats + SSPBO_STAT_CUR, 1ull);   // the cancelling form
-                    if (slot < (unsigned long long)p.flag_cap) { e_flag_idx[slot] = (unsigned int)gi; flagged = true; }
+                    if (slot < (unsigned long long)p.flag_cap) {
+                        e_flag_idx[slot] = (unsigned int)gi; flagged = true;
+                        e_flag_idx[p.flag_cap + slot] = __float_as_uint(flagged_score_bound(mu, var, prior, e_lam, e_gamma));
+                    }
                     else atomicAdd(e_stats + SSPBO_STAT_OVERFLOW, 1ull);
                 }
                 if (!flagged) {
