@@ -20,6 +20,19 @@ from . import _lib
 from .agents import SSPAgent
 
 
+def _unpack_keys(keys):
+    """numpy form of sspbo_key_unpack for an int64 array of packed keys: (scores float64, indices int64).
+    key = orderable(score) << 32 | (0xFFFFFFFF - index); orderable(u) = ~u for negative floats, u | 0x80000000 otherwise."""
+    k = np.asarray(keys).astype(np.int64).view(np.uint64)
+    ob = (k >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(ob & np.uint32(0x80000000), ob & np.uint32(0x7FFFFFFF), ~ob).astype(np.uint32)
+    scores = bits.view(np.float32).astype(np.float64)
+    scores[ob == np.uint32(0xFFFFFFFF)] = np.nan                 # NaN counts as the maximum
+    scores[k == 0] = -np.inf                                     # no candidate scored
+    idx = (np.uint64(0xFFFFFFFF) - (k & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    return scores, idx
+
+
 class BatchedRuns:
     def __init__(self, agents: list[SSPAgent], candidates, n_streams: int = 8):
         assert len(agents) > 0
@@ -75,9 +88,7 @@ class BatchedRuns:
             eng.score(self.candidates, float(lam[r]), float(gam[r]))
             score, idx_r = eng.best()
             keys[r] = np.array(_lib.key_pack(score, idx_r), dtype=np.uint64).astype(np.int64)
-        unpacked = [_lib.key_unpack(int(k)) for k in keys]
-        scores = np.array([u[0] for u in unpacked])
-        idx = np.array([u[1] for u in unpacked], dtype=np.int64)
+        scores, idx = _unpack_keys(keys)                         # vectorised sspbo_key_unpack (thousands of runs per lock-step)
         pts = self.candidates[torch.as_tensor(idx, device=self.device)].double().cpu().numpy()
         return scores, idx, pts
 

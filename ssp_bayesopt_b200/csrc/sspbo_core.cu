@@ -1050,15 +1050,35 @@ __global__ void k_grid_points(const double* __restrict__ axes, GridDesc g, int64
 // =====================================================================================
 // host side
 // =====================================================================================
+// Context buffers come from the device's stream-ordered pool (kept, not returned to the driver, when freed): a context is ~30
+// buffers, and thousands of contexts are created for config C4 -- plain cudaMalloc + synchronous memset cost 20 ms per context.
+// Every creation path ends with a device synchronisation, after which the memory is valid on any stream.
+static void dev_pool_keep(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
+// (a few buffers are plain cudaMalloc allocations: those go back through cudaFree)
 template <typename T>
-static int dev_alloc(sspbo_ctx* ctx, T** p, size_t count) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
-    SSPBO_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
-    SSPBO_CUDA(ctx, cudaMemset(*p, 0, count * sizeof(T)));
-    return SSPBO_OK;
+static void dev_free(T** p) {
+    if (!*p) return;
+    if (cudaFreeAsync(*p, 0) != cudaSuccess) { cudaGetLastError(); cudaFree(*p); }
+    *p = nullptr;
 }
 template <typename T>
-static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+static int dev_alloc(sspbo_ctx* ctx, T** p, size_t count) {
+    if (*p) dev_free(p);
+    dev_pool_keep(ctx->device);
+    SSPBO_CUDA(ctx, cudaMallocAsync((void**)p, count * sizeof(T), 0));
+    SSPBO_CUDA(ctx, cudaMemsetAsync(*p, 0, count * sizeof(T), 0));
+    return SSPBO_OK;
+}
+
 
 extern "C" int sspbo_abi_version(void) { return 1; }
 
@@ -1079,6 +1099,7 @@ extern "C" int sspbo_ctx_create(int device, sspbo_ctx** out) {
 }
 
 static void free_blr(sspbo_ctx* ctx) {
+    cudaDeviceSynchronize();                              // work on non-blocking streams may still use the buffers (pool frees are stream-ordered on stream 0 only)
     sspbo_f8_release(ctx);
     timing_release(ctx);
     if (ctx->batch_pin) { cudaFreeHost(ctx->batch_pin); cudaFree(ctx->batch_dev); cudaEventDestroy(ctx->batch_event); ctx->batch_pin = nullptr; ctx->batch_dev = nullptr; }
@@ -1161,6 +1182,7 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     if (!ctx) return SSPBO_EINVAL;
     if (!A_plus || !inv_ls || K < 1 || n < 1 || n > 16) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set: need K>=1, 1<=n<=16");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->K) SSPBO_CUDA(ctx, cudaDeviceSynchronize());     // re-programming: the old tables may still be read on other streams
     if (K != ctx->K || !ctx->has_factor) { free_blr(ctx); sspbo_umma_release(ctx); }
     if (K != ctx->K) ctx->enc_K = 0;
     const int d = 2 * K + 1;

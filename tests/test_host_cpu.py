@@ -323,3 +323,17 @@ def test_sinc_kernel_reference_properties():
     sinc_score = GaussianProcessClassifier(kernel=SincKernel(), random_state=0).fit(X, y).score(X, y)
     rbf_score = GaussianProcessClassifier(kernel=1.0 * RBF(1.0), random_state=0).fit(X, y).score(X, y)
     assert np.allclose(sinc_score, rbf_score, atol=2e-2), (rbf_score, sinc_score)
+
+
+def test_vectorised_key_unpack_matches_c():
+    """BatchedRuns unpacks thousands of keys per lock-step with numpy; same results as sspbo_key_unpack."""
+    from ssp_bayesopt_b200 import _lib
+    from ssp_bayesopt_b200.batched import _unpack_keys
+    vals = [(1.5, 3), (-2.25, 4000000000), (0.0, 7), (-0.0, 9), (1e30, 0), (-1e-30, 12), (float("inf"), 5), (float("nan"), 8)]
+    keys = np.array([_lib.key_pack(s, i) for s, i in vals], dtype=np.uint64).astype(np.int64)
+    sc, ix = _unpack_keys(keys)
+    for k, a, b in zip(keys, sc, ix):
+        s, i = _lib.key_unpack(int(k))
+        assert (a == s or (np.isnan(a) and np.isnan(s))) and b == i
+    sc, ix = _unpack_keys(np.zeros(2, dtype=np.int64))
+    assert np.all(np.isneginf(sc))
