@@ -382,3 +382,37 @@ def test_batched_runs_use_grouped_kernels(pkg):
     for a, b in zip(a_batch, a_single):
         assert rel(a.blr.m, b.blr.m) < 1e-10 and rel(a.blr.S, b.blr.S) < 1e-10
         assert a._scoring_engine().lowrank_info() == b._scoring_engine().lowrank_info()
+
+
+# ------------------------------------------------------------------------------------------ pruning of the float64 pass
+@pytest.mark.parametrize("lam,gamma", [(0.01, 0.0), (0.3, 0.0), (10.0, 0.0), (2.0, 50.0)])
+@pytest.mark.parametrize("fmt,T", [(0, 60), (1, 200)])
+def test_argmax_when_the_winner_is_a_flagged_candidate(pkg, lam, gamma, fmt, T):
+    """The float64 pass skips flagged candidates that cannot beat the best key.  With a small variance weight the arg-max IS a
+    flagged candidate (right next to the best observation: high mean, almost no variance left), so the pruning must keep it:
+    key-only calls (the pruning path) against the oracle's arg-max and against the call with outputs (no pruning)."""
+    from ssp_bayesopt_b200 import _lib
+    sp, model, ref, X = _c3_setup(pkg, T)
+    eng = sp.engine
+    eng.set_operand_format(fmt)
+    xc = _mixed_candidates(X, 8000, seed=11)
+    phis = orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc.astype(np.float64))
+    ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, lam, gamma)
+    ref_score = ref_mu.ravel() + ref_acq
+    srt = np.argsort(ref_score)[::-1]
+    eng.score_stats(reset=True)
+    eng.score(xc, lam, gamma, engine=_lib.ENGINE_UMMA_LR)                     # key only: pruned float64 pass
+    st = eng.score_stats(reset=True)                                          # (best() below reads and resets the counters itself)
+    eng.score(xc, lam, gamma, engine=_lib.ENGINE_UMMA_LR)
+    s, idx = eng.best()
+    _, (mu, var, acq) = eng.score(xc, lam, gamma, want_outputs=True, engine=_lib.ENGINE_UMMA_LR)
+    s2, idx2 = eng.best()
+    assert (s, idx) == (s2, idx2)                                             # pruning changes nothing
+    if (ref_score[srt[0]] - ref_score[srt[1]]) > RTOL_SCORE * abs(ref_score[srt[0]]):
+        assert idx == int(srt[0]), (idx, int(srt[0]))
+    assert abs(s - ref_score.max()) <= RTOL_SCORE * abs(ref_score.max())
+    assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+    assert st["flagged"] >= 60 and st["overflow"] == 0
+    if lam <= 0.01:                                                           # the winner sits among the flagged ones here
+        assert ref_var[srt[0]] < 0.3 / 0.01
+    eng.set_operand_format(None)
