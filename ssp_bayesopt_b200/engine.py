@@ -385,21 +385,22 @@ class DeviceEngine:
         N = xt.shape[0]
         out = torch.empty((3, max(N, 1)), dtype=torch.float32, device=self._dev())
         ptrs = [C.c_void_p(out[i].data_ptr()) for i in range(3)]
-        self._best.zero_()
-        self._pending = []
-        self._lr_used = False
+        # eval() may sit between chunked best_candidate(..., reset_best=False) calls: the running key and its pending calls are
+        # settled first and left alone; this call scores into a key of its own
+        self.settle()
+        key = torch.zeros(1, dtype=torch.int64, device=self._dev())
 
         def call():
             rc = self.lib.sspbo_score(self._ctx, C.c_void_p(xt.data_ptr()), self._dtype_code(xt), N, 0, float(lam),
-                                      float(gamma_t), ptrs[0], ptrs[1], ptrs[2], C.c_void_p(self._best.data_ptr()),
+                                      float(gamma_t), ptrs[0], ptrs[1], ptrs[2], C.c_void_p(key.data_ptr()),
                                       int(engine), self._stream())
             self._check(rc, "sspbo_score")
         call()
-        self._pending.append(call)
         if self.lib.sspbo_last_engine(self._ctx) in _RERUN_ENGINES:
-            self._lr_used = True
-            if self._needs_rerun():
-                self._replay()
+            for _ in range(3):                                       # flag-list overflow / out-of-bound rows: the context switched engines
+                if not self._needs_rerun():
+                    break
+                call()
         host = out[:, :N].cpu().numpy().astype(np.float64)           # one D2H; the widening happens on the host
         return host[0], host[1], host[2]
 

@@ -416,3 +416,19 @@ def test_argmax_when_the_winner_is_a_flagged_candidate(pkg, lam, gamma, fmt, T):
     if lam <= 0.01:                                                           # the winner sits among the flagged ones here
         assert ref_var[srt[0]] < 0.3 / 0.01
     eng.set_operand_format(None)
+
+
+def test_eval_between_chunked_selection_keeps_the_running_key(pkg):
+    """SSPAgent.eval on a large set between best_candidate(..., reset_best=False) chunks must not disturb the running key."""
+    sp, model, ref, X = _c3_setup(pkg, 20)
+    agt_eng = sp.engine
+    xc = orc.counter_uniform(0, 0, 6000, 6)
+    agt_eng.score(xc[:3000], 10.0, 0.0, index0=0, reset_best=True)
+    mu, var, acq = agt_eng.eval_host(xc[100:400], 10.0, 0.0)                 # 300 rows: the tensor route
+    agt_eng.score(xc[3000:], 10.0, 0.0, index0=3000, reset_best=False)
+    s, idx = agt_eng.best()
+    agt_eng.score(xc, 10.0, 0.0)
+    s_all, idx_all = agt_eng.best()
+    assert (s, idx) == (s_all, idx_all)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc[100:400].astype(np.float64)), ref, 10.0, 0.0)
+    assert_scores_close(mu, acq, ref_mu, ref_acq)
