@@ -281,7 +281,13 @@ class BayesianOptimization:
 
             update_start = time.perf_counter_ns()
             # eval(x_t) under the current posterior, then update(x_t, y_t, var_t) (:299-303): one device round trip
-            if hasattr(agt, 'observe'):
+            pure_ucb = isinstance(getattr(agt, 'gamma_c', None), (int, float)) and agt.gamma_c == 0
+            if pure_ucb and not self.verbose and hasattr(agt, 'observe'):
+                # gamma_t += 0 * var_t: nothing of eval(x_t) is used, so the update is only enqueued -- no read-back, no second
+                # synchronisation in the step; the next selection queues behind it on the stream
+                agt.update(x_t, y_t, 0.0, step_num=t + n0)
+                mu_t = var_t = phi_t = None
+            elif hasattr(agt, 'observe'):
                 mu_t, var_t, phi_t = agt.observe(x_t, y_t, step_num=t + n0)
             else:
                 mu_t, var_t, phi_t = agt.eval(x_t)

@@ -2154,6 +2154,14 @@ extern "C" int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const do
     if (k == 0) return SSPBO_OK;
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (k == 1 && ctx->d <= SSPBO_CLUSTER_UPDATE_MAX_D) {
+        // small spaces: the observation of a BO step in ONE launch -- a cluster of four CTAs encodes the point, applies the
+        // update and refreshes the scoring operands (the cooperative kernel's grid barriers and the two helper launches around
+        // it cost more than the arithmetic at d = 151); larger spaces want the whole machine's bandwidth for the d x d state
+        sspbo_ctx* one[1] = {ctx};
+        const int rc = sspbo_blr_update_runs(one, 1, x_host, ts_host, st, nullptr, ctx->want_obs ? ctx->obs_out : nullptr);
+        if (rc != SSPBO_EUNSUPPORTED) return rc;
+    }
     const size_t nl = (size_t)ctx->n * ctx->L;
     const size_t stage = 64 * nl * sizeof(double);       // sized by the row width: thousands of contexts may coexist (C4)
     if (ctx->obs_pin) SSPBO_CUDA(ctx, cudaEventSynchronize(ctx->obs_event));       // the previous upload has left the pinned buffer

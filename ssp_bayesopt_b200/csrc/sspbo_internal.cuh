@@ -169,6 +169,7 @@ constexpr int SSPBO_F8_MIN_BN = 144;
 // reaches 1e-4 of the sum for candidates almost on top of an observation; candidates whose variance is below this fraction
 // of the prior variance |phi|^2 / alpha are re-scored by the float64 pass (measured on B200: 1.3e-4 at 0.3 % of the prior).
 constexpr double SSPBO_F8_FLAG_FRACTION = 0.1;
+constexpr int SSPBO_CLUSTER_UPDATE_MAX_D = 320;  // single observations up to this dimension take the clustered one-launch update
 constexpr unsigned SSPBO_FLAG_CAP = 1u << 17;    // flagged candidates per sspbo_score call that get the exact pass
 // device counters (unsigned long long each)
 enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (reset by its exact pass)
@@ -227,7 +228,8 @@ int sspbo_score_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
 void sspbo_umma_release(sspbo_ctx* ctx);
 int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, float* out, int pitch, cudaStream_t st);
 // one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
-int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed);
+int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed,
+                          double* obs_out = nullptr);
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
                            double* vd_row, double* obs_out, cudaStream_t st);
 // low-rank engines with the A operand in tensor memory: prototypes in sspbo_lr_common.cuh (they take a candidate descriptor)

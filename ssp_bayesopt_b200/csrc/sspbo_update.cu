@@ -336,7 +336,8 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
 // One observation for each of R independent runs (one context each, all on one device) in one launch.  Returns
 // SSPBO_EUNSUPPORTED -- nothing enqueued, no state touched -- when a run is not a plain SSP-space posterior with the fused
 // update available (trajectory / normalised contexts, raw-feature BLRs); the caller then takes the per-run path.
-int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed) {
+int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed,
+                          double* obs_out) {
     if (R <= 0) return SSPBO_OK;
     sspbo_ctx* c0 = ctxs[0];
     int d_max = 0, n_max = 0;
@@ -383,7 +384,7 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
         p.phi = c->obs_phi; p.S = c->S; p.Sinv = c->Sinv; p.b = c->b; p.m = c->m; p.Sp = c->Sp; p.mp = c->mp;
         p.twiddle = c->twiddle; p.inv_perm = c->inv_perm; p.col_of_rank = c->col_of_rank;
         p.v = c->v; p.psi = c->psi; p.y = c->y;
-        p.vh_row = nullptr; p.vl_row = nullptr; p.vd_row = nullptr; p.obs_out = nullptr;
+        p.vh_row = nullptr; p.vl_row = nullptr; p.vd_row = nullptr; p.obs_out = (R == 1) ? obs_out : nullptr;
         if (c->lr_valid) {                                                 // the row of V this observation appends
             if (c->lr_rank >= SSPBO_LR_MAX) c->lr_valid = false;
             else {
