@@ -1052,7 +1052,6 @@ __global__ void k_grid_points(const double* __restrict__ axes, GridDesc g, int64
 // =====================================================================================
 // Context buffers come from the device's stream-ordered pool (kept, not returned to the driver, when freed): a context is ~30
 // buffers, and thousands of contexts are created for config C4 -- plain cudaMalloc + synchronous memset cost 20 ms per context.
-// Every creation path ends with a device synchronisation, after which the memory is valid on any stream.
 static void dev_pool_keep(int device) {
     static bool done[64] = {};
     if (device < 0 || device >= 64 || done[device]) return;
@@ -1076,6 +1075,7 @@ static int dev_alloc(sspbo_ctx* ctx, T** p, size_t count) {
     dev_pool_keep(ctx->device);
     SSPBO_CUDA(ctx, cudaMallocAsync((void**)p, count * sizeof(T), 0));
     SSPBO_CUDA(ctx, cudaMemsetAsync(*p, 0, count * sizeof(T), 0));
+    SSPBO_CUDA(ctx, cudaStreamSynchronize(0));            // allocated and cleared before any (non-blocking) caller stream can touch it
     return SSPBO_OK;
 }
 
