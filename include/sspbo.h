@@ -72,6 +72,13 @@ const char* sspbo_last_error(const sspbo_ctx* ctx);
  * inv_ls_host: 1/length_scale per axis (n).  d = 2K+1 (conjsym, sspspace.py:821-827).
  * Re-setting the space keeps the BLR state only if K is unchanged. */
 int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus_host, const double* inv_ls_host, int K, int n);
+/* One phase matrix per agent (SSPMultiAgent._set_ssp_space with same_agt_x_space=False or a list of distinct ssp_x_spaces,
+ * agents/ssp_multi_agent.py:51-66): n_cls tables of one shape, A_plus_host n_cls x K x n, inv_ls_host n_cls x n.  Waypoint j of
+ * a candidate row is encoded with table j % n_cls -- rows laid out (traj_len, n_agents, x_dim) as SSPMultiAgent.encode reshapes
+ * them (ssp_multi_agent.py:178) -- by every consumer (encode, the SIMT / low-rank / fp16+e4m3 scorers, the float64 passes);
+ * the dense-factor tcgen05 engine and sspbo_encode_f32 report SSPBO_EUNSUPPORTED.  Until sspbo_space_set_waypoints is called
+ * (L a multiple of n_cls) a row is n_cls waypoints with no time phases.  1 <= n_cls <= 16. */
+int sspbo_space_set_classes(sspbo_ctx* ctx, const double* A_plus_host, const double* inv_ls_host, int K, int n, int n_cls);
 
 /* Trajectory mode (SSPTrajectoryAgent.encode, agents/ssp_traj_agent.py:145-163):
  * candidates are rows of L waypoints (L*n values); the spectrum is the sum over

@@ -98,6 +98,71 @@ def gen_multi_agent(agents):
     np.savez_compressed(os.path.join(OUT, "multi_agent.npz"), **out)
 
 
+def gen_multi_agent_sep(agents):
+    """9b. multi-agent trajectory agent with ONE RandomSSPSpace PER AGENT (same_agt_x_space=False, ssp_multi_agent.py:58-66),
+    each on its own rows of domain_bounds: encode, eval, decode; and the K-fold length-scale search of the multi-agent agent
+    (ssp_multi_agent.py:131-164), which the reference can only run with one agent (its x0 has n_agents + 1 entries against two
+    bounds) -- every objective evaluation recorded as in gen_lengthscale_cv."""
+    from ssp_bayes_opt.agents import ssp_multi_agent as ref_mod
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    out = {}
+    for tag, (n_agents, L, ssp_dim, seed) in {"s3": (3, 4, 51, 2), "s2": (2, 5, 121, 7)}.items():
+        xd = 2
+        bm = np.array([[-2.0, 2.0], [-2.0, 2.0], [-1.0, 3.0], [0.0, 2.5], [-3.0, 1.0], [-2.0, 2.0]])[:n_agents * xd]
+        rng = np.random.default_rng(60 + n_agents)
+        lo, hi = np.tile(bm[:, 0], L), np.tile(bm[:, 1], L)                # candidate layout (traj_len, n_agents, x_dim)
+        trajs = rng.uniform(lo, hi, size=(12, L * n_agents * xd))
+        tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / (L * n_agents)
+        with quiet:
+            agt = agents.SSPMultiAgent(trajs, tys, n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim,
+                                       domain_bounds=bm, length_scale=0.8, time_length_scale=1.2, seed=seed,
+                                       same_agt_x_space=False, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+        assert agt.ssp_x_spaces[0] is not agt.ssp_x_spaces[1]
+        xc = rng.uniform(lo, hi, size=(40, L * n_agents * xd))
+        mu, var, acq = agt.eval(xc)
+        out.update({f"{tag}_Ax": np.stack([sp.phase_matrix for sp in agt.ssp_x_spaces]), f"{tag}_At": agt.ssp_t_space.phase_matrix,
+                    f"{tag}_ls_x": np.stack([np.ravel(sp.length_scale) for sp in agt.ssp_x_spaces]),
+                    f"{tag}_ls_t": np.ravel(agt.ssp_t_space.length_scale),
+                    f"{tag}_agent_sps": agt.agent_sps, f"{tag}_timestep_ssps": agt.timestep_ssps,
+                    f"{tag}_trajs": trajs, f"{tag}_tys": tys, f"{tag}_xc": xc, f"{tag}_phi": agt.encode(xc),
+                    f"{tag}_mu": mu, f"{tag}_var": var, f"{tag}_acq": acq, f"{tag}_beta": np.float64(np.ravel(agt.blr.beta)[0]),
+                    f"{tag}_m": agt.blr.m, f"{tag}_S": agt.blr.S,
+                    f"{tag}_init_pts": np.stack([agt.init_samples[i][1] for i in range(n_agents)]),
+                    f"{tag}_decoded": agt.decode(agt.encode(xc[:1])), f"{tag}_bounds": bm,
+                    f"{tag}_dims": np.array([n_agents, L, xd, ssp_dim, seed])})
+    # length-scale search, one agent
+    L, xd = 4, 2
+    bt = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    rng = np.random.default_rng(41)
+    trajs = rng.uniform(-2, 2, size=(14, L * xd))
+    tys = (np.sin(trajs[:, ::2]).sum(axis=1, keepdims=True) - 0.3 * np.sum(trajs[:, 1::2] ** 2, axis=1, keepdims=True)) / L
+    log = []
+    real_minimize = ref_mod.minimize
+
+    def recording_minimize(fun, *a, **kw):
+        def wrapped(x):
+            v = fun(x)
+            log.append((np.array(x, dtype=np.float64).ravel().copy(), float(v)))
+            return v
+        kw["x0"] = np.ravel(kw["x0"])                  # (2, 1) -> (2,): see gen_lengthscale_cv
+        return real_minimize(wrapped, *a, **kw)
+
+    ref_mod.minimize = recording_minimize
+    try:
+        with quiet:
+            agt = agents.SSPMultiAgent(trajs, tys, n_agents=1, x_dim=xd, traj_len=L, ssp_dim=51, domain_bounds=bt, seed=3,
+                                       decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    finally:
+        ref_mod.minimize = real_minimize
+    out.update(cv_Ax=agt.ssp_x_spaces[0].phase_matrix, cv_At=agt.ssp_t_space.phase_matrix, cv_agent_sps=agt.agent_sps,
+               cv_trajs=trajs, cv_tys=tys, cv_bounds=bt, cv_eval_x=np.stack([x for x, _ in log]),
+               cv_eval_f=np.array([f for _, f in log]),
+               cv_result=np.concatenate([np.ravel(agt.ssp_x_spaces[0].length_scale)[:1], np.ravel(agt.ssp_t_space.length_scale)[:1]]),
+               cv_beta=np.float64(np.ravel(agt.blr.beta)[0]), cv_m=agt.blr.m)
+    np.savez_compressed(os.path.join(OUT, "multi_agent_sep.npz"), **out)
+    print("multi_agent_sep.npz written")
+
+
 def gen_lengthscale_cv(agents):
     """10. K-fold length-scale search of the trajectory agent (ssp_traj_agent.py:113-143): every objective evaluation
     scipy's L-BFGS-B makes inside the live reference is recorded, together with the result."""
@@ -198,6 +263,9 @@ def main():
     quiet = contextlib.redirect_stdout(io.StringIO())
     if "--only-acq-ascent" in sys.argv[1:]:
         gen_acq_ascent(sspspace, agents)
+        return
+    if "--only-multi-agent-sep" in sys.argv[1:]:
+        gen_multi_agent_sep(agents)
         return
     if "--only-multi-agent" in sys.argv[1:]:
         gen_multi_agent(agents)
@@ -351,6 +419,7 @@ def main():
                         ssps=ssps_o, set_pts=set_pts, x0=dec0, decoded=dec)
     gen_acq_ascent(sspspace, agents)
     gen_multi_agent(agents)
+    gen_multi_agent_sep(agents)
     gen_lengthscale_cv(agents)
     gen_lengthscale_gp(sspspace, agents)
     gen_rff(agents)

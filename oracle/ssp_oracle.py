@@ -346,31 +346,62 @@ def sp_vectors(domain_size, dim, rng) -> np.ndarray:
     return np.fft.ifft(fv, axis=-1).real
 
 
+def _per_agent(obj, n_agents):
+    """One entry per agent: a list / stacked array of per-agent items, or one shared item."""
+    if isinstance(obj, (list, tuple)):
+        assert len(obj) == n_agents
+        return list(obj)
+    return [obj] * n_agents
+
+
 def multi_agent_encode(x_phase_matrix, x_length_scale, timestep_ssps, agent_sps, x, traj_len, n_agents, x_dim):
-    """phi = unit(sum_i bind(a_i, sum_j bind(T_j, phi_x(x_ji)))), input layout (traj_len, n_agents, x_dim).
-    Ref: ssp_multi_agent.py:166-186 (agents sharing one x space)."""
+    """phi = unit(sum_i bind(a_i, sum_j bind(T_j, phi_x_i(x_ji)))), input layout (traj_len, n_agents, x_dim).
+    x_phase_matrix / x_length_scale: one shared space, or lists with one entry per agent (same_agt_x_space=False).
+    Ref: ssp_multi_agent.py:166-186."""
     x = np.atleast_2d(x)
     pts = x.reshape(-1, traj_len, n_agents, x_dim)
-    total = np.zeros((x.shape[0], x_phase_matrix.shape[0]))
+    As, lss = _per_agent(x_phase_matrix, n_agents), _per_agent(x_length_scale, n_agents)
+    total = np.zeros((x.shape[0], As[0].shape[0]))
     for i in range(n_agents):
         si = np.zeros_like(total)
         for j in range(traj_len):
-            si = si + bind(timestep_ssps[j, :], encode(x_phase_matrix, x_length_scale, pts[:, j, i, :]))
+            si = si + bind(timestep_ssps[j, :], encode(As[i], lss[i], pts[:, j, i, :]))
         total = total + bind(agent_sps[i, :], si)
     return total / np.linalg.norm(total, axis=-1, keepdims=True)
 
 
 def multi_agent_decode_from_set(ssp, timestep_ssps, agent_sps, sample_ssps, sample_points):
-    """Unbind tag and timestep, from-set decode each query.  Ref: ssp_multi_agent.py:195-208."""
+    """Unbind tag and timestep, from-set decode each query against the agent's own sample set (lists with one entry per
+    agent, or one shared set).  Ref: ssp_multi_agent.py:195-208."""
     ssp = np.atleast_2d(ssp)
     ssp = ssp / np.linalg.norm(ssp, axis=-1, keepdims=True)
     L, n_agents = timestep_ssps.shape[0], agent_sps.shape[0]
-    out = np.zeros((L, n_agents, sample_points.shape[1]))
+    sss, sps = _per_agent(sample_ssps, n_agents), _per_agent(sample_points, n_agents)
+    out = np.zeros((L, n_agents, sps[0].shape[1]))
     for i in range(n_agents):
         sspi = bind(invert(agent_sps[i:i + 1]), ssp)
         queries = bind(invert(timestep_ssps), sspi)
-        out[:, i, :] = decode_from_set(queries, sample_ssps, sample_points)
+        out[:, i, :] = decode_from_set(queries, sss[i], sps[i])
     return out.reshape(-1)
+
+
+def multi_agent_lengthscale_cv_loss(x_phase_matrix, t_phase_matrix, agent_sps, length_scale, xs, ys, traj_len, n_agents, x_dim):
+    """Objective of the multi-agent length-scale search at length_scale = (ls_x, ls_t) -- the reference reads entries 0 and 1
+    only and gives every agent's x space ls_x: K-fold (min(n, 50) folds) negative predictive log-likelihood of a fresh BLR
+    per fold on the L2-normalised encodings, timestep SSPs at linspace(0, L, L).  Ref: ssp_multi_agent.py:131-157."""
+    ls_x, ls_t = float(length_scale[0]), float(length_scale[1])
+    T = encode(t_phase_matrix, np.array([ls_t]), np.linspace(0, traj_len, traj_len).reshape(-1, 1))
+    As = _per_agent(x_phase_matrix, n_agents)
+    phis = multi_agent_encode(As, [ls_x * np.ones(x_dim)] * n_agents, T, agent_sps, xs, traj_len, n_agents, x_dim)
+    errors = []
+    for train, test in kfold_indices(xs.shape[0], min(xs.shape[0], 50)):
+        b = BLR(phis.shape[1])
+        b.update(phis[train], ys[train])
+        mu, var = b.predict(phis[test])
+        diff = ys[test].flatten() - mu.flatten()
+        loss = -0.5 * np.log(var) - np.divide(np.power(diff, 2), var)
+        errors.append(np.sum(-loss))
+    return np.sum(errors)
 
 
 # --------------------------------------------------------------------------

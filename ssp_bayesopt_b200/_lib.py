@@ -29,6 +29,7 @@ SIGNATURES = {
     "sspbo_ctx_destroy": (None, [_vp]),
     "sspbo_last_error": (C.c_char_p, [_vp]),
     "sspbo_space_set": (_i, [_vp, _pd, _pd, _i, _i]),
+    "sspbo_space_set_classes": (_i, [_vp, _pd, _pd, _i, _i, _i]),
     "sspbo_space_set_traj": (_i, [_vp, _pd, _i]),
     "sspbo_space_set_waypoints": (_i, [_vp, _pd, _pi, _i, _i]),
     "sspbo_space_dims": (_i, [_vp, _pi, _pi, _pi, _pi]),

@@ -144,8 +144,13 @@ class BayesianOptimization:
             if acq_candidates == 'grid':
                 acq_candidates = 'uniform'                           # a grid over L*x_dim axes is not meaningful
             waypoints = agt.traj_len * getattr(agt, 'n_agents', 1)
-            box = np.asarray(agt.domain_bounds, dtype=np.float64)[:agt.x_dim]
-            lo, hi = np.tile(box[:, 0], waypoints), np.tile(box[:, 1], waypoints)
+            box = np.asarray(agt.domain_bounds, dtype=np.float64)
+            per_row = getattr(agt, 'n_agents', 1) * agt.x_dim
+            if not getattr(agt, '_shared_x_space', True) and box.shape[0] >= per_row:   # one box per agent (rows i*x_dim ...)
+                lo, hi = np.tile(box[:per_row, 0], agt.traj_len), np.tile(box[:per_row, 1], agt.traj_len)
+            else:
+                box = box[:agt.x_dim]
+                lo, hi = np.tile(box[:, 0], waypoints), np.tile(box[:, 1], waypoints)
         if acq_candidates == 'grid':
             if candidates_per_dim is None:
                 candidates_per_dim = int(np.min([100, int(np.ceil((1e7 / agt.ssp_dim) ** (1 / self.data_dim)))]))

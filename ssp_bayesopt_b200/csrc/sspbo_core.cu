@@ -42,10 +42,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 template <typename XT>
 __device__ __forceinline__ void psi_entry(const XT* __restrict__ xrow, const double* __restrict__ A_turns,
                                           const double* __restrict__ tau_turns, int n, int K, int L, int k,
-                                          double& cs, double& sn) {
+                                          double& cs, double& sn, int ncls = 1) {
+    // ncls > 1: waypoint j reads the frequency table of class j % ncls (one x space per agent, A_turns = ncls x K x n)
     cs = 0.0; sn = 0.0;
-    const double* Ak = A_turns + (size_t)k * n;
-    for (int j = 0; j < L; ++j) {
+    for (int j = 0, cl = 0; j < L; ++j) {
+        const double* Ak = A_turns + ((size_t)cl * K + k) * n;
+        if (++cl == ncls) cl = 0;
         double t = tau_turns ? tau_turns[(size_t)j * K + k] : 0.0;
         for (int a = 0; a < n; ++a) t = fma(Ak[a], (double)xrow[j * n + a], t);
         t -= rint(t);                                   // exact range reduction to [-1/2, 1/2] turns
@@ -64,7 +66,7 @@ template <typename XT, int ENC_CPB>
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
          const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi,
-         int deriv_axis) {
+         int deriv_axis, int ncls) {
     // deriv_axis >= 0 (L == 1): d phi / d x_a instead of phi -- the spectrum exp(i theta_k) becomes i w_ka exp(i theta_k),
     // w_ka = A+_ka / l_a, i.e. (cos, sin) -> (-w sin, w cos) and no DC term (sspspace.py:300-305)
     extern __shared__ double psi_s[];                   // ENC_CPB x d
@@ -77,7 +79,7 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
             int c = i / K, k = i - c * K;
             if (base + c < N) {
                 double cs, sn;
-                psi_entry(x + (base + c) * nl, A_turns, tau_turns, n, K, L, k, cs, sn);
+                psi_entry(x + (base + c) * nl, A_turns, tau_turns, n, K, L, k, cs, sn, ncls);
                 if (deriv_axis >= 0) {
                     const double w = 6.283185307179586476925286766559 * A_turns[(size_t)k * n + deriv_axis];
                     const double c0 = cs;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(EX_THREADS)
 k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns,
                 const double* __restrict__ tau_turns, int n, int K, int L, double dc, const int* __restrict__ inv_perm,
                 const int* __restrict__ perm, const double* __restrict__ Sp, const double* __restrict__ mp, int RB,
-                double* __restrict__ part_q, double* __restrict__ part_mu) {
+                double* __restrict__ part_q, double* __restrict__ part_mu, int ncls) {
     extern __shared__ double psi_s[];                   // EX_G x d, permuted (rank) order
     __shared__ double red[EX_G][EX_THREADS / 32];
     const int d = 2 * K + 1, nl = n * L;
@@ -468,7 +470,7 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
             if (base + c < count) {
                 const int64_t row = base + c;
                 if (f == 0) cs = dc;
-                else psi_entry(x + row * nl, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
+                else psi_entry(x + row * nl, A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
             else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
@@ -531,7 +533,7 @@ k_exact_partial(const XT* __restrict__ x, int64_t N, const double* __restrict__ 
 // Everything one float64 pass needs (one context): k_exact_lowrank takes it by value, k_exact_lowrank_runs reads one per run
 struct ExactArgs {
     const void* x; sspbo_lr::CandDesc cand; const unsigned int* list; const unsigned long long* count_ptr; unsigned int cap;
-    const double *A_turns, *tau_turns; int n, K, L; double dc_value; int normalize;
+    const double *A_turns, *tau_turns; int n, K, L, ncls; double dc_value; int normalize;
     const int *inv_perm, *perm; const double* Vd; int r; const double* mp;
     double inv_beta, prior_var, lam, gamma_t; int64_t index0;
     float *mu_out, *var_out, *acq_out; unsigned long long* best;
@@ -545,7 +547,7 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
     const unsigned int* __restrict__ list = ea.list;
     const unsigned int cap = ea.cap;
     const double* __restrict__ A_turns = ea.A_turns; const double* __restrict__ tau_turns = ea.tau_turns;
-    const int n = ea.n, K = ea.K, L = ea.L, normalize = ea.normalize, r = ea.r;
+    const int n = ea.n, K = ea.K, L = ea.L, ncls = ea.ncls, normalize = ea.normalize, r = ea.r;
     const double dc_value = ea.dc_value, inv_beta = ea.inv_beta, prior_var = ea.prior_var, lam = ea.lam, gamma_t = ea.gamma_t;
     const int* __restrict__ inv_perm = ea.inv_perm; const int* __restrict__ perm = ea.perm;
     const double* __restrict__ Vd = ea.Vd; const double* __restrict__ mp = ea.mp;
@@ -597,8 +599,8 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
             double cs = 0.0, sn = 0.0;
             if (base + c < count) {
                 if (f == 0) cs = dc_value;
-                else if (cand.mode != 0) psi_entry(xs_gen[c], A_turns, tau_turns, n, K, L, f - 1, cs, sn);
-                else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn);
+                else if (cand.mode != 0) psi_entry(xs_gen[c], A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
+                else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
             else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
@@ -1179,20 +1181,29 @@ extern "C" int sspbo_timing_read(sspbo_ctx* ctx, double* scorer_ms, double* flag
 static int build_p32_tables(sspbo_ctx* ctx);
 
 extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const double* inv_ls, int K, int n) {
+    return sspbo_space_set_classes(ctx, A_plus, inv_ls, K, n, 1);
+}
+
+/* n_cls phase matrices of one shape (A_plus: n_cls x K x n, inv_ls: n_cls x n): waypoint j of a candidate row is encoded with
+ * table j % n_cls -- SSPMultiAgent with one RandomSSPSpace per agent (ssp_multi_agent.py:58-66, same_agt_x_space=False), rows
+ * laid out (traj_len, n_agents, x_dim).  Followed by sspbo_space_set_waypoints with L a multiple of n_cls. */
+extern "C" int sspbo_space_set_classes(sspbo_ctx* ctx, const double* A_plus, const double* inv_ls, int K, int n, int n_cls) {
     if (!ctx) return SSPBO_EINVAL;
     if (!A_plus || !inv_ls || K < 1 || n < 1 || n > 16) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set: need K>=1, 1<=n<=16");
+    if (n_cls < 1 || n_cls > 16) SSPBO_FAIL(ctx, SSPBO_EINVAL, "space_set_classes: 1 <= n_cls <= 16");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->K) SSPBO_CUDA(ctx, cudaDeviceSynchronize());     // re-programming: the old tables may still be read on other streams
     if (K != ctx->K || !ctx->has_factor) { free_blr(ctx); sspbo_umma_release(ctx); }
     if (K != ctx->K) ctx->enc_K = 0;
     const int d = 2 * K + 1;
-    std::vector<double> At((size_t)K * n);
-    std::vector<float> Af((size_t)K * n);
+    std::vector<double> At((size_t)n_cls * K * n);
+    std::vector<float> Af(At.size());
     double mx = 0.0;
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < n_cls * K; ++k) {
+        const double* il = inv_ls + (size_t)(k / K) * n;
         double rs = 0.0;
         for (int a = 0; a < n; ++a) {
-            double t = A_plus[(size_t)k * n + a] * inv_ls[a] / kTwoPi;
+            double t = A_plus[(size_t)k * n + a] * il[a] / kTwoPi;
             At[(size_t)k * n + a] = t; Af[(size_t)k * n + a] = (float)t; rs += fabs(t);
         }
         mx = fmax(mx, rs);
@@ -1204,8 +1215,8 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
         tw[i].x = cospi(frac); tw[i].y = sinpi(frac);
     }
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->A_turns, (size_t)K * n))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A_turns_f32, (size_t)K * n))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->A_turns, At.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->A_turns_f32, At.size()))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->twiddle, (size_t)d))) return rc;
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns, At.data(), At.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A_turns_f32, Af.data(), Af.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1214,18 +1225,20 @@ extern "C" int sspbo_space_set(sspbo_ctx* ctx, const double* A_plus, const doubl
     {   // frequency table of the tcgen05 scorer: row f = A_turns of frequency f (f = 0: DC, f > K: padding) -> zeros
         int kc, bn, nc, nj;
         sspbo_umma_dims(K, &kc, &bn, &nc, &nj);
-        std::vector<long long> op((size_t)(kc / 2) * n, 0ll);
+        std::vector<long long> op((size_t)n_cls * (kc / 2) * n, 0ll);       // one table per class, back to back
         ctx->umma_range_ok = true;
-        for (int f = 1; f <= K; ++f)
-            for (int a = 0; a < n; ++a) {
-                double t = At[(size_t)(f - 1) * n + a];
-                if (!(fabs(t) < 2147483648.0)) { ctx->umma_range_ok = false; t = 0.0; }
-                op[(size_t)f * n + a] = llrint(t * 4294967296.0);                  // Q31.32 turns per unit of x
-            }
+        for (int c = 0; c < n_cls; ++c)
+            for (int f = 1; f <= K; ++f)
+                for (int a = 0; a < n; ++a) {
+                    double t = At[((size_t)c * K + f - 1) * n + a];
+                    if (!(fabs(t) < 2147483648.0)) { ctx->umma_range_ok = false; t = 0.0; }
+                    op[((size_t)c * (kc / 2) + f) * n + a] = llrint(t * 4294967296.0);   // Q31.32 turns per unit of x
+                }
         if ((rc = dev_alloc(ctx, &ctx->Aq_op, op.size()))) return rc;
         SSPBO_CUDA(ctx, cudaMemcpy(ctx->Aq_op, op.data(), op.size() * sizeof(long long), cudaMemcpyHostToDevice));
     }
-    ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
+    ctx->K = K; ctx->n = n; ctx->d = d; ctx->L = 1; ctx->n_cls = n_cls; ctx->dp = sspbo_pad64(d); ctx->max_turns = mx;
+    if (n_cls > 1) { ctx->L = n_cls; ctx->dc = (double)n_cls; ctx->normalize = false; }   // one waypoint per table until set_waypoints
     double amax = 0.0;
     for (size_t i = 0; i < At.size(); ++i) amax = fmax(amax, fabs(At[i]));
     ctx->a_absmax = amax;
@@ -1247,10 +1260,12 @@ static int build_p32_tables(sspbo_ctx* ctx) {
         if (ctx->max_turns * ctx->x_absmax <= 15.5) {           // + half a turn of timestep phase in trajectory mode
             int kc, bn, nc, nj;
             sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
-            std::vector<float> op((size_t)(kc / 2) * ctx->n, 0.f);
-            for (int f = 1; f <= ctx->K; ++f)
-                for (int a = 0; a < ctx->n; ++a)
-                    op[(size_t)f * ctx->n + a] = (float)(ctx->host_A_turns[(size_t)(f - 1) * ctx->n + a] * kTwoPi);
+            const int ncls = ctx->n_cls, nfq = kc / 2;
+            std::vector<float> op((size_t)ncls * nfq * ctx->n, 0.f);
+            for (int c = 0; c < ncls; ++c)
+                for (int f = 1; f <= ctx->K; ++f)
+                    for (int a = 0; a < ctx->n; ++a)
+                        op[((size_t)c * nfq + f) * ctx->n + a] = (float)(ctx->host_A_turns[((size_t)c * ctx->K + f - 1) * ctx->n + a] * kTwoPi);
             int rc;
             if ((rc = dev_alloc(ctx, &ctx->Af_op, op.size()))) return rc;
             SSPBO_CUDA(ctx, cudaMemcpy(ctx->Af_op, op.data(), op.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1258,7 +1273,7 @@ static int build_p32_tables(sspbo_ctx* ctx) {
             // scorer of many runs reads it from global memory instead of staging one table per launch in shared memory
             std::vector<float> gen(op.size(), 0.f);
             const int NFq = 16;
-            for (int f = 0; f < kc / 2; ++f)
+            for (int f = 0; f < ncls * nfq; ++f)                              // (nfq is a multiple of 16: blocks never straddle classes)
                 for (int a = 0; a < ctx->n; ++a)
                     gen[((size_t)(f / NFq) * ctx->n + a) * NFq + (f % NFq)] = op[(size_t)f * ctx->n + a];
             if ((rc = dev_alloc(ctx, &ctx->Af_gen, gen.size()))) return rc;
@@ -1281,13 +1296,14 @@ static int build_p32_tables(sspbo_ctx* ctx) {
     if (fa < 0 || err + ldexp(1.0, -23) > ldexp(1.0, -20)) return SSPBO_OK;
     int kc, bn, nc, nj;
     sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
-    std::vector<int> op((size_t)(kc / 2) * ctx->n, 0);
-    for (int f = 1; f <= ctx->K; ++f)
-        for (int a = 0; a < ctx->n; ++a)
-        {
-            long long q = llrint(ctx->host_A_turns[(size_t)(f - 1) * ctx->n + a] * ldexp(1.0, fa));
-            op[(size_t)f * ctx->n + a] = (int)(q > 2147483647ll ? 2147483647ll : (q < -2147483647ll ? -2147483647ll : q));
-        }
+    std::vector<int> op((size_t)ctx->n_cls * (kc / 2) * ctx->n, 0);
+    for (int c = 0; c < ctx->n_cls; ++c)
+        for (int f = 1; f <= ctx->K; ++f)
+            for (int a = 0; a < ctx->n; ++a)
+            {
+                long long q = llrint(ctx->host_A_turns[((size_t)c * ctx->K + f - 1) * ctx->n + a] * ldexp(1.0, fa));
+                op[((size_t)c * (kc / 2) + f) * ctx->n + a] = (int)(q > 2147483647ll ? 2147483647ll : (q < -2147483647ll ? -2147483647ll : q));
+            }
     int rc;
     if ((rc = dev_alloc(ctx, &ctx->A32_op, op.size()))) return rc;
     SSPBO_CUDA(ctx, cudaMemcpy(ctx->A32_op, op.data(), op.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1312,6 +1328,7 @@ extern "C" int sspbo_space_set_waypoints(sspbo_ctx* ctx, const double* tau_host,
     if (!ctx) return SSPBO_EINVAL;
     if (ctx->K == 0) SSPBO_FAIL(ctx, SSPBO_ESTATE, "space_set_traj before space_set");
     if (L < 1 || L > 64) SSPBO_FAIL(ctx, SSPBO_EINVAL, "traj length must be in [1, 64]");
+    if (L % ctx->n_cls) SSPBO_FAIL(ctx, SSPBO_EINVAL, "waypoints per row (%d) must be a multiple of the %d frequency tables", L, ctx->n_cls);
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32); dev_free(&ctx->tauq_op); dev_free(&ctx->tauf_op);
     ctx->L = L;
@@ -1413,7 +1430,7 @@ static int encode_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, 
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_encode<XT, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         k_encode<XT, CPB><<<grid, ENC_THREADS, smem, st>>>((const XT*)x, N, ctx->A_turns, ctx->tau_turns, ctx->twiddle,     \
                                                            ctx->n, ctx->K, ctx->L, ctx->dc, ctx->normalize ? 1 : 0, phi_out, \
-                                                           deriv_axis);                                                   \
+                                                           deriv_axis, ctx->n_cls);                                       \
     } while (0)
     if (x_dtype == SSPBO_F32) {
         if (cpb == ENC_CPB_SMALL) SSPBO_ENC_LAUNCH(float, ENC_CPB_SMALL); else SSPBO_ENC_LAUNCH(float, ENC_CPB_BATCH);
@@ -1476,7 +1493,7 @@ extern "C" int sspbo_encode_f32(sspbo_ctx* ctx, const void* x, int x_dtype, int6
     cudaStream_t st = (cudaStream_t)stream;
     int kc, bn, nc, nj, rc;
     sspbo_umma_dims(ctx->K, &kc, &bn, &nc, &nj);
-    if (ctx->n > 8 || !ctx->umma_range_ok || nc > 8 || (ctx->L != 1 && (ctx->n > 3 || !ctx->tauq_op)) || ctx->normalize)
+    if (ctx->n > 8 || !ctx->umma_range_ok || nc > 8 || (ctx->L != 1 && (ctx->n > 3 || !ctx->tauq_op)) || ctx->normalize || ctx->n_cls != 1)
         SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "encode_f32: shape outside the tcgen05 kernel (n=%d, d=%d, L=%d)", ctx->n, ctx->d, ctx->L);
     if (!ctx->blr_ready || !ctx->has_factor) {           // geometry normally set by blr_init
         ctx->KC_pad = kc; ctx->BN = bn; ctx->n_chunks = nc; ctx->NJ_pad = nj;
@@ -1824,7 +1841,7 @@ extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, d
 static void fill_exact_args(const sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, int64_t index0, double lam, double gamma_t,
                             float* mu, float* var, float* acq, unsigned long long* best, bool full, ExactArgs* ea) {
     ea->x = cand.x; ea->cand = cand; ea->list = ctx->flag_idx; ea->count_ptr = ctx->stats + SSPBO_STAT_CUR; ea->cap = SSPBO_FLAG_CAP;
-    ea->A_turns = ctx->A_turns; ea->tau_turns = ctx->tau_turns; ea->n = ctx->n; ea->K = ctx->K; ea->L = ctx->L;
+    ea->A_turns = ctx->A_turns; ea->tau_turns = ctx->tau_turns; ea->n = ctx->n; ea->K = ctx->K; ea->L = ctx->L; ea->ncls = ctx->n_cls;
     ea->dc_value = ctx->dc; ea->normalize = ctx->normalize ? 1 : 0; ea->inv_perm = ctx->inv_perm; ea->perm = ctx->perm;
     ea->Vd = full ? ctx->Sp : ctx->Vd; ea->r = full ? ctx->d : ctx->lr_rank; ea->mp = ctx->mp;
     ea->inv_beta = 1.0 / ctx->beta; ea->prior_var = 1.0 / ctx->alpha; ea->lam = lam; ea->gamma_t = gamma_t; ea->index0 = index0;
@@ -1885,11 +1902,11 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     if (x_dtype == SSPBO_F32) {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_exact_partial<float><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const float*)x, N, ctx->A_turns,
-            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu, ctx->n_cls);
     } else {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_exact_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_exact_partial<double><<<dim3(gx, RB), EX_THREADS, smem, st>>>((const double*)x, N, ctx->A_turns,
-            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu);
+            ctx->tau_turns, ctx->n, ctx->K, ctx->L, ctx->dc, ctx->inv_perm, ctx->perm, ctx->Sp, ctx->mp, RB, part_q, part_mu, ctx->n_cls);
     }
     SSPBO_LAUNCH_CHECK(ctx);
     const int fb = (int)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024);

@@ -23,8 +23,9 @@ struct sspbo_ctx {
 
     // ---- space ----
     int K = 0, n = 0, d = 0, L = 1;
+    int n_cls = 1;                   // frequency tables (one x space per agent of a multi-agent encoder): waypoint j reads table j % n_cls
     int dp = 0;                      // d padded to a multiple of 64 (operand leading dimension)
-    double* A_turns = nullptr;       // K x n : A+ * inv_ls / (2 pi)  -> theta in turns (float64)
+    double* A_turns = nullptr;       // n_cls x K x n : A+ * inv_ls / (2 pi)  -> theta in turns (float64)
     float*  A_turns_f32 = nullptr;   // same, float32
     double* tau_turns = nullptr;     // L x K : trajectory time phases in turns (nullptr when L == 1)
     float*  tau_turns_f32 = nullptr;

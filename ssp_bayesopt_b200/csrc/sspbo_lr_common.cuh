@@ -47,6 +47,7 @@ struct Params {
     const long long* Aq_op; const int* A32_op; const float* Af_op; const float* mscale; double x_scale; float x_absmax;
     // trajectory mode: L waypoints per candidate; per-timestep phase offsets (L x KC_pad/2): Q0.64 turns / float32 radians
     int L; const unsigned long long* tauq; const float* tauf; float nrm_scale, nrm_offset;   // |phi|^2 = nrm_scale * sum(C^2 + S^2) - nrm_offset
+    int n_cls;                          // frequency tables staged back to back; waypoint j reads table j % n_cls (one x space per agent)
     int KC_pad, BN, n_chunks, n_kb, nb;
     int na, acc_cols, n_bufs;           // A ring slots; columns per accumulator buffer; buffers alternating (1 or 2)
     int split_issue;                    // BN > 128: next k-block's barrier waits between the two halves of the MMAs
@@ -183,7 +184,9 @@ __device__ __forceinline__ void gen_half(const Params& p, const uint8_t* tables,
         for (int i = 0; i < NF; ++i) { cs[i] = 0.f; sn[i] = 0.f; }
         const int nf = p.KC_pad >> 1, fbase = kb * 32 + half * NF;
         const void* xp = p.cand.x; const int x_f64 = p.cand.x_f64;
-        for (int j = 0; j < p.L; ++j) {
+        for (int j = 0, cl = 0; j < p.L; ++j) {
+            const int fcls = cl * nf + fbase;                 // first frequency of this block in the waypoint's table
+            if (++cl == p.n_cls) cl = 0;
             if constexpr (PH == 2) {
                 float xf[NDIM];
 #pragma unroll
@@ -197,7 +200,7 @@ __device__ __forceinline__ void gen_half(const Params& p, const uint8_t* tables,
                     for (int a = 0; a < NDIM; ++a) oor |= !(fabsf(xf[a]) <= p.x_absmax);
                     if (oor) atomicAdd(p.stats + SSPBO_STAT_OOR, 1ull);
                 }
-                const float* Afblk = (const float*)tables + (size_t)fbase * NDIM;      // [axis][NF]
+                const float* Afblk = (const float*)tables + (size_t)fcls * NDIM;       // [axis][NF]
                 const float* tf = p.tauf + (size_t)j * nf + fbase;
 #pragma unroll
                 for (int i = 0; i < NF; ++i) {
@@ -216,7 +219,7 @@ __device__ __forceinline__ void gen_half(const Params& p, const uint8_t* tables,
                     if (g0 < N) v0 = x_f64 ? __ldg((const double*)xp + o) : (double)__ldg((const float*)xp + o);
                     x0[a] = (unsigned long long)__double2ll_rn(v0 * 4294967296.0);
                 }
-                const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)fbase * NDIM;
+                const unsigned long long* Ablk = (const unsigned long long*)Aq_s + (size_t)fcls * NDIM;
                 const unsigned long long* tq = p.tauq + (size_t)j * nf + fbase;
 #pragma unroll
                 for (int i = 0; i < NF; ++i) {
@@ -301,13 +304,13 @@ __device__ __forceinline__ void load_tables(const Params& p, uint8_t* tables, in
         // axis-major inside every block of NF frequencies: one LDS.128 feeds four independent multiply-add chains
         int* A32_s = (int*)tables;
         const int* src = PH == 1 ? p.A32_op : (const int*)p.Af_op;
-        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += nthreads) {
-            const int f = i / NDIM, a = i - f * NDIM;
+        for (int i = threadIdx.x; i < p.n_cls * (p.KC_pad / 2) * NDIM; i += nthreads) {
+            const int f = i / NDIM, a = i - f * NDIM;         // (KC_pad / 2 is a multiple of NF: blocks never straddle tables)
             A32_s[((f / NF) * NDIM + a) * NF + (f % NF)] = src[i];
         }
     } else {
         long long* Aq_s = (long long*)tables;
-        for (int i = threadIdx.x; i < (p.KC_pad / 2) * NDIM; i += nthreads) Aq_s[i] = p.Aq_op[i];
+        for (int i = threadIdx.x; i < p.n_cls * (p.KC_pad / 2) * NDIM; i += nthreads) Aq_s[i] = p.Aq_op[i];
     }
 }
 

@@ -88,7 +88,7 @@ k_score_f8(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     const int b_slot_bytes = 2 * b_tile_bytes;
     uint8_t* b_ring = smem;
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
-    float* mp_s = (float*)((long long*)tables + (size_t)(p.KC_pad / 2) * NDIM);     // m' in operand order (KC_pad)
+    float* mp_s = (float*)((long long*)tables + (size_t)p.n_cls * (p.KC_pad / 2) * NDIM);   // m' in operand order (KC_pad)
     // partial sums of the tiles in flight, [NRM_DEPTH tiles][GEN_W warps of a quadrant][128 rows]: mu, and |phi|^2 in trajectory mode
     float* mu_part = mp_s + p.KC_pad;
     float* nrm_part = mu_part + NRM_DEPTH * GEN_W * BM;
@@ -550,7 +550,7 @@ struct F8State {
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
-    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
+    return (size_t)ctx->n_cls * (ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (size_t)ctx->KC_pad * sizeof(float) +
            (ctx->L != 1 ? 2 : 1) * NRM_DEPTH * GEN_W * BM * sizeof(float) + (2 * NA_F8 + 2 * MAX_NB + 4) * 8 + 16;
 }
 

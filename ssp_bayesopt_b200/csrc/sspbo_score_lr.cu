@@ -58,7 +58,7 @@ k_score_lr(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ C
     uint8_t* tables = b_ring + (size_t)p.nb * b_slot_bytes;
     long long* Aq_s = (long long*)tables;                                   // (KC_pad/2) x NDIM (int32 in the P32 path)
     // |phi|^2 partial sums of the tiles in flight, [NRM_DEPTH tiles][GEN_W warps of a quadrant][128 rows] (trajectory mode)
-    float* nrm_part = (float*)(Aq_s + (size_t)(p.KC_pad / 2) * NDIM);
+    float* nrm_part = (float*)(Aq_s + (size_t)p.n_cls * (p.KC_pad / 2) * NDIM);
     uint64_t* bars = (uint64_t*)(nrm_part + (TRAJ ? NRM_DEPTH * GEN_W * BM : 0));
     // barrier map: a_full[NA] a_empty[NA] b_full[nb] b_empty[nb] tmem_full[2] tmem_empty[2]
     const uint32_t bar0 = smem_u32(bars);
@@ -476,7 +476,7 @@ struct LrState {
 };
 
 size_t table_bytes(const sspbo_ctx* ctx) {
-    return (size_t)(ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (ctx->L != 1 ? NRM_DEPTH * GEN_W * BM * sizeof(float) : 0) +
+    return (size_t)ctx->n_cls * (ctx->KC_pad / 2) * ctx->n * sizeof(long long) + (ctx->L != 1 ? NRM_DEPTH * GEN_W * BM * sizeof(float) : 0) +
            (2 * NA_MAX + 2 * MAX_NB + 4) * 8 + 16;
 }
 
@@ -560,7 +560,7 @@ void sspbo_lr_fill_common(const sspbo_ctx* ctx, const CandDesc& cand, int64_t N,
     p.flag_below = (float)(SSPBO_LR_FLAG_FRACTION / ctx->alpha);
     p.mu = mu; p.var = var; p.acq = acq; p.best = best;
     p.flag_idx = ctx->flag_idx; p.stats = ctx->stats; p.flag_cap = SSPBO_FLAG_CAP;
-    p.L = ctx->L; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
+    p.L = ctx->L; p.n_cls = ctx->n_cls; p.tauq = (const unsigned long long*)ctx->tauq_op; p.tauf = ctx->tauf_op;
     {   // |phi|^2 = (1/d) (psi_0^2 + 2 sum_{k>=1} (C_k^2 + S_k^2)); the generators sum C^2 + S^2 over every operand frequency,
         // including the DC term (= dc^2, weight 1 not 2) and the padding frequencies (= L^2 each, weight 0)
         const double d = (double)ctx->d, L2 = (double)ctx->L * ctx->L;

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(ST_THREADS)
 k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* __restrict__ A_turns,
              const double* __restrict__ tau_turns, int n, int K, int L, int dp, const float* __restrict__ Rt,
              const float* __restrict__ mp, float dc, int normalize, float inv_beta, float lam, float gamma_t, float* __restrict__ mu_out,
-             float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best) {
+             float* __restrict__ var_out, float* __restrict__ acq_out, unsigned long long* __restrict__ best, int ncls) {
     extern __shared__ __align__(16) float smem[];
     float* psiT = smem;                                   // dp x ST_TC, k-major
     float* red = smem + (size_t)dp * ST_TC;               // ST_TC x 8 (warps)  then  ST_TC x 16 (mu slices)
@@ -35,8 +35,9 @@ k_score_simt(const XT* __restrict__ x, int64_t N, int64_t index0, const double* 
             float cs = 0.f, sn = 0.f;
             if (base + c < N) {
                 const XT* xr = x + (base + c) * nl;
-                const double* Ak = A_turns + (size_t)k * n;
-                for (int j = 0; j < L; ++j) {
+                for (int j = 0, cl = 0; j < L; ++j) {
+                    const double* Ak = A_turns + ((size_t)cl * K + k) * n;      // waypoint j reads frequency table j % ncls
+                    if (++cl == ncls) cl = 0;
                     double t = tau_turns ? tau_turns[(size_t)j * K + k] : 0.0;
                     for (int a = 0; a < n; ++a) t = fma(Ak[a], (double)xr[j * n + a], t);
                     float tr = (float)(t - rint(t));
@@ -145,12 +146,12 @@ int sspbo_score_simt_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t 
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_score_simt<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_simt<float><<<blocks, ST_THREADS, smem, st>>>((const float*)x, N, index0, ctx->A_turns, ctx->tau_turns, ctx->n,
                                                               ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, (float)ctx->dc, ctx->normalize ? 1 : 0, inv_beta, lam,
-                                                              gamma_t, mu, var, acq, best);
+                                                              gamma_t, mu, var, acq, best, ctx->n_cls);
     } else {
         SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_score_simt<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_simt<double><<<blocks, ST_THREADS, smem, st>>>((const double*)x, N, index0, ctx->A_turns, ctx->tau_turns, ctx->n,
                                                                ctx->K, ctx->L, ctx->dp, ctx->Rt_f32, ctx->mp_f32, (float)ctx->dc, ctx->normalize ? 1 : 0, inv_beta, lam,
-                                                               gamma_t, mu, var, acq, best);
+                                                               gamma_t, mu, var, acq, best, ctx->n_cls);
     }
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;

@@ -652,7 +652,7 @@ int sspbo_make_map_f16(sspbo_ctx* ctx, void* map, const void* base, int KC_pad, 
 int sspbo_score_umma_supported(const sspbo_ctx* ctx) {
     if (!ctx->has_factor || ctx->n > MAX_N || ctx->K < 1 || !ctx->umma_range_ok || ctx->n_chunks > 8) return 0;
     if (ctx->L != 1 && (ctx->n > MAX_TRAJ_N || ctx->L > 64 || !ctx->tauq_op)) return 0;
-    if (ctx->normalize) return 0;                  // |phi| is not formed by the dense-factor kernel
+    if (ctx->normalize || ctx->n_cls != 1) return 0;   // |phi| is not formed by the dense-factor kernel; one frequency table
     int major = 0;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device) != cudaSuccess || major != 10) return 0;
     int max_smem = 0;

@@ -107,6 +107,23 @@ class DeviceEngine:
         self._check(rc, "sspbo_space_set")
         self.d, self.K, self.n, self.L = d, K, n, 1
 
+    def set_space_classes(self, phase_matrices, length_scales) -> None:
+        """One phase matrix per agent (all (d, n)): waypoint j of a row is encoded with matrix j % len(phase_matrices)
+        (SSPMultiAgent with per-agent x spaces, ssp_multi_agent.py:58-66).  Followed by set_waypoints."""
+        As = [np.asarray(A, dtype=np.float64) for A in phase_matrices]
+        d, n = As[0].shape
+        if d % 2 != 1 or d < 3 or any(A.shape != (d, n) for A in As):
+            raise ValueError("phase matrices must share one (2K+1, n) shape")
+        K = (d - 1) // 2
+        a_plus = np.ascontiguousarray(np.stack([A[1:K + 1] for A in As]))
+        inv_ls = np.ascontiguousarray(np.stack([1.0 / np.asarray(ls, dtype=np.float64).reshape(-1) * np.ones(n)
+                                                for ls in length_scales]))
+        assert inv_ls.shape == (len(As), n)
+        rc = self.lib.sspbo_space_set_classes(self._ctx, a_plus.ctypes.data_as(_lib._pd), inv_ls.ctypes.data_as(_lib._pd),
+                                              K, n, len(As))
+        self._check(rc, "sspbo_space_set_classes")
+        self.d, self.K, self.n, self.L = d, K, n, (len(As) if len(As) > 1 else 1)
+
     def set_xbound(self, x_absmax: float) -> None:
         """Declared bound on |x| of every candidate coordinate (max |domain_bounds|); 0 = unknown."""
         self._check(self.lib.sspbo_space_set_xbound(self._ctx, float(x_absmax)), "sspbo_space_set_xbound")

@@ -432,3 +432,135 @@ def test_eval_between_chunked_selection_keeps_the_running_key(pkg):
     assert (s, idx) == (s_all, idx_all)
     ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, 0.25 * np.ones(6), xc[100:400].astype(np.float64)), ref, 10.0, 0.0)
     assert_scores_close(mu, acq, ref_mu, ref_acq)
+
+
+# ------------------------------------------------------------------ multi-agent: one x space per agent, length-scale search
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["s3", "s2"])
+def test_multi_agent_per_agent_spaces_golden(pkg, golden, tag):
+    """SSPMultiAgent(same_agt_x_space=False): one RandomSSPSpace per agent on its own rows of domain_bounds
+    (ssp_multi_agent.py:58-66), one frequency table per agent on the device (sspbo_space_set_classes).  Against the live
+    reference (tests/golden/multi_agent_sep.npz): phase matrices, normalised encode, posterior, eval through every engine
+    that forms |phi| and both operand formats, per-agent decode."""
+    from ssp_bayesopt_b200 import _lib
+    g = golden("multi_agent_sep.npz")
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g[f"{tag}_dims"])
+    agt = pkg.SSPMultiAgent(g[f"{tag}_trajs"], g[f"{tag}_tys"], n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=ssp_dim,
+                            domain_bounds=g[f"{tag}_bounds"], length_scale=0.8, time_length_scale=1.2, seed=seed,
+                            same_agt_x_space=False, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    for i in range(n_agents):
+        assert np.array_equal(agt.ssp_x_spaces[i].phase_matrix, g[f"{tag}_Ax"][i])
+        assert np.array_equal(np.asarray(agt.ssp_x_spaces[i].domain_bounds), g[f"{tag}_bounds"][i * xd:(i + 1) * xd])
+    np.testing.assert_allclose(agt.agent_sps, g[f"{tag}_agent_sps"], atol=1e-15)
+    phi = agt.encode(g[f"{tag}_xc"])
+    np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=5e-13)
+    assert abs(float(np.ravel(agt.blr.beta)[0]) - float(g[f"{tag}_beta"])) <= 1e-12 * float(g[f"{tag}_beta"])
+    assert rel(agt.blr.m, g[f"{tag}_m"]) < 1e-9 and rel(agt.blr.S, g[f"{tag}_S"]) < 1e-9
+    mu, var, acq = agt.eval(g[f"{tag}_xc"])                                   # 40 candidates: exact float64 engine
+    assert_scores_close(mu, acq, g[f"{tag}_mu"], g[f"{tag}_acq"])
+    np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=RTOL_SCORE)
+    eng = agt._scoring_engine()
+    for code, name, fmt in ((_lib.ENGINE_SIMT, "simt", -1), (_lib.ENGINE_UMMA_LR, "umma-lowrank", 0),
+                            (_lib.ENGINE_UMMA_LR, "umma-lowrank", 1)):
+        for ph in (1, 0):                                                     # float32 / Q31.32 phase arithmetic
+            eng.set_policy(phase32=ph, operand_format=fmt)
+            _, (mu, var, acq) = eng.score(g[f"{tag}_xc"], 5.0, 0.0, want_outputs=True, engine=code)
+            assert eng.last_engine() == name
+            assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), g[f"{tag}_mu"], g[f"{tag}_acq"])
+            np.testing.assert_allclose(var.double().cpu().numpy(), g[f"{tag}_var"], rtol=RTOL_SCORE)
+    eng.set_policy(phase32=1, operand_format=-1)
+    with pytest.raises(_lib.SspboError):                                      # the dense-factor kernel: one table, no |phi|
+        eng.score(g[f"{tag}_xc"], 5.0, 0.0, engine=_lib.ENGINE_UMMA)
+    assert np.array_equal(agt.decode(phi[:1]), g[f"{tag}_decoded"])
+
+
+@pytest.mark.gpu
+def test_multi_agent_per_agent_spaces_tcgen05_and_driver(pkg):
+    """A larger candidate set over per-agent spaces (d = 301, 3 agents x 6 timesteps): AUTO takes the low-rank tcgen05 engine
+    in trajectory mode; scores and the arg-max against the oracle restatement (ssp_multi_agent.py:166-186), distinct spaces
+    passed as a list; a context re-programmed from shared to per-agent tables; then the BO driver."""
+    from ssp_bayesopt_b200 import _lib
+    n_agents, L, xd, ssp_dim, N = 3, 6, 2, 301, 3000
+    bounds = np.array([[-2.0, 2.0], [-2.0, 2.0], [-1.0, 3.0], [0.0, 2.5], [-3.0, 1.0], [-2.0, 2.0]])
+    lo, hi = np.tile(bounds[:, 0], L), np.tile(bounds[:, 1], L)
+    rng = np.random.default_rng(23)
+    trajs = rng.uniform(lo, hi, (14, L * n_agents * xd))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / (L * n_agents)
+    spaces = [pkg.RandomSSPSpace(xd, ssp_dim=ssp_dim, domain_bounds=bounds[i * xd:(i + 1) * xd], length_scale=1, rng=40 + i)
+              for i in range(n_agents)]
+    agt = pkg.SSPMultiAgent(trajs, tys, n_agents=n_agents, x_dim=xd, traj_len=L, ssp_x_spaces=spaces, domain_bounds=bounds,
+                            length_scale=0.7, time_length_scale=1.2, seed=1, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    As = [sp.phase_matrix for sp in spaces]
+    T = orc.traj_timestep_ssps(agt.ssp_t_space.phase_matrix, np.array([1.2]), L)
+    tags = orc.sp_vectors(n_agents, As[0].shape[0], 1)
+    enc = lambda x: orc.multi_agent_encode(As, [0.7 * np.ones(2)] * n_agents, T, tags, x, L, n_agents, xd)
+    np.testing.assert_allclose(agt.encode(trajs[:5]), enc(trajs[:5]), atol=5e-13)
+    ref = orc.BLR(As[0].shape[0])
+    ref.update(enc(trajs), tys)
+    xc = rng.uniform(lo, hi, (N, L * n_agents * xd)).astype(np.float32)
+    xc[:4] = trajs[:4].astype(np.float32)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(enc(xc.astype(np.float64)), ref, 5.0, 0.0)
+    ref_score = ref_mu.ravel() + ref_acq
+    eng = agt._scoring_engine()
+    for ph in (1, 0):
+        for fmt in (0, 1):
+            eng.set_policy(phase32=ph, operand_format=fmt)
+            _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True)
+            assert eng.last_engine() == "umma-lowrank"
+            assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+            np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+            srt = np.sort(ref_score)[::-1]
+            if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
+                assert eng.best()[1] == int(np.argmax(ref_score))
+    eng.set_policy(phase32=1, operand_format=-1)
+    # the rows of a candidate are (timestep, agent): swapping two agents' coordinates changes the encoding
+    sw = trajs[:3].reshape(3, L, n_agents, xd)[:, :, [1, 0, 2], :].reshape(3, -1)
+    assert np.max(np.abs(agt.encode(sw) - agt.encode(trajs[:3]))) > 1e-3
+    f = lambda x: float(-np.sum(np.asarray(x) ** 2) / (L * n_agents))
+    opt = pkg.BayesianOptimization(f=lambda x, info=None: f(x), bounds=bounds)
+    opt.maximize(init_points=(trajs, tys), n_iter=3, agent_type="ssp-multi", n_agents=n_agents, x_dim=xd, traj_len=L,
+                 ssp_dim=ssp_dim, length_scale=0.8, time_length_scale=1.2, seed=1, same_agt_x_space=False,
+                 decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0, n_candidates=20000)
+    assert opt.xs.shape == (17, L * n_agents * xd)
+    assert np.all(opt.xs >= lo - 1e-9) and np.all(opt.xs <= hi + 1e-9)
+
+
+@pytest.mark.gpu
+def test_multi_agent_length_scale_search(pkg, golden):
+    """SSPMultiAgent without `length_scale`: the K-fold search of ssp_multi_agent.py:131-164 with encodings and Gram matrix
+    from the device, against every objective evaluation recorded inside the live reference (one agent, the only case the
+    reference's own scipy call accepts); then three agents with their own spaces, objective against the oracle."""
+    g = golden("multi_agent_sep.npz")
+    agt = pkg.SSPMultiAgent(g["cv_trajs"], g["cv_tys"], n_agents=1, x_dim=2, traj_len=4, ssp_dim=51, domain_bounds=g["cv_bounds"],
+                            seed=3, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    assert np.array_equal(agt.ssp_x_spaces[0].phase_matrix, g["cv_Ax"]) and np.array_equal(agt.ssp_t_space.phase_matrix, g["cv_At"])
+    found = agt.length_scale()
+    for x, f in list(zip(g["cv_eval_x"], g["cv_eval_f"]))[::5]:
+        np.testing.assert_allclose(agt._cv_loss(x, g["cv_trajs"], g["cv_tys"]), f, rtol=1e-9)
+    f_found = agt._cv_loss(found, g["cv_trajs"], g["cv_tys"])
+    f_ref = agt._cv_loss(g["cv_result"], g["cv_trajs"], g["cv_tys"])
+    np.testing.assert_allclose(f_ref, g["cv_eval_f"].min(), rtol=1e-9)
+    assert f_found <= f_ref + 2e-3 * abs(f_ref)
+    # three agents, own spaces: the objective at a few trial points against the oracle; the agent works afterwards
+    n_agents, L, xd = 3, 3, 2
+    bounds = np.array([[-2.0, 2.0]] * (n_agents * xd))
+    rng = np.random.default_rng(8)
+    trajs = rng.uniform(-2, 2, (12, L * n_agents * xd))
+    tys = -np.sum(trajs ** 2, axis=1, keepdims=True) / (L * n_agents)
+    agt = pkg.SSPMultiAgent(trajs, tys, n_agents=n_agents, x_dim=xd, traj_len=L, ssp_dim=65, domain_bounds=bounds, seed=5,
+                            same_agt_x_space=False, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    ls = agt.length_scale()
+    assert ls.shape == (n_agents + 1,) and np.all(ls[:n_agents] == ls[0]) and np.all(ls >= 1 / np.sqrt(12) - 1e-12)
+    As = [sp.phase_matrix for sp in agt.ssp_x_spaces]
+    for trial in ((4.0, 4.0), (0.9, 2.5), (ls[0], ls[-1])):
+        want = orc.multi_agent_lengthscale_cv_loss(As, agt.ssp_t_space.phase_matrix, agt.agent_sps, trial, trajs, tys, L, n_agents, xd)
+        np.testing.assert_allclose(agt._cv_loss(trial, trajs, tys), want, rtol=1e-9)
+    assert agt._cv_loss((ls[0], ls[-1]), trajs, tys) <= agt._cv_loss((4.0, 4.0), trajs, tys) + 1e-9
+    # _cv_loss left the context at the trial scales / timesteps 0 .. L: re-point it as the constructor does
+    for sp in agt.ssp_x_spaces:
+        sp.update_lengthscale(ls[0])
+    agt.ssp_t_space.update_lengthscale(ls[-1])
+    agt._point_engine(np.linspace(1, L + 1, L).reshape(-1, 1))
+    T = orc.traj_timestep_ssps(agt.ssp_t_space.phase_matrix, np.array([ls[-1]]), L)
+    want = orc.multi_agent_encode(As, [ls[0] * np.ones(xd)] * n_agents, T, agt.agent_sps, trajs[:4], L, n_agents, xd)
+    np.testing.assert_allclose(agt.encode(trajs[:4]), want, atol=5e-13)

@@ -178,6 +178,46 @@ def test_multi_agent_matches_reference(golden, tag):
     assert np.array_equal(dec, g[f"{tag}_decoded"])
 
 
+@pytest.mark.parametrize("tag", ["s3", "s2"])
+def test_multi_agent_per_agent_spaces_match_reference(golden, tag):
+    """The same with one RandomSSPSpace per agent on its own rows of domain_bounds (same_agt_x_space=False,
+    agents/ssp_multi_agent.py:58-66): phase matrices drawn with rng = seed + i, encode, BLR, eval, per-agent decode."""
+    g = golden("multi_agent_sep.npz")
+    n_agents, L, xd, ssp_dim, seed = (int(v) for v in g[f"{tag}_dims"])
+    As, lss = list(g[f"{tag}_Ax"]), list(g[f"{tag}_ls_x"])
+    d = As[0].shape[0]
+    for i in range(n_agents):
+        assert np.array_equal(orc.random_phase_matrix(xd, ssp_dim, rng=seed + i), As[i])
+    assert not np.array_equal(As[0], As[1])
+    tags = orc.sp_vectors(n_agents, d, seed)
+    np.testing.assert_allclose(tags, g[f"{tag}_agent_sps"], atol=1e-15)
+    T = orc.traj_timestep_ssps(g[f"{tag}_At"], g[f"{tag}_ls_t"], L)
+    phi = orc.multi_agent_encode(As, lss, T, tags, g[f"{tag}_xc"], L, n_agents, xd)
+    np.testing.assert_allclose(phi, g[f"{tag}_phi"], atol=1e-14)
+    model = orc.BLR(d)
+    model.update(orc.multi_agent_encode(As, lss, T, tags, g[f"{tag}_trajs"], L, n_agents, xd), g[f"{tag}_tys"])
+    np.testing.assert_allclose(model.m, g[f"{tag}_m"], rtol=1e-9, atol=1e-12)
+    mu, var, acq = orc.agent_eval(phi, model, 5.0, 0.0)
+    np.testing.assert_allclose(mu, g[f"{tag}_mu"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(var, g[f"{tag}_var"], rtol=1e-9)
+    np.testing.assert_allclose(acq, g[f"{tag}_acq"], rtol=1e-9)
+    pts = list(g[f"{tag}_init_pts"])
+    ssps = [orc.encode(As[i], lss[i], pts[i]) for i in range(n_agents)]
+    dec = orc.multi_agent_decode_from_set(phi[:1], T, tags, ssps, pts)
+    assert np.array_equal(dec, g[f"{tag}_decoded"])
+
+
+def test_multi_agent_lengthscale_cv_objective_matches_reference(golden):
+    """oracle.multi_agent_lengthscale_cv_loss against every objective evaluation of the live reference's
+    SSPMultiAgent._optimize_lengthscale (ssp_multi_agent.py:131-164; one agent -- the reference's x0 / bounds only agree
+    then), recorded by oracle/gen_golden.py."""
+    g = golden("multi_agent_sep.npz")
+    assert len(g["cv_eval_f"]) > 20
+    for x, f in list(zip(g["cv_eval_x"], g["cv_eval_f"]))[::5]:
+        v = orc.multi_agent_lengthscale_cv_loss(g["cv_Ax"], g["cv_At"], g["cv_agent_sps"], x, g["cv_trajs"], g["cv_tys"], 4, 1, 2)
+        np.testing.assert_allclose(v, f, rtol=1e-10)
+
+
 def test_lengthscale_cv_objective_matches_reference(golden):
     """oracle.traj_lengthscale_cv_loss against every objective evaluation scipy's L-BFGS-B made inside the live reference's
     SSPTrajectoryAgent._optimize_lengthscale (ssp_traj_agent.py:113-143), recorded by oracle/gen_golden.py."""
