@@ -463,12 +463,14 @@ def test_multi_agent_per_agent_spaces_golden(pkg, golden, tag):
     for code, name, fmt in ((_lib.ENGINE_SIMT, "simt", -1), (_lib.ENGINE_UMMA_LR, "umma-lowrank", 0),
                             (_lib.ENGINE_UMMA_LR, "umma-lowrank", 1)):
         for ph in (1, 0):                                                     # float32 / Q31.32 phase arithmetic
-            eng.set_policy(phase32=ph, operand_format=fmt)
+            eng.set_policy(phase32=ph)
+            eng.set_operand_format(fmt if fmt >= 0 else None)
             _, (mu, var, acq) = eng.score(g[f"{tag}_xc"], 5.0, 0.0, want_outputs=True, engine=code)
             assert eng.last_engine() == name
             assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), g[f"{tag}_mu"], g[f"{tag}_acq"])
             np.testing.assert_allclose(var.double().cpu().numpy(), g[f"{tag}_var"], rtol=RTOL_SCORE)
-    eng.set_policy(phase32=1, operand_format=-1)
+    eng.set_policy(phase32=1)
+    eng.set_operand_format(None)
     with pytest.raises(_lib.SspboError):                                      # the dense-factor kernel: one table, no |phi|
         eng.score(g[f"{tag}_xc"], 5.0, 0.0, engine=_lib.ENGINE_UMMA)
     assert np.array_equal(agt.decode(phi[:1]), g[f"{tag}_decoded"])
@@ -504,7 +506,8 @@ def test_multi_agent_per_agent_spaces_tcgen05_and_driver(pkg):
     eng = agt._scoring_engine()
     for ph in (1, 0):
         for fmt in (0, 1):
-            eng.set_policy(phase32=ph, operand_format=fmt)
+            eng.set_policy(phase32=ph)
+            eng.set_operand_format(fmt)
             _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True)
             assert eng.last_engine() == "umma-lowrank"
             assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
@@ -512,7 +515,8 @@ def test_multi_agent_per_agent_spaces_tcgen05_and_driver(pkg):
             srt = np.sort(ref_score)[::-1]
             if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
                 assert eng.best()[1] == int(np.argmax(ref_score))
-    eng.set_policy(phase32=1, operand_format=-1)
+    eng.set_policy(phase32=1)
+    eng.set_operand_format(None)
     # the rows of a candidate are (timestep, agent): swapping two agents' coordinates changes the encoding
     sw = trajs[:3].reshape(3, L, n_agents, xd)[:, :, [1, 0, 2], :].reshape(3, -1)
     assert np.max(np.abs(agt.encode(sw) - agt.encode(trajs[:3]))) > 1e-3
