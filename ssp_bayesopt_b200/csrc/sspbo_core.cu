@@ -1111,6 +1111,7 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
     dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); dev_free(&ctx->mscale); ctx->lr_rank = 0; ctx->lr_valid = false;
+    dev_free(&ctx->phi_ring); ctx->sp_applied = 0; ctx->sinv_pending = 0;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -1580,6 +1581,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     }
     ctx->has_factor = with_factor;
     ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false; ctx->lr_flag_frac = 0.0;
+    ctx->sp_applied = 0; ctx->sinv_pending = 0;
     if (with_factor && !ctx->stats) {
         if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
             (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)2 * SSPBO_FLAG_CAP)))
@@ -1617,6 +1619,62 @@ extern "C" int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_se
     return SSPBO_OK;
 }
 
+// ---- deferred maintenance of Sp and S_inv (see sspbo_update.cu) ----
+// Sp[i][j] -= sum_r V[r][i] V[r][j] over the rows the fused updates appended without touching Sp
+__global__ void k_sp_fold(double* __restrict__ Sp, const double* __restrict__ Vd, int r0, int r1, int d) {
+    const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double acc = Sp[(size_t)i * d + j];
+    for (int r = r0; r < r1; ++r) acc = fma(-__ldg(Vd + (size_t)r * d + i), __ldg(Vd + (size_t)r * d + j), acc);
+    Sp[(size_t)i * d + j] = acc;
+}
+// S_inv[i][j] += beta phi_r[i] phi_r[j] for the observations of the ring, in their order (blr.py:60): the same sequence of
+// fused multiply-adds the eager update performs, so S_inv is bit-identical either way
+__global__ void k_sinv_flush(double* __restrict__ Sinv, const double* __restrict__ ring, int count, double beta, int d) {
+    const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double acc = Sinv[(size_t)i * d + j];
+    for (int r = 0; r < count; ++r) acc = fma(beta * __ldg(ring + (size_t)r * d + i), __ldg(ring + (size_t)r * d + j), acc);
+    Sinv[(size_t)i * d + j] = acc;
+}
+
+int sspbo_ensure_sp(sspbo_ctx* ctx, cudaStream_t st) {
+    if (!ctx->has_factor || ctx->sp_applied >= ctx->lr_rank) return SSPBO_OK;
+    const int d = ctx->d;
+    k_sp_fold<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sp, ctx->Vd, ctx->sp_applied, ctx->lr_rank, d);
+    SSPBO_LAUNCH_CHECK(ctx);
+    ctx->sp_applied = ctx->lr_rank;
+    return SSPBO_OK;
+}
+
+int sspbo_ensure_sinv(sspbo_ctx* ctx, cudaStream_t st) {
+    if (ctx->sinv_pending <= 0) return SSPBO_OK;
+    const int d = ctx->d;
+    k_sinv_flush<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sinv, ctx->phi_ring, ctx->sinv_pending, ctx->beta, d);
+    SSPBO_LAUNCH_CHECK(ctx);
+    ctx->sinv_pending = 0;
+    return SSPBO_OK;
+}
+
+int sspbo_update_prepare(sspbo_ctx* ctx, bool append, cudaStream_t st, double** ring_row) {
+    int rc;
+    *ring_row = nullptr;
+    if (!append) {                                       // the kernel updates Sp and S_inv itself: they must be current
+        if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
+        return SSPBO_OK;
+    }
+    if (!ctx->phi_ring && (rc = dev_alloc(ctx, &ctx->phi_ring, (size_t)SSPBO_SINV_RING * ctx->d))) return rc;
+    if (ctx->sinv_pending >= SSPBO_SINV_RING && (rc = sspbo_ensure_sinv(ctx, st))) return rc;
+    *ring_row = ctx->phi_ring + (size_t)ctx->sinv_pending * ctx->d;
+    return SSPBO_OK;
+}
+
+void sspbo_update_done(sspbo_ctx* ctx, bool appended, bool deferred) {
+    if (appended) ctx->lr_rank++;
+    if (deferred) ctx->sinv_pending++;
+    else ctx->sp_applied = ctx->lr_rank;                 // the kernel applied this observation to Sp itself
+}
+
 extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double* ts_host, int k, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
     if (!ctx->blr_ready) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_update before blr_init");
@@ -1640,12 +1698,19 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     vh = ctx->Vh + off; vl = ctx->Vl + off; vd = ctx->Vd + (size_t)ctx->lr_rank * d; append = true;
                 }
             }
-            const int rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd,
-                                                  (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr, st);
-            if (rc == SSPBO_OK) { if (append) ctx->lr_rank++; m_current = (i == k - 1); continue; }
+            double* ring_row = nullptr;
+            int rc = sspbo_update_prepare(ctx, append, st, &ring_row);
+            if (rc) return rc;
+            rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd,
+                                        (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr, ring_row, st);
+            if (rc == SSPBO_OK) { sspbo_update_done(ctx, append, ring_row != nullptr); m_current = (i == k - 1); continue; }
             if (rc != SSPBO_EUNSUPPORTED) return rc;
             // nothing was written: fall through to the unfused kernels, for this and every later observation
             ctx->unfused_update = true;
+        }
+        {   // the separate kernels update Sp and S_inv in place
+            int rc;
+            if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
         }
         // --- phi-space posterior, blr.py:60-70 ---
         k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, phi, ctx->v, d);                       // v = S phi
@@ -1671,6 +1736,7 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     k_lr_append<<<(d + 255) / 256, 256, 0, st>>>(ctx->y, ctx->scal + 2, ctx->col_of_rank, d, ctx->r_scale,
                                                                  ctx->Vh + off, ctx->Vl + off, ctx->Vd + (size_t)ctx->lr_rank * d);
                     ctx->lr_rank++;
+                    ctx->sp_applied = ctx->lr_rank;
                 }
             }
         }
@@ -1705,6 +1771,8 @@ int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st) {
     if (!ctx->has_factor) SSPBO_FAIL(ctx, SSPBO_ESTATE, "scoring needs a BLR created over an SSP space (blr_init)");
     const int d = ctx->d;
     if (ctx->factor_dirty) {                                    // L = chol(Sp), blocked, in place on a copy
+        const int rc_sp = sspbo_ensure_sp(ctx, st);
+        if (rc_sp) return rc_sp;
         SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->R, ctx->Sp, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
         for (int k0 = 0; k0 < d; k0 += CH_NB) {
             k_chol_diag<<<1, dim3(CH_NB, CH_NB), 0, st>>>(ctx->R, d, k0);
@@ -1746,6 +1814,7 @@ extern "C" int sspbo_blr_get(sspbo_ctx* ctx, double* m, double* S, double* Sinv,
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d;
+    if (Sinv) { const int rc = sspbo_ensure_sinv(ctx, st); if (rc) return rc; }
     if (m) SSPBO_CUDA(ctx, cudaMemcpyAsync(m, ctx->m, d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (S) SSPBO_CUDA(ctx, cudaMemcpyAsync(S, ctx->S, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (Sinv) SSPBO_CUDA(ctx, cudaMemcpyAsync(Sinv, ctx->Sinv, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1764,6 +1833,10 @@ extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d, dd = d * d;
+    {
+        int rc;
+        if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
+    }
     const double* src[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->Sp, ctx->mp};
     const size_t cnt[6] = {dd, dd, d, d, dd, d};
     size_t off = 0;
@@ -1795,6 +1868,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
     ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
+    ctx->sinv_pending = 0;                                       // (the imported S_inv is complete)
     if (ctx->has_factor) {
         double rank = -1.0;                                      // the rows of V travel with the packed state
         SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1808,6 +1882,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
         ctx->v8_rank = 0; ctx->v8_row0_dirty = true;
         ctx->lr_valid = rank >= 0.0 && rank <= (double)SSPBO_LR_MAX;
         ctx->lr_rank = ctx->lr_valid ? (int)rank : 0;
+        ctx->sp_applied = ctx->lr_rank;                          // the imported Sp is complete
         if (ctx->lr_valid && ctx->lr_rank > 0) {
             k_lr_rebuild<<<dim3(((int)d + 255) / 256, ctx->lr_rank), 256, 0, st>>>(ctx->Vd, ctx->col_of_rank, (int)d, ctx->KC_pad,
                                                                                     ctx->r_scale, ctx->Vh, ctx->Vl);
@@ -1854,6 +1929,7 @@ static int score_flagged_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, 
     const size_t smem = (size_t)EX_G * d * sizeof(double);
     const int gx = 2 * ctx->sm_count;
     const bool full = !ctx->lr_valid;
+    if (full) { const int rc_sp = sspbo_ensure_sp(ctx, st); if (rc_sp) return rc_sp; }
     const double* rows = full ? ctx->Sp : ctx->Vd;
     const int r = full ? d : ctx->lr_rank;
     ExactArgs ea;
@@ -1885,6 +1961,7 @@ int sspbo_score_exact_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
     }
     // row blocks: a group of EX_G candidates is reduced against Sp by RB CTAs, so that a handful of candidates (eval(x_t))
     // spreads over the machine instead of streaming all of Sp through one SM
+    { const int rc_sp = sspbo_ensure_sp(ctx, st); if (rc_sp) return rc_sp; }
     const int64_t groups = (N + EX_G - 1) / EX_G;
     int RB = 1;
     while (RB < EX_RB_MAX && groups * RB < 2 * ctx->sm_count) RB *= 2;

@@ -9,6 +9,11 @@
 //       S -= coef v v^T,  S_inv += beta phi phi^T,  Sp -= coef' y y^T (my rows);  b += beta t phi;  row of V appended;
 //       m = S b for my rows from the updated values in the same pass
 //   P3  m' = B^T m (my frequencies)
+// Deferred form (UpdateParams::defer, whenever the observation appends a row to V): Sp and S_inv are NOT touched.  Sp = B^T S B
+// gives y = Sp psi = B^T (S phi) = B^T v, an analysis DFT of v (no read of Sp), and psi.y = phi.v; the row of V carries
+// everything Sp needs (Sp -= row^T row, folded in by sspbo_ensure_sp when a consumer wants the matrix), and phi goes into a
+// small ring from which S_inv += beta phi phi^T is applied later in the same order (sspbo_ensure_sinv).  The launch then reads
+// S once and reads + writes it once: 3 d^2 doubles instead of 8 d^2.
 // Float64 throughout, no atomics: the result is bitwise reproducible, so replicated contexts (one per GPU) stay identical.
 // S is updated in the symmetric form v v^T (the reference forms (S phi)(phi^T S), which differs from it by the O(1e-13)
 // asymmetry its S accumulates; both are the same rank-one update of the same posterior).
@@ -25,6 +30,8 @@ constexpr int UP_WARPS = UP_THREADS / 32;
 
 struct UpdateParams {
     int d, K, has_factor, finalize;
+    int defer;                             // Sp and S_inv are brought up to date later (row of V / ring of phi); needs vd_row and phi_ring
+    double* phi_ring;                      // defer: where this observation's phi is kept for S_inv
     double beta, t, r_scale;
     const double* phi;
     double *S, *Sinv, *b, *m;
@@ -120,7 +127,8 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
     }
 
     // ---- P0: psi (rank order) and v = S phi ----
-    if (p.has_factor && !psi_given)
+    const bool defer = p.defer != 0;
+    if (p.has_factor && !psi_given && !defer)
         up_analysis(phi, d, K, p.twiddle, gw, nw, lane, [&](int k, double c, double s) {
             if (k == 0) __stcg(p.psi + p.inv_perm[0], c);
             else { __stcg(p.psi + p.inv_perm[k], c); __stcg(p.psi + p.inv_perm[K + k], -s); }
@@ -136,7 +144,16 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
     team.sync();
 
     // ---- P1: y = Sp psi ----
-    if (p.has_factor) {
+    if (p.has_factor && defer) {                                        // = B^T v in rank order: an analysis DFT of v
+        for (int j = tid; j < d; j += UP_THREADS) yv[j] = __ldcg(p.v + j);
+        __syncthreads();
+        const double s0 = 1.0 / d, sk = 2.0 / d;
+        up_analysis(yv, d, K, p.twiddle, gw, nw, lane, [&](int k, double c, double s) {
+            if (k == 0) __stcg(p.y + p.inv_perm[0], s0 * c);
+            else { __stcg(p.y + p.inv_perm[k], sk * c); __stcg(p.y + p.inv_perm[K + k], -sk * s); }
+        });
+        team.sync();                                                    // (every CTA has also finished reading yv as v)
+    } else if (p.has_factor) {
         for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.psi + j);
         __syncthreads();
         for (int i = gw; i < d; i += nw) {
@@ -157,13 +174,13 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
         part[0] = fma(phi[j], vj, part[0]);
         if (p.has_factor) {
             const double yj = __ldcg(p.y + j);
-            part[1] = fma(vec[j], yj, part[1]);                          // vec still holds psi
+            if (!defer) part[1] = fma(vec[j], yj, part[1]);              // vec still holds psi
             yv[j] = yj;
         }
     }
     up_block_reduce<4>(part, red, tot);
     const double coef = p.beta / (1.0 + p.beta * tot[0]);               // blr.py:64-67 (Sherman-Morrison)
-    const double coef2 = p.beta / (1.0 + p.beta * tot[1]);
+    const double coef2 = defer ? coef : p.beta / (1.0 + p.beta * tot[1]);   // psi.y = phi.v
     if (p.obs_out && cta == 0 && tid == 0) p.obs_out[1] = 1.0 / p.beta + tot[0];   // blr.py:96 before the update
     __syncthreads();                                                    // everyone has read psi from vec
     for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.v + j);
@@ -178,9 +195,9 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
             const double s = fma(-cv, vec[j], srow[j]);
             srow[j] = s;
             acc = fma(s, bp[j], acc);
-            irow[j] = fma(bphi, phi[j], irow[j]);                       // blr.py:60: S_inv += beta phi phi^T
+            if (!defer) irow[j] = fma(bphi, phi[j], irow[j]);            // blr.py:60: S_inv += beta phi phi^T
         }
-        if (p.has_factor) {
+        if (p.has_factor && !defer) {
             double* prow = p.Sp + (size_t)i * d;
             const double cy = coef2 * yv[i];
 #pragma unroll 4
@@ -196,6 +213,7 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
         const double sq = sqrt(coef2);
         for (int j = gt; j < d; j += nt) {
             p.b[j] = bp[j];
+            if (defer) p.phi_ring[j] = phi[j];
             if (p.vd_row) {
                 const double v0 = yv[j] * sq;
                 p.vd_row[j] = v0;
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__(UP_THREADS, 4) k_blr_update_runs(const RunUpda
 // One observation.  Returns SSPBO_EUNSUPPORTED (without touching the state) when the device cannot run it; the caller then
 // falls back to the unfused kernels.
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
-                           double* vd_row, double* obs_out, cudaStream_t st) {
+                           double* vd_row, double* obs_out, double* phi_ring_row, cudaStream_t st) {
     const int d = ctx->d;
     const size_t smem = ((size_t)4 * d + UP_WARPS * 4 + 4) * sizeof(double);
     if (ctx->fused_update_ok < 0) {                       // probe once
@@ -325,6 +343,7 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
     p.twiddle = ctx->twiddle; p.inv_perm = ctx->inv_perm; p.col_of_rank = ctx->col_of_rank;
     p.v = ctx->v; p.psi = ctx->psi; p.y = ctx->y;
     p.vh_row = vh_row; p.vl_row = vl_row; p.vd_row = vd_row; p.obs_out = obs_out;
+    p.defer = (phi_ring_row && vd_row && ctx->has_factor) ? 1 : 0; p.phi_ring = phi_ring_row;
     int G = (d + UP_WARPS - 1) / UP_WARPS;
     if (G > ctx->sm_count) G = ctx->sm_count;
     void* args[] = {(void*)&p};
@@ -392,6 +411,11 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
                 p.vh_row = c->Vh + off; p.vl_row = c->Vl + off; p.vd_row = c->Vd + (size_t)c->lr_rank * d;
             }
         }
+        {   // with a row of V to append, Sp and S_inv are left for later (ring of phi); otherwise they are made current here
+            const int rc_p = sspbo_update_prepare(c, p.vd_row != nullptr, st, &p.phi_ring);
+            if (rc_p) { if (failed) *failed = r; return rc_p; }
+            p.defer = p.phi_ring ? 1 : 0;
+        }
         u.x = dx + (size_t)r * n_max; u.A_turns = c->A_turns; u.n = c->n; u.dc = c->dc; u.phi_out = c->obs_phi;
         u.perm = c->perm; u.mp_op = c->mp_op; u.vh0 = c->Vh; u.vl0 = c->Vl; u.mscale = c->mscale;
         for (int a = 0; a < c->n; ++a) hx[(size_t)r * n_max + a] = x_host[(size_t)r * c->n + a];
@@ -411,7 +435,7 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
     c0->launches++;
     for (int r = 0; r < R; ++r) {
         sspbo_ctx* c = ctxs[r];
-        if (hp[r].up.vd_row) c->lr_rank++;
+        sspbo_update_done(c, hp[r].up.vd_row != nullptr, hp[r].up.defer != 0);
         c->v8_row0_dirty = true;
         c->operands_dirty = true; c->factor_dirty = true; c->f8_factor_dirty = true;
     }
