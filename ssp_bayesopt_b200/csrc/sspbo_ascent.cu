@@ -272,6 +272,7 @@ extern "C" int sspbo_acq_ascent(sspbo_ctx* ctx, const double* phi0, int R, doubl
         SSPBO_CUDA(ctx, cudaMalloc((void**)&ctx->aa_work, need * sizeof(double)));
         ctx->aa_cap = need;
     }
+    { const int rc = sspbo_ensure_s(ctx, st); if (rc) return rc; }       // S and m as of the last observation
     for (int r0 = 0; r0 < R; r0 += AA_RT) {
         AscentParams p;
         p.S = ctx->S; p.m = ctx->m; p.phi0 = phi0 + (size_t)r0 * d;

@@ -1111,7 +1111,8 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->mp); dev_free(&ctx->Rt_f32); dev_free(&ctx->mp_f32);
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
     dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); dev_free(&ctx->mscale); ctx->lr_rank = 0; ctx->lr_valid = false;
-    dev_free(&ctx->phi_ring); ctx->sp_applied = 0; ctx->sinv_pending = 0;
+    dev_free(&ctx->psi_ring); dev_free(&ctx->syn_rows); dev_free(&ctx->bpsi); dev_free(&ctx->lr_gh);
+    ctx->sp_applied = 0; ctx->s_applied = 0; ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = false;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
 }
@@ -1581,7 +1582,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     }
     ctx->has_factor = with_factor;
     ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false; ctx->lr_flag_frac = 0.0;
-    ctx->sp_applied = 0; ctx->sinv_pending = 0;
+    ctx->sp_applied = 0; ctx->s_applied = 0; ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true;
     if (with_factor && !ctx->stats) {
         if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
             (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)2 * SSPBO_FLAG_CAP)))
@@ -1610,6 +1611,12 @@ extern "C" int sspbo_blr_init_dim(sspbo_ctx* ctx, int d, double alpha) {
 extern "C" int sspbo_blr_set_beta(sspbo_ctx* ctx, double beta) {
     if (!ctx) return SSPBO_EINVAL;
     if (!(beta > 0) || !isfinite(beta)) SSPBO_FAIL(ctx, SSPBO_EINVAL, "beta must be positive and finite");
+    if (ctx->has_beta && beta != ctx->beta && ctx->sinv_pending > 0) {   // pending S_inv terms carry the old precision
+        SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+        const int rc = sspbo_ensure_sinv(ctx, 0);
+        if (rc) return rc;
+        SSPBO_CUDA(ctx, cudaStreamSynchronize(0));
+    }
     ctx->beta = beta; ctx->has_beta = true;
     return SSPBO_OK;
 }
@@ -1619,17 +1626,16 @@ extern "C" int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_se
     return SSPBO_OK;
 }
 
-// ---- deferred maintenance of Sp and S_inv (see sspbo_update.cu) ----
-// Sp[i][j] -= sum_r V[r][i] V[r][j] over the rows the fused updates appended without touching Sp
-__global__ void k_sp_fold(double* __restrict__ Sp, const double* __restrict__ Vd, int r0, int r1, int d) {
+// ---- the state the low-rank updates leave behind (k_blr_update_lr, sspbo_update.cu), brought up to date on demand ----
+// M[i][j] -= sum_r rows[r][i] rows[r][j]   (Sp from the rows of V; S from their phi-space images)
+__global__ void k_rows_fold(double* __restrict__ M, const double* __restrict__ rows, int r0, int r1, int d) {
     const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
-    double acc = Sp[(size_t)i * d + j];
-    for (int r = r0; r < r1; ++r) acc = fma(-__ldg(Vd + (size_t)r * d + i), __ldg(Vd + (size_t)r * d + j), acc);
-    Sp[(size_t)i * d + j] = acc;
+    double acc = M[(size_t)i * d + j];
+    for (int r = r0; r < r1; ++r) acc = fma(-__ldg(rows + (size_t)r * d + i), __ldg(rows + (size_t)r * d + j), acc);
+    M[(size_t)i * d + j] = acc;
 }
-// S_inv[i][j] += beta phi_r[i] phi_r[j] for the observations of the ring, in their order (blr.py:60): the same sequence of
-// fused multiply-adds the eager update performs, so S_inv is bit-identical either way
+// S_inv[i][j] += beta phi_r[i] phi_r[j] for the observations of the ring, in their order (blr.py:60)
 __global__ void k_sinv_flush(double* __restrict__ Sinv, const double* __restrict__ ring, int count, double beta, int d) {
     const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
@@ -1637,42 +1643,108 @@ __global__ void k_sinv_flush(double* __restrict__ Sinv, const double* __restrict
     for (int r = 0; r < count; ++r) acc = fma(beta * __ldg(ring + (size_t)r * d + i), __ldg(ring + (size_t)r * d + j), acc);
     Sinv[(size_t)i * d + j] = acc;
 }
+// out[row][j] = s0 w_0 + sk sum_k (w_Ck cos(2 pi j k / d) - w_Sk sin(2 pi j k / d)), w = row of `in` read through `src` (rank of
+// every natural index; null: natural order).  (s0, sk) = (1/d, 2/d): phi = B psi (sspspace.py:275) and b = B b_psi;
+// (1, 1): B D^-1 w, the phi-space image of a row of V and m from m'.
+__global__ void k_synth_rows(const double* __restrict__ in, int K, const int* __restrict__ src, const double2* __restrict__ twiddle,
+                             double s0, double sk, double* __restrict__ out) {
+    extern __shared__ double w_s[];                     // d, natural order
+    const int d = 2 * K + 1;
+    const double* w = in + (size_t)blockIdx.y * d;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) w_s[k] = w[src ? src[k] : k];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double acc = 0.0;
+    int idx = 0;
+    for (int k = 1; k <= K; ++k) {
+        idx += j; if (idx >= d) idx -= d;
+        const double2 tw = __ldg(twiddle + idx);
+        acc = fma(w_s[k], tw.x, fma(-w_s[K + k], tw.y, acc));
+    }
+    out[(size_t)blockIdx.y * d + j] = fma(sk, acc, s0 * w_s[0]);
+}
+
+static int synth_rows(sspbo_ctx* ctx, const double* in, int rows, const int* src, double s0, double sk, double* out, cudaStream_t st) {
+    const int d = ctx->d;
+    k_synth_rows<<<dim3((d + 255) / 256, rows), 256, (size_t)d * sizeof(double), st>>>(in, ctx->K, src, ctx->twiddle, s0, sk, out);
+    SSPBO_LAUNCH_CHECK(ctx);
+    return SSPBO_OK;
+}
 
 int sspbo_ensure_sp(sspbo_ctx* ctx, cudaStream_t st) {
     if (!ctx->has_factor || ctx->sp_applied >= ctx->lr_rank) return SSPBO_OK;
     const int d = ctx->d;
-    k_sp_fold<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sp, ctx->Vd, ctx->sp_applied, ctx->lr_rank, d);
+    k_rows_fold<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sp, ctx->Vd, ctx->sp_applied, ctx->lr_rank, d);
     SSPBO_LAUNCH_CHECK(ctx);
     ctx->sp_applied = ctx->lr_rank;
+    return SSPBO_OK;
+}
+
+int sspbo_ensure_bm(sspbo_ctx* ctx, cudaStream_t st) {
+    if (!ctx->has_factor || !ctx->bm_stale) return SSPBO_OK;
+    int rc;
+    const double d = (double)ctx->d;
+    if ((rc = synth_rows(ctx, ctx->bpsi, 1, ctx->inv_perm, 1.0 / d, 2.0 / d, ctx->b, st))) return rc;     // b = B b_psi
+    if ((rc = synth_rows(ctx, ctx->mp, 1, nullptr, 1.0, 1.0, ctx->m, st))) return rc;                      // m = B D^-1 m'
+    ctx->bm_stale = false;
+    return SSPBO_OK;
+}
+
+int sspbo_ensure_s(sspbo_ctx* ctx, cudaStream_t st) {
+    int rc;
+    if ((rc = sspbo_ensure_bm(ctx, st))) return rc;
+    if (!ctx->has_factor || ctx->s_applied >= ctx->lr_rank) return SSPBO_OK;
+    const int d = ctx->d;
+    while (ctx->s_applied < ctx->lr_rank) {             // S -= u u^T, u = B D^-1 (row of V): a ring's worth of rows per pass over S
+        const int cnt = ctx->lr_rank - ctx->s_applied < SSPBO_SINV_RING ? ctx->lr_rank - ctx->s_applied : SSPBO_SINV_RING;
+        if ((rc = synth_rows(ctx, ctx->Vd + (size_t)ctx->s_applied * d, cnt, ctx->inv_perm, 1.0, 1.0, ctx->syn_rows, st))) return rc;
+        k_rows_fold<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->S, ctx->syn_rows, 0, cnt, d);
+        SSPBO_LAUNCH_CHECK(ctx);
+        ctx->s_applied += cnt;
+    }
     return SSPBO_OK;
 }
 
 int sspbo_ensure_sinv(sspbo_ctx* ctx, cudaStream_t st) {
     if (ctx->sinv_pending <= 0) return SSPBO_OK;
     const int d = ctx->d;
-    k_sinv_flush<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sinv, ctx->phi_ring, ctx->sinv_pending, ctx->beta, d);
+    int rc;
+    if ((rc = synth_rows(ctx, ctx->psi_ring, ctx->sinv_pending, nullptr, 1.0 / d, 2.0 / d, ctx->syn_rows, st))) return rc;   // phi = B psi
+    k_sinv_flush<<<dim3((d + 255) / 256, d), 256, 0, st>>>(ctx->Sinv, ctx->syn_rows, ctx->sinv_pending, ctx->beta, d);
     SSPBO_LAUNCH_CHECK(ctx);
     ctx->sinv_pending = 0;
     return SSPBO_OK;
 }
 
-int sspbo_update_prepare(sspbo_ctx* ctx, bool append, cudaStream_t st, double** ring_row) {
+int sspbo_ensure_all(sspbo_ctx* ctx, cudaStream_t st) {
     int rc;
-    *ring_row = nullptr;
-    if (!append) {                                       // the kernel updates Sp and S_inv itself: they must be current
-        if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
-        return SSPBO_OK;
-    }
-    if (!ctx->phi_ring && (rc = dev_alloc(ctx, &ctx->phi_ring, (size_t)SSPBO_SINV_RING * ctx->d))) return rc;
-    if (ctx->sinv_pending >= SSPBO_SINV_RING && (rc = sspbo_ensure_sinv(ctx, st))) return rc;
-    *ring_row = ctx->phi_ring + (size_t)ctx->sinv_pending * ctx->d;
+    if ((rc = sspbo_ensure_s(ctx, st)) || (rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
     return SSPBO_OK;
 }
 
-void sspbo_update_done(sspbo_ctx* ctx, bool appended, bool deferred) {
-    if (appended) ctx->lr_rank++;
-    if (deferred) ctx->sinv_pending++;
-    else ctx->sp_applied = ctx->lr_rank;                 // the kernel applied this observation to Sp itself
+int sspbo_lr_update_prepare(sspbo_ctx* ctx, cudaStream_t st, double** ring_row) {
+    int rc;
+    const size_t d = ctx->d;
+    if (!ctx->psi_ring) {
+        if ((rc = dev_alloc(ctx, &ctx->psi_ring, (size_t)SSPBO_SINV_RING * d)) || (rc = dev_alloc(ctx, &ctx->syn_rows, (size_t)SSPBO_SINV_RING * d)) ||
+            (rc = dev_alloc(ctx, &ctx->bpsi, d)) || (rc = dev_alloc(ctx, &ctx->lr_gh, (size_t)2 * SSPBO_LR_MAX + 32)))
+            return rc;
+        ctx->bpsi_stale = true;
+    }
+    if (ctx->bpsi_stale) {                              // b_psi = D^-1 B^T b after eager updates / an import (b is current then)
+        k_analysis<<<ctx->K + 1, 128, 0, st>>>(ctx->b, ctx->bpsi, ctx->twiddle, ctx->K, 1.0, 1.0, ctx->inv_perm);
+        SSPBO_LAUNCH_CHECK(ctx);
+        ctx->bpsi_stale = false;
+    }
+    if (ctx->sinv_pending >= SSPBO_SINV_RING && (rc = sspbo_ensure_sinv(ctx, st))) return rc;
+    *ring_row = ctx->psi_ring + (size_t)ctx->sinv_pending * d;
+    return SSPBO_OK;
+}
+
+void sspbo_eager_update_done(sspbo_ctx* ctx) {
+    ctx->sp_applied = ctx->lr_rank; ctx->s_applied = ctx->lr_rank;
+    ctx->bpsi_stale = true;
 }
 
 extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double* ts_host, int k, void* stream) {
@@ -1686,8 +1758,25 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
     const double beta = ctx->beta;
     dim3 g1((d + 255) / 256, d);
     bool m_current = false;                              // m, m' already refreshed by the last fused launch
+    bool tail_done = false;                              // ... and the operand-order copies of m' too (low-rank kernel)
     for (int i = 0; i < k; ++i) {
         const double* phi = phis + (size_t)i * d;
+        if (!ctx->unfused_update && ctx->has_factor && ctx->lr_valid) {      // low-rank form: O(rank d), one cluster launch
+            if (ctx->lr_rank >= SSPBO_LR_MAX) ctx->lr_valid = false;
+            else {
+                sspbo_ctx* one[1] = {ctx};
+                const double* ph[1] = {phi};
+                const int rc = sspbo_blr_update_lr(one, 1, nullptr, ph, ts_host + i, st, nullptr,
+                                                   (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr);
+                if (rc == SSPBO_OK) { m_current = true; tail_done = true; continue; }
+                if (rc != SSPBO_EUNSUPPORTED) return rc;
+            }
+        }
+        {   // the kernels below keep the d x d state and the phi-space vectors current themselves: fold in what is pending
+            const int rc = sspbo_ensure_all(ctx, st);
+            if (rc) return rc;
+            tail_done = false;
+        }
         if (!ctx->unfused_update) {                      // one cooperative launch per observation
             __half *vh = nullptr, *vl = nullptr; double* vd = nullptr;
             bool append = false;
@@ -1698,20 +1787,14 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     vh = ctx->Vh + off; vl = ctx->Vl + off; vd = ctx->Vd + (size_t)ctx->lr_rank * d; append = true;
                 }
             }
-            double* ring_row = nullptr;
-            int rc = sspbo_update_prepare(ctx, append, st, &ring_row);
-            if (rc) return rc;
-            rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd,
-                                        (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr, ring_row, st);
-            if (rc == SSPBO_OK) { sspbo_update_done(ctx, append, ring_row != nullptr); m_current = (i == k - 1); continue; }
+            const int rc = sspbo_blr_update_fused(ctx, phi, ts_host[i], i == k - 1, vh, vl, vd,
+                                                  (ctx->want_obs && k == 1) ? ctx->obs_out : nullptr, st);
+            if (rc == SSPBO_OK) { if (append) ctx->lr_rank++; sspbo_eager_update_done(ctx); m_current = (i == k - 1); continue; }
             if (rc != SSPBO_EUNSUPPORTED) return rc;
             // nothing was written: fall through to the unfused kernels, for this and every later observation
             ctx->unfused_update = true;
         }
-        {   // the separate kernels update Sp and S_inv in place
-            int rc;
-            if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
-        }
+        m_current = false;
         // --- phi-space posterior, blr.py:60-70 ---
         k_gemv_rows<<<(d + 7) / 8, 256, 0, st>>>(ctx->S, phi, ctx->v, d);                       // v = S phi
         SSPBO_LAUNCH_CHECK(ctx);
@@ -1736,7 +1819,6 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                     k_lr_append<<<(d + 255) / 256, 256, 0, st>>>(ctx->y, ctx->scal + 2, ctx->col_of_rank, d, ctx->r_scale,
                                                                  ctx->Vh + off, ctx->Vl + off, ctx->Vd + (size_t)ctx->lr_rank * d);
                     ctx->lr_rank++;
-                    ctx->sp_applied = ctx->lr_rank;
                 }
             }
         }
@@ -1747,6 +1829,7 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
         SSPBO_LAUNCH_CHECK(ctx);
         k_axpy<<<(d + 255) / 256, 256, 0, st>>>(ctx->b, phi, beta * ts_host[i], d);              // b += beta t phi
         SSPBO_LAUNCH_CHECK(ctx);
+        sspbo_eager_update_done(ctx);
     }
     if (k > 0) {
         if (!m_current) {
@@ -1758,8 +1841,10 @@ extern "C" int sspbo_blr_update(sspbo_ctx* ctx, const double* phis, const double
                 k_analysis<<<K + 1, 128, 0, st>>>(ctx->m, ctx->mp, ctx->twiddle, K, 1.0 / d, 2.0 / d, nullptr);   // m' = B^T m
                 SSPBO_LAUNCH_CHECK(ctx);
             }
-            k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
-            SSPBO_LAUNCH_CHECK(ctx);
+            if (!tail_done) {
+                k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
+                SSPBO_LAUNCH_CHECK(ctx);
+            }
             ctx->v8_row0_dirty = true;
         }
         ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
@@ -1814,7 +1899,13 @@ extern "C" int sspbo_blr_get(sspbo_ctx* ctx, double* m, double* S, double* Sinv,
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d;
-    if (Sinv) { const int rc = sspbo_ensure_sinv(ctx, st); if (rc) return rc; }
+    {
+        int rc = 0;
+        if (m && !S) rc = sspbo_ensure_bm(ctx, st);
+        if (S) rc = sspbo_ensure_s(ctx, st);
+        if (!rc && Sinv) rc = sspbo_ensure_sinv(ctx, st);
+        if (rc) return rc;
+    }
     if (m) SSPBO_CUDA(ctx, cudaMemcpyAsync(m, ctx->m, d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (S) SSPBO_CUDA(ctx, cudaMemcpyAsync(S, ctx->S, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (Sinv) SSPBO_CUDA(ctx, cudaMemcpyAsync(Sinv, ctx->Sinv, d * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1834,8 +1925,8 @@ extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d, dd = d * d;
     {
-        int rc;
-        if ((rc = sspbo_ensure_sp(ctx, st)) || (rc = sspbo_ensure_sinv(ctx, st))) return rc;
+        const int rc = sspbo_ensure_all(ctx, st);
+        if (rc) return rc;
     }
     const double* src[6] = {ctx->S, ctx->Sinv, ctx->b, ctx->m, ctx->Sp, ctx->mp};
     const size_t cnt[6] = {dd, dd, d, d, dd, d};
@@ -1868,7 +1959,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     }
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
     ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
-    ctx->sinv_pending = 0;                                       // (the imported S_inv is complete)
+    ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true;   // (S_inv, b, m complete; b_psi follows from b)
     if (ctx->has_factor) {
         double rank = -1.0;                                      // the rows of V travel with the packed state
         SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1882,7 +1973,7 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
         ctx->v8_rank = 0; ctx->v8_row0_dirty = true;
         ctx->lr_valid = rank >= 0.0 && rank <= (double)SSPBO_LR_MAX;
         ctx->lr_rank = ctx->lr_valid ? (int)rank : 0;
-        ctx->sp_applied = ctx->lr_rank;                          // the imported Sp is complete
+        ctx->sp_applied = ctx->lr_rank; ctx->s_applied = ctx->lr_rank;     // the imported matrices are complete
         if (ctx->lr_valid && ctx->lr_rank > 0) {
             k_lr_rebuild<<<dim3(((int)d + 255) / 256, ctx->lr_rank), 256, 0, st>>>(ctx->Vd, ctx->col_of_rank, (int)d, ctx->KC_pad,
                                                                                     ctx->r_scale, ctx->Vh, ctx->Vl);
@@ -1905,6 +1996,7 @@ extern "C" int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi, int64_t N, d
     SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks64 = (N + PRED_CPB - 1) / PRED_CPB;
     int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 4 ? blocks64 : (int64_t)ctx->sm_count * 4);
+    { const int rc = sspbo_ensure_s(ctx, (cudaStream_t)stream); if (rc) return rc; }
     k_predict<<<blocks, 256, smem, (cudaStream_t)stream>>>(phi, N, ctx->S, ctx->m, ctx->d, 1.0 / ctx->beta, mu, var);
     SSPBO_LAUNCH_CHECK(ctx);
     return SSPBO_OK;
@@ -2248,6 +2340,11 @@ extern "C" int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const do
     if (k == 0) return SSPBO_OK;
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (k == 1) {                                        // low-rank form: the cluster encodes the point itself, any d
+        sspbo_ctx* one[1] = {ctx};
+        const int rc = sspbo_blr_update_lr(one, 1, x_host, nullptr, ts_host, st, nullptr, ctx->want_obs ? ctx->obs_out : nullptr);
+        if (rc != SSPBO_EUNSUPPORTED) return rc;
+    }
     if (k == 1 && ctx->d <= SSPBO_CLUSTER_UPDATE_MAX_D) {
         // small spaces: the observation of a BO step in ONE launch -- a cluster of four CTAs encodes the point, applies the
         // update and refreshes the scoring operands (the cooperative kernel's grid barriers and the two helper launches around

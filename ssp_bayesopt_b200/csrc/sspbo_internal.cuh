@@ -76,12 +76,18 @@ struct sspbo_ctx {
     int lr_rank = 0;
     double export_rank = -1.0;       // staging scalar of sspbo_blr_export
     bool lr_valid = false;           // every update since blr_init appended its row (false after import / rank overflow)
-    // deferred maintenance (fused updates that append a row of V never touch Sp / S_inv, sspbo_update.cu): Sp lacks the rows
-    // [sp_applied, lr_rank) of V (Sp -= row^T row), S_inv lacks the sinv_pending observations kept in phi_ring
-    // (S_inv += beta phi phi^T).  sspbo_ensure_sp / sspbo_ensure_sinv bring them up to date for the consumers that read them.
-    int sp_applied = 0;
-    double* phi_ring = nullptr;      // SSPBO_SINV_RING x d
+    // Low-rank updates (k_blr_update_lr, sspbo_update.cu) touch only the rows of V, b_psi and m'; the d x d state and the
+    // phi-space vectors follow when a consumer asks (sspbo_ensure_*): Sp lacks the rows [sp_applied, lr_rank) of V
+    // (Sp -= row^T row), S the rows [s_applied, lr_rank) (S -= u u^T, u = B D^-1 row), S_inv the sinv_pending observations
+    // whose psi sits in psi_ring (S_inv += beta phi phi^T, phi = B psi), b and m are stale when bm_stale (b = B b_psi,
+    // m = B D^-1 m').  The eager kernels keep all of it current and leave b_psi behind (bpsi_stale: b_psi = D^-1 B^T b).
+    int sp_applied = 0, s_applied = 0;
+    double* psi_ring = nullptr;      // SSPBO_SINV_RING x d, natural order
     int sinv_pending = 0;
+    double* bpsi = nullptr;          // d, rank order: beta sum_t t psi_t
+    bool bm_stale = false, bpsi_stale = false;
+    double* lr_gh = nullptr;         // scratch of k_blr_update_lr: 2 SSPBO_LR_MAX + 32 doubles
+    double* syn_rows = nullptr;      // scratch: SSPBO_SINV_RING x d rows synthesised into phi-space
     bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead
     bool f8_disabled = false;        // policy: the factor form's own flag list overflowed, AUTO uses the engines that never flag
     bool p32_disabled = false;       // policy: candidates outside the declared |x| bound were seen
@@ -238,7 +244,7 @@ int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
 int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed,
                           double* obs_out = nullptr);
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
-                           double* vd_row, double* obs_out, double* phi_ring_row, cudaStream_t st);
+                           double* vd_row, double* obs_out, cudaStream_t st);
 // low-rank engines with the A operand in tensor memory: prototypes in sspbo_lr_common.cuh (they take a candidate descriptor)
 int sspbo_score_lr_supported(const sspbo_ctx* ctx);
 void sspbo_lr_release(sspbo_ctx* ctx);
@@ -248,14 +254,18 @@ double sspbo_f8_cost(const sspbo_ctx* ctx, int form);
 // L = chol(Sp) into ctx->R when the psi-space covariance changed since the last factorisation
 int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st);
 constexpr int SSPBO_SINV_RING = 32;
-// Sp / S_inv current (folds in what the deferred updates left out); no-ops when nothing is pending
+// what the low-rank updates left out, folded in (no-ops when nothing is pending): Sp; S and m; S_inv; b; everything
 int sspbo_ensure_sp(sspbo_ctx* ctx, cudaStream_t st);
+int sspbo_ensure_s(sspbo_ctx* ctx, cudaStream_t st);
 int sspbo_ensure_sinv(sspbo_ctx* ctx, cudaStream_t st);
-// Before a fused posterior update.  append (the observation appends a row of V): *ring_row = where the kernel keeps phi for
-// S_inv (the ring is flushed first when full) and Sp / S_inv are left for later; otherwise both are brought up to date and
-// *ring_row = nullptr (the kernel updates them itself).  sspbo_update_done: bookkeeping after the launch was enqueued.
-int sspbo_update_prepare(sspbo_ctx* ctx, bool append, cudaStream_t st, double** ring_row);
-void sspbo_update_done(sspbo_ctx* ctx, bool appended, bool deferred);
+int sspbo_ensure_bm(sspbo_ctx* ctx, cudaStream_t st);
+int sspbo_ensure_all(sspbo_ctx* ctx, cudaStream_t st);
+// before a low-rank update: scratch buffers, b_psi current, *ring_row = where the kernel keeps psi for S_inv
+int sspbo_lr_update_prepare(sspbo_ctx* ctx, cudaStream_t st, double** ring_row);
+// after an eager update (which keeps the d x d state current itself)
+void sspbo_eager_update_done(sspbo_ctx* ctx);
+int sspbo_blr_update_lr(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* const* phi_dev, const double* ts_host,
+                        cudaStream_t st, int* failed, double* obs_out);
 // CUtensorMap (passed as void*) of a K-major fp16 operand [rows x KC_pad], box 64 columns x BN rows, 128-byte swizzle
 int sspbo_make_map_f16(sspbo_ctx* ctx, void* map, const void* base, int KC_pad, int rows, int BN);
 int sspbo_refresh_operands(sspbo_ctx* ctx, cudaStream_t st);

@@ -9,11 +9,6 @@
 //       S -= coef v v^T,  S_inv += beta phi phi^T,  Sp -= coef' y y^T (my rows);  b += beta t phi;  row of V appended;
 //       m = S b for my rows from the updated values in the same pass
 //   P3  m' = B^T m (my frequencies)
-// Deferred form (UpdateParams::defer, whenever the observation appends a row to V): Sp and S_inv are NOT touched.  Sp = B^T S B
-// gives y = Sp psi = B^T (S phi) = B^T v, an analysis DFT of v (no read of Sp), and psi.y = phi.v; the row of V carries
-// everything Sp needs (Sp -= row^T row, folded in by sspbo_ensure_sp when a consumer wants the matrix), and phi goes into a
-// small ring from which S_inv += beta phi phi^T is applied later in the same order (sspbo_ensure_sinv).  The launch then reads
-// S once and reads + writes it once: 3 d^2 doubles instead of 8 d^2.
 // Float64 throughout, no atomics: the result is bitwise reproducible, so replicated contexts (one per GPU) stay identical.
 // S is updated in the symmetric form v v^T (the reference forms (S phi)(phi^T S), which differs from it by the O(1e-13)
 // asymmetry its S accumulates; both are the same rank-one update of the same posterior).
@@ -30,8 +25,6 @@ constexpr int UP_WARPS = UP_THREADS / 32;
 
 struct UpdateParams {
     int d, K, has_factor, finalize;
-    int defer;                             // Sp and S_inv are brought up to date later (row of V / ring of phi); needs vd_row and phi_ring
-    double* phi_ring;                      // defer: where this observation's phi is kept for S_inv
     double beta, t, r_scale;
     const double* phi;
     double *S, *Sinv, *b, *m;
@@ -127,8 +120,7 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
     }
 
     // ---- P0: psi (rank order) and v = S phi ----
-    const bool defer = p.defer != 0;
-    if (p.has_factor && !psi_given && !defer)
+    if (p.has_factor && !psi_given)
         up_analysis(phi, d, K, p.twiddle, gw, nw, lane, [&](int k, double c, double s) {
             if (k == 0) __stcg(p.psi + p.inv_perm[0], c);
             else { __stcg(p.psi + p.inv_perm[k], c); __stcg(p.psi + p.inv_perm[K + k], -s); }
@@ -144,16 +136,7 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
     team.sync();
 
     // ---- P1: y = Sp psi ----
-    if (p.has_factor && defer) {                                        // = B^T v in rank order: an analysis DFT of v
-        for (int j = tid; j < d; j += UP_THREADS) yv[j] = __ldcg(p.v + j);
-        __syncthreads();
-        const double s0 = 1.0 / d, sk = 2.0 / d;
-        up_analysis(yv, d, K, p.twiddle, gw, nw, lane, [&](int k, double c, double s) {
-            if (k == 0) __stcg(p.y + p.inv_perm[0], s0 * c);
-            else { __stcg(p.y + p.inv_perm[k], sk * c); __stcg(p.y + p.inv_perm[K + k], -sk * s); }
-        });
-        team.sync();                                                    // (every CTA has also finished reading yv as v)
-    } else if (p.has_factor) {
+    if (p.has_factor) {
         for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.psi + j);
         __syncthreads();
         for (int i = gw; i < d; i += nw) {
@@ -174,13 +157,13 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
         part[0] = fma(phi[j], vj, part[0]);
         if (p.has_factor) {
             const double yj = __ldcg(p.y + j);
-            if (!defer) part[1] = fma(vec[j], yj, part[1]);              // vec still holds psi
+            part[1] = fma(vec[j], yj, part[1]);                          // vec still holds psi
             yv[j] = yj;
         }
     }
     up_block_reduce<4>(part, red, tot);
     const double coef = p.beta / (1.0 + p.beta * tot[0]);               // blr.py:64-67 (Sherman-Morrison)
-    const double coef2 = defer ? coef : p.beta / (1.0 + p.beta * tot[1]);   // psi.y = phi.v
+    const double coef2 = p.beta / (1.0 + p.beta * tot[1]);
     if (p.obs_out && cta == 0 && tid == 0) p.obs_out[1] = 1.0 / p.beta + tot[0];   // blr.py:96 before the update
     __syncthreads();                                                    // everyone has read psi from vec
     for (int j = tid; j < d; j += UP_THREADS) vec[j] = __ldcg(p.v + j);
@@ -195,9 +178,9 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
             const double s = fma(-cv, vec[j], srow[j]);
             srow[j] = s;
             acc = fma(s, bp[j], acc);
-            if (!defer) irow[j] = fma(bphi, phi[j], irow[j]);            // blr.py:60: S_inv += beta phi phi^T
+            irow[j] = fma(bphi, phi[j], irow[j]);                       // blr.py:60: S_inv += beta phi phi^T
         }
-        if (p.has_factor && !defer) {
+        if (p.has_factor) {
             double* prow = p.Sp + (size_t)i * d;
             const double cy = coef2 * yv[i];
 #pragma unroll 4
@@ -213,7 +196,6 @@ __device__ __forceinline__ void blr_update_body(const UpdateParams& p, Team& tea
         const double sq = sqrt(coef2);
         for (int j = gt; j < d; j += nt) {
             p.b[j] = bp[j];
-            if (defer) p.phi_ring[j] = phi[j];
             if (p.vd_row) {
                 const double v0 = yv[j] * sq;
                 p.vd_row[j] = v0;
@@ -320,12 +302,169 @@ __global__ void __launch_bounds__(UP_THREADS, 4) k_blr_update_runs(const RunUpda
     }
 }
 
+// ---- the same observation in low-rank form: O(rank x d) instead of O(d^2) ---------------------------------------------------
+// While every observation has appended its row to V (Sp = Sp0 - V^T V, Sp0 the diagonal prior), the whole update can be done
+// in psi-space from the rows of V alone:
+//     psi = D^-1 B^T phi (or straight from the point),   g = V psi,   h = V b_psi'        (b_psi' = b_psi + beta t psi)
+//     y = Sp psi = Sp0 psi - V^T g,      a = psi . y,      coef = beta / (1 + beta a),      new row of V = sqrt(coef) y
+//     m' = Sp_new b_psi' = (Sp0 b_psi' - V^T h) - coef (y . b_psi') y
+// -- the identities behind it: phi = B psi, Sp = B^T S B, b = B b_psi, m' = B^T m = B^T S b = Sp b_psi, m . phi = m' . psi.
+// Nothing of the d x d state (S, S_inv, Sp) nor the phi-space b and m is read or written; they are brought up to date when a
+// consumer asks for them (sspbo_ensure_* in sspbo_core.cu: S -= u u^T with u = B D^-1 row, Sp -= row^T row, S_inv from the ring
+// of psi, b = B b_psi, m = B D^-1 m').  One thread-block cluster per run; V is read twice (the second time from L2).
+// Float64, fixed summation orders: replicated contexts stay bit-identical.
+struct RunLR {
+    int d, K, n, rank, KC_pad;
+    double beta, t, alpha, dc, r_scale;
+    const double* x;                      // the run's point (n float64, device) -- or
+    const double* phi_in;                 // its encoding (d float64, device) when x is null
+    const double* A_turns; const double2* twiddle;
+    const int *perm, *inv_perm, *col_of_rank;
+    double* Vd;                           // rows 0 .. rank-1 in rank order; row `rank` is written
+    __half *Vh, *Vl;                      // operand images: row 0 = m', row r + 1 = observation r
+    double *bpsi, *mp;                    // b_psi (rank order), m' (natural order)
+    double* psi_ring_row;                 // psi of this observation in natural order, kept for S_inv
+    double* gh;                           // scratch: g[LR_MAX], h[LR_MAX], cluster partial sums [2][16]
+    double* psi_x;                        // scratch d: psi in rank order (phi_in path)
+    float* mp_op; float* mscale;
+    double* obs_out;                      // nullable: (m . phi, 1/beta + phi^T S phi) under the posterior before this update
+};
+
+__global__ void __launch_bounds__(UP_THREADS, 2) k_blr_update_lr(const RunLR* __restrict__ runs) {
+    extern __shared__ __align__(16) double sm[];
+    ClusterTeam team;
+    const int run = blockIdx.x / team.size();
+    const RunLR& r = runs[run];
+    const int d = r.d, K = r.K, rank = r.rank, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = team.rank(), ncta = team.size();
+    const int gw = cta * UP_WARPS + warp, nw = ncta * UP_WARPS;
+    double* psi = sm;                     // d, rank order
+    double* bps = psi + d;                // d, b_psi + beta t psi
+    double* ys = bps + d;                 // d: y (my slice), before that phi_in
+    double* ms = ys + d;                  // d: Sp0 b_psi' - V^T h (my slice)
+    double* gs = ms + d;                  // SSPBO_LR_MAX
+    double* hs = gs + SSPBO_LR_MAX;       // SSPBO_LR_MAX
+    double* red = hs + SSPBO_LR_MAX;      // UP_WARPS x 4
+    double* tot = red + UP_WARPS * 4;     // 4
+
+    // ---- psi (rank order) ----
+    if (r.x) {                            // from the point: every CTA evaluates all K phases (sspspace.py:270-275)
+        for (int k = tid; k < K; k += UP_THREADS) {
+            double t = 0.0;
+            for (int a = 0; a < r.n; ++a) t = fma(r.A_turns[(size_t)k * r.n + a], r.x[a], t);
+            t -= rint(t);
+            double sn, cs;
+            sincospi(2.0 * t, &sn, &cs);
+            psi[r.inv_perm[1 + k]] = cs; psi[r.inv_perm[1 + K + k]] = sn;
+        }
+        if (tid == 0) psi[r.inv_perm[0]] = r.dc;
+    } else {                              // from phi: psi = D^-1 B^T phi, the frequencies shared out over the cluster
+        for (int j = tid; j < d; j += UP_THREADS) ys[j] = r.phi_in[j];
+        __syncthreads();
+        up_analysis(ys, d, K, r.twiddle, gw, nw, lane, [&](int k, double c, double s) {
+            if (k == 0) __stcg(r.psi_x + r.inv_perm[0], c);
+            else { __stcg(r.psi_x + r.inv_perm[k], c); __stcg(r.psi_x + r.inv_perm[K + k], -s); }
+        });
+        team.sync();
+        for (int j = tid; j < d; j += UP_THREADS) psi[j] = __ldcg(r.psi_x + j);
+    }
+    __syncthreads();
+    for (int j = tid; j < d; j += UP_THREADS) bps[j] = fma(r.beta * r.t, psi[j], r.bpsi[j]);
+    if (cta == 0) {
+        for (int j = tid; j < d; j += UP_THREADS) r.psi_ring_row[r.perm[j]] = psi[j];
+        if (r.obs_out) {                  // predictive mean under the old posterior: m . phi = m' . psi
+            double mu[1] = {0.0};
+            for (int j = tid; j < d; j += UP_THREADS) mu[0] = fma(r.mp[r.perm[j]], psi[j], mu[0]);
+            up_block_reduce<1>(mu, red, tot);
+            if (tid == 0) r.obs_out[0] = tot[0];
+        }
+    }
+    __syncthreads();
+
+    // ---- g = V psi, h = V b_psi' : one warp per row ----
+    for (int i = gw; i < rank; i += nw) {
+        const double* row = r.Vd + (size_t)i * d;
+        double g = 0.0, h = 0.0;
+#pragma unroll 4
+        for (int j = lane; j < d; j += 32) { const double v = row[j]; g = fma(v, psi[j], g); h = fma(v, bps[j], h); }
+        g = up_warp_sum(g); h = up_warp_sum(h);
+        if (lane == 0) { __stcg(r.gh + i, g); __stcg(r.gh + SSPBO_LR_MAX + i, h); }
+    }
+    team.sync();
+    for (int i = tid; i < rank; i += UP_THREADS) { gs[i] = __ldcg(r.gh + i); hs[i] = __ldcg(r.gh + SSPBO_LR_MAX + i); }
+    __syncthreads();
+
+    // ---- my slice of y = Sp0 psi - V^T g and of Sp0 b_psi' - V^T h ; partial sums of psi . y and y . b_psi' ----
+    const int j0 = (int)((long long)d * cta / ncta), j1 = (int)((long long)d * (cta + 1) / ncta);
+    const double p0 = 1.0 / ((double)d * r.alpha), pk = 2.0 / ((double)d * r.alpha);      // Sp0 = B^T B / alpha (diagonal)
+    double part[2] = {0.0, 0.0};
+    for (int j = j0 + tid; j < j1; j += UP_THREADS) {
+        const double sp0 = (r.perm[j] == 0) ? p0 : pk;
+        double y = sp0 * psi[j], mm = sp0 * bps[j];
+        for (int i = 0; i < rank; ++i) {
+            const double v = r.Vd[(size_t)i * d + j];
+            y = fma(-gs[i], v, y); mm = fma(-hs[i], v, mm);
+        }
+        ys[j] = y; ms[j] = mm;
+        part[0] = fma(psi[j], y, part[0]); part[1] = fma(y, bps[j], part[1]);
+    }
+    up_block_reduce<2>(part, red, tot);
+    if (tid < 2) __stcg(r.gh + 2 * SSPBO_LR_MAX + tid * 16 + cta, tot[tid]);
+    team.sync();
+    double a = 0.0, yb = 0.0;
+    for (int c = 0; c < ncta; ++c) { a += __ldcg(r.gh + 2 * SSPBO_LR_MAX + c); yb += __ldcg(r.gh + 2 * SSPBO_LR_MAX + 16 + c); }
+    const double coef = r.beta / (1.0 + r.beta * a);                    // blr.py:64-67 (Sherman-Morrison)
+    if (r.obs_out && cta == 0 && tid == 0) r.obs_out[1] = 1.0 / r.beta + a;   // blr.py:96 before the update
+
+    // ---- the new row of V, m', b_psi (my slice) ----
+    {
+        const double sq = sqrt(coef), cyb = coef * yb;
+        double* vd_row = r.Vd + (size_t)rank * d;
+        __half* vh_row = r.Vh + (size_t)(rank + 1) * r.KC_pad;
+        __half* vl_row = r.Vl + (size_t)(rank + 1) * r.KC_pad;
+        for (int j = j0 + tid; j < j1; j += UP_THREADS) {
+            const double y = ys[j];
+            const double v0 = y * sq;
+            vd_row[j] = v0;
+            const double vs = v0 * r.r_scale;
+            const __half hh = __double2half(vs);
+            const int c = r.col_of_rank[j];
+            vh_row[c] = hh;
+            vl_row[c] = __double2half(vs - (double)__half2float(hh));
+            __stcg(r.mp + r.perm[j], fma(-cyb, y, ms[j]));
+            r.bpsi[j] = bps[j];
+        }
+    }
+    team.sync();                                                         // m' complete
+    if (cta != 0) return;
+    // tail (k_mp_op): m' scaled by a power of two into row 0 of the operand images, and in operand order as float32
+    double mx = 0.0;
+    for (int k = tid; k < d; k += UP_THREADS) mx = fmax(mx, fabs(__ldcg(r.mp + k)));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    double m_all = 0.0;
+    for (int w = 0; w < UP_WARPS; ++w) m_all = fmax(m_all, red[w]);
+    const double sc = (m_all > 0.0 && isfinite(m_all)) ? exp2(floor(log2(1024.0 / m_all))) : 1.0;
+    if (tid == 0) *r.mscale = (float)(1.0 / sc);
+    for (int kk = tid; kk < d; kk += UP_THREADS) {
+        const double m = __ldcg(r.mp + r.perm[kk]);
+        const int c = r.col_of_rank[kk];
+        r.mp_op[c] = (float)m;
+        const double v = m * sc;
+        const __half h = __double2half(v);
+        r.Vh[c] = h;
+        r.Vl[c] = __double2half(v - (double)__half2float(h));
+    }
+}
+
 }  // namespace
 
 // One observation.  Returns SSPBO_EUNSUPPORTED (without touching the state) when the device cannot run it; the caller then
 // falls back to the unfused kernels.
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
-                           double* vd_row, double* obs_out, double* phi_ring_row, cudaStream_t st) {
+                           double* vd_row, double* obs_out, cudaStream_t st) {
     const int d = ctx->d;
     const size_t smem = ((size_t)4 * d + UP_WARPS * 4 + 4) * sizeof(double);
     if (ctx->fused_update_ok < 0) {                       // probe once
@@ -343,7 +482,6 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
     p.twiddle = ctx->twiddle; p.inv_perm = ctx->inv_perm; p.col_of_rank = ctx->col_of_rank;
     p.v = ctx->v; p.psi = ctx->psi; p.y = ctx->y;
     p.vh_row = vh_row; p.vl_row = vl_row; p.vd_row = vd_row; p.obs_out = obs_out;
-    p.defer = (phi_ring_row && vd_row && ctx->has_factor) ? 1 : 0; p.phi_ring = phi_ring_row;
     int G = (d + UP_WARPS - 1) / UP_WARPS;
     if (G > ctx->sm_count) G = ctx->sm_count;
     void* args[] = {(void*)&p};
@@ -358,6 +496,10 @@ int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool fin
 int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed,
                           double* obs_out) {
     if (R <= 0) return SSPBO_OK;
+    {   // every run can append its row of V: the low-rank form, O(rank d) per run
+        const int rc = sspbo_blr_update_lr(ctxs, R, x_host, nullptr, ts_host, st, failed, obs_out);
+        if (rc != SSPBO_EUNSUPPORTED) return rc;
+    }
     sspbo_ctx* c0 = ctxs[0];
     int d_max = 0, n_max = 0;
     for (int r = 0; r < R; ++r) {
@@ -396,6 +538,10 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
             if (cudaMalloc((void**)&c->obs_phi, (size_t)d * sizeof(double)) != cudaSuccess) { if (failed) *failed = r; SSPBO_FAIL(c, SSPBO_ECUDA, "update_batch: out of device memory"); }
             c->obs_phi_cap = (size_t)d;
         }
+        {   // this kernel keeps the d x d state current itself: fold in what low-rank updates left pending
+            const int rc = sspbo_ensure_all(c, st);
+            if (rc) { if (failed) *failed = r; return rc; }
+        }
         RunUpdate& u = hp[r];
         UpdateParams& p = u.up;
         p.d = d; p.K = c->K; p.has_factor = 1; p.finalize = 1;
@@ -410,11 +556,6 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
                 const size_t off = (size_t)(c->lr_rank + 1) * c->KC_pad;
                 p.vh_row = c->Vh + off; p.vl_row = c->Vl + off; p.vd_row = c->Vd + (size_t)c->lr_rank * d;
             }
-        }
-        {   // with a row of V to append, Sp and S_inv are left for later (ring of phi); otherwise they are made current here
-            const int rc_p = sspbo_update_prepare(c, p.vd_row != nullptr, st, &p.phi_ring);
-            if (rc_p) { if (failed) *failed = r; return rc_p; }
-            p.defer = p.phi_ring ? 1 : 0;
         }
         u.x = dx + (size_t)r * n_max; u.A_turns = c->A_turns; u.n = c->n; u.dc = c->dc; u.phi_out = c->obs_phi;
         u.perm = c->perm; u.mp_op = c->mp_op; u.vh0 = c->Vh; u.vl0 = c->Vl; u.mscale = c->mscale;
@@ -435,7 +576,81 @@ int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, c
     c0->launches++;
     for (int r = 0; r < R; ++r) {
         sspbo_ctx* c = ctxs[r];
-        sspbo_update_done(c, hp[r].up.vd_row != nullptr, hp[r].up.defer != 0);
+        if (hp[r].up.vd_row) c->lr_rank++;
+        sspbo_eager_update_done(c);
+        c->v8_row0_dirty = true;
+        c->operands_dirty = true; c->factor_dirty = true; c->f8_factor_dirty = true;
+    }
+    return SSPBO_OK;
+}
+
+// One observation for each of R runs in low-rank form (k_blr_update_lr), one launch.  x_host (R rows of n, nullable) or
+// phi_dev (R device pointers to d-vectors).  SSPBO_EUNSUPPORTED -- nothing enqueued, no state touched -- unless every run is a
+// posterior over an SSP space whose observations have all appended their row to V and that has room for one more.
+int sspbo_blr_update_lr(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* const* phi_dev, const double* ts_host,
+                        cudaStream_t st, int* failed, double* obs_out) {
+    if (R <= 0) return SSPBO_OK;
+    sspbo_ctx* c0 = ctxs[0];
+    int d_max = 0, n_max = 0;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        if (!c || c->K == 0 || !c->blr_ready || !c->has_beta || !c->has_factor || c->unfused_update || !c->lr_valid ||
+            c->lr_rank >= SSPBO_LR_MAX || c->device != c0->device)
+            return SSPBO_EUNSUPPORTED;
+        if (x_host && (c->L != 1 || c->normalize || c->n != c0->n)) return SSPBO_EUNSUPPORTED;
+        d_max = c->d > d_max ? c->d : d_max;
+        n_max = c->n > n_max ? c->n : n_max;
+    }
+    int cluster_ok = 0;
+    cudaDeviceGetAttribute(&cluster_ok, cudaDevAttrClusterLaunch, c0->device);
+    const size_t smem = ((size_t)4 * d_max + 2 * SSPBO_LR_MAX + UP_WARPS * 4 + 4) * sizeof(double);
+    if (!cluster_ok || smem > 100 * 1024) return SSPBO_EUNSUPPORTED;
+    SSPBO_CUDA(c0, cudaSetDevice(c0->device));
+    const size_t bytes = (size_t)R * sizeof(RunLR) + (size_t)R * n_max * sizeof(double);
+    if (c0->batch_pin) SSPBO_CUDA(c0, cudaEventSynchronize(c0->batch_event));   // the previous upload has left the pinned buffer
+    if (bytes > c0->batch_bytes) {
+        if (c0->batch_pin) { SSPBO_CUDA(c0, cudaStreamSynchronize(st)); cudaFreeHost(c0->batch_pin); cudaFree(c0->batch_dev); c0->batch_pin = nullptr; c0->batch_dev = nullptr; }
+        else SSPBO_CUDA(c0, cudaEventCreateWithFlags(&c0->batch_event, cudaEventDisableTiming));
+        c0->batch_bytes = 0;
+        SSPBO_CUDA(c0, cudaMallocHost(&c0->batch_pin, bytes));
+        SSPBO_CUDA(c0, cudaMalloc(&c0->batch_dev, bytes));
+        c0->batch_bytes = bytes;
+    }
+    RunLR* hp = (RunLR*)c0->batch_pin;
+    double* hx = (double*)((char*)c0->batch_pin + (size_t)R * sizeof(RunLR));
+    const RunLR* dp = (const RunLR*)c0->batch_dev;
+    const double* dx = (const double*)((const char*)c0->batch_dev + (size_t)R * sizeof(RunLR));
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        double* ring_row = nullptr;
+        const int rc = sspbo_lr_update_prepare(c, st, &ring_row);           // scratch, b_psi current, room in the ring of psi
+        if (rc) { if (failed) *failed = r; return rc; }
+        RunLR& u = hp[r];
+        u.d = c->d; u.K = c->K; u.n = c->n; u.rank = c->lr_rank; u.KC_pad = c->KC_pad;
+        u.beta = c->beta; u.t = ts_host[r]; u.alpha = c->alpha; u.dc = c->dc; u.r_scale = c->r_scale;
+        u.x = x_host ? dx + (size_t)r * n_max : nullptr; u.phi_in = x_host ? nullptr : phi_dev[r];
+        u.A_turns = c->A_turns; u.twiddle = c->twiddle; u.perm = c->perm; u.inv_perm = c->inv_perm; u.col_of_rank = c->col_of_rank;
+        u.Vd = c->Vd; u.Vh = c->Vh; u.Vl = c->Vl; u.bpsi = c->bpsi; u.mp = c->mp; u.psi_ring_row = ring_row;
+        u.gh = c->lr_gh; u.psi_x = c->psi; u.mp_op = c->mp_op; u.mscale = c->mscale;
+        u.obs_out = (R == 1) ? obs_out : nullptr;
+        if (x_host) for (int a = 0; a < c->n; ++a) hx[(size_t)r * n_max + a] = x_host[(size_t)r * c->n + a];
+    }
+    SSPBO_CUDA(c0, cudaMemcpyAsync(c0->batch_dev, c0->batch_pin, bytes, cudaMemcpyHostToDevice, st));
+    SSPBO_CUDA(c0, cudaEventRecord(c0->batch_event, st));
+    // one cluster per run: 4 CTAs (8 from d = 768 on) share the rows of V and the components of y
+    const int G = d_max >= 768 ? 8 : 4;
+    SSPBO_CUDA(c0, cudaFuncSetAttribute(k_blr_update_lr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(R * G)); cfg.blockDim = dim3(UP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SSPBO_CUDA(c0, cudaLaunchKernelEx(&cfg, k_blr_update_lr, dp));
+    c0->launches++;
+    for (int r = 0; r < R; ++r) {
+        sspbo_ctx* c = ctxs[r];
+        c->lr_rank++; c->sinv_pending++; c->bm_stale = true;
         c->v8_row0_dirty = true;
         c->operands_dirty = true; c->factor_dirty = true; c->f8_factor_dirty = true;
     }
