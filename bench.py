@@ -649,7 +649,7 @@ def encode_only(eng, cand, peaks, n=1 << 16, reps=3):
 
 
 def update_cost(agt, sp, orc, reps=20):
-    """One posterior observation: device float64 rank-one update (encode x_t + K3, about 15 launches) against the
+    """One posterior observation: device float64 rank-one update (x_t encoded inside K3's single launch) against the
     reference's expression restated in numpy (blr.py:63-75, O(d^3) as written there), same d."""
     import torch
     rng = np.random.default_rng(11)
@@ -661,6 +661,11 @@ def update_cost(agt, sp, orc, reps=20):
         agt.update(xs[i:i + 1], np.atleast_2d(ys[i]), np.array([0.0]))
     torch.cuda.synchronize()
     gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    # the low-rank updates leave S, S_inv, b, m for later: what reading them afterwards costs (all `reps` observations folded in)
+    t0 = time.perf_counter()
+    agt._scoring_engine().blr_get(m=True, S=True, Sinv=True)
+    torch.cuda.synchronize()
+    fold_ms = (time.perf_counter() - t0) * 1e3
     ref = orc.BLR(sp.ssp_dim, beta=1.0)
     phis = orc.encode(sp.phase_matrix, LS * np.ones(N_DIM), xs[:3])
     ref.update(phis[:1], np.atleast_2d(ys[0]))
@@ -669,8 +674,9 @@ def update_cost(agt, sp, orc, reps=20):
         ref.update(phis[i:i + 1], np.atleast_2d(ys[i]))
     cpu_ms = (time.perf_counter() - t0) / 2 * 1e3
     return {"gpu_ms_per_observation": gpu_ms, "cpu_port_ms_per_observation": cpu_ms, "d": int(sp.ssp_dim),
-            "note": "wall clock incl. host calls; the device update is O(d^2) float64 (S, S_inv, psi-space covariance, one "
-                    "operand row), the reference expression O(d^3)"}
+            "dense_state_on_demand_ms": fold_ms, "dense_state_observations_folded": reps,
+            "note": "wall clock incl. host calls; the device update is float64 in low-rank form, O(rank d) from the rows of V "
+                    "(k_blr_update_lr; S, S_inv, psi-space covariance follow on demand), the reference expression O(d^3)"}
 
 
 def acq_ascent_cost(agt, sp, orc, restarts=8, steps=100, reps=5):

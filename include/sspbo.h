@@ -157,6 +157,11 @@ int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev
 int64_t sspbo_blr_export_size(const sspbo_ctx* ctx);          /* number of float64 in the packed state */
 int sspbo_blr_export(sspbo_ctx* ctx, double* packed_dev, void* stream);
 int sspbo_blr_import(sspbo_ctx* ctx, const double* packed_dev, double beta, void* stream);
+/* rank word of the packed state sspbo_blr_export would write now: number of valid low-rank rows, -1 when they are not valid */
+int sspbo_blr_rank(const sspbo_ctx* ctx, int* lr_rank);
+/* sspbo_blr_import for a caller that knows that word (the exporting context is in the same process: a posterior restored
+ * every step, a drift guard): skips the synchronising read-back of it, so the import is purely stream-ordered */
+int sspbo_blr_import_ranked(sspbo_ctx* ctx, const double* packed_dev, double beta, int lr_rank, void* stream);
 /* blr.py:84-97: var = 1/beta + diag(phi S phi^T), mu = m^T phi^T.  phi_dev N x d f64 -> mu (N), var (N) f64 */
 int sspbo_blr_predict(sspbo_ctx* ctx, const double* phi_dev, int64_t N, double* mu_dev, double* var_dev, void* stream);
 

@@ -1944,7 +1944,19 @@ extern "C" int sspbo_blr_export(sspbo_ctx* ctx, double* packed, void* stream) {
     }
     return SSPBO_OK;
 }
+static int blr_import_impl(sspbo_ctx* ctx, const double* packed, double beta, bool rank_known, int lr_rank_known, void* stream);
 extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double beta, void* stream) {
+    return blr_import_impl(ctx, packed, beta, false, -1, stream);
+}
+extern "C" int sspbo_blr_import_ranked(sspbo_ctx* ctx, const double* packed, double beta, int lr_rank, void* stream) {
+    return blr_import_impl(ctx, packed, beta, true, lr_rank, stream);
+}
+extern "C" int sspbo_blr_rank(const sspbo_ctx* ctx, int* lr_rank) {
+    if (!ctx || !lr_rank) return SSPBO_EINVAL;
+    *lr_rank = (ctx->blr_ready && ctx->has_factor && ctx->lr_valid) ? ctx->lr_rank : -1;
+    return SSPBO_OK;
+}
+static int blr_import_impl(sspbo_ctx* ctx, const double* packed, double beta, bool rank_known, int lr_rank_known, void* stream) {
     if (!ctx) return SSPBO_EINVAL;
     if (!ctx->blr_ready || !packed) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_import: not initialised / null");
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1961,9 +1973,11 @@ extern "C" int sspbo_blr_import(sspbo_ctx* ctx, const double* packed, double bet
     ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
     ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true;   // (S_inv, b, m complete; b_psi follows from b)
     if (ctx->has_factor) {
-        double rank = -1.0;                                      // the rows of V travel with the packed state
-        SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
-        SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+        double rank = (double)lr_rank_known;                     // the rows of V travel with the packed state
+        if (!rank_known) {
+            SSPBO_CUDA(ctx, cudaMemcpyAsync(&rank, packed + off, sizeof(double), cudaMemcpyDeviceToHost, st));
+            SSPBO_CUDA(ctx, cudaStreamSynchronize(st));
+        }
         off += 1;
         SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->Vd, packed + off, (size_t)SSPBO_LR_MAX * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
         const size_t img = (size_t)(SSPBO_LR_MAX + 1) * ctx->KC_pad * sizeof(__half);
@@ -2388,7 +2402,7 @@ extern "C" int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, dou
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (ctx->unfused_update || ctx->fused_update_ok <= 0) {   // fused kernel unavailable (or not probed yet): the two calls it replaces
+    if (ctx->unfused_update || !sspbo_fused_update_available(ctx)) {   // no single-launch update on this device: the two calls it replaces
         double acq;
         if ((rc = sspbo_eval_host(ctx, x_host, 1, 0.0, 0.0, mu_host, var_host, &acq, stream))) return rc;
         return sspbo_blr_update_x(ctx, x_host, &t, 1, stream);

@@ -243,6 +243,7 @@ int sspbo_encode_umma_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t
 // one observation of the posterior update in one cooperative launch (sspbo_update.cu); SSPBO_EUNSUPPORTED -> unfused kernels
 int sspbo_blr_update_runs(sspbo_ctx* const* ctxs, int R, const double* x_host, const double* ts_host, cudaStream_t st, int* failed,
                           double* obs_out = nullptr);
+bool sspbo_fused_update_available(sspbo_ctx* ctx);
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
                            double* vd_row, double* obs_out, cudaStream_t st);
 // low-rank engines with the A operand in tensor memory: prototypes in sspbo_lr_common.cuh (they take a candidate descriptor)

@@ -461,19 +461,25 @@ __global__ void __launch_bounds__(UP_THREADS, 2) k_blr_update_lr(const RunLR* __
 
 }  // namespace
 
+// whether the single-launch updates (cooperative grid / clusters) can run on this device at this dimension; probed once
+bool sspbo_fused_update_available(sspbo_ctx* ctx) {
+    const size_t smem = ((size_t)4 * ctx->d + UP_WARPS * 4 + 4) * sizeof(double);
+    if (ctx->fused_update_ok < 0) {
+        int smem_max = 0, coop = 0;
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        ctx->fused_update_ok = (coop && smem <= (size_t)smem_max && smem <= 200 * 1024) ? 1 : 0;
+    }
+    return ctx->fused_update_ok > 0;
+}
+
 // One observation.  Returns SSPBO_EUNSUPPORTED (without touching the state) when the device cannot run it; the caller then
 // falls back to the unfused kernels.
 int sspbo_blr_update_fused(sspbo_ctx* ctx, const double* phi, double t, bool finalize, __half* vh_row, __half* vl_row,
                            double* vd_row, double* obs_out, cudaStream_t st) {
     const int d = ctx->d;
     const size_t smem = ((size_t)4 * d + UP_WARPS * 4 + 4) * sizeof(double);
-    if (ctx->fused_update_ok < 0) {                       // probe once
-        int smem_max = 0, coop = 0;
-        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        ctx->fused_update_ok = (coop && smem <= (size_t)smem_max) ? 1 : 0;
-    }
-    if (!ctx->fused_update_ok || smem > 200 * 1024) return SSPBO_EUNSUPPORTED;
+    if (!sspbo_fused_update_available(ctx)) return SSPBO_EUNSUPPORTED;
     SSPBO_CUDA(ctx, cudaFuncSetAttribute(k_blr_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UpdateParams p;
     p.d = d; p.K = ctx->K; p.has_factor = ctx->has_factor ? 1 : 0; p.finalize = finalize ? 1 : 0;

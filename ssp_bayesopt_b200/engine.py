@@ -280,11 +280,22 @@ class DeviceEngine:
         n = self.lib.sspbo_blr_export_size(self._ctx)
         buf = self.torch.empty(n, dtype=self.torch.float64, device=self._dev())
         self._check(self.lib.sspbo_blr_export(self._ctx, C.c_void_p(buf.data_ptr()), self._stream()), "sspbo_blr_export")
+        buf.sspbo_lr_rank = self.blr_rank()         # travels with the tensor inside this process: lets blr_import skip a read-back
         return buf
+
+    def blr_rank(self) -> int:
+        """Number of valid low-rank rows of the posterior (= observations so far), -1 when they are not valid."""
+        r = C.c_int(-1)
+        self._check(self.lib.sspbo_blr_rank(self._ctx, C.byref(r)), "sspbo_blr_rank")
+        return int(r.value)
 
     def blr_import(self, buf, beta) -> None:
         assert buf.numel() == self.lib.sspbo_blr_export_size(self._ctx)
-        rc = self.lib.sspbo_blr_import(self._ctx, C.c_void_p(buf.data_ptr()), float(beta or 0.0), self._stream())
+        rank = getattr(buf, "sspbo_lr_rank", None)
+        if rank is None:                            # (a buffer received from another process: the rank word is read back)
+            rc = self.lib.sspbo_blr_import(self._ctx, C.c_void_p(buf.data_ptr()), float(beta or 0.0), self._stream())
+        else:
+            rc = self.lib.sspbo_blr_import_ranked(self._ctx, C.c_void_p(buf.data_ptr()), float(beta or 0.0), int(rank), self._stream())
         self._check(rc, "sspbo_blr_import")
 
     def blr_predict(self, phi):

@@ -568,3 +568,74 @@ def test_multi_agent_length_scale_search(pkg, golden):
     T = orc.traj_timestep_ssps(agt.ssp_t_space.phase_matrix, np.array([ls[-1]]), L)
     want = orc.multi_agent_encode(As, [ls[0] * np.ones(xd)] * n_agents, T, agt.agent_sps, trajs[:4], L, n_agents, xd)
     np.testing.assert_allclose(agt.encode(trajs[:4]), want, atol=5e-13)
+
+
+# ------------------------------------------------------------------ low-rank posterior updates: the dense state on demand
+@pytest.mark.gpu
+def test_low_rank_updates_keep_the_dense_state_on_demand(pkg):
+    """Updates in low-rank form (k_blr_update_lr) touch only the rows of V, b_psi and m'; S, S_inv, b, m and Sp are folded in
+    when somebody reads them.  Sequences that exercise every hand-over -- more pending observations than the S_inv ring
+    holds, reads between updates (predict: S and m; tiny eval: Sp; attribute reads), the unfused kernels in between, a
+    multi-point update, export / import -- against the oracle's BLR (blr.py:39-97) at every checkpoint."""
+    from ssp_bayesopt_b200 import _lib
+    rng = np.random.default_rng(12)
+    bounds = np.array([[-2.0, 2.0]] * 3)
+    sp = pkg.RandomSSPSpace(3, ssp_dim=129, domain_bounds=bounds, length_scale=0.7, rng=2)
+    d = sp.ssp_dim
+    X = rng.uniform(-2, 2, (120, 3))
+    y = (np.sin(X[:, :1]) - 0.4 * X[:, 1:2] ** 2 + 0.1 * X[:, 2:3])
+    phis = orc.encode(sp.phase_matrix, 0.7 * np.ones(3), X)
+    agt = pkg.SSPAgent(X[:6], y[:6], sp, length_scale=0.7, decoder_method="from-set", gamma_c=0.0, beta_ucb=5.0)
+    eng = agt._scoring_engine()
+    ref = orc.BLR(d)
+    ref.update(phis[:6], y[:6])
+
+    def check(tag):
+        model = agt.blr
+        assert rel(model.m, ref.m) < 1e-8, (tag, rel(model.m, ref.m))
+        assert rel(model.S, ref.S) < 1e-8, (tag, rel(model.S, ref.S))
+        assert rel(model.S_inv, ref.S_inv) < 1e-10, (tag, rel(model.S_inv, ref.S_inv))
+        xq = rng.uniform(-2, 2, (5, 3))
+        mu, var, _ = agt.eval(xq)                                           # float64 engine over Sp
+        rmu, rvar = ref.predict(orc.encode(sp.phase_matrix, 0.7 * np.ones(3), xq))
+        np.testing.assert_allclose(np.ravel(mu), np.ravel(rmu), rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(np.ravel(var), np.ravel(rvar), rtol=1e-7)
+        pmu, pvar = model.predict(phis[:4])                                  # k_predict over S, m
+        rmu, rvar = ref.predict(phis[:4])
+        np.testing.assert_allclose(np.ravel(pmu), np.ravel(rmu), rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(np.ravel(pvar), np.ravel(rvar), rtol=1e-7)
+
+    check("initial design")
+    i = 6
+    for _ in range(40):                                                      # more than the ring of 32, nothing read in between
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0); ref.update(phis[i:i + 1], y[i:i + 1]); i += 1
+    check("40 single observations")
+    for _ in range(3):                                                       # reads between single observations
+        mu, var = eng.observe(X[i], float(y[i, 0]))
+        rmu, rvar = ref.predict(phis[i:i + 1])
+        np.testing.assert_allclose([mu, var], [float(np.ravel(rmu)[0]), float(np.ravel(rvar)[0])], rtol=1e-7, atol=1e-9)
+        ref.update(phis[i:i + 1], y[i:i + 1]); i += 1
+        check("observe + read")
+    assert eng.lib.sspbo_set_update_path(eng._ctx, 0) == 0                   # the separate kernels, which update everything in place
+    for _ in range(3):
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0); ref.update(phis[i:i + 1], y[i:i + 1]); i += 1
+    assert eng.lib.sspbo_set_update_path(eng._ctx, 1) == 0
+    for _ in range(5):                                                       # back to the low-rank form: b_psi rebuilt from b
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0); ref.update(phis[i:i + 1], y[i:i + 1]); i += 1
+    check("unfused kernels in between")
+    agt.update(X[i:i + 7], y[i:i + 7], 0.0); ref.update(phis[i:i + 7], y[i:i + 7]); i += 7     # several points in one call
+    check("seven points in one call")
+    packed = eng.blr_export()                                                # complete state leaves; low-rank rows travel with it
+    for _ in range(4):
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0)
+    eng.blr_import(packed, None)
+    for _ in range(4):
+        agt.update(X[i:i + 1], y[i:i + 1], 0.0); ref.update(phis[i:i + 1], y[i:i + 1]); i += 1
+    check("after import")
+    # scoring with every engine still agrees with the reference posterior
+    xc = rng.uniform(-2, 2, (3000, 3)).astype(np.float32)
+    ref_mu, ref_var, ref_acq = orc.agent_eval(orc.encode(sp.phase_matrix, 0.7 * np.ones(3), xc.astype(np.float64)), ref, 5.0, 0.0)
+    for code in (_lib.ENGINE_UMMA_LR, _lib.ENGINE_UMMA, _lib.ENGINE_SIMT, _lib.ENGINE_EXACT):
+        _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True, engine=code)
+        assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
+        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
