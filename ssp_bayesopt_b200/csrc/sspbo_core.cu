@@ -566,41 +566,22 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
     unsigned long long my_best = 0ull;
     // arg-max only (no per-candidate outputs): a flagged candidate whose score bound cannot beat the best key so far is skipped
     const bool prune = best != nullptr && !mu_out && !var_out && !acq_out;
-    __shared__ int keep_s;
-    for (int64_t base = (int64_t)cta * EX_G; base < count; base += (int64_t)ncta * EX_G) {
-        __syncthreads();
-        if (prune) {
-            if (threadIdx.x == 0) {
-                const unsigned int ob = (unsigned int)(*(volatile unsigned long long*)best >> 32);     // orderable bits of the best score
-                int keep = 0;
-                if (ob != 0xffffffffu) {                                                             // (NaN already won)
-                    const float bs = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
-                    for (int c = 0; c < EX_G && base + c < count; ++c) {
-                        const float ub = __uint_as_float(list[cap + base + c]);
-                        if (!(ub + 1e-3f * (fabsf(ub) + fabsf(bs)) < bs) || ob == 0u) ++keep;
-                    }
-                }
-                keep_s = keep;
-                if (keep) atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)keep);
-            }
-            __syncthreads();
-            if (keep_s == 0) continue;
-        } else if (threadIdx.x == 0) {
-            const int64_t nhere = count - base < EX_G ? count - base : EX_G;
-            atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)nhere);
-        }
+    // one group: the EX_G (or fewer) flagged rows in grp_rows
+    __shared__ unsigned int grp_rows[EX_G];
+    __shared__ int grp_n;
+    auto score_group = [&]() {
         if (cand.mode != 0) {
-            if (threadIdx.x < EX_G && base + threadIdx.x < count)
-                sspbo_lr::cand_row_rt(cand, n, index0 + (int64_t)list[base + threadIdx.x], xs_gen[threadIdx.x]);
+            if ((int)threadIdx.x < grp_n)
+                sspbo_lr::cand_row_rt(cand, n, index0 + (int64_t)grp_rows[threadIdx.x], xs_gen[threadIdx.x]);
             __syncthreads();
         }
         for (int i = threadIdx.x; i < EX_G * (K + 1); i += blockDim.x) {
             const int c = i / (K + 1), f = i - c * (K + 1);
             double cs = 0.0, sn = 0.0;
-            if (base + c < count) {
+            if (c < grp_n) {
                 if (f == 0) cs = dc_value;
                 else if (cand.mode != 0) psi_entry(xs_gen[c], A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
-                else psi_entry(x + (int64_t)list[base + c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
+                else psi_entry(x + (int64_t)grp_rows[c] * n * L, A_turns, tau_turns, n, K, L, f - 1, cs, sn, ncls);
             }
             if (f == 0) psi_s[c * d + inv_perm[0]] = cs;
             else { psi_s[c * d + inv_perm[f]] = cs; psi_s[c * d + inv_perm[K + f]] = sn; }
@@ -647,7 +628,7 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
             for (int c = 0; c < EX_G; ++c) red[c][warp] = q[c];
         }
         __syncthreads();
-        if (warp < EX_G && base + warp < count) {       // one warp per candidate: mu, then the final scalars
+        if (warp < grp_n) {       // one warp per candidate: mu, then the final scalars
             double u = 0.0, ss = 0.0;
             for (int rk = lane; rk < d; rk += 32) {
                 const double pv = psi_s[warp * d + rk];
@@ -665,13 +646,77 @@ __device__ __forceinline__ void exact_lowrank_body(const ExactArgs& ea, int cta,
                 if (normalize) { u *= rsqrt(nrm2); qq /= nrm2; }                        // phi / |phi|
                 const double var = FULL ? inv_beta + qq : inv_beta + (prior_var * (normalize ? 1.0 : nrm2) - qq);   // blr.py:96
                 const double acq = lam * (sqrt(var + gamma_t) - sqrt(gamma_t));         // ssp_agent.py:136
-                const int64_t row = (int64_t)list[base + warp];
+                const int64_t row = (int64_t)grp_rows[warp];
                 if (mu_out) mu_out[row] = (float)u;
                 if (var_out) var_out[row] = (float)var;
                 if (acq_out) acq_out[row] = (float)acq;
                 const unsigned long long key = sspbo_pack((float)(u + acq), (unsigned long long)(index0 + row));
                 if (key > my_best) my_best = key;
             }
+        }
+    };
+    if (!prune) {
+        for (int64_t base = (int64_t)cta * EX_G; base < count; base += (int64_t)ncta * EX_G) {
+            __syncthreads();
+            if (threadIdx.x < EX_G && base + threadIdx.x < count) grp_rows[threadIdx.x] = list[base + threadIdx.x];
+            if (threadIdx.x == 0) {
+                const int64_t nhere = count - base < EX_G ? count - base : EX_G;
+                grp_n = (int)nhere;
+                atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)nhere);
+            }
+            __syncthreads();
+            score_group();
+        }
+    } else {
+        // the whole block tests one flagged candidate per thread against the best key so far; the survivors are queued in
+        // shared memory and scored EX_G at a time (a run of config C4 flags ~10 % of its grid -- everything close to an
+        // observation -- and almost none of it can still win)
+        __shared__ unsigned int queue[EXL_THREADS + EX_G];
+        __shared__ int q_n, warp_cnt[EXL_THREADS / 32];
+        if (threadIdx.x == 0) q_n = 0;
+        __syncthreads();
+        const int T = (int)blockDim.x, nwarps = T >> 5;
+        for (int64_t blk = (int64_t)cta * T; blk < count; blk += (int64_t)ncta * T) {
+            const int64_t i = blk + threadIdx.x;
+            bool keep = false;
+            unsigned int row = 0;
+            if (i < count) {
+                const unsigned int ob = (unsigned int)(*(volatile unsigned long long*)best >> 32);   // orderable bits of the best score
+                row = list[i];
+                if (ob == 0u) keep = true;                                                       // no key yet
+                else if (ob != 0xffffffffu) {                                                    // (else NaN already won)
+                    const float bs = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);
+                    const float ub = __uint_as_float(list[cap + i]);
+                    keep = !(ub + 1e-3f * (fabsf(ub) + fabsf(bs)) < bs);
+                }
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = q_n, tot = 0;
+            for (int w = 0; w < nwarps; ++w) { if (w < warp) off += warp_cnt[w]; tot += warp_cnt[w]; }
+            if (keep) queue[off + __popc(bal & ((1u << lane) - 1u))] = row;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                q_n += tot;
+                if (tot) atomicAdd(const_cast<unsigned long long*>(count_ptr) - SSPBO_STAT_CUR + SSPBO_STAT_RESCORED, (unsigned long long)tot);
+            }
+            __syncthreads();
+            while (q_n >= EX_G) {                                                                // (block-uniform)
+                if (threadIdx.x < EX_G) grp_rows[threadIdx.x] = queue[q_n - EX_G + threadIdx.x];
+                if (threadIdx.x == 0) grp_n = EX_G;
+                __syncthreads();
+                score_group();
+                __syncthreads();
+                if (threadIdx.x == 0) q_n -= EX_G;
+                __syncthreads();
+            }
+        }
+        if (q_n > 0) {
+            if ((int)threadIdx.x < q_n) grp_rows[threadIdx.x] = queue[threadIdx.x];
+            if (threadIdx.x == 0) grp_n = q_n;
+            __syncthreads();
+            score_group();
         }
     }
     if (lane == 0 && my_best && best) atomicMax(best, my_best);

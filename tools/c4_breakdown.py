@@ -36,3 +36,15 @@ for _ in range(steps):
     acc["select_wall"] += t1 - t0; acc["update_wall"] += t3 - t2
     acc["select_gpu"] += ev[0].elapsed_time(ev[1]) * 1e-3; acc["update_gpu"] += ev[2].elapsed_time(ev[3]) * 1e-3
 print({k: round(v / steps * 1e3, 3) for k, v in acc.items()}, f"ms per lock-step of {R} runs; rank {agents[0]._scoring_engine().lowrank_info()['rank']}")
+
+if os.environ.get("C4_PROFILE"):
+    # kernel-level view of one lock-step (CUPTI through torch.profiler): which launches make up the selection / update
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        scores, idx, pts = br.select()
+        br.update(pts, himmelblau(pts))
+        torch.cuda.synchronize()
+    rows = [(e.key, e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total, e.count) for e in prof.key_averages()]
+    rows = [r for r in rows if r[1] > 0]
+    for name, us, cnt in sorted(rows, key=lambda r: -r[1])[:14]:
+        print(f"{us / 1e3:9.3f} ms  x{cnt:<5d} {name[:110]}")
