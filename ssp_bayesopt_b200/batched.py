@@ -53,6 +53,17 @@ class BatchedRuns:
         self._width = self._engines[0].n * self._engines[0].L
         assert all(e.n * e.L == self._width for e in self._engines), "runs must share the candidate row width"
         assert self.candidates.shape[1] == self._width
+        self._read_scalars()
+
+    def _read_scalars(self):
+        """Acquisition scalars of every run as arrays (lambda, gamma_t): read from the agents once, then stepped here
+        (vectorised) and written back, so a lock-step of thousands of runs does not pay thousands of method calls."""
+        self._lam = np.array([a.var_weight for a in self.agents], dtype=np.float64)
+        self._gam = np.array([a._gamma() for a in self.agents], dtype=np.float64)
+        # pure UCB with a constant weight step: gamma_t ignores the predictive variance and lambda += var_decay
+        self._pure_ucb = all(isinstance(a.gamma_c, (int, float)) and a.gamma_c == 0 and isinstance(a.var_decay, (int, float))
+                             for a in self.agents)
+        self._decay = np.array([a.var_decay if isinstance(a.var_decay, (int, float)) else 0.0 for a in self.agents], dtype=np.float64)
 
     def select(self):
         """Arg-max candidate of every run.  Returns (scores (R,), indices (R,), points (R, n))."""
@@ -61,8 +72,7 @@ class BatchedRuns:
         for s in self.streams:
             s.wait_stream(cur)
         R = len(self.agents)
-        lam = np.array([a.var_weight for a in self.agents], dtype=np.float64)
-        gam = np.array([a._gamma() for a in self.agents], dtype=np.float64)
+        lam, gam = self._lam, self._gam
         self._keys.zero_()
         for s in self.streams:
             s.wait_stream(cur)                                   # ... and the zeroed keys / status words
@@ -95,7 +105,7 @@ class BatchedRuns:
     def update(self, xs, ys):
         """xs (R, n), ys (R,): one observation per run."""
         torch = self.torch
-        if all(isinstance(a.gamma_c, (int, float)) and a.gamma_c == 0 for a in self.agents):
+        if self._pure_ucb:
             # pure UCB: gamma_t ignores the predictive variance, so nothing is read back: one library call enqueues every
             # run's encode + posterior update
             xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(len(self.agents), self._width)
@@ -110,13 +120,15 @@ class BatchedRuns:
                 _lib.check(self._lib, self._engines[max(failed.value, 0)]._ctx, rc, f"sspbo_update_batch (run {failed.value})")
             for s in self.streams:
                 cur.wait_stream(s)
-            for a in self.agents:
-                a._step_scalars(0.0, self._step_num)
+            self._lam = self._lam + self._decay                  # ssp_agent.py:208-218 with sigma_t unused (gamma_c = 0)
+            for a, lam_r in zip(self.agents, self._lam.tolist()):
+                a.var_weight = lam_r
             self._step_num += 1
             return
         for r, agt in enumerate(self.agents):
             agt.observe(np.atleast_2d(xs[r]), np.atleast_2d(ys[r]), step_num=self._step_num)   # eval(x_t) + update in one device round trip
         self._step_num += 1
+        self._read_scalars()
 
     def step(self, objective):
         """One lock-step with a vectorised objective f(points (R, n)) -> (R,)."""
