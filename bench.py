@@ -346,9 +346,10 @@ def run_native(args):
         for c0 in range(0, n_local, chunk):
             agt.best_candidate(x_dev[c0:c0 + chunk], index0=start + c0, reset_best=first)
             first = False
-        eng.settle()                                              # low-rank pass counters (synchronises; replays if asked)
-        dist.allreduce_best(eng._best)
-        return eng.best()                                         # D2H of the 8-byte key (synchronises)
+        if world > 1:
+            eng.settle()                                          # local key final (low-rank pass counters; replays if asked) ...
+            dist.allreduce_best(eng._best)                        # ... before it is combined across ranks
+        return eng.best()                                         # counters + the 8-byte key in one synchronising read-back
 
     def winner_row(gidx):
         u = orc.counter_uniform(0, gidx, 1, N_DIM)                # any rank can regenerate any candidate
@@ -401,8 +402,9 @@ def run_native(args):
         # public API on HOST candidates: SSPAgent.best_candidate streams the pinned shard to the GPU in chunks
         # (H2D inside the timed region, overlapped with the scoring), then the 8-byte key is read back
         agt.best_candidate(host, index0=start)
-        eng.settle()
-        dist.allreduce_best(eng._best)
+        if world > 1:
+            eng.settle()
+            dist.allreduce_best(eng._best)
         score, gidx = eng.best()
         observe_and_restore(gidx)
         return score, gidx
@@ -419,8 +421,9 @@ def run_native(args):
     # ---- the same step with the candidate set described instead of shipped (counter-based stream generated in the kernel) ----
     def gen_step():
         eng.score_generated("uniform", n_local, float(agt.var_weight), agt._gamma(), index0=start, seed=0)
-        eng.settle()
-        dist.allreduce_best(eng._best)
+        if world > 1:
+            eng.settle()
+            dist.allreduce_best(eng._best)
         score, gidx = eng.best()
         observe_and_restore(gidx)
         return score, gidx
