@@ -653,13 +653,13 @@ int sspbo_score_lr_launch(sspbo_ctx* ctx, const CandDesc& cand, int64_t N, int64
 
 // Grouped scoring of R independent runs over one explicit candidate set: fills runs_host[r] (the caller uploads the array to
 // runs_dev and has it resident when the launch executes) and enqueues ONE launch.  SSPBO_EUNSUPPORTED, with nothing enqueued,
-// when the runs do not share a layout (same rank, table size and |x| bound; split-fp16 operands, i.e. rank <= 127; float32
-// phase chain; n <= 4; plain spaces).
+// when the runs do not share a layout (same rank <= 255, table size and |x| bound; split-fp16 operands; float32 phase chain;
+// n <= 4; plain spaces).
 int sspbo_score_lr_runs_prepare(sspbo_ctx* const* ctxs, int R, int64_t N, const double* lam, const double* gamma_t,
                                 unsigned long long* keys_dev, RunScore* runs_host) {
     sspbo_ctx* c0 = ctxs[0];
     const int bn = (c0->lr_rank + 1 + 15) / 16 * 16;
-    if (bn > 128 || N < 1024) return SSPBO_EUNSUPPORTED;
+    if (bn > 256 || N < 1024) return SSPBO_EUNSUPPORTED;    // (rank <= 255: one chunk of split-fp16 operand rows)
     for (int r = 0; r < R; ++r) {
         sspbo_ctx* c = ctxs[r];
         if (!c || !sspbo_score_lr_supported(c) || c->lr_disabled || c->operand_format >= 1 || c->L != 1 || c->normalize ||

@@ -639,3 +639,39 @@ def test_low_rank_updates_keep_the_dense_state_on_demand(pkg):
         _, (mu, var, acq) = eng.score(xc, 5.0, 0.0, want_outputs=True, engine=code)
         assert_scores_close(mu.double().cpu().numpy(), acq.double().cpu().numpy(), ref_mu, ref_acq)
         np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+
+
+@pytest.mark.gpu
+def test_batched_runs_grouped_kernels_beyond_rank_127(pkg):
+    """The grouped scorer of config C4 keeps serving a lock-step once the runs hold more than 127 observations (one chunk of
+    up to 256 split-fp16 operand rows): still a handful of launches per lock-step, same picks as independently stepped agents
+    pinned to the same operand format."""
+    bounds = np.array([[-5.0, 5.0], [-5.0, 5.0]])
+    R, steps, n0 = 5, 3, 150
+    def make():
+        out = []
+        for r in range(R):
+            sp = pkg.RandomSSPSpace(2, ssp_dim=512, domain_bounds=bounds, length_scale=1.0, rng=r)
+            xs0 = np.random.default_rng(700 + r).uniform(-5, 5, (n0, 2))
+            out.append(pkg.SSPAgent(xs0, himmelblau(xs0).reshape(-1, 1), sp, gamma_c=0.0, beta_ucb=10.0, length_scale=1.0))
+        return out
+    grid = orc.grid_sample_points(bounds, 60)
+    a_batch, a_single = make(), make()
+    for a in a_single:
+        a._scoring_engine().set_operand_format(0)
+    runs = pkg.BatchedRuns(a_batch, grid, n_streams=2)
+    engines = [a._scoring_engine() for a in a_batch]
+    assert engines[0].lowrank_info()["rank"] == n0
+    for _ in range(steps):
+        before = sum(e.launch_count() for e in engines)
+        pts, ys, scores = runs.step(himmelblau)
+        launched = sum(e.launch_count() for e in engines) - before
+        assert launched <= 5, launched
+        for r, agt in enumerate(a_single):
+            agt.best_candidate(grid)
+            s, idx = agt._scoring_engine().best()
+            assert abs(s - scores[r]) <= 1e-6 * abs(s)
+            assert np.array_equal(grid[idx], pts[r])
+            agt.update(grid[idx:idx + 1], np.atleast_2d(himmelblau(grid[idx:idx + 1])), 0.0)
+    for a, b in zip(a_batch, a_single):
+        assert rel(a.blr.m, b.blr.m) < 1e-10 and rel(a.blr.S, b.blr.S) < 1e-10
