@@ -136,10 +136,16 @@ int sspbo_blr_init_dim(sspbo_ctx* ctx, int d, double alpha);
 int sspbo_blr_set_beta(sspbo_ctx* ctx, double beta);         /* blr.py:54-59 computed by the host mirror */
 int sspbo_blr_get_beta(const sspbo_ctx* ctx, double* beta, int* is_set);
 /* blr.py:60-77: S_inv += beta Phi^T Phi; for each row: Sherman-Morrison on S; m = S b.
- * phis_dev: k x d float64 (device); ts_host: k float64 (host). */
+ * phis_dev: k x d float64 (device); ts_host: k float64 (host).
+ * Over an SSP space, while every observation so far has appended its row to the low-rank form (up to 511 of them), an
+ * observation is applied in that form -- psi-space, O(rank d), one launch (k_blr_update_lr) -- and S, S_inv, b, m and the
+ * psi-space covariance are brought up to date when something reads them (sspbo_blr_get / _predict / _export, the ascent, the
+ * factor-form scorers); the values are those of the reference's update to float64 rounding.  Otherwise (and for raw-feature
+ * posteriors) the dense O(d^2) update runs. */
 int sspbo_blr_update(sspbo_ctx* ctx, const double* phis_dev, const double* ts_host, int k, void* stream);
-/* Posterior update path: fused != 0 (default) = one cooperative launch per observation (sspbo_update.cu) where the device
- * supports it, 0 = the separate GEMV / rank-one kernels (sspbo_core.cu; also the automatic fallback). */
+/* Posterior update path: fused != 0 (default) = one launch per observation (sspbo_update.cu: the low-rank form, else the
+ * cooperative dense kernel) where the device supports it, 0 = the separate GEMV / rank-one kernels (sspbo_core.cu; also the
+ * automatic fallback). */
 int sspbo_set_update_path(sspbo_ctx* ctx, int fused);
 
 /* SSPAgent.update (agents/ssp_agent.py:187-206) for k <= 64 HOST points: x_host k x (n*L) float64 is staged through pinned
@@ -147,7 +153,7 @@ int sspbo_set_update_path(sspbo_ctx* ctx, int fused);
 int sspbo_blr_update_x(sspbo_ctx* ctx, const double* x_host, const double* ts_host, int k, void* stream);
 /* One BO observation for one HOST point x_t: (*mu_host, *var_host) = BLR predictive mean / variance at phi(x_t) under the
  * CURRENT posterior (what SSPAgent.eval returns, agents/ssp_agent.py:133-135, float64), then the posterior update with
- * target t (SSPAgent.update, :187-206).  Both come out of the same cooperative update launch; synchronises once. */
+ * target t (SSPAgent.update, :187-206).  Both come out of the same update launch; synchronises once. */
 int sspbo_observe(sspbo_ctx* ctx, const double* x_host, double t, double* mu_host, double* var_host, void* stream);
 /* copies of the posterior (attributes BLR.m (d), BLR.S (d x d), BLR.S_inv (d x d)); any pointer may be NULL */
 int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev, void* stream);
@@ -273,7 +279,7 @@ int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_de
  * the caller.  sspbo_update_batch: for r < R: sspbo_blr_update_x(ctxs[r], row r of x_host (R x n*L float64), ts_host[r]).
  * Both only enqueue work.  The caller orders every stream of `streams` after the work that precedes the call and waits for
  * all of them afterwards.  Runs that share a layout (plain SSP spaces of one dimension n <= 4 and table size, the same
- * posterior rank <= 127 as in a lock-step, the float32 phase path) are served by GROUPED kernels on streams[0]: one launch of
+ * posterior rank <= 255 as in a lock-step, the float32 phase path) are served by GROUPED kernels on streams[0]: one launch of
  * the fused scorer over (run, tile), one of the float64 pass over (run, flagged group), one for the status words; and one
  * launch for all updates (a thread-block cluster per run encodes the run's point, applies the float64 rank-one update and
  * refreshes the run's scoring operands).  Otherwise the per-run calls go to streams[r % n_streams].  On error the first
