@@ -629,7 +629,7 @@ def encode_only(eng, cand, peaks, n=1 << 16, reps=3):
     gbs = n * eng.d * 8 / sec / 1e9
     out = {"f64": {"kernel": "k_encode (float64 phi to HBM)", "candidates": n, "candidates_per_s": n / sec,
                    "hbm_write_gbs": gbs, "hbm_peak_gbs": peaks["hbm"], "frac_of_hbm_peak": gbs / peaks["hbm"],
-                   "note": "2 d K float64 FMA per candidate: bound by the FP64 pipe; the fused scorer never materialises phi"}}
+                   "note": "d K float64 FMA per candidate (output columns j and d - j share their products): bound by the FP64 pipe; the fused scorer never materialises phi"}}
     n32 = min(cand.shape[0], 1 << 20)
     x32 = cand[:n32]
     eng.encode_f32_device(x32)

@@ -102,19 +102,24 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
             }
             __syncthreads();
         }
-        // small batches: gridDim.y blocks share a group of candidates, each takes a slice of the output columns
-        const int j0 = (int)((long long)d * blockIdx.y / gridDim.y), j1 = (int)((long long)d * (blockIdx.y + 1) / gridDim.y);
+        // Output columns come in pairs: cos(2 pi (d - j) k / d) = cos(2 pi j k / d) and sin(...) changes sign, so with
+        // E_j = sum_k C_k cos(2 pi j k / d) and O_j = sum_k S_k sin(2 pi j k / d):  phi_j = (psi_0 + 2 (E_j - O_j)) / d and
+        // phi_{d-j} = (psi_0 + 2 (E_j + O_j)) / d -- the same two FMAs per frequency now yield two columns (the FP64 pipe is
+        // what bounds this kernel).  Work items are the half-columns h = 0 .. K.
+        // small batches: gridDim.y blocks share a group of candidates, each takes a slice of the half-columns
+        const int nh = K + 1;
+        const int j0 = (int)((long long)nh * blockIdx.y / gridDim.y), j1 = (int)((long long)nh * (blockIdx.y + 1) / gridDim.y);
         if constexpr (ENC_CPB == 1) {
-            // one candidate per block: when the column slice is narrower than the block, the spare warps split the
-            // frequency sum (k-parts) and the partial sums are folded through shared memory in a fixed order
-            __shared__ double part_s[ENC_THREADS];
+            // one candidate per block: when the slice is narrower than the block, the spare warps split the frequency sum
+            // (k-parts) and the partial sums are folded through shared memory in a fixed order
+            __shared__ double part_e[ENC_THREADS], part_o[ENC_THREADS];
             const int ncol = j1 - j0;
             const int lanes_per = 32 * ((ncol + 31) / 32);
             const int kparts = lanes_per >= ENC_THREADS ? 1 : ENC_THREADS / lanes_per;
             for (int jb = 0; jb < ncol; jb += ENC_THREADS) {            // one trip when ncol <= ENC_THREADS
                 const int part = kparts == 1 ? 0 : threadIdx.x / lanes_per;
                 const int jl = jb + (kparts == 1 ? threadIdx.x : threadIdx.x % lanes_per);
-                double acc = 0.0;
+                double ae = 0.0, ao = 0.0;
                 if (part < kparts && jl < ncol) {
                     const int j = j0 + jl;
                     const int kb = 1 + (int)((long long)K * part / kparts), ke = 1 + (int)((long long)K * (part + 1) / kparts);
@@ -123,36 +128,50 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                     for (int k = kb; k < ke; ++k) {
                         idx += j; if (idx >= d) idx -= d;   // (j*k) mod d
                         const double2 tw = __ldg(twiddle + idx);
-                        acc = fma(psi_s[k], tw.x, fma(-psi_s[K + k], tw.y, acc));
+                        ae = fma(psi_s[k], tw.x, ae);
+                        ao = fma(psi_s[K + k], tw.y, ao);
                     }
                 }
                 if (kparts > 1) {
                     __syncthreads();
-                    part_s[threadIdx.x] = acc;
+                    part_e[threadIdx.x] = ae; part_o[threadIdx.x] = ao;
                     __syncthreads();
                     if (part == 0 && jl < ncol)
-                        for (int q = 1; q < kparts; ++q) acc += part_s[q * lanes_per + (threadIdx.x % lanes_per)];
+                        for (int q = 1; q < kparts; ++q) {
+                            ae += part_e[q * lanes_per + (threadIdx.x % lanes_per)];
+                            ao += part_o[q * lanes_per + (threadIdx.x % lanes_per)];
+                        }
                 }
-                if (part == 0 && jl < ncol)
-                    phi[base * d + j0 + jl] = (psi_s[0] + 2.0 * acc) * inv_d * (normalize ? scale_s[0] : 1.0);
+                if (part == 0 && jl < ncol) {
+                    const int j = j0 + jl;
+                    const double sc = inv_d * (normalize ? scale_s[0] : 1.0);
+                    phi[base * d + j] = (psi_s[0] + 2.0 * (ae - ao)) * sc;
+                    if (j > 0) phi[base * d + d - j] = (psi_s[0] + 2.0 * (ae + ao)) * sc;
+                }
             }
         } else
         for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-            double acc[ENC_CPB];
+            double ae[ENC_CPB], ao[ENC_CPB];
 #pragma unroll
-            for (int c = 0; c < ENC_CPB; ++c) acc[c] = 0.0;
+            for (int c = 0; c < ENC_CPB; ++c) { ae[c] = 0.0; ao[c] = 0.0; }
             int idx = 0;
 #pragma unroll 4
             for (int k = 1; k <= K; ++k) {
                 idx += j; if (idx >= d) idx -= d;       // (j*k) mod d
                 const double2 tw = __ldg(twiddle + idx);
 #pragma unroll
-                for (int c = 0; c < ENC_CPB; ++c)
-                    acc[c] = fma(psi_s[c * d + k], tw.x, fma(-psi_s[c * d + K + k], tw.y, acc[c]));
+                for (int c = 0; c < ENC_CPB; ++c) {
+                    ae[c] = fma(psi_s[c * d + k], tw.x, ae[c]);
+                    ao[c] = fma(psi_s[c * d + K + k], tw.y, ao[c]);
+                }
             }
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c)
-                if (base + c < N) phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * acc[c]) * inv_d * (normalize ? scale_s[c] : 1.0);
+                if (base + c < N) {
+                    const double sc = inv_d * (normalize ? scale_s[c] : 1.0);
+                    phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * (ae[c] - ao[c])) * sc;
+                    if (j > 0) phi[(base + c) * d + d - j] = (psi_s[c * d] + 2.0 * (ae[c] + ao[c])) * sc;
+                }
         }
     }
 }
@@ -1470,7 +1489,7 @@ static int encode_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, 
     int64_t blocks64 = (N + cpb - 1) / cpb;
     int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 8 ? blocks64 : (int64_t)ctx->sm_count * 8);
     int slices = 1;                                      // a handful of candidates (e.g. x_t of a BO step): spread the columns
-    while (slices < 16 && (int64_t)blocks * slices < 2 * ctx->sm_count && ctx->d / (slices * 2) >= 32) slices *= 2;
+    while (slices < 16 && (int64_t)blocks * slices < 2 * ctx->sm_count && (ctx->K + 1) / (slices * 2) >= 32) slices *= 2;
     const dim3 grid(blocks, slices);
 #define SSPBO_ENC_LAUNCH(XT, CPB)                                                                                          \
     do {                                                                                                                   \
