@@ -330,7 +330,7 @@ struct RunLR {
     double* obs_out;                      // nullable: (m . phi, 1/beta + phi^T S phi) under the posterior before this update
 };
 
-__global__ void __launch_bounds__(UP_THREADS, 2) k_blr_update_lr(const RunLR* __restrict__ runs) {
+__global__ void __launch_bounds__(UP_THREADS, 4) k_blr_update_lr(const RunLR* __restrict__ runs) {
     extern __shared__ __align__(16) double sm[];
     ClusterTeam team;
     const int run = blockIdx.x / team.size();
@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(UP_THREADS, 2) k_blr_update_lr(const RunLR* __
     for (int j = j0 + tid; j < j1; j += UP_THREADS) {
         const double sp0 = (r.perm[j] == 0) ? p0 : pk;
         double y = sp0 * psi[j], mm = sp0 * bps[j];
-        for (int i = 0; i < rank; ++i) {
+#pragma unroll 4
+        for (int i = 0; i < rank; ++i) {                                 // (the loads of several rows in flight)
             const double v = r.Vd[(size_t)i * d + j];
             y = fma(-gs[i], v, y); mm = fma(-hs[i], v, mm);
         }
