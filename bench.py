@@ -719,7 +719,7 @@ def acq_ascent_cost(agt, sp, orc, restarts=8, steps=100, reps=5):
                     "together; CPU = scipy L-BFGS-B on the oracle's acquisition_func per restart"}
 
 
-def bo_step_c2(pkg, n_iter=30):
+def bo_step_c2(pkg, n_iter=250):
     """'ms per BO step' of BASELINE config C2 through the public driver: Branin, ssp-hex ssp_dim=151, 1000 x 1000
     candidate grid, `BayesianOptimization.maximize` (fused scoring of the 1e6 grid + winner read-back + target
     evaluation + eval(x_t) + float64 posterior update per step)."""
@@ -731,9 +731,13 @@ def bo_step_c2(pkg, n_iter=30):
     opt.maximize(init_points=(xs0, branin(xs0).reshape(-1, 1)), n_iter=n_iter, agent_type="ssp-hex", ssp_dim=151,
                  length_scale=1.0, beta_ucb=10.0, gamma_c=0.0, candidates_per_dim=1000)
     ft = opt.full_times[5:] * 1e-6                                  # ns -> ms, skip the first (warm-up) steps
-    out = {"config": "C2: Branin 2-D ssp-hex d=151, 1e6-point candidate grid, BayesianOptimization.maximize",
+    out = {"config": f"C2: Branin 2-D ssp-hex d=151, 1e6-point candidate grid, BayesianOptimization.maximize, {n_iter} iterations",
            "ms_per_bo_step": float(np.mean(ft)), "ms_min": float(np.min(ft)), "steps": int(len(ft)),
-           "candidates_per_s": float(1e6 / (np.mean(opt.times[5:]) * 1e-9)), "best_target": float(opt.max["target"])}
+           "candidates_per_s": float(1e6 / (np.mean(opt.times[5:]) * 1e-9)), "best_target": float(opt.max["target"]),
+           # the posterior gains one observation per step (rank 10 + step): the step time by stretch of the run
+           "ms_by_iteration": {f"{a}-{b}": float(np.mean(opt.full_times[a:b]) * 1e-6)
+                               for a, b in ((5, 50), (50, 118), (118, 200), (200, n_iter)) if b <= n_iter and b > a},
+           "engine_at_end": opt.agt._scoring_engine().last_engine()}
     # the same step through the reference's arithmetic (numpy oracle port) on the host: eval + argmax over a bounded sample of
     # the grid (extrapolated to 1e6 points) plus the reference's posterior update expression
     from oracle import ssp_oracle as orc

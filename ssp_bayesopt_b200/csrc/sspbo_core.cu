@@ -2213,8 +2213,8 @@ static int score_dispatch(sspbo_ctx* ctx, sspbo_lr::CandDesc cand, int64_t N, in
     if (engine == SSPBO_ENGINE_AUTO) {
         const bool lr_wanted = lr_ok && !ctx->lr_disabled;
         if (N <= 64) engine = SSPBO_ENGINE_EXACT;               // e.g. eval(x_t) of every BO step: no factorisation needed
-        else if (N >= 1024 && f8_ok && !ctx->f8_disabled)       // whichever form passes fewer operand rows x k-blocks per tile
-            engine = (lr_wanted && sspbo_f8_cost(ctx, 0) <= sspbo_f8_cost(ctx, 1)) ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA_F8;
+        else if (N >= 1024 && f8_ok && !ctx->f8_disabled)       // whichever form is estimated to take less time (sspbo_f8_cost)
+            engine = (lr_wanted && sspbo_f8_cost(ctx, 0, N) <= sspbo_f8_cost(ctx, 1, N)) ? SSPBO_ENGINE_UMMA_LR : SSPBO_ENGINE_UMMA_F8;
         else if (N >= 1024 && lr_wanted && 2 * (ctx->lr_rank + 1) <= (ctx->d >= 128 ? 3 : 1) * ctx->d)
             engine = SSPBO_ENGINE_UMMA_LR;
         else if (N >= 1024 && umma_ok) engine = SSPBO_ENGINE_UMMA;

@@ -251,7 +251,7 @@ int sspbo_score_lr_supported(const sspbo_ctx* ctx);
 void sspbo_lr_release(sspbo_ctx* ctx);
 void sspbo_f8_release(sspbo_ctx* ctx);
 int sspbo_score_f8_supported(const sspbo_ctx* ctx, int form);
-double sspbo_f8_cost(const sspbo_ctx* ctx, int form);
+double sspbo_f8_cost(const sspbo_ctx* ctx, int form, int64_t N);
 // L = chol(Sp) into ctx->R when the psi-space covariance changed since the last factorisation
 int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st);
 constexpr int SSPBO_SINV_RING = 32;

@@ -663,20 +663,30 @@ int sspbo_score_f8_supported(const sspbo_ctx* ctx, int form) {
     return nc <= MAX_CHUNKS;
 }
 
-// k-block passes of 256-row-equivalents per tile: the cost model SSPBO_ENGINE_AUTO compares the two forms with
-double sspbo_f8_cost(const sspbo_ctx* ctx, int form) {
+// Estimated seconds of one scoring call of N candidates in the low-rank (0) or the factor form (1): the cost model
+// SSPBO_ENGINE_AUTO compares the two with.  A k-block pass over a tile costs max(rows x 3.9 ns, 0.5 us) -- the tensor pipe
+// (measured: 256 rows x 16 k-blocks = 15.8 us at rank 255, d = 1023) or the generators, whichever binds -- and every SM
+// sees ceil(N / 128 / SMs) tiles.  The low-rank form pays for its float64 pass over flagged candidates; the factor form pays
+// for refreshing the factor when the posterior has changed since the last call (the rows since folded into the psi-space
+// covariance, a Cholesky factorisation, the operand images: ~0.1 ms of small launches + d^3/3 float64 flops), which at small d
+// outweighs any difference between the scorers (config C2 late in its run: d = 151, rank > 118).
+double sspbo_f8_cost(const sspbo_ctx* ctx, int form, int64_t N) {
     const int n_kb = ctx->KC_pad / BK;
+    const double tiles = ceil((double)N / (double)BM / (double)(ctx->sm_count > 0 ? ctx->sm_count : 148));
+    auto pass = [](int rows) { const double t = rows * 3.9e-9; return t > 0.5e-6 ? t : 0.5e-6; };
     if (form == 0) {
         const int rows = ctx->lr_rank, nc = (rows + 255) / 256;
         const int bn = ((rows + nc - 1) / nc + 15) / 16 * 16;
         // plus the float64 pass over the flagged candidates: one of its candidate-rows costs ~36 tensor-pass candidate-rows
         // (measured at rank 511, 1.4 % flagged: 4.3 ms of 12.9 ms per 4.19M candidates)
-        return (double)nc * bn * n_kb * (1.0 + 36.0 * ctx->lr_flag_frac);
+        return tiles * nc * n_kb * pass(bn) * (1.0 + 36.0 * ctx->lr_flag_frac);
     }
     int bn, nc;
     factor_geometry(ctx, &bn, &nc);
     double cost = 0.0;
-    for (int c = 0; c < nc; ++c) cost += (double)bn * (n_kb - ctx->host_col_of_rank[c * bn] / 64);
+    for (int c = 0; c < nc; ++c) cost += (double)(n_kb - ctx->host_col_of_rank[c * bn] / 64) * pass(bn);
+    cost *= tiles;
+    if (ctx->factor_dirty) cost += 1.0e-4 + (double)ctx->d * ctx->d * ctx->d / 3.0 / 4.0e11;
     return cost;
 }
 

@@ -22,6 +22,7 @@ namespace {
 
 constexpr int UP_THREADS = 256;
 constexpr int UP_WARPS = UP_THREADS / 32;
+constexpr int LR_CB = 128;             // components per pass of the second sweep over V in k_blr_update_lr
 
 struct UpdateParams {
     int d, K, has_factor, finalize;
@@ -395,19 +396,38 @@ __global__ void __launch_bounds__(UP_THREADS, 4) k_blr_update_lr(const RunLR* __
     __syncthreads();
 
     // ---- my slice of y = Sp0 psi - V^T g and of Sp0 b_psi' - V^T h ; partial sums of psi . y and y . b_psi' ----
+    // The warps share out the rows of V (row i to warp i mod 8, lanes along the components: coalesced), 128 components of the
+    // slice per pass; their partial sums meet in shared memory and are added in warp order.
     const int j0 = (int)((long long)d * cta / ncta), j1 = (int)((long long)d * (cta + 1) / ncta);
     const double p0 = 1.0 / ((double)d * r.alpha), pk = 2.0 / ((double)d * r.alpha);      // Sp0 = B^T B / alpha (diagonal)
+    double* py = tot + 4;                 // UP_WARPS x LR_CB partial sums of -V^T g
+    double* pm = py + UP_WARPS * LR_CB;   // ... and of -V^T h
     double part[2] = {0.0, 0.0};
-    for (int j = j0 + tid; j < j1; j += UP_THREADS) {
-        const double sp0 = (r.perm[j] == 0) ? p0 : pk;
-        double y = sp0 * psi[j], mm = sp0 * bps[j];
-#pragma unroll 4
-        for (int i = 0; i < rank; ++i) {                                 // (the loads of several rows in flight)
-            const double v = r.Vd[(size_t)i * d + j];
-            y = fma(-gs[i], v, y); mm = fma(-hs[i], v, mm);
+    for (int q0 = j0; q0 < j1; q0 += LR_CB) {
+        double ay[LR_CB / 32], am[LR_CB / 32];
+#pragma unroll
+        for (int q = 0; q < LR_CB / 32; ++q) { ay[q] = 0.0; am[q] = 0.0; }
+        for (int i = warp; i < rank; i += UP_WARPS) {
+            const double g = gs[i], h = hs[i];
+            const double* row = r.Vd + (size_t)i * d + q0;
+#pragma unroll
+            for (int q = 0; q < LR_CB / 32; ++q) {
+                const int jj = q * 32 + lane;
+                if (q0 + jj < j1) { const double v = row[jj]; ay[q] = fma(-g, v, ay[q]); am[q] = fma(-h, v, am[q]); }
+            }
         }
-        ys[j] = y; ms[j] = mm;
-        part[0] = fma(psi[j], y, part[0]); part[1] = fma(y, bps[j], part[1]);
+        __syncthreads();                                                 // (the previous pass has read py / pm)
+#pragma unroll
+        for (int q = 0; q < LR_CB / 32; ++q) { py[warp * LR_CB + q * 32 + lane] = ay[q]; pm[warp * LR_CB + q * 32 + lane] = am[q]; }
+        __syncthreads();
+        const int j = q0 + tid;
+        if (tid < LR_CB && j < j1) {
+            const double sp0 = (r.perm[j] == 0) ? p0 : pk;
+            double y = sp0 * psi[j], mm = sp0 * bps[j];
+            for (int w = 0; w < UP_WARPS; ++w) { y += py[w * LR_CB + tid]; mm += pm[w * LR_CB + tid]; }
+            ys[j] = y; ms[j] = mm;
+            part[0] = fma(psi[j], y, part[0]); part[1] = fma(y, bps[j], part[1]);
+        }
     }
     up_block_reduce<2>(part, red, tot);
     if (tid < 2) __stcg(r.gh + 2 * SSPBO_LR_MAX + tid * 16 + cta, tot[tid]);
@@ -610,7 +630,7 @@ int sspbo_blr_update_lr(sspbo_ctx* const* ctxs, int R, const double* x_host, con
     }
     int cluster_ok = 0;
     cudaDeviceGetAttribute(&cluster_ok, cudaDevAttrClusterLaunch, c0->device);
-    const size_t smem = ((size_t)4 * d_max + 2 * SSPBO_LR_MAX + UP_WARPS * 4 + 4) * sizeof(double);
+    const size_t smem = ((size_t)4 * d_max + 2 * SSPBO_LR_MAX + UP_WARPS * 4 + 4 + 2 * UP_WARPS * LR_CB) * sizeof(double);
     if (!cluster_ok || smem > 100 * 1024) return SSPBO_EUNSUPPORTED;
     SSPBO_CUDA(c0, cudaSetDevice(c0->device));
     const size_t bytes = (size_t)R * sizeof(RunLR) + (size_t)R * n_max * sizeof(double);
