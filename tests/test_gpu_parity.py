@@ -393,8 +393,9 @@ def test_score_lowrank_beyond_half_rank_small_space(pkg, T):
     ref_mu, ref_var, ref_acq = orc.agent_eval(phis, ref, 10.0, 0.0)
     eng.score_stats(reset=True)
     _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True)              # AUTO
-    # 16-row granules x 3 k-blocks: the low-rank form while its rows (T) stay below the factor's (d = 151 -> 160)
-    assert eng.last_engine() == ("umma-lowrank" if T <= 160 else "umma-factor-f8")
+    # AUTO estimates the time of both forms: at d = 151 the factor form would have to refresh its factor for this posterior
+    # (fold, Cholesky, operand images: ~0.1 ms), far more than the few extra operand rows of the low-rank form cost here
+    assert eng.last_engine() == "umma-lowrank"
     mu, var, acq = (t.double().cpu().numpy() for t in (mu, var, acq))
     assert_scores_close(mu, acq, ref_mu, ref_acq)
     np.testing.assert_allclose(var, ref_var, rtol=RTOL_SCORE)
@@ -402,11 +403,17 @@ def test_score_lowrank_beyond_half_rank_small_space(pkg, T):
     srt = np.sort(ref_score)[::-1]
     if (srt[0] - srt[1]) > RTOL_SCORE * abs(srt[0]):
         assert eng.best()[1] == int(np.argmax(ref_score))
-    if T > 160:                                                                   # the low-rank form stays available on request
+    if T > 160:                                                                   # more rows than the factor has: the factor form on request
         from ssp_bayesopt_b200 import _lib
-        _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True, engine=_lib.ENGINE_UMMA_LR)
-        assert eng.last_engine() == "umma-lowrank"
-        np.testing.assert_allclose(var.double().cpu().numpy(), ref_var, rtol=RTOL_SCORE)
+        _, (mu, var, acq) = eng.score(xc, 10.0, 0.0, want_outputs=True, engine=_lib.ENGINE_UMMA_F8)
+        assert eng.last_engine() == "umma-factor-f8"
+        mu, var, acq = (t.double().cpu().numpy() for t in (mu, var, acq))
+        assert_scores_close(mu, acq, ref_mu, ref_acq)
+        np.testing.assert_allclose(var, ref_var, rtol=RTOL_SCORE)
+        # ... and AUTO takes it once the factor is fresh and the set is large enough for the rows to matter
+        big = np.tile(xc, (600, 1))
+        eng.score(big, 10.0, 0.0)
+        assert eng.last_engine() == "umma-factor-f8"
 
 
 def test_score_lowrank_12d(pkg):
