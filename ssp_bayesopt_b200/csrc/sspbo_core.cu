@@ -63,13 +63,14 @@ constexpr int ENC_CPB_BATCH = 8, ENC_CPB_SMALL = 1, ENC_SMALL_N = 64;
 constexpr int ENC_THREADS = 256;
 
 template <typename XT, int ENC_CPB>
-__global__ void __launch_bounds__(ENC_THREADS)
+__global__ void __launch_bounds__(ENC_THREADS, 2)
 k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns, const double* __restrict__ tau_turns,
          const double2* __restrict__ twiddle, int n, int K, int L, double dc, int normalize, double* __restrict__ phi,
          int deriv_axis, int ncls) {
     // deriv_axis >= 0 (L == 1): d phi / d x_a instead of phi -- the spectrum exp(i theta_k) becomes i w_ka exp(i theta_k),
     // w_ka = A+_ka / l_a, i.e. (cos, sin) -> (-w sin, w cos) and no DC term (sspspace.py:300-305)
-    extern __shared__ double psi_s[];                   // ENC_CPB x d
+    extern __shared__ double2 psi_p[];                  // ENC_CPB x K pairs (cos, sin) of the spectrum: one 16-byte load per frequency
+    __shared__ double dc_s[ENC_CPB];                    // its DC term
     __shared__ double scale_s[ENC_CPB];                 // 1 / |phi| per candidate when normalising, else 1
     const int d = 2 * K + 1;
     const int nl = n * L;
@@ -85,9 +86,8 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                     const double c0 = cs;
                     cs = -w * sn; sn = w * c0;
                 }
-                psi_s[c * d + 1 + k] = cs;
-                psi_s[c * d + 1 + K + k] = sn;
-                if (k == 0) psi_s[c * d] = deriv_axis >= 0 ? 0.0 : dc;
+                psi_p[c * K + k] = make_double2(cs, sn);
+                if (k == 0) dc_s[c] = deriv_axis >= 0 ? 0.0 : dc;
             }
         }
         __syncthreads();
@@ -96,7 +96,10 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
             const int c = threadIdx.x >> 5;
             if (c < ENC_CPB && base + c < N) {
                 double ss = 0.0;
-                for (int k = 1 + (threadIdx.x & 31); k < d; k += 32) ss = fma(psi_s[c * d + k], psi_s[c * d + k], ss);
+                for (int k = (threadIdx.x & 31); k < K; k += 32) {
+                    const double2 pv = psi_p[c * K + k];
+                    ss = fma(pv.x, pv.x, fma(pv.y, pv.y, ss));
+                }
                 ss = warp_sum(ss);
                 if ((threadIdx.x & 31) == 0) scale_s[c] = rsqrt((dc * dc + 2.0 * ss) * inv_d);
             }
@@ -128,8 +131,9 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                     for (int k = kb; k < ke; ++k) {
                         idx += j; if (idx >= d) idx -= d;   // (j*k) mod d
                         const double2 tw = __ldg(twiddle + idx);
-                        ae = fma(psi_s[k], tw.x, ae);
-                        ao = fma(psi_s[K + k], tw.y, ao);
+                        const double2 pv = psi_p[k - 1];
+                        ae = fma(pv.x, tw.x, ae);
+                        ao = fma(pv.y, tw.y, ao);
                     }
                 }
                 if (kparts > 1) {
@@ -145,32 +149,46 @@ k_encode(const XT* __restrict__ x, int64_t N, const double* __restrict__ A_turns
                 if (part == 0 && jl < ncol) {
                     const int j = j0 + jl;
                     const double sc = inv_d * (normalize ? scale_s[0] : 1.0);
-                    phi[base * d + j] = (psi_s[0] + 2.0 * (ae - ao)) * sc;
-                    if (j > 0) phi[base * d + d - j] = (psi_s[0] + 2.0 * (ae + ao)) * sc;
+                    phi[base * d + j] = (dc_s[0] + 2.0 * (ae - ao)) * sc;
+                    if (j > 0) phi[base * d + d - j] = (dc_s[0] + 2.0 * (ae + ao)) * sc;
                 }
             }
         } else
-        for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-            double ae[ENC_CPB], ao[ENC_CPB];
+        // two half-columns per thread (j and j + blockDim.x): every psi value read from shared memory feeds four FMAs
+        for (int j = j0 + threadIdx.x; j < j1; j += 2 * blockDim.x) {
+            const int jb = j + blockDim.x;
+            const bool two = jb < j1;
+            double ae[ENC_CPB], ao[ENC_CPB], be[ENC_CPB], bo[ENC_CPB];
 #pragma unroll
-            for (int c = 0; c < ENC_CPB; ++c) { ae[c] = 0.0; ao[c] = 0.0; }
-            int idx = 0;
-#pragma unroll 4
+            for (int c = 0; c < ENC_CPB; ++c) { ae[c] = 0.0; ao[c] = 0.0; be[c] = 0.0; bo[c] = 0.0; }
+            int idx = 0, idb = 0;
+            const int jbm = two ? jb : j;               // (a lone column computes itself twice; the copy is not stored)
+#pragma unroll 2
             for (int k = 1; k <= K; ++k) {
                 idx += j; if (idx >= d) idx -= d;       // (j*k) mod d
+                idb += jbm; if (idb >= d) idb -= d;
                 const double2 tw = __ldg(twiddle + idx);
+                const double2 tb = __ldg(twiddle + idb);
 #pragma unroll
                 for (int c = 0; c < ENC_CPB; ++c) {
-                    ae[c] = fma(psi_s[c * d + k], tw.x, ae[c]);
-                    ao[c] = fma(psi_s[c * d + K + k], tw.y, ao[c]);
+                    const double2 pv = psi_p[c * K + k - 1];
+                    const double pc = pv.x, ps = pv.y;
+                    ae[c] = fma(pc, tw.x, ae[c]);
+                    ao[c] = fma(ps, tw.y, ao[c]);
+                    be[c] = fma(pc, tb.x, be[c]);
+                    bo[c] = fma(ps, tb.y, bo[c]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < ENC_CPB; ++c)
                 if (base + c < N) {
                     const double sc = inv_d * (normalize ? scale_s[c] : 1.0);
-                    phi[(base + c) * d + j] = (psi_s[c * d] + 2.0 * (ae[c] - ao[c])) * sc;
-                    if (j > 0) phi[(base + c) * d + d - j] = (psi_s[c * d] + 2.0 * (ae[c] + ao[c])) * sc;
+                    phi[(base + c) * d + j] = (dc_s[c] + 2.0 * (ae[c] - ao[c])) * sc;
+                    if (j > 0) phi[(base + c) * d + d - j] = (dc_s[c] + 2.0 * (ae[c] + ao[c])) * sc;
+                    if (two) {
+                        phi[(base + c) * d + jb] = (dc_s[c] + 2.0 * (be[c] - bo[c])) * sc;
+                        phi[(base + c) * d + d - jb] = (dc_s[c] + 2.0 * (be[c] + bo[c])) * sc;
+                    }
                 }
         }
     }
@@ -1485,7 +1503,7 @@ static int encode_launch(sspbo_ctx* ctx, const void* x, int x_dtype, int64_t N, 
     SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int cpb = N <= ENC_SMALL_N ? ENC_CPB_SMALL : ENC_CPB_BATCH;
-    size_t smem = (size_t)cpb * ctx->d * sizeof(double);
+    size_t smem = (size_t)cpb * ctx->K * sizeof(double2);
     int64_t blocks64 = (N + cpb - 1) / cpb;
     int blocks = (int)(blocks64 < (int64_t)ctx->sm_count * 8 ? blocks64 : (int64_t)ctx->sm_count * 8);
     int slices = 1;                                      // a handful of candidates (e.g. x_t of a BO step): spread the columns
