@@ -346,10 +346,9 @@ def run_native(args):
         for c0 in range(0, n_local, chunk):
             agt.best_candidate(x_dev[c0:c0 + chunk], index0=start + c0, reset_best=first)
             first = False
-        if world > 1:
-            eng.settle()                                          # local key final (low-rank pass counters; replays if asked) ...
-            dist.allreduce_best(eng._best)                        # ... before it is combined across ranks
-        return eng.best()                                         # counters + the 8-byte key in one synchronising read-back
+        # one rank: counters + the 8-byte key in one synchronising read-back; several: first the key exchange over peer memory
+        # (one kernel writing into every peer's slots; NCCL all-reduce of the key if peer access is not available)
+        return dist.reduce_best(eng)
 
     def winner_row(gidx):
         u = orc.counter_uniform(0, gidx, 1, N_DIM)                # any rank can regenerate any candidate
@@ -402,10 +401,7 @@ def run_native(args):
         # public API on HOST candidates: SSPAgent.best_candidate streams the pinned shard to the GPU in chunks
         # (H2D inside the timed region, overlapped with the scoring), then the 8-byte key is read back
         agt.best_candidate(host, index0=start)
-        if world > 1:
-            eng.settle()
-            dist.allreduce_best(eng._best)
-        score, gidx = eng.best()
+        score, gidx = dist.reduce_best(eng)
         observe_and_restore(gidx)
         return score, gidx
     e2e_step()
@@ -421,10 +417,7 @@ def run_native(args):
     # ---- the same step with the candidate set described instead of shipped (counter-based stream generated in the kernel) ----
     def gen_step():
         eng.score_generated("uniform", n_local, float(agt.var_weight), agt._gamma(), index0=start, seed=0)
-        if world > 1:
-            eng.settle()
-            dist.allreduce_best(eng._best)
-        score, gidx = eng.best()
+        score, gidx = dist.reduce_best(eng)
         observe_and_restore(gidx)
         return score, gidx
     gen_step()
@@ -484,6 +477,8 @@ def run_native(args):
                        "candidates_per_gpu_per_step": n_local, "candidates_per_step": total, "chunk": chunk,
                        "engine": engine_used, "posterior_rank": info["rank"], "phase32": info["phase32"],
                        "parallelism": f"candidate-shard x{world}",
+                       "key_reduction": ("none (one rank)" if world == 1 else
+                                         "peer-memory exchange kernel (sspbo_dist.cu)" if eng._exchange_on else "NCCL all_reduce(MAX)"),
                        "l2": "inputs (300 MB candidate shard) larger than L2; posterior operands rewritten every step",
                        "last_winner": {"score": last[0], "index": last[1]}},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",

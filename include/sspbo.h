@@ -273,6 +273,21 @@ int sspbo_bind(sspbo_ctx* ctx, const double* a_dev, int qa, const double* b_dev,
  * mirror solves; encoding at the trial length scales and this product are the only O(d) steps. */
 int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_dev, void* stream);
 
+/* ---- multi-GPU winner selection over peer memory (one process per GPU on one NVLink / NVSwitch node) ----
+ * The all_reduce(MAX) of the packed key without a collective library inside the BO step: ONE small kernel per step writes
+ * this rank's key (and whether its scoring pass asks for a rerun) straight into every peer's slot array and waits for the
+ * peers' words.  Set-up, once per context: sspbo_dist_init returns a 64-byte handle of this rank's slot array; the caller
+ * gathers the handles of all ranks (torch.distributed / MPI / files -- not this library's business) and hands them, in rank
+ * order, to sspbo_dist_connect.  Per step: sspbo_dist_exchange (asynchronous, every rank the same number of times) replaces
+ * *best_dev by the maximum over the ranks; the following sspbo_score_finish reports rerun != 0 when ANY rank asks for it (then
+ * every rank recomputes its shard and exchanges again) and an error when a peer did not arrive within ~2 s.
+ * Replaces: dist.allreduce_best (NCCL) of this repo; in the reference the step is np.argmax over one array
+ * (bayesian_optimization.py:291). */
+int sspbo_dist_init(sspbo_ctx* ctx, int rank, int world, unsigned char* handle_out /* 64 bytes */);
+int sspbo_dist_connect(sspbo_ctx* ctx, const unsigned char* handles /* world x 64 bytes, rank order */);
+int sspbo_dist_ready(const sspbo_ctx* ctx);
+int sspbo_dist_exchange(sspbo_ctx* ctx, unsigned long long* best_dev, void* stream);
+
 /* ---- lock-step of many independent runs (BASELINE config C4: 4096 runs, one context each) ---------------------
  * sspbo_score_batch: for r < R: sspbo_score(ctxs[r], x_dev, ..., lam[r], gamma_t[r], key = keys_dev + r, AUTO engine); all
  * runs share the candidate set x_dev (N rows) and must share its row width n*L.  keys_dev (R packed keys) must be zeroed by

@@ -59,6 +59,10 @@ SIGNATURES = {
     "sspbo_blr_import": (_i, [_vp, _vp, _d, _vp]),
     "sspbo_blr_import_ranked": (_i, [_vp, _vp, _d, _i, _vp]),
     "sspbo_blr_rank": (_i, [_vp, _pi]),
+    "sspbo_dist_init": (_i, [_vp, _i, _i, _vp]),
+    "sspbo_dist_connect": (_i, [_vp, _vp]),
+    "sspbo_dist_ready": (_i, [_vp]),
+    "sspbo_dist_exchange": (_i, [_vp, _vp, _vp]),
     "sspbo_blr_predict": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sspbo_score": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp, _i, _vp]),
     "sspbo_score_generated": (_i, [_vp, _i, _u64, _vp, _pi, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp, _i, _vp]),

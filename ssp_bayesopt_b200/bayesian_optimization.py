@@ -198,10 +198,7 @@ class BayesianOptimization:
         if key is None:
             eng._best.zero_()
             key = eng._best
-        if dist.is_distributed():
-            eng.settle()                               # local key final before it is combined across ranks
-            dist.allreduce_best(key)
-        score, gidx = eng.best()
+        score, gidx = dist.reduce_best(eng)            # one process: eng.best(); one per GPU: key exchange over peer memory
         if cand.get('lookup') is not None:             # every rank can name the winning row without touching the device
             return score, gidx, np.asarray(cand['lookup'](gidx), dtype=np.float64).reshape(1, -1)
         # owner of the winning row publishes it (one small broadcast; single-GPU: a D2H copy of one row)

@@ -1204,6 +1204,7 @@ extern "C" void sspbo_ctx_destroy(sspbo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     sspbo_umma_release(ctx);
     sspbo_lr_release(ctx);
+    sspbo_dist_release(ctx);
     free_blr(ctx);
     dev_free(&ctx->A_turns); dev_free(&ctx->A_turns_f32); dev_free(&ctx->tau_turns); dev_free(&ctx->tau_turns_f32);
     dev_free(&ctx->twiddle); dev_free(&ctx->scal); dev_free(&ctx->Aq_op); dev_free(&ctx->tauq_op);
@@ -2384,7 +2385,8 @@ extern "C" int sspbo_score_finish(sspbo_ctx* ctx, const unsigned long long* key_
     if (h[SSPBO_STAT_OOR] > 0) ctx->p32_disabled = true;
     if (ctx->last_engine == SSPBO_ENGINE_UMMA_LR && h[SSPBO_STAT_SCORED] >= 4096)       // what the float64 pass really costs
         ctx->lr_flag_frac = (double)h[SSPBO_STAT_RESCORED] / (double)h[SSPBO_STAT_SCORED];
-    if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0) ? 1 : 0;
+    if (rerun) *rerun = (h[SSPBO_STAT_OVERFLOW] > 0 || h[SSPBO_STAT_OOR] > 0 || (h[SSPBO_STAT_PEER] & 1ull)) ? 1 : 0;
+    if (h[SSPBO_STAT_PEER] & 2ull) SSPBO_FAIL(ctx, SSPBO_ECUDA, "key exchange: a peer rank did not arrive within the time limit");
     return SSPBO_OK;
 }
 

@@ -129,6 +129,7 @@ struct sspbo_ctx {
     void* umma = nullptr;
     void* lr_state = nullptr;
     void* f8_state = nullptr;
+    void* dist_state = nullptr;      // peer-memory key exchange (sspbo_dist.cu)
     // fp16 + e4m3 operand format (sspbo_score_f8.cu), built lazily: V8 = e4m3 companion of (Vh, Vl), rows 1 .. v8_rank
     // current; (Fh, F8) = images of [m'; L^T] for the factor form
     uint8_t* V8 = nullptr; int v8_rank = 0; bool v8_row0_dirty = true;
@@ -191,6 +192,7 @@ enum { SSPBO_STAT_CUR = 0,       // flagged candidates of the call in flight (re
        SSPBO_STAT_OOR = 3,       // candidates outside the declared |x| bound of the 32-bit phase path
        SSPBO_STAT_SCORED = 4,    // candidates scored by the low-rank pass since the last reset
        SSPBO_STAT_RESCORED = 5,  // flagged candidates the float64 pass really re-scored (the others could not win the arg-max)
+       SSPBO_STAT_PEER = 6,      // multi-GPU key exchange (sspbo_dist.cu): bit 0 = some rank asks for a rerun, bit 1 = a peer never arrived
        SSPBO_STAT_COUNT = 8 };
 
 // Timing experiments (tools/kbench.py): built only with -DSSPBO_EXPERIMENTS (`make EXPERIMENTS=1`).  SSPBO_DEBUG bits:
@@ -254,6 +256,7 @@ int sspbo_score_f8_supported(const sspbo_ctx* ctx, int form);
 double sspbo_f8_cost(const sspbo_ctx* ctx, int form, int64_t N);
 // L = chol(Sp) into ctx->R when the psi-space covariance changed since the last factorisation
 int sspbo_refresh_factor(sspbo_ctx* ctx, cudaStream_t st);
+void sspbo_dist_release(sspbo_ctx* ctx);
 constexpr int SSPBO_SINV_RING = 32;
 // what the low-rank updates left out, folded in (no-ops when nothing is pending): Sp; S and m; S_inv; b; everything
 int sspbo_ensure_sp(sspbo_ctx* ctx, cudaStream_t st);

@@ -44,6 +44,22 @@ def allreduce_best(key_tensor):
     return key_tensor
 
 
+def reduce_best(engine):
+    """(score, index) of the best candidate over all ranks, on every rank, after the rank's scoring calls; synchronises once.
+    One process per GPU of an NVLink node: the keys are exchanged by one kernel over peer memory (csrc/sspbo_dist.cu,
+    `DeviceEngine.best_global`); if that cannot be set up on every rank (no peer access, SSPBO_DIST_EXCHANGE=0, more than 16
+    ranks) the key goes through `allreduce_best` (NCCL) as before.  A single process: `engine.best()`."""
+    if not is_distributed():
+        return engine.best()
+    if engine._exchange_on is None:
+        engine.dist_connect()
+    if engine._exchange_on:
+        return engine.best_global()
+    engine.settle()                                # local key final before it is combined across ranks
+    allreduce_best(engine._best)
+    return engine.best()
+
+
 def allgather_best(key_tensor, shard_start: int):
     """Winner over ranks when the GLOBAL candidate index does not fit the key's 32 index bits (more than 2^32 candidates per
     step): every rank scores its shard with indices local to the shard (index0 = 0, shard < 2^32 rows) and the ranks exchange

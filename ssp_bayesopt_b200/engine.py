@@ -49,6 +49,7 @@ class DeviceEngine:
         self._best = self.torch.zeros(1, dtype=self.torch.int64, device=self._dev())
         self._blr_owner = None       # weakref to the BayesianLinearRegression whose posterior lives in this context
         self._pending = []           # score calls since the last key reset (replayed if the device asks for a rerun)
+        self._exchange_on = None     # peer-memory key exchange across ranks: None = not set up yet (dist_connect)
         self._lr_used = False        # ... and whether any of them ran the low-rank engine
 
     # ------------------------------------------------------------------ plumbing
@@ -546,6 +547,55 @@ class DeviceEngine:
         if self._pending and self._lr_used and st["rerun"]:
             self._replay()
             _, key = self._finish()
+        self._pending = []
+        return _lib.key_unpack(key)
+
+    # ------------------------------------------------------------------ multi-GPU: key exchange over peer memory
+    def dist_connect(self) -> bool:
+        """Collective over torch.distributed (call on every rank): sets up the peer-memory key exchange of sspbo_dist.cu --
+        every rank exports its slot array, the 64-byte handles are all-gathered, every rank maps its peers' arrays.  Returns
+        whether the exchange is usable on ALL ranks (otherwise the NCCL all-reduce of dist.allreduce_best stays in use)."""
+        import os
+        import torch.distributed as td
+        rank, world = td.get_rank(), td.get_world_size()
+        ok, mine = 1, bytes(64)
+        if os.environ.get("SSPBO_DIST_EXCHANGE", "1") == "0" or world > 16:
+            ok = 0
+        else:
+            buf = (C.c_ubyte * 64)()
+            if self.lib.sspbo_dist_init(self._ctx, rank, world, buf) == 0:
+                mine = bytes(buf)
+            else:
+                ok = 0
+        gathered = [None] * world
+        td.all_gather_object(gathered, (ok, mine))
+        if all(g[0] for g in gathered):
+            blob = b"".join(g[1] for g in gathered)
+            arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            ok = 1 if self.lib.sspbo_dist_connect(self._ctx, arr) == 0 else 0
+        else:
+            ok = 0
+        flag = self.torch.tensor([ok], dtype=self.torch.int32, device=self._dev())
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        self._exchange_on = bool(int(flag.item()))
+        return self._exchange_on
+
+    def best_global(self):
+        """(score, index) of the best key over ALL ranks (call on every rank; synchronises once): one kernel writes this
+        rank's key into every peer's slot array and takes the maximum of what the peers wrote (sspbo_dist_exchange), then the
+        usual read-back.  When any rank's scoring pass asks for a rerun, every rank recomputes its shard and exchanges again."""
+        best_ptr = C.c_void_p(self._best.data_ptr())
+        self._check(self.lib.sspbo_dist_exchange(self._ctx, best_ptr, self._stream()), "sspbo_dist_exchange")
+        st, key = self._finish()
+        if st["rerun"]:
+            if self._pending:
+                self._replay()                            # (zeroes the key, recomputes this rank's calls with the safer engines)
+            else:
+                self._best.zero_()
+            self._check(self.lib.sspbo_dist_exchange(self._ctx, best_ptr, self._stream()), "sspbo_dist_exchange")
+            st, key = self._finish()
+            if st["rerun"]:
+                raise _lib.SspboError(f"scoring still asks for a rerun after every rank recomputed its shard: {st}")
         self._pending = []
         return _lib.key_unpack(key)
 
