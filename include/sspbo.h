@@ -285,6 +285,9 @@ int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_de
  * (bayesian_optimization.py:291). */
 int sspbo_dist_init(sspbo_ctx* ctx, int rank, int world, unsigned char* handle_out /* 64 bytes */);
 int sspbo_dist_connect(sspbo_ctx* ctx, const unsigned char* handles /* world x 64 bytes, rank order */);
+/* ranks inside one process (IPC handles cannot be opened by their exporter): exchange the slot arrays themselves */
+int sspbo_dist_slots(sspbo_ctx* ctx, void** slots_out);
+int sspbo_dist_connect_ptrs(sspbo_ctx* ctx, void* const* slot_ptrs /* world pointers, rank order */);
 int sspbo_dist_ready(const sspbo_ctx* ctx);
 int sspbo_dist_exchange(sspbo_ctx* ctx, unsigned long long* best_dev, void* stream);
 

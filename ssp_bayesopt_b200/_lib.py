@@ -62,6 +62,8 @@ SIGNATURES = {
     "sspbo_dist_init": (_i, [_vp, _i, _i, _vp]),
     "sspbo_dist_connect": (_i, [_vp, _vp]),
     "sspbo_dist_ready": (_i, [_vp]),
+    "sspbo_dist_slots": (_i, [_vp, C.POINTER(C.c_void_p)]),
+    "sspbo_dist_connect_ptrs": (_i, [_vp, C.POINTER(C.c_void_p)]),
     "sspbo_dist_exchange": (_i, [_vp, _vp, _vp]),
     "sspbo_blr_predict": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sspbo_score": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp, _i, _vp]),

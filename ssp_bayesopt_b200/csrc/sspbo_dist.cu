@@ -120,6 +120,29 @@ extern "C" int sspbo_dist_connect(sspbo_ctx* ctx, const unsigned char* handles) 
     return SSPBO_OK;
 }
 
+/* The same for ranks that live in ONE process (a thread per GPU, or several contexts in a test): IPC handles cannot be opened
+ * by the process that exported them, so such ranks hand each other the slot arrays themselves.  slots_out: this rank's array
+ * (after sspbo_dist_init); slot_ptrs: the arrays of all ranks in rank order (peer access between their devices enabled by
+ * the caller). */
+extern "C" int sspbo_dist_slots(sspbo_ctx* ctx, void** slots_out) {
+    if (!ctx || !slots_out) return SSPBO_EINVAL;
+    DistState* ds = (DistState*)ctx->dist_state;
+    if (!ds) SSPBO_FAIL(ctx, SSPBO_ESTATE, "dist_slots before dist_init");
+    *slots_out = ds->slots;
+    return SSPBO_OK;
+}
+extern "C" int sspbo_dist_connect_ptrs(sspbo_ctx* ctx, void* const* slot_ptrs) {
+    if (!ctx) return SSPBO_EINVAL;
+    DistState* ds = (DistState*)ctx->dist_state;
+    if (!ds || !slot_ptrs) SSPBO_FAIL(ctx, SSPBO_ESTATE, "dist_connect_ptrs before dist_init");
+    for (int p = 0; p < ds->world; ++p) {
+        if (!slot_ptrs[p]) SSPBO_FAIL(ctx, SSPBO_EINVAL, "dist_connect_ptrs: null slot array of rank %d", p);
+        ds->peer[p] = (p == ds->rank) ? ds->slots : (unsigned long long*)slot_ptrs[p];
+    }
+    ds->connected = true;
+    return SSPBO_OK;
+}
+
 extern "C" int sspbo_dist_ready(const sspbo_ctx* ctx) {
     const DistState* ds = ctx ? (const DistState*)ctx->dist_state : nullptr;
     return (ds && ds->connected) ? 1 : 0;

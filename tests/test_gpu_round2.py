@@ -675,3 +675,61 @@ def test_batched_runs_grouped_kernels_beyond_rank_127(pkg):
             agt.update(grid[idx:idx + 1], np.atleast_2d(himmelblau(grid[idx:idx + 1])), 0.0)
     for a, b in zip(a_batch, a_single):
         assert rel(a.blr.m, b.blr.m) < 1e-10 and rel(a.blr.S, b.blr.S) < 1e-10
+
+
+# ------------------------------------------------------------------ multi-GPU key exchange over peer memory (sspbo_dist.cu)
+@pytest.mark.gpu
+def test_key_exchange_between_contexts(pkg):
+    """The peer-memory winner selection with three 'ranks' living in this process on one GPU (slot arrays handed over as
+    pointers, each rank on its own stream so the three exchange kernels are resident together): every rank ends up with the
+    maximum key, over several exchanges (both slot buffers), and a rank whose scoring pass asks for a rerun makes every
+    rank's read-back report it."""
+    import ctypes as C
+    import torch
+    from ssp_bayesopt_b200 import _lib
+    world = 3
+    bounds = np.array([[-2.0, 2.0], [-2.0, 2.0]])
+    sp = pkg.HexagonalSSPSpace(2, ssp_dim=51, domain_bounds=bounds, length_scale=0.7)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-2, 2, (12, 2))
+    y = -np.sum(X ** 2, axis=1, keepdims=True)
+    agents = [pkg.SSPAgent(X, y, sp, length_scale=0.7, gamma_c=0.0, beta_ucb=5.0) for _ in range(world)]   # same posterior
+    engs = [a._scoring_engine() for a in agents]
+    lib = engs[0].lib
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    slots = (C.c_void_p * world)()
+    for r, e in enumerate(engs):
+        buf = (C.c_ubyte * 64)()
+        assert lib.sspbo_dist_init(e._ctx, r, world, buf) == 0
+        p = C.c_void_p()
+        assert lib.sspbo_dist_slots(e._ctx, C.byref(p)) == 0
+        slots[r] = p.value
+    for e in engs:
+        assert lib.sspbo_dist_connect_ptrs(e._ctx, slots) == 0 and lib.sspbo_dist_ready(e._ctx) == 1
+    cand = rng.uniform(-1.9, 1.9, (6000, 2)).astype(np.float32)               # (stays inside the declared |x| <= 2 when shifted below)
+    shard = [cand[r * 2000:(r + 1) * 2000] for r in range(world)]
+    for step in range(3):                                                      # exchanges 0, 1, 2: both slot buffers
+        want = None
+        for r, e in enumerate(engs):
+            e.score(shard[r] + np.float32(0.01 * step), 5.0, 0.0, index0=r * 2000)
+            torch.cuda.synchronize()
+            k = int(e._best.item()) & 0xFFFFFFFFFFFFFFFF
+            want = k if want is None else max(want, k)
+        for r, e in enumerate(engs):                                           # all three kernels in flight together
+            with torch.cuda.stream(streams[r]):
+                assert lib.sspbo_dist_exchange(e._ctx, C.c_void_p(e._best.data_ptr()), C.c_void_p(streams[r].cuda_stream)) == 0
+        torch.cuda.synchronize()
+        for e in engs:
+            st, key = e._finish()
+            assert key == want and not st["rerun"]
+    # rank 1 sees candidates outside its declared |x| bound on the fast phase path: everybody is told to rerun
+    far = shard[1].copy(); far[0] = [7.0, -9.0]
+    for r, e in enumerate(engs):
+        e.score(far if r == 1 else shard[r], 5.0, 0.0, index0=r * 2000)
+    torch.cuda.synchronize()
+    for r, e in enumerate(engs):
+        with torch.cuda.stream(streams[r]):
+            assert lib.sspbo_dist_exchange(e._ctx, C.c_void_p(e._best.data_ptr()), C.c_void_p(streams[r].cuda_stream)) == 0
+    torch.cuda.synchronize()
+    flags = [e._finish()[0] for e in engs]
+    assert all(f["rerun"] for f in flags) and flags[1]["out_of_range"] >= 1 and flags[0]["out_of_range"] == 0
