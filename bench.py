@@ -339,6 +339,7 @@ def run_native(args):
     cand = eng.fill_uniform(0, start, n_local)                    # resident shard, 300 MB > L2 (126 MB)
     chunk = args.chunk
     saved, beta0 = eng.blr_export(), eng.blr_beta()               # the rank-N_OBS posterior every step starts from
+    eng.blr_checkpoint()                                          # ... and the cheap way back to it (low-rank form: one small kernel)
     torch.cuda.synchronize()
 
     def select(x_dev):
@@ -357,7 +358,9 @@ def run_native(args):
     def observe_and_restore(gidx):
         x_t = winner_row(gidx)
         agt.update(x_t, np.atleast_2d(orc.hartmann6(x_t)), np.array([0.0]))   # encode x_t + float64 rank-one update on device
-        eng.blr_import(saved, beta0)                              # back to rank N_OBS: every step scores the same posterior
+        if not eng.blr_rollback():                                # back to rank N_OBS: every step scores the same posterior
+            eng.blr_import(saved, beta0)                          # (the dense state absorbed the observation: full restore)
+            eng.blr_checkpoint()
 
     def bo_step(x_dev):
         score, gidx = select(x_dev)

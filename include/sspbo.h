@@ -163,6 +163,13 @@ int sspbo_blr_get(sspbo_ctx* ctx, double* m_dev, double* S_dev, double* Sinv_dev
 int64_t sspbo_blr_export_size(const sspbo_ctx* ctx);          /* number of float64 in the packed state */
 int sspbo_blr_export(sspbo_ctx* ctx, double* packed_dev, void* stream);
 int sspbo_blr_import(sspbo_ctx* ctx, const double* packed_dev, double beta, void* stream);
+/* Checkpoint / rollback of a posterior in low-rank form (fantasy observations of batch BO, a posterior pinned at one rank):
+ * sspbo_blr_checkpoint remembers the state after the observations so far; sspbo_blr_rollback undoes every observation made
+ * since -- one small kernel: b_psi, m' and the scorer's copies back, the appended operand rows zeroed -- and reports
+ * SSPBO_EUNSUPPORTED, leaving everything as it is, when the d x d state has meanwhile absorbed a later observation (S, S_inv
+ * or the psi-space covariance was read, or more than 32 observations were made): restore an exported state then. */
+int sspbo_blr_checkpoint(sspbo_ctx* ctx, void* stream);
+int sspbo_blr_rollback(sspbo_ctx* ctx, void* stream);
 /* rank word of the packed state sspbo_blr_export would write now: number of valid low-rank rows, -1 when they are not valid */
 int sspbo_blr_rank(const sspbo_ctx* ctx, int* lr_rank);
 /* sspbo_blr_import for a caller that knows that word (the exporting context is in the same process: a posterior restored

@@ -59,6 +59,8 @@ SIGNATURES = {
     "sspbo_blr_import": (_i, [_vp, _vp, _d, _vp]),
     "sspbo_blr_import_ranked": (_i, [_vp, _vp, _d, _i, _vp]),
     "sspbo_blr_rank": (_i, [_vp, _pi]),
+    "sspbo_blr_checkpoint": (_i, [_vp, _vp]),
+    "sspbo_blr_rollback": (_i, [_vp, _vp]),
     "sspbo_dist_init": (_i, [_vp, _i, _i, _vp]),
     "sspbo_dist_connect": (_i, [_vp, _vp]),
     "sspbo_dist_ready": (_i, [_vp]),

@@ -1194,6 +1194,7 @@ static void free_blr(sspbo_ctx* ctx) {
     dev_free(&ctx->Rh); dev_free(&ctx->Rl); dev_free(&ctx->mp_op);
     dev_free(&ctx->Vh); dev_free(&ctx->Vl); dev_free(&ctx->Vd); dev_free(&ctx->mscale); ctx->lr_rank = 0; ctx->lr_valid = false;
     dev_free(&ctx->psi_ring); dev_free(&ctx->syn_rows); dev_free(&ctx->bpsi); dev_free(&ctx->lr_gh);
+    dev_free(&ctx->ck_vec); dev_free(&ctx->ck_mp_op); dev_free(&ctx->ck_row0); dev_free(&ctx->ck_mscale); ctx->ck_valid = false;
     ctx->sp_applied = 0; ctx->s_applied = 0; ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = false;
     dev_free(&ctx->v); dev_free(&ctx->psi); dev_free(&ctx->y); dev_free(&ctx->z); dev_free(&ctx->phi_tmp);
     ctx->blr_ready = false; ctx->has_beta = false;
@@ -1665,7 +1666,7 @@ static int blr_alloc(sspbo_ctx* ctx, int d, double alpha, bool with_factor) {
     }
     ctx->has_factor = with_factor;
     ctx->lr_rank = 0; ctx->lr_valid = with_factor; ctx->lr_disabled = false; ctx->lr_flag_frac = 0.0;
-    ctx->sp_applied = 0; ctx->s_applied = 0; ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true;
+    ctx->sp_applied = 0; ctx->s_applied = 0; ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true; ctx->ck_valid = false;
     if (with_factor && !ctx->stats) {
         if ((rc = dev_alloc(ctx, &ctx->stats, (size_t)SSPBO_STAT_COUNT)) ||
             (rc = dev_alloc(ctx, &ctx->flag_idx, (size_t)2 * SSPBO_FLAG_CAP)))
@@ -2055,6 +2056,7 @@ static int blr_import_impl(sspbo_ctx* ctx, const double* packed, double beta, bo
     if (beta > 0) { ctx->beta = beta; ctx->has_beta = true; }
     ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
     ctx->sinv_pending = 0; ctx->bm_stale = false; ctx->bpsi_stale = true;   // (S_inv, b, m complete; b_psi follows from b)
+    ctx->ck_valid = false;
     if (ctx->has_factor) {
         double rank = (double)lr_rank_known;                     // the rows of V travel with the packed state
         if (!rank_known) {
@@ -2079,6 +2081,75 @@ static int blr_import_impl(sspbo_ctx* ctx, const double* packed, double beta, bo
         k_mp_op<<<1, 1024, 0, st>>>(ctx->mp, ctx->perm, ctx->col_of_rank, (int)d, ctx->mp_op, ctx->Vh, ctx->Vl, ctx->mscale);
         SSPBO_LAUNCH_CHECK(ctx);
     }
+    return SSPBO_OK;
+}
+
+// ---- checkpoint / rollback of the low-rank posterior -----------------------------------------------------------------------
+// While updates run in low-rank form an observation only appends a row of V and rewrites b_psi, m' and the scorer's copies of
+// m'; undoing the observations since a checkpoint is therefore one small kernel: those vectors back, the appended operand rows
+// zeroed, the rank reset.  (Fantasy observations of batch BO -- "kriging believer" / "constant liar" -- and a posterior that a
+// benchmark pins at one rank.)  Not possible once the d x d state has absorbed a later observation (something read S, S_inv or
+// the psi-space covariance, or the ring of S_inv terms was flushed): rollback then reports SSPBO_EUNSUPPORTED and the caller
+// restores an exported state instead.
+__global__ void k_ck_copy(const double* __restrict__ vec_src, double* __restrict__ bpsi, double* __restrict__ mp, int d,
+                          const float* __restrict__ mpop_src, float* __restrict__ mp_op, const __half* __restrict__ row0_src,
+                          __half* __restrict__ vh, __half* __restrict__ vl, int KC, const float* __restrict__ ms_src,
+                          float* __restrict__ mscale, int zero_r0, int zero_r1, uint8_t* __restrict__ v8) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int j = gt; j < d; j += nt) { bpsi[j] = vec_src[j]; mp[j] = vec_src[d + j]; }
+    for (int c = gt; c < KC; c += nt) { mp_op[c] = mpop_src[c]; vh[c] = row0_src[c]; vl[c] = row0_src[KC + c]; }
+    if (gt == 0) *mscale = *ms_src;
+    // operand rows of the observations being undone (row r + 1 holds observation r)
+    const size_t z0 = (size_t)(zero_r0 + 1) * KC, z1 = (size_t)(zero_r1 + 1) * KC;
+    for (size_t i = z0 + gt; i < z1; i += nt) { vh[i] = __float2half(0.f); vl[i] = __float2half(0.f); }
+    if (v8) for (size_t i = 2 * z0 + gt; i < 2 * z1; i += nt) v8[i] = 0;
+}
+
+extern "C" int sspbo_blr_checkpoint(sspbo_ctx* ctx, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->blr_ready || !ctx->has_factor || !ctx->lr_valid || ctx->unfused_update)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "blr_checkpoint: needs a posterior over an SSP space in low-rank form");
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    double* ring_row = nullptr;
+    if ((rc = sspbo_ensure_bm(ctx, st)) || (rc = sspbo_lr_update_prepare(ctx, st, &ring_row))) return rc;    // b_psi allocated and current
+    const int d = ctx->d, KC = ctx->KC_pad;
+    if (!ctx->ck_vec) {
+        if ((rc = dev_alloc(ctx, &ctx->ck_vec, (size_t)2 * d)) || (rc = dev_alloc(ctx, &ctx->ck_mp_op, (size_t)KC)) ||
+            (rc = dev_alloc(ctx, &ctx->ck_row0, (size_t)2 * KC)) || (rc = dev_alloc(ctx, &ctx->ck_mscale, (size_t)1)))
+            return rc;
+    }
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_vec, ctx->bpsi, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_vec + d, ctx->mp, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_mp_op, ctx->mp_op, (size_t)KC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_row0, ctx->Vh, (size_t)KC * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_row0 + KC, ctx->Vl, (size_t)KC * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    SSPBO_CUDA(ctx, cudaMemcpyAsync(ctx->ck_mscale, ctx->mscale, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ctx->ck_valid = true; ctx->ck_rank = ctx->lr_rank; ctx->ck_sinv_pending = ctx->sinv_pending;
+    return SSPBO_OK;
+}
+
+extern "C" int sspbo_blr_rollback(sspbo_ctx* ctx, void* stream) {
+    if (!ctx) return SSPBO_EINVAL;
+    if (!ctx->ck_valid) SSPBO_FAIL(ctx, SSPBO_ESTATE, "blr_rollback without a checkpoint");
+    const int undone = ctx->lr_rank - ctx->ck_rank;
+    if (!ctx->lr_valid || undone < 0 || ctx->s_applied > ctx->ck_rank || ctx->sp_applied > ctx->ck_rank ||
+        ctx->sinv_pending != ctx->ck_sinv_pending + undone || ctx->bpsi_stale)
+        SSPBO_FAIL(ctx, SSPBO_EUNSUPPORTED, "blr_rollback: the dense state has absorbed observations made after the checkpoint");
+    if (undone == 0) return SSPBO_OK;
+    SSPBO_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int zero_r1 = ctx->lr_rank;
+    uint8_t* v8 = (ctx->V8 && ctx->v8_rank > ctx->ck_rank) ? ctx->V8 : nullptr;
+    k_ck_copy<<<8, 256, 0, st>>>(ctx->ck_vec, ctx->bpsi, ctx->mp, ctx->d, ctx->ck_mp_op, ctx->mp_op, ctx->ck_row0, ctx->Vh, ctx->Vl,
+                                  ctx->KC_pad, ctx->ck_mscale, ctx->mscale, ctx->ck_rank, zero_r1, v8);
+    SSPBO_LAUNCH_CHECK(ctx);
+    ctx->launches++;
+    ctx->lr_rank = ctx->ck_rank; ctx->sinv_pending = ctx->ck_sinv_pending;
+    if (ctx->v8_rank > ctx->ck_rank) ctx->v8_rank = ctx->ck_rank;
+    ctx->bm_stale = true;                                       // (b and m may have been brought up to date in between)
+    ctx->v8_row0_dirty = true; ctx->operands_dirty = true; ctx->factor_dirty = true; ctx->f8_factor_dirty = true;
     return SSPBO_OK;
 }
 

@@ -86,6 +86,10 @@ struct sspbo_ctx {
     int sinv_pending = 0;
     double* bpsi = nullptr;          // d, rank order: beta sum_t t psi_t
     bool bm_stale = false, bpsi_stale = false;
+    // checkpoint of the low-rank posterior (sspbo_blr_checkpoint / _rollback): b_psi and m' (2 d doubles), m' in operand order
+    // (KC_pad floats), row 0 of the operand images (2 KC_pad halves), the scale of that row; and the bookkeeping at that moment
+    double* ck_vec = nullptr; float* ck_mp_op = nullptr; __half* ck_row0 = nullptr; float* ck_mscale = nullptr;
+    bool ck_valid = false; int ck_rank = 0, ck_sinv_pending = 0;
     double* lr_gh = nullptr;         // scratch of k_blr_update_lr: 2 SSPBO_LR_MAX + 32 doubles
     double* syn_rows = nullptr;      // scratch: SSPBO_SINV_RING x d rows synthesised into phi-space
     bool lr_disabled = false;        // policy: too many candidates needed the exact pass, use the full factor instead

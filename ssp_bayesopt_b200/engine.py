@@ -284,6 +284,19 @@ class DeviceEngine:
         buf.sspbo_lr_rank = self.blr_rank()         # travels with the tensor inside this process: lets blr_import skip a read-back
         return buf
 
+    def blr_checkpoint(self) -> None:
+        """Remember the posterior as it is now (low-rank form); `blr_rollback` returns to it."""
+        self._check(self.lib.sspbo_blr_checkpoint(self._ctx, self._stream()), "sspbo_blr_checkpoint")
+
+    def blr_rollback(self) -> bool:
+        """Undo the observations made since `blr_checkpoint` (one small kernel).  False -- nothing changed -- when the dense
+        state has absorbed one of them in the meantime; restore an exported state (`blr_import`) then."""
+        rc = self.lib.sspbo_blr_rollback(self._ctx, self._stream())
+        if rc == -4:                                  # SSPBO_EUNSUPPORTED
+            return False
+        self._check(rc, "sspbo_blr_rollback")
+        return True
+
     def blr_rank(self) -> int:
         """Number of valid low-rank rows of the posterior (= observations so far), -1 when they are not valid."""
         r = C.c_int(-1)

@@ -733,3 +733,42 @@ def test_key_exchange_between_contexts(pkg):
     torch.cuda.synchronize()
     flags = [e._finish()[0] for e in engs]
     assert all(f["rerun"] for f in flags) and flags[1]["out_of_range"] >= 1 and flags[0]["out_of_range"] == 0
+
+
+# ------------------------------------------------------------------ checkpoint / rollback of the low-rank posterior
+@pytest.mark.gpu
+def test_posterior_checkpoint_and_rollback(pkg):
+    """`blr_checkpoint` / `blr_rollback`: observations made after a checkpoint are undone by one small kernel while the
+    posterior is in low-rank form -- scores, picks and (after a later read) m, S, S_inv equal those of an agent that never
+    saw them -- and rollback declines once the dense state has absorbed one of them."""
+    rng = np.random.default_rng(21)
+    bounds = np.array([[-2.0, 2.0]] * 3)
+    def make():
+        sp = pkg.RandomSSPSpace(3, ssp_dim=257, domain_bounds=bounds, length_scale=0.6, rng=4)
+        return pkg.SSPAgent(X[:20], y[:20], sp, length_scale=0.6, gamma_c=0.0, beta_ucb=5.0)
+    X = rng.uniform(-2, 2, (60, 3))
+    y = np.cos(X[:, :1]) - 0.3 * X[:, 1:2] * X[:, 2:3]
+    a, ref_agent = make(), make()
+    ea, er = a._scoring_engine(), ref_agent._scoring_engine()
+    cand = rng.uniform(-2, 2, (4000, 3)).astype(np.float32)
+    ea.blr_checkpoint()
+    for rounds in range(3):                                                    # fantasise five observations, undo them, repeat
+        for i in range(20, 25):
+            a.update(X[i:i + 1], y[i:i + 1] + rounds, 0.0)
+        assert ea.blr_rank() == 25
+        a.best_candidate(cand); s_f, _ = ea.best()
+        assert ea.blr_rollback() and ea.blr_rank() == 20
+        a.best_candidate(cand); ref_agent.best_candidate(cand)
+        assert ea.best() == er.best()                                          # same kernel, same operands: identical key
+    # both agents now take the same real observations
+    for i in range(25, 30):
+        a.update(X[i:i + 1], y[i:i + 1], 0.0); ref_agent.update(X[i:i + 1], y[i:i + 1], 0.0)
+    assert rel(a.blr.m, ref_agent.blr.m) < 1e-12 and rel(a.blr.S, ref_agent.blr.S) < 1e-12
+    assert rel(a.blr.S_inv, ref_agent.blr.S_inv) < 1e-12
+    # the attribute reads above folded observations 20..24 (the real ones) into S: the checkpoint at rank 20 is out of reach
+    assert ea.blr_rollback() is False and ea.blr_rank() == 25
+    ea.blr_checkpoint()                                                        # a new one at rank 25 works again
+    a.update(X[30:31], y[30:31], 0.0)
+    assert ea.blr_rollback() and ea.blr_rank() == 25
+    a.best_candidate(cand); ref_agent.best_candidate(cand)
+    assert ea.best() == er.best()
