@@ -287,7 +287,7 @@ int sspbo_gram(sspbo_ctx* ctx, const double* phi_dev, int n, double* gram_out_de
  * gathers the handles of all ranks (torch.distributed / MPI / files -- not this library's business) and hands them, in rank
  * order, to sspbo_dist_connect.  Per step: sspbo_dist_exchange (asynchronous, every rank the same number of times) replaces
  * *best_dev by the maximum over the ranks; the following sspbo_score_finish reports rerun != 0 when ANY rank asks for it (then
- * every rank recomputes its shard and exchanges again) and an error when a peer did not arrive within ~2 s.
+ * every rank recomputes its shard and exchanges again) and an error when a peer did not arrive within ~10 s.
  * Replaces: dist.allreduce_best (NCCL) of this repo; in the reference the step is np.argmax over one array
  * (bayesian_optimization.py:291). */
 int sspbo_dist_init(sspbo_ctx* ctx, int rank, int world, unsigned char* handle_out /* 64 bytes */);

@@ -8,8 +8,8 @@
 // e + 1 before every peer has started it, i.e. finished e).  In exchange e lane p of the one warp writes {key, flag, e} into
 // slot r of peer p's array (the epoch word last, after a system-scope fence), then polls slot p of its own array until the
 // epoch word equals e.  The warp then reduces max(key) / or(flag); lane 0 stores the global key over the local one and the
-// flag into the context's counters, where sspbo_score_finish finds it.  A bounded poll (about two seconds) turns a missing
-// peer into an error instead of a hang.
+// flag into the context's counters, where sspbo_score_finish finds it.  A bounded poll (about ten seconds: ranks may be
+// that far apart on their first step) turns a missing peer into an error instead of a hang.
 #include "sspbo_internal.cuh"
 #include <string.h>
 
@@ -51,7 +51,7 @@ __global__ void k_key_exchange(const ExchangeArgs a) {
         const long long t0 = clock64();
         bool ok = true;
         while (src[2] != a.epoch) {
-            if (clock64() - t0 > 4000000000ll) { ok = false; break; }                  // ~2 s: a peer never arrived
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }                 // ~10 s: a peer never arrived
             __nanosleep(200);
         }
         __threadfence_system();
