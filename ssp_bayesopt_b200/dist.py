@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, candidates sharded by contiguous index range, one
-all-reduce(max) of the packed (score, index) key per BO step.
+maximum over the ranks' packed (score, index) keys per BO step -- `reduce_best`: one kernel
+over NVLink peer memory (csrc/sspbo_dist.cu), or an NCCL all-reduce(max) where peer mappings are not available.
 
-No data-path collective other than that 8-byte reduction exists: the posterior is replicated and every
+No data-path exchange other than that 8-byte reduction exists: the posterior is replicated and every
 rank applies the same deterministic float64 rank-one update.  `broadcast_posterior` is the optional
 drift guard / late-joiner path the north star mentions (S, S_inv, b, m, R, m' packed, 3 d^2 + 3 d doubles).
 """

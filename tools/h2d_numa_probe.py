@@ -91,6 +91,46 @@ def main():
         del host
 
     measure("as launched")
+
+    def measure_wc(tag):
+        """The same with write-combined pinned memory (cudaHostAlloc, cudaHostAllocWriteCombined): no cache snooping on the
+        DMA reads."""
+        rt = ctypes.CDLL("libcudart.so.12")
+        ptr = ctypes.c_void_p()
+        rc = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(n * 4), ctypes.c_uint(4))
+        if rc != 0:
+            if rank == 0:
+                print(f"{tag}: cudaHostAlloc failed ({rc})", flush=True)
+            return
+        buf = (ctypes.c_float * n).from_address(ptr.value)
+        host = torch.frombuffer(buf, dtype=torch.float32)
+        host.copy_(src)
+        if rank == 0:
+            print(f"   write-combined buffer is_pinned={host.is_pinned()}", flush=True)
+        for _ in range(2):
+            dev.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(6):
+            dev.copy_(host, non_blocking=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        gbs = torch.tensor([6 * n * 4 / ev[0].elapsed_time(ev[1]) / 1e6], device="cuda")
+        allg = [torch.zeros_like(gbs) for _ in range(world)]
+        if world > 1:
+            td.all_gather(allg, gbs)
+        else:
+            allg = [gbs]
+        vals = [float(v) for v in allg]
+        if rank == 0:
+            print(f"{tag:32s} per rank {' '.join(f'{v:5.1f}' for v in vals)}  sum {sum(vals):6.1f} GB/s", flush=True)
+        del host, buf
+        rt.cudaFreeHost(ptr)
+
+    measure_wc("write-combined pinned")
     all_nodes = sorted(nd)
     if gpu_node >= 0 and gpu_node in nd:
         os.sched_setaffinity(0, nd[gpu_node])
