@@ -485,12 +485,30 @@ class DeviceEngine:
         done = [torch.cuda.Event(), torch.cuda.Event()]
         self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
         # short first piece: its copy is the only one no scoring overlaps; the following ones grow by 1.5x, about the ratio
-        # of link to scoring rate at d = 1023, so the copy of piece i + 1 fits under the scoring of piece i
-        pieces, c0, n = [], 0, int(first_piece or max(chunk >> 2, 1 << 15))
-        while c0 < N:
-            n = min(n, chunk, N - c0)
-            pieces.append((c0, n))
-            c0, n = c0 + n, int(n * growth)
+        # of link to scoring rate at d = 1023, so the copy of piece i + 1 fits under the scoring of piece i.  The schedule
+        # ramps down again at the end: the scoring of the LAST piece is the only one no copy overlaps
+        # (12.5e6 candidates: 0.5, 0.8, 1.2, 1.8, 2.1, ..., 1.8, 1.2, 0.8, 0.5 million).
+        front, back, remaining, n = [], [], int(N), int(first_piece or max(chunk >> 2, 1 << 15))
+        while remaining > 0:
+            n = min(n, chunk)
+            take = min(n, remaining)
+            front.append(take); remaining -= take
+            if remaining > 0:
+                take = min(n, remaining)
+                back.append(take); remaining -= take
+            n = int(n * growth)
+        sizes = front + back[::-1]
+        for i in range(len(sizes)):                              # a small remainder (where the two ramps meet) joins a neighbour
+            if sizes[i] < 4096 and len(sizes) > 1:
+                for j in (i - 1, i + 1):
+                    if 0 <= j < len(sizes) and sizes[j] + sizes[i] <= chunk:
+                        sizes[j] += sizes[i]; sizes[i] = 0
+                        break
+        pieces, c0 = [], 0
+        for take in sizes:
+            if take:
+                pieces.append((c0, take))
+                c0 += take
         for i, (c0, n) in enumerate(pieces):
             b = i & 1
             with torch.cuda.stream(self._copy_stream):
