@@ -449,7 +449,7 @@ class DeviceEngine:
     def score_host(self, x_host, lam, gamma_t, index0=0, engine=_lib.ENGINE_AUTO, chunk=1 << 21, reset_best=True,
                    first_piece=None, growth=1.5):
         """Fused scoring of candidates that live in HOST memory (numpy or CPU tensor, ideally pinned): the set is
-        streamed through two device staging buffers so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
+        streamed through three device staging buffers so the H2D copies of the next chunks overlap the kernel of chunk i.
         Returns the device key tensor (nothing is synchronised)."""
         torch = self.torch
         xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host))
@@ -464,7 +464,7 @@ class DeviceEngine:
         N = xt.shape[0]
         key = (xt.dtype, cols, chunk)
         if getattr(self, "_stage_key", None) != key:
-            self._stage = [torch.empty((chunk, cols), dtype=xt.dtype, device=self._dev()) for _ in range(2)]
+            self._stage = [torch.empty((chunk, cols), dtype=xt.dtype, device=self._dev()) for _ in range(3)]
             self._stage_key = key
             self._copy_stream = torch.cuda.Stream(device=self._dev())
         compute = torch.cuda.current_stream(self.device)
@@ -481,8 +481,9 @@ class DeviceEngine:
     def _score_host_stream(self, xt, N, lam, gamma_t, index0, engine, chunk, first_piece=None, growth=1.5):
         torch = self.torch
         compute = torch.cuda.current_stream(self.device)
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
+        nbuf = len(self._stage)                                  # three staging buffers: the copy engine may run two pieces ahead
+        copied = [torch.cuda.Event() for _ in range(nbuf)]
+        done = [torch.cuda.Event() for _ in range(nbuf)]
         self._copy_stream.wait_stream(compute)                   # staging buffers may still be read by earlier work
         # short first piece: its copy is the only one no scoring overlaps; the following ones grow by 1.5x, about the ratio
         # of link to scoring rate at d = 1023, so the copy of piece i + 1 fits under the scoring of piece i.  The schedule
@@ -510,9 +511,9 @@ class DeviceEngine:
                 pieces.append((c0, take))
                 c0 += take
         for i, (c0, n) in enumerate(pieces):
-            b = i & 1
+            b = i % nbuf
             with torch.cuda.stream(self._copy_stream):
-                if i >= 2:
+                if i >= nbuf:
                     self._copy_stream.wait_event(done[b])
                 self._stage[b][:n].copy_(xt[c0:c0 + n], non_blocking=True)
                 copied[b].record(self._copy_stream)
