@@ -31,6 +31,34 @@ def require_cuda(device=None):
     return int(torch.device("cuda", device).index if not isinstance(device, int) else device)
 
 
+def stream_pieces(N, chunk, first_piece=None, growth=1.5):
+    """Piece schedule [(start, count), ...] of a host candidate set streamed through the staging buffers: a short first piece
+    (its copy is the only one no scoring overlaps), pieces growing by `growth` up to `chunk`, and the mirror image at the end
+    (the scoring of the last piece is the only one no copy overlaps).  A remainder below 4096 rows joins a neighbour."""
+    front, back, remaining, n = [], [], int(N), int(first_piece or max(chunk >> 2, 1 << 15))
+    while remaining > 0:
+        n = min(n, chunk)
+        take = min(n, remaining)
+        front.append(take); remaining -= take
+        if remaining > 0:
+            take = min(n, remaining)
+            back.append(take); remaining -= take
+        n = int(n * growth)
+    sizes = front + back[::-1]
+    i = len(front) - 1 if len(front) > len(back) else len(front)   # the piece taken last: where the two ramps meet
+    if len(sizes) > 1 and sizes[i] < 4096:                       # a small remainder joins a neighbour
+        for j in (i - 1, i + 1):
+            if 0 <= j < len(sizes) and sizes[j] + sizes[i] <= chunk:
+                sizes[j] += sizes[i]; sizes[i] = 0
+                break
+    pieces, c0 = [], 0
+    for take in sizes:
+        if take:
+            pieces.append((c0, take))
+            c0 += take
+    return pieces
+
+
 class DeviceEngine:
     """Owns a device context: SSP space tables, the float64 BLR posterior and its scoring factor."""
 
@@ -489,27 +517,7 @@ class DeviceEngine:
         # of link to scoring rate at d = 1023, so the copy of piece i + 1 fits under the scoring of piece i.  The schedule
         # ramps down again at the end: the scoring of the LAST piece is the only one no copy overlaps
         # (12.5e6 candidates: 0.5, 0.8, 1.2, 1.8, 2.1, ..., 1.8, 1.2, 0.8, 0.5 million).
-        front, back, remaining, n = [], [], int(N), int(first_piece or max(chunk >> 2, 1 << 15))
-        while remaining > 0:
-            n = min(n, chunk)
-            take = min(n, remaining)
-            front.append(take); remaining -= take
-            if remaining > 0:
-                take = min(n, remaining)
-                back.append(take); remaining -= take
-            n = int(n * growth)
-        sizes = front + back[::-1]
-        for i in range(len(sizes)):                              # a small remainder (where the two ramps meet) joins a neighbour
-            if sizes[i] < 4096 and len(sizes) > 1:
-                for j in (i - 1, i + 1):
-                    if 0 <= j < len(sizes) and sizes[j] + sizes[i] <= chunk:
-                        sizes[j] += sizes[i]; sizes[i] = 0
-                        break
-        pieces, c0 = [], 0
-        for take in sizes:
-            if take:
-                pieces.append((c0, take))
-                c0 += take
+        pieces = stream_pieces(N, chunk, first_piece, growth)
         for i, (c0, n) in enumerate(pieces):
             b = i % nbuf
             with torch.cuda.stream(self._copy_stream):

@@ -337,3 +337,21 @@ def test_vectorised_key_unpack_matches_c():
         assert (a == s or (np.isnan(a) and np.isnan(s))) and b == i
     sc, ix = _unpack_keys(np.zeros(2, dtype=np.int64))
     assert np.all(np.isneginf(sc))
+
+
+def test_host_streaming_piece_schedule():
+    """engine.stream_pieces: the pieces of a host candidate set cover it exactly, never exceed the staging buffer, ramp up from
+    a short first piece and down to a short last one, and no sliver is left where the ramps meet."""
+    from ssp_bayesopt_b200.engine import stream_pieces
+    chunk = 1 << 21
+    for N in (1, 100, 40_000, (1 << 19), (1 << 19) + 1, 3_000_001, 12_500_000, 100_000_003):
+        p = stream_pieces(N, chunk)
+        assert p[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(p, p[1:])) and p[-1][0] + p[-1][1] == N
+        assert all(0 < n <= chunk for _, n in p)
+        if N >= 1 << 20:
+            assert all(n >= 4096 for _, n in p)
+    sizes = [n for _, n in stream_pieces(12_500_000, chunk)]
+    assert sizes[0] == 1 << 19 and sizes[-1] == 1 << 19 and max(sizes) == chunk
+    k = sizes.index(max(sizes))
+    assert sizes[:k + 1] == sorted(sizes[:k + 1]) and sizes[-4:] == sorted(sizes[-4:], reverse=True)
+    assert [n for _, n in stream_pieces(5000, chunk, first_piece=1000, growth=2.0)] == [1000, 3000, 1000]
