@@ -163,6 +163,7 @@ struct sspbo_ctx {
         if (e__ != cudaSuccess) {                                                          \
             snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, \
                      #expr, cudaGetErrorString(e__));                                      \
+            (void)cudaGetLastError(); /* reported here: must not resurface at a later launch check */ \
             return SSPBO_ECUDA;                                                            \
         }                                                                                  \
     } while (0)
