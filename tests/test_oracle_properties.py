@@ -105,3 +105,44 @@ def test_encode_and_deriv_is_the_derivative_of_encode():
             e = np.zeros(n); e[a] = h
             fd = (orc.encode(A, ls, x + e) - orc.encode(A, ls, x - e)) / (2 * h)
             np.testing.assert_allclose(grad[:, :, a], fd, atol=5e-9)
+
+
+@settings(**SETTINGS)
+@given(seed=st.integers(0, 10_000), n_agents=st.integers(1, 3), L=st.integers(1, 4))
+def test_multi_agent_encode_structure(seed, n_agents, L):
+    """Multi-agent encoder (ssp_multi_agent.py:166-186): unit norm; identical per-agent spaces give the shared-space encoding;
+    and the spectrum of the un-normalised sum is the sum over the (timestep, agent) waypoints of unit phasors
+    exp(i (A_i x_ji / l_i + phase(T_j) + phase(a_i))) -- the identity the device encoder evaluates (one frequency table per
+    agent, one phase-offset row per waypoint)."""
+    rng = np.random.default_rng(seed)
+    xd, ssp_dim = 2, 31
+    As = [orc.random_phase_matrix(xd, ssp_dim, rng=seed + i) for i in range(n_agents)]
+    lss = [rng.uniform(0.5, 2.0) * np.ones(xd) for _ in range(n_agents)]
+    At = orc.random_phase_matrix(1, ssp_dim, rng=seed + 17)
+    T = orc.traj_timestep_ssps(At, np.array([1.3]), L)
+    tags = orc.sp_vectors(n_agents, ssp_dim, seed)
+    x = rng.uniform(-2, 2, (5, L * n_agents * xd))
+    phi = orc.multi_agent_encode(As, lss, T, tags, x, L, n_agents, xd)
+    np.testing.assert_allclose(np.linalg.norm(phi, axis=1), 1.0, atol=1e-12)
+    same = orc.multi_agent_encode([As[0]] * n_agents, [lss[0]] * n_agents, T, tags, x, L, n_agents, xd)
+    shared = orc.multi_agent_encode(As[0], lss[0], T, tags, x, L, n_agents, xd)
+    np.testing.assert_allclose(same, shared, atol=1e-14)
+    K = (ssp_dim - 1) // 2
+    pts = x.reshape(-1, L, n_agents, xd)
+    tag_ph = np.angle(np.fft.fft(tags, axis=-1))[:, 1:K + 1]
+    t_ph = np.angle(np.fft.fft(T, axis=-1))[:, 1:K + 1]
+    spec = np.zeros((x.shape[0], K), dtype=complex)
+    for j in range(L):
+        for i in range(n_agents):
+            theta = pts[:, j, i, :] @ (As[i][1:K + 1] / lss[i]).T
+            spec += np.exp(1j * (theta + t_ph[j] + tag_ph[i]))
+    un = phi * 0
+    for s in range(x.shape[0]):                                           # the same sum through explicit binds, un-normalised
+        acc = np.zeros(ssp_dim)
+        for i in range(n_agents):
+            si = np.zeros(ssp_dim)
+            for j in range(L):
+                si = si + orc.bind(T[j], orc.encode(As[i], lss[i], pts[s:s + 1, j, i, :])[0])
+            acc = acc + orc.bind(tags[i], si)
+        un[s] = acc
+    np.testing.assert_allclose(np.fft.fft(un, axis=-1)[:, 1:K + 1], spec, atol=1e-10)
