@@ -772,3 +772,33 @@ def test_posterior_checkpoint_and_rollback(pkg):
     assert ea.blr_rollback() and ea.blr_rank() == 25
     a.best_candidate(cand); ref_agent.best_candidate(cand)
     assert ea.best() == er.best()
+
+
+# ------------------------------------------------------------------ config C2 over its whole run
+@pytest.mark.gpu
+def test_c2_full_run_stays_on_the_low_rank_form(pkg):
+    """BASELINE config C2 as specified -- Branin, hex d = 151, the 1000 x 1000 grid, 250 iterations -- through
+    `BayesianOptimization.maximize`: the posterior reaches rank 260 > d, and the engine choice (estimated time of both forms,
+    including the factor refresh a changed posterior costs) keeps every step on the low-rank form; the run finds Branin's
+    optimum on the grid, and late steps cost about what early ones do (no step pays a Cholesky refresh)."""
+    bounds = np.array([[-5.0, 10.0], [0.0, 15.0]])
+    a, b, c, r, s, t = 1, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6., 10., 1 / (8 * np.pi)
+    branin = lambda x: -(a * (x[:, 1] - b * x[:, 0] ** 2 + c * x[:, 0] - r) ** 2 + s * (1 - t) * np.cos(x[:, 0]) + s)
+    xs0 = np.random.default_rng(0).uniform(bounds[:, 0], bounds[:, 1], (10, 2))
+    opt = pkg.BayesianOptimization(f=branin, bounds=bounds)
+    opt.maximize(init_points=(xs0, branin(xs0).reshape(-1, 1)), n_iter=250, agent_type="ssp-hex", ssp_dim=151,
+                 length_scale=1.0, beta_ucb=10.0, gamma_c=0.0, candidates_per_dim=1000)
+    eng = opt.agt._scoring_engine()
+    info = eng.lowrank_info()
+    assert info["rank"] == 260 and info["valid"] and not info["disabled"]
+    assert eng.last_engine() == "umma-lowrank"
+    assert opt.max["target"] > -0.41                                         # Branin's maxima of -f are -0.3979
+    ft = opt.full_times * 1e-6                                               # ms per step
+    assert np.median(ft[200:]) < 3.0 * np.median(ft[20:60])
+    # the posterior still equals the oracle's after the 260 observations
+    ref = orc.BLR(151)
+    phis = orc.encode(opt.agt.ssp_space.phase_matrix, np.ones(2), opt.xs)
+    ref.update(phis[:10], opt.ys[:10].reshape(-1, 1))
+    for i in range(10, len(opt.xs)):
+        ref.update(phis[i:i + 1], opt.ys[i:i + 1].reshape(-1, 1))
+    assert rel(opt.agt.blr.m, ref.m) < 1e-6 and rel(opt.agt.blr.S, ref.S) < 1e-6
