@@ -2190,8 +2190,6 @@ static int score_flagged_launch(sspbo_ctx* ctx, const sspbo_lr::CandDesc& cand, 
     const int gx = 2 * ctx->sm_count;
     const bool full = !ctx->lr_valid;
     if (full) { const int rc_sp = sspbo_ensure_sp(ctx, st); if (rc_sp) return rc_sp; }
-    const double* rows = full ? ctx->Sp : ctx->Vd;
-    const int r = full ? d : ctx->lr_rank;
     ExactArgs ea;
     fill_exact_args(ctx, cand, index0, lam, gamma_t, mu, var, acq, best, full, &ea);
 #define SSPBO_FLAGGED_LAUNCH(XT, FULL)                                                                                             \

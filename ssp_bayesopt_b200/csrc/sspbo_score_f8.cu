@@ -37,13 +37,6 @@ __device__ __forceinline__ void umma_f8_ts_acc(uint32_t d_tmem, uint32_t a_tmem,
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
 }
 
-// fp16 pair -> e4m3 pair (low half -> low byte)
-__device__ __forceinline__ uint32_t e4m3x2_of_half2(uint32_t h2) {
-    uint16_t r;
-    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
-    return (uint32_t)r;
-}
-
 // float32 pair -> e4m3 pair (first operand -> low byte), one rounding
 __device__ __forceinline__ uint32_t e4m3x2_of_floats(float lo, float hi) {
     uint16_t r;
