@@ -148,6 +148,21 @@ mine = torch.from_numpy(np.concatenate([seen["xs"].ravel(), seen["ys"].ravel(), 
 both = [torch.empty_like(mine) for _ in range(2)]
 td.all_gather(both, mine)
 assert torch.equal(both[0], both[1]) and seen["xs"].shape == (6, 2) and seen["perimeter"].shape == (3, 2)
+# dist.reduce_best with an engine that cannot use the peer-memory exchange (here: a stand-in without a GPU): the key is made
+# final locally, max-reduced (the NCCL path of the product, gloo here) and read back; every rank gets the global winner
+class _Eng:
+    _exchange_on = False
+    def __init__(self, score, idx):
+        key = _lib.key_pack(score, idx)
+        self._best = torch.tensor([key - (1 << 64) if key >= (1 << 63) else key], dtype=torch.int64)
+        self.settled = False
+    def settle(self): self.settled = True
+    def best(self): return _lib.key_unpack(int(self._best.item()))
+for c in [((0.5, 10), (0.75, 2000000)), ((1.0, 9), (1.0, 3)), ((-2.0, 1), (-1.0, 4000000000))]:
+    e = _Eng(*c[r])
+    got = dist.reduce_best(e)
+    want = _lib.key_unpack(max(_lib.key_pack(*c[0]), _lib.key_pack(*c[1])))
+    assert e.settled and got == want, (got, want)
 td.destroy_process_group()
 print("ok", r)
 '''
